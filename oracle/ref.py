@@ -1,0 +1,198 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes loader for oracle/_ref/libsocref_<tag>.so, i.e. the reference's
+own kernels compiled in place by oracle/build_ref.py.  Same call shapes as oracle/orc.py so tests can
+run either and compare.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import build_ref
+
+c_fp = C.POINTER(C.c_float)
+c_ip = C.POINTER(C.c_int32)
+
+
+def _fp(a):
+    return a.ctypes.data_as(c_fp)
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_ip)
+
+
+def available(cfg=None):
+    return build_ref.reference_available() or (cfg is not None and __import__("os").path.exists(build_ref.lib_path(cfg)))
+
+
+class Reference:
+    def __init__(self, cloud, gl=0.01, bins=2500, map_nside=None, **opts):
+        cfg = dict(NX=cloud.NX, NY=cloud.NY, NZ=cloud.NZ, LEVELS=cloud.LEVELS, CELLS=cloud.CELLS, BINS=bins, GL=gl)
+        for k, v in opts.items():
+            cfg[k.upper()] = v
+        if map_nside is not None:
+            cfg["MAP_NSIDE"] = map_nside
+        path = build_ref.build(cfg)
+        if path is None:
+            raise RuntimeError("reference library for %s not available" % build_ref.tag_of(cfg))
+        self.L = C.CDLL(path)
+        self.L.ref_atomic_count.restype = C.c_ulong
+        self.cloud = cloud
+        self.opts = opts
+        self.lcells = np.ascontiguousarray(cloud.LCELLS, np.int32)
+        self.off = np.ascontiguousarray(cloud.OFF, np.int32)
+        self.dens = np.ascontiguousarray(cloud.DENS, np.float32)
+        self.par = np.zeros(max(1, cloud.CELLS - cloud.NX * cloud.NY * cloud.NZ), np.int32)
+        self.L.ref_parents(C.c_int(1024), _fp(self.dens), _ip(self.lcells), _ip(self.off), _ip(self.par))
+        n = cloud.CELLS
+        self.tabs = np.zeros(n, np.float32)
+        self.xab = np.zeros(n, np.float32)
+        self.int_ = np.zeros(n, np.float32)
+        self.intx = np.zeros(n, np.float32)
+        self.inty = np.zeros(n, np.float32)
+        self.intz = np.zeros(n, np.float32)
+        self._d = np.zeros(4, np.float32)
+        self._di = np.zeros(4, np.int32)
+
+    def threads(self):
+        return self.L.ref_threads()
+
+    def set_threads(self, n):
+        self.L.ref_set_threads(C.c_int(n))
+
+    def atomic_count(self, reset=True):
+        return int(self.L.ref_atomic_count(C.c_int(1 if reset else 0)))
+
+    def zero(self, tag):
+        if tag == 0:
+            self.tabs[:] = 0
+            self.xab[:] = 0
+        else:
+            self.int_[:] = 0
+            self.intx[:] = 0
+            self.inty[:] = 0
+            self.intz[:] = 0
+
+    def _f(self, a, dummy=None):
+        if a is None:
+            return _fp(self._d)
+        a = np.ascontiguousarray(a, np.float32)
+        self._keep.append(a)
+        return _fp(a)
+
+    def _i(self, a):
+        if a is None:
+            return _ip(self._di)
+        a = np.ascontiguousarray(a, np.int32)
+        self._keep.append(a)
+        return _ip(a)
+
+    def sim_pb(self, global_, source, packets, batch, seed, bg, tw, abs_=0.0, sca=0.0, dsc=None, csc=None, emit=None,
+               emwei=None, opt=None, pspos=None, ps=None, xps_nside=None, xps_side=None, xps_area=None, **_):
+        self._keep = []
+        a, s = np.array([abs_], np.float32), np.array([sca], np.float32)
+        self.L.ref_sim_pb(C.c_int(global_), C.c_int(source), C.c_int(packets), C.c_int(batch), C.c_float(seed),
+                          _fp(a), _fp(s), C.c_float(bg), self._f(pspos), self._f(ps), C.c_float(tw),
+                          _ip(self.lcells), _ip(self.off), _ip(self.par), _fp(self.dens), self._f(emit),
+                          _fp(self.tabs), self._f(dsc), self._f(csc), _fp(self.xab), self._f(emwei),
+                          _fp(self.int_), _fp(self.intx), _fp(self.inty), _fp(self.intz), self._f(opt),
+                          _fp(self._d), self._i(xps_nside), self._i(xps_side), self._f(xps_area))
+
+    def sim_hp(self, global_, packets, batch, seed, tw, abs_=0.0, sca=0.0, dsc=None, csc=None, opt=None, hpbg=None,
+               hpbgp=None, **_):
+        self._keep = []
+        a, s = np.array([abs_], np.float32), np.array([sca], np.float32)
+        self.L.ref_sim_hp(C.c_int(global_), C.c_int(packets), C.c_int(batch), C.c_float(seed), _fp(a), _fp(s),
+                          C.c_float(tw), _ip(self.lcells), _ip(self.off), _ip(self.par), _fp(self.dens),
+                          _fp(self._d), _fp(self.tabs), self._f(dsc), self._f(csc), _fp(self.xab), _fp(self.int_),
+                          _fp(self.intx), _fp(self.inty), _fp(self.intz), self._f(opt), self._f(hpbg),
+                          self._f(hpbgp), _fp(self._d))
+
+    def sim_cl(self, global_, packets, batch, seed, tw, abs_=0.0, sca=0.0, dsc=None, csc=None, emit=None, emwei=None,
+               opt=None, **_):
+        self._keep = []
+        a, s = np.array([abs_], np.float32), np.array([sca], np.float32)
+        self.L.ref_sim_cl(C.c_int(global_), C.c_int(2), C.c_int(packets), C.c_int(batch), C.c_float(seed), _fp(a),
+                          _fp(s), C.c_float(tw), _ip(self.lcells), _ip(self.off), _ip(self.par), _fp(self.dens),
+                          self._f(emit), _fp(self.tabs), self._f(dsc), self._f(csc), _fp(self.xab), self._f(emwei),
+                          _fp(self.int_), _fp(self.intx), _fp(self.inty), _fp(self.intz), _ip(self._di),
+                          self._f(opt), _fp(self._d))
+
+    def eq_temperature(self, level, adhoc, kE, Emin, NE, ttt, emit, tnew):
+        ttt = np.ascontiguousarray(ttt, np.float32)
+        emit = np.ascontiguousarray(emit, np.float32)
+        self.L.ref_eq_temperature(C.c_int(4096), C.c_int(level), C.c_float(adhoc), C.c_float(kE), C.c_float(Emin),
+                                  C.c_int(NE), _ip(self.off), _ip(self.lcells), _fp(ttt), _fp(self.dens), _fp(emit),
+                                  _fp(tnew))
+
+    def emission(self, freq, fabs_, t):
+        t = np.ascontiguousarray(t, np.float32)
+        out = np.zeros(self.cloud.CELLS, np.float32)
+        self.L.ref_emission(C.c_int(4096), C.c_float(freq), C.c_float(fabs_), _fp(self.dens), _fp(t), _fp(out))
+        return out
+
+    def mapping(self, map_dx, npx, npy, emit, dir_, ra, de, abs_, sca, centre, intobs=(-1e12, 0, 0), opt=None,
+                save_colden=0):
+        self._keep = []
+        m = np.zeros(npx * npy, np.float32)
+        t = np.zeros(npx * npy, np.float32)
+        v = [np.ascontiguousarray(x, np.float32) for x in (dir_, ra, de, centre, intobs)]
+        emit = np.ascontiguousarray(emit, np.float32)
+        glob = (1 + (npx * npy) // 8) * 8
+        self.L.ref_mapping(C.c_int(glob), C.c_float(map_dx), C.c_int(npx), C.c_int(npy), _fp(m), _fp(emit),
+                           _fp(v[0]), _fp(v[1]), _fp(v[2]), _ip(self.lcells), _ip(self.off), _ip(self.par),
+                           _fp(self.dens), C.c_float(abs_), C.c_float(sca), _fp(v[3]), _fp(v[4]), self._f(opt),
+                           _fp(t), C.c_int(save_colden))
+        return m.reshape(npy, npx), t.reshape(npy, npx)
+
+    def healpix_mapping(self, nside, emit, abs_, sca, intobs, opt=None, save_colden=0):
+        self._keep = []
+        n = 12 * nside * nside
+        m, t = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        z = np.zeros(3, np.float32)
+        io = np.ascontiguousarray(intobs, np.float32)
+        emit = np.ascontiguousarray(emit, np.float32)
+        self.L.ref_healpix_mapping(C.c_int(n), C.c_float(1.0), C.c_int(nside), C.c_int(0), _fp(m), _fp(emit),
+                                   _fp(z), _fp(z), _fp(z), _ip(self.lcells), _ip(self.off), _ip(self.par),
+                                   _fp(self.dens), C.c_float(abs_), C.c_float(sca), _fp(z), _fp(io), self._f(opt),
+                                   _fp(t), C.c_int(save_colden))
+        return m, t
+
+    def _v3(self, a):
+        a = np.ascontiguousarray(np.asarray(a, np.float32)[:, :3].reshape(-1))
+        self._keep.append(a)
+        return _fp(a)
+
+    def sca_ps(self, global_, packets, batch, seed, ndir, npx, npy, map_dx, centre, odirs, ora, ode, abs_=0.0,
+               sca=0.0, dsc=None, csc=None, opt=None, pspos=None, ps=None, **_):
+        self._keep = []
+        a, s = np.array([abs_], np.float32), np.array([sca], np.float32)
+        out = np.zeros(ndir * npx * npy, np.float32)
+        ce = np.ascontiguousarray(centre, np.float32)
+        self.L.ref_sca_ps(C.c_int(global_), C.c_int(packets), C.c_int(batch), C.c_float(seed), _fp(a), _fp(s),
+                          C.c_float(0.0), self._f(pspos), self._f(ps), _ip(self.lcells), _ip(self.off),
+                          _ip(self.par), _fp(self.dens), self._f(dsc), self._f(csc), C.c_int(ndir), self._v3(odirs),
+                          C.c_int(npx), C.c_int(npy), C.c_float(map_dx), _fp(ce), self._v3(ora), self._v3(ode),
+                          _fp(out), _fp(self._d), self._f(opt), _fp(self._d), _fp(self._d), _fp(self._d))
+        return out.reshape(ndir, npy, npx)
+
+    def sca_pb(self, global_, source, packets, batch, seed, bg, ndir, npx, npy, map_dx, centre, odirs, ora, ode,
+               abs_=0.0, sca=0.0, dsc=None, csc=None, opt=None, pspos=None, ps=None, **_):
+        self._keep = []
+        a, s = np.array([abs_], np.float32), np.array([sca], np.float32)
+        out = np.zeros(ndir * npx * npy, np.float32)
+        ce = np.ascontiguousarray(centre, np.float32)
+        self.L.ref_sca_pb(C.c_int(global_), C.c_int(source), C.c_int(packets), C.c_int(batch), C.c_float(seed),
+                          _fp(a), _fp(s), C.c_float(bg), self._f(pspos), self._f(ps), _ip(self.lcells),
+                          _ip(self.off), _ip(self.par), _fp(self.dens), self._f(dsc), self._f(csc), C.c_int(ndir),
+                          self._v3(odirs), C.c_int(npx), C.c_int(npy), C.c_float(map_dx), _fp(ce), self._v3(ora),
+                          self._v3(ode), _fp(out), _fp(self._d), self._f(opt), _fp(self._d), _fp(self._d),
+                          _fp(self._d))
+        return out.reshape(ndir, npy, npx)
+
+
+def rng_stream(lib, seed, id_, gsize, n):
+    out = np.zeros(n, np.uint32)
+    st = np.zeros(2, np.uint32)
+    lib.ref_rng_stream(C.c_float(seed), C.c_long(id_), C.c_long(gsize), C.c_int(n),
+                       out.ctypes.data_as(C.c_void_p), st.ctypes.data_as(C.c_void_p))
+    return st, out

@@ -31,6 +31,7 @@ static void flush_counter() {
 extern "C" {
 
 int ref_threads(void) { return omp_get_max_threads(); }
+void ref_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 unsigned long ref_atomic_count(int reset) { flush_counter(); unsigned long v = g_atomic_total; if (reset) g_atomic_total = 0; return v; }
 
 // MWC64X known-answer helper: first n outputs of the stream of work item `id`

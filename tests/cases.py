@@ -1,0 +1,211 @@
+"""Small seeded cases of the hot path, written against the common call shape shared by
+oracle.orc.Oracle, oracle.ref.Reference and soc_b200.backend.Backend, so that the same case can be run
+on the reference kernels (CPU shim), the plain-C oracle and the CUDA library and compared.
+
+Each case is   name -> (make_cloud, opts, run)   where run(X) returns {output name: ndarray}.
+"""
+import numpy as np
+
+from soc_b200 import synth
+from soc_b200.formats import Cloud
+from soc_b200.hostmath import observer_directions
+
+BINS = 2500
+DSC6, CSC6 = synth.hg_tables(0.6, BINS)
+DSC0, CSC0 = synth.hg_tables(0.0, BINS)
+
+
+def _reg(n):
+    return lambda: synth.regular_cloud(n)
+
+
+def _oct(nroot, levels, frac=0.2, seed=3):
+    return lambda: synth.octree_cloud(nroot, levels, refine_fraction=frac, seed=seed)
+
+
+def _tau_scale(cloud, tau):
+    """ABS/SCA per unit density so that the mean optical depth across the root grid is ~tau."""
+    m = cloud.DENS[:cloud.NX * cloud.NY * cloud.NZ]
+    mean = float(np.mean(np.where(m > 0, m, 1.0)))
+    return tau / (cloud.NX * mean)
+
+
+def run_bg(batch=2, tau_a=1.5, tau_s=2.5, seed=0.4, g=True):
+    def run(X):
+        c = X.cloud
+        glob = 8 * c.AREA
+        k = _tau_scale(c, 1.0)
+        X.zero(0)
+        X.zero(1)
+        X.sim_pb(glob, 1, glob * batch, batch, seed, 1.0, 0.7, abs_=tau_a * k, sca=tau_s * k,
+                 dsc=DSC6 if g else DSC0, csc=CSC6 if g else CSC0)
+        return dict(tabs=X.tabs.copy(), int=X.int_.copy())
+    return run
+
+
+def run_ps(pspos, batch=6, glob=2048, tau_a=2.0, tau_s=2.0, seed=0.31, **extra):
+    def run(X):
+        c = X.cloud
+        k = _tau_scale(c, 1.0)
+        ps = np.linspace(1.0, 2.0, len(pspos)).astype(np.float32)
+        X.zero(0)
+        X.zero(1)
+        X.sim_pb(glob, 0, glob * batch, batch * len(pspos), seed, 0.0, 1.3, abs_=tau_a * k, sca=tau_s * k,
+                 dsc=DSC6, csc=CSC6, pspos=np.asarray(pspos, np.float32).reshape(-1), ps=ps, **extra)
+        return dict(tabs=X.tabs.copy(), int=X.int_.copy())
+    return run
+
+
+def run_abu(batch=2, seed=0.77):
+    def run(X):
+        c = X.cloud
+        glob = 8 * c.AREA
+        k = _tau_scale(c, 1.0)
+        rng = np.random.default_rng(5)
+        opt = np.empty((c.CELLS, 2), np.float32)
+        opt[:, 0] = k * (1.0 + rng.random(c.CELLS))
+        opt[:, 1] = k * (1.5 + 2 * rng.random(c.CELLS))
+        X.zero(0)
+        X.zero(1)
+        X.sim_pb(glob, 1, glob * batch, batch, seed, 2.0, 1.0, dsc=DSC6, csc=CSC6, opt=opt.reshape(-1))
+        return dict(tabs=X.tabs.copy(), int=X.int_.copy())
+    return run
+
+
+def run_hp(weighted, batch=3, seed=0.52):
+    def run(X):
+        c = X.cloud
+        k = _tau_scale(c, 1.0)
+        rng = np.random.default_rng(11)
+        sky = (0.2 + rng.random(49152)).astype(np.float32)
+        sky[20000:20400] *= 30.0
+        hpbgp = None
+        if weighted:
+            p = sky.astype(np.float64) / sky.mean()
+            p = np.clip(p, 1e-3, 1e4)
+            p /= p.sum()
+            w = (1.0 / 49152.0) / p
+            hpbgp = np.cumsum(p)
+            hpbgp[-1] = 1.00001
+            sky = (sky * w).astype(np.float32)
+            hpbgp = hpbgp.astype(np.float32)
+        glob = 1024
+        X.zero(0)
+        X.zero(1)
+        X.sim_hp(glob, glob * batch, batch, seed, 0.9, abs_=1.2 * k, sca=2.0 * k, dsc=DSC6, csc=CSC6, hpbg=sky,
+                 hpbgp=hpbgp)
+        return dict(tabs=X.tabs.copy())
+    return run
+
+
+def run_cl(emweight, batch=2, glob=512, seed=0.13):
+    def run(X):
+        c = X.cloud
+        k = _tau_scale(c, 1.0)
+        rng = np.random.default_rng(7)
+        emit = np.where(c.DENS > 0, c.DENS * (0.5 + rng.random(c.CELLS)), 0.0).astype(np.float32)
+        emwei = None
+        if emweight:
+            emwei = (3.0 * rng.random(c.CELLS)).astype(np.float32)
+            emwei[::7] = 0.0
+        X.zero(0)
+        X.zero(1)
+        X.sim_cl(glob, c.CELLS * batch, batch, seed, 1.1, abs_=2.0 * k, sca=1.5 * k, dsc=DSC6, csc=CSC6, emit=emit,
+                 emwei=emwei)
+        return dict(tabs=X.tabs.copy(), xab=X.xab.copy())
+    return run
+
+
+def run_map(npix, dirs, map_dx=1.0, intobs=None, colden=0, abu=False, centre_off=0.0):
+    def run(X):
+        c = X.cloud
+        k = _tau_scale(c, 1.0)
+        rng = np.random.default_rng(9)
+        emit = np.where(c.DENS > 0, 1.0 + rng.random(c.CELLS), 0.0).astype(np.float32)
+        opt = None
+        if abu:
+            opt = np.empty((c.CELLS, 2), np.float32)
+            opt[:, 0] = k * (0.5 + rng.random(c.CELLS))
+            opt[:, 1] = k * (0.5 + rng.random(c.CELLS))
+            opt = opt.reshape(-1)
+        out = {}
+        _, od, ra, de = observer_directions([d[0] for d in dirs], [d[1] for d in dirs])
+        centre = np.array([0.5 * c.NX + centre_off, 0.5 * c.NY, 0.5 * c.NZ - centre_off], np.float32)
+        for i in range(len(dirs)):
+            io = (-1e12, 0.0, 0.0) if intobs is None else intobs
+            m, t = X.mapping(map_dx, npix[0], npix[1], emit, od[i], ra[i], de[i], 1.2 * k, 0.8 * k, centre,
+                             intobs=io, opt=opt, save_colden=colden)
+            out["map%d" % i] = m.copy()
+            out["tau%d" % i] = t.copy()
+        return out
+    return run
+
+
+def run_hpmap(nside, intobs):
+    def run(X):
+        c = X.cloud
+        k = _tau_scale(c, 1.0)
+        rng = np.random.default_rng(9)
+        emit = np.where(c.DENS > 0, 1.0 + rng.random(c.CELLS), 0.0).astype(np.float32)
+        m, t = X.healpix_mapping(nside, emit, 1.0 * k, 1.0 * k, np.asarray(intobs, np.float32))
+        return dict(map=m.copy(), tau=t.copy())
+    return run
+
+
+def run_sca(kind, npix=(24, 20), dirs=((0.0, 0.0), (70.0, 30.0)), batch=3, glob=1024, seed=0.61, pspos=None):
+    def run(X):
+        c = X.cloud
+        k = _tau_scale(c, 1.0)
+        _, od, ra, de = observer_directions([d[0] for d in dirs], [d[1] for d in dirs])
+        centre = np.array([0.5 * c.NX, 0.5 * c.NY, 0.5 * c.NZ], np.float32)
+        args = (len(dirs), npix[0], npix[1], 0.9 * c.NX / npix[0], centre, od, ra, de)
+        if kind == "ps":
+            pp = np.asarray(pspos, np.float32)
+            ps = np.linspace(1.0, 2.0, len(pp)).astype(np.float32)
+            out = X.sca_ps(glob, glob * batch, batch * len(pp), seed, *args, abs_=1.0 * k, sca=2.5 * k, dsc=DSC6,
+                           csc=CSC6, pspos=pp.reshape(-1), ps=ps)
+        else:
+            g = 8 * c.AREA
+            out = X.sca_pb(g, 1, g * batch, batch, seed, 1.5, *args, abs_=1.0 * k, sca=2.5 * k, dsc=DSC6, csc=CSC6)
+        return dict(out=out.copy())
+    return run
+
+
+# name -> (cloud factory, option dict (former -D macros), run)
+CASES = {
+    "bg_reg16":        (_reg(16), {}, run_bg()),
+    "bg_reg16_iso":    (_reg(16), {}, run_bg(g=False, tau_s=6.0)),
+    "bg_reg12_int":    (_reg(12), dict(noabsorbed=0), run_bg(batch=3, seed=0.9)),
+    "bg_reg12_int2":   (_reg(12), dict(save_intensity=2), run_bg(batch=2, seed=0.23)),
+    "bg_reg12_abu":    (_reg(12), dict(with_abu=1), run_abu()),
+    "bg_oct8_3":       (_oct(8, 3), {}, run_bg(batch=2)),
+    "bg_oct6_4":       (_oct(6, 4, 0.25, 8), dict(noabsorbed=0), run_bg(batch=3, seed=0.66)),
+    "ps_reg16_in":     (_reg(16), dict(no_ps=2), run_ps([(8.3, 8.3, 8.3), (3.7, 11.2, 5.1)])),
+    "ps_oct8_in":      (_oct(8, 3), dict(no_ps=1), run_ps([(4.3, 4.2, 3.9)], batch=12)),
+    "ps_reg12_ext0":   (_reg(12), dict(no_ps=1, ps_method=0), run_ps([(6.0, 6.0, 20.0)], batch=40)),
+    "ps_reg12_ext1":   (_reg(12), dict(no_ps=1, ps_method=1), run_ps([(-9.0, 5.0, 7.0)], batch=20)),
+    "ps_reg12_ext2":   (_reg(12), dict(no_ps=1, ps_method=2),
+                        run_ps([(6.0, 17.0, 16.0)], batch=10, xps_nside=[2], xps_side=[2, 4, 0],
+                               xps_area=[0.5, 0.5, 0.0])),
+    "ps_reg12_ext5":   (_reg(12), dict(no_ps=1, ps_method=5),
+                        run_ps([(6.0, 6.0, 25.0)], batch=10, xps_nside=[1], xps_side=[4, 0, 0],
+                               xps_area=[0.8, 0.0, 0.0])),
+    "hp_reg12":        (_reg(12), {}, run_hp(False)),
+    "hp_reg12_w":      (_reg(12), dict(hpbg_weighted=1), run_hp(True)),
+    "cl_reg10":        (_reg(10), {}, run_cl(False)),
+    "cl_oct6_ew_ali":  (_oct(6, 3), dict(use_emweight=1, with_ali=1), run_cl(True)),
+    "map_reg16":       (_reg(16), {}, run_map((20, 16), [(0.0, 0.0), (90.0, 0.0), (60.0, 30.0)])),
+    "map_reg16_colden": (_reg(16), {}, run_map((16, 16), [(35.0, 110.0)], map_dx=0.7, colden=1, centre_off=0.8)),
+    "map_reg120_dbl":  (lambda: Cloud(120, 8, 8, [120 * 64], synth.plummer_density(120)[56:64, 56:64, :].ravel()),
+                        {}, run_map((30, 8), [(90.0, 90.0), (50.0, 20.0)], map_dx=3.9)),
+    "map_oct8_3":      (_oct(8, 3), dict(with_abu=1), run_map((24, 24), [(0.0, 0.0), (60.0, 30.0)], map_dx=0.4, abu=True)),
+    "map_oct6_4_thr":  (_oct(6, 4, 0.25, 8), dict(level_threshold=1), run_map((20, 20), [(120.0, 200.0)], map_dx=0.35)),
+    "map_reg16_persp": (_reg(16), {}, run_map((32, 16), [(0.0, 0.0)], intobs=(7.3, 8.4, 9.1))),
+    "hpmap_oct8_3":    (_oct(8, 3), {}, run_hpmap(8, (4.2, 3.3, 5.1))),
+    "sca_ps_reg16":    (_reg(16), dict(no_ps=2), run_sca("ps", pspos=[(8.3, 8.3, 8.3), (4.1, 10.7, 12.2)])),
+    "sca_ps_oct8":     (_oct(8, 3), dict(no_ps=1, ffs=0), run_sca("ps", pspos=[(4.3, 4.2, 3.9)], batch=8)),
+    "sca_bg_reg12":    (_reg(12), {}, run_sca("bg", batch=1)),
+    "sca_bg_oct6":     (_oct(6, 3), {}, run_sca("bg", batch=1, dirs=((45.0, 45.0),))),
+}
+
+MAP_NSIDE = {"hpmap_oct8_3": 8}

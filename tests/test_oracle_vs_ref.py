@@ -1,0 +1,65 @@
+"""Pins the plain-C oracle (oracle/soc_oracle.c) against the reference's own kernels compiled in place
+from /root/reference (oracle/_ref via oracle/build_ref.py).  Both run single-threaded with identical
+MWC64X streams, so the Monte Carlo outputs must agree to float rounding, not just statistically.
+
+Skipped where neither /root/reference nor a prebuilt oracle/_ref library exists (e.g. the GPU box);
+tests/test_oracle_golden.py covers those machines with committed vectors."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import build_ref, orc, ref
+from tests.cases import CASES, MAP_NSIDE
+
+pytestmark = pytest.mark.skipif(not build_ref.reference_available(), reason="/root/reference not present")
+
+
+def _run(name):
+    make, opts, run = CASES[name]
+    cloud = make()
+    O = orc.Oracle(cloud, **opts)
+    R = ref.Reference(cloud, map_nside=MAP_NSIDE.get(name), **opts)
+    orc.set_threads(1)          # one thread: work items run in id order, float sums in the same order
+    R.set_threads(1)
+    return run(O), run(R), O, R
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_case_matches_reference(name):
+    o, r, O, R = _run(name)
+    for key in r:
+        a, b = o[key].astype(np.float64), r[key].astype(np.float64)
+        assert a.shape == b.shape
+        assert np.isfinite(a).all() and np.isfinite(b).all(), key
+        scale = np.abs(b).max() + 1e-300
+        if scale < 1e-290:
+            assert np.abs(a).max() < 1e-290
+            continue
+        # identical streams + identical arithmetic: at most a handful of cells may differ by rounding
+        bad = np.abs(a - b) > 2e-6 * scale
+        assert bad.mean() < 2e-3, "%s/%s: %d of %d differ (max %.3e of %.3e)" % (
+            name, key, bad.sum(), bad.size, np.abs(a - b).max(), scale)
+        assert abs(a.sum() - b.sum()) <= 1e-5 * abs(b.sum()) + 1e-300
+
+
+def test_rng_known_answers():
+    """MWC64X stream seeding: oracle == reference for several ids / seeds (mwc64x_rng.cl, skip_mwc.cl)."""
+    from tests.cases import CASES
+    make, opts, _ = CASES["bg_reg16"]
+    R = ref.Reference(make(), **opts)
+    for seed in (0.4, 0.123, 0.99999):
+        for id_ in (0, 1, 2, 12345, 3145727, 2 ** 25 - 1):
+            s1, o1 = orc.rng_stream(seed, id_, 8)
+            s2, o2 = ref.rng_stream(R.L, seed, id_, 2 ** 26, 8)
+            assert (s1 == s2).all() and (o1 == o2).all()
+
+
+def test_step_counter_matches_atomic_count():
+    """The oracle's cell-step counter equals the number of float atomic adds the reference performs."""
+    make, opts, run = CASES["bg_reg16"]
+    cloud = make()
+    O, R = orc.Oracle(cloud, **opts), ref.Reference(cloud, **opts)
+    R.atomic_count(reset=True)          # the shared object (and its counter) may have been used before
+    run(O), run(R)
+    assert O.counters.steps == R.atomic_count()
