@@ -1,0 +1,163 @@
+/* soc_b200 -- C ABI of the B200 (sm_100a) implementation of SOC's photon-packet hot path.
+ *
+ * This is the drop-in boundary: every entry point replaces one use of pyopencl by the reference
+ * drivers ASOC.py / ASOCS.py (context + queue, cl.Buffer + enqueue_copy, Program.build options,
+ * and the kernel launches).  Plain pointers and sizes only; all functions return 0 on success and
+ * a negative soc_status otherwise, with a human-readable message in soc_last_error().
+ * Calls are made from one host thread per context (like the reference's single in-order queue);
+ * launches are asynchronous on the context's stream, downloads and soc_sync() synchronise.
+ *
+ * Reference interfaces replaced (paths relative to the reference tree):
+ *   soc_create / soc_destroy / soc_sync     cl.Context, cl.CommandQueue, queue.finish()
+ *                                           (ASOC_aux.py:1188-1256, ASOC.py:336, 1461)
+ *   soc_set_params                          the -D macro list of Program.build (ASOC.py:344-396,
+ *                                           ASOCS.py:133-152)
+ *   soc_set_grid                            LCELLS/OFF/DENS/PAR buffers + kernel Parents
+ *                                           (ASOC.py:428-454, 524-527, 580-586; kernel_ASOC_aux.c:688)
+ *   soc_upload / soc_download / soc_clear   cl.Buffer + cl.enqueue_copy (ASOC.py:1174-1236, 1484, 1533)
+ *   soc_zero_amc                            kernel ZeroAMC (kernel_ASOC_aux.c:657; ASOC.py:1115, 1183)
+ *   soc_sim_pb / soc_sim_hp / soc_sim_cl    kernels SimRAM_PB / SimRAM_HP / SimRAM_CL
+ *                                           (kernel_ASOC.c:15, 831, 1223; ASOC.py:1317-1419, 1847)
+ *   soc_eq_temperature / soc_emission       kernels EqTemperature / Emission
+ *                                           (kernel_ASOC_aux.c:745, 793; ASOC.py:2027-2040, 2185-2197)
+ *   soc_mapping / soc_healpix_mapping       kernels Mapping / HealpixMapping
+ *                                           (kernel_ASOC_map.c:496, 890; ASOC.py:3127-3139)
+ *   soc_sca_zero_out / soc_sca_ps / _pb     kernels zero_out / SimRAM_PS / SimRAM_PB of
+ *                                           kernel_ASOC_sca.c:14, 1462, 471 (ASOCS.py:515, 665-708)
+ * New (no counterpart in the single-device reference):
+ *   soc_set_shard, soc_device_ptr           packet sharding over ranks and the device addresses a
+ *                                           host-side NCCL all-reduce needs
+ *   soc_set_rng_mode, soc_set_tuning,
+ *   soc_get_counters, soc_last_launch_ms,
+ *   soc_stream                              stream layout, accumulation engine, work counters, device timing
+ */
+#ifndef SOC_B200_H
+#define SOC_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct soc_context soc_context;
+
+enum soc_status {
+    SOC_OK = 0,
+    SOC_ERR_CUDA = -1,         /* CUDA runtime error (message has the CUDA error string)      */
+    SOC_ERR_ARG = -2,          /* bad argument / unknown buffer / size mismatch               */
+    SOC_ERR_STATE = -3,        /* call order: grid or params or a required buffer is missing  */
+    SOC_ERR_UNSUPPORTED = -4   /* option of the reference that this library does not implement */
+};
+
+/* The compile-time options of the reference kernels (ASOC.py:344-362) as run-time values.
+ * Options that cannot work in the reference as shipped (DIR_WEIGHT, PS_METHOD 3) or that are out of
+ * scope (WITH_MSF, ROI, DO_SPLIT, MIRROR, POLSTAT) are rejected with SOC_ERR_UNSUPPORTED. */
+typedef struct soc_params {
+    int32_t bins;              /* BINS: length of the DSC / CSC tables                        */
+    int32_t no_ps;             /* NO_PS (>=1)                                                 */
+    int32_t ps_method;         /* PS_METHOD 0,1,2,4,5                                         */
+    int32_t with_abu;          /* WITH_ABU: per-cell opacities in OPT[2*CELLS]                */
+    int32_t with_ali;          /* WITH_ALI: self-absorptions of SimRAM_CL go to XAB           */
+    int32_t noabsorbed;        /* NOABSORBED==0 -> per-frequency absorptions into INT         */
+    int32_t save_intensity;    /* SAVE_INTENSITY 0,1,2                                        */
+    int32_t use_emweight;      /* USE_EMWEIGHT 0,1                                            */
+    int32_t hpbg_weighted;     /* HPBG_WEIGHTED                                               */
+    int32_t ffs;               /* FFS: forced first scattering (scattered-light kernels)      */
+    int32_t step_weight;       /* STEP_WEIGHT <=0,1,2                                         */
+    int32_t level_threshold;   /* LEVEL_THRESHOLD (maps)                                      */
+    int32_t with_msf, mirror, dir_weight, do_split, roi_flags, map_interpolation; /* must be 0 */
+    float   sw_a, sw_b;        /* SW_A, SW_B                                                  */
+    float   length;            /* LENGTH = GL*PARSEC rounded as "%.5e" (ASOC.py:347,356)      */
+    float   factor;            /* FACTOR (1e20)                                               */
+    float   adhoc;             /* ADHOC (1.0)                                                 */
+    float   reserved;
+} soc_params;
+
+/* Device buffers.  Names are those of the reference's kernel arguments. */
+enum soc_buffer {
+    SOC_BUF_DENS = 0, SOC_BUF_PAR, SOC_BUF_TABS, SOC_BUF_XAB, SOC_BUF_INT, SOC_BUF_INTX, SOC_BUF_INTY,
+    SOC_BUF_INTZ, SOC_BUF_EMIT, SOC_BUF_EMWEI, SOC_BUF_OPT, SOC_BUF_DSC, SOC_BUF_CSC, SOC_BUF_PSPOS,
+    SOC_BUF_PS, SOC_BUF_XPS_NSIDE, SOC_BUF_XPS_SIDE, SOC_BUF_XPS_AREA, SOC_BUF_HPBG, SOC_BUF_HPBGP,
+    SOC_BUF_MAP, SOC_BUF_SAVETAU, SOC_BUF_OUT, SOC_BUF_ODIR, SOC_BUF_ORA, SOC_BUF_ODE, SOC_BUF_TTT,
+    SOC_BUF_TNEW, SOC_BUF_COUNT
+};
+
+/* Stream layout of the Monte Carlo kernels. */
+enum soc_rng_mode {
+    SOC_RNG_REFERENCE = 0,     /* MWC64X, one stream per reference work item (bit-compatible seeding) */
+    SOC_RNG_PACKET = 1         /* counter-based Philox4x32-10, one stream per photon packet            */
+};
+
+/* Work counters accumulated by the kernels. */
+typedef struct soc_counters {
+    uint64_t packets;          /* emitted photon packets                                  */
+    uint64_t steps;            /* cell-steps: absorption updates incl. partial steps; for the
+                                  scattered-light and map kernels every GetStep counts   */
+    uint64_t scatterings;
+    uint64_t peels;            /* peel-off rays (scattered-light kernels)                 */
+    uint64_t launches;         /* kernel launches issued by this context                  */
+    uint64_t reserved[3];
+} soc_counters;
+
+const char *soc_last_error(void);
+int  soc_version(void);
+
+int  soc_create(int device_ordinal, soc_context **ctx);
+int  soc_destroy(soc_context *ctx);
+int  soc_sync(soc_context *ctx);
+
+int  soc_set_params(soc_context *ctx, const soc_params *p);
+int  soc_set_grid(soc_context *ctx, int32_t nx, int32_t ny, int32_t nz, int32_t levels, int64_t cells,
+                  const int32_t *lcells, const int32_t *off, const float *dens);
+int  soc_set_rng_mode(soc_context *ctx, int mode);
+int  soc_set_shard(soc_context *ctx, int rank, int world);
+/* Accumulation engine of the absorption counters: deposit_mode 0 = one red.global.add.f32 per lane and step,
+ * 1 = lanes of a warp that hit the same cell are combined first, 2 = 1 + a shared-memory tile of cells around
+ * the point source.  refill_lanes: a warp takes new packets when at least this many lanes are idle (1..32).
+ * aggregate_steps: lanes are combined only while some packet of the warp is younger than this many steps. */
+int  soc_set_tuning(soc_context *ctx, int deposit_mode, int refill_lanes, int aggregate_steps);
+
+int  soc_upload(soc_context *ctx, int buffer, const void *host, size_t nbytes);
+int  soc_download(soc_context *ctx, int buffer, void *host, size_t nbytes);
+int  soc_clear(soc_context *ctx, int buffer, size_t nbytes);     /* allocate (if needed) and zero */
+void *soc_device_ptr(soc_context *ctx, int buffer, size_t *nbytes);
+
+int  soc_zero_amc(soc_context *ctx, int tag);
+
+/* `global` is the reference launch's global work size (number of work items); it defines the packet
+ * decomposition exactly as ASOC.py:1032-1092 does. */
+int  soc_sim_pb(soc_context *ctx, int source, int packets, int batch, float seed, float abs, float sca,
+                float bg, float tw, int global);
+int  soc_sim_hp(soc_context *ctx, int packets, int batch, float seed, float abs, float sca, float tw, int global);
+int  soc_sim_cl(soc_context *ctx, int source, int packets, int batch, float seed, float abs, float sca, float tw,
+                int global);
+
+/* EqTemperature: reads EMIT (absorbed energy) and DENS, writes TNEW for cells of `level`; TTT holds the
+ * E->T table.  Emission: reads TNEW, writes EMIT. */
+int  soc_eq_temperature(soc_context *ctx, int level, float adhoc, float kE, float Emin, int NE);
+int  soc_emission(soc_context *ctx, float freq, float fabs);
+
+/* Mapping: reads EMIT, DENS (OPT); writes MAP and SAVETAU [npix_y*npix_x]. intobs[0] <= -1e10 selects the
+ * orthographic projection. */
+int  soc_mapping(soc_context *ctx, float map_dx, int npix_x, int npix_y, const float dir[3], const float ra[3],
+                 const float de[3], float abs, float sca, const float centre[3], const float intobs[3],
+                 int save_colden);
+int  soc_healpix_mapping(soc_context *ctx, int nside, float abs, float sca, const float intobs[3], int save_colden);
+
+/* Scattered light (ASOCS.py).  ODIR/ORA/ODE are [ndir*3] floats (x,y,z), OUT is [ndir*npix_y*npix_x]. */
+int  soc_sca_zero_out(soc_context *ctx, int ndir, int npix_x, int npix_y);
+int  soc_sca_ps(soc_context *ctx, int packets, int batch, float seed, float abs, float sca, int ndir, int npix_x,
+                int npix_y, float map_dx, const float centre[3], int global);
+int  soc_sca_pb(soc_context *ctx, int source, int packets, int batch, float seed, float abs, float sca, float bg,
+                int ndir, int npix_x, int npix_y, float map_dx, const float centre[3], int global);
+
+int  soc_get_counters(soc_context *ctx, soc_counters *out);
+int  soc_reset_counters(soc_context *ctx);
+int  soc_last_launch_ms(soc_context *ctx, float *ms);     /* device time of the most recent kernel launch */
+void *soc_stream(soc_context *ctx);                       /* the context's cudaStream_t (for NCCL / event timing) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

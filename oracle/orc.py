@@ -230,6 +230,10 @@ def set_threads(n):
     lib().orc_set_threads(C.c_int(n))
 
 
+def set_chunk(n):
+    lib().orc_set_chunk(C.c_int(n))
+
+
 def threads():
     return lib().orc_threads()
 

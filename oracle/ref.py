@@ -59,6 +59,9 @@ class Reference:
     def set_threads(self, n):
         self.L.ref_set_threads(C.c_int(n))
 
+    def set_chunk(self, n):
+        self.L.ref_set_chunk(C.c_int(n))
+
     def atomic_count(self, reset=True):
         return int(self.L.ref_atomic_count(C.c_int(1 if reset else 0)))
 

@@ -12,7 +12,7 @@ extern thread_local unsigned long clshim_atomic_ok;
 #define REF_PARALLEL_FOR(GLOBAL, BODY)                                          \
     do {                                                                        \
         const long _g = (long)(GLOBAL);                                         \
-        _Pragma("omp parallel for schedule(dynamic,256)")                       \
+        _Pragma("omp parallel for schedule(runtime)")                       \
         for (long _id = 0; _id < _g; ++_id) {                                   \
             clshim_gid = (size_t)_id; clshim_gsize = (size_t)_g;                \
             BODY;                                                               \

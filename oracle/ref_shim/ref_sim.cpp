@@ -32,6 +32,9 @@ extern "C" {
 
 int ref_threads(void) { return omp_get_max_threads(); }
 void ref_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+// work items handed to a host thread at a time (OpenMP dynamic schedule); 256 unless changed
+void ref_set_chunk(int n) { omp_set_schedule(omp_sched_dynamic, n > 0 ? n : 256); }
+static struct RefInitSchedule { RefInitSchedule() { omp_set_schedule(omp_sched_dynamic, 256); } } ref_init_schedule;
 unsigned long ref_atomic_count(int reset) { flush_counter(); unsigned long v = g_atomic_total; if (reset) g_atomic_total = 0; return v; }
 
 // MWC64X known-answer helper: first n outputs of the stream of work item `id`

@@ -80,6 +80,9 @@ void orc_rng_stream_base(uint64_t base, int64_t id, int n, uint32_t *out, uint32
 }
 int orc_threads(void) { return omp_get_max_threads(); }
 void orc_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+/* work items handed to a host thread at a time (OpenMP dynamic schedule) */
+void orc_set_chunk(int n) { omp_set_schedule(omp_sched_dynamic, n > 0 ? n : 64); }
+__attribute__((constructor)) static void orc_init_schedule(void) { omp_set_schedule(omp_sched_dynamic, 64); }
 
 /* =================================================================================================
  * Grid navigation.  `KIND` selects the simulation kernels' variant (kernel_ASOC_aux.c) or the map
@@ -530,7 +533,7 @@ void orc_sim_pb(const OrcParams *P, const OrcGrid *G, const OrcSimBufs *B, int g
                 int batch, float seed, float bg, float tw, OrcCounters *C) {
     (void)packets;
     uint64_t np = 0, ns = 0, nsc = 0;
-    #pragma omp parallel for schedule(dynamic,256) reduction(+:np,ns,nsc)
+    #pragma omp parallel for schedule(runtime) reduction(+:np,ns,nsc)
     for (int id = 0; id < global; id++) {
         sim_t S; S.P = P; S.B = B; S.N = nav_make(P, G); S.tw = tw;
         S.use_int = (P->save_intensity == 1 || P->save_intensity == 2 || P->noabsorbed == 0);
@@ -582,7 +585,7 @@ void orc_sim_hp(const OrcParams *P, const OrcGrid *G, const OrcSimBufs *B, int g
                 float seed, float tw, OrcCounters *C) {
     (void)packets;
     uint64_t np = 0, ns = 0, nsc = 0;
-    #pragma omp parallel for schedule(dynamic,256) reduction(+:np,ns,nsc)
+    #pragma omp parallel for schedule(runtime) reduction(+:np,ns,nsc)
     for (int id = 0; id < global; id++) {
         sim_t S; S.P = P; S.B = B; S.N = nav_make(P, G); S.tw = tw;
         S.use_int = (P->save_intensity == 1 || P->save_intensity == 2 || P->noabsorbed == 0);
@@ -644,7 +647,7 @@ void orc_sim_cl(const OrcParams *P, const OrcGrid *G, const OrcSimBufs *B, int g
                 float seed, float tw, OrcCounters *C) {
     (void)packets;
     uint64_t np = 0, ns = 0, nsc = 0;
-    #pragma omp parallel for schedule(dynamic,64) reduction(+:np,ns,nsc)
+    #pragma omp parallel for schedule(runtime) reduction(+:np,ns,nsc)
     for (int id = 0; id < global; id++) {
         sim_t S; S.P = P; S.B = B; S.N = nav_make(P, G); S.tw = tw;
         S.use_int = (P->save_intensity == 1 || P->save_intensity == 2 || P->noabsorbed == 0);
@@ -771,7 +774,7 @@ void orc_mapping(const OrcParams *P, const OrcGrid *G, float map_dx, int npx, in
     v3 CE = { centre[0], centre[1], centre[2] }, IO = { intobs[0], intobs[1], intobs[2] };
     nav_t N = nav_make(P, G);
     uint64_t steps = 0;
-    #pragma omp parallel for schedule(dynamic,64) reduction(+:steps)
+    #pragma omp parallel for schedule(runtime) reduction(+:steps)
     for (int id = 0; id < npx * npy; id++) {
         uint64_t s = 0;
         map_pixel(P, &N, id, map_dx, npx, npy, map, emit, D, R, E, abs_, sca_, CE, IO, opt, savetau, save_colden, &s);
@@ -811,7 +814,7 @@ static void map_pix2ang(int nside, int ipix, float *phi, float *theta) {      /*
 void orc_healpix_mapping(const OrcParams *P, const OrcGrid *G, int nside, float *map, const float *emit, float abs_,
                          float sca_, const float *intobs, const float *opt, float *savetau, int save_colden) {
     nav_t N = nav_make(P, G);
-    #pragma omp parallel for schedule(dynamic,64)
+    #pragma omp parallel for schedule(runtime)
     for (int id = 0; id < 12 * nside * nside; id++) {
         float DTAU, TAU = 0.0f, PHOTONS = 0.0f, colden = 0.0f, dx, theta, phi;
         v3 POS, TMP; int ind, level = 0, oind;
@@ -953,7 +956,7 @@ void orc_sca_ps(const OrcParams *P, const OrcGrid *G, const OrcSimBufs *B, const
                 int packets, int batch, float seed, OrcCounters *C) {
     (void)packets;
     uint64_t np = 0, ns = 0, nsc = 0, npl = 0;
-    #pragma omp parallel for schedule(dynamic,64) reduction(+:np,ns,nsc,npl)
+    #pragma omp parallel for schedule(runtime) reduction(+:np,ns,nsc,npl)
     for (int id = 0; id < global; id++) {
         sca_t S; S.P = P; S.B = B; S.O = O; S.N = nav_make(P, G); memset(&S.c, 0, sizeof(S.c));
         rng_t rng; rng_seed(&rng, seed, (uint64_t)id);
@@ -975,7 +978,7 @@ void orc_sca_pb(const OrcParams *P, const OrcGrid *G, const OrcSimBufs *B, const
     const int NX = P->nx, NY = P->ny, NZ = P->nz;
     const int AREA = 2 * (NX * NY + NY * NZ + NZ * NX);
     uint64_t np = 0, ns = 0, nsc = 0, npl = 0;
-    #pragma omp parallel for schedule(dynamic,64) reduction(+:np,ns,nsc,npl)
+    #pragma omp parallel for schedule(runtime) reduction(+:np,ns,nsc,npl)
     for (int id = 0; id < global; id++) {
         if (source == 1 && id >= 8 * AREA) continue;
         sca_t S; S.P = P; S.B = B; S.O = O; S.N = nav_make(P, G); memset(&S.c, 0, sizeof(S.c));

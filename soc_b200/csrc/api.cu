@@ -1,0 +1,627 @@
+// soc_b200 -- the C ABI (include/soc_b200.h): context, device buffers, launches.
+//
+// One context = one CUDA device + one in-order stream, mirroring the reference's single pyopencl
+// queue (ASOC_aux.py:1188-1256).  Uploads and launches are asynchronous on that stream; downloads and
+// soc_sync() synchronise.  Errors never abort: every entry point returns a negative soc_status and
+// leaves a message for soc_last_error().
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <climits>
+#include <new>
+#include "sim.cuh"
+#include "map.cuh"
+#include "aux.cuh"
+#include "sca.cuh"
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail(SOC_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define NEED_CTX(c) do { if ((c) == nullptr) return fail(SOC_ERR_ARG, "null context"); \
+    cudaError_t e_ = cudaSetDevice((c)->device); if (e_ != cudaSuccess) \
+    return fail(SOC_ERR_CUDA, "cudaSetDevice(%d): %s", (c)->device, cudaGetErrorString(e_)); } while (0)
+
+struct DevBuf { void *ptr; size_t bytes; };
+
+struct soc_context {
+    int device, sms;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    bool timed;
+    DevBuf buf[SOC_BUF_COUNT];
+    unsigned long long *counters;      // device: packets, steps, scatterings, stuck, peels, work, -, -
+    unsigned long long launches;
+    soc_params P;
+    bool have_params, have_grid;
+    GridDesc G;
+    int rng_mode, rank, world;
+    int deposit, refill, agg_steps;
+    uint64_t pow2k[26];
+};
+
+static const char *buf_name(int b) {
+    static const char *n[SOC_BUF_COUNT] = { "DENS", "PAR", "TABS", "XAB", "INT", "INTX", "INTY", "INTZ", "EMIT", "EMWEI",
+        "OPT", "DSC", "CSC", "PSPOS", "PS", "XPS_NSIDE", "XPS_SIDE", "XPS_AREA", "HPBG", "HPBGP", "MAP", "SAVETAU", "OUT",
+        "ODIR", "ORA", "ODE", "TTT", "TNEW" };
+    return (b >= 0 && b < SOC_BUF_COUNT) ? n[b] : "?";
+}
+
+static int ensure(soc_context *c, int b, size_t bytes) {
+    if (b < 0 || b >= SOC_BUF_COUNT) return fail(SOC_ERR_ARG, "unknown buffer id %d", b);
+    if (c->buf[b].ptr != nullptr && c->buf[b].bytes == bytes) return SOC_OK;
+    if (c->buf[b].ptr != nullptr) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->buf[b].ptr)); c->buf[b].ptr = nullptr; c->buf[b].bytes = 0; }
+    if (bytes == 0) return SOC_OK;
+    CU(cudaMalloc(&c->buf[b].ptr, bytes));
+    c->buf[b].bytes = bytes;
+    return SOC_OK;
+}
+static int ensure_zeroed(soc_context *c, int b, size_t bytes) {
+    bool fresh = !(c->buf[b].ptr != nullptr && c->buf[b].bytes == bytes);
+    int r = ensure(c, b, bytes);
+    if (r != SOC_OK) return r;
+    if (fresh && bytes) CU(cudaMemsetAsync(c->buf[b].ptr, 0, bytes, c->stream));
+    return SOC_OK;
+}
+template <class T> static T *dptr(soc_context *c, int b) { return reinterpret_cast<T *>(c->buf[b].ptr); }
+static int need(soc_context *c, int b, size_t min_bytes, const char *who) {
+    if (c->buf[b].ptr == nullptr || c->buf[b].bytes < min_bytes)
+        return fail(SOC_ERR_STATE, "%s: buffer %s missing or too small (%zu < %zu bytes)", who, buf_name(b), c->buf[b].bytes, min_bytes);
+    return SOC_OK;
+}
+
+extern "C" {
+
+const char *soc_last_error(void) { return g_err; }
+int soc_version(void) { return 100; }
+
+int soc_create(int device_ordinal, soc_context **out) {
+    if (out == nullptr) return fail(SOC_ERR_ARG, "soc_create: null output pointer");
+    *out = nullptr;
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (device_ordinal < 0 || device_ordinal >= ndev) return fail(SOC_ERR_ARG, "soc_create: device %d of %d", device_ordinal, ndev);
+    CU(cudaSetDevice(device_ordinal));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device_ordinal));
+    if (prop.major < 10) return fail(SOC_ERR_UNSUPPORTED, "soc_create: device %s is sm_%d%d, this library is built for sm_100a", prop.name, prop.major, prop.minor);
+    soc_context *c = new (std::nothrow) soc_context();
+    if (c == nullptr) return fail(SOC_ERR_ARG, "out of host memory");
+    memset(c, 0, sizeof(*c));
+    c->device = device_ordinal; c->sms = prop.multiProcessorCount;
+    c->rng_mode = SOC_RNG_PACKET; c->rank = 0; c->world = 1;
+    c->deposit = DEP_RED; c->refill = 8; c->agg_steps = 24;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&c->ev0));
+    CU(cudaEventCreate(&c->ev1));
+    CU(cudaMalloc(&c->counters, 8 * sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(c->counters, 0, 8 * sizeof(unsigned long long), c->stream));
+    uint64_t p = mwc_powmod(MWC_A, 274877906944ull);            // A^(2^38)
+    for (int k = 0; k < 26; k++) { c->pow2k[k] = p; p = mwc_mulmod(p, p); }
+    *out = c;
+    return SOC_OK;
+}
+
+int soc_destroy(soc_context *c) {
+    if (c == nullptr) return SOC_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (int b = 0; b < SOC_BUF_COUNT; b++) if (c->buf[b].ptr) cudaFree(c->buf[b].ptr);
+    cudaFree(c->counters);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return SOC_OK;
+}
+
+int soc_sync(soc_context *c) {
+    NEED_CTX(c);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    return SOC_OK;
+}
+
+int soc_set_params(soc_context *c, const soc_params *p) {
+    NEED_CTX(c);
+    if (p == nullptr) return fail(SOC_ERR_ARG, "soc_set_params: null");
+    if (p->with_msf || p->mirror || p->dir_weight || p->do_split || p->roi_flags || p->map_interpolation)
+        return fail(SOC_ERR_UNSUPPORTED, "soc_set_params: WITH_MSF / MIRROR / DIR_WEIGHT / DO_SPLIT / ROI / MAP_INTERPOLATION are not implemented");
+    if (p->ps_method == 3 || p->ps_method < 0 || p->ps_method > 5)
+        return fail(SOC_ERR_UNSUPPORTED, "soc_set_params: PS_METHOD %d (the reference's method 3 does not compile either)", p->ps_method);
+    if (p->bins < 2) return fail(SOC_ERR_ARG, "soc_set_params: BINS=%d", p->bins);
+    if (p->no_ps < 1) return fail(SOC_ERR_ARG, "soc_set_params: NO_PS must be >= 1 (ASOC.py:344 passes max(1,NO_PS))");
+    if (p->save_intensity < 0 || p->save_intensity > 2) return fail(SOC_ERR_ARG, "soc_set_params: SAVE_INTENSITY=%d", p->save_intensity);
+    if (!(p->length > 0.0f) || !(p->factor > 0.0f) || !(p->adhoc > 0.0f)) return fail(SOC_ERR_ARG, "soc_set_params: LENGTH, FACTOR, ADHOC must be positive");
+    c->P = *p;
+    c->have_params = true;
+    return SOC_OK;
+}
+
+int soc_set_grid(soc_context *c, int32_t nx, int32_t ny, int32_t nz, int32_t levels, int64_t cells,
+                 const int32_t *lcells, const int32_t *off, const float *dens) {
+    NEED_CTX(c);
+    if (nx < 1 || ny < 1 || nz < 1 || levels < 1 || levels > SOC_MAX_LEVELS || lcells == nullptr || off == nullptr || dens == nullptr)
+        return fail(SOC_ERR_ARG, "soc_set_grid: bad dimensions (levels must be 1..%d)", SOC_MAX_LEVELS);
+    if (cells < 1 || cells > INT_MAX) return fail(SOC_ERR_ARG, "soc_set_grid: CELLS=%lld exceeds the int32 cell index of the file formats", (long long)cells);
+    long long sum = 0;
+    for (int l = 0; l < levels; l++) {
+        if (off[l] != sum || lcells[l] < 0) return fail(SOC_ERR_ARG, "soc_set_grid: OFF/LCELLS inconsistent at level %d", l);
+        if (l > 0 && (lcells[l] % 8) != 0) return fail(SOC_ERR_ARG, "soc_set_grid: level %d does not consist of octets", l);
+        sum += lcells[l];
+    }
+    if (sum != cells || (long long)nx * ny * nz != lcells[0]) return fail(SOC_ERR_ARG, "soc_set_grid: sum(LCELLS) != CELLS or LCELLS[0] != NX*NY*NZ");
+    GridDesc &G = c->G;
+    memset(&G, 0, sizeof(G));
+    G.nx = nx; G.ny = ny; G.nz = nz; G.levels = levels; G.cells = (int)cells; G.nxyz = nx * ny * nz;
+    G.area = 2 * (nx * ny + ny * nz + nz * nx);
+    G.dbl_sim = nx > (levels < 3 ? 399 : 100);            // DIMLIM, kernel_ASOC_aux.c:25-37
+    G.dbl_map = nx > 100;                                 // kernel_ASOC_map.c:302
+    for (int l = 0; l < levels; l++) { G.off[l] = off[l]; G.lcells[l] = lcells[l]; }
+    int r = ensure(c, SOC_BUF_DENS, (size_t)cells * 4);
+    if (r != SOC_OK) return r;
+    CU(cudaMemcpyAsync(c->buf[SOC_BUF_DENS].ptr, dens, (size_t)cells * 4, cudaMemcpyHostToDevice, c->stream));
+    size_t npar = (size_t)(cells - G.nxyz);
+    r = ensure(c, SOC_BUF_PAR, (npar > 0 ? npar : 1) * 4);
+    if (r != SOC_OK) return r;
+    G.dens = dptr<float>(c, SOC_BUF_DENS);
+    G.par = dptr<int>(c, SOC_BUF_PAR);
+    if (levels > 1) { launch_parents(G, dptr<int>(c, SOC_BUF_PAR), c->stream); c->launches += levels - 1; }
+    CU(cudaGetLastError());
+    c->have_grid = true;
+    return SOC_OK;
+}
+
+int soc_set_rng_mode(soc_context *c, int mode) {
+    NEED_CTX(c);
+    if (mode != SOC_RNG_REFERENCE && mode != SOC_RNG_PACKET) return fail(SOC_ERR_ARG, "soc_set_rng_mode: %d", mode);
+    c->rng_mode = mode;
+    return SOC_OK;
+}
+
+int soc_set_shard(soc_context *c, int rank, int world) {
+    NEED_CTX(c);
+    if (world < 1 || rank < 0 || rank >= world) return fail(SOC_ERR_ARG, "soc_set_shard: rank %d of %d", rank, world);
+    c->rank = rank; c->world = world;
+    return SOC_OK;
+}
+
+int soc_set_tuning(soc_context *c, int deposit_mode, int refill_lanes, int aggregate_steps) {
+    NEED_CTX(c);
+    if (deposit_mode < DEP_RED || deposit_mode > DEP_TILE) return fail(SOC_ERR_ARG, "soc_set_tuning: deposit mode %d", deposit_mode);
+    if (refill_lanes < 1 || refill_lanes > 32) return fail(SOC_ERR_ARG, "soc_set_tuning: refill lanes %d", refill_lanes);
+    c->deposit = deposit_mode; c->refill = refill_lanes; c->agg_steps = aggregate_steps;
+    return SOC_OK;
+}
+
+int soc_upload(soc_context *c, int b, const void *host, size_t nbytes) {
+    NEED_CTX(c);
+    if (b == SOC_BUF_DENS || b == SOC_BUF_PAR) return fail(SOC_ERR_ARG, "soc_upload: %s is set by soc_set_grid", buf_name(b));
+    if (host == nullptr && nbytes) return fail(SOC_ERR_ARG, "soc_upload(%s): null host pointer", buf_name(b));
+    int r = ensure(c, b, nbytes);
+    if (r != SOC_OK) return r;
+    if (nbytes) CU(cudaMemcpyAsync(c->buf[b].ptr, host, nbytes, cudaMemcpyHostToDevice, c->stream));
+    return SOC_OK;
+}
+
+int soc_download(soc_context *c, int b, void *host, size_t nbytes) {
+    NEED_CTX(c);
+    if (b < 0 || b >= SOC_BUF_COUNT) return fail(SOC_ERR_ARG, "unknown buffer id %d", b);
+    if (host == nullptr && nbytes) return fail(SOC_ERR_ARG, "soc_download(%s): null host pointer", buf_name(b));
+    if (c->buf[b].ptr == nullptr || c->buf[b].bytes < nbytes)
+        return fail(SOC_ERR_ARG, "soc_download(%s): %zu bytes requested, buffer holds %zu", buf_name(b), nbytes, c->buf[b].bytes);
+    if (nbytes) CU(cudaMemcpyAsync(host, c->buf[b].ptr, nbytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return SOC_OK;
+}
+
+int soc_clear(soc_context *c, int b, size_t nbytes) {
+    NEED_CTX(c);
+    if (b == SOC_BUF_DENS || b == SOC_BUF_PAR) return fail(SOC_ERR_ARG, "soc_clear: %s is set by soc_set_grid", buf_name(b));
+    int r = ensure(c, b, nbytes);
+    if (r != SOC_OK) return r;
+    if (nbytes) CU(cudaMemsetAsync(c->buf[b].ptr, 0, nbytes, c->stream));
+    return SOC_OK;
+}
+
+void *soc_device_ptr(soc_context *c, int b, size_t *nbytes) {
+    if (c == nullptr || b < 0 || b >= SOC_BUF_COUNT) { if (nbytes) *nbytes = 0; return nullptr; }
+    if (nbytes) *nbytes = c->buf[b].bytes;
+    return c->buf[b].ptr;
+}
+
+void *soc_stream(soc_context *c) { return c ? (void *)c->stream : nullptr; }
+
+static bool wants_int(const soc_params &P) { return P.save_intensity == 1 || P.save_intensity == 2 || P.noabsorbed == 0; }
+
+int soc_zero_amc(soc_context *c, int tag) {
+    NEED_CTX(c);
+    if (!c->have_grid || !c->have_params) return fail(SOC_ERR_STATE, "soc_zero_amc: grid and params first");
+    const size_t n = (size_t)c->G.cells * 4;
+    int r;
+    if (tag == 0) {
+        if ((r = soc_clear(c, SOC_BUF_TABS, n)) != SOC_OK) return r;
+        if (c->P.with_ali && (r = soc_clear(c, SOC_BUF_XAB, n)) != SOC_OK) return r;
+    } else {
+        if (wants_int(c->P) && (r = soc_clear(c, SOC_BUF_INT, n)) != SOC_OK) return r;
+        if (c->P.save_intensity == 2) {
+            if ((r = soc_clear(c, SOC_BUF_INTX, n)) != SOC_OK) return r;
+            if ((r = soc_clear(c, SOC_BUF_INTY, n)) != SOC_OK) return r;
+            if ((r = soc_clear(c, SOC_BUF_INTZ, n)) != SOC_OK) return r;
+        }
+    }
+    return SOC_OK;
+}
+
+// kernel_ASOC.c:77: base offset of the MWC64X streams from the float seed
+static uint64_t seed_to_base(float seed) {
+    volatile float a = seed * 7.0f;
+    volatile float b = a * 3.1415926535897f;
+    volatile float f = fmodf(b, 1.0f);
+    volatile float g = f * (float)4294967296L;
+    return (uint64_t)g;
+}
+
+static int sim_common(soc_context *c, SimArgs &A, int kind, int batch, float seed, float kabs, float ksca, float tw,
+                      int global, const char *who) {
+    if (!c->have_grid || !c->have_params) return fail(SOC_ERR_STATE, "%s: soc_set_grid and soc_set_params first", who);
+    if (batch < 1 || global < 1) return fail(SOC_ERR_ARG, "%s: batch=%d global=%d", who, batch, global);
+    const soc_params &P = c->P;
+    const size_t n = (size_t)c->G.cells * 4;
+    int r;
+    memset(&A, 0, sizeof(A));
+    A.G = c->G;
+    if ((r = ensure_zeroed(c, SOC_BUF_TABS, n)) != SOC_OK) return r;
+    if (P.with_ali && (r = ensure_zeroed(c, SOC_BUF_XAB, n)) != SOC_OK) return r;
+    A.use_int = wants_int(P) ? 1 : 0;
+    A.save_int2 = P.save_intensity == 2;
+    if (A.use_int && (r = ensure_zeroed(c, SOC_BUF_INT, n)) != SOC_OK) return r;
+    if (A.save_int2) {
+        if ((r = ensure_zeroed(c, SOC_BUF_INTX, n)) != SOC_OK) return r;
+        if ((r = ensure_zeroed(c, SOC_BUF_INTY, n)) != SOC_OK) return r;
+        if ((r = ensure_zeroed(c, SOC_BUF_INTZ, n)) != SOC_OK) return r;
+    }
+    if ((r = need(c, SOC_BUF_CSC, (size_t)P.bins * 4, who)) != SOC_OK) return r;
+    if (P.with_abu && (r = need(c, SOC_BUF_OPT, 2 * n, who)) != SOC_OK) return r;
+    A.tabs = dptr<float>(c, SOC_BUF_TABS); A.xab = dptr<float>(c, SOC_BUF_XAB);
+    A.inten = dptr<float>(c, SOC_BUF_INT); A.intx = dptr<float>(c, SOC_BUF_INTX);
+    A.inty = dptr<float>(c, SOC_BUF_INTY); A.intz = dptr<float>(c, SOC_BUF_INTZ);
+    A.emit = dptr<float>(c, SOC_BUF_EMIT); A.emwei = dptr<float>(c, SOC_BUF_EMWEI); A.opt = dptr<float>(c, SOC_BUF_OPT);
+    A.dsc = dptr<float>(c, SOC_BUF_DSC); A.csc = dptr<float>(c, SOC_BUF_CSC);
+    A.pspos = dptr<float>(c, SOC_BUF_PSPOS); A.ps = dptr<float>(c, SOC_BUF_PS); A.xps_area = dptr<float>(c, SOC_BUF_XPS_AREA);
+    A.xps_nside = dptr<int>(c, SOC_BUF_XPS_NSIDE); A.xps_side = dptr<int>(c, SOC_BUF_XPS_SIDE);
+    A.hpbg = dptr<float>(c, SOC_BUF_HPBG); A.hpbgp = dptr<float>(c, SOC_BUF_HPBGP);
+    A.kabs = kabs; A.ksca = ksca; A.tw = tw; A.adhoc = P.adhoc; A.sw_a = P.sw_a; A.sw_b = P.sw_b;
+    A.kind = kind; A.batch = batch; A.global = global;
+    A.bins = P.bins; A.no_ps = P.no_ps; A.ps_method = P.ps_method; A.with_abu = P.with_abu; A.with_ali = P.with_ali;
+    A.use_emweight = P.use_emweight; A.hpbg_weighted = P.hpbg_weighted; A.step_weight = P.step_weight;
+    A.rank = c->rank; A.world = c->world;
+    long long ms = 100LL * ((long long)c->G.nx + c->G.ny + c->G.nz) << (c->G.levels - 1);
+    A.max_steps = (int)(ms > INT_MAX ? INT_MAX : ms);
+    A.deposit = c->deposit; A.refill = c->refill; A.agg_steps = c->agg_steps;
+    A.counters = c->counters; A.work = c->counters + 5;
+    // stream layouts
+    A.mwc.base_offset = seed_to_base(seed);
+    A.mwc.base_state = mwc_mulmod(MWC_BASEID, mwc_powmod(MWC_A, A.mwc.base_offset));
+    for (int k = 0; k < 26; k++) A.mwc.pow2k[k] = c->pow2k[k];
+    uint32_t sb; memcpy(&sb, &seed, 4);
+    A.phx.k0 = sb; A.phx.k1 = 0x534F4332u; A.phx.tag = (uint32_t)kind; A.phx.pad = 0;
+    return SOC_OK;
+}
+
+static int sim_launch(soc_context *c, SimArgs &A, const char *who) {
+    const bool oct = A.G.levels > 1, dbl = A.G.dbl_sim != 0;
+    int threads, blocks;
+    if (c->rng_mode == SOC_RNG_REFERENCE) {
+        threads = 128;
+        long long local = (A.nunits - A.rank + A.world - 1) / A.world;
+        blocks = (int)((local + threads - 1) / threads);
+        if (blocks < 1) blocks = 1;
+    } else {
+        threads = 256;
+        blocks = c->sms * sim_blocks_per_sm(c->rng_mode, oct, dbl, threads);
+        long long local = (A.nunits - A.rank + A.world - 1) / A.world;
+        long long needb = (local + threads - 1) / threads;
+        if (needb < blocks) blocks = (int)(needb < 1 ? 1 : needb);
+        CU(cudaMemsetAsync(A.work, 0, sizeof(unsigned long long), c->stream));
+    }
+    CU(cudaEventRecord(c->ev0, c->stream));
+    launch_sim(A, c->rng_mode, blocks, threads, c->stream);
+    CU(cudaEventRecord(c->ev1, c->stream));
+    c->timed = true;
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(SOC_ERR_CUDA, "%s: launch failed: %s", who, cudaGetErrorString(e));
+    return SOC_OK;
+}
+
+int soc_sim_pb(soc_context *c, int source, int packets, int batch, float seed, float abs, float sca, float bg, float tw, int global) {
+    NEED_CTX(c);
+    (void)packets;
+    if (source != 0 && source != 1) return fail(SOC_ERR_UNSUPPORTED, "soc_sim_pb: SOURCE=%d (ROI loading is not implemented)", source);
+    SimArgs A;
+    int r = sim_common(c, A, source == 0 ? SIM_PS : SIM_BG, batch, seed, abs, sca, tw, global, "soc_sim_pb");
+    if (r != SOC_OK) return r;
+    A.bg = bg;
+    if (source == 0) {
+        const size_t nps = (size_t)c->P.no_ps;
+        if ((r = need(c, SOC_BUF_PSPOS, nps * 12, "soc_sim_pb")) != SOC_OK) return r;
+        if ((r = need(c, SOC_BUF_PS, nps * 4, "soc_sim_pb")) != SOC_OK) return r;
+        if (c->P.ps_method == 2) {
+            if ((r = need(c, SOC_BUF_XPS_NSIDE, nps * 4, "soc_sim_pb")) != SOC_OK) return r;
+        }
+        if (c->P.ps_method == 2 || c->P.ps_method == 5) {
+            if ((r = need(c, SOC_BUF_XPS_SIDE, nps * 12, "soc_sim_pb")) != SOC_OK) return r;
+            if ((r = need(c, SOC_BUF_XPS_AREA, nps * 12, "soc_sim_pb")) != SOC_OK) return r;
+        }
+    }
+    if (c->rng_mode == SOC_RNG_REFERENCE) A.nunits = global;
+    else A.nunits = (source == 1 ? (long long)(8LL * c->G.area < global ? 8LL * c->G.area : global) : (long long)global) * batch;
+    // shared-memory tile around the first point source (regular grids)
+    if (A.deposit == DEP_TILE) {
+        if (source == 0 && c->G.levels == 1 && c->P.no_ps == 1) {
+            float p[3];
+            CU(cudaMemcpyAsync(p, c->buf[SOC_BUF_PSPOS].ptr, 12, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            int o[3], dim[3] = { c->G.nx, c->G.ny, c->G.nz };
+            for (int k = 0; k < 3; k++) {
+                o[k] = (int)floorf(p[k]) - SOC_TILE_N / 2;
+                if (o[k] > dim[k] - SOC_TILE_N) o[k] = dim[k] - SOC_TILE_N;
+                if (o[k] < 0) o[k] = 0;
+            }
+            A.tile_x0 = o[0]; A.tile_y0 = o[1]; A.tile_z0 = o[2];
+            A.tile_lo = o[2] * c->G.nx * c->G.ny;
+            A.tile_span = SOC_TILE_N * c->G.nx * c->G.ny;
+        } else A.deposit = DEP_WARP;
+    }
+    return sim_launch(c, A, "soc_sim_pb");
+}
+
+int soc_sim_hp(soc_context *c, int packets, int batch, float seed, float abs, float sca, float tw, int global) {
+    NEED_CTX(c);
+    (void)packets;
+    SimArgs A;
+    int r = sim_common(c, A, SIM_HP, batch, seed, abs, sca, tw, global, "soc_sim_hp");
+    if (r != SOC_OK) return r;
+    if ((r = need(c, SOC_BUF_HPBG, 49152 * 4, "soc_sim_hp")) != SOC_OK) return r;
+    if (c->P.hpbg_weighted && (r = need(c, SOC_BUF_HPBGP, 49152 * 4, "soc_sim_hp")) != SOC_OK) return r;
+    // kernel_ASOC.c:878: work items beyond 8*AREA return without simulating anything
+    long long items = 8LL * c->G.area < global ? 8LL * c->G.area : global;
+    A.nunits = (c->rng_mode == SOC_RNG_REFERENCE) ? global : items * batch;
+    if (A.deposit == DEP_TILE) A.deposit = DEP_WARP;
+    return sim_launch(c, A, "soc_sim_hp");
+}
+
+int soc_sim_cl(soc_context *c, int source, int packets, int batch, float seed, float abs, float sca, float tw, int global) {
+    NEED_CTX(c);
+    (void)packets; (void)source;
+    SimArgs A;
+    int r = sim_common(c, A, SIM_CL, batch, seed, abs, sca, tw, global, "soc_sim_cl");
+    if (r != SOC_OK) return r;
+    const size_t n = (size_t)c->G.cells * 4;
+    if ((r = need(c, SOC_BUF_EMIT, n, "soc_sim_cl")) != SOC_OK) return r;
+    if (c->P.use_emweight && (r = need(c, SOC_BUF_EMWEI, n, "soc_sim_cl")) != SOC_OK) return r;
+    if (c->P.use_emweight > 1) return fail(SOC_ERR_UNSUPPORTED, "soc_sim_cl: USE_EMWEIGHT=2 is not implemented");
+    A.nunits = (c->rng_mode == SOC_RNG_REFERENCE) ? global : c->G.cells;
+    if (A.deposit == DEP_TILE) A.deposit = DEP_WARP;
+    return sim_launch(c, A, "soc_sim_cl");
+}
+
+int soc_eq_temperature(soc_context *c, int level, float adhoc, float kE, float Emin, int NE) {
+    NEED_CTX(c);
+    if (!c->have_grid || !c->have_params) return fail(SOC_ERR_STATE, "soc_eq_temperature: grid and params first");
+    if (level < 0 || level >= c->G.levels || NE < 2) return fail(SOC_ERR_ARG, "soc_eq_temperature: level %d NE %d", level, NE);
+    const size_t n = (size_t)c->G.cells * 4;
+    int r;
+    if ((r = need(c, SOC_BUF_TTT, (size_t)NE * 4, "soc_eq_temperature")) != SOC_OK) return r;
+    if ((r = need(c, SOC_BUF_EMIT, n, "soc_eq_temperature")) != SOC_OK) return r;
+    if ((r = ensure_zeroed(c, SOC_BUF_TNEW, n)) != SOC_OK) return r;
+    launch_eq_temperature(c->G, level, adhoc, kE, Emin, NE, c->P.factor, c->P.length, dptr<float>(c, SOC_BUF_TTT),
+                          dptr<float>(c, SOC_BUF_EMIT), dptr<float>(c, SOC_BUF_TNEW), c->stream);
+    c->launches++;
+    CU(cudaGetLastError());
+    return SOC_OK;
+}
+
+int soc_emission(soc_context *c, float freq, float fabs_) {
+    NEED_CTX(c);
+    if (!c->have_grid || !c->have_params) return fail(SOC_ERR_STATE, "soc_emission: grid and params first");
+    const size_t n = (size_t)c->G.cells * 4;
+    int r;
+    if ((r = need(c, SOC_BUF_TNEW, n, "soc_emission")) != SOC_OK) return r;
+    if ((r = ensure(c, SOC_BUF_EMIT, n)) != SOC_OK) return r;
+    launch_emission(c->G.cells, freq, fabs_, c->P.factor, c->P.length, dptr<float>(c, SOC_BUF_TNEW), dptr<float>(c, SOC_BUF_EMIT), c->stream);
+    c->launches++;
+    CU(cudaGetLastError());
+    return SOC_OK;
+}
+
+static int map_common(soc_context *c, MapArgs &M, size_t npixels, float abs, float sca, int save_colden, const char *who) {
+    if (!c->have_grid || !c->have_params) return fail(SOC_ERR_STATE, "%s: grid and params first", who);
+    const size_t n = (size_t)c->G.cells * 4;
+    int r;
+    if ((r = need(c, SOC_BUF_EMIT, n, who)) != SOC_OK) return r;
+    if (c->P.with_abu && (r = need(c, SOC_BUF_OPT, 2 * n, who)) != SOC_OK) return r;
+    if ((r = ensure(c, SOC_BUF_MAP, npixels * 4)) != SOC_OK) return r;
+    if ((r = ensure(c, SOC_BUF_SAVETAU, npixels * 4)) != SOC_OK) return r;
+    memset(&M, 0, sizeof(M));
+    M.G = c->G;
+    M.map = dptr<float>(c, SOC_BUF_MAP); M.savetau = dptr<float>(c, SOC_BUF_SAVETAU);
+    M.emit = dptr<float>(c, SOC_BUF_EMIT); M.opt = dptr<float>(c, SOC_BUF_OPT);
+    M.kabs = abs; M.ksca = sca; M.length = c->P.length;
+    M.with_abu = c->P.with_abu; M.level_threshold = c->P.level_threshold; M.save_colden = save_colden;
+    M.counters = c->counters;
+    return SOC_OK;
+}
+
+int soc_mapping(soc_context *c, float map_dx, int npix_x, int npix_y, const float dir[3], const float ra[3],
+                const float de[3], float abs, float sca, const float centre[3], const float intobs[3], int save_colden) {
+    NEED_CTX(c);
+    if (npix_x < 1 || npix_y < 1 || !dir || !ra || !de || !centre || !intobs) return fail(SOC_ERR_ARG, "soc_mapping: bad arguments");
+    MapArgs M;
+    int r = map_common(c, M, (size_t)npix_x * npix_y, abs, sca, save_colden, "soc_mapping");
+    if (r != SOC_OK) return r;
+    M.dir = { dir[0], dir[1], dir[2] }; M.ra = { ra[0], ra[1], ra[2] }; M.de = { de[0], de[1], de[2] };
+    M.centre = { centre[0], centre[1], centre[2] }; M.intobs = { intobs[0], intobs[1], intobs[2] };
+    M.map_dx = map_dx; M.npx = npix_x; M.npy = npix_y;
+    CU(cudaEventRecord(c->ev0, c->stream));
+    launch_mapping(M, false, c->stream);
+    CU(cudaEventRecord(c->ev1, c->stream));
+    c->timed = true; c->launches++;
+    CU(cudaGetLastError());
+    return SOC_OK;
+}
+
+int soc_healpix_mapping(soc_context *c, int nside, float abs, float sca, const float intobs[3], int save_colden) {
+    NEED_CTX(c);
+    if (nside < 1 || nside > 8192 || !intobs) return fail(SOC_ERR_ARG, "soc_healpix_mapping: bad arguments");
+    MapArgs M;
+    int r = map_common(c, M, (size_t)12 * nside * nside, abs, sca, save_colden, "soc_healpix_mapping");
+    if (r != SOC_OK) return r;
+    M.intobs = { intobs[0], intobs[1], intobs[2] };
+    M.nside = nside;
+    CU(cudaEventRecord(c->ev0, c->stream));
+    launch_mapping(M, true, c->stream);
+    CU(cudaEventRecord(c->ev1, c->stream));
+    c->timed = true; c->launches++;
+    CU(cudaGetLastError());
+    return SOC_OK;
+}
+
+// ---- scattered light ------------------------------------------------------------------------------------------
+int soc_sca_zero_out(soc_context *c, int ndir, int npix_x, int npix_y) {
+    NEED_CTX(c);
+    if (ndir < 1 || npix_x < 1 || npix_y < 1) return fail(SOC_ERR_ARG, "soc_sca_zero_out: bad arguments");
+    return soc_clear(c, SOC_BUF_OUT, (size_t)ndir * npix_x * npix_y * 4);
+}
+
+static int sca_common(soc_context *c, ScaArgs &S, int kind, int batch, float seed, float abs, float sca, int ndir,
+                      int npix_x, int npix_y, float map_dx, const float centre[3], int global, const char *who) {
+    if (!c->have_grid || !c->have_params) return fail(SOC_ERR_STATE, "%s: grid and params first", who);
+    if (batch < 1 || global < 1 || ndir < 1 || npix_x < 1 || npix_y < 1 || centre == nullptr)
+        return fail(SOC_ERR_ARG, "%s: bad arguments (Healpix observers, NDIR<0, are not implemented)", who);
+    const soc_params &P = c->P;
+    if (kind == SIM_PS && P.ps_method != 0 && P.ps_method != 1)
+        return fail(SOC_ERR_UNSUPPORTED, "%s: PS_METHOD %d reads XPS_* through mistyped pointers in the reference (kernel_ASOC_sca.c:1486)", who, P.ps_method);
+    const size_t n = (size_t)c->G.cells * 4, nd = (size_t)ndir * 12;
+    int r;
+    if ((r = need(c, SOC_BUF_CSC, (size_t)P.bins * 4, who)) != SOC_OK) return r;
+    if ((r = need(c, SOC_BUF_DSC, (size_t)P.bins * 4, who)) != SOC_OK) return r;
+    if ((r = need(c, SOC_BUF_ODIR, nd, who)) != SOC_OK) return r;
+    if ((r = need(c, SOC_BUF_ORA, nd, who)) != SOC_OK) return r;
+    if ((r = need(c, SOC_BUF_ODE, nd, who)) != SOC_OK) return r;
+    if (P.with_abu && (r = need(c, SOC_BUF_OPT, 2 * n, who)) != SOC_OK) return r;
+    if ((r = ensure_zeroed(c, SOC_BUF_OUT, (size_t)ndir * npix_x * npix_y * 4)) != SOC_OK) return r;
+    memset(&S, 0, sizeof(S));
+    S.G = c->G;
+    S.out = dptr<float>(c, SOC_BUF_OUT);
+    S.opt = dptr<float>(c, SOC_BUF_OPT); S.dsc = dptr<float>(c, SOC_BUF_DSC); S.csc = dptr<float>(c, SOC_BUF_CSC);
+    S.pspos = dptr<float>(c, SOC_BUF_PSPOS); S.ps = dptr<float>(c, SOC_BUF_PS);
+    S.odir = dptr<float>(c, SOC_BUF_ODIR); S.ora = dptr<float>(c, SOC_BUF_ORA); S.ode = dptr<float>(c, SOC_BUF_ODE);
+    S.kabs = abs; S.ksca = sca; S.map_dx = map_dx;
+    S.centre = { centre[0], centre[1], centre[2] };
+    S.kind = kind; S.batch = batch; S.global = global; S.ndir = ndir; S.npx = npix_x; S.npy = npix_y;
+    S.bins = P.bins; S.no_ps = P.no_ps; S.ps_method = P.ps_method; S.with_abu = P.with_abu; S.ffs = P.ffs;
+    S.rank = c->rank; S.world = c->world;
+    long long ms = 100LL * ((long long)c->G.nx + c->G.ny + c->G.nz) << (c->G.levels - 1);
+    S.max_steps = (int)(ms > INT_MAX ? INT_MAX : ms);
+    S.counters = c->counters; S.work = c->counters + 5;
+    S.mwc.base_offset = seed_to_base(seed);
+    S.mwc.base_state = mwc_mulmod(MWC_BASEID, mwc_powmod(MWC_A, S.mwc.base_offset));
+    for (int k = 0; k < 26; k++) S.mwc.pow2k[k] = c->pow2k[k];
+    uint32_t sb; memcpy(&sb, &seed, 4);
+    S.phx.k0 = sb; S.phx.k1 = 0x534F4353u; S.phx.tag = (uint32_t)kind; S.phx.pad = 0;
+    return SOC_OK;
+}
+
+static int sca_launch(soc_context *c, ScaArgs &S, const char *who) {
+    const int threads = 128;
+    long long local = (S.nunits - S.rank + S.world - 1) / S.world;
+    int blocks;
+    if (c->rng_mode == SOC_RNG_REFERENCE) blocks = (int)((local + threads - 1) / threads);
+    else {
+        blocks = c->sms * sca_blocks_per_sm(c->G.levels > 1, c->G.dbl_sim != 0, threads);
+        long long needb = (local + threads - 1) / threads;
+        if (needb < blocks) blocks = (int)needb;
+        CU(cudaMemsetAsync(S.work, 0, sizeof(unsigned long long), c->stream));
+    }
+    if (blocks < 1) blocks = 1;
+    CU(cudaEventRecord(c->ev0, c->stream));
+    launch_sca(S, c->rng_mode, blocks, threads, c->stream);
+    CU(cudaEventRecord(c->ev1, c->stream));
+    c->timed = true; c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(SOC_ERR_CUDA, "%s: launch failed: %s", who, cudaGetErrorString(e));
+    return SOC_OK;
+}
+
+int soc_sca_ps(soc_context *c, int packets, int batch, float seed, float abs, float sca, int ndir, int npix_x, int npix_y,
+               float map_dx, const float centre[3], int global) {
+    NEED_CTX(c);
+    (void)packets;
+    ScaArgs S;
+    int r = sca_common(c, S, SIM_PS, batch, seed, abs, sca, ndir, npix_x, npix_y, map_dx, centre, global, "soc_sca_ps");
+    if (r != SOC_OK) return r;
+    const size_t nps = (size_t)c->P.no_ps;
+    if ((r = need(c, SOC_BUF_PSPOS, nps * 12, "soc_sca_ps")) != SOC_OK) return r;
+    if ((r = need(c, SOC_BUF_PS, nps * 4, "soc_sca_ps")) != SOC_OK) return r;
+    S.flavour = 0;
+    S.nunits = (c->rng_mode == SOC_RNG_REFERENCE) ? global : (long long)global * batch;
+    return sca_launch(c, S, "soc_sca_ps");
+}
+
+int soc_sca_pb(soc_context *c, int source, int packets, int batch, float seed, float abs, float sca, float bg, int ndir,
+               int npix_x, int npix_y, float map_dx, const float centre[3], int global) {
+    NEED_CTX(c);
+    (void)packets;
+    if (source != 0 && source != 1) return fail(SOC_ERR_UNSUPPORTED, "soc_sca_pb: SOURCE=%d", source);
+    ScaArgs S;
+    int r = sca_common(c, S, source == 0 ? SIM_PS : SIM_BG, batch, seed, abs, sca, ndir, npix_x, npix_y, map_dx, centre, global, "soc_sca_pb");
+    if (r != SOC_OK) return r;
+    if (source == 0) {
+        const size_t nps = (size_t)c->P.no_ps;
+        if ((r = need(c, SOC_BUF_PSPOS, nps * 12, "soc_sca_pb")) != SOC_OK) return r;
+        if ((r = need(c, SOC_BUF_PS, nps * 4, "soc_sca_pb")) != SOC_OK) return r;
+    }
+    S.bg = bg; S.flavour = 1;
+    long long items = (source == 1 && 8LL * c->G.area < global) ? 8LL * c->G.area : global;
+    S.nunits = (c->rng_mode == SOC_RNG_REFERENCE) ? global : items * batch;
+    return sca_launch(c, S, "soc_sca_pb");
+}
+
+int soc_get_counters(soc_context *c, soc_counters *out) {
+    NEED_CTX(c);
+    if (out == nullptr) return fail(SOC_ERR_ARG, "soc_get_counters: null");
+    unsigned long long h[8];
+    CU(cudaMemcpyAsync(h, c->counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    memset(out, 0, sizeof(*out));
+    out->packets = h[0]; out->steps = h[1]; out->scatterings = h[2]; out->peels = h[4];
+    out->launches = c->launches; out->reserved[0] = h[3];       // reserved[0] = packets killed by the step guard
+    return SOC_OK;
+}
+
+int soc_reset_counters(soc_context *c) {
+    NEED_CTX(c);
+    CU(cudaMemsetAsync(c->counters, 0, 8 * sizeof(unsigned long long), c->stream));
+    c->launches = 0;
+    return SOC_OK;
+}
+
+int soc_last_launch_ms(soc_context *c, float *ms) {
+    NEED_CTX(c);
+    if (ms == nullptr) return fail(SOC_ERR_ARG, "soc_last_launch_ms: null");
+    if (!c->timed) return fail(SOC_ERR_STATE, "soc_last_launch_ms: nothing launched yet");
+    CU(cudaEventSynchronize(c->ev1));
+    CU(cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return SOC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,66 @@
+// soc_b200 -- small grid-wide kernels around the packet kernels.
+//   Parents        kernel_ASOC_aux.c:688-718   PAR[child] = parent, from the links stored in DENS
+//   EqTemperature  kernel_ASOC_aux.c:745-787   absorbed energy -> equilibrium dust temperature via the E->T table
+//   Emission       kernel_ASOC_aux.c:793-807   modified black body emission of every cell at one frequency
+// All three stream through the cell arrays once (grid-stride, coalesced).
+#include "aux.cuh"
+
+namespace {
+
+__global__ void parents_kernel(GridDesc G, int *par, int level) {
+    const int n = G.lcells[level];
+    for (int ipar = blockIdx.x * blockDim.x + threadIdx.x; ipar < n; ipar += gridDim.x * blockDim.x) {
+        float link = G.dens[G.off[level] + ipar];
+        if (link < 1.0e-10f) {
+            int first = link_index(link);
+            int *dst = par + (G.off[level + 1] - G.nxyz + first);
+            #pragma unroll
+            for (int i = 0; i < 8; i++) dst[i] = ipar;
+        }
+    }
+}
+
+__global__ void eq_temperature_kernel(GridDesc G, int level, float adhoc, float kE, float Emin, int NE, float factor,
+                                      float length, const float *__restrict__ ttt, const float *__restrict__ emit,
+                                      float *__restrict__ tnew) {
+    const float scale = (6.62607e-27f * factor) / length;
+    const float oplgkE = 1.0f / log10f(kE);
+    const float l8 = powf(8.0f, (float)level);
+    const int n = G.lcells[level];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int ind = G.off[level] + i;
+        float rho = G.dens[ind];
+        float Ein = (scale / adhoc) * emit[ind] * l8 / rho;
+        int iE = clampi((int)floorf(oplgkE * log10f(Ein / Emin)), 0, NE - 2);
+        float wi = (Emin * powf(kE, (float)(iE + 1)) - Ein) / (Emin * powf(kE, (float)iE) * (kE - 1.0f));
+        tnew[ind] = (rho > 1.0e-7f) ? clampf(wi * ttt[iE] + (1.0f - wi) * ttt[iE + 1], 3.0f, 1600.0f) : 10.0f;
+    }
+}
+
+__global__ void emission_kernel(int cells, float freq, float fabs_, float factor, float length,
+                                const float *__restrict__ t, float *__restrict__ emit) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += gridDim.x * blockDim.x)
+        emit[i] = (2.79639459e-20f * factor) * fabs_ * (freq * freq / (expf(4.7995074e-11f * freq / t[i]) - 1.0f)) / length;
+}
+
+inline int grid_for(long long n, int threads) {
+    long long b = (n + threads - 1) / threads;
+    const long long cap = 148LL * 16;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+void launch_parents(const GridDesc &G, int *par, cudaStream_t stream) {
+    for (int level = 0; level < G.levels - 1; level++)
+        parents_kernel<<<grid_for(G.lcells[level], 256), 256, 0, stream>>>(G, par, level);
+}
+void launch_eq_temperature(const GridDesc &G, int level, float adhoc, float kE, float Emin, int NE, float factor,
+                           float length, const float *ttt, const float *emit, float *tnew, cudaStream_t stream) {
+    eq_temperature_kernel<<<grid_for(G.lcells[level], 256), 256, 0, stream>>>(G, level, adhoc, kE, Emin, NE, factor,
+                                                                             length, ttt, emit, tnew);
+}
+void launch_emission(int cells, float freq, float fabs_, float factor, float length, const float *t, float *emit,
+                     cudaStream_t stream) {
+    emission_kernel<<<grid_for(cells, 256), 256, 0, stream>>>(cells, freq, fabs_, factor, length, t, emit);
+}

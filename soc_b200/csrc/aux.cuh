@@ -1,0 +1,9 @@
+// soc_b200 -- small grid-wide kernels: parent table, equilibrium temperature, emission.
+#pragma once
+#include "common.cuh"
+
+void launch_parents(const GridDesc &G, int *par, cudaStream_t stream);
+void launch_eq_temperature(const GridDesc &G, int level, float adhoc, float kE, float Emin, int NE, float factor,
+                           float length, const float *ttt, const float *emit, float *tnew, cudaStream_t stream);
+void launch_emission(int cells, float freq, float fabs_, float factor, float length, const float *t, float *emit,
+                     cudaStream_t stream);

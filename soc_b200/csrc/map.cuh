@@ -1,0 +1,15 @@
+// soc_b200 -- arguments of the map ray-tracer kernels.
+#pragma once
+#include "common.cuh"
+
+struct MapArgs {
+    GridDesc G;
+    float *map, *savetau;                                  // [npy*npx] or [12*nside^2]
+    const float *__restrict__ emit, *__restrict__ opt;     // [cells], [2*cells]
+    vec3 dir, ra, de, centre, intobs;
+    float map_dx, kabs, ksca, length;
+    int npx, npy, nside, with_abu, level_threshold, save_colden;
+    unsigned long long *counters;
+};
+
+void launch_mapping(const MapArgs &M, bool healpix, cudaStream_t stream);

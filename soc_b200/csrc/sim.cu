@@ -1,0 +1,434 @@
+// soc_b200 -- Monte Carlo photon-packet kernels of the emission / absorption run.
+//
+// Replaces the reference kernels SimRAM_PB (point sources + isotropic background), SimRAM_HP (Healpix
+// background) and SimRAM_CL (emission from the cells): kernel_ASOC.c:15-824, 831-1206, 1223-1684.
+//
+// Two launch layouts share every line of the physics:
+//   * item kernel   (SOC_RNG_REFERENCE): one thread = one work item of the reference launch, seeded with the
+//     reference's MWC64X stream for that work item and drawing random numbers in the reference's order.  With
+//     the same inputs the absorption counters agree with the CPU oracle to float rounding -- this is the
+//     parity layout.
+//   * stream kernel (SOC_RNG_PACKET): persistent warps; one Philox stream per photon packet keyed by the
+//     global packet number, idle lanes are refilled from a global work counter so that warps stay full, and
+//     packet q is simulated by rank q % world -- results do not depend on the number of GPUs except for the
+//     order of the float additions.  This is the production layout.
+//
+// Per cell-step the kernels touch DENS[cell] (4 B gather, carried in a register from the step that entered
+// the cell) and TABS[cell] (+INT[cell]) through red.global.add.f32; nothing else leaves the SM.
+#include "sim.cuh"
+#include "emit.cuh"
+
+#define FULL 0xffffffffu
+
+namespace {
+
+struct Counters { unsigned long long packets, steps, scat, stuck; };
+
+// ---- accumulation ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add(float *p, float v) { atomicAdd(p, v); }   // result unused -> RED.E.ADD.F32
+
+// Sum `v` over the lanes in `peers` (all of which call this with the same set); returns the total on the
+// lowest lane of the set.  log2(|peers|) shuffle rounds.
+__device__ __forceinline__ float reduce_peers(unsigned peers, float v, int lane) {
+    int rel = __popc(peers & ((1u << lane) - 1u));            // my position within the set
+    unsigned higher = peers & (0xfffffffeu << lane);
+    while (__any_sync(peers, higher != 0u)) {
+        int next = __ffs(higher);
+        float t = __shfl_sync(peers, v, (next - 1) & 31);
+        if (next) v += t;
+        bool done = rel & 1;
+        higher &= __ballot_sync(peers, !done);
+        rel >>= 1;
+    }
+    return v;
+}
+
+struct Deposit {
+    const SimArgs &A;
+    float *tile;        // shared-memory tile or nullptr
+    __device__ __forceinline__ Deposit(const SimArgs &a, float *t) : A(a), tile(t) {}
+
+    __device__ __forceinline__ void one(int oind, float delta, const vec3 &dir, int eidx, int level, int ind) const {
+        if (A.with_ali && oind == eidx) red_add(&A.xab[oind], delta * A.tw);                 // kernel_ASOC.c:1486-1494
+        else {
+            float v = delta * A.tw * A.adhoc;
+            bool in_tile = false;
+            if (tile != nullptr && level == 0 && (unsigned)(ind - A.tile_lo) < (unsigned)A.tile_span) {
+                int ix = ind % A.G.nx, iy = (ind / A.G.nx) % A.G.ny, iz = ind / (A.G.nx * A.G.ny);
+                unsigned tx = (unsigned)(ix - A.tile_x0), ty = (unsigned)(iy - A.tile_y0), tz = (unsigned)(iz - A.tile_z0);
+                if (tx < SOC_TILE_N && ty < SOC_TILE_N && tz < SOC_TILE_N) {
+                    atomicAdd(&tile[(tz * SOC_TILE_N + ty) * SOC_TILE_N + tx], v);
+                    in_tile = true;
+                }
+            }
+            if (!in_tile) red_add(&A.tabs[oind], v);
+        }
+        if (A.use_int) red_add(&A.inten[oind], delta);
+        if (A.save_int2) {
+            red_add(&A.intx[oind], delta * dir.x); red_add(&A.inty[oind], delta * dir.y); red_add(&A.intz[oind], delta * dir.z);
+        }
+    }
+
+    // Called by every lane of the warp; `dep` says whether this lane has something to add.
+    __device__ __forceinline__ void all(bool dep, int oind, float delta, const vec3 &dir, int eidx, int level, int ind,
+                                        bool aggregate) const {
+        if (!aggregate || A.save_int2 || A.with_ali) {
+            if (dep) one(oind, delta, dir, eidx, level, ind);
+            return;
+        }
+        unsigned act = __ballot_sync(FULL, dep);
+        if (!dep) return;
+        int lane = threadIdx.x & 31;
+        unsigned peers = __match_any_sync(act, oind);
+        if (peers != (1u << lane)) {
+            delta = reduce_peers(peers, delta, lane);
+            if (lane != __ffs(peers) - 1) return;
+        }
+        one(oind, delta, dir, eidx, level, ind);
+    }
+};
+
+// ---- sampling --------------------------------------------------------------------------------------------
+// free path incl. the optional step weighting, kernel_ASOC.c:516-541
+template <class RNG>
+__device__ __forceinline__ float sample_free_path(const SimArgs &A, RNG &rng, float &photons) {
+    float fp;
+    if (A.step_weight <= 0) fp = -logf(rng.uniform());
+    else if (A.step_weight == 1) {
+        fp = -logf(rng.uniform()) / A.sw_a;
+        photons *= expf(A.sw_a * fp - fp) / A.sw_a;
+    } else {
+        float a = A.sw_a, b = A.sw_b;
+        fp = -logf((-b + sqrtf(b * b + 4.0f * rng.uniform() * (1.0f - b))) / (2.0f - 2.0f * b)) / a;
+        photons *= 1.0f / (a * b * expf((1.0f - a) * fp) + 2.0f * a * (1.0f - b) * expf((1.0f - 2.0f * a) * fp));
+    }
+    return fp;
+}
+
+// ---- emission: Healpix background (kernel_ASOC.c:885-947) ---------------------------------------------------
+template <class RNG, bool OCT>
+__device__ void emit_hp(const SimArgs &A, RNG &rng, Packet &pk) {
+    const GridDesc &G = A.G;
+    const float NX = (float)G.nx, NY = (float)G.ny, NZ = (float)G.nz;
+    int ipix;
+    if (A.hpbg_weighted < 1) {
+        ipix = clampi((int)floorf(rng.uniform() * 49152), 0, 49151);
+    } else {
+        float x = rng.uniform();
+        int lo = 0, hi = 49151;
+        for (int i = 0; i < 10; i++) {
+            ipix = (lo + hi) / 2;
+            if (A.hpbgp[ipix] > x) hi = ipix; else lo = ipix;
+        }
+        for (ipix = lo; ipix <= hi; ipix++) if (A.hpbgp[ipix] >= x) break;
+    }
+    pk.photons = A.hpbg[ipix];
+    float phi, theta, st, ct, sp, cp;
+    pix2ang_ring(64, ipix, phi, theta, SOC_PI);
+    sincosf(theta, &st, &ct); sincosf(phi, &sp, &cp);
+    pk.dir.x = st * cp; pk.dir.y = st * sp; pk.dir.z = -ct;
+    fix_direction(pk.dir);
+    float x = fabsf(pk.dir.x), y = fabsf(pk.dir.y), z = fabsf(pk.dir.z);
+    float ds = xadd(xadd(x, y), z);
+    x = xdiv(x, ds); y = xdiv(y, ds); z = xdiv(z, ds);
+    ds = rng.uniform();
+    float v1 = rng.uniform(), v2 = rng.uniform();
+    if (ds < x)                { pk.pos.y = v1 * NY; pk.pos.z = v2 * NZ; pk.pos.x = (pk.dir.x > 0.0f) ? SOC_PEPS : (NX - SOC_PEPS); }
+    else if (ds < xadd(x, y))  { pk.pos.x = v1 * NX; pk.pos.z = v2 * NZ; pk.pos.y = (pk.dir.y > 0.0f) ? SOC_PEPS : (NY - SOC_PEPS); }
+    else                       { pk.pos.x = v1 * NX; pk.pos.y = v2 * NY; pk.pos.z = (pk.dir.z > 0.0f) ? SOC_PEPS : (NZ - SOC_PEPS); }
+    locate<OCT>(G, pk);
+}
+
+// ---- emission: one ray from cell `icell` (kernel_ASOC.c:1323-1393) ------------------------------------------
+template <class RNG>
+__device__ void emit_cl(const SimArgs &A, RNG &rng, int icell, float pwei, Packet &pk) {
+    const GridDesc &G = A.G;
+    int ind = icell, level;
+    for (level = 0; level < G.levels - 1; level++) {
+        ind -= G.lcells[level];
+        if (ind < 0) { ind += G.lcells[level]; break; }
+    }
+    float X0, Y0, Z0;
+    if (level == 0) { X0 = ind % G.nx; Y0 = (ind / G.nx) % G.ny; Z0 = ind / (G.nx * G.ny); }
+    else { int sid = ind & 7; X0 = sid & 1; Y0 = (sid >> 1) & 1; Z0 = sid >> 2; }
+    pk.photons = A.emit[icell] * pwei;
+    pk.pos.x = xadd(X0, rng.uniform()); pk.pos.y = xadd(Y0, rng.uniform()); pk.pos.z = xadd(Z0, rng.uniform());
+    isotropic(rng, pk.dir);
+    pk.level = level; pk.ind = ind; pk.rho = G.dens[icell];
+    pk.eidx = A.with_ali ? icell : -1;
+}
+
+// Packets-per-cell rule of SimRAM_CL (kernel_ASOC.c:1293-1316).  Returns the number of rays (0 = skip the cell).
+__device__ __forceinline__ int cl_rays(const SimArgs &A, int icell, float &pwei) {
+    if (A.use_emweight > 0) {
+        pwei = A.emwei[icell];
+        if (pwei < 1e-10f || A.G.dens[icell] <= 0.0f) return 0;
+        int batch = (int)floorf(pwei);
+        if (batch < 1) { batch = 1; pwei = (float)(1.0 / (double)(pwei + 1.0e-30f)); }
+        else           { pwei = (float)(1.0 / (double)((float)batch + 1.0e-9f)); }
+        return batch;
+    }
+    pwei = 1.0f / ((float)A.batch + 1.0e-9f);
+    return A.batch;
+}
+
+template <class RNG>
+__device__ __forceinline__ void start_packet(const SimArgs &A, RNG &rng, Packet &pk, bool fixdir) {
+    if (fixdir) fix_direction(pk.dir);
+    pk.free_path = sample_free_path(A, rng, pk.photons);
+    pk.tau = 0.0f; pk.scat = 0; pk.nstep = 0;
+}
+
+// ---- one cell-step of the propagation loop (kernel_ASOC.c:556-820 / 1448-1679) -------------------------------
+// Part 1: geometry + optical depths; decides between a full step and a scattering inside the cell and
+// returns the energy to deposit.  Part 2 (finish_step) updates the packet.  The deposit sits between the
+// two so that the whole warp reaches it together.
+struct StepTmp { vec3 pos0; float rho0, tauA, dx; int ind0, level0, oind; bool scatter; };
+
+template <bool CL, bool OCT, bool DBL>
+__device__ __forceinline__ bool begin_step(const SimArgs &A, Packet &pk, StepTmp &t, float &delta, Counters &cnt) {
+    const GridDesc &G = A.G;
+    t.oind = OCT ? G.off[pk.level] + pk.ind : pk.ind;
+    t.ind0 = pk.ind; t.level0 = pk.level; t.pos0 = pk.pos; t.rho0 = pk.rho;
+    float ds = get_step<OCT, DBL, false>(G, pk.pos, pk.dir, pk.level, pk.ind, pk.rho);
+    float kabs = A.kabs, ksca = A.ksca;
+    if (A.with_abu) { float2 o = reinterpret_cast<const float2 *>(A.opt)[t.oind]; kabs = o.x; ksca = o.y; }
+    t.tauA = ds * t.rho0 * kabs;
+    float dtau = ds * t.rho0 * ksca;
+    t.scatter = pk.free_path < (pk.tau + dtau);
+    if (t.scatter) {
+        pk.scat++;
+        if (CL && pk.scat > 20) return false;                      // kernel_ASOC.c:1552-1556: dies before the deposit
+        dtau = pk.free_path - pk.tau;
+        t.dx = dtau / (ksca * t.rho0);
+        t.tauA = t.dx * t.rho0 * kabs;
+        cnt.scat++;
+    } else {
+        pk.tau += dtau;
+    }
+    delta = (t.tauA > SOC_TAULIM) ? (pk.photons * (1.0f - expf(-t.tauA))) : (pk.photons * t.tauA * (1.0f - 0.5f * t.tauA));
+    cnt.steps++;
+    return true;
+}
+
+template <class RNG, bool CL, bool OCT>
+__device__ __forceinline__ bool finish_step(const SimArgs &A, Packet &pk, const StepTmp &t, RNG &rng) {
+    pk.photons *= expf(-t.tauA);
+    if (t.scatter) {
+        float dx = OCT ? ldexpf(t.dx, t.level0) : t.dx;
+        dx = fmaxf(0.0f, dx - 2.0f * SOC_PEPS);
+        pk.pos.x = xadd(t.pos0.x, xmul(dx, pk.dir.x)); pk.pos.y = xadd(t.pos0.y, xmul(dx, pk.dir.y)); pk.pos.z = xadd(t.pos0.z, xmul(dx, pk.dir.z));
+        pk.free_path = sample_free_path(A, rng, pk.photons);
+        pk.ind = t.ind0; pk.level = t.level0; pk.rho = t.rho0;
+        scatter_direction(pk.dir, A.csc, A.bins, rng);
+        pk.tau = 0.0f;
+        if (!CL && pk.scat > 20) return false;                     // kernel_ASOC.c:801-804
+        return true;
+    }
+    if (!CL && pk.level == t.level0 && pk.ind == t.ind0) {         // failed step: kernel_ASOC.c:649-665
+        pk.pos.x = xadd(pk.pos.x, xmul(SOC_PEPS, pk.dir.x)); pk.pos.y = xadd(pk.pos.y, xmul(SOC_PEPS, pk.dir.y)); pk.pos.z = xadd(pk.pos.z, xmul(SOC_PEPS, pk.dir.z));
+    }
+    return pk.ind >= 0;
+}
+
+__device__ __forceinline__ void flush_counters(const SimArgs &A, const Counters &c) {
+    warp_add_counter(A.counters + 0, c.packets);
+    warp_add_counter(A.counters + 1, c.steps);
+    warp_add_counter(A.counters + 2, c.scat);
+    warp_add_counter(A.counters + 3, c.stuck);
+}
+
+__device__ __forceinline__ float *tile_begin(const SimArgs &A, float *smem) {
+    if (A.deposit != DEP_TILE) return nullptr;
+    for (int i = threadIdx.x; i < SOC_TILE_CELLS; i += blockDim.x) smem[i] = 0.0f;
+    __syncthreads();
+    return smem;
+}
+__device__ __forceinline__ void tile_end(const SimArgs &A, float *tile) {
+    if (tile == nullptr) return;
+    __syncthreads();
+    const GridDesc &G = A.G;
+    for (int i = threadIdx.x; i < SOC_TILE_CELLS; i += blockDim.x) {
+        float v = tile[i];
+        if (v != 0.0f) {
+            int tx = i % SOC_TILE_N, ty = (i / SOC_TILE_N) % SOC_TILE_N, tz = i / (SOC_TILE_N * SOC_TILE_N);
+            int ix = A.tile_x0 + tx, iy = A.tile_y0 + ty, iz = A.tile_z0 + tz;
+            if (ix < G.nx && iy < G.ny && iz < G.nz) red_add(&A.tabs[(iz * G.ny + iy) * G.nx + ix], v);
+        }
+    }
+}
+
+// =================================================================================================================
+// Item kernel: thread <-> reference work item.
+// =================================================================================================================
+template <class RNG, bool OCT, bool DBL>
+__global__ void __launch_bounds__(128) sim_item_kernel(const __grid_constant__ SimArgs A) {
+    __shared__ float smem[SOC_TILE_CELLS];
+    float *tile = tile_begin(A, smem);
+    Deposit dep(A, OCT ? nullptr : tile);
+    Counters cnt = { 0, 0, 0, 0 };
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long id = t * A.world + A.rank;
+    bool have = id < A.nunits;
+    if (A.kind == SIM_BG || A.kind == SIM_HP) have = have && id < 8LL * A.G.area;      // kernel_ASOC.c:96, 878
+    if (A.kind == SIM_CL) have = have && id < A.G.cells;
+    RNG rng;
+    if (have) rng.seed_item(A, (unsigned long long)id);
+    Packet pk; pk.ind = -1; pk.level = 0; pk.eidx = -1; pk.rho = 0.0f;
+    bool alive = false;
+    int III = 0, icell = (int)id - A.global, nray = 0;        // CL: icell advances by `global` per cell
+    float pwei = 1.0f;
+    const bool agg = A.deposit != DEP_RED;
+    for (;;) {
+        if (!alive && have) {
+            // next packet of this work item
+            if (A.kind == SIM_CL) {
+                while (III >= nray) {
+                    long long nc = (long long)icell + A.global;
+                    if (nc >= A.G.cells) { have = false; break; }
+                    icell = (int)nc; III = 0;
+                    nray = cl_rays(A, icell, pwei);
+                }
+                if (have) {
+                    III++;
+                    emit_cl(A, rng, icell, pwei, pk);
+                    start_packet(A, rng, pk, true);
+                    cnt.packets++; alive = true;
+                }
+            } else if (III < A.batch) {
+                if (A.kind == SIM_PS)      emit_ps<SimArgs, RNG, OCT>(A, rng, III, pk);
+                else if (A.kind == SIM_BG) emit_bg<SimArgs, RNG, OCT>(A, rng, (int)id, pk);
+                else                       emit_hp<RNG, OCT>(A, rng, pk);
+                start_packet(A, rng, pk, A.kind != SIM_HP);
+                III++; cnt.packets++;
+                alive = pk.ind >= 0;
+            } else have = false;
+        }
+        if (!__any_sync(FULL, alive || have)) break;
+        StepTmp st; float delta = 0.0f; bool d = false;
+        if (alive) {
+            if (A.kind == SIM_CL) d = begin_step<true, OCT, DBL>(A, pk, st, delta, cnt);
+            else                  d = begin_step<false, OCT, DBL>(A, pk, st, delta, cnt);
+            if (!d) alive = false;
+        }
+        dep.all(d, st.oind, delta, pk.dir, pk.eidx, st.level0, st.ind0, agg);
+        if (alive) {
+            if (A.kind == SIM_CL) alive = finish_step<RNG, true, OCT>(A, pk, st, rng);
+            else                  alive = finish_step<RNG, false, OCT>(A, pk, st, rng);
+            if (++pk.nstep > A.max_steps) { alive = false; cnt.stuck++; }
+        }
+    }
+    tile_end(A, tile);
+    flush_counters(A, cnt);
+}
+
+// =================================================================================================================
+// Stream kernel: persistent warps, one Philox stream per packet, idle lanes refilled from a work counter.
+// Units: PS/BG/HP one packet; CL one cell (all its rays on one lane, ray number in the Philox counter).
+// =================================================================================================================
+template <bool OCT, bool DBL>
+__global__ void __launch_bounds__(256) sim_stream_kernel(const __grid_constant__ SimArgs A) {
+    __shared__ float smem[SOC_TILE_CELLS];
+    float *tile = tile_begin(A, smem);
+    Deposit dep(A, OCT ? nullptr : tile);
+    Counters cnt = { 0, 0, 0, 0 };
+    const int lane = threadIdx.x & 31;
+    const long long nlocal = (A.nunits - A.rank + A.world - 1) / A.world;
+    RngPhilox rng;
+    Packet pk; pk.ind = -1; pk.level = 0; pk.eidx = -1; pk.rho = 0.0f;
+    bool alive = false, more = true;
+    int icell = 0, iray = 0, nray = 0;
+    float pwei = 1.0f;
+    const bool agg = A.deposit != DEP_RED;
+    const int refill = A.refill;
+    for (;;) {
+        unsigned idle = __ballot_sync(FULL, !alive);
+        if (idle == FULL || (__popc(idle) >= refill && __any_sync(FULL, more))) {
+            // hand new units to the lanes that need one
+            bool need = !alive && more && iray >= nray;
+            unsigned nm = __ballot_sync(FULL, need);
+            if (nm) {
+                int leader = __ffs(nm) - 1;
+                unsigned long long base = 0;
+                if (lane == leader) base = atomicAdd(A.work, (unsigned long long)__popc(nm));
+                base = __shfl_sync(FULL, base, leader);
+                if (need) {
+                    long long u = (long long)base + __popc(nm & ((1u << lane) - 1u));
+                    if (u >= nlocal) more = false;
+                    else {
+                        unsigned long long q = (unsigned long long)u * A.world + A.rank;
+                        if (A.kind == SIM_CL) {
+                            icell = (int)q; iray = 0;
+                            nray = cl_rays(A, icell, pwei);
+                        } else {
+                            rng.seed(A.phx, q);
+                            int id = (int)(q / (unsigned)A.batch), III = (int)(q % (unsigned)A.batch);
+                            if (A.kind == SIM_PS)      emit_ps<SimArgs, RngPhilox, OCT>(A, rng, III, pk);
+                            else if (A.kind == SIM_BG) emit_bg<SimArgs, RngPhilox, OCT>(A, rng, id, pk);
+                            else                       emit_hp<RngPhilox, OCT>(A, rng, pk);
+                            start_packet(A, rng, pk, A.kind != SIM_HP);
+                            cnt.packets++;
+                            alive = pk.ind >= 0;
+                        }
+                    }
+                }
+            }
+            if (A.kind == SIM_CL && !alive && iray < nray) {
+                rng.seed(A.phx, (unsigned long long)(unsigned)icell | ((unsigned long long)(unsigned)iray << 32));
+                iray++;
+                emit_cl(A, rng, icell, pwei, pk);
+                start_packet(A, rng, pk, true);
+                cnt.packets++; alive = true;
+            }
+            if (!__any_sync(FULL, alive || more || iray < nray)) break;
+        }
+        StepTmp st; float delta = 0.0f; bool d = false;
+        if (alive) {
+            if (A.kind == SIM_CL) d = begin_step<true, OCT, DBL>(A, pk, st, delta, cnt);
+            else                  d = begin_step<false, OCT, DBL>(A, pk, st, delta, cnt);
+            if (!d) alive = false;
+        }
+        dep.all(d, st.oind, delta, pk.dir, pk.eidx, st.level0, st.ind0, agg && __any_sync(FULL, d && pk.nstep < A.agg_steps));
+        if (alive) {
+            if (A.kind == SIM_CL) alive = finish_step<RngPhilox, true, OCT>(A, pk, st, rng);
+            else                  alive = finish_step<RngPhilox, false, OCT>(A, pk, st, rng);
+            if (++pk.nstep > A.max_steps) { alive = false; cnt.stuck++; }
+        }
+    }
+    tile_end(A, tile);
+    flush_counters(A, cnt);
+}
+
+// MWC64X work-item stream with the item-kernel interface
+struct RngMwcItem : RngMwc {
+    __device__ __forceinline__ void seed_item(const SimArgs &A, unsigned long long id) { seed(A.mwc, id); }
+};
+
+}  // namespace
+
+void launch_sim(const SimArgs &A, int rng_mode, int blocks, int threads, cudaStream_t stream) {
+    const bool oct = A.G.levels > 1, dbl = A.G.dbl_sim != 0;
+    if (rng_mode == SOC_RNG_REFERENCE) {
+        if (!oct)      sim_item_kernel<RngMwcItem, false, false><<<blocks, threads, 0, stream>>>(A);
+        else if (!dbl) sim_item_kernel<RngMwcItem, true, false><<<blocks, threads, 0, stream>>>(A);
+        else           sim_item_kernel<RngMwcItem, true, true><<<blocks, threads, 0, stream>>>(A);
+    } else {
+        if (!oct)      sim_stream_kernel<false, false><<<blocks, threads, 0, stream>>>(A);
+        else if (!dbl) sim_stream_kernel<true, false><<<blocks, threads, 0, stream>>>(A);
+        else           sim_stream_kernel<true, true><<<blocks, threads, 0, stream>>>(A);
+    }
+}
+
+int sim_blocks_per_sm(int rng_mode, bool octree, bool dbl, int threads) {
+    int n = 0;
+    if (rng_mode == SOC_RNG_REFERENCE) {
+        if (!octree)   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sim_item_kernel<RngMwcItem, false, false>, threads, 0);
+        else if (!dbl) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sim_item_kernel<RngMwcItem, true, false>, threads, 0);
+        else           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sim_item_kernel<RngMwcItem, true, true>, threads, 0);
+    } else {
+        if (!octree)   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sim_stream_kernel<false, false>, threads, 0);
+        else if (!dbl) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sim_stream_kernel<true, false>, threads, 0);
+        else           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sim_stream_kernel<true, true>, threads, 0);
+    }
+    return n > 0 ? n : 1;
+}

@@ -1,0 +1,45 @@
+// soc_b200 -- arguments of the Monte Carlo packet kernels (emission / absorption run).
+#pragma once
+#include "common.cuh"
+
+enum SimKind { SIM_PS = 0, SIM_BG = 1, SIM_HP = 2, SIM_CL = 3 };
+
+// accumulation engine of the absorption counters (north-star item b)
+enum DepositMode {
+    DEP_RED = 0,        // one red.global.add.f32 per lane and step
+    DEP_WARP = 1,       // lanes of a warp that hit the same cell are combined first (__match_any_sync)
+    DEP_TILE = 2        // DEP_WARP + a shared-memory tile of cells around the (first) point source
+};
+
+#define SOC_TILE_N 16                    // shared-memory tile edge (cells); SOC_TILE_N^3 floats = 16 KiB
+#define SOC_TILE_CELLS (SOC_TILE_N * SOC_TILE_N * SOC_TILE_N)
+
+struct SimArgs {
+    GridDesc G;
+    // accumulators [cells]
+    float *tabs, *xab, *inten, *intx, *inty, *intz;
+    // inputs
+    const float *__restrict__ emit, *__restrict__ emwei, *__restrict__ opt;
+    const float *__restrict__ dsc, *__restrict__ csc;
+    const float *__restrict__ pspos, *__restrict__ ps, *__restrict__ xps_area;
+    const int *__restrict__ xps_nside, *__restrict__ xps_side;
+    const float *__restrict__ hpbg, *__restrict__ hpbgp;
+    float kabs, ksca, bg, tw, adhoc, sw_a, sw_b;
+    int kind, batch, global;
+    int bins, no_ps, ps_method, with_abu, with_ali, use_int, save_int2, use_emweight, hpbg_weighted, step_weight;
+    long long nunits;            // work units: reference work items (RNG mode 0) or packets / cells (mode 1)
+    int rank, world;
+    int max_steps;               // guard against packets that never leave (counted as stuck)
+    int deposit;                 // DepositMode
+    int refill;                  // stream kernel: refill a warp when at least this many lanes are idle
+    int agg_steps;               // stream kernel: combine lanes only while a packet is younger than this
+    int tile_x0, tile_y0, tile_z0;   // DEP_TILE: root-grid origin of the shared-memory tile
+    int tile_lo, tile_span;          // first root-cell index of the tile's z-slab and the slab's length
+    unsigned long long *counters;   // packets, steps, scatterings, stuck
+    unsigned long long *work;       // stream kernel: next unit to hand out
+    MwcLaunch mwc;
+    PhiloxLaunch phx;
+};
+
+void launch_sim(const SimArgs &A, int rng_mode, int blocks, int threads, cudaStream_t stream);
+int  sim_blocks_per_sm(int rng_mode, bool octree, bool dbl, int threads);
