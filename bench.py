@@ -340,7 +340,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--deposit", type=int, default=0)
+    ap.add_argument("--deposit", type=int, default=2)
     ap.add_argument("--refill", type=int, default=8)
     ap.add_argument("--agg-steps", type=int, default=24)
     ap.add_argument("--kernel-times", action="store_true")

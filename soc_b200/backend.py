@@ -158,7 +158,7 @@ class Device:
     def set_shard(self, rank, world):
         self._ck(self.L.soc_set_shard(self.ctx, int(rank), int(world)))
 
-    def set_tuning(self, deposit=DEP_RED, refill=8, aggregate_steps=24):
+    def set_tuning(self, deposit=DEP_TILE, refill=8, aggregate_steps=24):
         self._ck(self.L.soc_set_tuning(self.ctx, int(deposit), int(refill), int(aggregate_steps)))
 
     def upload(self, buf, array, dtype=np.float32):

@@ -39,6 +39,7 @@ struct soc_context {
     bool timed;
     DevBuf buf[SOC_BUF_COUNT];
     unsigned long long *counters;      // device: packets, steps, scatterings, stuck, peels, work, -, -
+    float *acc; size_t acc_bytes;      // per-launch scratch accumulator of the stream kernels (all zero between launches)
     unsigned long long launches;
     soc_params P;
     bool have_params, have_grid;
@@ -98,7 +99,7 @@ int soc_create(int device_ordinal, soc_context **out) {
     memset(c, 0, sizeof(*c));
     c->device = device_ordinal; c->sms = prop.multiProcessorCount;
     c->rng_mode = SOC_RNG_PACKET; c->rank = 0; c->world = 1;
-    c->deposit = DEP_RED; c->refill = 8; c->agg_steps = 24;
+    c->deposit = DEP_TILE; c->refill = 8; c->agg_steps = 24;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
@@ -116,6 +117,7 @@ int soc_destroy(soc_context *c) {
     cudaStreamSynchronize(c->stream);
     for (int b = 0; b < SOC_BUF_COUNT; b++) if (c->buf[b].ptr) cudaFree(c->buf[b].ptr);
     cudaFree(c->counters);
+    if (c->acc) cudaFree(c->acc);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -332,8 +334,19 @@ static int sim_launch(soc_context *c, SimArgs &A, const char *who) {
         if (needb < blocks) blocks = (int)(needb < 1 ? 1 : needb);
         CU(cudaMemsetAsync(A.work, 0, sizeof(unsigned long long), c->stream));
     }
+    if (c->rng_mode != SOC_RNG_REFERENCE) {
+        const size_t n = (size_t)A.G.cells * 4;
+        if (c->acc == nullptr || c->acc_bytes != n) {
+            if (c->acc) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->acc)); c->acc = nullptr; }
+            CU(cudaMalloc(&c->acc, n));
+            c->acc_bytes = n;
+            CU(cudaMemsetAsync(c->acc, 0, n, c->stream));
+        }
+        A.acc = c->acc; A.use_acc = 1;
+    }
     CU(cudaEventRecord(c->ev0, c->stream));
     launch_sim(A, c->rng_mode, blocks, threads, c->stream);
+    if (A.use_acc) { launch_fold_acc(A, c->stream); c->launches++; }
     CU(cudaEventRecord(c->ev1, c->stream));
     c->timed = true;
     c->launches++;

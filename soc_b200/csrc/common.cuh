@@ -126,6 +126,19 @@ struct RngMwc {
 
 // Philox4x32-10 (Salmon et al. 2011): counter = (packet lo, packet hi, draw block, stream tag), key from the seed.
 struct PhiloxLaunch { uint32_t k0, k1, tag, pad; };
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t a, uint32_t b,
+                                              uint32_t &o0, uint32_t &o1, uint32_t &o2, uint32_t &o3) {
+    #pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ a; c1 = lo1; c2 = hi0 ^ c3 ^ b; c3 = lo0;
+        a += 0x9E3779B9u; b += 0xBB67AE85u;
+    }
+    o0 = c0; o1 = c1; o2 = c2; o3 = c3;
+}
+// uint32 -> [0,1] like Rand() of the reference (kernel_ASOC_aux.c:127)
+__device__ __forceinline__ float u32_to_unit(uint32_t v) { return __uint2float_rn(v) * 2.3283064365386963e-10f; }
 struct RngPhilox {
     uint32_t p0, p1, blk, tag, k0, k1;
     uint32_t buf0, buf1, buf2, buf3;
@@ -134,15 +147,8 @@ struct RngPhilox {
         p0 = (uint32_t)id; p1 = (uint32_t)(id >> 32); blk = 0; tag = L.tag; k0 = L.k0; k1 = L.k1; have = 0;
     }
     __device__ __forceinline__ void refill() {
-        uint32_t c0 = p0, c1 = p1, c2 = blk, c3 = tag, a = k0, b = k1;
-        #pragma unroll
-        for (int r = 0; r < 10; r++) {
-            uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-            uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-            c0 = hi1 ^ c1 ^ a; c1 = lo1; c2 = hi0 ^ c3 ^ b; c3 = lo0;
-            a += 0x9E3779B9u; b += 0xBB67AE85u;
-        }
-        buf0 = c0; buf1 = c1; buf2 = c2; buf3 = c3; blk++; have = 4;
+        philox4x32_10(p0, p1, blk, tag, k0, k1, buf0, buf1, buf2, buf3);
+        blk++; have = 4;
     }
     __device__ __forceinline__ uint32_t next() {
         if (have == 0) refill();

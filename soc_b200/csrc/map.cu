@@ -23,6 +23,10 @@ __device__ __forceinline__ vec3 back(const vec3 &p, float s, const vec3 &d) {   
     return r;
 }
 
+// exp() correctly rounded to float: 1-exp(-dtau) cancels for dtau just above 1e-3, where one ulp of expf is
+// 6e-5 of the term -- beyond the 1e-5 contract.  The map kernel has only NPIX rays, so fp64 here is free.
+__device__ __forceinline__ float exp_cr(float x) { return (float)exp((double)x); }
+
 // the integration loop shared by both kernels
 template <bool OCT, bool DBL, bool HEALPIX>
 __device__ __forceinline__ void integrate(const MapArgs &M, vec3 POS, const vec3 &TMP, int id, unsigned long long &steps) {
@@ -40,8 +44,8 @@ __device__ __forceinline__ void integrate(const MapArgs &M, vec3 POS, const vec3
         float sx = get_step<OCT, DBL, true>(G, POS, TMP, level, ind, rho);
         float DTAU = xmul(xmul(sx, dens), kext);
         if (HEALPIX || M.level_threshold <= 0 || olevel >= M.level_threshold) {
-            float w = (DTAU < 1.0e-3f) ? xsub(1.0f, xmul(0.5f, DTAU)) : xdiv(xsub(1.0f, expf(-DTAU)), DTAU);
-            PHOTONS = xadd(PHOTONS, xmul(xmul(xmul(xmul(expf(-TAU), w), sx), em), dens));
+            float w = (DTAU < 1.0e-3f) ? xsub(1.0f, xmul(0.5f, DTAU)) : xdiv(xsub(1.0f, exp_cr(-DTAU)), DTAU);
+            PHOTONS = xadd(PHOTONS, xmul(xmul(xmul(xmul(exp_cr(-TAU), w), sx), em), dens));
         }
         TAU = xadd(TAU, DTAU);
         if (HEALPIX || M.save_colden > 0) colden = xadd(colden, xmul(sx, dens));

@@ -22,7 +22,7 @@
 
 namespace {
 
-struct Counters { unsigned long long packets, steps, scat, stuck; };
+struct Counters { unsigned packets, steps, scat, stuck; };      // per thread; widened when flushed
 
 // ---- accumulation ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void red_add(float *p, float v) { atomicAdd(p, v); }   // result unused -> RED.E.ADD.F32
@@ -51,7 +51,8 @@ struct Deposit {
     __device__ __forceinline__ void one(int oind, float delta, const vec3 &dir, int eidx, int level, int ind) const {
         if (A.with_ali && oind == eidx) red_add(&A.xab[oind], delta * A.tw);                 // kernel_ASOC.c:1486-1494
         else {
-            float v = delta * A.tw * A.adhoc;
+            float v = A.use_acc ? delta : delta * A.tw * A.adhoc;
+            float *main = A.use_acc ? A.acc : A.tabs;
             bool in_tile = false;
             if (tile != nullptr && level == 0 && (unsigned)(ind - A.tile_lo) < (unsigned)A.tile_span) {
                 int ix = ind % A.G.nx, iy = (ind / A.G.nx) % A.G.ny, iz = ind / (A.G.nx * A.G.ny);
@@ -61,9 +62,9 @@ struct Deposit {
                     in_tile = true;
                 }
             }
-            if (!in_tile) red_add(&A.tabs[oind], v);
+            if (!in_tile) red_add(&main[oind], v);
         }
-        if (A.use_int) red_add(&A.inten[oind], delta);
+        if (A.use_int && !A.use_acc) red_add(&A.inten[oind], delta);
         if (A.save_int2) {
             red_add(&A.intx[oind], delta * dir.x); red_add(&A.inty[oind], delta * dir.y); red_add(&A.intz[oind], delta * dir.z);
         }
@@ -253,7 +254,7 @@ __device__ __forceinline__ void tile_end(const SimArgs &A, float *tile) {
         if (v != 0.0f) {
             int tx = i % SOC_TILE_N, ty = (i / SOC_TILE_N) % SOC_TILE_N, tz = i / (SOC_TILE_N * SOC_TILE_N);
             int ix = A.tile_x0 + tx, iy = A.tile_y0 + ty, iz = A.tile_z0 + tz;
-            if (ix < G.nx && iy < G.ny && iz < G.nz) red_add(&A.tabs[(iz * G.ny + iy) * G.nx + ix], v);
+            if (ix < G.nx && iy < G.ny && iz < G.nz) red_add(&(A.use_acc ? A.acc : A.tabs)[(iz * G.ny + iy) * G.nx + ix], v);
         }
     }
 }
@@ -399,12 +400,290 @@ __global__ void __launch_bounds__(256) sim_stream_kernel(const __grid_constant__
     flush_counters(A, cnt);
 }
 
+// =================================================================================================================
+// Fast kernel: the production path on regular grids (LEVELS == 1).
+//
+// Same physics and the same Philox packet streams as the stream kernel, but the cell-to-cell stepping is an
+// incremental 3-D DDA written for the SM instead of a restatement of GetStep/Index:
+//   * the packet carries (ix,iy,iz), the distances tx,ty,tz along the ray to the next x/y/z face and their
+//     increments 1/|d|; one step is min3 + three subtractions + one integer increment -- no division, no
+//     fmod, no float->int conversion, and exact geometry (no PEPS overshoot, so no "failed step" nudge);
+//   * the density of the next cell is requested at the top of the step, before the optical-depth and exp()
+//     work of the current cell, so the gather latency overlaps a full step of arithmetic;
+//   * the only random numbers inside the loop are drawn at a scattering: one Philox block keyed by
+//     (packet, scattering number) -- no generator state lives in registers across steps;
+//   * one red.global.add.f32 per step into the scratch accumulator (folded into TABS / INT afterwards).
+// The position inside the cell is implied by (tx,ty,tz): frac = d>0 ? 1-t|d| : t|d|.
+// =================================================================================================================
+struct FastPk {
+    float tx, ty, tz, rdx, rdy, rdz;
+    vec3 dir;
+    int ix, iy, iz, ind;
+    float rho, photons, free_path, tau;
+    float2 opt;                      // per-cell (kabs, ksca) of the current cell (WITH_ABU)
+    int scat, nstep, eidx;
+    unsigned long long rid;          // Philox stream id of the packet
+};
+
+struct RngBlock {                    // four uniforms from one Philox block
+    uint32_t a, b, c, d; int k;
+    __device__ __forceinline__ RngBlock(const PhiloxLaunch &L, unsigned long long id, unsigned blk) {
+        philox4x32_10((uint32_t)id, (uint32_t)(id >> 32), blk, L.tag, L.k0, L.k1, a, b, c, d);
+        k = 0;
+    }
+    __device__ __forceinline__ float uniform() {
+        uint32_t v = (k == 0) ? a : ((k == 1) ? b : ((k == 2) ? c : d));
+        k++;
+        return u32_to_unit(v);
+    }
+};
+
+__device__ __forceinline__ float face_distance(float frac, float d, float rd) {
+    frac = fminf(fmaxf(frac, 0.0f), 1.0f);
+    return ((d > 0.0f) ? (1.0f - frac) : frac) * rd;
+}
+
+__device__ __forceinline__ void fast_from_packet(const SimArgs &A, const Packet &pk, FastPk &f) {
+    const GridDesc &G = A.G;
+    f.ix = clampi((int)floorf(pk.pos.x), 0, G.nx - 1);
+    f.iy = clampi((int)floorf(pk.pos.y), 0, G.ny - 1);
+    f.iz = clampi((int)floorf(pk.pos.z), 0, G.nz - 1);
+    f.ind = (f.iz * G.ny + f.iy) * G.nx + f.ix;
+    f.dir = pk.dir;
+    f.rdx = 1.0f / fabsf(pk.dir.x); f.rdy = 1.0f / fabsf(pk.dir.y); f.rdz = 1.0f / fabsf(pk.dir.z);
+    f.tx = face_distance(pk.pos.x - (float)f.ix, pk.dir.x, f.rdx);
+    f.ty = face_distance(pk.pos.y - (float)f.iy, pk.dir.y, f.rdy);
+    f.tz = face_distance(pk.pos.z - (float)f.iz, pk.dir.z, f.rdz);
+    f.rho = pk.rho; f.photons = pk.photons; f.free_path = pk.free_path; f.tau = 0.0f;
+    f.scat = 0; f.nstep = 0; f.eidx = pk.eidx;
+    if (A.with_abu) f.opt = __ldg(reinterpret_cast<const float2 *>(A.opt) + f.ind);
+}
+
+// Rotate d by the polar angle acos(ct) and a uniform azimuth phi.  Same distribution as Deflect()
+// (kernel_ASOC_aux.c:499-533) -- the azimuth is uniform either way -- without its acos/sincos chain.
+__device__ __forceinline__ void rotate_direction(vec3 &d, float ct, float phi) {
+    float st = sqrtf(fmaxf(0.0f, 1.0f - ct * ct)), sp, cp;
+    __sincosf(phi, &sp, &cp);
+    float w2 = 1.0f - d.z * d.z;
+    vec3 n;
+    if (w2 > 1.0e-6f) {
+        float iw = rsqrtf(w2);
+        n.x = st * (d.x * d.z * cp - d.y * sp) * iw + d.x * ct;
+        n.y = st * (d.y * d.z * cp + d.x * sp) * iw + d.y * ct;
+        n.z = -st * cp * w2 * iw + d.z * ct;
+    } else {
+        float sg = d.z > 0.0f ? 1.0f : -1.0f;
+        n.x = st * cp; n.y = st * sp; n.z = sg * ct;
+    }
+    d = n;
+}
+
+// DEP: accumulation engine (DepositMode).  GENERAL = false drops the per-cell opacities, the intensity vector,
+// the ALI split and the cell-emission source from the loop (uniform tests the common runs never take).
+template <int DEP, bool GENERAL>
+__global__ void __launch_bounds__(256, 4) sim_fast_kernel(const __grid_constant__ SimArgs A) {
+    __shared__ float smem[DEP == DEP_TILE ? SOC_TILE_CELLS : 1];
+    float *tile = (DEP == DEP_TILE) ? tile_begin(A, smem) : nullptr;
+    const GridDesc &G = A.G;
+    Counters cnt = { 0, 0, 0, 0 };
+    const int lane = threadIdx.x & 31;
+    const long long nlocal = (A.nunits - A.rank + A.world - 1) / A.world;
+    const int sy_ = G.nx, sz_ = G.nx * G.ny;
+    const bool cl = GENERAL && A.kind == SIM_CL;
+    const bool abu = GENERAL && A.with_abu;
+    FastPk f; f.ind = 0; f.rid = 0; f.eidx = -1;
+    bool alive = false, more = true;
+    int icell = 0, iray = 0, nray = 0;
+    float pwei = 1.0f;
+    const int refill = A.refill;
+    for (;;) {
+        unsigned idle = __ballot_sync(FULL, !alive);
+        if (idle == FULL || (__popc(idle) >= refill && __any_sync(FULL, more))) {
+            bool need = !alive && more && iray >= nray;
+            unsigned nm = __ballot_sync(FULL, need);
+            unsigned long long q = 0;
+            bool got = false;
+            if (nm) {
+                int leader = __ffs(nm) - 1;
+                unsigned long long base = 0;
+                if (lane == leader) base = atomicAdd(A.work, (unsigned long long)__popc(nm));
+                base = __shfl_sync(FULL, base, leader);
+                if (need) {
+                    long long u = (long long)base + __popc(nm & ((1u << lane) - 1u));
+                    if (u >= nlocal) more = false;
+                    else { q = (unsigned long long)u * A.world + A.rank; got = true; }
+                }
+            }
+            if (got && cl) { icell = (int)q; iray = 0; nray = cl_rays(A, icell, pwei); got = false; }
+            if (cl && !alive && iray < nray) {
+                q = (unsigned long long)(unsigned)icell | ((unsigned long long)(unsigned)iray << 32);
+                iray++; got = true;
+            }
+            if (got) {
+                RngPhilox rng; rng.seed(A.phx, q);
+                Packet pk; pk.ind = -1; pk.level = 0; pk.eidx = -1; pk.rho = 0.0f;
+                if (GENERAL && cl) emit_cl(A, rng, icell, pwei, pk);
+                else {
+                    int id = (int)(q / (unsigned)A.batch), III = (int)(q % (unsigned)A.batch);
+                    if (A.kind == SIM_PS)      emit_ps<SimArgs, RngPhilox, false>(A, rng, III, pk);
+                    else if (A.kind == SIM_BG) emit_bg<SimArgs, RngPhilox, false>(A, rng, id, pk);
+                    else                       emit_hp<RngPhilox, false>(A, rng, pk);
+                }
+                start_packet(A, rng, pk, A.kind != SIM_HP);
+                cnt.packets++;
+                alive = pk.ind >= 0;
+                if (alive) { fast_from_packet(A, pk, f); f.rid = q; }
+            }
+            if (!__any_sync(FULL, alive || more || iray < nray)) break;
+        }
+        // ---- one cell-step ---------------------------------------------------------------------------------
+        bool d = false; float delta = 0.0f; int oind = f.ind;
+        bool sc = false; float rho_n = 0.0f; int nind = 0; bool inb = false; float tmin = 0.0f; int ax = 0;
+        float2 opt_n = make_float2(0.0f, 0.0f);
+        const bool was_alive = alive;
+        if (alive) {
+            // which face comes first, and the cell behind it; its density is requested right away
+            tmin = fminf(f.tx, fminf(f.ty, f.tz));
+            ax = (f.tx <= f.ty && f.tx <= f.tz) ? 0 : ((f.ty <= f.tz) ? 1 : 2);
+            int c = (ax == 0) ? f.ix : ((ax == 1) ? f.iy : f.iz);
+            float dd = (ax == 0) ? f.dir.x : ((ax == 1) ? f.dir.y : f.dir.z);
+            int lim = (ax == 0) ? G.nx : ((ax == 1) ? G.ny : G.nz);
+            int stride = (ax == 0) ? 1 : ((ax == 1) ? sy_ : sz_);
+            int sgn = dd > 0.0f ? 1 : -1;
+            inb = (unsigned)(c + sgn) < (unsigned)lim;
+            nind = f.ind + sgn * stride;
+            if (inb) {
+                rho_n = __ldg(G.dens + nind);
+                if (abu) opt_n = __ldg(reinterpret_cast<const float2 *>(A.opt) + nind);
+            }
+            float kabs = A.kabs, ksca = A.ksca;
+            if (abu) { kabs = f.opt.x; ksca = f.opt.y; }
+            float dtau = tmin * f.rho * ksca, tauA;
+            sc = f.free_path < f.tau + dtau;
+            d = true;
+            if (sc) {
+                f.scat++;
+                if (cl && f.scat > 20) { d = false; alive = false; }
+                tmin = fminf(tmin, (f.free_path - f.tau) / (ksca * f.rho));
+            } else f.tau += dtau;
+            tauA = tmin * f.rho * kabs;
+            float e = expf(-tauA);
+            delta = (tauA > SOC_TAULIM) ? (f.photons * (1.0f - e)) : (f.photons * tauA * (1.0f - 0.5f * tauA));
+            if (d) { f.photons *= e; f.nstep++; }
+        }
+        // ---- deposit: one red.global.add.f32 (or a shared-memory tile / warp-combined add) ------------------
+        if (GENERAL && (A.save_int2 || A.with_ali)) {
+            if (d) {
+                if (A.with_ali && oind == f.eidx) red_add(&A.xab[oind], delta * A.tw);
+                else red_add(&A.acc[oind], delta);
+                if (A.save_int2) {
+                    red_add(&A.intx[oind], delta * f.dir.x); red_add(&A.inty[oind], delta * f.dir.y); red_add(&A.intz[oind], delta * f.dir.z);
+                }
+            }
+        } else if (DEP == DEP_RED) {
+            if (d) red_add(&A.acc[oind], delta);
+        } else {
+            bool comb = __any_sync(FULL, d && f.nstep < A.agg_steps);
+            if (comb) {
+                unsigned act = __ballot_sync(FULL, d);
+                if (d) {
+                    unsigned peers = __match_any_sync(act, oind);
+                    if (peers != (1u << lane)) {
+                        delta = reduce_peers(peers, delta, lane);
+                        if (lane != __ffs(peers) - 1) d = false;
+                    }
+                }
+            }
+            if (d) {
+                bool in_tile = false;
+                if (DEP == DEP_TILE && (unsigned)(oind - A.tile_lo) < (unsigned)A.tile_span) {
+                    unsigned tx = (unsigned)(f.ix - A.tile_x0), ty = (unsigned)(f.iy - A.tile_y0), tz = (unsigned)(f.iz - A.tile_z0);
+                    if (tx < SOC_TILE_N && ty < SOC_TILE_N && tz < SOC_TILE_N) {
+                        atomicAdd(&tile[(tz * SOC_TILE_N + ty) * SOC_TILE_N + tx], delta);
+                        in_tile = true;
+                    }
+                }
+                if (!in_tile) red_add(&A.acc[oind], delta);
+            }
+        }
+        if (alive) {
+            f.tx -= tmin; f.ty -= tmin; f.tz -= tmin;
+            if (sc) {
+                // position inside the cell from the face distances, then a new direction
+                float fx = (f.dir.x > 0.0f) ? 1.0f - f.tx * fabsf(f.dir.x) : f.tx * fabsf(f.dir.x);
+                float fy = (f.dir.y > 0.0f) ? 1.0f - f.ty * fabsf(f.dir.y) : f.ty * fabsf(f.dir.y);
+                float fz = (f.dir.z > 0.0f) ? 1.0f - f.tz * fabsf(f.dir.z) : f.tz * fabsf(f.dir.z);
+                RngBlock rb(A.phx, f.rid, 0x10000u + (unsigned)f.scat);
+                f.free_path = sample_free_path(A, rb, f.photons);
+                float ct = A.csc[clampi((int)(rb.uniform() * A.bins), 0, A.bins - 1)];
+                rotate_direction(f.dir, ct, SOC_TWOPI * rb.uniform());
+                fix_direction(f.dir);
+                f.rdx = 1.0f / fabsf(f.dir.x); f.rdy = 1.0f / fabsf(f.dir.y); f.rdz = 1.0f / fabsf(f.dir.z);
+                f.tx = face_distance(fx, f.dir.x, f.rdx);
+                f.ty = face_distance(fy, f.dir.y, f.rdy);
+                f.tz = face_distance(fz, f.dir.z, f.rdz);
+                f.tau = 0.0f;
+                if (!cl && f.scat > 20) alive = false;
+            } else {
+                if (ax == 0)      { f.ix += (f.dir.x > 0.0f) ? 1 : -1; f.tx = f.rdx; }
+                else if (ax == 1) { f.iy += (f.dir.y > 0.0f) ? 1 : -1; f.ty = f.rdy; }
+                else              { f.iz += (f.dir.z > 0.0f) ? 1 : -1; f.tz = f.rdz; }
+                f.ind = nind; f.rho = rho_n;
+                if (abu) f.opt = opt_n;
+                alive = inb;
+            }
+            if (f.nstep > A.max_steps) { alive = false; cnt.stuck++; }
+        }
+        if (was_alive && !alive) { cnt.steps += f.nstep; cnt.scat += min(f.scat, 20); }     // packet finished
+    }
+    tile_end(A, tile);
+    flush_counters(A, cnt);
+}
+
+// TABS += acc * TW*ADHOC ; INT += acc ; acc = 0   (float4 streams; acc is all-zero again afterwards)
+__global__ void __launch_bounds__(256) fold_acc_kernel(float *__restrict__ acc, float *__restrict__ tabs, float *__restrict__ inten,
+                                                       float scale, long long n) {
+    const long long n4 = n >> 2, stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 a = reinterpret_cast<float4 *>(acc)[i];
+        if (a.x != 0.0f || a.y != 0.0f || a.z != 0.0f || a.w != 0.0f) {
+            float4 t = reinterpret_cast<float4 *>(tabs)[i];
+            t.x += a.x * scale; t.y += a.y * scale; t.z += a.z * scale; t.w += a.w * scale;
+            reinterpret_cast<float4 *>(tabs)[i] = t;
+            if (inten != nullptr) {
+                float4 v = reinterpret_cast<float4 *>(inten)[i];
+                v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+                reinterpret_cast<float4 *>(inten)[i] = v;
+            }
+            reinterpret_cast<float4 *>(acc)[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+    }
+    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float a = acc[i];
+        if (a != 0.0f) { tabs[i] += a * scale; if (inten != nullptr) inten[i] += a; acc[i] = 0.0f; }
+    }
+}
+
 // MWC64X work-item stream with the item-kernel interface
 struct RngMwcItem : RngMwc {
     __device__ __forceinline__ void seed_item(const SimArgs &A, unsigned long long id) { seed(A.mwc, id); }
 };
 
 }  // namespace
+
+static void launch_fast(const SimArgs &A, int blocks, int threads, cudaStream_t stream) {
+    const bool general = A.with_abu || A.save_int2 || A.with_ali || A.kind == SIM_CL;
+    const int dep = (A.save_int2 || A.with_ali) ? DEP_RED : A.deposit;
+    if (general) {
+        if (dep == DEP_RED)       sim_fast_kernel<DEP_RED, true><<<blocks, threads, 0, stream>>>(A);
+        else if (dep == DEP_WARP) sim_fast_kernel<DEP_WARP, true><<<blocks, threads, 0, stream>>>(A);
+        else                      sim_fast_kernel<DEP_TILE, true><<<blocks, threads, 0, stream>>>(A);
+    } else {
+        if (dep == DEP_RED)       sim_fast_kernel<DEP_RED, false><<<blocks, threads, 0, stream>>>(A);
+        else if (dep == DEP_WARP) sim_fast_kernel<DEP_WARP, false><<<blocks, threads, 0, stream>>>(A);
+        else                      sim_fast_kernel<DEP_TILE, false><<<blocks, threads, 0, stream>>>(A);
+    }
+}
 
 void launch_sim(const SimArgs &A, int rng_mode, int blocks, int threads, cudaStream_t stream) {
     const bool oct = A.G.levels > 1, dbl = A.G.dbl_sim != 0;
@@ -413,7 +692,7 @@ void launch_sim(const SimArgs &A, int rng_mode, int blocks, int threads, cudaStr
         else if (!dbl) sim_item_kernel<RngMwcItem, true, false><<<blocks, threads, 0, stream>>>(A);
         else           sim_item_kernel<RngMwcItem, true, true><<<blocks, threads, 0, stream>>>(A);
     } else {
-        if (!oct)      sim_stream_kernel<false, false><<<blocks, threads, 0, stream>>>(A);
+        if (!oct)      launch_fast(A, blocks, threads, stream);
         else if (!dbl) sim_stream_kernel<true, false><<<blocks, threads, 0, stream>>>(A);
         else           sim_stream_kernel<true, true><<<blocks, threads, 0, stream>>>(A);
     }
@@ -426,9 +705,17 @@ int sim_blocks_per_sm(int rng_mode, bool octree, bool dbl, int threads) {
         else if (!dbl) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sim_item_kernel<RngMwcItem, true, false>, threads, 0);
         else           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sim_item_kernel<RngMwcItem, true, true>, threads, 0);
     } else {
-        if (!octree)   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sim_stream_kernel<false, false>, threads, 0);
+        if (!octree)   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sim_fast_kernel<DEP_TILE, true>, threads, 0);
         else if (!dbl) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sim_stream_kernel<true, false>, threads, 0);
         else           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sim_stream_kernel<true, true>, threads, 0);
     }
     return n > 0 ? n : 1;
+}
+
+void launch_fold_acc(const SimArgs &A, cudaStream_t stream) {
+    const long long n = A.G.cells;
+    long long b = ((n >> 2) + 255) / 256;
+    const long long cap = 148LL * 8;
+    fold_acc_kernel<<<(int)(b < 1 ? 1 : (b > cap ? cap : b)), 256, 0, stream>>>(A.acc, A.tabs, A.use_int ? A.inten : nullptr,
+                                                                              A.tw * A.adhoc, n);
 }

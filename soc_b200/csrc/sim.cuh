@@ -18,6 +18,10 @@ struct SimArgs {
     GridDesc G;
     // accumulators [cells]
     float *tabs, *xab, *inten, *intx, *inty, *intz;
+    // per-launch scratch accumulator [cells]: the stream kernels add the unweighted absorbed energy here and
+    // fold_acc() spreads it to TABS (x TW*ADHOC) and INT afterwards -- one atomic per cell-step instead of two
+    float *acc;
+    int use_acc;
     // inputs
     const float *__restrict__ emit, *__restrict__ emwei, *__restrict__ opt;
     const float *__restrict__ dsc, *__restrict__ csc;
@@ -42,4 +46,5 @@ struct SimArgs {
 };
 
 void launch_sim(const SimArgs &A, int rng_mode, int blocks, int threads, cudaStream_t stream);
+void launch_fold_acc(const SimArgs &A, cudaStream_t stream);     // TABS += acc*TW*ADHOC; INT += acc; acc = 0
 int  sim_blocks_per_sm(int rng_mode, bool octree, bool dbl, int threads);
