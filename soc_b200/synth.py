@@ -115,5 +115,5 @@ def isrf_like_background(freq, scale=1.0):
 def blackbody_source(freq, t=10000.0, lum_lsun=1.0):
     """Luminosity per Hz [erg/s/Hz] of a black body of temperature t normalised to lum_lsun."""
     b = planck(freq, t)
-    lum = 3.846e33 * lum_lsun * b / np.trapz(b, freq)
+    lum = 3.846e33 * lum_lsun * b / np.trapezoid(b, freq)
     return lum.astype(np.float32)

@@ -1,0 +1,185 @@
+"""TEST INFRASTRUCTURE ONLY: an object with the interface of soc_b200.backend.Device whose "kernels" are the
+CPU oracle (oracle/orc.py).  The drivers in soc_b200/ take a device factory, so the same driver code can be
+run end to end on the CUDA library and on the oracle and the output files compared -- and the host logic
+(ini parsing, weights, file formats, rank sharding) can be tested on machines without a GPU.
+
+Sharding: with world > 1 every rank runs the complete launch with a rank-dependent seed and contributes 1/world
+of it, so that the sum over ranks is a valid Monte Carlo estimate like the packet-sharded CUDA path.
+"""
+import ctypes as C
+
+import numpy as np
+
+from oracle import orc
+from soc_b200 import backend as bk
+
+
+class _Counters:
+    def __init__(self, c):
+        self.packets, self.steps, self.scatterings, self.peels = c.packets, c.steps, c.scatterings, c.peels
+        self.launches, self.reserved = 0, [0, 0, 0]
+
+
+class OracleDevice:
+    def __init__(self, ordinal=0):
+        self.O = None
+        self.params = {}
+        self.buf = {}
+        self.rank, self.world = 0, 1
+        self.cloud = None
+
+    # ---- configuration ------------------------------------------------------------------------------------
+    def set_params(self, **kw):
+        if kw.get("with_msf") or kw.get("mirror") or kw.get("do_split"):
+            raise bk.SocError("unsupported option")
+        self.params = dict(kw)
+        if self.cloud is not None:
+            self._make()
+
+    def set_grid(self, cloud):
+        self.cloud = cloud
+        self._make()
+
+    def _make(self):
+        p = dict(self.params)
+        length = p.pop("length")
+        bins = p.pop("bins", 2500)
+        for k in ("factor", "adhoc", "with_msf", "mirror", "dir_weight", "do_split", "roi_flags", "map_interpolation"):
+            p.pop(k, None)
+        self.O = orc.Oracle(self.cloud, gl=0.01, bins=bins, **p)
+        self.O.P.length = length
+        self.n = self.cloud.CELLS
+
+    def set_rng_mode(self, mode):
+        pass
+
+    def set_shard(self, rank, world):
+        self.rank, self.world = rank, world
+
+    def set_tuning(self, *a, **k):
+        pass
+
+    def sync(self):
+        pass
+
+    def close(self):
+        pass
+
+    def stream(self):
+        return None
+
+    # ---- buffers --------------------------------------------------------------------------------------------
+    _ACC = {bk.BUF_TABS: "tabs", bk.BUF_XAB: "xab", bk.BUF_INT: "int_", bk.BUF_INTX: "intx", bk.BUF_INTY: "inty",
+            bk.BUF_INTZ: "intz"}
+
+    def host_view(self, b, count):
+        if b in self._ACC:
+            return getattr(self.O, self._ACC[b])[:count]
+        return self.buf[b][:count]
+
+    def upload(self, b, array, dtype=np.float32):
+        if b in self._ACC:
+            getattr(self.O, self._ACC[b])[:] = np.asarray(array, np.float32)
+        else:
+            self.buf[b] = np.array(array, dtype).reshape(-1).copy()
+        return array
+
+    def download(self, b, n, dtype=np.float32, out=None):
+        src = self.host_view(b, n)
+        if out is None:
+            return np.array(src[:n], dtype)
+        out[:] = src[:n]
+        return out
+
+    def clear(self, b, nbytes):
+        self.buf[b] = np.zeros(nbytes // 4, np.float32)
+
+    def device_ptr(self, b):
+        if b in self._ACC:
+            return 1, 4 * self.n
+        a = self.buf.get(b)
+        return (1, a.nbytes) if a is not None else (None, 0)
+
+    def zero_amc(self, tag):
+        self.O.zero(tag)
+
+    # ---- launches -------------------------------------------------------------------------------------------
+    def _g(self, b):
+        return self.buf.get(b)
+
+    def _sharded(self, run, seed):
+        """Run a launch; with world > 1 every rank contributes 1/world of a full launch with its own seed."""
+        if self.world == 1:
+            run(seed)
+            return
+        keep = {k: getattr(self.O, k).copy() for k in self._ACC.values()}
+        for k in self._ACC.values():
+            getattr(self.O, k)[:] = 0.0
+        run(float(np.fmod(seed + 0.37 * self.rank + 0.011, 1.0)))
+        for k in self._ACC.values():
+            a = getattr(self.O, k)
+            a[:] = keep[k] + a / np.float32(self.world)
+
+    def sim_pb(self, source, packets, batch, seed, abs_, sca, bg, tw, global_):
+        self._sharded(lambda s: self.O.sim_pb(global_, source, packets, batch, s, bg, tw, abs_=abs_, sca=sca,
+                                              dsc=self._g(bk.BUF_DSC), csc=self._g(bk.BUF_CSC), opt=self._g(bk.BUF_OPT),
+                                              pspos=self._g(bk.BUF_PSPOS), ps=self._g(bk.BUF_PS),
+                                              xps_nside=self._g(bk.BUF_XPS_NSIDE), xps_side=self._g(bk.BUF_XPS_SIDE),
+                                              xps_area=self._g(bk.BUF_XPS_AREA)), seed)
+
+    def sim_hp(self, packets, batch, seed, abs_, sca, tw, global_):
+        self._sharded(lambda s: self.O.sim_hp(global_, packets, batch, s, tw, abs_=abs_, sca=sca, dsc=self._g(bk.BUF_DSC),
+                                              csc=self._g(bk.BUF_CSC), opt=self._g(bk.BUF_OPT), hpbg=self._g(bk.BUF_HPBG),
+                                              hpbgp=self._g(bk.BUF_HPBGP)), seed)
+
+    def sim_cl(self, source, packets, batch, seed, abs_, sca, tw, global_):
+        self._sharded(lambda s: self.O.sim_cl(global_, packets, batch, s, tw, abs_=abs_, sca=sca, dsc=self._g(bk.BUF_DSC),
+                                              csc=self._g(bk.BUF_CSC), opt=self._g(bk.BUF_OPT), emit=self._g(bk.BUF_EMIT),
+                                              emwei=self._g(bk.BUF_EMWEI)), seed)
+
+    def eq_temperature(self, level, adhoc, kE, Emin, NE):
+        if bk.BUF_TNEW not in self.buf or self.buf[bk.BUF_TNEW].size != self.n:
+            self.buf[bk.BUF_TNEW] = np.zeros(self.n, np.float32)
+        self.O.eq_temperature(level, adhoc, kE, Emin, NE, self.buf[bk.BUF_TTT], self.buf[bk.BUF_EMIT], self.buf[bk.BUF_TNEW])
+
+    def emission(self, freq, fabs_):
+        self.buf[bk.BUF_EMIT] = self.O.emission(freq, fabs_, self.buf[bk.BUF_TNEW])
+
+    def mapping(self, map_dx, npx, npy, dir_, ra, de, abs_, sca, centre, intobs, save_colden):
+        m, t = self.O.mapping(map_dx, npx, npy, self.buf[bk.BUF_EMIT], dir_, ra, de, abs_, sca, centre, intobs=intobs,
+                              opt=self._g(bk.BUF_OPT), save_colden=save_colden)
+        self.buf[bk.BUF_MAP], self.buf[bk.BUF_SAVETAU] = m.reshape(-1), t.reshape(-1)
+
+    def healpix_mapping(self, nside, abs_, sca, intobs, save_colden):
+        m, t = self.O.healpix_mapping(nside, self.buf[bk.BUF_EMIT], abs_, sca, intobs, opt=self._g(bk.BUF_OPT),
+                                      save_colden=save_colden)
+        self.buf[bk.BUF_MAP], self.buf[bk.BUF_SAVETAU] = m, t
+
+    def sca_zero_out(self, ndir, npx, npy):
+        self.buf[bk.BUF_OUT] = np.zeros(ndir * npx * npy, np.float32)
+
+    def _obs(self, ndir):
+        return [self.buf[b].reshape(ndir, 3) for b in (bk.BUF_ODIR, bk.BUF_ORA, bk.BUF_ODE)]
+
+    def sca_ps(self, packets, batch, seed, abs_, sca, ndir, npx, npy, map_dx, centre, global_):
+        od, ra, de = self._obs(ndir)
+        out = self.O.sca_ps(global_, packets, batch, seed, ndir, npx, npy, map_dx, centre, od, ra, de, abs_=abs_, sca=sca,
+                            dsc=self._g(bk.BUF_DSC), csc=self._g(bk.BUF_CSC), opt=self._g(bk.BUF_OPT),
+                            pspos=self._g(bk.BUF_PSPOS), ps=self._g(bk.BUF_PS))
+        self.buf[bk.BUF_OUT] = self.buf[bk.BUF_OUT] + out.reshape(-1) / np.float32(self.world)
+
+    def sca_pb(self, source, packets, batch, seed, abs_, sca, bg, ndir, npx, npy, map_dx, centre, global_):
+        od, ra, de = self._obs(ndir)
+        out = self.O.sca_pb(global_, source, packets, batch, seed, bg, ndir, npx, npy, map_dx, centre, od, ra, de, abs_=abs_,
+                            sca=sca, dsc=self._g(bk.BUF_DSC), csc=self._g(bk.BUF_CSC), opt=self._g(bk.BUF_OPT),
+                            pspos=self._g(bk.BUF_PSPOS), ps=self._g(bk.BUF_PS))
+        self.buf[bk.BUF_OUT] = self.buf[bk.BUF_OUT] + out.reshape(-1) / np.float32(self.world)
+
+    def counters(self):
+        return _Counters(self.O.counters)
+
+    def reset_counters(self):
+        C.memset(C.byref(self.O.counters), 0, C.sizeof(self.O.counters))
+
+    def last_launch_ms(self):
+        return 0.0

@@ -1,0 +1,90 @@
+"""End-to-end tests of the ASOC driver's host logic on the CPU: the driver runs unchanged, its device is the
+oracle-backed stand-in of tests/oracle_device.py.  Checks the process contract (files, formats, headers), the
+unit chain (sane temperatures), and the rank logic with two gloo ranks."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from soc_b200 import asoc
+from soc_b200.formats import read_otfile, read_map_file, read_cells_freq_file
+from soc_b200.ini import User
+from tests.model import write_model
+from tests.oracle_device import OracleDevice
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(tmp, **kw):
+    ini, cloud = write_model(str(tmp), **kw)
+    cwd = os.getcwd()
+    os.chdir(str(tmp))
+    try:
+        asoc.main(["ASOC.py", "model.ini"], device_factory=OracleDevice)
+    finally:
+        os.chdir(cwd)
+    return cloud
+
+
+def test_ini_keywords_prefix_matching(tmp_path):
+    ini, _ = write_model(str(tmp_path), pspac=1000, extra="DEFS -D X=1 # c\nmapum 100 250\nCLT\nsavetau tau -1 250\nstepweight 2 0.5 0.3\n")
+    U = User(ini)
+    assert U.file_cloud == "model.cloud" and U.DSC_BINS == 500 and U.BGPAC == 40000 and U.PSPAC == 1000
+    assert U.NO_PS == 1 and abs(U.PSPOS[0][0] - 6.3) < 1e-6 and U.NOABSORBED == 1 and "CLT" in U.KEYS
+    assert len(U.SINGLE_MAP_FREQ) == 2 and U.SINGLE_MAP_FREQ[0] < U.SINGLE_MAP_FREQ[1]
+    assert U.savetau_freq[0] == 0.0 and U.STEP_WEIGHT == [2, 0.5, 0.3]
+    assert len(U.OBS_THETA) == 2 and U.unsupported() == []
+    open(ini, "a").write("split 1\npolmap a b c\n")
+    assert len(User(ini).unsupported()) == 2
+
+
+def test_background_run_writes_the_reference_files(tmp_path):
+    cloud = _run(tmp_path, n=10, bgpac=30000)
+    n = cloud.CELLS
+    assert (np.fromfile(tmp_path / "packet.info", np.int32) == [30016, 0, 0, 0]).all()
+    T = read_otfile(str(tmp_path / "model.T"))
+    assert T.shape == (n,) and (T >= 3.0).all() and (T < 60.0).all() and T.std() > 0.01
+    hdr = np.fromfile(tmp_path / "model.T", np.int32, 6)
+    assert list(hdr[:5]) == [10, 10, 10, 1, n] and hdr[5] == n
+    em = read_cells_freq_file(str(tmp_path / "emit.data"))
+    assert em.shape == (n, 8) and (em >= 0).all() and em.max() > 0
+    for idir in range(2):
+        m = read_map_file(str(tmp_path / ("map_dir_%02d.bin" % idir)))
+        assert m.shape == (8, 10, 10) and np.isfinite(m).all() and m[:4].min() > 0.0
+
+
+def test_absorbed_file_and_octree(tmp_path):
+    cloud = _run(tmp_path, n=6, octree=True, bgpac=20000, pspac=33000, noabsorbed=False, absorbed=True, maps=False)
+    a = read_cells_freq_file(str(tmp_path / "abs.data"))
+    assert a.shape == (cloud.CELLS, 8)
+    parents = cloud.DENS <= 0.0
+    assert (a[parents] == np.float32(-1.0e20)).all()
+    assert (a[~parents] >= 0.0).all() and (a[~parents].sum(axis=0) > 0).all()
+
+
+def test_cell_emission_iterations_with_reference_field(tmp_path):
+    cloud = _run(tmp_path, n=8, bgpac=20000, cellpac=8 ** 3 * 4, iterations=2, maps=False, extra="reference 1\n")
+    T = read_otfile(str(tmp_path / "model.T"))
+    assert (T >= 3.0).all() and (T < 80.0).all()
+
+
+def test_two_gloo_ranks_agree_with_one(tmp_path):
+    """world_size 2 over gloo: both ranks run, rank 0 writes; temperatures agree with the 1-rank run within noise."""
+    one = tmp_path / "one"
+    two = tmp_path / "two"
+    _run(one, n=8, bgpac=60000, pspac=33000)
+    write_model(str(two), n=8, bgpac=60000, pspac=33000)
+    (two / "run.py").write_text(
+        "import sys\nsys.path.insert(0, %r)\nfrom soc_b200 import asoc\nfrom tests.oracle_device import OracleDevice\n"
+        "asoc.main(['ASOC.py', 'model.ini'], device_factory=OracleDevice)\n" % ROOT)
+    env = dict(os.environ, SOC_DIST_BACKEND="gloo", OMP_NUM_THREADS="2")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", "run.py"], cwd=str(two), env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    T1, T2 = read_otfile(str(one / "model.T")), read_otfile(str(two / "model.T"))
+    assert np.abs(T2 / T1 - 1.0).max() < 0.05
+    m1, m2 = read_map_file(str(one / "map_dir_00.bin")), read_map_file(str(two / "map_dir_00.bin"))
+    assert np.abs(m2[:2] / m1[:2] - 1.0).max() < 0.1
