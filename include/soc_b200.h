@@ -27,7 +27,7 @@
  * New (no counterpart in the single-device reference):
  *   soc_set_shard, soc_device_ptr           packet sharding over ranks and the device addresses a
  *                                           host-side NCCL all-reduce needs
- *   soc_set_rng_mode, soc_set_tuning,
+ *   soc_set_rng_mode, soc_set_tuning, soc_set_geometry,
  *   soc_get_counters, soc_last_launch_ms,
  *   soc_stream                              stream layout, accumulation engine, work counters, device timing
  */
@@ -117,6 +117,11 @@ int  soc_set_shard(soc_context *ctx, int rank, int world);
  * the point source.  refill_lanes: a warp takes new packets when at least this many lanes are idle (1..32).
  * aggregate_steps: lanes are combined only while some packet of the warp is younger than this many steps. */
 int  soc_set_tuning(soc_context *ctx, int deposit_mode, int refill_lanes, int aggregate_steps);
+
+/* Cell stepping of the production layout on regular grids: 0 (default) = exact incremental DDA, 1 = the
+ * reference's GetStep arithmetic (PEPS overshoot, 2*PEPS pull-back at scatterings, kernel_ASOC_aux.c:282-315).
+ * The two differ only where the mean free path is comparable to PEPS = 1e-4 cells. */
+int  soc_set_geometry(soc_context *ctx, int mode);
 
 int  soc_upload(soc_context *ctx, int buffer, const void *host, size_t nbytes);
 int  soc_download(soc_context *ctx, int buffer, void *host, size_t nbytes);

@@ -326,6 +326,7 @@ def main(argv=None, device_factory=None):
                    level_threshold=USER.LEVEL_THRESHOLD, length=length, factor=FACTOR, adhoc=ADHOC)
     dev.set_grid(cloud)
     dev.set_rng_mode(bk.RNG_REFERENCE if 'REFSTREAMS' in USER.KEYS else bk.RNG_PACKET)
+    dev.set_geometry(1 if 'REFGEOMETRY' in USER.KEYS else 0)
     dev.set_shard(comm.rank, comm.world)
     if USER.NO_PS > 0:
         dev.upload(bk.BUF_PSPOS, np.ascontiguousarray(USER.PSPOS[:USER.NO_PS].reshape(-1)))

@@ -45,7 +45,7 @@ struct soc_context {
     bool have_params, have_grid;
     GridDesc G;
     int rng_mode, rank, world;
-    int deposit, refill, agg_steps;
+    int deposit, refill, agg_steps, geometry;
     uint64_t pow2k[26];
 };
 
@@ -203,6 +203,13 @@ int soc_set_tuning(soc_context *c, int deposit_mode, int refill_lanes, int aggre
     return SOC_OK;
 }
 
+int soc_set_geometry(soc_context *c, int mode) {
+    NEED_CTX(c);
+    if (mode != 0 && mode != 1) return fail(SOC_ERR_ARG, "soc_set_geometry: %d", mode);
+    c->geometry = mode;
+    return SOC_OK;
+}
+
 int soc_upload(soc_context *c, int b, const void *host, size_t nbytes) {
     NEED_CTX(c);
     if (b == SOC_BUF_DENS || b == SOC_BUF_PAR) return fail(SOC_ERR_ARG, "soc_upload: %s is set by soc_set_grid", buf_name(b));
@@ -307,7 +314,7 @@ static int sim_common(soc_context *c, SimArgs &A, int kind, int batch, float see
     A.rank = c->rank; A.world = c->world;
     long long ms = 100LL * ((long long)c->G.nx + c->G.ny + c->G.nz) << (c->G.levels - 1);
     A.max_steps = (int)(ms > INT_MAX ? INT_MAX : ms);
-    A.deposit = c->deposit; A.refill = c->refill; A.agg_steps = c->agg_steps;
+    A.deposit = c->deposit; A.refill = c->refill; A.agg_steps = c->agg_steps; A.ref_geometry = c->geometry;
     A.counters = c->counters; A.work = c->counters + 5;
     // stream layouts
     A.mwc.base_offset = seed_to_base(seed);

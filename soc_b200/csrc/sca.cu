@@ -94,7 +94,9 @@ __device__ __forceinline__ void advance(const ScaArgs &S, Lane &L, RNG &rng, Sca
         if (r.ind >= 0) return;
         float tau = r.tau, W;
         if (S.flavour == 0) { W = -expm1f(-tau); L.free_path = -logf(1.0f - W * rng.uniform()); }
-        else                { W = 1.0f - expf(-tau); L.free_path = (float)(-log(1.0 - (double)(W * rng.uniform()))); }
+        // 1-exp(-tau) in single precision is quantised to 6e-8 (the reference's SimRAM_PB does exactly this); the
+        // correctly rounded exp keeps the quantisation identical to a host OpenCL/libm evaluation
+        else                { W = 1.0f - (float)exp(-(double)tau); L.free_path = (float)(-log(1.0 - (double)(W * rng.uniform()))); }
         L.photons *= W;
         r.pos = L.kpos; r.level = L.klevel; r.ind = L.kind_; r.rho = L.krho; r.tau = 0.0f;
         L.mode = (tau < 1.0e-22f) ? RAY_IDLE : RAY_MAIN;

@@ -692,7 +692,8 @@ void launch_sim(const SimArgs &A, int rng_mode, int blocks, int threads, cudaStr
         else if (!dbl) sim_item_kernel<RngMwcItem, true, false><<<blocks, threads, 0, stream>>>(A);
         else           sim_item_kernel<RngMwcItem, true, true><<<blocks, threads, 0, stream>>>(A);
     } else {
-        if (!oct)      launch_fast(A, blocks, threads, stream);
+        if (!oct && !A.ref_geometry) launch_fast(A, blocks, threads, stream);
+        else if (!oct) sim_stream_kernel<false, false><<<blocks, threads, 0, stream>>>(A);
         else if (!dbl) sim_stream_kernel<true, false><<<blocks, threads, 0, stream>>>(A);
         else           sim_stream_kernel<true, true><<<blocks, threads, 0, stream>>>(A);
     }

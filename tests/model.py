@@ -32,7 +32,7 @@ def write_model(path, n=12, octree=False, nfreq=8, bgpac=40000, pspac=0, cellpac
         fp.write("cloud        model.cloud\n")
         fp.write("optical      toy.dust%s\n" % ("  abu.bin" if abundance else ""))
         fp.write("dsc          toy.dsc %d\n" % bins)
-        fp.write("gridlength   0.02\ndensity      3.0e4   # scaling of densities\n")
+        fp.write("gridlength   0.02\ndensity      %.3e   # scaling of densities\n" % (6.0 / n))   # tau_V across the model ~ 10
         fp.write("background   bg.bin  1.0\n")
         fp.write("bgpackets    %d\n" % bgpac)
         if pspac > 0:

@@ -59,6 +59,9 @@ class OracleDevice:
     def set_tuning(self, *a, **k):
         pass
 
+    def set_geometry(self, mode):
+        pass
+
     def sync(self):
         pass
 

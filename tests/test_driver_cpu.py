@@ -88,3 +88,18 @@ def test_two_gloo_ranks_agree_with_one(tmp_path):
     assert np.abs(T2 / T1 - 1.0).max() < 0.05
     m1, m2 = read_map_file(str(one / "map_dir_00.bin")), read_map_file(str(two / "map_dir_00.bin"))
     assert np.abs(m2[:2] / m1[:2] - 1.0).max() < 0.1
+
+
+def test_scattered_light_driver_writes_outcoming(tmp_path):
+    from soc_b200 import asocs
+    from soc_b200.formats import read_outcoming
+    ini, cloud = write_model(str(tmp_path), n=8, bgpac=20000, pspac=66000)
+    cwd = os.getcwd()
+    os.chdir(str(tmp_path))
+    try:
+        asocs.main(["ASOCS.py", "model.ini"], device_factory=OracleDevice)
+    finally:
+        os.chdir(cwd)
+    freq, out = read_outcoming(str(tmp_path / "outcoming.socs"))
+    assert out.shape == (8, 2, 8, 8) and len(freq) == 8
+    assert np.isfinite(out).all() and (out >= 0).all() and out[4:].max() > 0

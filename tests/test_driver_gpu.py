@@ -1,0 +1,92 @@
+"""End-to-end: the ASOC driver on the CUDA library against the same driver on the oracle-backed device.
+Same ini, same input files; output files compared (temperatures, emitted, absorbed, maps)."""
+import os
+
+import numpy as np
+import pytest
+
+from soc_b200 import asoc
+from soc_b200.formats import read_otfile, read_map_file, read_cells_freq_file
+from tests.model import write_model
+from tests.oracle_device import OracleDevice
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(path, factory, **kw):
+    ini, cloud = write_model(str(path), **kw)
+    cwd = os.getcwd()
+    os.chdir(str(path))
+    try:
+        asoc.main(["ASOC.py", "model.ini"], device_factory=factory)
+    finally:
+        os.chdir(cwd)
+    return cloud
+
+
+@pytest.mark.parametrize("octree", [False, True])
+def test_reference_streams_reproduce_the_oracle_run(tmp_path, octree):
+    """REFSTREAMS: same MWC64X streams as the reference => temperatures and maps equal to rounding."""
+    kw = dict(n=8, octree=octree, bgpac=30000, pspac=33000, extra="REFSTREAMS\nCLT\n")
+    _run(tmp_path / "gpu", None, **kw)
+    _run(tmp_path / "cpu", OracleDevice, **kw)
+    Tg, Tc = read_otfile(str(tmp_path / "gpu" / "model.T")), read_otfile(str(tmp_path / "cpu" / "model.T"))
+    # identical streams: nearly every cell agrees to rounding; a few small cells see a packet whose path flipped
+    d = np.abs(Tg - Tc) / Tc.max()
+    assert np.median(d) < 1e-5 and (d > 1e-3).mean() < 0.02 and d.max() < 0.03
+    for idir in range(2):
+        mg = read_map_file(str(tmp_path / "gpu" / ("map_dir_%02d.bin" % idir)))
+        mc = read_map_file(str(tmp_path / "cpu" / ("map_dir_%02d.bin" % idir)))
+        ok = mc[:3] > 0
+        assert np.abs(mg[:3][ok] / mc[:3][ok] - 1.0).max() < 5e-3
+
+
+def test_production_streams_agree_within_noise(tmp_path):
+    kw = dict(n=12, bgpac=400000, pspac=330000, noabsorbed=False, absorbed=True, maps=False)
+    cloud = _run(tmp_path / "gpu", None, **kw)
+    _run(tmp_path / "cpu", OracleDevice, **kw)
+    ag = read_cells_freq_file(str(tmp_path / "gpu" / "abs.data")).astype(np.float64)
+    ac = read_cells_freq_file(str(tmp_path / "cpu" / "abs.data")).astype(np.float64)
+    assert ag.shape == ac.shape == (cloud.CELLS, 8)
+    # total absorbed photons per frequency: ~1e6 packets => well below 1 %
+    tg, tc = ag.sum(axis=0), ac.sum(axis=0)
+    ok = tc > 0
+    assert np.abs(tg[ok] / tc[ok] - 1.0).max() < 0.01
+    # per cell: relative noise of a cell ~ 1/sqrt(hits) ~ 2-3 %
+    f = np.argmax(tc)
+    rel = np.abs(ag[:, f] / ac[:, f] - 1.0)
+    assert np.median(rel) < 0.05 and rel.max() < 0.5
+
+
+def test_temperatures_with_cell_emission(tmp_path):
+    kw = dict(n=10, bgpac=200000, cellpac=10 ** 3 * 20, iterations=2, maps=True)
+    _run(tmp_path / "gpu", None, **kw)
+    _run(tmp_path / "cpu", OracleDevice, **kw)
+    Tg, Tc = read_otfile(str(tmp_path / "gpu" / "model.T")), read_otfile(str(tmp_path / "cpu" / "model.T"))
+    assert np.abs(Tg / Tc - 1.0).mean() < 0.01 and np.abs(Tg / Tc - 1.0).max() < 0.06
+    mg = read_map_file(str(tmp_path / "gpu" / "map_dir_00.bin"))
+    mc = read_map_file(str(tmp_path / "cpu" / "map_dir_00.bin"))
+    assert np.abs(mg[:2] / mc[:2] - 1.0).max() < 0.1
+
+
+def test_scattered_light_driver(tmp_path):
+    from soc_b200 import asocs
+    from soc_b200.formats import read_outcoming
+    res = []
+    for name, fac in (("gpu", None), ("cpu", OracleDevice)):
+        d = tmp_path / name
+        write_model(str(d), n=10, bgpac=200000, pspac=655360)
+        cwd = os.getcwd()
+        os.chdir(str(d))
+        try:
+            asocs.main(["ASOCS.py", "model.ini"], device_factory=fac)
+        finally:
+            os.chdir(cwd)
+        res.append(read_outcoming(str(d / "outcoming.socs"))[1].astype(np.float64))
+    g, c = res
+    for f in range(8):
+        if c[f].sum() > 0:
+            assert abs(g[f].sum() / c[f].sum() - 1.0) < 0.02, f
+    f = int(np.argmax(c.sum(axis=(1, 2, 3))))
+    ok = c[f] > 0.2 * c[f].max()
+    assert np.median(np.abs(g[f][ok] / c[f][ok] - 1.0)) < 0.1

@@ -107,6 +107,7 @@ def _repeat(X, runner_factory, K, key="tabs"):
 STAT_CASES = {
     # name: (cloud, options, runner factory(seed), output key)
     "bg_reg16": (_reg(16), {}, lambda s: run_bg(batch=4, seed=s), "tabs"),
+    "bg_reg16_refgeo": (_reg(16), {}, lambda s: run_bg(batch=4, seed=s), "tabs"),
     "bg_reg16_iso": (_reg(16), {}, lambda s: run_bg(batch=4, seed=s, g=False, tau_s=6.0), "tabs"),
     "bg_oct8_3": (_oct(8, 3), {}, lambda s: run_bg(batch=8, seed=s), "tabs"),
     "bg_oct6_4_int": (_oct(6, 4, 0.25, 8), dict(noabsorbed=0), lambda s: run_bg(batch=8, seed=s), "int"),
@@ -134,6 +135,8 @@ def test_packet_streams_statistical_parity(name):
     O = orc.Oracle(cloud, **opts)
     a = _repeat(O, fac, K, key)
     B = _backend(cloud, backend.RNG_PACKET, **opts)
+    if name.endswith("_refgeo"):
+        B.dev.set_geometry(1)
     b = _repeat(B, fac, K, key)
     chi2, dof, tot, tot_sigma = chi2_per_dof(b, a, min_rel=1e-4)
     assert dof > 300
