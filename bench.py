@@ -108,6 +108,15 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
 def cpu_leg(w, seconds_target=12.0, use_ref=True):
     """Times the reference's CPU implementation of the same step on a bounded sample of its work items.
     Returns packets/s, cell-steps/s, cores, kind, sample description."""
@@ -123,28 +132,32 @@ def cpu_leg(w, seconds_target=12.0, use_ref=True):
     if X is None:
         X = orc.Oracle(cloud, **REF_OPTS)
     cores = X.threads() if kind == "reference" else orc.threads()
-    # sample: a fraction of the work items of each of the two launches, with the job's own BATCH per work item
-    # (the per-work-item MWC64X seeding cost keeps its real share), half of the time budget each
-    rate_guess = 2.0e6 * cores                               # cell-steps/s
-    pk_budget = 0.5 * seconds_target * rate_guess / (1.0 * cloud.NX)
-    g = int(min(w["bg_glob"], max(8 * cores, pk_budget / w["bg_batch"])))
-    gp = int(min(w["ps_glob"], max(8 * cores, pk_budget / w["ps_batch"])))
     (X.set_chunk if kind == "reference" else orc.set_chunk)(4)
     common = dict(abs_=w["kabs"], sca=w["ksca"], dsc=w["dsc"], csc=w["csc"])
-    X.zero(0), X.zero(1)
-    if kind == "reference":
-        X.atomic_count(reset=True)
-    else:
-        s0 = X.counters.steps
-    t0 = time.perf_counter()
-    X.sim_pb(g, 1, g * w["bg_batch"], w["bg_batch"], SEED, w["bg"], w["tw"], **common)
-    X.sim_pb(gp, 0, gp * w["ps_batch"], w["ps_batch"], SEED, 0.0, w["tw"], pspos=w["pspos"], ps=w["ps"], **common)
-    dt = time.perf_counter() - t0
-    packets = g * w["bg_batch"] + gp * w["ps_batch"]
-    if kind == "reference":
-        steps = X.atomic_count() // 2                      # one TABS and one INT update per cell-step
-    else:
-        steps = X.counters.steps - s0
+
+    def sample(g, gp):
+        """g background work items and gp point-source work items, each with the job's own BATCH (so the
+        per-work-item MWC64X seeding keeps its real share).  Returns seconds, packets, cell-steps."""
+        X.zero(0), X.zero(1)
+        if kind == "reference":
+            X.atomic_count(reset=True)
+        else:
+            s0 = X.counters.steps
+        t0 = time.perf_counter()
+        X.sim_pb(g, 1, g * w["bg_batch"], w["bg_batch"], SEED, w["bg"], w["tw"], **common)
+        X.sim_pb(gp, 0, gp * w["ps_batch"], w["ps_batch"], SEED, 0.0, w["tw"], pspos=w["pspos"], ps=w["ps"], **common)
+        dt = time.perf_counter() - t0
+        steps = X.atomic_count() // 2 if kind == "reference" else X.counters.steps - s0   # TABS + INT add per step
+        return dt, g * w["bg_batch"] + gp * w["ps_batch"], steps
+
+    # calibrate on a ~1 s sample, then size the timed sample for `seconds_target`; equal packets from both launches
+    gp = 4 * cores
+    g = max(4 * cores, gp * w["ps_batch"] // w["bg_batch"])
+    dt, pk, _ = sample(g, gp)
+    scale = max(1.0, seconds_target / max(dt, 1e-3))
+    gp = int(min(w["ps_glob"], gp * scale))
+    g = int(min(w["bg_glob"], g * scale))
+    dt, packets, steps = sample(g, gp)
     sample = "%d of %d background work items x %d packets + %d of %d point-source work items x %d packets (%.1f s)" % (
         g, w["bg_glob"], w["bg_batch"], gp, w["ps_glob"], w["ps_batch"], dt)
     return packets / dt, steps / dt, cores, kind, sample
@@ -307,6 +320,7 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = measured_peak()
+        traffic = measured_traffic() if world == 1 else None
         achieved = ksteps * ALG_BYTES_PER_STEP / (kavg * 1e-3) / 1e9
         line = {
             "metric": "photon_packets_per_s", "value": packets / (ms * 1e-3), "unit": "packets/s",
@@ -319,7 +333,8 @@ def run_ours(args):
                     "d2h_bytes_per_step": 4 * n, "ms_per_step": ems / args.steps},
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "sim_stream_kernel<regular> (background launch)",
+                         "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
+                         "kernel": "sim_fast_kernel<DEP_WARP,false> (background launch)",
                          "kernel_ms": kavg, "cell_steps_per_launch": ksteps, "alg_bytes_per_cell_step": ALG_BYTES_PER_STEP,
                          "peak_source": peak_src},
             "stuck_packets": counts[3].item(),
