@@ -45,7 +45,7 @@ struct soc_context {
     bool have_params, have_grid;
     GridDesc G;
     int rng_mode, rank, world;
-    int deposit, refill, agg_steps, geometry;
+    int deposit, refill, agg_steps, geometry, sc_batch;
     uint64_t pow2k[26];
 };
 
@@ -99,7 +99,7 @@ int soc_create(int device_ordinal, soc_context **out) {
     memset(c, 0, sizeof(*c));
     c->device = device_ordinal; c->sms = prop.multiProcessorCount;
     c->rng_mode = SOC_RNG_PACKET; c->rank = 0; c->world = 1;
-    c->deposit = DEP_TILE; c->refill = 8; c->agg_steps = 24;
+    c->deposit = DEP_TILE; c->refill = 8; c->agg_steps = 24; c->sc_batch = 4;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
@@ -314,7 +314,7 @@ static int sim_common(soc_context *c, SimArgs &A, int kind, int batch, float see
     A.rank = c->rank; A.world = c->world;
     long long ms = 100LL * ((long long)c->G.nx + c->G.ny + c->G.nz) << (c->G.levels - 1);
     A.max_steps = (int)(ms > INT_MAX ? INT_MAX : ms);
-    A.deposit = c->deposit; A.refill = c->refill; A.agg_steps = c->agg_steps; A.ref_geometry = c->geometry;
+    A.deposit = c->deposit; A.refill = c->refill; A.agg_steps = c->agg_steps; A.ref_geometry = c->geometry; A.sc_batch = c->sc_batch;
     A.counters = c->counters; A.work = c->counters + 5;
     // stream layouts
     A.mwc.base_offset = seed_to_base(seed);
@@ -399,8 +399,9 @@ int soc_sim_pb(soc_context *c, int source, int packets, int batch, float seed, f
             A.tile_x0 = o[0]; A.tile_y0 = o[1]; A.tile_z0 = o[2];
             A.tile_lo = o[2] * c->G.nx * c->G.ny;
             A.tile_span = SOC_TILE_N * c->G.nx * c->G.ny;
-        } else A.deposit = DEP_WARP;
+        } else A.deposit = (source == 0) ? DEP_WARP : DEP_RED;     // only point-source packets share their first cells
     }
+    if (source != 0 && A.deposit == DEP_WARP) A.deposit = DEP_RED;
     return sim_launch(c, A, "soc_sim_pb");
 }
 
@@ -415,7 +416,7 @@ int soc_sim_hp(soc_context *c, int packets, int batch, float seed, float abs, fl
     // kernel_ASOC.c:878: work items beyond 8*AREA return without simulating anything
     long long items = 8LL * c->G.area < global ? 8LL * c->G.area : global;
     A.nunits = (c->rng_mode == SOC_RNG_REFERENCE) ? global : items * batch;
-    if (A.deposit == DEP_TILE) A.deposit = DEP_WARP;
+    A.deposit = DEP_RED;
     return sim_launch(c, A, "soc_sim_hp");
 }
 
@@ -430,7 +431,7 @@ int soc_sim_cl(soc_context *c, int source, int packets, int batch, float seed, f
     if (c->P.use_emweight && (r = need(c, SOC_BUF_EMWEI, n, "soc_sim_cl")) != SOC_OK) return r;
     if (c->P.use_emweight > 1) return fail(SOC_ERR_UNSUPPORTED, "soc_sim_cl: USE_EMWEIGHT=2 is not implemented");
     A.nunits = (c->rng_mode == SOC_RNG_REFERENCE) ? global : c->G.cells;
-    if (A.deposit == DEP_TILE) A.deposit = DEP_WARP;
+    A.deposit = DEP_RED;
     return sim_launch(c, A, "soc_sim_cl");
 }
 

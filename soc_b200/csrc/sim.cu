@@ -17,6 +17,7 @@
 // the cell) and TABS[cell] (+INT[cell]) through red.global.add.f32; nothing else leaves the SM.
 #include "sim.cuh"
 #include "emit.cuh"
+#include "walk.cuh"
 
 #define FULL 0xffffffffu
 
@@ -459,23 +460,36 @@ __device__ __forceinline__ void fast_from_packet(const SimArgs &A, const Packet 
     if (A.with_abu) f.opt = __ldg(reinterpret_cast<const float2 *>(A.opt) + f.ind);
 }
 
-// Rotate d by the polar angle acos(ct) and a uniform azimuth phi.  Same distribution as Deflect()
-// (kernel_ASOC_aux.c:499-533) -- the azimuth is uniform either way -- without its acos/sincos chain.
-__device__ __forceinline__ void rotate_direction(vec3 &d, float ct, float phi) {
-    float st = sqrtf(fmaxf(0.0f, 1.0f - ct * ct)), sp, cp;
+// New direction after a scattering: rotate d by the polar angle acos(ct) and a uniform azimuth phi -- the same
+// distribution as Deflect() (kernel_ASOC_aux.c:499-533; the azimuth is uniform either way) without its acos /
+// sincos chain -- then the reference's clamp |d_i| >= DEPS and renormalisation (kernel_ASOC.c:508-511).
+// Approximate SFU functions (2 ulp) are enough here: the result is a random direction.
+__device__ __forceinline__ void scatter_rotate(vec3 &d, float ct, float phi) {
+    const float s2 = fmaxf(0.0f, 1.0f - ct * ct);
+    const float st = s2 * rsqrtf(fmaxf(s2, 1.0e-30f));
+    float sp, cp;
     __sincosf(phi, &sp, &cp);
-    float w2 = 1.0f - d.z * d.z;
+    const float w2 = 1.0f - d.z * d.z;
     vec3 n;
     if (w2 > 1.0e-6f) {
-        float iw = rsqrtf(w2);
+        const float iw = rsqrtf(w2);
         n.x = st * (d.x * d.z * cp - d.y * sp) * iw + d.x * ct;
         n.y = st * (d.y * d.z * cp + d.x * sp) * iw + d.y * ct;
         n.z = -st * cp * w2 * iw + d.z * ct;
     } else {
-        float sg = d.z > 0.0f ? 1.0f : -1.0f;
-        n.x = st * cp; n.y = st * sp; n.z = sg * ct;
+        n.x = st * cp; n.y = st * sp; n.z = (d.z > 0.0f) ? ct : -ct;
     }
-    d = n;
+    if (fabsf(n.x) < SOC_DEPS) n.x = SOC_DEPS;
+    if (fabsf(n.y) < SOC_DEPS) n.y = SOC_DEPS;
+    if (fabsf(n.z) < SOC_DEPS) n.z = SOC_DEPS;
+    const float il = rsqrtf(n.x * n.x + n.y * n.y + n.z * n.z);
+    d.x = n.x * il; d.y = n.y * il; d.z = n.z * il;
+}
+// free path of the production kernels: plain -log(u) through the SFU unless step weighting is on
+template <class RNG>
+__device__ __forceinline__ float free_path_fast(const SimArgs &A, RNG &rng, float &photons) {
+    if (A.step_weight <= 0) return -__logf(rng.uniform());
+    return sample_free_path(A, rng, photons);
 }
 
 // DEP: accumulation engine (DepositMode).  GENERAL = false drops the per-cell opacities, the intensity vector,
@@ -493,6 +507,7 @@ __global__ void __launch_bounds__(256, 4) sim_fast_kernel(const __grid_constant_
     const bool abu = GENERAL && A.with_abu;
     FastPk f; f.ind = 0; f.rid = 0; f.eidx = -1;
     bool alive = false, more = true;
+    bool wsc = false;                // the packet sits at a scattering point and waits for the batched scatter block
     int icell = 0, iray = 0, nray = 0;
     float pwei = 1.0f;
     const int refill = A.refill;
@@ -541,7 +556,32 @@ __global__ void __launch_bounds__(256, 4) sim_fast_kernel(const __grid_constant_
         bool sc = false; float rho_n = 0.0f; int nind = 0; bool inb = false; float tmin = 0.0f; int ax = 0;
         float2 opt_n = make_float2(0.0f, 0.0f);
         const bool was_alive = alive;
-        if (alive) {
+        // ---- scatterings, several lanes at a time: the block is long (Philox, table look-up, rotation) and only
+        // ~1 lane in 30 needs it in a given iteration, so lanes wait until A.sc_batch of them are at a scattering
+        // point (or nothing else can run) and then scatter together
+        {
+            const unsigned sm = __ballot_sync(FULL, alive && wsc);
+            if (sm && (__popc(sm) >= A.sc_batch || !__any_sync(FULL, alive && !wsc))) {
+                if (alive && wsc) {
+                    // position inside the cell from the face distances, then a new direction
+                    float fx = (f.dir.x > 0.0f) ? 1.0f - f.tx * fabsf(f.dir.x) : f.tx * fabsf(f.dir.x);
+                    float fy = (f.dir.y > 0.0f) ? 1.0f - f.ty * fabsf(f.dir.y) : f.ty * fabsf(f.dir.y);
+                    float fz = (f.dir.z > 0.0f) ? 1.0f - f.tz * fabsf(f.dir.z) : f.tz * fabsf(f.dir.z);
+                    RngBlock rb(A.phx, f.rid, 0x10000u + (unsigned)f.scat);
+                    f.free_path = free_path_fast(A, rb, f.photons);
+                    float ct = __ldg(A.csc + clampi((int)(rb.uniform() * A.bins), 0, A.bins - 1));
+                    scatter_rotate(f.dir, ct, SOC_TWOPI * rb.uniform());
+                    f.rdx = __fdividef(1.0f, fabsf(f.dir.x)); f.rdy = __fdividef(1.0f, fabsf(f.dir.y)); f.rdz = __fdividef(1.0f, fabsf(f.dir.z));
+                    f.tx = face_distance(fx, f.dir.x, f.rdx);
+                    f.ty = face_distance(fy, f.dir.y, f.rdy);
+                    f.tz = face_distance(fz, f.dir.z, f.rdz);
+                    f.tau = 0.0f;
+                    wsc = false;
+                }
+            }
+        }
+        const bool run = alive && !wsc;
+        if (run) {
             // which face comes first, and the cell behind it; its density is requested right away
             tmin = fminf(f.tx, fminf(f.ty, f.tz));
             ax = (f.tx <= f.ty && f.tx <= f.tz) ? 0 : ((f.ty <= f.tz) ? 1 : 2);
@@ -606,24 +646,11 @@ __global__ void __launch_bounds__(256, 4) sim_fast_kernel(const __grid_constant_
                 if (!in_tile) red_add(&A.acc[oind], delta);
             }
         }
-        if (alive) {
+        if (run && alive) {
             f.tx -= tmin; f.ty -= tmin; f.tz -= tmin;
             if (sc) {
-                // position inside the cell from the face distances, then a new direction
-                float fx = (f.dir.x > 0.0f) ? 1.0f - f.tx * fabsf(f.dir.x) : f.tx * fabsf(f.dir.x);
-                float fy = (f.dir.y > 0.0f) ? 1.0f - f.ty * fabsf(f.dir.y) : f.ty * fabsf(f.dir.y);
-                float fz = (f.dir.z > 0.0f) ? 1.0f - f.tz * fabsf(f.dir.z) : f.tz * fabsf(f.dir.z);
-                RngBlock rb(A.phx, f.rid, 0x10000u + (unsigned)f.scat);
-                f.free_path = sample_free_path(A, rb, f.photons);
-                float ct = A.csc[clampi((int)(rb.uniform() * A.bins), 0, A.bins - 1)];
-                rotate_direction(f.dir, ct, SOC_TWOPI * rb.uniform());
-                fix_direction(f.dir);
-                f.rdx = 1.0f / fabsf(f.dir.x); f.rdy = 1.0f / fabsf(f.dir.y); f.rdz = 1.0f / fabsf(f.dir.z);
-                f.tx = face_distance(fx, f.dir.x, f.rdx);
-                f.ty = face_distance(fy, f.dir.y, f.rdy);
-                f.tz = face_distance(fz, f.dir.z, f.rdz);
-                f.tau = 0.0f;
-                if (!cl && f.scat > 20) alive = false;
+                wsc = true;
+                if (!cl && f.scat > 20) { alive = false; wsc = false; }
             } else {
                 if (ax == 0)      { f.ix += (f.dir.x > 0.0f) ? 1 : -1; f.tx = f.rdx; }
                 else if (ax == 1) { f.iy += (f.dir.y > 0.0f) ? 1 : -1; f.ty = f.rdy; }
@@ -632,12 +659,177 @@ __global__ void __launch_bounds__(256, 4) sim_fast_kernel(const __grid_constant_
                 if (abu) f.opt = opt_n;
                 alive = inb;
             }
-            if (f.nstep > A.max_steps) { alive = false; cnt.stuck++; }
+            if (f.nstep > A.max_steps) { alive = false; wsc = false; cnt.stuck++; }
         }
         if (was_alive && !alive) { cnt.steps += f.nstep; cnt.scat += min(f.scat, 20); }     // packet finished
     }
     tile_end(A, tile);
     flush_counters(A, cnt);
+}
+
+// =================================================================================================================
+// Walk kernel: the production path on octree clouds (LEVELS > 1).  Same persistent-warp / refill / Philox /
+// scratch-accumulator design as the fast kernel; the stepping is the incremental octree walk of walk.cuh, taken
+// one hop (climb / cross / descend) per loop iteration so that lanes with long climbs do not idle the warp.
+// =================================================================================================================
+template <int DEP, bool GENERAL>
+__global__ void __launch_bounds__(256, 4) sim_walk_kernel(const __grid_constant__ SimArgs A) {
+    const GridDesc &G = A.G;
+    Counters cnt = { 0, 0, 0, 0 };
+    const int lane = threadIdx.x & 31;
+    const long long nlocal = (A.nunits - A.rank + A.world - 1) / A.world;
+    const bool cl = GENERAL && A.kind == SIM_CL;
+    const bool abu = GENERAL && A.with_abu;
+    Walker w; w.ind = -1; w.level = 0;
+    int phase = WALK_LEAF, ax = 0;
+    float photons = 0.0f, free_path = 0.0f, tau = 0.0f;
+    int scat = 0, nstep = 0, eidx = -1;
+    unsigned long long rid = 0;
+    bool alive = false, more = true;
+    int icell = 0, iray = 0, nray = 0;
+    float pwei = 1.0f;
+    const int refill = A.refill;
+    for (;;) {
+        unsigned idle = __ballot_sync(FULL, !alive);
+        if (idle == FULL || (__popc(idle) >= refill && __any_sync(FULL, more))) {
+            bool need = !alive && more && iray >= nray;
+            unsigned nm = __ballot_sync(FULL, need);
+            unsigned long long q = 0;
+            bool got = false;
+            if (nm) {
+                int leader = __ffs(nm) - 1;
+                unsigned long long base = 0;
+                if (lane == leader) base = atomicAdd(A.work, (unsigned long long)__popc(nm));
+                base = __shfl_sync(FULL, base, leader);
+                if (need) {
+                    long long u = (long long)base + __popc(nm & ((1u << lane) - 1u));
+                    if (u >= nlocal) more = false;
+                    else { q = (unsigned long long)u * A.world + A.rank; got = true; }
+                }
+            }
+            if (got && cl) { icell = (int)q; iray = 0; nray = cl_rays(A, icell, pwei); got = false; }
+            if (cl && !alive && iray < nray) {
+                q = (unsigned long long)(unsigned)icell | ((unsigned long long)(unsigned)iray << 32);
+                iray++; got = true;
+            }
+            if (got) {
+                RngPhilox rng; rng.seed(A.phx, q);
+                Packet pk; pk.ind = -1; pk.level = 0; pk.eidx = -1; pk.rho = 0.0f;
+                if (GENERAL && cl) emit_cl(A, rng, icell, pwei, pk);
+                else {
+                    int id = (int)(q / (unsigned)A.batch), III = (int)(q % (unsigned)A.batch);
+                    if (A.kind == SIM_PS)      emit_ps<SimArgs, RngPhilox, true>(A, rng, III, pk);
+                    else if (A.kind == SIM_BG) emit_bg<SimArgs, RngPhilox, true>(A, rng, id, pk);
+                    else                       emit_hp<RngPhilox, true>(A, rng, pk);
+                }
+                start_packet(A, rng, pk, A.kind != SIM_HP);
+                cnt.packets++;
+                alive = pk.ind >= 0;
+                if (alive) {
+                    walker_init<true>(G, w, pk.pos, pk.dir, pk.level, pk.ind, pk.rho);
+                    photons = pk.photons; free_path = pk.free_path; tau = 0.0f; scat = 0; nstep = 0; eidx = pk.eidx; rid = q;
+                    phase = WALK_LEAF;
+                }
+            }
+            if (!__any_sync(FULL, alive || more || iray < nray)) break;
+        }
+        // scatterings, several lanes at a time (see sim_fast_kernel)
+        {
+            const unsigned sm = __ballot_sync(FULL, alive && phase == WALK_SCATTER);
+            if (sm && (__popc(sm) >= A.sc_batch || !__any_sync(FULL, alive && phase != WALK_SCATTER))) {
+                if (alive && phase == WALK_SCATTER) {
+                    float fx, fy, fz;
+                    walker_fraction(w, fx, fy, fz);
+                    RngBlock rb(A.phx, rid, 0x10000u + (unsigned)scat);
+                    free_path = free_path_fast(A, rb, photons);
+                    float ct = __ldg(A.csc + clampi((int)(rb.uniform() * A.bins), 0, A.bins - 1));
+                    vec3 nd = w.d;
+                    scatter_rotate(nd, ct, SOC_TWOPI * rb.uniform());
+                    walker_set_direction(w, nd, fx, fy, fz);
+                    tau = 0.0f;
+                    phase = WALK_LEAF;
+                }
+            }
+        }
+        bool d = false, sc = false;
+        float delta = 0.0f, ds = 0.0f, tmin = 0.0f;
+        int oind = 0;
+        const bool was_alive = alive;
+        const bool ready = alive && phase == WALK_LEAF;
+        if (ready) {
+            // physics of the current leaf
+            oind = G.off[w.level] + w.ind;
+            tmin = fminf(w.tx, fminf(w.ty, w.tz));
+            ax = (w.tx <= w.ty && w.tx <= w.tz) ? 0 : ((w.ty <= w.tz) ? 1 : 2);
+            ds = fmaxf(tmin, 0.0f);
+            float kabs = A.kabs, ksca = A.ksca;
+            if (abu) { float2 o = __ldg(reinterpret_cast<const float2 *>(A.opt) + oind); kabs = o.x; ksca = o.y; }
+            const float dtau = ds * w.rho * ksca;
+            sc = free_path < tau + dtau;
+            d = true;
+            if (sc) {
+                scat++;
+                if (cl && scat > 20) { d = false; alive = false; }
+                ds = fminf(ds, (free_path - tau) / (ksca * w.rho));
+            } else tau += dtau;
+            const float tauA = ds * w.rho * kabs;
+            const float e = expf(-tauA);
+            delta = (tauA > SOC_TAULIM) ? (photons * (1.0f - e)) : (photons * tauA * (1.0f - 0.5f * tauA));
+            if (d) { photons *= e; nstep++; }
+        }
+        if (GENERAL && (A.save_int2 || A.with_ali)) {
+            if (d) {
+                if (A.with_ali && oind == eidx) red_add(&A.xab[oind], delta * A.tw);
+                else red_add(&A.acc[oind], delta);
+                if (A.save_int2) {
+                    red_add(&A.intx[oind], delta * w.d.x); red_add(&A.inty[oind], delta * w.d.y); red_add(&A.intz[oind], delta * w.d.z);
+                }
+            }
+        } else if (DEP == DEP_RED) {
+            if (d) red_add(&A.acc[oind], delta);
+        } else {
+            if (__any_sync(FULL, d && nstep < A.agg_steps)) {
+                unsigned act = __ballot_sync(FULL, d);
+                if (d) {
+                    unsigned peers = __match_any_sync(act, oind);
+                    if (peers != (1u << lane)) {
+                        delta = reduce_peers(peers, delta, lane);
+                        if (lane != __ffs(peers) - 1) d = false;
+                    }
+                }
+            }
+            if (d) red_add(&A.acc[oind], delta);
+        }
+        if (ready && alive) {
+            if (sc) {
+                w.tx -= ds; w.ty -= ds; w.tz -= ds;
+                phase = WALK_SCATTER;
+                if (!cl && scat > 20) { alive = false; phase = WALK_LEAF; }
+            } else {
+                w.tx -= tmin; w.ty -= tmin; w.tz -= tmin;
+                phase = WALK_CROSS;
+            }
+            if (nstep > A.max_steps) { alive = false; phase = WALK_LEAF; cnt.stuck++; }
+        }
+        // navigation, one hop of each kind per iteration: climb, try to cross, descend
+        if (alive && phase == WALK_CLIMB) { nav_climb(G, w, ax); phase = WALK_CROSS; }
+        if (alive && phase == WALK_CROSS) { phase = nav_cross(G, w, ax); if (w.ind < 0) alive = false; }
+        if (alive && phase == WALK_DESCEND) phase = nav_descend(G, w, ax);
+        if (was_alive && !alive) { cnt.steps += nstep; cnt.scat += min(scat, 20); }
+    }
+    flush_counters(A, cnt);
+}
+
+static void launch_walk(const SimArgs &A, int blocks, int threads, cudaStream_t stream) {
+    const bool general = A.with_abu || A.save_int2 || A.with_ali || A.kind == SIM_CL;
+    const bool red = (A.save_int2 || A.with_ali) || A.deposit == DEP_RED;
+    if (general) {
+        if (red) sim_walk_kernel<DEP_RED, true><<<blocks, threads, 0, stream>>>(A);
+        else     sim_walk_kernel<DEP_WARP, true><<<blocks, threads, 0, stream>>>(A);
+    } else {
+        if (red) sim_walk_kernel<DEP_RED, false><<<blocks, threads, 0, stream>>>(A);
+        else     sim_walk_kernel<DEP_WARP, false><<<blocks, threads, 0, stream>>>(A);
+    }
 }
 
 // TABS += acc * TW*ADHOC ; INT += acc ; acc = 0   (float4 streams; acc is all-zero again afterwards)
@@ -694,6 +886,7 @@ void launch_sim(const SimArgs &A, int rng_mode, int blocks, int threads, cudaStr
     } else {
         if (!oct && !A.ref_geometry) launch_fast(A, blocks, threads, stream);
         else if (!oct) sim_stream_kernel<false, false><<<blocks, threads, 0, stream>>>(A);
+        else if (!A.ref_geometry) launch_walk(A, blocks, threads, stream);
         else if (!dbl) sim_stream_kernel<true, false><<<blocks, threads, 0, stream>>>(A);
         else           sim_stream_kernel<true, true><<<blocks, threads, 0, stream>>>(A);
     }
@@ -707,8 +900,7 @@ int sim_blocks_per_sm(int rng_mode, bool octree, bool dbl, int threads) {
         else           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sim_item_kernel<RngMwcItem, true, true>, threads, 0);
     } else {
         if (!octree)   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sim_fast_kernel<DEP_TILE, true>, threads, 0);
-        else if (!dbl) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sim_stream_kernel<true, false>, threads, 0);
-        else           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sim_stream_kernel<true, true>, threads, 0);
+        else           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sim_walk_kernel<DEP_WARP, true>, threads, 0);
     }
     return n > 0 ? n : 1;
 }
