@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include <climits>
 #include <new>
@@ -99,7 +100,8 @@ int soc_create(int device_ordinal, soc_context **out) {
     memset(c, 0, sizeof(*c));
     c->device = device_ordinal; c->sms = prop.multiProcessorCount;
     c->rng_mode = SOC_RNG_PACKET; c->rank = 0; c->world = 1;
-    c->deposit = DEP_TILE; c->refill = 8; c->agg_steps = 24; c->sc_batch = 4;
+    c->deposit = DEP_TILE; c->refill = 8; c->agg_steps = 24; c->sc_batch = 0;        // 0 = by grid type
+    if (const char *e = getenv("SOC_SC_BATCH")) { int v = atoi(e); if (v >= 1 && v <= 32) c->sc_batch = v; }   // tuning knob
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
@@ -314,7 +316,7 @@ static int sim_common(soc_context *c, SimArgs &A, int kind, int batch, float see
     A.rank = c->rank; A.world = c->world;
     long long ms = 100LL * ((long long)c->G.nx + c->G.ny + c->G.nz) << (c->G.levels - 1);
     A.max_steps = (int)(ms > INT_MAX ? INT_MAX : ms);
-    A.deposit = c->deposit; A.refill = c->refill; A.agg_steps = c->agg_steps; A.ref_geometry = c->geometry; A.sc_batch = c->sc_batch;
+    A.deposit = c->deposit; A.refill = c->refill; A.agg_steps = c->agg_steps; A.ref_geometry = c->geometry; A.sc_batch = c->sc_batch > 0 ? c->sc_batch : (c->G.levels > 1 ? 3 : 1);
     A.counters = c->counters; A.work = c->counters + 5;
     // stream layouts
     A.mwc.base_offset = seed_to_base(seed);
@@ -399,9 +401,8 @@ int soc_sim_pb(soc_context *c, int source, int packets, int batch, float seed, f
             A.tile_x0 = o[0]; A.tile_y0 = o[1]; A.tile_z0 = o[2];
             A.tile_lo = o[2] * c->G.nx * c->G.ny;
             A.tile_span = SOC_TILE_N * c->G.nx * c->G.ny;
-        } else A.deposit = (source == 0) ? DEP_WARP : DEP_RED;     // only point-source packets share their first cells
+        } else A.deposit = DEP_WARP;
     }
-    if (source != 0 && A.deposit == DEP_WARP) A.deposit = DEP_RED;
     return sim_launch(c, A, "soc_sim_pb");
 }
 
@@ -416,7 +417,7 @@ int soc_sim_hp(soc_context *c, int packets, int batch, float seed, float abs, fl
     // kernel_ASOC.c:878: work items beyond 8*AREA return without simulating anything
     long long items = 8LL * c->G.area < global ? 8LL * c->G.area : global;
     A.nunits = (c->rng_mode == SOC_RNG_REFERENCE) ? global : items * batch;
-    A.deposit = DEP_RED;
+    if (A.deposit == DEP_TILE) A.deposit = DEP_WARP;
     return sim_launch(c, A, "soc_sim_hp");
 }
 
@@ -431,7 +432,7 @@ int soc_sim_cl(soc_context *c, int source, int packets, int batch, float seed, f
     if (c->P.use_emweight && (r = need(c, SOC_BUF_EMWEI, n, "soc_sim_cl")) != SOC_OK) return r;
     if (c->P.use_emweight > 1) return fail(SOC_ERR_UNSUPPORTED, "soc_sim_cl: USE_EMWEIGHT=2 is not implemented");
     A.nunits = (c->rng_mode == SOC_RNG_REFERENCE) ? global : c->G.cells;
-    A.deposit = DEP_RED;
+    if (A.deposit == DEP_TILE) A.deposit = DEP_WARP;
     return sim_launch(c, A, "soc_sim_cl");
 }
 
