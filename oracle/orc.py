@@ -25,7 +25,7 @@ def build(force=False):
 class OrcParams(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "nx", "ny", "nz", "levels", "cells", "bins", "no_ps", "ps_method", "with_abu", "with_ali", "noabsorbed",
-        "save_intensity", "use_emweight", "hpbg_weighted", "ffs", "step_weight", "level_threshold", "reserved0")] + \
+        "save_intensity", "use_emweight", "hpbg_weighted", "ffs", "step_weight", "level_threshold", "sca_exact_level")] + \
         [(n, C.c_float) for n in ("sw_a", "sw_b", "length", "factor", "adhoc", "reserved1")]
 
 
@@ -92,6 +92,7 @@ class Oracle:
         P.ffs = opts.get("ffs", 1)
         P.step_weight = opts.get("step_weight", -1)
         P.level_threshold = opts.get("level_threshold", 0)
+        P.sca_exact_level = opts.get("sca_exact_level", 0)
         P.sw_a, P.sw_b = opts.get("sw_a", 0.0), opts.get("sw_b", 0.0)
         P.length = float("%.5e" % (gl * 3.08567758e+18))     # -D LENGTH=%.5ef (ASOC.py:347,356)
         P.factor = 1.0e20

@@ -889,7 +889,10 @@ static void sca_propagate(sca_t *S, rng_t *r, v3 pos, v3 dir, int level, int ind
         if (P->with_abu) { kabs = B->opt[2 * (long)oind]; ksca = B->opt[2 * (long)oind + 1]; }
         else             { kabs = B->abs; ksca = B->sca; }
         dx = dtau / (ksca * N->dens[oind]);
-        dx = ldexpf(dx, level);                          /* sic: level of the *next* cell, kernel_ASOC_sca.c:958,1797 */
+        /* sic: the reference converts with the level of the *next* cell (kernel_ASOC_sca.c:958,1797), which displaces
+           the scattering point at refinement boundaries; sca_exact_level=1 is the geometrically exact variant that the
+           tests use as the expectation for the production CUDA kernel */
+        dx = ldexpf(dx, P->sca_exact_level ? level0 : level);
         pos0.x += dx * dir.x; pos0.y += dx * dir.y; pos0.z += dx * dir.z;
         photons *= expf(-free_path * kabs / ksca);
         /* peel-off towards every observer (orthographic maps): kernel_ASOC_sca.c:1010-1046 / 1849-1885 */

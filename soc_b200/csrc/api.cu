@@ -551,7 +551,7 @@ static int sca_common(soc_context *c, ScaArgs &S, int kind, int batch, float see
     S.centre = { centre[0], centre[1], centre[2] };
     S.kind = kind; S.batch = batch; S.global = global; S.ndir = ndir; S.npx = npix_x; S.npy = npix_y;
     S.bins = P.bins; S.no_ps = P.no_ps; S.ps_method = P.ps_method; S.with_abu = P.with_abu; S.ffs = P.ffs;
-    S.rank = c->rank; S.world = c->world;
+    S.rank = c->rank; S.world = c->world; S.ref_geometry = c->geometry; S.ev_batch = c->sc_batch > 0 ? c->sc_batch : 3;
     long long ms = 100LL * ((long long)c->G.nx + c->G.ny + c->G.nz) << (c->G.levels - 1);
     S.max_steps = (int)(ms > INT_MAX ? INT_MAX : ms);
     S.counters = c->counters; S.work = c->counters + 5;
@@ -564,7 +564,7 @@ static int sca_common(soc_context *c, ScaArgs &S, int kind, int batch, float see
 }
 
 static int sca_launch(soc_context *c, ScaArgs &S, const char *who) {
-    const int threads = 128;
+    const int threads = (c->rng_mode != SOC_RNG_REFERENCE && !c->geometry) ? 256 : 128;
     long long local = (S.nunits - S.rank + S.world - 1) / S.world;
     int blocks;
     if (c->rng_mode == SOC_RNG_REFERENCE) blocks = (int)((local + threads - 1) / threads);

@@ -159,6 +159,19 @@ struct RngPhilox {
     __device__ __forceinline__ float uniform() { return __uint2float_rn(next()) * 2.3283064365386963e-10f; }
 };
 
+struct RngBlock {                    // four uniforms from one Philox block
+    uint32_t a, b, c, d; int k;
+    __device__ __forceinline__ RngBlock(const PhiloxLaunch &L, unsigned long long id, unsigned blk) {
+        philox4x32_10((uint32_t)id, (uint32_t)(id >> 32), blk, L.tag, L.k0, L.k1, a, b, c, d);
+        k = 0;
+    }
+    __device__ __forceinline__ float uniform() {
+        uint32_t v = (k == 0) ? a : ((k == 1) ? b : ((k == 2) ? c : d));
+        k++;
+        return u32_to_unit(v);
+    }
+};
+
 // ---- grid navigation ------------------------------------------------------------------------------------
 // IndexG (kernel_ASOC_aux.c:131-165 / kernel_ASOC_map.c:187-220): global position -> leaf (level, ind);
 // converts p to level-local coordinates.  Returns the leaf density through `rho`.
@@ -320,6 +333,31 @@ __device__ __forceinline__ void scatter_direction(vec3 &d, const float *__restri
     fix_direction(d);
 }
 
+// New direction after a scattering: rotate d by the polar angle acos(ct) and a uniform azimuth phi -- the same
+// distribution as Deflect() (kernel_ASOC_aux.c:499-533; the azimuth is uniform either way) without its acos /
+// sincos chain -- then the reference's clamp |d_i| >= DEPS and renormalisation (kernel_ASOC.c:508-511).
+// Approximate SFU functions (2 ulp) are enough here: the result is a random direction.
+__device__ __forceinline__ void scatter_rotate(vec3 &d, float ct, float phi) {
+    const float s2 = fmaxf(0.0f, 1.0f - ct * ct);
+    const float st = s2 * rsqrtf(fmaxf(s2, 1.0e-30f));
+    float sp, cp;
+    __sincosf(phi, &sp, &cp);
+    const float w2 = 1.0f - d.z * d.z;
+    vec3 n;
+    if (w2 > 1.0e-6f) {
+        const float iw = rsqrtf(w2);
+        n.x = st * (d.x * d.z * cp - d.y * sp) * iw + d.x * ct;
+        n.y = st * (d.y * d.z * cp + d.x * sp) * iw + d.y * ct;
+        n.z = -st * cp * w2 * iw + d.z * ct;
+    } else {
+        n.x = st * cp; n.y = st * sp; n.z = (d.z > 0.0f) ? ct : -ct;
+    }
+    if (fabsf(n.x) < SOC_DEPS) n.x = SOC_DEPS;
+    if (fabsf(n.y) < SOC_DEPS) n.y = SOC_DEPS;
+    if (fabsf(n.z) < SOC_DEPS) n.z = SOC_DEPS;
+    const float il = rsqrtf(n.x * n.x + n.y * n.y + n.z * n.z);
+    d.x = n.x * il; d.y = n.y * il; d.z = n.z * il;
+}
 // ---- Healpix, RING scheme (kernel_ASOC_aux.c:945-1026; map flavour kernel_ASOC_map.c:59-140) ---------------
 __device__ inline int ang2pix_ring(int nside, float phi, float theta) {
     int nl2, nl4, ncap, npix, jp, jm, ipix1, ir, ip, kshift;

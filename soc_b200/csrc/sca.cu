@@ -12,6 +12,7 @@
 // per-cell opacities); per peel-off ray it does one red.global.add.f32 into the image.
 #include "sca.cuh"
 #include "emit.cuh"
+#include "walk.cuh"
 
 #define FULL 0xffffffffu
 
@@ -207,6 +208,165 @@ __global__ void __launch_bounds__(128) sca_stream_kernel(const __grid_constant__
     flush(S, cnt);
 }
 
+// =================================================================================================================
+// Production kernel: the three kinds of rays walk with the incremental octree walker of walk.cuh (regular grids
+// are the LEVELS == 1 case), one hop per iteration.  The packet's scattering point is kept as (cell, fractional
+// position, direction); look-ahead and peel-off rays are started from it with walker_set_direction().  The image
+// pixel of a peel-off ray follows from the scattering point alone: the exit point differs from it by a multiple of
+// the observer direction, which is perpendicular to the image axes RA and DE.
+// =================================================================================================================
+struct ScatterPoint {
+    float fx, fy, fz;          // fractional position inside the cell
+    vec3 dir;                  // packet direction (before the next scattering)
+    vec3 gpos;                 // root-grid position (for the image pixel), advanced along the walk
+    float rho;
+    int level, ind, ix, iy, iz;
+};
+
+__device__ __forceinline__ void ray_from_point(Walker &w, const ScatterPoint &k, const vec3 &dir) {
+    w.level = k.level; w.ind = k.ind; w.ix = k.ix; w.iy = k.iy; w.iz = k.iz; w.rho = k.rho;
+    walker_set_direction(w, dir, k.fx, k.fy, k.fz);
+}
+
+__device__ __forceinline__ float uniform_fast_log(float u) { return -__logf(u); }
+
+template <bool OCT>
+__global__ void __launch_bounds__(256, 3) sca_walk_kernel(const __grid_constant__ ScaArgs S) {
+    const GridDesc &G = S.G;
+    ScaCounters cnt = { 0, 0, 0, 0, 0 };
+    const int lane = threadIdx.x & 31;
+    const long long nlocal = (S.nunits - S.rank + S.world - 1) / S.world;
+    Walker w; w.ind = -1; w.level = 0;
+    ScatterPoint k;
+    int mode = RAY_IDLE, phase = WALK_LEAF, ax = 0, idir = 0, scat = 0, nstep = 0, nevent = 0;
+    float photons = 0.0f, free_path = 0.0f, tau = 0.0f;
+    unsigned long long rid = 0;
+    bool more = true;
+    for (;;) {
+        unsigned idle = __ballot_sync(FULL, mode == RAY_IDLE);
+        if (idle == FULL || (__popc(idle) >= 8 && __any_sync(FULL, more))) {
+            bool need = mode == RAY_IDLE && more;
+            unsigned nm = __ballot_sync(FULL, need);
+            if (nm) {
+                int leader = __ffs(nm) - 1;
+                unsigned long long base = 0;
+                if (lane == leader) base = atomicAdd(S.work, (unsigned long long)__popc(nm));
+                base = __shfl_sync(FULL, base, leader);
+                if (need) {
+                    long long u = (long long)base + __popc(nm & ((1u << lane) - 1u));
+                    if (u >= nlocal) more = false;
+                    else {
+                        rid = (unsigned long long)u * S.world + S.rank;
+                        RngPhilox rng; rng.seed(S.phx, rid);
+                        Packet pk; pk.ind = -1; pk.level = 0; pk.rho = 0.0f;
+                        emit_packet<RngPhilox, OCT>(S, rng, (int)(rid / (unsigned)S.batch), (int)(rid % (unsigned)S.batch), pk);
+                        cnt.packets++;
+                        photons = pk.photons; scat = 0; nstep = 0; nevent = 0; tau = 0.0f; phase = WALK_LEAF;
+                        if (pk.ind >= 0) {
+                            k.level = pk.level; k.ind = pk.ind; k.rho = pk.rho; k.dir = pk.dir;
+                            k.fx = pk.pos.x - floorf(pk.pos.x); k.fy = pk.pos.y - floorf(pk.pos.y); k.fz = pk.pos.z - floorf(pk.pos.z);
+                            int root = pk.ind;
+                            if (OCT) for (int l = pk.level; l > 0; l--) root = G.par[G.off[l] + root - G.nxyz];
+                            k.ix = root % G.nx; k.iy = (root / G.nx) % G.ny; k.iz = root / (G.nx * G.ny);
+                            k.gpos = pk.pos;
+                            if (OCT) root_position(G, k.gpos, pk.level, pk.ind);
+                            ray_from_point(w, k, k.dir);
+                            if (S.ffs > 0) mode = RAY_FFS;
+                            else { free_path = uniform_fast_log(rng.uniform()); mode = RAY_MAIN; }
+                        }
+                    }
+                }
+            }
+            if (!__any_sync(FULL, mode != RAY_IDLE || more)) break;
+        }
+        // ---- rays that have reached the surface, several lanes at a time (the block is long and rare per lane) ----
+        const unsigned em = __ballot_sync(FULL, mode != RAY_IDLE && phase == WALK_END);
+        if (em && (__popc(em) >= S.ev_batch || !__any_sync(FULL, mode != RAY_IDLE && phase != WALK_END)))
+        if (mode != RAY_IDLE && phase == WALK_END) {
+            phase = WALK_LEAF; nstep = 0;
+            if (mode == RAY_PEEL) {                                  // kernel_ASOC_sca.c:1010-1046 / 1849-1885
+                cnt.peels++;
+                const vec3 od = w.d;
+                float cos_theta = clampf(k.dir.x * od.x + k.dir.y * od.y + k.dir.z * od.z, -0.999f, +0.999f);
+                float delta = photons * __expf(-tau) * __ldg(S.dsc + clampi((int)(S.bins * (1.0f + cos_theta) * 0.5f), 0, S.bins - 1));
+                vec3 p = { k.gpos.x - S.centre.x, k.gpos.y - S.centre.y, k.gpos.z - S.centre.z };
+                const float *ra = S.ora + 3 * idir, *de = S.ode + 3 * idir;
+                int i = (int)((0.5f * S.npx - 0.00005f) + (p.x * ra[0] + p.y * ra[1] + p.z * ra[2]) / S.map_dx);
+                int j = (int)((0.5f * S.npy - 0.00005f) + (p.x * de[0] + p.y * de[1] + p.z * de[2]) / S.map_dx);
+                if (i >= 0 && j >= 0 && i < S.npx && j < S.npy) atomicAdd(&S.out[i + idir * S.npx * S.npy + j * S.npx], delta);
+                idir++;
+                tau = 0.0f;
+                if (idir < S.ndir) {
+                    vec3 nd = { S.odir[3 * idir], S.odir[3 * idir + 1], S.odir[3 * idir + 2] };
+                    ray_from_point(w, k, nd);
+                } else if (scat == 30) mode = RAY_IDLE;               // MAX_SCATTERINGS, kernel_ASOC_sca.c:5
+                else {
+                    RngBlock rb(S.phx, rid, 0x10000u + (unsigned)(nevent++));
+                    float ct = __ldg(S.csc + clampi((int)(rb.uniform() * S.bins), 0, S.bins - 1));
+                    vec3 nd = k.dir;
+                    scatter_rotate(nd, ct, SOC_TWOPI * rb.uniform());
+                    free_path = uniform_fast_log(rb.uniform());
+                    k.dir = nd;
+                    ray_from_point(w, k, nd);
+                    mode = RAY_MAIN;
+                }
+            } else if (mode == RAY_FFS) {                            // kernel_ASOC_sca.c:888-910 / 1720-1750
+                RngBlock rb(S.phx, rid, 0x10000u + (unsigned)(nevent++));
+                float W;
+                if (S.flavour == 0) { W = -expm1f(-tau); free_path = -logf(1.0f - W * rb.uniform()); }
+                else                { W = 1.0f - (float)exp(-(double)tau); free_path = (float)(-log(1.0 - (double)(W * rb.uniform()))); }
+                photons *= W;
+                mode = (tau < 1.0e-22f) ? RAY_IDLE : RAY_MAIN;
+                tau = 0.0f;
+                ray_from_point(w, k, k.dir);
+            } else mode = RAY_IDLE;                                   // the packet itself has left the cloud
+        }
+        // ---- one cell of whichever ray the lane is tracing -----------------------------------------------------
+        const bool ready = mode != RAY_IDLE && phase == WALK_LEAF;
+        if (ready) {
+            const int oind = OCT ? G.off[w.level] + w.ind : w.ind;
+            const float tmin = fminf(w.tx, fminf(w.ty, w.tz));
+            ax = (w.tx <= w.ty && w.tx <= w.tz) ? 0 : ((w.ty <= w.tz) ? 1 : 2);
+            float ds = fmaxf(tmin, 0.0f);
+            float kabs = S.kabs, ksca = S.ksca;
+            if (S.with_abu) { float2 o = __ldg(reinterpret_cast<const float2 *>(S.opt) + oind); kabs = o.x; ksca = o.y; }
+            cnt.steps++; nstep++;
+            bool go = true;
+            if (mode == RAY_PEEL) tau += ds * w.rho * (kabs + ksca);
+            else if (mode == RAY_FFS) tau += ds * w.rho * ksca;
+            else {
+                const float dtau = ds * w.rho * ksca;
+                if (free_path < tau + dtau) {
+                    // scattering inside this cell: remember the point, start the peel-off rays
+                    ds = fminf(ds, (free_path - tau) / (ksca * w.rho));
+                    w.tx -= ds; w.ty -= ds; w.tz -= ds;
+                    walker_fraction(w, k.fx, k.fy, k.fz);
+                    k.level = w.level; k.ind = w.ind; k.ix = w.ix; k.iy = w.iy; k.iz = w.iz; k.rho = w.rho; k.dir = w.d;
+                    k.gpos.x += ds * w.d.x; k.gpos.y += ds * w.d.y; k.gpos.z += ds * w.d.z;
+                    photons *= __expf(-free_path * kabs / ksca);
+                    scat++; cnt.scat++;
+                    idir = 0; mode = RAY_PEEL; tau = 0.0f; nstep = 0;
+                    vec3 od = { S.odir[0], S.odir[1], S.odir[2] };
+                    ray_from_point(w, k, od);
+                    go = false;
+                } else {
+                    tau += dtau;
+                    k.gpos.x += ds * w.d.x; k.gpos.y += ds * w.d.y; k.gpos.z += ds * w.d.z;
+                }
+            }
+            if (go) { w.tx -= tmin; w.ty -= tmin; w.tz -= tmin; phase = WALK_CROSS; }
+            if (nstep > S.max_steps) { mode = RAY_IDLE; phase = WALK_LEAF; cnt.stuck++; }
+        }
+        // ---- navigation: one hop of each kind ------------------------------------------------------------------
+        if (mode != RAY_IDLE) {
+            if (OCT && phase == WALK_CLIMB) { nav_climb(G, w, ax); phase = WALK_CROSS; }
+            if (phase == WALK_CROSS) { phase = nav_cross(G, w, ax); if (w.ind < 0) phase = WALK_END; }
+            if (OCT && phase == WALK_DESCEND) phase = nav_descend(G, w, ax);
+        }
+    }
+    flush(S, cnt);
+}
+
 }  // namespace
 
 void launch_sca(const ScaArgs &S, int rng_mode, int blocks, int threads, cudaStream_t stream) {
@@ -215,6 +375,9 @@ void launch_sca(const ScaArgs &S, int rng_mode, int blocks, int threads, cudaStr
         if (!oct)      sca_item_kernel<false, false><<<blocks, threads, 0, stream>>>(S);
         else if (!dbl) sca_item_kernel<true, false><<<blocks, threads, 0, stream>>>(S);
         else           sca_item_kernel<true, true><<<blocks, threads, 0, stream>>>(S);
+    } else if (!S.ref_geometry) {
+        if (!oct) sca_walk_kernel<false><<<blocks, threads, 0, stream>>>(S);
+        else      sca_walk_kernel<true><<<blocks, threads, 0, stream>>>(S);
     } else {
         if (!oct)      sca_stream_kernel<false, false><<<blocks, threads, 0, stream>>>(S);
         else if (!dbl) sca_stream_kernel<true, false><<<blocks, threads, 0, stream>>>(S);
@@ -224,6 +387,11 @@ void launch_sca(const ScaArgs &S, int rng_mode, int blocks, int threads, cudaStr
 
 int sca_blocks_per_sm(bool octree, bool dbl, int threads) {
     int n = 0;
+    if (threads == 256) {
+        if (!octree) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sca_walk_kernel<false>, threads, 0);
+        else         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sca_walk_kernel<true>, threads, 0);
+        return n > 0 ? n : 1;
+    }
     if (!octree)   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sca_stream_kernel<false, false>, threads, 0);
     else if (!dbl) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sca_stream_kernel<true, false>, threads, 0);
     else           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sca_stream_kernel<true, true>, threads, 0);

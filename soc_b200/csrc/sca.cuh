@@ -15,7 +15,8 @@ struct ScaArgs {
     int kind, flavour, batch, global, ndir, npx, npy;
     int bins, no_ps, ps_method, with_abu, ffs;
     long long nunits;
-    int rank, world, max_steps;
+    int rank, world, max_steps, ref_geometry;
+    int ev_batch;                      // production kernel: handle ray ends when this many lanes of the warp wait
     unsigned long long *counters;      // packets, steps, scatterings, stuck, peels
     unsigned long long *work;
     MwcLaunch mwc;

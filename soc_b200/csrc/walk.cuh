@@ -128,7 +128,7 @@ __device__ __forceinline__ float walker_advance(const GridDesc &G, Walker &w) {
 // leaves most lanes idle (measured: 8.7 of 32 lanes active).  The kernels therefore keep a per-lane phase and
 // perform at most one climb, one crossing attempt and one descent per iteration of their main loop, so that
 // all lanes always execute the same short blocks.
-enum WalkPhase { WALK_LEAF = 0, WALK_CLIMB = 1, WALK_DESCEND = 2, WALK_CROSS = 3, WALK_SCATTER = 4 };
+enum WalkPhase { WALK_LEAF = 0, WALK_CLIMB = 1, WALK_DESCEND = 2, WALK_CROSS = 3, WALK_SCATTER = 4, WALK_END = 5 };
 
 // one level up (phase CLIMB -> CROSS): faces of the other two axes move out where the child was on the near side
 __device__ __forceinline__ void nav_climb(const GridDesc &G, Walker &w, const int ax) {
