@@ -18,6 +18,8 @@
  *   soc_zero_amc                            kernel ZeroAMC (kernel_ASOC_aux.c:657; ASOC.py:1115, 1183)
  *   soc_sim_pb / soc_sim_hp / soc_sim_cl    kernels SimRAM_PB / SimRAM_HP / SimRAM_CL
  *                                           (kernel_ASOC.c:15, 831, 1223; ASOC.py:1317-1419, 1847)
+ *   soc_absorbed_begin / _add / _finish     FABSORBED[:,f] += TMP and the final scaling loop
+ *                                           (ASOC.py:1482-1497, 2782-2878), kept on the device
  *   soc_eq_temperature / soc_emission       kernels EqTemperature / Emission
  *                                           (kernel_ASOC_aux.c:745, 793; ASOC.py:2027-2040, 2185-2197)
  *   soc_mapping / soc_healpix_mapping       kernels Mapping / HealpixMapping
@@ -80,7 +82,7 @@ enum soc_buffer {
     SOC_BUF_INTZ, SOC_BUF_EMIT, SOC_BUF_EMWEI, SOC_BUF_OPT, SOC_BUF_DSC, SOC_BUF_CSC, SOC_BUF_PSPOS,
     SOC_BUF_PS, SOC_BUF_XPS_NSIDE, SOC_BUF_XPS_SIDE, SOC_BUF_XPS_AREA, SOC_BUF_HPBG, SOC_BUF_HPBGP,
     SOC_BUF_MAP, SOC_BUF_SAVETAU, SOC_BUF_OUT, SOC_BUF_ODIR, SOC_BUF_ORA, SOC_BUF_ODE, SOC_BUF_TTT,
-    SOC_BUF_TNEW, SOC_BUF_COUNT
+    SOC_BUF_TNEW, SOC_BUF_FABS, SOC_BUF_COUNT
 };
 
 /* Stream layout of the Monte Carlo kernels. */
@@ -142,6 +144,15 @@ int  soc_sim_cl(soc_context *ctx, int source, int packets, int batch, float seed
  * E->T table.  Emission: reads TNEW, writes EMIT. */
 int  soc_eq_temperature(soc_context *ctx, int level, float adhoc, float kE, float Emin, int NE);
 int  soc_emission(soc_context *ctx, float freq, float fabs);
+
+/* Device-resident absorbed file (the [CELLS, NFREQ] array of ASOC.py:1482-1497 and its final scaling,
+ * ASOC.py:2782-2878): _begin allocates and clears FABS[cells*nfreq] (frequency fastest, the file's layout),
+ * _add does FABS[:, ifreq] += INT, _finish multiplies every cell by coeff0 * 8^level / DENS, writes -1e20 into
+ * cells with DENS <= nnnlimit (parents are links, i.e. <= 0) and copies the array to `host` (cells*nfreq floats;
+ * NULL = leave it on the device, e.g. to all-reduce it first with finish_scale = 0). */
+int  soc_absorbed_begin(soc_context *ctx, int nfreq);
+int  soc_absorbed_add(soc_context *ctx, int ifreq);
+int  soc_absorbed_finish(soc_context *ctx, float coeff0, float nnnlimit, int finish_scale, float *host);
 
 /* Mapping: reads EMIT, DENS (OPT); writes MAP and SAVETAU [npix_y*npix_x]. intobs[0] <= -1e10 selects the
  * orthographic projection. */

@@ -341,7 +341,17 @@ def main(argv=None, device_factory=None):
     if not root:
         EMITTED = np.fromfile(USER.file_emitted, np.float32, offset=8).reshape(CELLS, REMIT_NFREQ)
     FABSORBED = None
-    if not USER.NOABSORBED and root:
+    # [CELLS, NFREQ] absorptions: kept on the device and scaled / transposed there when it fits
+    # (soc_absorbed_*), else accumulated on the host per frequency like the reference (ASOC.py:1482-1497)
+    fabs_on_device = False
+    if not USER.NOABSORBED and USER.MMAP_ABSORBED == 0 and 'HOSTABSORBED' not in USER.KEYS:
+        try:
+            dev.absorbed_begin(NFREQ)
+            fabs_on_device = True
+        except bk.SocError as e:
+            if VERBOSE:
+                print("absorptions stay on the host: %s" % e)
+    if not USER.NOABSORBED and root and not fabs_on_device:
         if USER.MMAP_ABSORBED > 0:
             with open(USER.file_absorbed, "wb") as fp:
                 np.asarray([CELLS, NFREQ], np.int32).tofile(fp)
@@ -414,11 +424,14 @@ def main(argv=None, device_factory=None):
         """Per-frequency absorptions / intensities after a launch (ASOC.py:1476-1519, 1879-1905)."""
         nonlocal Tpull
         t0 = time.time()
-        if use_int:
+        if fabs_on_device:
+            dev.absorbed_add(ifreq)                 # this rank's share; ranks are combined once at the end
+        host_int = USER.SAVE_INTENSITY in (1, 2) or (not USER.NOABSORBED and not fabs_on_device)
+        if use_int and host_int:
             comm.allreduce(dev, bk.BUF_INT, CELLS)
-        if (USER.SAVE_INTENSITY == 1 or not USER.NOABSORBED) and root:
+        if (USER.SAVE_INTENSITY == 1 or (not USER.NOABSORBED and not fabs_on_device)) and root:
             dev.download(bk.BUF_INT, CELLS, out=TMP)
-            if not USER.NOABSORBED:
+            if not USER.NOABSORBED and not fabs_on_device:
                 FABSORBED[:, ifreq] += TMP
             if USER.SAVE_INTENSITY == 1:
                 for level in range(LEVELS):
@@ -691,7 +704,16 @@ def main(argv=None, device_factory=None):
     # =============================================================================================================
     # absorbed file (ASOC.py:2782-2878), emitted file (:3971-3975)
     # =============================================================================================================
-    if not USER.NOABSORBED and root:
+    if fabs_on_device:
+        comm.allreduce(dev, bk.BUF_FABS, CELLS * NFREQ)
+        if root:
+            out = np.empty((CELLS, NFREQ), np.float32)
+            dev.absorbed_finish(float(FACTOR / (USER.GL * PARSEC)), float(USER.NNNLIMIT), True, out)
+            with open(USER.file_absorbed, 'wb') as fpa:
+                np.asarray([CELLS, NFREQ], np.int32).tofile(fpa)
+                out.tofile(fpa)
+            del out
+    elif not USER.NOABSORBED and root:
         for level in range(LEVELS):
             a, b = OFF[level], OFF[level] + LCELLS[level]
             coeff = (8.0 ** level) * (FACTOR / (USER.GL * PARSEC))

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, "_lib", "libsoc_b200.so")
 
 (BUF_DENS, BUF_PAR, BUF_TABS, BUF_XAB, BUF_INT, BUF_INTX, BUF_INTY, BUF_INTZ, BUF_EMIT, BUF_EMWEI, BUF_OPT, BUF_DSC,
  BUF_CSC, BUF_PSPOS, BUF_PS, BUF_XPS_NSIDE, BUF_XPS_SIDE, BUF_XPS_AREA, BUF_HPBG, BUF_HPBGP, BUF_MAP, BUF_SAVETAU,
- BUF_OUT, BUF_ODIR, BUF_ORA, BUF_ODE, BUF_TTT, BUF_TNEW, BUF_COUNT) = range(29)
+ BUF_OUT, BUF_ODIR, BUF_ORA, BUF_ODE, BUF_TTT, BUF_TNEW, BUF_FABS, BUF_COUNT) = range(30)
 
 RNG_REFERENCE, RNG_PACKET = 0, 1
 DEP_RED, DEP_WARP, DEP_TILE = 0, 1, 2
@@ -41,7 +41,7 @@ class SocCounters(C.Structure):
 
 _EXPORTS = """soc_last_error soc_version soc_create soc_destroy soc_sync soc_set_params soc_set_grid soc_set_rng_mode
 soc_set_shard soc_set_tuning soc_set_geometry soc_upload soc_download soc_clear soc_device_ptr soc_zero_amc soc_sim_pb soc_sim_hp
-soc_sim_cl soc_eq_temperature soc_emission soc_mapping soc_healpix_mapping soc_sca_zero_out soc_sca_ps soc_sca_pb
+soc_sim_cl soc_absorbed_begin soc_absorbed_add soc_absorbed_finish soc_eq_temperature soc_emission soc_mapping soc_healpix_mapping soc_sca_zero_out soc_sca_ps soc_sca_pb
 soc_get_counters soc_reset_counters soc_last_launch_ms soc_stream""".split()
 
 _lib = None
@@ -80,6 +80,9 @@ def load_library(path=None):
     L.soc_sim_hp.argtypes = [vp, i, i, f, f, f, f, i]
     L.soc_sim_cl.argtypes = [vp, i, i, i, f, f, f, f, i]
     L.soc_eq_temperature.argtypes = [vp, i, f, f, f, i]
+    L.soc_absorbed_begin.argtypes = [vp, i]
+    L.soc_absorbed_add.argtypes = [vp, i]
+    L.soc_absorbed_finish.argtypes = [vp, f, f, i, vp]
     L.soc_emission.argtypes = [vp, f, f]
     L.soc_mapping.argtypes = [vp, f, i, i, fp, fp, fp, f, f, fp, fp, i]
     L.soc_healpix_mapping.argtypes = [vp, i, f, f, fp, i]
@@ -198,6 +201,16 @@ class Device:
 
     def sim_cl(self, source, packets, batch, seed, abs_, sca, tw, global_):
         self._ck(self.L.soc_sim_cl(self.ctx, source, packets, batch, seed, abs_, sca, tw, global_))
+
+    def absorbed_begin(self, nfreq):
+        self._ck(self.L.soc_absorbed_begin(self.ctx, int(nfreq)))
+
+    def absorbed_add(self, ifreq):
+        self._ck(self.L.soc_absorbed_add(self.ctx, int(ifreq)))
+
+    def absorbed_finish(self, coeff0, nnnlimit, scale=True, out=None):
+        self._ck(self.L.soc_absorbed_finish(self.ctx, coeff0, nnnlimit, 1 if scale else 0, None if out is None else out.ctypes.data))
+        return out
 
     def eq_temperature(self, level, adhoc, kE, Emin, NE):
         self._ck(self.L.soc_eq_temperature(self.ctx, level, adhoc, kE, Emin, NE))

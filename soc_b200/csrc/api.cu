@@ -46,14 +46,15 @@ struct soc_context {
     bool have_params, have_grid;
     GridDesc G;
     int rng_mode, rank, world;
-    int deposit, refill, agg_steps, geometry, sc_batch;
+    int deposit, refill, agg_steps, geometry, sc_batch, nav_hops;
+    int fabs_nfreq;
     uint64_t pow2k[26];
 };
 
 static const char *buf_name(int b) {
     static const char *n[SOC_BUF_COUNT] = { "DENS", "PAR", "TABS", "XAB", "INT", "INTX", "INTY", "INTZ", "EMIT", "EMWEI",
         "OPT", "DSC", "CSC", "PSPOS", "PS", "XPS_NSIDE", "XPS_SIDE", "XPS_AREA", "HPBG", "HPBGP", "MAP", "SAVETAU", "OUT",
-        "ODIR", "ORA", "ODE", "TTT", "TNEW" };
+        "ODIR", "ORA", "ODE", "TTT", "TNEW", "FABS" };
     return (b >= 0 && b < SOC_BUF_COUNT) ? n[b] : "?";
 }
 
@@ -101,6 +102,8 @@ int soc_create(int device_ordinal, soc_context **out) {
     c->device = device_ordinal; c->sms = prop.multiProcessorCount;
     c->rng_mode = SOC_RNG_PACKET; c->rank = 0; c->world = 1;
     c->deposit = DEP_TILE; c->refill = 8; c->agg_steps = 24; c->sc_batch = 0;        // 0 = by grid type
+    c->nav_hops = 1;
+    if (const char *e = getenv("SOC_NAV_HOPS")) { int v = atoi(e); if (v >= 1 && v <= 8) c->nav_hops = v; }          // tuning knob
     if (const char *e = getenv("SOC_SC_BATCH")) { int v = atoi(e); if (v >= 1 && v <= 32) c->sc_batch = v; }   // tuning knob
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&c->ev0));
@@ -316,7 +319,7 @@ static int sim_common(soc_context *c, SimArgs &A, int kind, int batch, float see
     A.rank = c->rank; A.world = c->world;
     long long ms = 100LL * ((long long)c->G.nx + c->G.ny + c->G.nz) << (c->G.levels - 1);
     A.max_steps = (int)(ms > INT_MAX ? INT_MAX : ms);
-    A.deposit = c->deposit; A.refill = c->refill; A.agg_steps = c->agg_steps; A.ref_geometry = c->geometry; A.sc_batch = c->sc_batch > 0 ? c->sc_batch : (c->G.levels > 1 ? 3 : 1);
+    A.deposit = c->deposit; A.refill = c->refill; A.agg_steps = c->agg_steps; A.ref_geometry = c->geometry; A.nav_hops = c->nav_hops; A.sc_batch = c->sc_batch > 0 ? c->sc_batch : (c->G.levels > 1 ? 3 : 1);
     A.counters = c->counters; A.work = c->counters + 5;
     // stream layouts
     A.mwc.base_offset = seed_to_base(seed);
@@ -452,6 +455,48 @@ int soc_eq_temperature(soc_context *c, int level, float adhoc, float kE, float E
     return SOC_OK;
 }
 
+int soc_absorbed_begin(soc_context *c, int nfreq) {
+    NEED_CTX(c);
+    if (!c->have_grid || !c->have_params) return fail(SOC_ERR_STATE, "soc_absorbed_begin: grid and params first");
+    if (nfreq < 1) return fail(SOC_ERR_ARG, "soc_absorbed_begin: nfreq=%d", nfreq);
+    const size_t bytes = (size_t)c->G.cells * nfreq * 4;
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    if (c->buf[SOC_BUF_FABS].bytes != bytes && bytes > free_b + c->buf[SOC_BUF_FABS].bytes)
+        return fail(SOC_ERR_STATE, "soc_absorbed_begin: %zu bytes for the [CELLS,NFREQ] array do not fit (%zu free)", bytes, free_b);
+    int r = soc_clear(c, SOC_BUF_FABS, bytes);
+    if (r != SOC_OK) return r;
+    c->fabs_nfreq = nfreq;
+    return SOC_OK;
+}
+
+int soc_absorbed_add(soc_context *c, int ifreq) {
+    NEED_CTX(c);
+    if (c->fabs_nfreq < 1 || c->buf[SOC_BUF_FABS].ptr == nullptr) return fail(SOC_ERR_STATE, "soc_absorbed_add: soc_absorbed_begin first");
+    if (ifreq < 0 || ifreq >= c->fabs_nfreq) return fail(SOC_ERR_ARG, "soc_absorbed_add: ifreq %d of %d", ifreq, c->fabs_nfreq);
+    int r = need(c, SOC_BUF_INT, (size_t)c->G.cells * 4, "soc_absorbed_add");
+    if (r != SOC_OK) return r;
+    launch_absorbed_add(dptr<float>(c, SOC_BUF_FABS), dptr<float>(c, SOC_BUF_INT), c->G.cells, c->fabs_nfreq, ifreq, c->stream);
+    c->launches++;
+    CU(cudaGetLastError());
+    return SOC_OK;
+}
+
+int soc_absorbed_finish(soc_context *c, float coeff0, float nnnlimit, int finish_scale, float *host) {
+    NEED_CTX(c);
+    if (c->fabs_nfreq < 1 || c->buf[SOC_BUF_FABS].ptr == nullptr) return fail(SOC_ERR_STATE, "soc_absorbed_finish: soc_absorbed_begin first");
+    if (finish_scale) {
+        launch_absorbed_scale(c->G, dptr<float>(c, SOC_BUF_FABS), c->fabs_nfreq, coeff0, nnnlimit, c->stream);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    if (host != nullptr) {
+        CU(cudaMemcpyAsync(host, c->buf[SOC_BUF_FABS].ptr, c->buf[SOC_BUF_FABS].bytes, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return SOC_OK;
+}
+
 int soc_emission(soc_context *c, float freq, float fabs_) {
     NEED_CTX(c);
     if (!c->have_grid || !c->have_params) return fail(SOC_ERR_STATE, "soc_emission: grid and params first");
@@ -551,7 +596,7 @@ static int sca_common(soc_context *c, ScaArgs &S, int kind, int batch, float see
     S.centre = { centre[0], centre[1], centre[2] };
     S.kind = kind; S.batch = batch; S.global = global; S.ndir = ndir; S.npx = npix_x; S.npy = npix_y;
     S.bins = P.bins; S.no_ps = P.no_ps; S.ps_method = P.ps_method; S.with_abu = P.with_abu; S.ffs = P.ffs;
-    S.rank = c->rank; S.world = c->world; S.ref_geometry = c->geometry; S.ev_batch = c->sc_batch > 0 ? c->sc_batch : 3;
+    S.rank = c->rank; S.world = c->world; S.ref_geometry = c->geometry; S.ev_batch = c->sc_batch > 0 ? c->sc_batch : 3; S.nav_hops = c->nav_hops;
     long long ms = 100LL * ((long long)c->G.nx + c->G.ny + c->G.nz) << (c->G.levels - 1);
     S.max_steps = (int)(ms > INT_MAX ? INT_MAX : ms);
     S.counters = c->counters; S.work = c->counters + 5;

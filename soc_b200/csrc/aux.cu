@@ -43,6 +43,27 @@ __global__ void emission_kernel(int cells, float freq, float fabs_, float factor
         emit[i] = (2.79639459e-20f * factor) * fabs_ * (freq * freq / (expf(4.7995074e-11f * freq / t[i]) - 1.0f)) / length;
 }
 
+// FABS[cell, ifreq] += INT[cell]: coalesced read, one 4-byte write per cell row of the [cells, nfreq] array
+__global__ void absorbed_add_kernel(float *__restrict__ fabs, const float *__restrict__ inten, int cells, int nfreq, int ifreq) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += gridDim.x * blockDim.x) {
+        float v = inten[i];
+        if (v != 0.0f) fabs[(size_t)i * nfreq + ifreq] += v;
+    }
+}
+
+// absorbed-file scaling of ASOC.py:2793-2809: photons -> FACTOR * photons per H; parents / thin cells -> -1e20
+__global__ void absorbed_scale_kernel(GridDesc G, float *__restrict__ fabs, int nfreq, float coeff0, float nnnlimit) {
+    const size_t total = (size_t)G.cells * nfreq;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int cell = (int)(e / nfreq);
+        int level = 0;
+        while (level + 1 < G.levels && cell >= G.off[level + 1]) level++;
+        const float rho = G.dens[cell];
+        const float k = coeff0 * __int_as_float((127 + 3 * level) << 23) / rho;         // 8^level = 2^(3 level)
+        fabs[e] = (rho <= nnnlimit) ? -1.0e20f : fabs[e] * k;
+    }
+}
+
 inline int grid_for(long long n, int threads) {
     long long b = (n + threads - 1) / threads;
     const long long cap = 148LL * 16;
@@ -63,4 +84,10 @@ void launch_eq_temperature(const GridDesc &G, int level, float adhoc, float kE, 
 void launch_emission(int cells, float freq, float fabs_, float factor, float length, const float *t, float *emit,
                      cudaStream_t stream) {
     emission_kernel<<<grid_for(cells, 256), 256, 0, stream>>>(cells, freq, fabs_, factor, length, t, emit);
+}
+void launch_absorbed_add(float *fabs, const float *inten, int cells, int nfreq, int ifreq, cudaStream_t stream) {
+    absorbed_add_kernel<<<grid_for(cells, 256), 256, 0, stream>>>(fabs, inten, cells, nfreq, ifreq);
+}
+void launch_absorbed_scale(const GridDesc &G, float *fabs, int nfreq, float coeff0, float nnnlimit, cudaStream_t stream) {
+    absorbed_scale_kernel<<<grid_for((long long)G.cells * nfreq, 256), 256, 0, stream>>>(G, fabs, nfreq, coeff0, nnnlimit);
 }

@@ -7,3 +7,5 @@ void launch_eq_temperature(const GridDesc &G, int level, float adhoc, float kE, 
                            float length, const float *ttt, const float *emit, float *tnew, cudaStream_t stream);
 void launch_emission(int cells, float freq, float fabs_, float factor, float length, const float *t, float *emit,
                      cudaStream_t stream);
+void launch_absorbed_add(float *fabs, const float *inten, int cells, int nfreq, int ifreq, cudaStream_t stream);
+void launch_absorbed_scale(const GridDesc &G, float *fabs, int nfreq, float coeff0, float nnnlimit, cudaStream_t stream);

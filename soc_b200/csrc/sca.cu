@@ -358,10 +358,13 @@ __global__ void __launch_bounds__(256, 3) sca_walk_kernel(const __grid_constant_
             if (nstep > S.max_steps) { mode = RAY_IDLE; phase = WALK_LEAF; cnt.stuck++; }
         }
         // ---- navigation: one hop of each kind ------------------------------------------------------------------
-        if (mode != RAY_IDLE) {
-            if (OCT && phase == WALK_CLIMB) { nav_climb(G, w, ax); phase = WALK_CROSS; }
-            if (phase == WALK_CROSS) { phase = nav_cross(G, w, ax); if (w.ind < 0) phase = WALK_END; }
-            if (OCT && phase == WALK_DESCEND) phase = nav_descend(G, w, ax);
+        #pragma unroll 1
+        for (int hop = 0; hop < (OCT ? S.nav_hops : 1); hop++) {
+            if (mode != RAY_IDLE) {
+                if (OCT && phase == WALK_CLIMB) { nav_climb(G, w, ax); phase = WALK_CROSS; }
+                if (phase == WALK_CROSS) { phase = nav_cross(G, w, ax); if (w.ind < 0) phase = WALK_END; }
+                if (OCT && phase == WALK_DESCEND) phase = nav_descend(G, w, ax);
+            }
         }
     }
     flush(S, cnt);

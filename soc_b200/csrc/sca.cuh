@@ -16,6 +16,7 @@ struct ScaArgs {
     int bins, no_ps, ps_method, with_abu, ffs;
     long long nunits;
     int rank, world, max_steps, ref_geometry;
+    int nav_hops;                      // octree navigation rounds (climb / cross / descend) per loop iteration
     int ev_batch;                      // production kernel: handle ray ends when this many lanes of the warp wait
     unsigned long long *counters;      // packets, steps, scatterings, stuck, peels
     unsigned long long *work;

@@ -775,9 +775,12 @@ __global__ void __launch_bounds__(256, 4) sim_walk_kernel(const __grid_constant_
             if (nstep > A.max_steps) { alive = false; phase = WALK_LEAF; cnt.stuck++; }
         }
         // navigation, one hop of each kind per iteration: climb, try to cross, descend
-        if (alive && phase == WALK_CLIMB) { nav_climb(G, w, ax); phase = WALK_CROSS; }
-        if (alive && phase == WALK_CROSS) { phase = nav_cross(G, w, ax); if (w.ind < 0) alive = false; }
-        if (alive && phase == WALK_DESCEND) phase = nav_descend(G, w, ax);
+        #pragma unroll 1
+        for (int hop = 0; hop < A.nav_hops; hop++) {
+            if (alive && phase == WALK_CLIMB) { nav_climb(G, w, ax); phase = WALK_CROSS; }
+            if (alive && phase == WALK_CROSS) { phase = nav_cross(G, w, ax); if (w.ind < 0) alive = false; }
+            if (alive && phase == WALK_DESCEND) phase = nav_descend(G, w, ax);
+        }
         if (was_alive && !alive) { cnt.steps += nstep; cnt.scat += min(scat, 20); }
     }
     flush_counters(A, cnt);

@@ -37,6 +37,7 @@ struct SimArgs {
     int deposit;                 // DepositMode
     int refill;                  // stream kernel: refill a warp when at least this many lanes are idle
     int ref_geometry;            // regular grids: 1 = step with the reference's GetStep arithmetic instead of the DDA
+    int nav_hops;                // octree walk kernel: navigation rounds (climb / cross / descend) per loop iteration
     int sc_batch;                // production kernels: scatter when this many lanes of the warp wait at a scattering point
     int agg_steps;               // stream kernel: combine lanes only while a packet is younger than this
     int tile_x0, tile_y0, tile_z0;   // DEP_TILE: root-grid origin of the shared-memory tile

@@ -38,6 +38,19 @@ def lognormal_field(n, sigma=1.5, slope=-3.7, seed=12345):
     return np.exp(sigma * f - 0.5 * sigma * sigma).astype(np.float32)
 
 
+def box_cloud(nx, ny, nz, levels=1, refine_fraction=0.2, seed=7):
+    """Non-cubic test cloud: smooth random density on an nx*ny*nz root grid (x fastest), optionally refined like
+    octree_cloud()."""
+    rng = np.random.default_rng(seed)
+    z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    d0 = (0.4 + np.exp(-((x - 0.4 * nx) ** 2 / (0.3 * nx) ** 2 + (y - 0.6 * ny) ** 2 / (0.3 * ny) ** 2
+                          + (z - 0.5 * nz) ** 2 / (0.3 * nz) ** 2)) + 0.2 * rng.random((nz, ny, nx))).astype(np.float32)
+    if levels == 1:
+        return Cloud(nx, ny, nz, [nx * ny * nz], d0.ravel())
+    c = octree_cloud(1, levels, refine_fraction=refine_fraction, seed=seed, base=d0.ravel())
+    return Cloud(nx, ny, nz, c.LCELLS, c.DENS)
+
+
 def octree_cloud(nroot, levels, refine_fraction=0.15, sigma=1.5, seed=12345, base=None):
     """Hierarchical cloud in SOC's format (ASOC_aux.py:734-744): level 0 is an x-fastest nroot^3 grid,
     deeper levels are runs of 8 children ordered sid = 4z+2y+x; a refined cell stores the link

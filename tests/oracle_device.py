@@ -140,6 +140,25 @@ class OracleDevice:
                                               csc=self._g(bk.BUF_CSC), opt=self._g(bk.BUF_OPT), emit=self._g(bk.BUF_EMIT),
                                               emwei=self._g(bk.BUF_EMWEI)), seed)
 
+    def absorbed_begin(self, nfreq):
+        self.fabs = np.zeros((self.n, nfreq), np.float32)
+        self.buf[bk.BUF_FABS] = self.fabs.reshape(-1)
+
+    def absorbed_add(self, ifreq):
+        self.fabs[:, ifreq] += self.O.int_
+
+    def absorbed_finish(self, coeff0, nnnlimit, scale=True, out=None):
+        if scale:
+            c = self.cloud
+            for level in range(c.LEVELS):
+                sl = c.level_slice(level)
+                with np.errstate(all='ignore'):
+                    self.fabs[sl] *= (np.float32(coeff0) * np.float32(8.0 ** level) / c.DENS[sl]).reshape(-1, 1)
+                self.fabs[sl][c.DENS[sl] <= nnnlimit] = -1.0e20
+        if out is not None:
+            out[...] = self.fabs.reshape(out.shape)
+        return out
+
     def eq_temperature(self, level, adhoc, kE, Emin, NE):
         if bk.BUF_TNEW not in self.buf or self.buf[bk.BUF_TNEW].size != self.n:
             self.buf[bk.BUF_TNEW] = np.zeros(self.n, np.float32)

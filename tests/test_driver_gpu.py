@@ -90,3 +90,17 @@ def test_scattered_light_driver(tmp_path):
     f = int(np.argmax(c.sum(axis=(1, 2, 3))))
     ok = c[f] > 0.2 * c[f].max()
     assert np.median(np.abs(g[f][ok] / c[f][ok] - 1.0)) < 0.1
+
+
+def test_device_resident_absorbed_array_matches_host_accumulation(tmp_path):
+    """soc_absorbed_* (FABS kept, scaled and marked on the device) == the reference's host-side loop."""
+    kw = dict(n=6, octree=True, bgpac=40000, pspac=33000, noabsorbed=False, absorbed=True, maps=False)
+    cloud = _run(tmp_path / "dev", None, **kw)
+    _run(tmp_path / "host", None, extra="HOSTABSORBED\n", **kw)
+    a = read_cells_freq_file(str(tmp_path / "dev" / "abs.data")).astype(np.float64)
+    b = read_cells_freq_file(str(tmp_path / "host" / "abs.data")).astype(np.float64)
+    parents = cloud.DENS <= 0.0
+    assert (a[parents] == -1.0e20).all() and (b[parents] == -1.0e20).all()
+    leaves = ~parents
+    assert np.abs(a[leaves] - b[leaves]).max() <= 2e-5 * b[leaves].max()
+    assert np.abs(a[leaves].sum() / b[leaves].sum() - 1.0) < 1e-5

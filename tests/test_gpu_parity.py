@@ -15,6 +15,7 @@ import pytest
 
 from tests.cases import CASES, run_bg, run_ps, run_abu, run_hp, run_cl, run_sca, _reg, _oct
 from tests.stats import chi2_per_dof
+from soc_b200 import synth
 
 pytestmark = pytest.mark.gpu
 
@@ -107,6 +108,10 @@ def _repeat(X, runner_factory, K, key="tabs"):
 STAT_CASES = {
     # name: (cloud, options, runner factory(seed), output key)
     "bg_reg16": (_reg(16), {}, lambda s: run_bg(batch=4, seed=s), "tabs"),
+    "bg_box_20_12_8": (lambda: synth.box_cloud(20, 12, 8), {}, lambda s: run_bg(batch=6, seed=s), "tabs"),
+    "bg_box_oct_10_6_4": (lambda: synth.box_cloud(10, 6, 4, levels=4, refine_fraction=0.25), {}, lambda s: run_bg(batch=24, seed=s), "tabs"),
+    "ps_box_oct_10_6_4": (lambda: synth.box_cloud(10, 6, 4, levels=4, refine_fraction=0.25), dict(no_ps=1),
+                          lambda s: run_ps([(4.3, 3.2, 1.7)], batch=48, seed=s), "tabs"),
     "bg_reg16_refgeo": (_reg(16), {}, lambda s: run_bg(batch=4, seed=s), "tabs"),
     "bg_reg16_iso": (_reg(16), {}, lambda s: run_bg(batch=4, seed=s, g=False, tau_s=6.0), "tabs"),
     "bg_oct8_3": (_oct(8, 3), {}, lambda s: run_bg(batch=8, seed=s), "tabs"),
