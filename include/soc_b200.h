@@ -22,6 +22,7 @@
  *                                           (ASOC.py:1482-1497, 2782-2878), kept on the device
  *   soc_eq_temperature / soc_emission       kernels EqTemperature / Emission
  *                                           (kernel_ASOC_aux.c:745, 793; ASOC.py:2027-2040, 2185-2197)
+ *   soc_ps_tau                              kernel PSTau (kernel_ASOC_map.c:1545; ASOC.py:3576-3644)
  *   soc_mapping / soc_healpix_mapping       kernels Mapping / HealpixMapping
  *                                           (kernel_ASOC_map.c:496, 890; ASOC.py:3127-3139)
  *   soc_sca_zero_out / soc_sca_ps / _pb     kernels zero_out / SimRAM_PS / SimRAM_PB of
@@ -160,6 +161,10 @@ int  soc_mapping(soc_context *ctx, float map_dx, int npix_x, int npix_y, const f
                  const float de[3], float abs, float sca, const float centre[3], const float intobs[3],
                  int save_colden);
 int  soc_healpix_mapping(soc_context *ctx, int nside, float abs, float sca, const float intobs[3], int save_colden);
+
+/* PSTau (kernel_ASOC_map.c:1545; ASOC.py:3576-3644): optical depth and column density (x LENGTH) from each of the
+ * first `no` point sources in PSPOS towards the observer direction `dir`; results are copied to the host arrays. */
+int  soc_ps_tau(soc_context *ctx, int no, const float dir[3], float abs, float sca, float *colden_out, float *tau_out);
 
 /* Scattered light (ASOCS.py).  ODIR/ORA/ODE are [ndir*3] floats (x,y,z), OUT is [ndir*npix_y*npix_x]. */
 int  soc_sca_zero_out(soc_context *ctx, int ndir, int npix_x, int npix_y);

@@ -191,6 +191,16 @@ class Oracle:
                            _fp(v[4]), _fp(opt), _fp(t), C.c_int(save_colden), C.byref(self.counters))
         return m.reshape(npy, npx), t.reshape(npy, npx)
 
+    def ps_tau(self, pspos, dir_, abs_, sca, opt=None):
+        pp = np.ascontiguousarray(np.asarray(pspos, np.float32).reshape(-1))
+        no = len(pp) // 3
+        col, tau = np.zeros(no, np.float32), np.zeros(no, np.float32)
+        d = np.ascontiguousarray(dir_, np.float32)
+        opt = None if opt is None else np.ascontiguousarray(opt, np.float32)
+        self.L.orc_ps_tau(C.byref(self.P), C.byref(self.G), C.c_int(no), _fp(pp), _fp(d), C.c_float(abs_), C.c_float(sca),
+                          _fp(opt), _fp(col), _fp(tau))
+        return col, tau
+
     def healpix_mapping(self, nside, emit, abs_, sca, intobs, opt=None, save_colden=0):
         n = 12 * nside * nside
         m, t = np.zeros(n, np.float32), np.zeros(n, np.float32)

@@ -160,6 +160,18 @@ class Reference:
                                    _fp(t), C.c_int(save_colden))
         return m, t
 
+    def ps_tau(self, pspos, dir_, abs_, sca, opt=None):
+        self._keep = []
+        pp = np.ascontiguousarray(np.asarray(pspos, np.float32).reshape(-1, 3))
+        no = len(pp)
+        col, tau = np.zeros(no, np.float32), np.zeros(no, np.float32)
+        d = np.ascontiguousarray(dir_, np.float32)
+        z = np.zeros(3, np.float32)
+        self.L.ref_pstau(C.c_int(((no + 7) // 8) * 8), C.c_int(no), _fp(pp.reshape(-1)), _fp(d), _fp(z), _fp(z), _ip(self.lcells),
+                         _ip(self.off), _ip(self.par), _fp(self.dens), C.c_float(abs_), C.c_float(sca), self._f(opt),
+                         _fp(col), _fp(tau))
+        return col, tau
+
     def _v3(self, a):
         a = np.ascontiguousarray(np.asarray(a, np.float32)[:, :3].reshape(-1))
         self._keep.append(a)

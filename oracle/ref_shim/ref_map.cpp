@@ -2,6 +2,7 @@
 // HealpixMapping) on the host through cl_shim.h.  Separate translation unit:
 // the map kernels carry their own IndexG/Index/GetStep with different EPS/PEPS.
 #include "ref_common.h"
+#include <vector>
 
 namespace refm {
 #include "kernel_ASOC_map.c"
@@ -31,6 +32,15 @@ void ref_healpix_mapping(int global, float MAP_DX, int npx, int npy, float *MAP,
     REF_PARALLEL_FOR(global,
         refm::HealpixMapping(MAP_DX, NPIX, MAP, EMIT, d, ra, de, LCELLS, OFF, PAR, DENS, ABS, SCA, c, io, OPT,
                              SAVETAU, SAVE_COLDEN));
+}
+
+void ref_pstau(int global, int no, const float *PSPOS_xyz, const float *DIR, const float *RA, const float *DE,
+               const int *LCELLS, const int *OFF, int *PAR, float *DENS, float ABS, float SCA, float *OPT,
+               float *pscolden, float *pstau) {
+    float3 d(DIR[0], DIR[1], DIR[2]), ra(RA[0], RA[1], RA[2]), de(DE[0], DE[1], DE[2]);
+    std::vector<float3> pos(no);
+    for (int i = 0; i < no; i++) pos[i] = float3(PSPOS_xyz[3 * i], PSPOS_xyz[3 * i + 1], PSPOS_xyz[3 * i + 2]);
+    REF_PARALLEL_FOR(global, refm::PSTau(no, pos.data(), d, ra, de, LCELLS, OFF, PAR, DENS, ABS, SCA, OPT, pscolden, pstau));
 }
 
 }  // extern "C"

@@ -783,6 +783,29 @@ void orc_mapping(const OrcParams *P, const OrcGrid *G, float map_dx, int npx, in
     if (C) C->steps += steps;
 }
 
+/* PSTau: kernel_ASOC_map.c:1545-1599 -- optical depth and column density from every point source towards the observer */
+void orc_ps_tau(const OrcParams *P, const OrcGrid *G, int no, const float *pspos, const float *dir, float abs_, float sca_,
+                const float *opt, float *pscolden, float *pstau) {
+    nav_t N = nav_make(P, G);
+    v3 D = { dir[0], dir[1], dir[2] };
+    for (int id = 0; id < no; id++) {
+        float TAU = 0.0f, colden = 0.0f, sx, DTAU;
+        v3 POS = { pspos[3 * id], pspos[3 * id + 1], pspos[3 * id + 2] };
+        int ind, level = 0, oind;
+        index_g_map(&N, &POS, &level, &ind);
+        while (ind >= 0) {
+            oind = N.off[level] + ind;
+            sx = get_step_map(&N, &POS, &D, &level, &ind);
+            if (P->with_abu) DTAU = sx * N.dens[oind] * (opt[2 * (long)oind] + opt[2 * (long)oind + 1]);
+            else             DTAU = sx * N.dens[oind] * (sca_ + abs_);
+            TAU += DTAU;
+            colden += sx * N.dens[oind];
+        }
+        pscolden[id] = colden * P->length;
+        pstau[id] = TAU;
+    }
+}
+
 /* HealpixMapping: kernel_ASOC_map.c:890-966 (the NSIDE macro of the map program = nside here) */
 static void map_pix2ang(int nside, int ipix, float *phi, float *theta) {      /* kernel_ASOC_map.c:101-140 */
     int nl2, nl4, npix, ncap, iring, iphi, ip, ipix1;

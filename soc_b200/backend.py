@@ -41,7 +41,7 @@ class SocCounters(C.Structure):
 
 _EXPORTS = """soc_last_error soc_version soc_create soc_destroy soc_sync soc_set_params soc_set_grid soc_set_rng_mode
 soc_set_shard soc_set_tuning soc_set_geometry soc_upload soc_download soc_clear soc_device_ptr soc_zero_amc soc_sim_pb soc_sim_hp
-soc_sim_cl soc_absorbed_begin soc_absorbed_add soc_absorbed_finish soc_eq_temperature soc_emission soc_mapping soc_healpix_mapping soc_sca_zero_out soc_sca_ps soc_sca_pb
+soc_sim_cl soc_absorbed_begin soc_absorbed_add soc_absorbed_finish soc_eq_temperature soc_emission soc_mapping soc_healpix_mapping soc_ps_tau soc_sca_zero_out soc_sca_ps soc_sca_pb
 soc_get_counters soc_reset_counters soc_last_launch_ms soc_stream""".split()
 
 _lib = None
@@ -86,6 +86,7 @@ def load_library(path=None):
     L.soc_emission.argtypes = [vp, f, f]
     L.soc_mapping.argtypes = [vp, f, i, i, fp, fp, fp, f, f, fp, fp, i]
     L.soc_healpix_mapping.argtypes = [vp, i, f, f, fp, i]
+    L.soc_ps_tau.argtypes = [vp, i, fp, f, f, vp, vp]
     L.soc_sca_zero_out.argtypes = [vp, i, i, i]
     L.soc_sca_ps.argtypes = [vp, i, i, f, f, f, i, i, i, f, fp, i]
     L.soc_sca_pb.argtypes = [vp, i, i, i, f, f, f, f, i, i, i, f, fp, i]
@@ -227,6 +228,12 @@ class Device:
         k = _f3(intobs)
         self._ck(self.L.soc_healpix_mapping(self.ctx, nside, abs_, sca, k[1], save_colden))
 
+    def ps_tau(self, no, dir_, abs_, sca):
+        k = _f3(dir_)
+        col, tau = np.zeros(no, np.float32), np.zeros(no, np.float32)
+        self._ck(self.L.soc_ps_tau(self.ctx, no, k[1], abs_, sca, col.ctypes.data, tau.ctypes.data))
+        return col, tau
+
     def sca_zero_out(self, ndir, npx, npy):
         self._ck(self.L.soc_sca_zero_out(self.ctx, ndir, npx, npy))
 
@@ -364,6 +371,10 @@ class Backend:
         self.dev.healpix_mapping(nside, abs_, sca, intobs, save_colden)
         n = 12 * nside * nside
         return self.dev.download(BUF_MAP, n), self.dev.download(BUF_SAVETAU, n)
+
+    def ps_tau(self, pspos, dir_, abs_, sca, opt=None):
+        self._put(pspos=pspos, opt=opt)
+        return self.dev.ps_tau(len(np.asarray(pspos).reshape(-1)) // 3, dir_, abs_, sca)
 
     def _observers(self, odirs, ora, ode):
         for b, v in ((BUF_ODIR, odirs), (BUF_ORA, ora), (BUF_ODE, ode)):

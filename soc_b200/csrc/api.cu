@@ -562,6 +562,28 @@ int soc_healpix_mapping(soc_context *c, int nside, float abs, float sca, const f
     return SOC_OK;
 }
 
+int soc_ps_tau(soc_context *c, int no, const float dir[3], float abs, float sca, float *colden_out, float *tau_out) {
+    NEED_CTX(c);
+    if (no < 1 || !dir || !colden_out || !tau_out) return fail(SOC_ERR_ARG, "soc_ps_tau: bad arguments");
+    if (!c->have_grid || !c->have_params) return fail(SOC_ERR_STATE, "soc_ps_tau: grid and params first");
+    int r;
+    if ((r = need(c, SOC_BUF_PSPOS, (size_t)no * 12, "soc_ps_tau")) != SOC_OK) return r;
+    if (c->P.with_abu && (r = need(c, SOC_BUF_OPT, (size_t)c->G.cells * 8, "soc_ps_tau")) != SOC_OK) return r;
+    if ((r = ensure(c, SOC_BUF_MAP, (size_t)no * 4)) != SOC_OK) return r;
+    if ((r = ensure(c, SOC_BUF_SAVETAU, (size_t)no * 4)) != SOC_OK) return r;
+    MapArgs M;
+    memset(&M, 0, sizeof(M));
+    M.G = c->G; M.opt = dptr<float>(c, SOC_BUF_OPT); M.kabs = abs; M.ksca = sca; M.length = c->P.length; M.with_abu = c->P.with_abu;
+    M.dir = { dir[0], dir[1], dir[2] };
+    launch_pstau(M, no, dptr<float>(c, SOC_BUF_PSPOS), dptr<float>(c, SOC_BUF_MAP), dptr<float>(c, SOC_BUF_SAVETAU), c->stream);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(colden_out, c->buf[SOC_BUF_MAP].ptr, (size_t)no * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(tau_out, c->buf[SOC_BUF_SAVETAU].ptr, (size_t)no * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return SOC_OK;
+}
+
 // ---- scattered light ------------------------------------------------------------------------------------------
 int soc_sca_zero_out(soc_context *c, int ndir, int npix_x, int npix_y) {
     NEED_CTX(c);

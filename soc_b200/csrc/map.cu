@@ -138,7 +138,40 @@ __global__ void __launch_bounds__(128) healpix_mapping_kernel(const __grid_const
     warp_add_counter(M.counters + 1, steps);
 }
 
+// PSTau (kernel_ASOC_map.c:1545-1599): tau and column density from each point source towards the observer
+template <bool OCT, bool DBL>
+__global__ void pstau_kernel(const __grid_constant__ MapArgs M, int no, const float *__restrict__ pspos, float *__restrict__ colden_out,
+                             float *__restrict__ tau_out) {
+    const GridDesc &G = M.G;
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= no) return;
+    vec3 POS = { pspos[3 * id], pspos[3 * id + 1], pspos[3 * id + 2] };
+    int level = 0, ind;
+    float rho = 0.0f, TAU = 0.0f, colden = 0.0f;
+    index_global<OCT, true>(G, POS, level, ind, rho);
+    while (ind >= 0) {
+        const int oind = OCT ? G.off[level] + ind : ind;
+        const float dens = rho;
+        float kext;
+        if (M.with_abu) { float2 o = reinterpret_cast<const float2 *>(M.opt)[oind]; kext = xadd(o.x, o.y); }
+        else            kext = xadd(M.ksca, M.kabs);
+        const float sx = get_step<OCT, DBL, true>(G, POS, M.dir, level, ind, rho);
+        TAU = xadd(TAU, xmul(xmul(sx, dens), kext));
+        colden = xadd(colden, xmul(sx, dens));
+    }
+    colden_out[id] = xmul(colden, M.length);
+    tau_out[id] = TAU;
+}
+
 }  // namespace
+
+void launch_pstau(const MapArgs &M, int no, const float *pspos, float *colden, float *tau, cudaStream_t stream) {
+    const bool oct = M.G.levels > 1, dbl = M.G.dbl_map != 0;
+    const int threads = 32, blocks = (no + threads - 1) / threads;
+    if (!oct)      pstau_kernel<false, false><<<blocks, threads, 0, stream>>>(M, no, pspos, colden, tau);
+    else if (!dbl) pstau_kernel<true, false><<<blocks, threads, 0, stream>>>(M, no, pspos, colden, tau);
+    else           pstau_kernel<true, true><<<blocks, threads, 0, stream>>>(M, no, pspos, colden, tau);
+}
 
 void launch_mapping(const MapArgs &M, bool healpix, cudaStream_t stream) {
     const bool oct = M.G.levels > 1, dbl = M.G.dbl_map != 0;

@@ -13,3 +13,4 @@ struct MapArgs {
 };
 
 void launch_mapping(const MapArgs &M, bool healpix, cudaStream_t stream);
+void launch_pstau(const MapArgs &M, int no, const float *pspos, float *colden, float *tau, cudaStream_t stream);

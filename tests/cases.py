@@ -152,6 +152,26 @@ def run_hpmap(nside, intobs):
     return run
 
 
+def run_pstau(pspos, dirs, abu=False):
+    def run(X):
+        c = X.cloud
+        k = _tau_scale(c, 1.0)
+        rng = np.random.default_rng(9)
+        opt = None
+        if abu:
+            opt = np.empty((c.CELLS, 2), np.float32)
+            opt[:, 0] = k * (0.5 + rng.random(c.CELLS))
+            opt[:, 1] = k * (0.5 + rng.random(c.CELLS))
+            opt = opt.reshape(-1)
+        _, od, ra, de = observer_directions([d[0] for d in dirs], [d[1] for d in dirs])
+        out = {}
+        for i in range(len(dirs)):
+            col, tau = X.ps_tau(np.asarray(pspos, np.float32).reshape(-1), od[i], 1.2 * k, 0.8 * k, opt=opt)
+            out["colden%d" % i], out["tau%d" % i] = col.copy(), tau.copy()
+        return out
+    return run
+
+
 def run_sca(kind, npix=(24, 20), dirs=((0.0, 0.0), (70.0, 30.0)), batch=3, glob=1024, seed=0.61, pspos=None):
     def run(X):
         c = X.cloud
@@ -202,6 +222,8 @@ CASES = {
     "map_oct6_4_thr":  (_oct(6, 4, 0.25, 8), dict(level_threshold=1), run_map((20, 20), [(120.0, 200.0)], map_dx=0.35)),
     "map_reg16_persp": (_reg(16), {}, run_map((32, 16), [(0.0, 0.0)], intobs=(7.3, 8.4, 9.1))),
     "hpmap_oct8_3":    (_oct(8, 3), {}, run_hpmap(8, (4.2, 3.3, 5.1))),
+    "map_pstau_reg16":  (_reg(16), dict(no_ps=3), run_pstau([(8.3, 8.3, 8.3), (2.2, 13.1, 5.5), (15.6, 0.7, 9.9)], [(0.0, 0.0), (60.0, 30.0)])),
+    "map_pstau_oct8":   (_oct(8, 3), dict(no_ps=2, with_abu=1), run_pstau([(4.3, 4.2, 3.9), (1.1, 6.8, 2.4)], [(35.0, 110.0)], abu=True)),
     "sca_ps_reg16":    (_reg(16), dict(no_ps=2), run_sca("ps", pspos=[(8.3, 8.3, 8.3), (4.1, 10.7, 12.2)])),
     "sca_ps_oct8":     (_oct(8, 3), dict(no_ps=1, ffs=0), run_sca("ps", pspos=[(4.3, 4.2, 3.9)], batch=8)),
     "sca_bg_reg12":    (_reg(12), {}, run_sca("bg", batch=1)),

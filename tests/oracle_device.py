@@ -177,6 +177,9 @@ class OracleDevice:
                                       save_colden=save_colden)
         self.buf[bk.BUF_MAP], self.buf[bk.BUF_SAVETAU] = m, t
 
+    def ps_tau(self, no, dir_, abs_, sca):
+        return self.O.ps_tau(self.buf[bk.BUF_PSPOS][:3 * no], dir_, abs_, sca, opt=self._g(bk.BUF_OPT))
+
     def sca_zero_out(self, ndir, npx, npy):
         self.buf[bk.BUF_OUT] = np.zeros(ndir * npx * npy, np.float32)
 
