@@ -820,6 +820,18 @@ def main(argv=None, device_factory=None):
                 print("IFREQ=%3d/%3d  %9.2f um -- save_spe %d, save_tau %d, save_colden %d" % (IFREQ, NFREQ, um, save_spe, save_tau, save_colden))
         for fp in fpmap:
             fp.close()
+    if USER.NO_PS > 0 and USER.pssavetau_freq > 0.0 and USER.NPIX['y'] > 0 and root and len(USER.OBS_THETA) > 0:
+        # column density and optical depth from each point source towards the observers (ASOC.py:3576-3644)
+        IFREQ = int(np.argmin(np.abs(FFREQ - USER.pssavetau_freq)))
+        if abs(FFREQ[IFREQ] - USER.pssavetau_freq) > 0.001 * FFREQ[IFREQ]:
+            print("*** Requested frequency for PSSAVETAU is not in the frequency grid")
+        kabs, ksca = set_opacity(IFREQ)
+        dev.upload(bk.BUF_PSPOS, np.ascontiguousarray(USER.PSPOS[:USER.NO_PS].reshape(-1)))
+        for idir in range(len(USER.OBS_THETA)):
+            pscolden, pstau = dev.ps_tau(USER.NO_PS, ODIR[idir], kabs, ksca)
+            with open("%s_%d.dat" % (USER.file_pssavetau, idir), "w") as fp:
+                for i in range(USER.NO_PS):
+                    fp.write('%6d  %12.4e  %12.4e\n' % (i, pscolden[i], pstau[i]))
     Tmap = time.time() - t0
 
     if root and EMITTED is not None and not USER.MMAP_EMITTED and (not USER.NOSOLVE or USER.LOAD_TEMPERATURE):

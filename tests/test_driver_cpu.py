@@ -55,6 +55,13 @@ def test_background_run_writes_the_reference_files(tmp_path):
         assert m.shape == (8, 10, 10) and np.isfinite(m).all() and m[:4].min() > 0.0
 
 
+def test_pssavetau_writes_source_optical_depths(tmp_path):
+    _run(tmp_path, n=8, bgpac=10000, pspac=33000, extra="pssavetau pstau 100.0\n")
+    rows = np.loadtxt(str(tmp_path / "pstau_0.dat"), ndmin=2)
+    assert rows.shape == (1, 3) and rows[0, 1] > 0 and rows[0, 2] > 0
+    assert os.path.exists(str(tmp_path / "pstau_1.dat"))
+
+
 def test_absorbed_file_and_octree(tmp_path):
     cloud = _run(tmp_path, n=6, octree=True, bgpac=20000, pspac=33000, noabsorbed=False, absorbed=True, maps=False)
     a = read_cells_freq_file(str(tmp_path / "abs.data"))
