@@ -334,7 +334,7 @@ def run_ours(args):
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
-                         "kernel": "sim_fast_kernel<DEP_WARP,false> (background launch)",
+                         "kernel": "sim_lean_kernel<DEP_RED,%s> (background launch)" % ("brick" if os.environ.get("SOC_LAYOUT", "1") != "0" else "linear"),
                          "kernel_ms": kavg, "cell_steps_per_launch": ksteps, "alg_bytes_per_cell_step": ALG_BYTES_PER_STEP,
                          "peak_source": peak_src},
             "stuck_packets": counts[3].item(),

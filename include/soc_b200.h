@@ -30,7 +30,7 @@
  * New (no counterpart in the single-device reference):
  *   soc_set_shard, soc_device_ptr           packet sharding over ranks and the device addresses a
  *                                           host-side NCCL all-reduce needs
- *   soc_set_rng_mode, soc_set_tuning, soc_set_geometry,
+ *   soc_set_rng_mode, soc_set_tuning, soc_set_geometry, soc_set_layout,
  *   soc_get_counters, soc_last_launch_ms,
  *   soc_stream                              stream layout, accumulation engine, work counters, device timing
  */
@@ -125,6 +125,11 @@ int  soc_set_tuning(soc_context *ctx, int deposit_mode, int refill_lanes, int ag
  * reference's GetStep arithmetic (PEPS overshoot, 2*PEPS pull-back at scatterings, kernel_ASOC_aux.c:282-315).
  * The two differ only where the mean free path is comparable to PEPS = 1e-4 cells. */
 int  soc_set_geometry(soc_context *ctx, int mode);
+
+/* Cell order of the density / scratch accumulator inside the production kernel for regular grids with even
+ * dimensions: 1 (default) = 2x2x2 bricks (one 32-byte sector per brick), 0 = the reference's x-fastest order.
+ * Buffers seen through this ABI always use the reference order. */
+int  soc_set_layout(soc_context *ctx, int mode);
 
 int  soc_upload(soc_context *ctx, int buffer, const void *host, size_t nbytes);
 int  soc_download(soc_context *ctx, int buffer, void *host, size_t nbytes);

@@ -41,6 +41,8 @@ struct soc_context {
     DevBuf buf[SOC_BUF_COUNT];
     unsigned long long *counters;      // device: packets, steps, scatterings, stuck, peels, work, -, -
     float *acc; size_t acc_bytes;      // per-launch scratch accumulator of the stream kernels (all zero between launches)
+    float *dens_brick;                 // regular grids with even dimensions: DENS in 2x2x2-brick order (lean kernel)
+    int layout;                        // 1 = use the bricked copy where the kernel supports it
     unsigned long long launches;
     soc_params P;
     bool have_params, have_grid;
@@ -102,7 +104,8 @@ int soc_create(int device_ordinal, soc_context **out) {
     c->device = device_ordinal; c->sms = prop.multiProcessorCount;
     c->rng_mode = SOC_RNG_PACKET; c->rank = 0; c->world = 1;
     c->deposit = DEP_TILE; c->refill = 8; c->agg_steps = 24; c->sc_batch = 0;        // 0 = by grid type
-    c->nav_hops = 1;
+    c->nav_hops = 1; c->layout = 1;
+    if (const char *e = getenv("SOC_LAYOUT")) c->layout = atoi(e) != 0;                                               // tuning knob
     if (const char *e = getenv("SOC_NAV_HOPS")) { int v = atoi(e); if (v >= 1 && v <= 8) c->nav_hops = v; }          // tuning knob
     if (const char *e = getenv("SOC_SC_BATCH")) { int v = atoi(e); if (v >= 1 && v <= 32) c->sc_batch = v; }   // tuning knob
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -123,6 +126,7 @@ int soc_destroy(soc_context *c) {
     for (int b = 0; b < SOC_BUF_COUNT; b++) if (c->buf[b].ptr) cudaFree(c->buf[b].ptr);
     cudaFree(c->counters);
     if (c->acc) cudaFree(c->acc);
+    if (c->dens_brick) cudaFree(c->dens_brick);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -181,6 +185,12 @@ int soc_set_grid(soc_context *c, int32_t nx, int32_t ny, int32_t nz, int32_t lev
     G.dens = dptr<float>(c, SOC_BUF_DENS);
     G.par = dptr<int>(c, SOC_BUF_PAR);
     if (levels > 1) { launch_parents(G, dptr<int>(c, SOC_BUF_PAR), c->stream); c->launches += levels - 1; }
+    if (c->dens_brick) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->dens_brick)); c->dens_brick = nullptr; }
+    if (levels == 1 && nx % 2 == 0 && ny % 2 == 0 && nz % 2 == 0) {
+        CU(cudaMalloc(&c->dens_brick, (size_t)cells * 4));
+        launch_brick_permute(G, c->dens_brick, c->stream);
+        c->launches++;
+    }
     CU(cudaGetLastError());
     c->have_grid = true;
     return SOC_OK;
@@ -205,6 +215,13 @@ int soc_set_tuning(soc_context *c, int deposit_mode, int refill_lanes, int aggre
     if (deposit_mode < DEP_RED || deposit_mode > DEP_TILE) return fail(SOC_ERR_ARG, "soc_set_tuning: deposit mode %d", deposit_mode);
     if (refill_lanes < 1 || refill_lanes > 32) return fail(SOC_ERR_ARG, "soc_set_tuning: refill lanes %d", refill_lanes);
     c->deposit = deposit_mode; c->refill = refill_lanes; c->agg_steps = aggregate_steps;
+    return SOC_OK;
+}
+
+int soc_set_layout(soc_context *c, int mode) {
+    NEED_CTX(c);
+    if (mode != 0 && mode != 1) return fail(SOC_ERR_ARG, "soc_set_layout: %d", mode);
+    c->layout = mode;
     return SOC_OK;
 }
 
@@ -331,6 +348,7 @@ static int sim_common(soc_context *c, SimArgs &A, int kind, int batch, float see
 }
 
 static int sim_launch(soc_context *c, SimArgs &A, const char *who) {
+    A.nlocal = (A.nunits - A.rank + A.world - 1) / A.world;
     const bool oct = A.G.levels > 1, dbl = A.G.dbl_sim != 0;
     int threads, blocks;
     if (c->rng_mode == SOC_RNG_REFERENCE) {
@@ -355,6 +373,9 @@ static int sim_launch(soc_context *c, SimArgs &A, const char *who) {
             CU(cudaMemsetAsync(c->acc, 0, n, c->stream));
         }
         A.acc = c->acc; A.use_acc = 1;
+        A.dens_brick = c->layout ? c->dens_brick : nullptr;
+        A.brick = sim_uses_bricks(A, c->rng_mode) ? 1 : 0;
+        A.slab_xy = A.G.nx * A.G.ny; A.brick_by = 4 * A.G.nx - 2; A.brick_bz = 2 * A.G.nx * A.G.ny - 4;
     }
     CU(cudaEventRecord(c->ev0, c->stream));
     launch_sim(A, c->rng_mode, blocks, threads, c->stream);
@@ -404,7 +425,7 @@ int soc_sim_pb(soc_context *c, int source, int packets, int batch, float seed, f
             A.tile_x0 = o[0]; A.tile_y0 = o[1]; A.tile_z0 = o[2];
             A.tile_lo = o[2] * c->G.nx * c->G.ny;
             A.tile_span = SOC_TILE_N * c->G.nx * c->G.ny;
-        } else A.deposit = DEP_WARP;
+        } else A.deposit = (source == 0) ? DEP_WARP : DEP_RED;     // background packets do not share cells: plain adds
     }
     return sim_launch(c, A, "soc_sim_pb");
 }

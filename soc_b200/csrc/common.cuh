@@ -56,6 +56,10 @@ __device__ __forceinline__ vec3 normalize3(vec3 a) {
 }
 // a.x*b.x + a.y*b.y + a.z*b.z evaluated left to right without contraction
 __device__ __forceinline__ float dot3(const vec3 &a, const vec3 &b) { return xadd(xadd(xmul(a.x, b.x), xmul(a.y, b.y)), xmul(a.z, b.z)); }
+// 2^x through the SFU (ex2.approx.ftz: max relative error 2^-22)
+__device__ __forceinline__ float exp2f_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// 1/x through the SFU (rcp.approx.ftz: max relative error 2^-23), for normal x
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 

@@ -631,6 +631,234 @@ __global__ void __launch_bounds__(256, 4) sim_fast_kernel(const __grid_constant_
 }
 
 // =================================================================================================================
+// Lean kernel: the fast kernel for the common run (scalar opacities, TABS/INT only, point-source / background /
+// Healpix packets), rewritten for the two limits ncu showed on the fast kernel -- instruction issue (~200 warp
+// instructions per cell-step iteration) and the L1 -> L2 request interface (one RED plus 0.74 gather misses per
+// step):
+//   * per-axis state is (face distance, crossings left before the packet leaves the grid, index increment): the
+//     step is FMNMX3 + two compares + selects, no coordinate arithmetic, no bounds compare against the dimensions;
+//   * the absorbed fraction comes from ex2.approx (>= 0.01) or a 3-term series (< 0.01, error < 5e-8 relative);
+//     deposit = P*d and P -= deposit, so the energy of a packet is conserved to rounding;
+//   * scatter distance through rcp.approx, all of it branch-free; work counters live in shared memory and are
+//     touched once per packet (they were spilled to local memory and updated every iteration);
+//   * BRICK: DENS and the scratch accumulator are stored in 2x2x2 bricks = one 32-byte sector per brick, the cell
+//     behind the next face is in the sector just touched with probability 1/2 for any direction (x-fastest order:
+//     7/8 for steps along x, 0 otherwise = 0.29 on average).  The index increment per axis is one of two values
+//     picked by the parity bit of the axis, which is a bit of the bricked index itself.
+// Same Philox packet streams, same draw order and same physics as the fast kernel.
+// =================================================================================================================
+__device__ __forceinline__ int brick_index(int ix, int iy, int iz, int hx, int hy) {
+    return ((((iz >> 1) * hy + (iy >> 1)) * hx + (ix >> 1)) << 3) | ((iz & 1) << 2) | ((iy & 1) << 1) | (ix & 1);
+}
+
+template <bool BRICK>
+struct LeanPk {
+    float tx, ty, tz, rdx, rdy, rdz;     // distance to the next face per axis; 1/|d| (the direction itself is not kept:
+                                         // |d_i| = 1/rd_i, sign from upm)
+    int cx, cy, cz;                  // cell crossings left along each axis before the packet leaves the grid
+    int ind;                         // index of the current cell in the layout of the density array
+    int upm;                         // bit a set: the packet moves towards +axis a
+    float rho, photons, free_path, tau;
+    unsigned sn;                     // cell-steps taken (low 24 bits) and scatterings (high 8 bits) of the packet
+    unsigned u;                      // work unit of this rank; the Philox stream id is u*world + rank
+};
+#define LEAN_STEPS(sn) ((sn) & 0xffffffu)
+#define LEAN_SCAT(sn)  ((sn) >> 24)
+
+// direction-dependent part of the state from the fractional position (fx,fy,fz) inside cell (ix,iy,iz)
+template <bool BRICK>
+__device__ __forceinline__ void lean_set_direction(const GridDesc &G, LeanPk<BRICK> &f, const vec3 &d, int ix, int iy, int iz,
+                                                   float fx, float fy, float fz) {
+    f.rdx = rcp_approx(fabsf(d.x)); f.rdy = rcp_approx(fabsf(d.y)); f.rdz = rcp_approx(fabsf(d.z));     // |d_i| >= DEPS/sqrt(3)
+    f.tx = face_distance(fx, d.x, f.rdx); f.ty = face_distance(fy, d.y, f.rdy); f.tz = face_distance(fz, d.z, f.rdz);
+    const bool ux = d.x > 0.0f, uy = d.y > 0.0f, uz = d.z > 0.0f;
+    f.cx = ux ? G.nx - 1 - ix : ix; f.cy = uy ? G.ny - 1 - iy : iy; f.cz = uz ? G.nz - 1 - iz : iz;
+    f.upm = (ux ? 1 : 0) | (uy ? 2 : 0) | (uz ? 4 : 0);
+}
+
+// work counters: 32-bit native shared-memory adds, spilled to the 64-bit global counter before they can wrap
+__device__ __forceinline__ void count_add(unsigned *s32, unsigned long long *g64, unsigned v) {
+    const unsigned old = atomicAdd(s32, v);
+    if (old < 0x80000000u && old + v >= 0x80000000u) { atomicSub(s32, 0x80000000u); atomicAdd(g64, 0x80000000ull); }
+}
+
+template <int DEP, bool BRICK>
+__global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant__ SimArgs A) {
+    __shared__ float smem[DEP == DEP_TILE ? SOC_TILE_CELLS : 1];
+    __shared__ unsigned s_cnt[4];
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
+    float *tile = nullptr;
+    if (DEP == DEP_TILE) tile = tile_begin(A, smem); else __syncthreads();
+    const GridDesc &G = A.G;
+    const float *__restrict__ dens = BRICK ? A.dens_brick : G.dens;
+    const int lane = threadIdx.x & 31;
+    const float kabs = A.kabs, ksca = A.ksca;
+    LeanPk<BRICK> f; f.ind = 0; f.u = 0; f.rho = 0.0f; f.sn = 0;
+    bool alive = false, wsc = false;
+    bool more = true;                                        // warp-uniform: the work counter has not run out yet
+    for (;;) {
+        unsigned live = __ballot_sync(FULL, alive);
+        if (more ? (32 - __popc(live) >= A.refill) : (live == 0u)) {
+            if (!more) break;
+            const unsigned nm = ~live;                       // lanes that take a new packet
+            const int leader = __ffs(nm) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(A.work, (unsigned long long)__popc(nm));
+            base = __shfl_sync(FULL, base, leader);
+            if (!alive) {
+                const unsigned long long u = base + __popc(nm & ((1u << lane) - 1u));
+                if (u < (unsigned long long)A.nlocal) {
+                    const unsigned long long q = u * A.world + A.rank;
+                    RngPhilox rng; rng.seed(A.phx, q);
+                    Packet pk; pk.ind = -1; pk.level = 0; pk.eidx = -1; pk.rho = 0.0f;
+                    const int id = (int)(q / (unsigned)A.batch), III = (int)(q % (unsigned)A.batch);
+                    if (A.kind == SIM_PS)      emit_ps<SimArgs, RngPhilox, false>(A, rng, III, pk);
+                    else if (A.kind == SIM_BG) emit_bg<SimArgs, RngPhilox, false>(A, rng, id, pk);
+                    else                       emit_hp<RngPhilox, false>(A, rng, pk);
+                    start_packet(A, rng, pk, A.kind != SIM_HP);
+                    if (pk.ind >= 0) {
+                        alive = true; wsc = false;
+                        const int ix = clampi((int)floorf(pk.pos.x), 0, G.nx - 1), iy = clampi((int)floorf(pk.pos.y), 0, G.ny - 1),
+                                  iz = clampi((int)floorf(pk.pos.z), 0, G.nz - 1);
+                        lean_set_direction<BRICK>(G, f, pk.dir, ix, iy, iz, pk.pos.x - (float)ix, pk.pos.y - (float)iy, pk.pos.z - (float)iz);
+                        f.ind = BRICK ? brick_index(ix, iy, iz, G.nx >> 1, G.ny >> 1) : (iz * G.ny + iy) * G.nx + ix;
+                        f.rho = pk.rho; f.photons = pk.photons; f.free_path = pk.free_path; f.tau = 0.0f;
+                        f.sn = 0; f.u = (unsigned)u;
+                    }
+                }
+            }
+            more = base + (unsigned long long)__popc(nm) < (unsigned long long)A.nlocal;
+            if (lane == leader) {                                  // packets started by this warp
+                const unsigned long long left = base < (unsigned long long)A.nlocal ? (unsigned long long)A.nlocal - base : 0ull;
+                count_add(&s_cnt[0], A.counters + 0, (unsigned)min((unsigned long long)__popc(nm), left));
+            }
+            live = __ballot_sync(FULL, alive);
+            if (live == 0u && !more) break;
+        }
+        // ---- scatterings, batched over the lanes of the warp (see sim_fast_kernel) ------------------------------
+        {
+            const unsigned sm = __ballot_sync(FULL, wsc);
+            if (sm != 0u && (__popc(sm) >= A.sc_batch || sm == live)) {
+                if (wsc) {
+                    const bool ux = (f.upm & 1) != 0, uy = (f.upm & 2) != 0, uz = (f.upm & 4) != 0;
+                    const float adx = rcp_approx(f.rdx), ady = rcp_approx(f.rdy), adz = rcp_approx(f.rdz);
+                    const float ax = f.tx * adx, ay = f.ty * ady, az = f.tz * adz;
+                    const float fx = ux ? 1.0f - ax : ax, fy = uy ? 1.0f - ay : ay, fz = uz ? 1.0f - az : az;
+                    const int ix = ux ? G.nx - 1 - f.cx : f.cx, iy = uy ? G.ny - 1 - f.cy : f.cy, iz = uz ? G.nz - 1 - f.cz : f.cz;
+                    RngBlock rb(A.phx, (unsigned long long)f.u * A.world + A.rank, 0x10000u + LEAN_SCAT(f.sn));
+                    f.free_path = free_path_fast(A, rb, f.photons);
+                    const float ct = __ldg(A.csc + clampi((int)(rb.uniform() * A.bins), 0, A.bins - 1));
+                    vec3 nd = { ux ? adx : -adx, uy ? ady : -ady, uz ? adz : -adz };
+                    scatter_rotate(nd, ct, SOC_TWOPI * rb.uniform());
+                    lean_set_direction<BRICK>(G, f, nd, ix, iy, iz, fx, fy, fz);
+                    f.tau = 0.0f;
+                    wsc = false;
+                }
+            }
+        }
+        // ---- one cell-step ---------------------------------------------------------------------------------------
+        const bool run = alive && !wsc;
+        float delta = 0.0f, tmin = 0.0f, rho_n = 0.0f;
+        int nind = 0;
+        bool px = false, py = false, inb = false, sc = false;
+        const int oind = f.ind;
+        if (run) {
+            tmin = fminf(f.tx, fminf(f.ty, f.tz));
+            px = f.tx == tmin; py = !px && (f.ty == tmin);
+            // index increment: x-fastest order +-(1, nx, nx*ny); bricks: +-(1,2,4) inside the brick (the parity bit of the
+            // axis, a bit of the index itself, tells on which side of its brick the cell lies), else to the next brick
+            const int abit = px ? 1 : (py ? 2 : 4);
+            int mag;
+            if (BRICK) mag = (((f.ind ^ f.upm) & abit) != 0) ? abit : (px ? 7 : (py ? A.brick_by : A.brick_bz));
+            else       mag = px ? 1 : (py ? G.nx : A.slab_xy);
+            const int step = (f.upm & abit) ? mag : -mag;
+            const int crem = px ? f.cx : (py ? f.cy : f.cz);
+            nind = f.ind + step;
+            inb = crem > 0;
+            if (inb) rho_n = __ldg(dens + nind);
+            const float krho = ksca * f.rho;
+            const float tend = fmaf(tmin, krho, f.tau);
+            sc = f.free_path < tend;
+            const float tsc = (f.free_path - f.tau) * rcp_approx(krho);
+            if (sc) { tmin = fminf(tmin, tsc); f.sn += 1u << 24; } else f.tau = tend;
+            const float x = tmin * f.rho * kabs;
+            const float e = exp2f_approx(-1.4426950408889634f * x);
+            const float ser = x * fmaf(x, fmaf(x, 0.16666667f, -0.5f), 1.0f);
+            const float dfrac = (x < 0.01f) ? ser : (1.0f - e);
+            delta = f.photons * dfrac;
+            f.photons -= delta;
+            f.sn++;
+        }
+        // ---- deposit ----------------------------------------------------------------------------------------------
+        bool d = run;
+        if (DEP != DEP_RED) {
+            if (__any_sync(FULL, d && LEAN_STEPS(f.sn) < (unsigned)A.agg_steps)) {
+                const unsigned act = __ballot_sync(FULL, d);
+                if (d) {
+                    const unsigned peers = __match_any_sync(act, oind);
+                    if (peers != (1u << lane)) {
+                        delta = reduce_peers(peers, delta, lane);
+                        if (lane != __ffs(peers) - 1) d = false;
+                    }
+                }
+            }
+        }
+        if (d) {
+            bool in_tile = false;
+            if (DEP == DEP_TILE) {
+                // tile_lo/tile_span select the z-slab of the tile in the layout in use (set by the host)
+                if ((unsigned)(oind - A.tile_lo) < (unsigned)A.tile_span) {
+                    // coordinates at the time of the deposit: the crossing counters have not been updated yet
+                    const int ix = (f.upm & 1) ? G.nx - 1 - f.cx : f.cx, iy = (f.upm & 2) ? G.ny - 1 - f.cy : f.cy,
+                              iz = (f.upm & 4) ? G.nz - 1 - f.cz : f.cz;
+                    const unsigned ux = (unsigned)(ix - A.tile_x0), uy = (unsigned)(iy - A.tile_y0), uz = (unsigned)(iz - A.tile_z0);
+                    if (ux < SOC_TILE_N && uy < SOC_TILE_N && uz < SOC_TILE_N) {
+                        atomicAdd(&tile[(uz * SOC_TILE_N + uy) * SOC_TILE_N + ux], delta);
+                        in_tile = true;
+                    }
+                }
+            }
+            if (!in_tile) red_add(&A.acc[oind], delta);
+        }
+        if (run) {
+            f.tx -= tmin; f.ty -= tmin; f.tz -= tmin;
+            if (sc) {
+                wsc = true;
+                if (LEAN_SCAT(f.sn) > 20u) { alive = false; wsc = false; }
+            } else {
+                if (px)      { f.cx--; f.tx = f.rdx; }
+                else if (py) { f.cy--; f.ty = f.rdy; }
+                else         { f.cz--; f.tz = f.rdz; }
+                f.ind = nind; f.rho = rho_n;
+                alive = inb;
+            }
+            bool stuck = false;
+            if (LEAN_STEPS(f.sn) > (unsigned)A.max_steps) { alive = false; wsc = false; stuck = true; }
+            if (!alive) {                                       // packet finished: once per packet
+                count_add(&s_cnt[1], A.counters + 1, LEAN_STEPS(f.sn));
+                count_add(&s_cnt[2], A.counters + 2, min(LEAN_SCAT(f.sn), 20u));
+                if (stuck) count_add(&s_cnt[3], A.counters + 3, 1u);
+            }
+        }
+    }
+    if (DEP == DEP_TILE) {
+        // un-brick the tile flush: tile_end() adds into A.acc with x-fastest indices
+        __syncthreads();
+        for (int i = threadIdx.x; i < SOC_TILE_CELLS; i += blockDim.x) {
+            const float v = tile[i];
+            if (v != 0.0f) {
+                const int ux = i % SOC_TILE_N, uy = (i / SOC_TILE_N) % SOC_TILE_N, uz = i / (SOC_TILE_N * SOC_TILE_N);
+                const int ix = A.tile_x0 + ux, iy = A.tile_y0 + uy, iz = A.tile_z0 + uz;
+                if (ix < G.nx && iy < G.ny && iz < G.nz)
+                    red_add(&A.acc[BRICK ? brick_index(ix, iy, iz, G.nx >> 1, G.ny >> 1) : (iz * G.ny + iy) * G.nx + ix], v);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 4 && s_cnt[threadIdx.x]) atomicAdd(A.counters + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
+}
+
+// =================================================================================================================
 // Walk kernel: the production path on octree clouds (LEVELS > 1).  Same persistent-warp / refill / Philox /
 // scratch-accumulator design as the fast kernel; the stepping is the incremental octree walk of walk.cuh, taken
 // one hop (climb / cross / descend) per loop iteration so that lanes with long climbs do not idle the warp.
@@ -831,18 +1059,35 @@ struct RngMwcItem : RngMwc {
 
 }  // namespace
 
+template <bool BRICK>
+static void launch_lean(SimArgs A, int dep, int blocks, int threads, cudaStream_t stream) {
+    if (BRICK && dep == DEP_TILE) {          // z-slab of the shared-memory tile in bricked order
+        const int slab = 2 * A.G.nx * A.G.ny, z0 = A.tile_z0;
+        A.tile_lo = (z0 >> 1) * slab;
+        A.tile_span = (((z0 + SOC_TILE_N - 1) >> 1) - (z0 >> 1) + 1) * slab;
+    }
+    if (dep == DEP_RED)       sim_lean_kernel<DEP_RED, BRICK><<<blocks, threads, 0, stream>>>(A);
+    else if (dep == DEP_WARP) sim_lean_kernel<DEP_WARP, BRICK><<<blocks, threads, 0, stream>>>(A);
+    else                      sim_lean_kernel<DEP_TILE, BRICK><<<blocks, threads, 0, stream>>>(A);
+}
+
+static bool sim_is_general(const SimArgs &A) { return A.with_abu || A.save_int2 || A.with_ali || A.kind == SIM_CL; }
+
+// the lean kernel keeps the work unit in 32 bits and the step count of a packet in 24
+static bool sim_uses_lean(const SimArgs &A) { return !sim_is_general(A) && A.nlocal < (1LL << 32) && A.max_steps < (1 << 24) - 2; }
+
 static void launch_fast(const SimArgs &A, int blocks, int threads, cudaStream_t stream) {
-    const bool general = A.with_abu || A.save_int2 || A.with_ali || A.kind == SIM_CL;
     const int dep = (A.save_int2 || A.with_ali) ? DEP_RED : A.deposit;
-    if (general) {
+    if (!sim_uses_lean(A)) {
         if (dep == DEP_RED)       sim_fast_kernel<DEP_RED, true><<<blocks, threads, 0, stream>>>(A);
         else if (dep == DEP_WARP) sim_fast_kernel<DEP_WARP, true><<<blocks, threads, 0, stream>>>(A);
         else                      sim_fast_kernel<DEP_TILE, true><<<blocks, threads, 0, stream>>>(A);
-    } else {
-        if (dep == DEP_RED)       sim_fast_kernel<DEP_RED, false><<<blocks, threads, 0, stream>>>(A);
-        else if (dep == DEP_WARP) sim_fast_kernel<DEP_WARP, false><<<blocks, threads, 0, stream>>>(A);
-        else                      sim_fast_kernel<DEP_TILE, false><<<blocks, threads, 0, stream>>>(A);
-    }
+    } else if (A.brick) launch_lean<true>(A, dep, blocks, threads, stream);
+    else                launch_lean<false>(A, dep, blocks, threads, stream);
+}
+
+bool sim_uses_bricks(const SimArgs &A, int rng_mode) {
+    return sim_uses_lean(A) && rng_mode != SOC_RNG_REFERENCE && A.G.levels == 1 && !A.ref_geometry && !sim_is_general(A) && A.dens_brick != nullptr;
 }
 
 void launch_sim(const SimArgs &A, int rng_mode, int blocks, int threads, cudaStream_t stream) {
@@ -867,16 +1112,63 @@ int sim_blocks_per_sm(int rng_mode, bool octree, bool dbl, int threads) {
         else if (!dbl) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sim_item_kernel<RngMwcItem, true, false>, threads, 0);
         else           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sim_item_kernel<RngMwcItem, true, true>, threads, 0);
     } else {
-        if (!octree)   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sim_fast_kernel<DEP_TILE, true>, threads, 0);
+        if (!octree)   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sim_fast_kernel<DEP_TILE, true>, threads, 0);   // == the lean kernels (launch bounds 256 x 4)
         else           cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sim_walk_kernel<DEP_WARP, true>, threads, 0);
     }
     return n > 0 ? n : 1;
 }
 
+// bricked scratch accumulator -> TABS / INT in the reference's cell order.  One thread per x-pair of a brick: the
+// accumulator is read as float2 in its own order (coalesced), TABS / INT are updated 8 bytes at a time.
+__global__ void __launch_bounds__(256) fold_acc_brick_kernel(float *__restrict__ acc, float *__restrict__ tabs, float *__restrict__ inten,
+                                                             float scale, int nx, int ny, long long npairs) {
+    const int hx = nx >> 1, hy = ny >> 1;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += stride) {
+        float2 a = reinterpret_cast<float2 *>(acc)[i];
+        if (a.x != 0.0f || a.y != 0.0f) {
+            const long long b = i >> 2;
+            const int sub = (int)(i & 3);                         // (z parity, y parity)
+            const int bx = (int)(b % hx), by = (int)((b / hx) % hy), bz = (int)(b / ((long long)hx * hy));
+            const long long lin = ((long long)(2 * bz + (sub >> 1)) * ny + (2 * by + (sub & 1))) * nx + 2 * bx;
+            float2 t = *reinterpret_cast<float2 *>(tabs + lin);
+            t.x += a.x * scale; t.y += a.y * scale;
+            *reinterpret_cast<float2 *>(tabs + lin) = t;
+            if (inten != nullptr) {
+                float2 v = *reinterpret_cast<float2 *>(inten + lin);
+                v.x += a.x; v.y += a.y;
+                *reinterpret_cast<float2 *>(inten + lin) = v;
+            }
+            reinterpret_cast<float2 *>(acc)[i] = make_float2(0.0f, 0.0f);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) brick_permute_kernel(const float *__restrict__ dens, float *__restrict__ out, int nx, int ny, long long n) {
+    const int hx = nx >> 1, hy = ny >> 1;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const long long b = i >> 3;
+        const int sub = (int)(i & 7);
+        const int bx = (int)(b % hx), by = (int)((b / hx) % hy), bz = (int)(b / ((long long)hx * hy));
+        out[i] = dens[((long long)(2 * bz + (sub >> 2)) * ny + (2 * by + ((sub >> 1) & 1))) * nx + 2 * bx + (sub & 1)];
+    }
+}
+
+static int stream_grid(long long n) {
+    long long b = (n + 255) / 256;
+    const long long cap = 148LL * 8;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+void launch_brick_permute(const GridDesc &G, float *dens_brick, cudaStream_t stream) {
+    const long long n = G.nxyz;
+    brick_permute_kernel<<<stream_grid(n), 256, 0, stream>>>(G.dens, dens_brick, G.nx, G.ny, n);
+}
+
 void launch_fold_acc(const SimArgs &A, cudaStream_t stream) {
     const long long n = A.G.cells;
-    long long b = ((n >> 2) + 255) / 256;
-    const long long cap = 148LL * 8;
-    fold_acc_kernel<<<(int)(b < 1 ? 1 : (b > cap ? cap : b)), 256, 0, stream>>>(A.acc, A.tabs, A.use_int ? A.inten : nullptr,
-                                                                              A.tw * A.adhoc, n);
+    const float scale = A.tw * A.adhoc;
+    if (A.brick) fold_acc_brick_kernel<<<stream_grid(n >> 1), 256, 0, stream>>>(A.acc, A.tabs, A.use_int ? A.inten : nullptr, scale, A.G.nx, A.G.ny, n >> 1);
+    else         fold_acc_kernel<<<stream_grid(n >> 2), 256, 0, stream>>>(A.acc, A.tabs, A.use_int ? A.inten : nullptr, scale, n);
 }

@@ -22,6 +22,12 @@ struct SimArgs {
     // fold_acc() spreads it to TABS (x TW*ADHOC) and INT afterwards -- one atomic per cell-step instead of two
     float *acc;
     int use_acc;
+    // regular grids with even dimensions: a second copy of DENS in 2x2x2 bricks (one 32-byte sector per brick), so
+    // that the cell entered next shares the sector of the current one half of the time; `acc` then uses the same
+    // order and fold_acc() un-bricks it (brick = 1)
+    const float *__restrict__ dens_brick;
+    int brick;
+    int slab_xy, brick_by, brick_bz;   // nx*ny; index increments to the next brick along y and z
     // inputs
     const float *__restrict__ emit, *__restrict__ emwei, *__restrict__ opt;
     const float *__restrict__ dsc, *__restrict__ csc;
@@ -31,6 +37,7 @@ struct SimArgs {
     float kabs, ksca, bg, tw, adhoc, sw_a, sw_b;
     int kind, batch, global;
     int bins, no_ps, ps_method, with_abu, with_ali, use_int, save_int2, use_emweight, hpbg_weighted, step_weight;
+    long long nlocal;            // units of this rank: ceil((nunits - rank) / world)
     long long nunits;            // work units: reference work items (RNG mode 0) or packets / cells (mode 1)
     int rank, world;
     int max_steps;               // guard against packets that never leave (counted as stuck)
@@ -50,4 +57,6 @@ struct SimArgs {
 
 void launch_sim(const SimArgs &A, int rng_mode, int blocks, int threads, cudaStream_t stream);
 void launch_fold_acc(const SimArgs &A, cudaStream_t stream);     // TABS += acc*TW*ADHOC; INT += acc; acc = 0
+void launch_brick_permute(const GridDesc &G, float *dens_brick, cudaStream_t stream);   // DENS -> 2x2x2-brick order
+bool sim_uses_bricks(const SimArgs &A, int rng_mode);            // does launch_sim() take the bricked kernel?
 int  sim_blocks_per_sm(int rng_mode, bool octree, bool dbl, int threads);
