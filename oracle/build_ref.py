@@ -89,7 +89,7 @@ def tag_of(cfg):
     keys = ["NX", "NY", "NZ", "LEVELS", "CELLS"]
     opt = ["NO_PS", "PS_METHOD", "WITH_ABU", "NOABSORBED", "SAVE_INTENSITY", "USE_EMWEIGHT", "WITH_ALI",
            "HPBG_WEIGHTED", "FFS", "BINS", "MAP_NSIDE", "STEP_WEIGHT", "MIRROR", "MAP_INTERPOLATION",
-           "LEVEL_THRESHOLD", "GL"]
+           "LEVEL_THRESHOLD", "GL", "WITH_MSF", "NDUST"]
     s = "_".join(str(cfg[k]) for k in keys)
     for k in opt:
         if k in cfg:
@@ -118,8 +118,10 @@ def build(cfg, force=False, verbose=False):
             txt = re.sub(r"\(uint2\)\(", "uint2(", txt)
             open(os.path.join(tmp, f), "w").write(txt)
         flags = macro_flags(cfg)
+        # -ftrivial-auto-var-init=zero: the scattered-light SimRAM_CL indexes DSC with an uninitialised `idust` when
+        # WITH_MSF==0 (kernel_ASOC_sca.c:1140 vs :83 where SimRAM_HP initialises it); zero is what the single-dust run means
         common = ["g++", "-std=c++17", "-fpermissive", "-w", "-O2", "-fopenmp", "-fPIC", "-ffp-contract=off",
-                  "-I", tmp, "-I", SHIM]
+                  "-ftrivial-auto-var-init=zero", "-I", tmp, "-I", SHIM]
         objs = []
         for tu, extra in (("ref_sim.cpp", ["-DNSIDE=128"]),
                           ("ref_map.cpp", ["-DNSIDE=%d" % cfg.get("MAP_NSIDE", cfg["NX"])]),

@@ -26,7 +26,8 @@ class OrcParams(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "nx", "ny", "nz", "levels", "cells", "bins", "no_ps", "ps_method", "with_abu", "with_ali", "noabsorbed",
         "save_intensity", "use_emweight", "hpbg_weighted", "ffs", "step_weight", "level_threshold", "sca_exact_level")] + \
-        [(n, C.c_float) for n in ("sw_a", "sw_b", "length", "factor", "adhoc", "reserved1")]
+        [(n, C.c_float) for n in ("sw_a", "sw_b", "length", "factor", "adhoc", "reserved1")] + \
+        [(n, C.c_int32) for n in ("with_msf", "ndust", "mirror", "map_interpolation", "hg_test", "r2a", "r2b", "r2c")]
 
 
 class OrcGrid(C.Structure):
@@ -37,7 +38,8 @@ class OrcSimBufs(C.Structure):
     _fields_ = [(n, c_fp) for n in ("tabs", "xab", "intens", "intx", "inty", "intz", "emit", "emwei", "opt",
                                     "dsc", "csc")] + \
         [("abs", C.c_float), ("sca", C.c_float), ("pspos", c_fp), ("ps", c_fp), ("xps_nside", c_ip),
-         ("xps_side", c_ip), ("xps_area", c_fp), ("hpbg", c_fp), ("hpbgp", c_fp)]
+         ("xps_side", c_ip), ("xps_area", c_fp), ("hpbg", c_fp), ("hpbgp", c_fp), ("abu", c_fp), ("abs_v", c_fp),
+         ("sca_v", c_fp)]
 
 
 class OrcScaBufs(C.Structure):
@@ -78,6 +80,7 @@ class Oracle:
     def __init__(self, cloud, gl=0.01, bins=2500, **opts):
         self.L = lib()
         self.cloud = cloud
+        self.opts = dict(opts)
         P = OrcParams()
         P.nx, P.ny, P.nz, P.levels, P.cells = cloud.NX, cloud.NY, cloud.NZ, cloud.LEVELS, cloud.CELLS
         P.bins = bins
@@ -94,6 +97,9 @@ class Oracle:
         P.level_threshold = opts.get("level_threshold", 0)
         P.sca_exact_level = opts.get("sca_exact_level", 0)
         P.sw_a, P.sw_b = opts.get("sw_a", 0.0), opts.get("sw_b", 0.0)
+        P.with_msf, P.ndust, P.mirror = opts.get("with_msf", 0), opts.get("ndust", 1), opts.get("mirror", 0)
+        P.map_interpolation = opts.get("map_interpolation", 0)
+        P.hg_test = opts.get("hg_test", 0)
         P.length = float("%.5e" % (gl * 3.08567758e+18))     # -D LENGTH=%.5ef (ASOC.py:347,356)
         P.factor = 1.0e20
         P.adhoc = 1.0
@@ -115,7 +121,7 @@ class Oracle:
         self._keep = []
 
     def _bufs(self, abs_=0.0, sca=0.0, dsc=None, csc=None, emit=None, emwei=None, opt=None, pspos=None, ps=None,
-              xps_nside=None, xps_side=None, xps_area=None, hpbg=None, hpbgp=None):
+              xps_nside=None, xps_side=None, xps_area=None, hpbg=None, hpbgp=None, abu=None, abs_v=None, sca_v=None):
         def f(a):
             if a is None:
                 return None
@@ -139,6 +145,7 @@ class Oracle:
         B.pspos, B.ps = _fp(f(pspos)), _fp(f(ps))
         B.xps_nside, B.xps_side, B.xps_area = _ip(i(xps_nside)), _ip(i(xps_side)), _fp(f(xps_area))
         B.hpbg, B.hpbgp = _fp(f(hpbg)), _fp(f(hpbgp))
+        B.abu, B.abs_v, B.sca_v = _fp(f(abu)), _fp(f(abs_v)), _fp(f(sca_v))
         return B
 
     def zero(self, tag):
@@ -216,7 +223,7 @@ class Oracle:
         S.ndir, S.npix_x, S.npix_y, S.map_dx = ndir, npx, npy, map_dx
         S.centre[0], S.centre[1], S.centre[2] = [float(x) for x in centre]
         self._sk = [np.ascontiguousarray(np.asarray(x, np.float32)[:, :3].reshape(-1)) for x in (odirs, ora, ode)]
-        self.out = np.zeros(ndir * npx * npy, np.float32)
+        self.out = np.zeros(ndir * npx * npy if ndir > 0 else 12 * ndir * ndir, np.float32)
         S.odirs, S.ora, S.ode, S.out = _fp(self._sk[0]), _fp(self._sk[1]), _fp(self._sk[2]), _fp(self.out)
         return S
 
@@ -225,7 +232,7 @@ class Oracle:
         S = self._sca(ndir, npx, npy, map_dx, centre, odirs, ora, ode)
         self.L.orc_sca_ps(C.byref(self.P), C.byref(self.G), C.byref(B), C.byref(S), C.c_int(global_),
                           C.c_int(packets), C.c_int(batch), C.c_float(seed), C.byref(self.counters))
-        return self.out.reshape(ndir, npy, npx)
+        return self.out.reshape(ndir, npy, npx) if ndir > 0 else self.out
 
     def sca_pb(self, global_, source, packets, batch, seed, bg, ndir, npx, npy, map_dx, centre, odirs, ora, ode,
                **bufs):
@@ -234,7 +241,21 @@ class Oracle:
         self.L.orc_sca_pb(C.byref(self.P), C.byref(self.G), C.byref(B), C.byref(S), C.c_int(global_),
                           C.c_int(source), C.c_int(packets), C.c_int(batch), C.c_float(seed), C.c_float(bg),
                           C.byref(self.counters))
-        return self.out.reshape(ndir, npy, npx)
+        return self.out.reshape(ndir, npy, npx) if ndir > 0 else self.out
+
+    def sca_hp(self, global_, packets, batch, seed, ndir, npx, npy, map_dx, centre, odirs, ora, ode, **bufs):
+        B = self._bufs(**bufs)
+        S = self._sca(ndir, npx, npy, map_dx, centre, odirs, ora, ode)
+        self.L.orc_sca_hp(C.byref(self.P), C.byref(self.G), C.byref(B), C.byref(S), C.c_int(global_),
+                          C.c_int(packets), C.c_int(batch), C.c_float(seed), C.byref(self.counters))
+        return self.out.reshape(ndir, npy, npx) if ndir > 0 else self.out
+
+    def sca_cl(self, global_, packets, batch, seed, ndir, npx, npy, map_dx, centre, odirs, ora, ode, **bufs):
+        B = self._bufs(**bufs)
+        S = self._sca(ndir, npx, npy, map_dx, centre, odirs, ora, ode)
+        self.L.orc_sca_cl(C.byref(self.P), C.byref(self.G), C.byref(B), C.byref(S), C.c_int(global_),
+                          C.c_int(packets), C.c_int(batch), C.c_float(seed), C.byref(self.counters))
+        return self.out.reshape(ndir, npy, npx) if ndir > 0 else self.out
 
 
 def set_threads(n):

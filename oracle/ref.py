@@ -89,36 +89,43 @@ class Reference:
         self._keep.append(a)
         return _ip(a)
 
+    def _as(self, abs_, sca, abs_v, sca_v):
+        """ABS / SCA kernel arguments: one float each, or [NDUST] vectors with WITH_MSF."""
+        if abs_v is not None:
+            return np.ascontiguousarray(abs_v, np.float32), np.ascontiguousarray(sca_v, np.float32)
+        return np.array([abs_], np.float32), np.array([sca], np.float32)
+
     def sim_pb(self, global_, source, packets, batch, seed, bg, tw, abs_=0.0, sca=0.0, dsc=None, csc=None, emit=None,
-               emwei=None, opt=None, pspos=None, ps=None, xps_nside=None, xps_side=None, xps_area=None, **_):
+               emwei=None, opt=None, pspos=None, ps=None, xps_nside=None, xps_side=None, xps_area=None, abu=None,
+               abs_v=None, sca_v=None, **_):
         self._keep = []
-        a, s = np.array([abs_], np.float32), np.array([sca], np.float32)
+        a, s = self._as(abs_, sca, abs_v, sca_v)
         self.L.ref_sim_pb(C.c_int(global_), C.c_int(source), C.c_int(packets), C.c_int(batch), C.c_float(seed),
                           _fp(a), _fp(s), C.c_float(bg), self._f(pspos), self._f(ps), C.c_float(tw),
                           _ip(self.lcells), _ip(self.off), _ip(self.par), _fp(self.dens), self._f(emit),
                           _fp(self.tabs), self._f(dsc), self._f(csc), _fp(self.xab), self._f(emwei),
                           _fp(self.int_), _fp(self.intx), _fp(self.inty), _fp(self.intz), self._f(opt),
-                          _fp(self._d), self._i(xps_nside), self._i(xps_side), self._f(xps_area))
+                          self._f(abu), self._i(xps_nside), self._i(xps_side), self._f(xps_area))
 
     def sim_hp(self, global_, packets, batch, seed, tw, abs_=0.0, sca=0.0, dsc=None, csc=None, opt=None, hpbg=None,
-               hpbgp=None, **_):
+               hpbgp=None, abu=None, abs_v=None, sca_v=None, **_):
         self._keep = []
-        a, s = np.array([abs_], np.float32), np.array([sca], np.float32)
+        a, s = self._as(abs_, sca, abs_v, sca_v)
         self.L.ref_sim_hp(C.c_int(global_), C.c_int(packets), C.c_int(batch), C.c_float(seed), _fp(a), _fp(s),
                           C.c_float(tw), _ip(self.lcells), _ip(self.off), _ip(self.par), _fp(self.dens),
                           _fp(self._d), _fp(self.tabs), self._f(dsc), self._f(csc), _fp(self.xab), _fp(self.int_),
                           _fp(self.intx), _fp(self.inty), _fp(self.intz), self._f(opt), self._f(hpbg),
-                          self._f(hpbgp), _fp(self._d))
+                          self._f(hpbgp), self._f(abu))
 
     def sim_cl(self, global_, packets, batch, seed, tw, abs_=0.0, sca=0.0, dsc=None, csc=None, emit=None, emwei=None,
-               opt=None, **_):
+               opt=None, abu=None, abs_v=None, sca_v=None, **_):
         self._keep = []
-        a, s = np.array([abs_], np.float32), np.array([sca], np.float32)
+        a, s = self._as(abs_, sca, abs_v, sca_v)
         self.L.ref_sim_cl(C.c_int(global_), C.c_int(2), C.c_int(packets), C.c_int(batch), C.c_float(seed), _fp(a),
                           _fp(s), C.c_float(tw), _ip(self.lcells), _ip(self.off), _ip(self.par), _fp(self.dens),
                           self._f(emit), _fp(self.tabs), self._f(dsc), self._f(csc), _fp(self.xab), self._f(emwei),
                           _fp(self.int_), _fp(self.intx), _fp(self.inty), _fp(self.intz), _ip(self._di),
-                          self._f(opt), _fp(self._d))
+                          self._f(opt), self._f(abu))
 
     def eq_temperature(self, level, adhoc, kE, Emin, NE, ttt, emit, tnew):
         ttt = np.ascontiguousarray(ttt, np.float32)
@@ -177,32 +184,65 @@ class Reference:
         self._keep.append(a)
         return _fp(a)
 
+    def _out(self, ndir, npx, npy):
+        return np.zeros(ndir * npx * npy if ndir > 0 else 12 * ndir * ndir, np.float32)
+
+    @staticmethod
+    def _shape(out, ndir, npx, npy):
+        return out.reshape(ndir, npy, npx) if ndir > 0 else out
+
     def sca_ps(self, global_, packets, batch, seed, ndir, npx, npy, map_dx, centre, odirs, ora, ode, abs_=0.0,
-               sca=0.0, dsc=None, csc=None, opt=None, pspos=None, ps=None, **_):
+               sca=0.0, dsc=None, csc=None, opt=None, pspos=None, ps=None, abu=None, abs_v=None, sca_v=None, **_):
         self._keep = []
-        a, s = np.array([abs_], np.float32), np.array([sca], np.float32)
-        out = np.zeros(ndir * npx * npy, np.float32)
+        a, s = self._as(abs_, sca, abs_v, sca_v)
+        out = self._out(ndir, npx, npy)
         ce = np.ascontiguousarray(centre, np.float32)
         self.L.ref_sca_ps(C.c_int(global_), C.c_int(packets), C.c_int(batch), C.c_float(seed), _fp(a), _fp(s),
                           C.c_float(0.0), self._f(pspos), self._f(ps), _ip(self.lcells), _ip(self.off),
                           _ip(self.par), _fp(self.dens), self._f(dsc), self._f(csc), C.c_int(ndir), self._v3(odirs),
                           C.c_int(npx), C.c_int(npy), C.c_float(map_dx), _fp(ce), self._v3(ora), self._v3(ode),
-                          _fp(out), _fp(self._d), self._f(opt), _fp(self._d), _fp(self._d), _fp(self._d))
-        return out.reshape(ndir, npy, npx)
+                          _fp(out), self._f(abu), self._f(opt), _fp(self._d), _fp(self._d), _fp(self._d))
+        return self._shape(out, ndir, npx, npy)
 
     def sca_pb(self, global_, source, packets, batch, seed, bg, ndir, npx, npy, map_dx, centre, odirs, ora, ode,
-               abs_=0.0, sca=0.0, dsc=None, csc=None, opt=None, pspos=None, ps=None, **_):
+               abs_=0.0, sca=0.0, dsc=None, csc=None, opt=None, pspos=None, ps=None, abu=None, abs_v=None, sca_v=None, **_):
         self._keep = []
-        a, s = np.array([abs_], np.float32), np.array([sca], np.float32)
-        out = np.zeros(ndir * npx * npy, np.float32)
+        a, s = self._as(abs_, sca, abs_v, sca_v)
+        out = self._out(ndir, npx, npy)
         ce = np.ascontiguousarray(centre, np.float32)
         self.L.ref_sca_pb(C.c_int(global_), C.c_int(source), C.c_int(packets), C.c_int(batch), C.c_float(seed),
                           _fp(a), _fp(s), C.c_float(bg), self._f(pspos), self._f(ps), _ip(self.lcells),
                           _ip(self.off), _ip(self.par), _fp(self.dens), self._f(dsc), self._f(csc), C.c_int(ndir),
                           self._v3(odirs), C.c_int(npx), C.c_int(npy), C.c_float(map_dx), _fp(ce), self._v3(ora),
-                          self._v3(ode), _fp(out), _fp(self._d), self._f(opt), _fp(self._d), _fp(self._d),
+                          self._v3(ode), _fp(out), self._f(abu), self._f(opt), _fp(self._d), _fp(self._d),
                           _fp(self._d))
-        return out.reshape(ndir, npy, npx)
+        return self._shape(out, ndir, npx, npy)
+
+    def sca_hp(self, global_, packets, batch, seed, ndir, npx, npy, map_dx, centre, odirs, ora, ode, abs_=0.0,
+               sca=0.0, dsc=None, csc=None, opt=None, hpbg=None, hpbgp=None, abu=None, abs_v=None, sca_v=None, **_):
+        self._keep = []
+        a, s = self._as(abs_, sca, abs_v, sca_v)
+        out = self._out(ndir, npx, npy)
+        ce = np.ascontiguousarray(centre, np.float32)
+        self.L.ref_sca_hp(C.c_int(global_), C.c_int(packets), C.c_int(batch), C.c_float(seed), _fp(a), _fp(s),
+                          _ip(self.lcells), _ip(self.off), _ip(self.par), _fp(self.dens), self._f(dsc), self._f(csc),
+                          C.c_int(ndir), self._v3(odirs), C.c_int(npx), C.c_int(npy), C.c_float(map_dx), _fp(ce),
+                          self._v3(ora), self._v3(ode), _fp(out), self._f(abu), self._f(opt), self._f(hpbg),
+                          self._f(hpbgp))
+        return self._shape(out, ndir, npx, npy)
+
+    def sca_cl(self, global_, packets, batch, seed, ndir, npx, npy, map_dx, centre, odirs, ora, ode, abs_=0.0,
+               sca=0.0, dsc=None, csc=None, opt=None, emit=None, emwei=None, abu=None, abs_v=None, sca_v=None, **_):
+        self._keep = []
+        a, s = self._as(abs_, sca, abs_v, sca_v)
+        out = self._out(ndir, npx, npy)
+        ce = np.ascontiguousarray(centre, np.float32)
+        self.L.ref_sca_cl(C.c_int(global_), C.c_int(2), C.c_int(packets), C.c_int(batch), C.c_float(seed), _fp(a),
+                          _fp(s), _ip(self.lcells), _ip(self.off), _ip(self.par), _fp(self.dens), self._f(emit),
+                          self._f(dsc), self._f(csc), C.c_int(ndir), self._v3(odirs), C.c_int(npx), C.c_int(npy),
+                          C.c_float(map_dx), _fp(ce), self._v3(ora), self._v3(ode), _fp(out), self._f(opt),
+                          self._f(abu), self._f(emwei))
+        return self._shape(out, ndir, npx, npy)
 
 
 def rng_stream(lib, seed, id_, gsize, n):

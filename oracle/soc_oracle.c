@@ -218,6 +218,18 @@ static void surface(const nav_t *N, v3 *p, const v3 *d) {
     p->x += dx * d->x; p->y += dx * d->y; p->z += dx * d->z;
 }
 
+/* Mirror(): kernel_ASOC_aux.c:1054-1083, restated literally: `if (c) a ; b ;` -- the direction component of every
+ * enabled border is negated whether or not that border was crossed (a second enabled border of the same axis undoes
+ * the reflection). */
+static void mirror(const nav_t *N, int mask, v3 *p, v3 *d, int *level, int *ind) {
+    if (mask & 1)  { if (p->x < 0.0f)  p->x = S_EPS;          d->x = -d->x; index_g(N, p, level, ind); }
+    if (mask & 2)  { if (p->x > N->nx) p->x = N->nx - S_EPS;  d->x = -d->x; index_g(N, p, level, ind); }
+    if (mask & 4)  { if (p->y < 0.0f)  p->y = S_EPS;          d->y = -d->y; index_g(N, p, level, ind); }
+    if (mask & 8)  { if (p->y > N->ny) p->y = N->ny - S_EPS;  d->y = -d->y; index_g(N, p, level, ind); }
+    if (mask & 16) { if (p->z < 0.0f)  p->z = S_EPS;          d->z = -d->z; index_g(N, p, level, ind); }
+    if (mask & 32) { if (p->z > N->nz) p->z = N->nz - S_EPS;  d->z = -d->z; index_g(N, p, level, ind); }
+}
+
 /* Deflect(): kernel_ASOC_aux.c:499-533 */
 static void deflect(v3 *d, float cos_theta, float phi) {
     float cx = d->x, cy = d->y, cz = d->z;
@@ -385,6 +397,7 @@ static void propagate(sim_t *S, rng_t *r, v3 pos, v3 dir, int level, int ind, fl
             if (kind == 0 && level == level0 && ind == ind0) {             /* kernel_ASOC.c:649-665 */
                 pos.x += S_PEPS * dir.x; pos.y += S_PEPS * dir.y; pos.z += S_PEPS * dir.z;
             }
+            if (S->P->mirror > 0 && ind < 0) mirror(N, S->P->mirror, &pos, &dir, &level, &ind);   /* :686-688, 1540-1542 */
         }
         if (ind < 0) break;
         scatterings++;
@@ -401,7 +414,17 @@ static void propagate(sim_t *S, rng_t *r, v3 pos, v3 dir, int level, int ind, fl
         photons *= expf(-tauA);
         free_path = sample_free_path(S->P, r, &photons);
         ind = ind0; level = level0;
-        scatter(&dir, S->B->csc, S->P->bins, r);
+        if (S->P->with_msf > 0) {                                           /* kernel_ASOC.c:777-794 */
+            float sum = S->B->opt[2 * (long)oind + 1];
+            float u = 0.99999f * rnd(r);
+            int idust;
+            for (idust = 0; idust < S->P->ndust; idust++) {
+                u -= S->B->abu[idust + (long)oind * S->P->ndust] * S->B->sca_v[idust] / sum;
+                if (u <= 0.0) break;
+            }
+            if (idust >= S->P->ndust) idust = S->P->ndust - 1;
+            scatter(&dir, S->B->csc + idust * S->P->bins, S->P->bins, r);
+        } else scatter(&dir, S->B->csc, S->P->bins, r);
         S->c.scatterings++;
         if (kind == 0 && scatterings > 20) break;                           /* kernel_ASOC.c:801-804 */
     }
@@ -873,6 +896,27 @@ void orc_healpix_mapping(const OrcParams *P, const OrcGrid *G, int nside, float 
  * ================================================================================================= */
 typedef struct { const OrcParams *P; const OrcSimBufs *B; const OrcScaBufs *O; nav_t N; OrcCounters c; } sca_t;
 
+/* WITH_MSF: pick the scattering dust species of cell `oind` with probability ABU*SCA / sum (kernel_ASOC_sca.c:339-346,
+   992-999, 1052-1061 ...; kernel_ASOC.c:777-794).  Draws one random number; returns 0 without a draw when MSF is off. */
+/* kernel_ASOC_sca.c:349-355, 392-398, 1343-1349, 1387-1393: the `#ifdef HG_TEST` branch that is live in the shipped
+   SimRAM_HP / SimRAM_CL (HG_TEST is #defined, as 0, in kernel_ASOC_aux.c:1) */
+static inline float hg_test_fraction(float cos_theta) {
+    const float G = 0.65f;
+    return (1.0f / (4.0f * PI_F)) * (1.0f - G * G) / powf(1.0f + G * G - 2.0f * G * cos_theta, 1.5f);
+}
+static int msf_pick(sca_t *S, rng_t *r, int oind) {
+    const OrcParams *P = S->P; const OrcSimBufs *B = S->B;
+    if (P->with_msf <= 0) return 0;
+    float dx = B->opt[2 * (long)oind + 1];
+    float ds = 0.99999f * rnd(r);
+    int idust;
+    for (idust = 0; idust < P->ndust; idust++) {
+        ds -= B->abu[idust + (long)P->ndust * oind] * B->sca_v[idust] / dx;
+        if (ds <= 0.0f) break;
+    }
+    return idust < P->ndust ? idust : P->ndust - 1;   /* the sca kernels do not clamp (they would read past DSC); kernel_ASOC.c:789 does */
+}
+
 static void sca_propagate(sca_t *S, rng_t *r, v3 pos, v3 dir, int level, int ind, float photons, int flavour) {
     const OrcParams *P = S->P; const OrcSimBufs *B = S->B; const OrcScaBufs *O = S->O; const nav_t *N = &S->N;
     int ind0, level0, oind = 0, scatterings = 0;
@@ -888,9 +932,14 @@ static void sca_propagate(sca_t *S, rng_t *r, v3 pos, v3 dir, int level, int ind
             tau += ds * N->dens[oind] * ksca;
             S->c.steps++;
         }
-        if (tau < 1.0e-22f) ind = -1;
-        if (flavour == 0) { W = -expm1f(-tau); free_path = -logf(1.0f - W * rnd(r)); }
-        else              { W = 1.0f - expf(-tau); free_path = (float)(-log(1.0 - W * rnd(r))); }
+        if (flavour >= 2) {                       /* SimRAM_HP :279-287, SimRAM_CL :1257-1264: no draw for an empty line of sight */
+            if (tau < 1.0e-22f) return;
+            W = 1.0f - expf(-tau); free_path = (float)(-log(1.0 - W * rnd(r)));
+        } else {
+            if (tau < 1.0e-22f) ind = -1;
+            if (flavour == 0) { W = -expm1f(-tau); free_path = -logf(1.0f - W * rnd(r)); }
+            else              { W = 1.0f - expf(-tau); free_path = (float)(-log(1.0 - W * rnd(r))); }
+        }
         photons *= W;
     } else {
         free_path = -logf(rnd(r));
@@ -905,6 +954,7 @@ static void sca_propagate(sca_t *S, rng_t *r, v3 pos, v3 dir, int level, int ind
             S->c.steps++;
             if (free_path < (tau + dtau)) { ind = ind0; break; }
             tau += dtau;
+            if (P->mirror > 0 && ind < 0) mirror(N, P->mirror, &pos, &dir, &level, &ind);   /* kernel_ASOC_sca.c:280, 940, 1280, 1780 */
         }
         if (ind < 0) break;
         scatterings++; S->c.scatterings++;
@@ -918,6 +968,37 @@ static void sca_propagate(sca_t *S, rng_t *r, v3 pos, v3 dir, int level, int ind
         dx = ldexpf(dx, P->sca_exact_level ? level0 : level);
         pos0.x += dx * dir.x; pos0.y += dx * dir.y; pos0.z += dx * dir.z;
         photons *= expf(-free_path * kabs / ksca);
+        const float cclamp = (flavour >= 2) ? 0.9999f : 0.999f;            /* :356,1329 vs :991,1830 */
+        if (O->ndir < 0) {
+            /* Healpix image seen by an observer at ODIRS[0] (root-grid units), NSIDE = -NDIR:
+               kernel_ASOC_sca.c:312-378 (HP), 968-1008 (PB), 1309-1352 (CL), 1807-1847 (PS) */
+            v3 p = pos0, q = pos0, od;
+            int pind = ind0, plevel = level0, po;
+            root_pos(N, &q, level0, ind0);
+            od.x = O->odirs[0] - q.x; od.y = O->odirs[1] - q.y; od.z = O->odirs[2] - q.z;
+            dx = sqrtf(od.x * od.x + od.y * od.y + od.z * od.z);
+            delta = 1.0f / (dx * dx);
+            od = v3_norm(od);
+            tau = 0.0f;
+            while (dx > 0 && pind >= 0) {
+                po = N->off[plevel] + pind;
+                ds = get_step(N, &p, &od, &plevel, &pind);
+                if (flavour == 1) ds = (float)(fminf_(dx, ds) + 1.0e-6);      /* sic: double literal in SimRAM_PB :982 */
+                else              ds = fminf_(dx, ds) + 1.0e-6f;
+                dx -= ds;
+                if (P->with_abu) tau += ds * N->dens[po] * (B->opt[2 * (long)po] + B->opt[2 * (long)po + 1]);
+                else             tau += ds * N->dens[po] * (B->abs + B->sca);
+                S->c.steps++;
+            }
+            S->c.peels++;
+            float cos_theta = clampf(dir.x * od.x + dir.y * od.y + dir.z * od.z, -cclamp, +cclamp);
+            int idust = msf_pick(S, r, N->off[level0] + ind0);
+            if (flavour >= 2 && P->hg_test) delta *= photons * hg_test_fraction(cos_theta) * ((tau > TAULIM) ? (1.0f - expf(-tau)) : (tau * (1.0f - 0.5f * tau)));
+            else delta *= photons * expf(-tau) * B->dsc[idust * P->bins + clampi((int)(P->bins * (1.0f + cos_theta) * 0.5f), 0, P->bins - 1)];
+            float theta = acosf(-od.z), phi = atan2f(od.y, od.x);
+            int ipix = orc_ang2pix_ring(-O->ndir, phi, theta);
+            if (ipix >= 0) addf(&O->out[ipix], delta);
+        } else
         /* peel-off towards every observer (orthographic maps): kernel_ASOC_sca.c:1010-1046 / 1849-1885 */
         for (int idir = 0; idir < O->ndir; idir++) {
             v3 p = pos0, od = { O->odirs[3 * idir], O->odirs[3 * idir + 1], O->odirs[3 * idir + 2] };
@@ -931,8 +1012,10 @@ static void sca_propagate(sca_t *S, rng_t *r, v3 pos, v3 dir, int level, int ind
                 S->c.steps++;
             }
             S->c.peels++;
-            float cos_theta = clampf(dir.x * od.x + dir.y * od.y + dir.z * od.z, -0.999f, +0.999f);
-            delta = photons * expf(-tau) * B->dsc[clampi((int)(P->bins * (1.0f + cos_theta) * 0.5f), 0, P->bins - 1)];
+            float cos_theta = clampf(dir.x * od.x + dir.y * od.y + dir.z * od.z, -cclamp, +cclamp);
+            int idust = msf_pick(S, r, N->off[level0] + ind0);
+            if (flavour >= 2 && P->hg_test) delta = photons * hg_test_fraction(cos_theta) * ((tau > TAULIM) ? (1.0f - expf(-tau)) : (tau * (1.0f - 0.5f * tau)));
+            else delta = photons * expf(-tau) * B->dsc[idust * P->bins + clampi((int)(P->bins * (1.0f + cos_theta) * 0.5f), 0, P->bins - 1)];
             p.x -= O->centre[0]; p.y -= O->centre[1]; p.z -= O->centre[2];
             const float *ra = O->ora + 3 * idir, *de = O->ode + 3 * idir;
             int i = (int)((0.5f * O->npix_x - 0.00005f) + (p.x * ra[0] + p.y * ra[1] + p.z * ra[2]) / O->map_dx);
@@ -941,7 +1024,7 @@ static void sca_propagate(sca_t *S, rng_t *r, v3 pos, v3 dir, int level, int ind
                 addf(&O->out[i + idir * O->npix_x * O->npix_y + j * O->npix_x], delta);
         }
         pos = pos0; ind = ind0; level = level0;
-        scatter(&dir, B->csc, P->bins, r);
+        scatter(&dir, B->csc + msf_pick(S, r, N->off[level0] + ind0) * P->bins, P->bins, r);
         free_path = -logf(rnd(r));
         if (scatterings == 30) break;
     }
@@ -1049,6 +1132,113 @@ void orc_sca_pb(const OrcParams *P, const OrcGrid *G, const OrcSimBufs *B, const
             dir_fix(&dir);
             S.c.packets++;
             sca_propagate(&S, &rng, pos, dir, level, ind, photons, 1);
+        }
+        np += S.c.packets; ns += S.c.steps; nsc += S.c.scatterings; npl += S.c.peels;
+    }
+    if (C) { C->packets += np; C->steps += ns; C->scatterings += nsc; C->peels += npl; }
+}
+
+/* ---- scattered light, Healpix background: SimRAM_HP, kernel_ASOC_sca.c:40-470 --------------------- */
+void orc_sca_hp(const OrcParams *P, const OrcGrid *G, const OrcSimBufs *B, const OrcScaBufs *O, int global,
+                int packets, int batch, float seed, OrcCounters *C) {
+    (void)packets;
+    const int NX = P->nx, NY = P->ny, NZ = P->nz;
+    uint64_t np = 0, ns = 0, nsc = 0, npl = 0;
+    #pragma omp parallel for schedule(runtime) reduction(+:np,ns,nsc,npl)
+    for (int id = 0; id < global; id++) {
+        sca_t S; S.P = P; S.B = B; S.O = O; S.N = nav_make(P, G); memset(&S.c, 0, sizeof(S.c));
+        rng_t rng; rng_seed(&rng, seed, (uint64_t)id);
+        const float Rout = 0.5f * sqrtf(1.0f * NX * NX + NY * NY + NZ * NZ);
+        int ind = -1, level = 0, ind0, level0;
+        float photons, phi, theta, x, ds, dx;
+        v3 pos, pos0, dir;
+        for (int III = 0; III < batch; III++) {
+            if (P->hpbg_weighted < 1) {
+                ind = clampi((int)(floorf(rnd(&rng) * 49152)), 0, 49151);
+            } else {                                                         /* :117-129, 12 halvings here */
+                x = rnd(&rng); ind0 = 0; level0 = 49151;
+                for (int i = 0; i < 12; i++) {
+                    ind = (ind0 + level0) / 2;
+                    if (B->hpbgp[ind] > x) level0 = ind; else ind0 = ind;
+                }
+                for (ind = ind0; ind <= level0; ind++) if (B->hpbgp[ind] >= x) break;
+            }
+            photons = B->hpbg[ind];
+            orc_pix2ang_ring(64, ind, &phi, &theta);
+            dir.x = +sinf(theta) * cosf(phi); dir.y = +sinf(theta) * sinf(phi); dir.z = -cosf(theta);
+            dir_fix(&dir);
+            /* entry point: a disc of radius Rout facing the Healpix pixel, :149-217 */
+            ds = 2.0f * PI_F * rnd(&rng);
+            dx = sqrtf(rnd(&rng));
+            pos.x = dx * cosf(ds); pos.y = dx * sinf(ds); pos.z = sqrtf(1.001f - dx * dx);
+            pos0.x = pos.x * cosf(theta) + pos.z * sinf(theta);
+            pos0.y = pos.y;
+            pos0.z = -pos.x * sinf(theta) + pos.z * cosf(theta);
+            pos.x = pos0.x * cosf(PI_F - phi) + pos0.y * sinf(PI_F - phi);
+            pos.y = -pos0.x * sinf(PI_F - phi) + pos0.y * cosf(PI_F - phi);
+            pos.z = pos0.z;
+            pos.x = 0.5f * NX + Rout * pos.x; pos.y = 0.5f * NY + Rout * pos.y; pos.z = 0.5f * NZ + Rout * pos.z;
+            surface(&S.N, &pos, &dir);
+            index_g(&S.N, &pos, &level, &ind);
+            S.c.packets++;
+            if (ind < 0) continue;
+            sca_propagate(&S, &rng, pos, dir, level, ind, photons, 2);
+        }
+        np += S.c.packets; ns += S.c.steps; nsc += S.c.scatterings; npl += S.c.peels;
+    }
+    if (C) { C->packets += np; C->steps += ns; C->scatterings += nsc; C->peels += npl; }
+}
+
+/* ---- scattered light, emission from the cells: SimRAM_CL, kernel_ASOC_sca.c:1098-1461 ---------------- */
+void orc_sca_cl(const OrcParams *P, const OrcGrid *G, const OrcSimBufs *B, const OrcScaBufs *O, int global,
+                int packets, int batch_arg, float seed, OrcCounters *C) {
+    (void)packets;
+    uint64_t np = 0, ns = 0, nsc = 0, npl = 0;
+    #pragma omp parallel for schedule(runtime) reduction(+:np,ns,nsc,npl)
+    for (int id = 0; id < global; id++) {
+        if (id >= P->cells) continue;
+        sca_t S; S.P = P; S.B = B; S.O = O; S.N = nav_make(P, G); memset(&S.c, 0, sizeof(S.c));
+        const nav_t *N = &S.N;
+        rng_t rng; rng_seed(&rng, seed, (uint64_t)id);
+        int icell = id - global, iray = 0, batch = -1, ind, level, done = 0;
+        float pwei = 1.0f, X0, Y0, Z0;
+        while (!done) {
+            if (iray >= batch) {
+                iray = 0; pwei = 1.0f;
+                for (;;) {
+                    icell += global;
+                    if (icell >= P->cells) { done = 1; break; }
+                    if (P->use_emweight > 0) {
+                        pwei = B->emwei[icell];
+                        if (pwei < 1e-10f || N->dens[icell] <= 0.0f) continue;
+                        batch = (int)floorf(pwei);
+                        if (batch < 1) { batch = 1; pwei = (float)(1.0 / (pwei + 1.0e-30f)); }
+                        else           { pwei = (float)(1.0 / (batch + 1.0e-9f)); }
+                    } else {
+                        batch = batch_arg;
+                        pwei = 1.0f / (batch + 1.0e-9f);
+                    }
+                    break;
+                }
+                if (done) break;
+            }
+            ind = icell; iray++;
+            for (level = 0; level < P->levels - 1; level++) {
+                ind -= G->lcells[level];
+                if (ind < 0) { ind += G->lcells[level]; break; }
+            }
+            if (level == 0) { X0 = ind % P->nx; Y0 = (ind / P->nx) % P->ny; Z0 = ind / (P->nx * P->ny); }
+            else { int sid = ind % 8; X0 = sid % 2; Y0 = ((sid % 4) > 1) ? 1.0f : 0.0f; Z0 = sid / 4; }
+            float photons = B->emit[N->off[level] + ind] * pwei;
+            v3 pos, dir;
+            pos.x = X0 + rnd(&rng); pos.y = Y0 + rnd(&rng); pos.z = Z0 + rnd(&rng);
+            float phi = TWOPI * rnd(&rng);
+            float cos_theta = 0.999997f - 1.999995f * rnd(&rng);
+            float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+            dir.x = sin_theta * cosf(phi); dir.y = sin_theta * sinf(phi); dir.z = cos_theta;
+            dir_fix(&dir);
+            S.c.packets++;
+            sca_propagate(&S, &rng, pos, dir, level, ind, photons, 3);
         }
         np += S.c.packets; ns += S.c.steps; nsc += S.c.scatterings; npl += S.c.peels;
     }

@@ -43,6 +43,7 @@ struct soc_context {
     float *acc; size_t acc_bytes;      // per-launch scratch accumulator of the stream kernels (all zero between launches)
     float *dens_brick;                 // regular grids with even dimensions: DENS in 2x2x2-brick order (lean kernel)
     int layout;                        // 1 = use the bricked copy where the kernel supports it
+    int pend;                          // 1 = merged deposits (vector reds) in the lean kernel
     unsigned long long launches;
     soc_params P;
     bool have_params, have_grid;
@@ -105,6 +106,8 @@ int soc_create(int device_ordinal, soc_context **out) {
     c->rng_mode = SOC_RNG_PACKET; c->rank = 0; c->world = 1;
     c->deposit = DEP_TILE; c->refill = 8; c->agg_steps = 24; c->sc_batch = 0;        // 0 = by grid type
     c->nav_hops = 1; c->layout = 1;
+    c->pend = 0;          // measured on the bench step: 58.9 ms with, 59.0 ms without -- the merged reds trade L2 work for issue slots
+    if (const char *e = getenv("SOC_PEND")) c->pend = atoi(e) != 0;                                                    // tuning knob
     if (const char *e = getenv("SOC_LAYOUT")) c->layout = atoi(e) != 0;                                               // tuning knob
     if (const char *e = getenv("SOC_NAV_HOPS")) { int v = atoi(e); if (v >= 1 && v <= 8) c->nav_hops = v; }          // tuning knob
     if (const char *e = getenv("SOC_SC_BATCH")) { int v = atoi(e); if (v >= 1 && v <= 32) c->sc_batch = v; }   // tuning knob
@@ -368,13 +371,14 @@ static int sim_launch(soc_context *c, SimArgs &A, const char *who) {
         const size_t n = (size_t)A.G.cells * 4;
         if (c->acc == nullptr || c->acc_bytes != n) {
             if (c->acc) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->acc)); c->acc = nullptr; }
-            CU(cudaMalloc(&c->acc, n));
+            CU(cudaMalloc(&c->acc, n + 16));
             c->acc_bytes = n;
-            CU(cudaMemsetAsync(c->acc, 0, n, c->stream));
+            CU(cudaMemsetAsync(c->acc, 0, n + 16, c->stream));
         }
         A.acc = c->acc; A.use_acc = 1;
         A.dens_brick = c->layout ? c->dens_brick : nullptr;
         A.brick = sim_uses_bricks(A, c->rng_mode) ? 1 : 0;
+        A.pend = c->pend;
         A.slab_xy = A.G.nx * A.G.ny; A.brick_by = 4 * A.G.nx - 2; A.brick_bz = 2 * A.G.nx * A.G.ny - 4;
     }
     CU(cudaEventRecord(c->ev0, c->stream));

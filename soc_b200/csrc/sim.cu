@@ -682,9 +682,11 @@ __device__ __forceinline__ void count_add(unsigned *s32, unsigned long long *g64
     if (old < 0x80000000u && old + v >= 0x80000000u) { atomicSub(s32, 0x80000000u); atomicAdd(g64, 0x80000000ull); }
 }
 
-template <int DEP, bool BRICK>
+template <int DEP, bool BRICK, bool PEND>
 __global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant__ SimArgs A) {
     __shared__ float smem[DEP == DEP_TILE ? SOC_TILE_CELLS : 1];
+    __shared__ float s_pend[PEND ? 4 * 256 : 1];
+    int pend_h = -1;
     __shared__ unsigned s_cnt[4];
     if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
     float *tile = nullptr;
@@ -818,7 +820,22 @@ __global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant_
                     }
                 }
             }
-            if (!in_tile) red_add(&A.acc[oind], delta);
+            if (!in_tile) {
+                if (PEND) {
+                    // deposits of consecutive steps that fall into the same aligned group of four cells (half a brick)
+                    // are summed in a per-lane shared-memory slot and leave the SM as one red.global.add.v4.f32
+                    const int h = oind >> 2, k = oind & 3;
+                    float *slot = s_pend + threadIdx.x;
+                    // branch-free: read the slot, send it off if the group changes, write back old-or-zero plus delta
+                    const bool same = h == pend_h;
+                    float v0 = slot[0], v1 = slot[256], v2 = slot[512], v3 = slot[768];
+                    if (!same && pend_h >= 0) atomicAdd(reinterpret_cast<float4 *>(A.acc) + pend_h, make_float4(v0, v1, v2, v3));
+                    v0 = same ? v0 : 0.0f; v1 = same ? v1 : 0.0f; v2 = same ? v2 : 0.0f; v3 = same ? v3 : 0.0f;
+                    slot[0] = v0 + ((k == 0) ? delta : 0.0f); slot[256] = v1 + ((k == 1) ? delta : 0.0f);
+                    slot[512] = v2 + ((k == 2) ? delta : 0.0f); slot[768] = v3 + ((k == 3) ? delta : 0.0f);
+                    pend_h = h;
+                } else red_add(&A.acc[oind], delta);
+            }
         }
         if (run) {
             f.tx -= tmin; f.ty -= tmin; f.tz -= tmin;
@@ -840,6 +857,10 @@ __global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant_
                 if (stuck) count_add(&s_cnt[3], A.counters + 3, 1u);
             }
         }
+    }
+    if (PEND && pend_h >= 0) {
+        const float *slot = s_pend + threadIdx.x;
+        atomicAdd(reinterpret_cast<float4 *>(A.acc) + pend_h, make_float4(slot[0], slot[256], slot[512], slot[768]));
     }
     if (DEP == DEP_TILE) {
         // un-brick the tile flush: tile_end() adds into A.acc with x-fastest indices
@@ -1059,16 +1080,16 @@ struct RngMwcItem : RngMwc {
 
 }  // namespace
 
-template <bool BRICK>
+template <bool BRICK, bool PEND>
 static void launch_lean(SimArgs A, int dep, int blocks, int threads, cudaStream_t stream) {
     if (BRICK && dep == DEP_TILE) {          // z-slab of the shared-memory tile in bricked order
         const int slab = 2 * A.G.nx * A.G.ny, z0 = A.tile_z0;
         A.tile_lo = (z0 >> 1) * slab;
         A.tile_span = (((z0 + SOC_TILE_N - 1) >> 1) - (z0 >> 1) + 1) * slab;
     }
-    if (dep == DEP_RED)       sim_lean_kernel<DEP_RED, BRICK><<<blocks, threads, 0, stream>>>(A);
-    else if (dep == DEP_WARP) sim_lean_kernel<DEP_WARP, BRICK><<<blocks, threads, 0, stream>>>(A);
-    else                      sim_lean_kernel<DEP_TILE, BRICK><<<blocks, threads, 0, stream>>>(A);
+    if (dep == DEP_RED)       sim_lean_kernel<DEP_RED, BRICK, PEND><<<blocks, threads, 0, stream>>>(A);
+    else if (dep == DEP_WARP) sim_lean_kernel<DEP_WARP, BRICK, PEND><<<blocks, threads, 0, stream>>>(A);
+    else                      sim_lean_kernel<DEP_TILE, BRICK, PEND><<<blocks, threads, 0, stream>>>(A);
 }
 
 static bool sim_is_general(const SimArgs &A) { return A.with_abu || A.save_int2 || A.with_ali || A.kind == SIM_CL; }
@@ -1082,8 +1103,13 @@ static void launch_fast(const SimArgs &A, int blocks, int threads, cudaStream_t 
         if (dep == DEP_RED)       sim_fast_kernel<DEP_RED, true><<<blocks, threads, 0, stream>>>(A);
         else if (dep == DEP_WARP) sim_fast_kernel<DEP_WARP, true><<<blocks, threads, 0, stream>>>(A);
         else                      sim_fast_kernel<DEP_TILE, true><<<blocks, threads, 0, stream>>>(A);
-    } else if (A.brick) launch_lean<true>(A, dep, blocks, threads, stream);
-    else                launch_lean<false>(A, dep, blocks, threads, stream);
+    } else if (A.brick) {
+        if (A.pend) launch_lean<true, true>(A, dep, blocks, threads, stream);
+        else        launch_lean<true, false>(A, dep, blocks, threads, stream);
+    } else {
+        if (A.pend) launch_lean<false, true>(A, dep, blocks, threads, stream);
+        else        launch_lean<false, false>(A, dep, blocks, threads, stream);
+    }
 }
 
 bool sim_uses_bricks(const SimArgs &A, int rng_mode) {

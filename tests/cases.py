@@ -172,21 +172,78 @@ def run_pstau(pspos, dirs, abu=False):
     return run
 
 
-def run_sca(kind, npix=(24, 20), dirs=((0.0, 0.0), (70.0, 30.0)), batch=3, glob=1024, seed=0.61, pspos=None):
+def _msf_inputs(c, k, ndust=2, seed=21):
+    """Two dust species with different scattering functions: ABU[cells, ndust], ABS/SCA[ndust], OPT = sums."""
+    rng = np.random.default_rng(seed)
+    abu = (0.2 + rng.random((c.CELLS, ndust))).astype(np.float32)
+    abs_v = (k * np.linspace(0.8, 1.6, ndust)).astype(np.float32)
+    sca_v = (k * np.linspace(2.5, 1.0, ndust)).astype(np.float32)
+    opt = np.empty((c.CELLS, 2), np.float32)
+    opt[:, 0] = (abu * abs_v).sum(axis=1)
+    opt[:, 1] = (abu * sca_v).sum(axis=1)
+    gs = np.linspace(0.7, -0.2, ndust)
+    tabs = [synth.hg_tables(g, BINS) for g in gs]
+    dsc = np.concatenate([t[0] for t in tabs]).astype(np.float32)
+    csc = np.concatenate([t[1] for t in tabs]).astype(np.float32)
+    return dict(abu=abu.reshape(-1), abs_v=abs_v, sca_v=sca_v, opt=opt.reshape(-1), dsc=dsc, csc=csc)
+
+
+def run_bg_msf(batch=2, seed=0.44):
+    def run(X):
+        c = X.cloud
+        glob = 8 * c.AREA
+        k = _tau_scale(c, 1.0)
+        X.zero(0)
+        X.zero(1)
+        X.sim_pb(glob, 1, glob * batch, batch, seed, 1.0, 0.7, **_msf_inputs(c, k))
+        return dict(tabs=X.tabs.copy(), int=X.int_.copy())
+    return run
+
+
+def run_sca(kind, npix=(24, 20), dirs=((0.0, 0.0), (70.0, 30.0)), batch=3, glob=1024, seed=0.61, pspos=None,
+            hp_observer=None, nside=4, msf=False, emweight=False):
+    """kind: ps / bg / hp / cl.  hp_observer = (x,y,z): one Healpix image (NSIDE `nside`) seen from that position
+    instead of orthographic maps."""
     def run(X):
         c = X.cloud
         k = _tau_scale(c, 1.0)
         _, od, ra, de = observer_directions([d[0] for d in dirs], [d[1] for d in dirs])
         centre = np.array([0.5 * c.NX, 0.5 * c.NY, 0.5 * c.NZ], np.float32)
-        args = (len(dirs), npix[0], npix[1], 0.9 * c.NX / npix[0], centre, od, ra, de)
+        ndir = len(dirs)
+        if hp_observer is not None:
+            ndir = -nside
+            od = np.asarray([hp_observer], np.float32)
+            ra, de = ra[:1], de[:1]
+        args = (ndir, npix[0], npix[1], 0.9 * c.NX / npix[0], centre, od, ra, de)
+        opac = _msf_inputs(c, k) if msf else dict(abs_=1.0 * k, sca=2.5 * k, dsc=DSC6, csc=CSC6)
         if kind == "ps":
             pp = np.asarray(pspos, np.float32)
             ps = np.linspace(1.0, 2.0, len(pp)).astype(np.float32)
-            out = X.sca_ps(glob, glob * batch, batch * len(pp), seed, *args, abs_=1.0 * k, sca=2.5 * k, dsc=DSC6,
-                           csc=CSC6, pspos=pp.reshape(-1), ps=ps)
-        else:
+            out = X.sca_ps(glob, glob * batch, batch * len(pp), seed, *args, pspos=pp.reshape(-1), ps=ps, **opac)
+        elif kind == "bg":
             g = 8 * c.AREA
-            out = X.sca_pb(g, 1, g * batch, batch, seed, 1.5, *args, abs_=1.0 * k, sca=2.5 * k, dsc=DSC6, csc=CSC6)
+            out = X.sca_pb(g, 1, g * batch, batch, seed, 1.5, *args, **opac)
+        elif kind == "hp":
+            rng = np.random.default_rng(11)
+            sky = (0.2 + rng.random(49152)).astype(np.float32)
+            sky[20000:20400] *= 30.0
+            hpbgp = None
+            if X.opts.get("hpbg_weighted", 0):
+                p = np.clip(sky.astype(np.float64) / sky.mean(), 1e-3, 1e4)
+                p /= p.sum()
+                hpbgp = np.cumsum(p)
+                hpbgp[-1] = 1.00001
+                sky = (sky * (1.0 / 49152.0) / p).astype(np.float32)
+                hpbgp = hpbgp.astype(np.float32)
+            out = X.sca_hp(glob, glob * batch, batch, seed, *args, hpbg=sky, hpbgp=hpbgp, **opac)
+        else:
+            rng = np.random.default_rng(7)
+            emit = np.where(c.DENS > 0, c.DENS * (0.5 + rng.random(c.CELLS)), 0.0).astype(np.float32)
+            emwei = None
+            if emweight:
+                emwei = (3.0 * rng.random(c.CELLS)).astype(np.float32)
+                emwei[::7] = 0.0
+            out = X.sca_cl(glob, c.CELLS * batch, batch, seed, *args, emit=emit, emwei=emwei, **opac)
         return dict(out=out.copy())
     return run
 
@@ -228,6 +285,24 @@ CASES = {
     "sca_ps_oct8":     (_oct(8, 3), dict(no_ps=1, ffs=0), run_sca("ps", pspos=[(4.3, 4.2, 3.9)], batch=8)),
     "sca_bg_reg12":    (_reg(12), {}, run_sca("bg", batch=1)),
     "sca_bg_oct6":     (_oct(6, 3), {}, run_sca("bg", batch=1, dirs=((45.0, 45.0),))),
+    "sca_hp_reg12":    (_reg(12), {}, run_sca("hp", batch=4, glob=512)),
+    "sca_hp_oct6_w":   (_oct(6, 3), dict(hpbg_weighted=1, ffs=0), run_sca("hp", batch=4, glob=512, dirs=((120.0, 200.0),))),
+    "sca_cl_reg10":    (_reg(10), {}, run_sca("cl", batch=1, glob=256)),
+    "sca_cl_oct6_ew":  (_oct(6, 3), dict(use_emweight=1), run_sca("cl", batch=1, glob=256, emweight=True, dirs=((35.0, 110.0),))),
+    "sca_ps_reg12_hpobs": (_reg(12), dict(no_ps=1), run_sca("ps", pspos=[(6.3, 6.2, 5.9)], batch=6, glob=512,
+                                                           hp_observer=(5.1, 7.3, 6.6))),
+    "sca_bg_oct6_hpobs":  (_oct(6, 3), {}, run_sca("bg", batch=1, hp_observer=(20.0, -5.0, 3.0), nside=8)),
+    "sca_hp_reg12_hpobs": (_reg(12), {}, run_sca("hp", batch=4, glob=512, hp_observer=(5.1, 7.3, 6.6))),
+    "sca_cl_reg10_hpobs": (_reg(10), {}, run_sca("cl", batch=1, glob=256, hp_observer=(5.1, 3.3, 6.6))),
+    "bg_reg12_msf":    (_reg(12), dict(with_abu=1, with_msf=1, ndust=2, noabsorbed=0), run_bg_msf()),
+    "bg_oct6_msf":     (_oct(6, 3), dict(with_abu=1, with_msf=1, ndust=2), run_bg_msf(seed=0.91)),
+    "sca_bg_reg12_msf": (_reg(12), dict(with_abu=1, with_msf=1, ndust=2), run_sca("bg", batch=1, msf=True)),
+    "sca_ps_oct6_msf": (_oct(6, 3), dict(no_ps=1, with_abu=1, with_msf=1, ndust=2),
+                        run_sca("ps", pspos=[(3.3, 3.2, 2.9)], batch=8, glob=512, msf=True)),
+    "bg_reg12_mirror": (_reg(12), dict(mirror=1 + 4), run_bg(batch=2, seed=0.57)),
+    "bg_oct6_mirror":  (_oct(6, 3), dict(mirror=32), run_bg(batch=2, seed=0.58)),
+    "cl_reg10_mirror": (_reg(10), dict(mirror=16 + 2), run_cl(False)),
+    "sca_bg_reg12_mirror": (_reg(12), dict(mirror=1 + 8), run_sca("bg", batch=1)),
 }
 
 MAP_NSIDE = {"hpmap_oct8_3": 8}
