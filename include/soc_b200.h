@@ -25,8 +25,8 @@
  *   soc_ps_tau                              kernel PSTau (kernel_ASOC_map.c:1545; ASOC.py:3576-3644)
  *   soc_mapping / soc_healpix_mapping       kernels Mapping / HealpixMapping
  *                                           (kernel_ASOC_map.c:496, 890; ASOC.py:3127-3139)
- *   soc_sca_zero_out / soc_sca_ps / _pb     kernels zero_out / SimRAM_PS / SimRAM_PB of
- *                                           kernel_ASOC_sca.c:14, 1462, 471 (ASOCS.py:515, 665-708)
+ *   soc_sca_zero_out / soc_sca_ps / _pb     kernels zero_out / SimRAM_PS / SimRAM_PB / SimRAM_HP / SimRAM_CL of
+ *     / soc_sca_hp / soc_sca_cl             kernel_ASOC_sca.c:14, 1462, 471, 40, 1098 (ASOCS.py:515, 665-708)
  * New (no counterpart in the single-device reference):
  *   soc_set_shard, soc_device_ptr           packet sharding over ranks and the device addresses a
  *                                           host-side NCCL all-reduce needs
@@ -55,7 +55,7 @@ enum soc_status {
 
 /* The compile-time options of the reference kernels (ASOC.py:344-362) as run-time values.
  * Options that cannot work in the reference as shipped (DIR_WEIGHT, PS_METHOD 3) or that are out of
- * scope (WITH_MSF, ROI, DO_SPLIT, MIRROR, POLSTAT) are rejected with SOC_ERR_UNSUPPORTED. */
+ * scope (ROI, DO_SPLIT, POLSTAT) are rejected with SOC_ERR_UNSUPPORTED. */
 typedef struct soc_params {
     int32_t bins;              /* BINS: length of the DSC / CSC tables                        */
     int32_t no_ps;             /* NO_PS (>=1)                                                 */
@@ -69,12 +69,19 @@ typedef struct soc_params {
     int32_t ffs;               /* FFS: forced first scattering (scattered-light kernels)      */
     int32_t step_weight;       /* STEP_WEIGHT <=0,1,2                                         */
     int32_t level_threshold;   /* LEVEL_THRESHOLD (maps)                                      */
-    int32_t with_msf, mirror, dir_weight, do_split, roi_flags, map_interpolation; /* must be 0 */
+    int32_t with_msf;          /* WITH_MSF: one scattering function per dust species; needs with_abu, ABU, ABSV, SCAV and
+                                  DSC / CSC of ndust*bins entries (kernel_ASOC.c:777-794)        */
+    int32_t mirror;            /* MIRROR bit mask: 1 x=0, 2 x=NX, 4 y=0, 8 y=NY, 16 z=0, 32 z=NZ are reflecting borders
+                                  (ASOC.py:319-321, kernel_ASOC_aux.c:1054)                      */
+    int32_t dir_weight, do_split, roi_flags;   /* must be 0                                      */
+    int32_t map_interpolation; /* MAP_INTERPOLATION 0,1,2 (kernel_ASOC_map.c:656-811)            */
     float   sw_a, sw_b;        /* SW_A, SW_B                                                  */
     float   length;            /* LENGTH = GL*PARSEC rounded as "%.5e" (ASOC.py:347,356)      */
     float   factor;            /* FACTOR (1e20)                                               */
     float   adhoc;             /* ADHOC (1.0)                                                 */
     float   reserved;
+    int32_t ndust;             /* NDUST (only read when with_msf != 0)                            */
+    int32_t reserved2[3];
 } soc_params;
 
 /* Device buffers.  Names are those of the reference's kernel arguments. */
@@ -83,7 +90,10 @@ enum soc_buffer {
     SOC_BUF_INTZ, SOC_BUF_EMIT, SOC_BUF_EMWEI, SOC_BUF_OPT, SOC_BUF_DSC, SOC_BUF_CSC, SOC_BUF_PSPOS,
     SOC_BUF_PS, SOC_BUF_XPS_NSIDE, SOC_BUF_XPS_SIDE, SOC_BUF_XPS_AREA, SOC_BUF_HPBG, SOC_BUF_HPBGP,
     SOC_BUF_MAP, SOC_BUF_SAVETAU, SOC_BUF_OUT, SOC_BUF_ODIR, SOC_BUF_ORA, SOC_BUF_ODE, SOC_BUF_TTT,
-    SOC_BUF_TNEW, SOC_BUF_FABS, SOC_BUF_COUNT
+    SOC_BUF_TNEW, SOC_BUF_FABS,
+    SOC_BUF_ABU,               /* WITH_MSF: abundances [CELLS*NDUST], dust index fastest        */
+    SOC_BUF_ABSV, SOC_BUF_SCAV, /* WITH_MSF: the ABS / SCA kernel arguments as vectors [NDUST]  */
+    SOC_BUF_COUNT
 };
 
 /* Stream layout of the Monte Carlo kernels. */
@@ -171,12 +181,19 @@ int  soc_healpix_mapping(soc_context *ctx, int nside, float abs, float sca, cons
  * first `no` point sources in PSPOS towards the observer direction `dir`; results are copied to the host arrays. */
 int  soc_ps_tau(soc_context *ctx, int no, const float dir[3], float abs, float sca, float *colden_out, float *tau_out);
 
-/* Scattered light (ASOCS.py).  ODIR/ORA/ODE are [ndir*3] floats (x,y,z), OUT is [ndir*npix_y*npix_x]. */
+/* Scattered light (ASOCS.py).  ODIR/ORA/ODE are [ndir*3] floats (x,y,z), OUT is [ndir*npix_y*npix_x].
+ * ndir < 0 (ASOCS.py:44-47): one Healpix image of NSIDE = -ndir, RING order, seen by an observer at the position
+ * ODIR[0..2] (root-grid units); OUT is [12*NSIDE*NSIDE] and npix / map_dx / centre are ignored. */
 int  soc_sca_zero_out(soc_context *ctx, int ndir, int npix_x, int npix_y);
 int  soc_sca_ps(soc_context *ctx, int packets, int batch, float seed, float abs, float sca, int ndir, int npix_x,
                 int npix_y, float map_dx, const float centre[3], int global);
 int  soc_sca_pb(soc_context *ctx, int source, int packets, int batch, float seed, float abs, float sca, float bg,
                 int ndir, int npix_x, int npix_y, float map_dx, const float centre[3], int global);
+/* Healpix background (HPBG [+ HPBGP]) and emission from the cells (EMIT [+ EMWEI]) as sources of scattered light */
+int  soc_sca_hp(soc_context *ctx, int packets, int batch, float seed, float abs, float sca, int ndir, int npix_x,
+                int npix_y, float map_dx, const float centre[3], int global);
+int  soc_sca_cl(soc_context *ctx, int source, int packets, int batch, float seed, float abs, float sca, int ndir,
+                int npix_x, int npix_y, float map_dx, const float centre[3], int global);
 
 int  soc_get_counters(soc_context *ctx, soc_counters *out);
 int  soc_reset_counters(soc_context *ctx);

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, "_lib", "libsoc_b200.so")
 
 (BUF_DENS, BUF_PAR, BUF_TABS, BUF_XAB, BUF_INT, BUF_INTX, BUF_INTY, BUF_INTZ, BUF_EMIT, BUF_EMWEI, BUF_OPT, BUF_DSC,
  BUF_CSC, BUF_PSPOS, BUF_PS, BUF_XPS_NSIDE, BUF_XPS_SIDE, BUF_XPS_AREA, BUF_HPBG, BUF_HPBGP, BUF_MAP, BUF_SAVETAU,
- BUF_OUT, BUF_ODIR, BUF_ORA, BUF_ODE, BUF_TTT, BUF_TNEW, BUF_FABS, BUF_COUNT) = range(30)
+ BUF_OUT, BUF_ODIR, BUF_ORA, BUF_ODE, BUF_TTT, BUF_TNEW, BUF_FABS, BUF_ABU, BUF_ABSV, BUF_SCAV, BUF_COUNT) = range(33)
 
 RNG_REFERENCE, RNG_PACKET = 0, 1
 DEP_RED, DEP_WARP, DEP_TILE = 0, 1, 2
@@ -31,7 +31,8 @@ class SocParams(C.Structure):
         "bins", "no_ps", "ps_method", "with_abu", "with_ali", "noabsorbed", "save_intensity", "use_emweight",
         "hpbg_weighted", "ffs", "step_weight", "level_threshold", "with_msf", "mirror", "dir_weight", "do_split",
         "roi_flags", "map_interpolation")] + \
-        [(n, C.c_float) for n in ("sw_a", "sw_b", "length", "factor", "adhoc", "reserved")]
+        [(n, C.c_float) for n in ("sw_a", "sw_b", "length", "factor", "adhoc", "reserved")] + \
+        [("ndust", C.c_int32), ("reserved2", C.c_int32 * 3)]
 
 
 class SocCounters(C.Structure):
@@ -41,7 +42,7 @@ class SocCounters(C.Structure):
 
 _EXPORTS = """soc_last_error soc_version soc_create soc_destroy soc_sync soc_set_params soc_set_grid soc_set_rng_mode
 soc_set_shard soc_set_tuning soc_set_geometry soc_set_layout soc_upload soc_download soc_clear soc_device_ptr soc_zero_amc soc_sim_pb soc_sim_hp
-soc_sim_cl soc_absorbed_begin soc_absorbed_add soc_absorbed_finish soc_eq_temperature soc_emission soc_mapping soc_healpix_mapping soc_ps_tau soc_sca_zero_out soc_sca_ps soc_sca_pb
+soc_sim_cl soc_absorbed_begin soc_absorbed_add soc_absorbed_finish soc_eq_temperature soc_emission soc_mapping soc_healpix_mapping soc_ps_tau soc_sca_zero_out soc_sca_ps soc_sca_pb soc_sca_hp soc_sca_cl
 soc_get_counters soc_reset_counters soc_last_launch_ms soc_stream""".split()
 
 _lib = None
@@ -91,6 +92,8 @@ def load_library(path=None):
     L.soc_sca_zero_out.argtypes = [vp, i, i, i]
     L.soc_sca_ps.argtypes = [vp, i, i, f, f, f, i, i, i, f, fp, i]
     L.soc_sca_pb.argtypes = [vp, i, i, i, f, f, f, f, i, i, i, f, fp, i]
+    L.soc_sca_hp.argtypes = [vp, i, i, f, f, f, i, i, i, f, fp, i]
+    L.soc_sca_cl.argtypes = [vp, i, i, i, f, f, f, i, i, i, f, fp, i]
     L.soc_get_counters.argtypes = [vp, C.POINTER(SocCounters)]
     L.soc_reset_counters.argtypes = [vp]
     L.soc_last_launch_ms.argtypes = [vp, C.POINTER(C.c_float)]
@@ -147,6 +150,7 @@ class Device:
         p.do_split, p.roi_flags, p.map_interpolation = kw.get("do_split", 0), kw.get("roi_flags", 0), kw.get("map_interpolation", 0)
         p.sw_a, p.sw_b = kw.get("sw_a", 0.0), kw.get("sw_b", 0.0)
         p.length, p.factor, p.adhoc = kw["length"], kw.get("factor", 1.0e20), kw.get("adhoc", 1.0)
+        p.ndust = kw.get("ndust", 1)
         self._ck(self.L.soc_set_params(self.ctx, C.byref(p)))
         self.params = p
 
@@ -250,6 +254,15 @@ class Device:
         self._ck(self.L.soc_sca_pb(self.ctx, source, packets, batch, seed, abs_, sca, bg, ndir, npx, npy, map_dx, k[1],
                                    global_))
 
+    def sca_hp(self, packets, batch, seed, abs_, sca, ndir, npx, npy, map_dx, centre, global_):
+        k = _f3(centre)
+        self._ck(self.L.soc_sca_hp(self.ctx, packets, batch, seed, abs_, sca, ndir, npx, npy, map_dx, k[1], global_))
+
+    def sca_cl(self, source, packets, batch, seed, abs_, sca, ndir, npx, npy, map_dx, centre, global_):
+        k = _f3(centre)
+        self._ck(self.L.soc_sca_cl(self.ctx, source, packets, batch, seed, abs_, sca, ndir, npx, npy, map_dx, k[1],
+                                   global_))
+
     def counters(self):
         c = SocCounters()
         self._ck(self.L.soc_get_counters(self.ctx, C.byref(c)))
@@ -325,7 +338,8 @@ class Backend:
         table = dict(dsc=(BUF_DSC, np.float32), csc=(BUF_CSC, np.float32), emit=(BUF_EMIT, np.float32),
                      emwei=(BUF_EMWEI, np.float32), opt=(BUF_OPT, np.float32), pspos=(BUF_PSPOS, np.float32),
                      ps=(BUF_PS, np.float32), xps_nside=(BUF_XPS_NSIDE, np.int32), xps_side=(BUF_XPS_SIDE, np.int32),
-                     xps_area=(BUF_XPS_AREA, np.float32), hpbg=(BUF_HPBG, np.float32), hpbgp=(BUF_HPBGP, np.float32))
+                     xps_area=(BUF_XPS_AREA, np.float32), hpbg=(BUF_HPBG, np.float32), hpbgp=(BUF_HPBGP, np.float32),
+                     abu=(BUF_ABU, np.float32), abs_v=(BUF_ABSV, np.float32), sca_v=(BUF_SCAV, np.float32))
         for k, v in bufs.items():
             if v is None:
                 continue
@@ -385,13 +399,18 @@ class Backend:
             self.dev.upload(b, np.ascontiguousarray(np.asarray(v, np.float32)[:, :3].reshape(-1)))
         self.dev.sync()
 
+    def _sca_out(self, ndir, npx, npy):
+        if ndir < 0:
+            return self.dev.download(BUF_OUT, 12 * ndir * ndir)
+        return self.dev.download(BUF_OUT, ndir * npx * npy).reshape(ndir, npy, npx)
+
     def sca_ps(self, global_, packets, batch, seed, ndir, npx, npy, map_dx, centre, odirs, ora, ode, abs_=0.0, sca=0.0,
                **bufs):
         self._put(**bufs)
         self._observers(odirs, ora, ode)
         self.dev.sca_zero_out(ndir, npx, npy)
         self.dev.sca_ps(packets, batch, seed, abs_, sca, ndir, npx, npy, map_dx, centre, global_)
-        return self.dev.download(BUF_OUT, ndir * npx * npy).reshape(ndir, npy, npx)
+        return self._sca_out(ndir, npx, npy)
 
     def sca_pb(self, global_, source, packets, batch, seed, bg, ndir, npx, npy, map_dx, centre, odirs, ora, ode,
                abs_=0.0, sca=0.0, **bufs):
@@ -399,7 +418,23 @@ class Backend:
         self._observers(odirs, ora, ode)
         self.dev.sca_zero_out(ndir, npx, npy)
         self.dev.sca_pb(source, packets, batch, seed, abs_, sca, bg, ndir, npx, npy, map_dx, centre, global_)
-        return self.dev.download(BUF_OUT, ndir * npx * npy).reshape(ndir, npy, npx)
+        return self._sca_out(ndir, npx, npy)
+
+    def sca_hp(self, global_, packets, batch, seed, ndir, npx, npy, map_dx, centre, odirs, ora, ode, abs_=0.0, sca=0.0,
+               **bufs):
+        self._put(**bufs)
+        self._observers(odirs, ora, ode)
+        self.dev.sca_zero_out(ndir, npx, npy)
+        self.dev.sca_hp(packets, batch, seed, abs_, sca, ndir, npx, npy, map_dx, centre, global_)
+        return self._sca_out(ndir, npx, npy)
+
+    def sca_cl(self, global_, packets, batch, seed, ndir, npx, npy, map_dx, centre, odirs, ora, ode, abs_=0.0, sca=0.0,
+               **bufs):
+        self._put(**bufs)
+        self._observers(odirs, ora, ode)
+        self.dev.sca_zero_out(ndir, npx, npy)
+        self.dev.sca_cl(2, packets, batch, seed, abs_, sca, ndir, npx, npy, map_dx, centre, global_)
+        return self._sca_out(ndir, npx, npy)
 
     def close(self):
         self.dev.close()

@@ -57,7 +57,7 @@ struct soc_context {
 static const char *buf_name(int b) {
     static const char *n[SOC_BUF_COUNT] = { "DENS", "PAR", "TABS", "XAB", "INT", "INTX", "INTY", "INTZ", "EMIT", "EMWEI",
         "OPT", "DSC", "CSC", "PSPOS", "PS", "XPS_NSIDE", "XPS_SIDE", "XPS_AREA", "HPBG", "HPBGP", "MAP", "SAVETAU", "OUT",
-        "ODIR", "ORA", "ODE", "TTT", "TNEW", "FABS" };
+        "ODIR", "ORA", "ODE", "TTT", "TNEW", "FABS", "ABU", "ABSV", "SCAV" };
     return (b >= 0 && b < SOC_BUF_COUNT) ? n[b] : "?";
 }
 
@@ -146,8 +146,12 @@ int soc_sync(soc_context *c) {
 int soc_set_params(soc_context *c, const soc_params *p) {
     NEED_CTX(c);
     if (p == nullptr) return fail(SOC_ERR_ARG, "soc_set_params: null");
-    if (p->with_msf || p->mirror || p->dir_weight || p->do_split || p->roi_flags || p->map_interpolation)
-        return fail(SOC_ERR_UNSUPPORTED, "soc_set_params: WITH_MSF / MIRROR / DIR_WEIGHT / DO_SPLIT / ROI / MAP_INTERPOLATION are not implemented");
+    if (p->dir_weight || p->do_split || p->roi_flags)
+        return fail(SOC_ERR_UNSUPPORTED, "soc_set_params: DIR_WEIGHT / DO_SPLIT / ROI are not implemented");
+    if (p->with_msf && (!p->with_abu || p->ndust < 1))
+        return fail(SOC_ERR_ARG, "soc_set_params: WITH_MSF needs WITH_ABU and NDUST >= 1 (ASOC.py:1167)");
+    if (p->mirror < 0 || p->mirror > 63) return fail(SOC_ERR_ARG, "soc_set_params: MIRROR=%d", p->mirror);
+    if (p->map_interpolation < 0 || p->map_interpolation > 2) return fail(SOC_ERR_ARG, "soc_set_params: MAP_INTERPOLATION=%d", p->map_interpolation);
     if (p->ps_method == 3 || p->ps_method < 0 || p->ps_method > 5)
         return fail(SOC_ERR_UNSUPPORTED, "soc_set_params: PS_METHOD %d (the reference's method 3 does not compile either)", p->ps_method);
     if (p->bins < 2) return fail(SOC_ERR_ARG, "soc_set_params: BINS=%d", p->bins);
@@ -324,6 +328,13 @@ static int sim_common(soc_context *c, SimArgs &A, int kind, int batch, float see
     }
     if ((r = need(c, SOC_BUF_CSC, (size_t)P.bins * 4, who)) != SOC_OK) return r;
     if (P.with_abu && (r = need(c, SOC_BUF_OPT, 2 * n, who)) != SOC_OK) return r;
+    if (P.with_msf) {
+        if ((r = need(c, SOC_BUF_ABU, n * P.ndust, who)) != SOC_OK) return r;
+        if ((r = need(c, SOC_BUF_SCAV, (size_t)P.ndust * 4, who)) != SOC_OK) return r;
+        if ((r = need(c, SOC_BUF_CSC, (size_t)P.bins * P.ndust * 4, who)) != SOC_OK) return r;
+    }
+    A.abu = dptr<float>(c, SOC_BUF_ABU); A.scav = dptr<float>(c, SOC_BUF_SCAV);
+    A.with_msf = P.with_msf; A.ndust = P.with_msf ? P.ndust : 1; A.mirror = P.mirror;
     A.tabs = dptr<float>(c, SOC_BUF_TABS); A.xab = dptr<float>(c, SOC_BUF_XAB);
     A.inten = dptr<float>(c, SOC_BUF_INT); A.intx = dptr<float>(c, SOC_BUF_INTX);
     A.inty = dptr<float>(c, SOC_BUF_INTY); A.intz = dptr<float>(c, SOC_BUF_INTZ);
@@ -612,37 +623,55 @@ int soc_ps_tau(soc_context *c, int no, const float dir[3], float abs, float sca,
 // ---- scattered light ------------------------------------------------------------------------------------------
 int soc_sca_zero_out(soc_context *c, int ndir, int npix_x, int npix_y) {
     NEED_CTX(c);
+    if (ndir < 0) return soc_clear(c, SOC_BUF_OUT, (size_t)12 * ndir * ndir * 4);      // Healpix image, NSIDE = -ndir
     if (ndir < 1 || npix_x < 1 || npix_y < 1) return fail(SOC_ERR_ARG, "soc_sca_zero_out: bad arguments");
     return soc_clear(c, SOC_BUF_OUT, (size_t)ndir * npix_x * npix_y * 4);
 }
 
-static int sca_common(soc_context *c, ScaArgs &S, int kind, int batch, float seed, float abs, float sca, int ndir,
+static int sca_common(soc_context *c, ScaArgs &S, int kind, int flavour, int batch, float seed, float abs, float sca, int ndir,
                       int npix_x, int npix_y, float map_dx, const float centre[3], int global, const char *who) {
     if (!c->have_grid || !c->have_params) return fail(SOC_ERR_STATE, "%s: grid and params first", who);
-    if (batch < 1 || global < 1 || ndir < 1 || npix_x < 1 || npix_y < 1 || centre == nullptr)
-        return fail(SOC_ERR_ARG, "%s: bad arguments (Healpix observers, NDIR<0, are not implemented)", who);
+    if (batch < 1 || global < 1 || ndir == 0) return fail(SOC_ERR_ARG, "%s: bad arguments", who);
+    const int nside = ndir < 0 ? -ndir : 0;                    // Healpix image seen from ODIR[0..2] (ASOCS.py:44-47)
+    if (nside > 8192) return fail(SOC_ERR_ARG, "%s: NSIDE=%d", who, nside);
+    if (nside == 0 && (npix_x < 1 || npix_y < 1 || centre == nullptr)) return fail(SOC_ERR_ARG, "%s: bad map geometry", who);
     const soc_params &P = c->P;
     if (kind == SIM_PS && P.ps_method != 0 && P.ps_method != 1)
         return fail(SOC_ERR_UNSUPPORTED, "%s: PS_METHOD %d reads XPS_* through mistyped pointers in the reference (kernel_ASOC_sca.c:1486)", who, P.ps_method);
-    const size_t n = (size_t)c->G.cells * 4, nd = (size_t)ndir * 12;
+    const int nd_eff = nside ? 1 : ndir;
+    const size_t n = (size_t)c->G.cells * 4, nd = (size_t)nd_eff * 12;
+    const size_t npix = nside ? (size_t)12 * nside * nside : (size_t)ndir * npix_x * npix_y;
+    const int nsf = P.with_msf ? P.ndust : 1;
     int r;
-    if ((r = need(c, SOC_BUF_CSC, (size_t)P.bins * 4, who)) != SOC_OK) return r;
-    if ((r = need(c, SOC_BUF_DSC, (size_t)P.bins * 4, who)) != SOC_OK) return r;
+    if ((r = need(c, SOC_BUF_CSC, (size_t)P.bins * nsf * 4, who)) != SOC_OK) return r;
+    if ((r = need(c, SOC_BUF_DSC, (size_t)P.bins * nsf * 4, who)) != SOC_OK) return r;
     if ((r = need(c, SOC_BUF_ODIR, nd, who)) != SOC_OK) return r;
-    if ((r = need(c, SOC_BUF_ORA, nd, who)) != SOC_OK) return r;
-    if ((r = need(c, SOC_BUF_ODE, nd, who)) != SOC_OK) return r;
+    if (!nside) {
+        if ((r = need(c, SOC_BUF_ORA, nd, who)) != SOC_OK) return r;
+        if ((r = need(c, SOC_BUF_ODE, nd, who)) != SOC_OK) return r;
+    }
     if (P.with_abu && (r = need(c, SOC_BUF_OPT, 2 * n, who)) != SOC_OK) return r;
-    if ((r = ensure_zeroed(c, SOC_BUF_OUT, (size_t)ndir * npix_x * npix_y * 4)) != SOC_OK) return r;
+    if (P.with_msf) {
+        if ((r = need(c, SOC_BUF_ABU, n * P.ndust, who)) != SOC_OK) return r;
+        if ((r = need(c, SOC_BUF_SCAV, (size_t)P.ndust * 4, who)) != SOC_OK) return r;
+    }
+    if ((r = ensure_zeroed(c, SOC_BUF_OUT, npix * 4)) != SOC_OK) return r;
     memset(&S, 0, sizeof(S));
     S.G = c->G;
     S.out = dptr<float>(c, SOC_BUF_OUT);
     S.opt = dptr<float>(c, SOC_BUF_OPT); S.dsc = dptr<float>(c, SOC_BUF_DSC); S.csc = dptr<float>(c, SOC_BUF_CSC);
     S.pspos = dptr<float>(c, SOC_BUF_PSPOS); S.ps = dptr<float>(c, SOC_BUF_PS);
     S.odir = dptr<float>(c, SOC_BUF_ODIR); S.ora = dptr<float>(c, SOC_BUF_ORA); S.ode = dptr<float>(c, SOC_BUF_ODE);
+    S.hpbg = dptr<float>(c, SOC_BUF_HPBG); S.hpbgp = dptr<float>(c, SOC_BUF_HPBGP);
+    S.emit = dptr<float>(c, SOC_BUF_EMIT); S.emwei = dptr<float>(c, SOC_BUF_EMWEI);
+    S.abu = dptr<float>(c, SOC_BUF_ABU); S.scav = dptr<float>(c, SOC_BUF_SCAV);
     S.kabs = abs; S.ksca = sca; S.map_dx = map_dx;
-    S.centre = { centre[0], centre[1], centre[2] };
-    S.kind = kind; S.batch = batch; S.global = global; S.ndir = ndir; S.npx = npix_x; S.npy = npix_y;
+    if (centre) S.centre = { centre[0], centre[1], centre[2] };
+    S.kind = kind; S.flavour = flavour; S.batch = batch; S.global = global; S.ndir = nd_eff; S.nside = nside;
+    S.npx = nside ? 1 : npix_x; S.npy = nside ? 1 : npix_y;
     S.bins = P.bins; S.no_ps = P.no_ps; S.ps_method = P.ps_method; S.with_abu = P.with_abu; S.ffs = P.ffs;
+    S.hpbg_weighted = P.hpbg_weighted; S.use_emweight = P.use_emweight; S.with_ali = 0;
+    S.with_msf = P.with_msf; S.ndust = P.with_msf ? P.ndust : 1; S.mirror = P.mirror;
     S.rank = c->rank; S.world = c->world; S.ref_geometry = c->geometry; S.ev_batch = c->sc_batch > 0 ? c->sc_batch : 3; S.nav_hops = c->nav_hops;
     long long ms = 100LL * ((long long)c->G.nx + c->G.ny + c->G.nz) << (c->G.levels - 1);
     S.max_steps = (int)(ms > INT_MAX ? INT_MAX : ms);
@@ -681,12 +710,11 @@ int soc_sca_ps(soc_context *c, int packets, int batch, float seed, float abs, fl
     NEED_CTX(c);
     (void)packets;
     ScaArgs S;
-    int r = sca_common(c, S, SIM_PS, batch, seed, abs, sca, ndir, npix_x, npix_y, map_dx, centre, global, "soc_sca_ps");
+    int r = sca_common(c, S, SIM_PS, 0, batch, seed, abs, sca, ndir, npix_x, npix_y, map_dx, centre, global, "soc_sca_ps");
     if (r != SOC_OK) return r;
     const size_t nps = (size_t)c->P.no_ps;
     if ((r = need(c, SOC_BUF_PSPOS, nps * 12, "soc_sca_ps")) != SOC_OK) return r;
     if ((r = need(c, SOC_BUF_PS, nps * 4, "soc_sca_ps")) != SOC_OK) return r;
-    S.flavour = 0;
     S.nunits = (c->rng_mode == SOC_RNG_REFERENCE) ? global : (long long)global * batch;
     return sca_launch(c, S, "soc_sca_ps");
 }
@@ -697,17 +725,45 @@ int soc_sca_pb(soc_context *c, int source, int packets, int batch, float seed, f
     (void)packets;
     if (source != 0 && source != 1) return fail(SOC_ERR_UNSUPPORTED, "soc_sca_pb: SOURCE=%d", source);
     ScaArgs S;
-    int r = sca_common(c, S, source == 0 ? SIM_PS : SIM_BG, batch, seed, abs, sca, ndir, npix_x, npix_y, map_dx, centre, global, "soc_sca_pb");
+    int r = sca_common(c, S, source == 0 ? SIM_PS : SIM_BG, 1, batch, seed, abs, sca, ndir, npix_x, npix_y, map_dx, centre, global, "soc_sca_pb");
     if (r != SOC_OK) return r;
     if (source == 0) {
         const size_t nps = (size_t)c->P.no_ps;
         if ((r = need(c, SOC_BUF_PSPOS, nps * 12, "soc_sca_pb")) != SOC_OK) return r;
         if ((r = need(c, SOC_BUF_PS, nps * 4, "soc_sca_pb")) != SOC_OK) return r;
     }
-    S.bg = bg; S.flavour = 1;
+    S.bg = bg;
     long long items = (source == 1 && 8LL * c->G.area < global) ? 8LL * c->G.area : global;
     S.nunits = (c->rng_mode == SOC_RNG_REFERENCE) ? global : items * batch;
     return sca_launch(c, S, "soc_sca_pb");
+}
+
+int soc_sca_hp(soc_context *c, int packets, int batch, float seed, float abs, float sca, int ndir, int npix_x, int npix_y,
+               float map_dx, const float centre[3], int global) {
+    NEED_CTX(c);
+    (void)packets;
+    ScaArgs S;
+    int r = sca_common(c, S, SIM_HP, 2, batch, seed, abs, sca, ndir, npix_x, npix_y, map_dx, centre, global, "soc_sca_hp");
+    if (r != SOC_OK) return r;
+    if ((r = need(c, SOC_BUF_HPBG, 49152 * 4, "soc_sca_hp")) != SOC_OK) return r;
+    if (c->P.hpbg_weighted && (r = need(c, SOC_BUF_HPBGP, 49152 * 4, "soc_sca_hp")) != SOC_OK) return r;
+    S.nunits = (c->rng_mode == SOC_RNG_REFERENCE) ? global : (long long)global * batch;
+    return sca_launch(c, S, "soc_sca_hp");
+}
+
+int soc_sca_cl(soc_context *c, int source, int packets, int batch, float seed, float abs, float sca, int ndir, int npix_x,
+               int npix_y, float map_dx, const float centre[3], int global) {
+    NEED_CTX(c);
+    (void)packets; (void)source;
+    ScaArgs S;
+    int r = sca_common(c, S, SIM_CL, 3, batch, seed, abs, sca, ndir, npix_x, npix_y, map_dx, centre, global, "soc_sca_cl");
+    if (r != SOC_OK) return r;
+    const size_t n = (size_t)c->G.cells * 4;
+    if ((r = need(c, SOC_BUF_EMIT, n, "soc_sca_cl")) != SOC_OK) return r;
+    if (c->P.use_emweight && (r = need(c, SOC_BUF_EMWEI, n, "soc_sca_cl")) != SOC_OK) return r;
+    if (c->P.use_emweight > 1) return fail(SOC_ERR_UNSUPPORTED, "soc_sca_cl: USE_EMWEIGHT=2 is not implemented");
+    S.nunits = (c->rng_mode == SOC_RNG_REFERENCE) ? global : c->G.cells;
+    return sca_launch(c, S, "soc_sca_cl");
 }
 
 int soc_get_counters(soc_context *c, soc_counters *out) {

@@ -305,7 +305,33 @@ __device__ __forceinline__ void to_surface(const GridDesc &G, vec3 &p, const vec
     p.x = xadd(p.x, xmul(dx, d.x)); p.y = xadd(p.y, xmul(dx, d.y)); p.z = xadd(p.z, xmul(dx, d.z));
 }
 
+// Mirror (kernel_ASOC_aux.c:1054-1083), literally: every enabled border negates its direction component whether or
+// not it was crossed (`if (c) a ; b ;`).  Used by the parity / reference-geometry kernels; the production kernels
+// reflect only the crossed border.
+template <bool OCT>
+__device__ __forceinline__ void mirror_literal(const GridDesc &G, int mask, vec3 &p, vec3 &d, int &level, int &ind, float &rho) {
+    const float EPS = 5.0e-4f;
+    if (mask & 1)  { if (p.x < 0.0f)         p.x = EPS;                       d.x = -d.x; index_global<OCT, false>(G, p, level, ind, rho); }
+    if (mask & 2)  { if (p.x > (float)G.nx)  p.x = xsub((float)G.nx, EPS);    d.x = -d.x; index_global<OCT, false>(G, p, level, ind, rho); }
+    if (mask & 4)  { if (p.y < 0.0f)         p.y = EPS;                       d.y = -d.y; index_global<OCT, false>(G, p, level, ind, rho); }
+    if (mask & 8)  { if (p.y > (float)G.ny)  p.y = xsub((float)G.ny, EPS);    d.y = -d.y; index_global<OCT, false>(G, p, level, ind, rho); }
+    if (mask & 16) { if (p.z < 0.0f)         p.z = EPS;                       d.z = -d.z; index_global<OCT, false>(G, p, level, ind, rho); }
+    if (mask & 32) { if (p.z > (float)G.nz)  p.z = xsub((float)G.nz, EPS);    d.z = -d.z; index_global<OCT, false>(G, p, level, ind, rho); }
+}
+
 // ---- scattering ---------------------------------------------------------------------------------------------
+// WITH_MSF: the dust species that scatters in cell `oind`, drawn with probability ABU*SCA / sum(ABU*SCA)
+// (kernel_ASOC.c:777-794; the sum is OPT[2*oind+1]).  `u` is a uniform random number.
+__device__ __forceinline__ int msf_pick(const float *__restrict__ abu, const float *__restrict__ scav, int ndust, float sum, int oind, float u) {
+    float ds = xmul(0.99999f, u);
+    int i;
+    for (i = 0; i < ndust; i++) {
+        ds = xsub(ds, xdiv(xmul(abu[i + (size_t)oind * ndust], scav[i]), sum));
+        if (ds <= 0.0f) break;
+    }
+    return min(i, ndust - 1);
+}
+
 __device__ __forceinline__ void fix_direction(vec3 &d) {             // kernel_ASOC.c:508-511
     if (fabsf(d.x) < SOC_DEPS) d.x = SOC_DEPS;
     if (fabsf(d.y) < SOC_DEPS) d.y = SOC_DEPS;

@@ -137,3 +137,114 @@ __device__ void emit_bg(const ARGS &A, RNG &rng, int id, Packet &pk) {
     locate<OCT>(G, pk);
 }
 
+
+// ---- emission: Healpix background (kernel_ASOC.c:885-947) ---------------------------------------------------
+template <class ARGS, class RNG, bool OCT>
+__device__ void emit_hp(const ARGS &A, RNG &rng, Packet &pk) {
+    const GridDesc &G = A.G;
+    const float NX = (float)G.nx, NY = (float)G.ny, NZ = (float)G.nz;
+    int ipix;
+    if (A.hpbg_weighted < 1) {
+        ipix = clampi((int)floorf(rng.uniform() * 49152), 0, 49151);
+    } else {
+        float x = rng.uniform();
+        int lo = 0, hi = 49151;
+        for (int i = 0; i < 10; i++) {
+            ipix = (lo + hi) / 2;
+            if (A.hpbgp[ipix] > x) hi = ipix; else lo = ipix;
+        }
+        for (ipix = lo; ipix <= hi; ipix++) if (A.hpbgp[ipix] >= x) break;
+    }
+    pk.photons = A.hpbg[ipix];
+    float phi, theta, st, ct, sp, cp;
+    pix2ang_ring(64, ipix, phi, theta, SOC_PI);
+    sincosf(theta, &st, &ct); sincosf(phi, &sp, &cp);
+    pk.dir.x = st * cp; pk.dir.y = st * sp; pk.dir.z = -ct;
+    fix_direction(pk.dir);
+    float x = fabsf(pk.dir.x), y = fabsf(pk.dir.y), z = fabsf(pk.dir.z);
+    float ds = xadd(xadd(x, y), z);
+    x = xdiv(x, ds); y = xdiv(y, ds); z = xdiv(z, ds);
+    ds = rng.uniform();
+    float v1 = rng.uniform(), v2 = rng.uniform();
+    if (ds < x)                { pk.pos.y = v1 * NY; pk.pos.z = v2 * NZ; pk.pos.x = (pk.dir.x > 0.0f) ? SOC_PEPS : (NX - SOC_PEPS); }
+    else if (ds < xadd(x, y))  { pk.pos.x = v1 * NX; pk.pos.z = v2 * NZ; pk.pos.y = (pk.dir.y > 0.0f) ? SOC_PEPS : (NY - SOC_PEPS); }
+    else                       { pk.pos.x = v1 * NX; pk.pos.y = v2 * NY; pk.pos.z = (pk.dir.z > 0.0f) ? SOC_PEPS : (NZ - SOC_PEPS); }
+    locate<OCT>(G, pk);
+}
+
+// ---- emission: one ray from cell `icell` (kernel_ASOC.c:1323-1393) ------------------------------------------
+template <class ARGS, class RNG>
+__device__ void emit_cl(const ARGS &A, RNG &rng, int icell, float pwei, Packet &pk) {
+    const GridDesc &G = A.G;
+    int ind = icell, level;
+    for (level = 0; level < G.levels - 1; level++) {
+        ind -= G.lcells[level];
+        if (ind < 0) { ind += G.lcells[level]; break; }
+    }
+    float X0, Y0, Z0;
+    if (level == 0) { X0 = ind % G.nx; Y0 = (ind / G.nx) % G.ny; Z0 = ind / (G.nx * G.ny); }
+    else { int sid = ind & 7; X0 = sid & 1; Y0 = (sid >> 1) & 1; Z0 = sid >> 2; }
+    pk.photons = A.emit[icell] * pwei;
+    pk.pos.x = xadd(X0, rng.uniform()); pk.pos.y = xadd(Y0, rng.uniform()); pk.pos.z = xadd(Z0, rng.uniform());
+    isotropic(rng, pk.dir);
+    pk.level = level; pk.ind = ind; pk.rho = G.dens[icell];
+    pk.eidx = A.with_ali ? icell : -1;
+}
+
+// Packets-per-cell rule of SimRAM_CL (kernel_ASOC.c:1293-1316).  Returns the number of rays (0 = skip the cell).
+template <class ARGS>
+__device__ __forceinline__ int cl_rays(const ARGS &A, int icell, float &pwei) {
+    if (A.use_emweight > 0) {
+        pwei = A.emwei[icell];
+        if (pwei < 1e-10f || A.G.dens[icell] <= 0.0f) return 0;
+        int batch = (int)floorf(pwei);
+        if (batch < 1) { batch = 1; pwei = (float)(1.0 / (double)(pwei + 1.0e-30f)); }
+        else           { pwei = (float)(1.0 / (double)((float)batch + 1.0e-9f)); }
+        return batch;
+    }
+    pwei = 1.0f / ((float)A.batch + 1.0e-9f);
+    return A.batch;
+}
+
+
+// ---- emission: Healpix background of the scattered-light run (kernel_ASOC_sca.c:104-217) ------------------------
+// Unlike the absorption run's SimRAM_HP the packet enters through a disc of radius Rout facing the sky pixel and
+// is stepped onto the cloud surface; packets that miss the cloud are dropped (ind < 0).
+template <class ARGS, class RNG, bool OCT>
+__device__ void emit_hp_sca(const ARGS &A, RNG &rng, Packet &pk) {
+    const GridDesc &G = A.G;
+    const float NX = (float)G.nx, NY = (float)G.ny, NZ = (float)G.nz;
+    const float Rout = xmul(0.5f, sqrtf(xadd(xadd(xmul(xmul(1.0f, NX), NX), xmul(NY, NY)), xmul(NZ, NZ))));
+    int ipix;
+    if (A.hpbg_weighted < 1) {
+        ipix = clampi((int)floorf(rng.uniform() * 49152), 0, 49151);
+    } else {
+        float x = rng.uniform();
+        int lo = 0, hi = 49151;
+        for (int i = 0; i < 12; i++) {
+            ipix = (lo + hi) / 2;
+            if (A.hpbgp[ipix] > x) hi = ipix; else lo = ipix;
+        }
+        for (ipix = lo; ipix <= hi; ipix++) if (A.hpbgp[ipix] >= x) break;
+    }
+    pk.photons = A.hpbg[ipix];
+    float phi, theta, st, ct, sp, cp;
+    pix2ang_ring(64, ipix, phi, theta, SOC_PI);
+    sincosf(theta, &st, &ct); sincosf(phi, &sp, &cp);
+    pk.dir.x = xmul(st, cp); pk.dir.y = xmul(st, sp); pk.dir.z = -ct;
+    fix_direction(pk.dir);
+    float ds = xmul(xmul(2.0f, SOC_PI), rng.uniform());
+    float dx = sqrtf(rng.uniform());
+    float sd, cd;
+    sincosf(ds, &sd, &cd);
+    vec3 p = { xmul(dx, cd), xmul(dx, sd), sqrtf(xsub(1.001f, xmul(dx, dx))) };
+    vec3 q = { xadd(xmul(p.x, ct), xmul(p.z, st)), p.y, xadd(xmul(-p.x, st), xmul(p.z, ct)) };
+    float s2, c2;
+    sincosf(xsub(SOC_PI, phi), &s2, &c2);
+    p.x = xadd(xmul(q.x, c2), xmul(q.y, s2));
+    p.y = xadd(xmul(-q.x, s2), xmul(q.y, c2));
+    p.z = q.z;
+    pk.pos.x = xadd(xmul(0.5f, NX), xmul(Rout, p.x)); pk.pos.y = xadd(xmul(0.5f, NY), xmul(Rout, p.y)); pk.pos.z = xadd(xmul(0.5f, NZ), xmul(Rout, p.z));
+    to_surface(G, pk.pos, pk.dir);
+    locate<OCT>(G, pk);
+}

@@ -19,6 +19,7 @@
 namespace {
 
 enum RayMode { RAY_IDLE = 0, RAY_FFS = 1, RAY_MAIN = 2, RAY_PEEL = 3 };
+enum { SRC_PS = 0, SRC_BG = 1, SRC_HP = 2, SRC_CL = 3 };         // == SimKind
 
 struct Ray { vec3 pos, dir; float rho, tau; int level, ind; };
 
@@ -26,16 +27,21 @@ struct Lane {
     Ray r;              // the ray being stepped
     vec3 kpos, kdir;    // packet position / direction kept while look-ahead or peel-off rays are traced
     float krho, photons, free_path;
+    float dleft, dscale;      // Healpix observer: distance left to the observer, 1/d^2
     int klevel, kind_, mode, idir, scat, nstep;
 };
 
 struct ScaCounters { unsigned long long packets, steps, scat, stuck, peels; };
+
+// cos(theta) clamp before the DSC look-up: SimRAM_PS/PB use 0.999, SimRAM_HP/CL 0.9999 (kernel_ASOC_sca.c:991,1830 / 356,1329)
+__device__ __forceinline__ float cos_clamp(const ScaArgs &S) { return (S.flavour >= 2) ? 0.9999f : 0.999f; }
 
 template <class RNG, bool OCT>
 __device__ __forceinline__ void begin_packet(const ScaArgs &S, Lane &L, RNG &rng, const Packet &pk) {
     L.kpos = pk.pos; L.kdir = pk.dir; L.krho = pk.rho; L.klevel = pk.level; L.kind_ = pk.ind;
     L.photons = pk.photons; L.scat = 0; L.nstep = 0;
     L.r.pos = pk.pos; L.r.dir = pk.dir; L.r.rho = pk.rho; L.r.level = pk.level; L.r.ind = pk.ind; L.r.tau = 0.0f;
+    if (S.flavour >= 2 && pk.ind < 0) { L.mode = RAY_IDLE; return; }       // SimRAM_HP: `if (ind<0) continue`, no draw
     if (S.ffs > 0) {
         L.mode = RAY_FFS;
         if (pk.ind < 0) {              // nothing to look ahead through: tau = 0, the draw still happens
@@ -49,8 +55,20 @@ __device__ __forceinline__ void begin_packet(const ScaArgs &S, Lane &L, RNG &rng
     }
 }
 
+template <bool OCT>
 __device__ __forceinline__ void start_peel(const ScaArgs &S, Lane &L) {
     L.r.pos = L.kpos; L.r.level = L.klevel; L.r.ind = L.kind_; L.r.rho = L.krho; L.r.tau = 0.0f;
+    if (S.nside > 0) {
+        // Healpix image seen from the position odir[0..2]: kernel_ASOC_sca.c:312-332, 968-988, 1309-1329, 1807-1827
+        vec3 q = L.kpos;
+        if (OCT) root_position(S.G, q, L.klevel, L.kind_);
+        vec3 od = { xsub(S.odir[0], q.x), xsub(S.odir[1], q.y), xsub(S.odir[2], q.z) };
+        const float dx = sqrtf(xadd(xadd(xmul(od.x, od.x), xmul(od.y, od.y)), xmul(od.z, od.z)));
+        L.dleft = dx;
+        L.dscale = xdiv(1.0f, xmul(dx, dx));
+        L.r.dir.x = xdiv(od.x, dx); L.r.dir.y = xdiv(od.y, dx); L.r.dir.z = xdiv(od.z, dx);
+        return;
+    }
     L.r.dir.x = S.odir[3 * L.idir]; L.r.dir.y = S.odir[3 * L.idir + 1]; L.r.dir.z = S.odir[3 * L.idir + 2];
 }
 
@@ -69,31 +87,54 @@ __device__ __forceinline__ void advance(const ScaArgs &S, Lane &L, RNG &rng, Sca
     if (S.with_abu) { float2 o = reinterpret_cast<const float2 *>(S.opt)[oind]; kabs = o.x; ksca = o.y; }
     cnt.steps++;
     if (L.mode == RAY_PEEL) {
-        r.tau += ds * rho0 * (kabs + ksca);
-        if (r.ind >= 0) return;
-        // the peel-off ray has reached the surface: kernel_ASOC_sca.c:1010-1046 / 1849-1885
+        if (S.nside > 0) {
+            // sic: the step is cut at the observer and lengthened by 1e-6 (a double literal in SimRAM_PB, :982)
+            ds = (S.flavour == 1) ? (float)((double)fminf(L.dleft, ds) + 1.0e-6) : xadd(fminf(L.dleft, ds), 1.0e-6f);
+            L.dleft = xsub(L.dleft, ds);
+            r.tau = xadd(r.tau, xmul(xmul(ds, rho0), xadd(kabs, ksca)));
+            if (L.dleft > 0.0f && r.ind >= 0) return;
+        } else {
+            r.tau += ds * rho0 * (kabs + ksca);
+            if (r.ind >= 0) return;
+        }
+        // the peel-off ray has reached the surface (or the observer): kernel_ASOC_sca.c:1010-1046 / 1849-1885
         cnt.peels++;
-        float cos_theta = clampf(dot3(L.kdir, r.dir), -0.999f, +0.999f);
-        float delta = L.photons * expf(-r.tau) * S.dsc[clampi((int)xmul(xmul((float)S.bins, xadd(1.0f, cos_theta)), 0.5f), 0, S.bins - 1)];
-        vec3 p = { xsub(r.pos.x, S.centre.x), xsub(r.pos.y, S.centre.y), xsub(r.pos.z, S.centre.z) };
-        const vec3 ra = { S.ora[3 * L.idir], S.ora[3 * L.idir + 1], S.ora[3 * L.idir + 2] };
-        const vec3 de = { S.ode[3 * L.idir], S.ode[3 * L.idir + 1], S.ode[3 * L.idir + 2] };
-        int i = (int)xadd(xsub(xmul(0.5f, (float)S.npx), 0.00005f), xdiv(dot3(p, ra), S.map_dx));
-        int j = (int)xadd(xsub(xmul(0.5f, (float)S.npy), 0.00005f), xdiv(dot3(p, de), S.map_dx));
-        if (i >= 0 && j >= 0 && i < S.npx && j < S.npy) atomicAdd(&S.out[i + L.idir * S.npx * S.npy + j * S.npx], delta);
-        L.idir++;
-        if (L.idir < S.ndir) { start_peel(S, L); return; }
+        const float cc = cos_clamp(S);
+        float cos_theta = clampf(dot3(L.kdir, r.dir), -cc, +cc);
+        const int ocell = OCT ? G.off[L.klevel] + L.kind_ : L.kind_;
+        const float *dsc = S.dsc;
+        if (S.with_msf) dsc += S.bins * msf_pick(S.abu, S.scav, S.ndust, S.opt[2 * (size_t)ocell + 1], ocell, rng.uniform());
+        float delta = L.photons * expf(-r.tau) * dsc[clampi((int)xmul(xmul((float)S.bins, xadd(1.0f, cos_theta)), 0.5f), 0, S.bins - 1)];
+        if (S.nside > 0) {
+            delta *= L.dscale;
+            const float theta = acosf(-r.dir.z), phi = atan2f(r.dir.y, r.dir.x);
+            const int ipix = ang2pix_ring(S.nside, phi, theta);
+            if (ipix >= 0) atomicAdd(&S.out[ipix], delta);
+            L.idir = 1;
+        } else {
+            vec3 p = { xsub(r.pos.x, S.centre.x), xsub(r.pos.y, S.centre.y), xsub(r.pos.z, S.centre.z) };
+            const vec3 ra = { S.ora[3 * L.idir], S.ora[3 * L.idir + 1], S.ora[3 * L.idir + 2] };
+            const vec3 de = { S.ode[3 * L.idir], S.ode[3 * L.idir + 1], S.ode[3 * L.idir + 2] };
+            int i = (int)xadd(xsub(xmul(0.5f, (float)S.npx), 0.00005f), xdiv(dot3(p, ra), S.map_dx));
+            int j = (int)xadd(xsub(xmul(0.5f, (float)S.npy), 0.00005f), xdiv(dot3(p, de), S.map_dx));
+            if (i >= 0 && j >= 0 && i < S.npx && j < S.npy) atomicAdd(&S.out[i + L.idir * S.npx * S.npy + j * S.npx], delta);
+            L.idir++;
+        }
+        if (L.idir < S.ndir) { start_peel<OCT>(S, L); return; }
         // all observers done: scatter and continue the random walk from the scattering point
         r.pos = L.kpos; r.level = L.klevel; r.ind = L.kind_; r.rho = L.krho; r.dir = L.kdir; r.tau = 0.0f;
-        scatter_direction(r.dir, S.csc, S.bins, rng);
+        const float *csc = S.csc;
+        if (S.with_msf) csc += S.bins * msf_pick(S.abu, S.scav, S.ndust, S.opt[2 * (size_t)ocell + 1], ocell, rng.uniform());
+        scatter_direction(r.dir, csc, S.bins, rng);
         L.free_path = -logf(rng.uniform());
         L.mode = (L.scat == 30) ? RAY_IDLE : RAY_MAIN;                     // MAX_SCATTERINGS, kernel_ASOC_sca.c:5
         return;
     }
-    if (L.mode == RAY_FFS) {                                                // kernel_ASOC_sca.c:888-910 / 1720-1750
+    if (L.mode == RAY_FFS) {                                                // kernel_ASOC_sca.c:888-910 / 1720-1750 / 268-290 / 1246-1266
         r.tau += ds * rho0 * ksca;
         if (r.ind >= 0) return;
         float tau = r.tau, W;
+        if (S.flavour >= 2 && tau < 1.0e-22f) { L.mode = RAY_IDLE; return; }    // SimRAM_HP / CL: next packet, no draw
         if (S.flavour == 0) { W = -expm1f(-tau); L.free_path = -logf(1.0f - W * rng.uniform()); }
         // 1-exp(-tau) in single precision is quantised to 6e-8 (the reference's SimRAM_PB does exactly this); the
         // correctly rounded exp keeps the quantisation identical to a host OpenCL/libm evaluation
@@ -114,18 +155,20 @@ __device__ __forceinline__ void advance(const ScaArgs &S, Lane &L, RNG &rng, Sca
         L.kdir = r.dir; L.klevel = level0; L.kind_ = ind0; L.krho = rho0;
         L.photons *= expf(-L.free_path * kabs / ksca);
         L.idir = 0; L.mode = RAY_PEEL;
-        start_peel(S, L);
+        start_peel<OCT>(S, L);
         return;
     }
     r.tau += dtau;
+    if (S.mirror && r.ind < 0) mirror_literal<OCT>(G, S.mirror, r.pos, r.dir, r.level, r.ind, r.rho);      // :280, 940, 1280, 1780
     if (r.ind < 0) L.mode = RAY_IDLE;
 }
 
+// one packet of a point source / the isotropic background / the Healpix sky (kernel_ASOC_sca.c:520-808, 104-220)
 template <class RNG, bool OCT>
 __device__ __forceinline__ void emit_packet(const ScaArgs &S, RNG &rng, int id, int III, Packet &pk) {
-    if (S.kind == 0) emit_ps<ScaArgs, RNG, OCT>(S, rng, III, pk);
-    else             emit_bg<ScaArgs, RNG, OCT>(S, rng, id, pk);
-    fix_direction(pk.dir);
+    if (S.kind == SRC_PS)      { emit_ps<ScaArgs, RNG, OCT>(S, rng, III, pk); fix_direction(pk.dir); }
+    else if (S.kind == SRC_BG) { emit_bg<ScaArgs, RNG, OCT>(S, rng, id, pk); fix_direction(pk.dir); }
+    else                       emit_hp_sca<ScaArgs, RNG, OCT>(S, rng, pk);
 }
 
 __device__ __forceinline__ void flush(const ScaArgs &S, const ScaCounters &c) {
@@ -143,15 +186,31 @@ __global__ void __launch_bounds__(128) sca_item_kernel(const __grid_constant__ S
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long id = t * S.world + S.rank;
     bool have = id < S.nunits;
-    if (S.kind == 1) have = have && id < 8LL * S.G.area;
+    if (S.kind == SRC_BG) have = have && id < 8LL * S.G.area;
+    if (S.kind == SRC_CL) have = have && id < S.G.cells;
     RngMwc rng;
     if (have) rng.seed(S.mwc, (unsigned long long)id);
     Lane L; L.mode = RAY_IDLE;
     Packet pk; pk.ind = -1; pk.level = 0; pk.rho = 0.0f;
-    int III = 0;
+    int III = 0, icell = (int)id - S.global, nray = 0;     // CL: icell advances by `global` per cell
+    float pwei = 1.0f;
     for (;;) {
         if (L.mode == RAY_IDLE && have) {
-            if (III < S.batch) {
+            if (S.kind == SRC_CL) {                          // kernel_ASOC_sca.c:1150-1230
+                while (III >= nray) {
+                    long long nc = (long long)icell + S.global;
+                    if (nc >= S.G.cells) { have = false; break; }
+                    icell = (int)nc; III = 0;
+                    nray = cl_rays(S, icell, pwei);
+                }
+                if (have) {
+                    III++;
+                    emit_cl(S, rng, icell, pwei, pk);
+                    fix_direction(pk.dir);
+                    cnt.packets++;
+                    begin_packet<RngMwc, OCT>(S, L, rng, pk);
+                }
+            } else if (III < S.batch) {
                 emit_packet<RngMwc, OCT>(S, rng, (int)id, III, pk);
                 III++; cnt.packets++;
                 begin_packet<RngMwc, OCT>(S, L, rng, pk);
@@ -166,7 +225,7 @@ __global__ void __launch_bounds__(128) sca_item_kernel(const __grid_constant__ S
     flush(S, cnt);
 }
 
-// persistent warps, one Philox stream per packet, idle lanes refilled from the work counter
+// persistent warps, one Philox stream per packet (CL: per cell and ray), idle lanes refilled from the work counter
 template <bool OCT, bool DBL>
 __global__ void __launch_bounds__(128) sca_stream_kernel(const __grid_constant__ ScaArgs S) {
     ScaCounters cnt = { 0, 0, 0, 0, 0 };
@@ -176,10 +235,12 @@ __global__ void __launch_bounds__(128) sca_stream_kernel(const __grid_constant__
     Lane L; L.mode = RAY_IDLE;
     Packet pk; pk.ind = -1; pk.level = 0; pk.rho = 0.0f;
     bool more = true;
+    int icell = 0, iray = 0, nray = 0;
+    float pwei = 1.0f;
     for (;;) {
         unsigned idle = __ballot_sync(FULL, L.mode == RAY_IDLE);
         if (idle == FULL || (__popc(idle) >= 8 && __any_sync(FULL, more))) {
-            bool need = L.mode == RAY_IDLE && more;
+            bool need = L.mode == RAY_IDLE && more && iray >= nray;
             unsigned nm = __ballot_sync(FULL, need);
             if (nm) {
                 int leader = __ffs(nm) - 1;
@@ -191,14 +252,25 @@ __global__ void __launch_bounds__(128) sca_stream_kernel(const __grid_constant__
                     if (u >= nlocal) more = false;
                     else {
                         unsigned long long q = (unsigned long long)u * S.world + S.rank;
-                        rng.seed(S.phx, q);
-                        emit_packet<RngPhilox, OCT>(S, rng, (int)(q / (unsigned)S.batch), (int)(q % (unsigned)S.batch), pk);
-                        cnt.packets++;
-                        begin_packet<RngPhilox, OCT>(S, L, rng, pk);
+                        if (S.kind == SRC_CL) { icell = (int)q; iray = 0; nray = cl_rays(S, icell, pwei); }
+                        else {
+                            rng.seed(S.phx, q);
+                            emit_packet<RngPhilox, OCT>(S, rng, (int)(q / (unsigned)S.batch), (int)(q % (unsigned)S.batch), pk);
+                            cnt.packets++;
+                            begin_packet<RngPhilox, OCT>(S, L, rng, pk);
+                        }
                     }
                 }
             }
-            if (!__any_sync(FULL, L.mode != RAY_IDLE || more)) break;
+            if (S.kind == SRC_CL && L.mode == RAY_IDLE && iray < nray) {
+                rng.seed(S.phx, (unsigned long long)(unsigned)icell | ((unsigned long long)(unsigned)iray << 32));
+                iray++;
+                emit_cl(S, rng, icell, pwei, pk);
+                fix_direction(pk.dir);
+                cnt.packets++;
+                begin_packet<RngPhilox, OCT>(S, L, rng, pk);
+            }
+            if (!__any_sync(FULL, L.mode != RAY_IDLE || more || iray < nray)) break;
         }
         if (L.mode != RAY_IDLE) {
             advance<RngPhilox, OCT, DBL>(S, L, rng, cnt);
@@ -240,13 +312,18 @@ __global__ void __launch_bounds__(256, 3) sca_walk_kernel(const __grid_constant_
     ScatterPoint k;
     int mode = RAY_IDLE, phase = WALK_LEAF, ax = 0, idir = 0, scat = 0, nstep = 0, nevent = 0;
     float photons = 0.0f, free_path = 0.0f, tau = 0.0f;
+    float dleft = 0.0f, dscale = 1.0f;            // Healpix observer: distance left on the peel-off ray, 1/d^2
     unsigned long long rid = 0;
     bool more = true;
+    int icell = 0, iray = 0, nray = 0;            // SimRAM_CL: cell of this lane and its rays
+    float pwei = 1.0f;
+    const float cclamp = cos_clamp(S);
     for (;;) {
         unsigned idle = __ballot_sync(FULL, mode == RAY_IDLE);
         if (idle == FULL || (__popc(idle) >= 8 && __any_sync(FULL, more))) {
-            bool need = mode == RAY_IDLE && more;
+            bool need = mode == RAY_IDLE && more && iray >= nray;
             unsigned nm = __ballot_sync(FULL, need);
+            bool got = false;
             if (nm) {
                 int leader = __ffs(nm) - 1;
                 unsigned long long base = 0;
@@ -257,27 +334,36 @@ __global__ void __launch_bounds__(256, 3) sca_walk_kernel(const __grid_constant_
                     if (u >= nlocal) more = false;
                     else {
                         rid = (unsigned long long)u * S.world + S.rank;
-                        RngPhilox rng; rng.seed(S.phx, rid);
-                        Packet pk; pk.ind = -1; pk.level = 0; pk.rho = 0.0f;
-                        emit_packet<RngPhilox, OCT>(S, rng, (int)(rid / (unsigned)S.batch), (int)(rid % (unsigned)S.batch), pk);
-                        cnt.packets++;
-                        photons = pk.photons; scat = 0; nstep = 0; nevent = 0; tau = 0.0f; phase = WALK_LEAF;
-                        if (pk.ind >= 0) {
-                            k.level = pk.level; k.ind = pk.ind; k.rho = pk.rho; k.dir = pk.dir;
-                            k.fx = pk.pos.x - floorf(pk.pos.x); k.fy = pk.pos.y - floorf(pk.pos.y); k.fz = pk.pos.z - floorf(pk.pos.z);
-                            int root = pk.ind;
-                            if (OCT) for (int l = pk.level; l > 0; l--) root = G.par[G.off[l] + root - G.nxyz];
-                            k.ix = root % G.nx; k.iy = (root / G.nx) % G.ny; k.iz = root / (G.nx * G.ny);
-                            k.gpos = pk.pos;
-                            if (OCT) root_position(G, k.gpos, pk.level, pk.ind);
-                            ray_from_point(w, k, k.dir);
-                            if (S.ffs > 0) mode = RAY_FFS;
-                            else { free_path = uniform_fast_log(rng.uniform()); mode = RAY_MAIN; }
-                        }
+                        if (S.kind == SRC_CL) { icell = (int)rid; iray = 0; nray = cl_rays(S, icell, pwei); }
+                        else got = true;
                     }
                 }
             }
-            if (!__any_sync(FULL, mode != RAY_IDLE || more)) break;
+            if (S.kind == SRC_CL && mode == RAY_IDLE && iray < nray) {
+                rid = (unsigned long long)(unsigned)icell | ((unsigned long long)(unsigned)iray << 32);
+                iray++; got = true;
+            }
+            if (got) {
+                RngPhilox rng; rng.seed(S.phx, rid);
+                Packet pk; pk.ind = -1; pk.level = 0; pk.rho = 0.0f;
+                if (S.kind == SRC_CL) { emit_cl(S, rng, icell, pwei, pk); fix_direction(pk.dir); }
+                else emit_packet<RngPhilox, OCT>(S, rng, (int)(rid / (unsigned)S.batch), (int)(rid % (unsigned)S.batch), pk);
+                cnt.packets++;
+                photons = pk.photons; scat = 0; nstep = 0; nevent = 0; tau = 0.0f; phase = WALK_LEAF;
+                if (pk.ind >= 0) {
+                    k.level = pk.level; k.ind = pk.ind; k.rho = pk.rho; k.dir = pk.dir;
+                    k.fx = pk.pos.x - floorf(pk.pos.x); k.fy = pk.pos.y - floorf(pk.pos.y); k.fz = pk.pos.z - floorf(pk.pos.z);
+                    int root = pk.ind;
+                    if (OCT) for (int l = pk.level; l > 0; l--) root = G.par[G.off[l] + root - G.nxyz];
+                    k.ix = root % G.nx; k.iy = (root / G.nx) % G.ny; k.iz = root / (G.nx * G.ny);
+                    k.gpos = pk.pos;
+                    if (OCT) root_position(G, k.gpos, pk.level, pk.ind);
+                    ray_from_point(w, k, k.dir);
+                    if (S.ffs > 0) mode = RAY_FFS;
+                    else { free_path = uniform_fast_log(rng.uniform()); mode = RAY_MAIN; }
+                }
+            }
+            if (!__any_sync(FULL, mode != RAY_IDLE || more || iray < nray)) break;
         }
         // ---- rays that have reached the surface, several lanes at a time (the block is long and rare per lane) ----
         const unsigned em = __ballot_sync(FULL, mode != RAY_IDLE && phase == WALK_END);
@@ -287,14 +373,27 @@ __global__ void __launch_bounds__(256, 3) sca_walk_kernel(const __grid_constant_
             if (mode == RAY_PEEL) {                                  // kernel_ASOC_sca.c:1010-1046 / 1849-1885
                 cnt.peels++;
                 const vec3 od = w.d;
-                float cos_theta = clampf(k.dir.x * od.x + k.dir.y * od.y + k.dir.z * od.z, -0.999f, +0.999f);
-                float delta = photons * __expf(-tau) * __ldg(S.dsc + clampi((int)(S.bins * (1.0f + cos_theta) * 0.5f), 0, S.bins - 1));
-                vec3 p = { k.gpos.x - S.centre.x, k.gpos.y - S.centre.y, k.gpos.z - S.centre.z };
-                const float *ra = S.ora + 3 * idir, *de = S.ode + 3 * idir;
-                int i = (int)((0.5f * S.npx - 0.00005f) + (p.x * ra[0] + p.y * ra[1] + p.z * ra[2]) / S.map_dx);
-                int j = (int)((0.5f * S.npy - 0.00005f) + (p.x * de[0] + p.y * de[1] + p.z * de[2]) / S.map_dx);
-                if (i >= 0 && j >= 0 && i < S.npx && j < S.npy) atomicAdd(&S.out[i + idir * S.npx * S.npy + j * S.npx], delta);
-                idir++;
+                float cos_theta = clampf(k.dir.x * od.x + k.dir.y * od.y + k.dir.z * od.z, -cclamp, +cclamp);
+                const int kcell = OCT ? G.off[k.level] + k.ind : k.ind;
+                // WITH_MSF: one Philox block per peel-off ray / scattering for the dust species draws
+                const float *dsc = S.dsc;
+                if (S.with_msf) {
+                    RngBlock rm(S.phx, rid, 0x20000u + (unsigned)(scat * 64 + idir));
+                    dsc += S.bins * msf_pick(S.abu, S.scav, S.ndust, __ldg(S.opt + 2 * (size_t)kcell + 1), kcell, rm.uniform());
+                }
+                float delta = photons * __expf(-tau) * __ldg(dsc + clampi((int)(S.bins * (1.0f + cos_theta) * 0.5f), 0, S.bins - 1));
+                if (S.nside > 0) {                                    // Healpix image seen from odir[0..2]
+                    const int ipix = ang2pix_ring(S.nside, atan2f(od.y, od.x), acosf(-od.z));
+                    if (ipix >= 0) atomicAdd(&S.out[ipix], delta * dscale);
+                    idir = S.ndir;
+                } else {
+                    vec3 p = { k.gpos.x - S.centre.x, k.gpos.y - S.centre.y, k.gpos.z - S.centre.z };
+                    const float *ra = S.ora + 3 * idir, *de = S.ode + 3 * idir;
+                    int i = (int)((0.5f * S.npx - 0.00005f) + (p.x * ra[0] + p.y * ra[1] + p.z * ra[2]) / S.map_dx);
+                    int j = (int)((0.5f * S.npy - 0.00005f) + (p.x * de[0] + p.y * de[1] + p.z * de[2]) / S.map_dx);
+                    if (i >= 0 && j >= 0 && i < S.npx && j < S.npy) atomicAdd(&S.out[i + idir * S.npx * S.npy + j * S.npx], delta);
+                    idir++;
+                }
                 tau = 0.0f;
                 if (idir < S.ndir) {
                     vec3 nd = { S.odir[3 * idir], S.odir[3 * idir + 1], S.odir[3 * idir + 2] };
@@ -302,23 +401,29 @@ __global__ void __launch_bounds__(256, 3) sca_walk_kernel(const __grid_constant_
                 } else if (scat == 30) mode = RAY_IDLE;               // MAX_SCATTERINGS, kernel_ASOC_sca.c:5
                 else {
                     RngBlock rb(S.phx, rid, 0x10000u + (unsigned)(nevent++));
-                    float ct = __ldg(S.csc + clampi((int)(rb.uniform() * S.bins), 0, S.bins - 1));
+                    const float u_ct = rb.uniform(), u_phi = rb.uniform(), u_fp = rb.uniform();
+                    const float *csc = S.csc;
+                    if (S.with_msf) csc += S.bins * msf_pick(S.abu, S.scav, S.ndust, __ldg(S.opt + 2 * (size_t)kcell + 1), kcell, rb.uniform());
+                    float ct = __ldg(csc + clampi((int)(u_ct * S.bins), 0, S.bins - 1));
                     vec3 nd = k.dir;
-                    scatter_rotate(nd, ct, SOC_TWOPI * rb.uniform());
-                    free_path = uniform_fast_log(rb.uniform());
+                    scatter_rotate(nd, ct, SOC_TWOPI * u_phi);
+                    free_path = uniform_fast_log(u_fp);
                     k.dir = nd;
                     ray_from_point(w, k, nd);
                     mode = RAY_MAIN;
                 }
             } else if (mode == RAY_FFS) {                            // kernel_ASOC_sca.c:888-910 / 1720-1750
-                RngBlock rb(S.phx, rid, 0x10000u + (unsigned)(nevent++));
-                float W;
-                if (S.flavour == 0) { W = -expm1f(-tau); free_path = -logf(1.0f - W * rb.uniform()); }
-                else                { W = 1.0f - (float)exp(-(double)tau); free_path = (float)(-log(1.0 - (double)(W * rb.uniform()))); }
-                photons *= W;
-                mode = (tau < 1.0e-22f) ? RAY_IDLE : RAY_MAIN;
-                tau = 0.0f;
-                ray_from_point(w, k, k.dir);
+                if (S.flavour >= 2 && tau < 1.0e-22f) mode = RAY_IDLE;         // SimRAM_HP / CL: nothing on the line of sight
+                else {
+                    RngBlock rb(S.phx, rid, 0x10000u + (unsigned)(nevent++));
+                    float W;
+                    if (S.flavour == 0) { W = -expm1f(-tau); free_path = -logf(1.0f - W * rb.uniform()); }
+                    else                { W = 1.0f - (float)exp(-(double)tau); free_path = (float)(-log(1.0 - (double)(W * rb.uniform()))); }
+                    photons *= W;
+                    mode = (tau < 1.0e-22f) ? RAY_IDLE : RAY_MAIN;
+                    tau = 0.0f;
+                    ray_from_point(w, k, k.dir);
+                }
             } else mode = RAY_IDLE;                                   // the packet itself has left the cloud
         }
         // ---- one cell of whichever ray the lane is tracing -----------------------------------------------------
@@ -332,7 +437,14 @@ __global__ void __launch_bounds__(256, 3) sca_walk_kernel(const __grid_constant_
             if (S.with_abu) { float2 o = __ldg(reinterpret_cast<const float2 *>(S.opt) + oind); kabs = o.x; ksca = o.y; }
             cnt.steps++; nstep++;
             bool go = true;
-            if (mode == RAY_PEEL) tau += ds * w.rho * (kabs + ksca);
+            if (mode == RAY_PEEL) {
+                if (S.nside > 0) {                                    // the ray ends at the observer
+                    ds = fminf(ds, dleft);
+                    dleft -= ds;
+                    if (dleft <= 0.0f) { go = false; phase = WALK_END; }
+                }
+                tau += ds * w.rho * (kabs + ksca);
+            }
             else if (mode == RAY_FFS) tau += ds * w.rho * ksca;
             else {
                 const float dtau = ds * w.rho * ksca;
@@ -346,7 +458,18 @@ __global__ void __launch_bounds__(256, 3) sca_walk_kernel(const __grid_constant_
                     photons *= __expf(-free_path * kabs / ksca);
                     scat++; cnt.scat++;
                     idir = 0; mode = RAY_PEEL; tau = 0.0f; nstep = 0;
-                    vec3 od = { S.odir[0], S.odir[1], S.odir[2] };
+                    vec3 od;
+                    if (S.nside > 0) {
+                        od.x = S.odir[0] - k.gpos.x; od.y = S.odir[1] - k.gpos.y; od.z = S.odir[2] - k.gpos.z;
+                        const float d2 = od.x * od.x + od.y * od.y + od.z * od.z;
+                        const float id_ = rsqrtf(fmaxf(d2, 1.0e-30f));
+                        dleft = d2 * id_; dscale = id_ * id_;
+                        od.x *= id_; od.y *= id_; od.z *= id_;
+                        // the walker needs non-zero direction components
+                        if (fabsf(od.x) < 1.0e-6f) od.x = 1.0e-6f;
+                        if (fabsf(od.y) < 1.0e-6f) od.y = 1.0e-6f;
+                        if (fabsf(od.z) < 1.0e-6f) od.z = 1.0e-6f;
+                    } else { od.x = S.odir[0]; od.y = S.odir[1]; od.z = S.odir[2]; }
                     ray_from_point(w, k, od);
                     go = false;
                 } else {
@@ -362,7 +485,11 @@ __global__ void __launch_bounds__(256, 3) sca_walk_kernel(const __grid_constant_
         for (int hop = 0; hop < (OCT ? S.nav_hops : 1); hop++) {
             if (mode != RAY_IDLE) {
                 if (OCT && phase == WALK_CLIMB) { nav_climb(G, w, ax); phase = WALK_CROSS; }
-                if (phase == WALK_CROSS) { phase = nav_cross(G, w, ax); if (w.ind < 0) phase = WALK_END; }
+                if (phase == WALK_CROSS) {
+                    // only the packet itself is reflected by a mirror border; look-ahead and peel-off rays leave
+                    phase = nav_cross(G, w, ax, mode == RAY_MAIN ? S.mirror : 0);
+                    if (w.ind < 0) phase = WALK_END;
+                }
                 if (OCT && phase == WALK_DESCEND) phase = nav_descend(G, w, ax);
             }
         }

@@ -107,73 +107,6 @@ __device__ __forceinline__ float sample_free_path(const SimArgs &A, RNG &rng, fl
     return fp;
 }
 
-// ---- emission: Healpix background (kernel_ASOC.c:885-947) ---------------------------------------------------
-template <class RNG, bool OCT>
-__device__ void emit_hp(const SimArgs &A, RNG &rng, Packet &pk) {
-    const GridDesc &G = A.G;
-    const float NX = (float)G.nx, NY = (float)G.ny, NZ = (float)G.nz;
-    int ipix;
-    if (A.hpbg_weighted < 1) {
-        ipix = clampi((int)floorf(rng.uniform() * 49152), 0, 49151);
-    } else {
-        float x = rng.uniform();
-        int lo = 0, hi = 49151;
-        for (int i = 0; i < 10; i++) {
-            ipix = (lo + hi) / 2;
-            if (A.hpbgp[ipix] > x) hi = ipix; else lo = ipix;
-        }
-        for (ipix = lo; ipix <= hi; ipix++) if (A.hpbgp[ipix] >= x) break;
-    }
-    pk.photons = A.hpbg[ipix];
-    float phi, theta, st, ct, sp, cp;
-    pix2ang_ring(64, ipix, phi, theta, SOC_PI);
-    sincosf(theta, &st, &ct); sincosf(phi, &sp, &cp);
-    pk.dir.x = st * cp; pk.dir.y = st * sp; pk.dir.z = -ct;
-    fix_direction(pk.dir);
-    float x = fabsf(pk.dir.x), y = fabsf(pk.dir.y), z = fabsf(pk.dir.z);
-    float ds = xadd(xadd(x, y), z);
-    x = xdiv(x, ds); y = xdiv(y, ds); z = xdiv(z, ds);
-    ds = rng.uniform();
-    float v1 = rng.uniform(), v2 = rng.uniform();
-    if (ds < x)                { pk.pos.y = v1 * NY; pk.pos.z = v2 * NZ; pk.pos.x = (pk.dir.x > 0.0f) ? SOC_PEPS : (NX - SOC_PEPS); }
-    else if (ds < xadd(x, y))  { pk.pos.x = v1 * NX; pk.pos.z = v2 * NZ; pk.pos.y = (pk.dir.y > 0.0f) ? SOC_PEPS : (NY - SOC_PEPS); }
-    else                       { pk.pos.x = v1 * NX; pk.pos.y = v2 * NY; pk.pos.z = (pk.dir.z > 0.0f) ? SOC_PEPS : (NZ - SOC_PEPS); }
-    locate<OCT>(G, pk);
-}
-
-// ---- emission: one ray from cell `icell` (kernel_ASOC.c:1323-1393) ------------------------------------------
-template <class RNG>
-__device__ void emit_cl(const SimArgs &A, RNG &rng, int icell, float pwei, Packet &pk) {
-    const GridDesc &G = A.G;
-    int ind = icell, level;
-    for (level = 0; level < G.levels - 1; level++) {
-        ind -= G.lcells[level];
-        if (ind < 0) { ind += G.lcells[level]; break; }
-    }
-    float X0, Y0, Z0;
-    if (level == 0) { X0 = ind % G.nx; Y0 = (ind / G.nx) % G.ny; Z0 = ind / (G.nx * G.ny); }
-    else { int sid = ind & 7; X0 = sid & 1; Y0 = (sid >> 1) & 1; Z0 = sid >> 2; }
-    pk.photons = A.emit[icell] * pwei;
-    pk.pos.x = xadd(X0, rng.uniform()); pk.pos.y = xadd(Y0, rng.uniform()); pk.pos.z = xadd(Z0, rng.uniform());
-    isotropic(rng, pk.dir);
-    pk.level = level; pk.ind = ind; pk.rho = G.dens[icell];
-    pk.eidx = A.with_ali ? icell : -1;
-}
-
-// Packets-per-cell rule of SimRAM_CL (kernel_ASOC.c:1293-1316).  Returns the number of rays (0 = skip the cell).
-__device__ __forceinline__ int cl_rays(const SimArgs &A, int icell, float &pwei) {
-    if (A.use_emweight > 0) {
-        pwei = A.emwei[icell];
-        if (pwei < 1e-10f || A.G.dens[icell] <= 0.0f) return 0;
-        int batch = (int)floorf(pwei);
-        if (batch < 1) { batch = 1; pwei = (float)(1.0 / (double)(pwei + 1.0e-30f)); }
-        else           { pwei = (float)(1.0 / (double)((float)batch + 1.0e-9f)); }
-        return batch;
-    }
-    pwei = 1.0f / ((float)A.batch + 1.0e-9f);
-    return A.batch;
-}
-
 template <class RNG>
 __device__ __forceinline__ void start_packet(const SimArgs &A, RNG &rng, Packet &pk, bool fixdir) {
     if (fixdir) fix_direction(pk.dir);
@@ -222,7 +155,10 @@ __device__ __forceinline__ bool finish_step(const SimArgs &A, Packet &pk, const 
         pk.pos.x = xadd(t.pos0.x, xmul(dx, pk.dir.x)); pk.pos.y = xadd(t.pos0.y, xmul(dx, pk.dir.y)); pk.pos.z = xadd(t.pos0.z, xmul(dx, pk.dir.z));
         pk.free_path = sample_free_path(A, rng, pk.photons);
         pk.ind = t.ind0; pk.level = t.level0; pk.rho = t.rho0;
-        scatter_direction(pk.dir, A.csc, A.bins, rng);
+        const float *csc = A.csc;
+        if (A.with_msf)                                                // kernel_ASOC.c:777-794
+            csc += A.bins * msf_pick(A.abu, A.scav, A.ndust, A.opt[2 * (size_t)t.oind + 1], t.oind, rng.uniform());
+        scatter_direction(pk.dir, csc, A.bins, rng);
         pk.tau = 0.0f;
         if (!CL && pk.scat > 20) return false;                     // kernel_ASOC.c:801-804
         return true;
@@ -230,6 +166,7 @@ __device__ __forceinline__ bool finish_step(const SimArgs &A, Packet &pk, const 
     if (!CL && pk.level == t.level0 && pk.ind == t.ind0) {         // failed step: kernel_ASOC.c:649-665
         pk.pos.x = xadd(pk.pos.x, xmul(SOC_PEPS, pk.dir.x)); pk.pos.y = xadd(pk.pos.y, xmul(SOC_PEPS, pk.dir.y)); pk.pos.z = xadd(pk.pos.z, xmul(SOC_PEPS, pk.dir.z));
     }
+    if (A.mirror && pk.ind < 0) mirror_literal<OCT>(A.G, A.mirror, pk.pos, pk.dir, pk.level, pk.ind, pk.rho);   // :686, 1064, 1540
     return pk.ind >= 0;
 }
 
@@ -300,7 +237,7 @@ __global__ void __launch_bounds__(128) sim_item_kernel(const __grid_constant__ S
             } else if (III < A.batch) {
                 if (A.kind == SIM_PS)      emit_ps<SimArgs, RNG, OCT>(A, rng, III, pk);
                 else if (A.kind == SIM_BG) emit_bg<SimArgs, RNG, OCT>(A, rng, (int)id, pk);
-                else                       emit_hp<RNG, OCT>(A, rng, pk);
+                else                       emit_hp<SimArgs, RNG, OCT>(A, rng, pk);
                 start_packet(A, rng, pk, A.kind != SIM_HP);
                 III++; cnt.packets++;
                 alive = pk.ind >= 0;
@@ -367,7 +304,7 @@ __global__ void __launch_bounds__(256) sim_stream_kernel(const __grid_constant__
                             int id = (int)(q / (unsigned)A.batch), III = (int)(q % (unsigned)A.batch);
                             if (A.kind == SIM_PS)      emit_ps<SimArgs, RngPhilox, OCT>(A, rng, III, pk);
                             else if (A.kind == SIM_BG) emit_bg<SimArgs, RngPhilox, OCT>(A, rng, id, pk);
-                            else                       emit_hp<RngPhilox, OCT>(A, rng, pk);
+                            else                       emit_hp<SimArgs, RngPhilox, OCT>(A, rng, pk);
                             start_packet(A, rng, pk, A.kind != SIM_HP);
                             cnt.packets++;
                             alive = pk.ind >= 0;
@@ -505,7 +442,7 @@ __global__ void __launch_bounds__(256, 4) sim_fast_kernel(const __grid_constant_
                     int id = (int)(q / (unsigned)A.batch), III = (int)(q % (unsigned)A.batch);
                     if (A.kind == SIM_PS)      emit_ps<SimArgs, RngPhilox, false>(A, rng, III, pk);
                     else if (A.kind == SIM_BG) emit_bg<SimArgs, RngPhilox, false>(A, rng, id, pk);
-                    else                       emit_hp<RngPhilox, false>(A, rng, pk);
+                    else                       emit_hp<SimArgs, RngPhilox, false>(A, rng, pk);
                 }
                 start_packet(A, rng, pk, A.kind != SIM_HP);
                 cnt.packets++;
@@ -532,8 +469,11 @@ __global__ void __launch_bounds__(256, 4) sim_fast_kernel(const __grid_constant_
                     float fz = (f.dir.z > 0.0f) ? 1.0f - f.tz * fabsf(f.dir.z) : f.tz * fabsf(f.dir.z);
                     RngBlock rb(A.phx, f.rid, 0x10000u + (unsigned)f.scat);
                     f.free_path = free_path_fast(A, rb, f.photons);
-                    float ct = __ldg(A.csc + clampi((int)(rb.uniform() * A.bins), 0, A.bins - 1));
-                    scatter_rotate(f.dir, ct, SOC_TWOPI * rb.uniform());
+                    const float u_ct = rb.uniform(), u_phi = rb.uniform();
+                    const float *csc = A.csc;
+                    if (GENERAL && A.with_msf) csc += A.bins * msf_pick(A.abu, A.scav, A.ndust, f.opt.y, f.ind, rb.uniform());
+                    float ct = __ldg(csc + clampi((int)(u_ct * A.bins), 0, A.bins - 1));
+                    scatter_rotate(f.dir, ct, SOC_TWOPI * u_phi);
                     f.rdx = __fdividef(1.0f, fabsf(f.dir.x)); f.rdy = __fdividef(1.0f, fabsf(f.dir.y)); f.rdz = __fdividef(1.0f, fabsf(f.dir.z));
                     f.tx = face_distance(fx, f.dir.x, f.rdx);
                     f.ty = face_distance(fy, f.dir.y, f.rdy);
@@ -615,12 +555,20 @@ __global__ void __launch_bounds__(256, 4) sim_fast_kernel(const __grid_constant_
                 wsc = true;
                 if (!cl && f.scat > 20) { alive = false; wsc = false; }
             } else {
-                if (ax == 0)      { f.ix += (f.dir.x > 0.0f) ? 1 : -1; f.tx = f.rdx; }
-                else if (ax == 1) { f.iy += (f.dir.y > 0.0f) ? 1 : -1; f.ty = f.rdy; }
-                else              { f.iz += (f.dir.z > 0.0f) ? 1 : -1; f.tz = f.rdz; }
-                f.ind = nind; f.rho = rho_n;
-                if (abu) f.opt = opt_n;
-                alive = inb;
+                const float da = (ax == 0) ? f.dir.x : ((ax == 1) ? f.dir.y : f.dir.z);
+                if (!inb && (A.mirror & ((da > 0.0f ? 2 : 1) << (2 * ax)))) {
+                    // reflecting border: same cell, the crossed component of the direction changes sign
+                    if (ax == 0)      { f.dir.x = -f.dir.x; f.tx = f.rdx; }
+                    else if (ax == 1) { f.dir.y = -f.dir.y; f.ty = f.rdy; }
+                    else              { f.dir.z = -f.dir.z; f.tz = f.rdz; }
+                } else {
+                    if (ax == 0)      { f.ix += (f.dir.x > 0.0f) ? 1 : -1; f.tx = f.rdx; }
+                    else if (ax == 1) { f.iy += (f.dir.y > 0.0f) ? 1 : -1; f.ty = f.rdy; }
+                    else              { f.iz += (f.dir.z > 0.0f) ? 1 : -1; f.tz = f.rdz; }
+                    f.ind = nind; f.rho = rho_n;
+                    if (abu) f.opt = opt_n;
+                    alive = inb;
+                }
             }
             if (f.nstep > A.max_steps) { alive = false; wsc = false; cnt.stuck++; }
         }
@@ -716,7 +664,7 @@ __global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant_
                     const int id = (int)(q / (unsigned)A.batch), III = (int)(q % (unsigned)A.batch);
                     if (A.kind == SIM_PS)      emit_ps<SimArgs, RngPhilox, false>(A, rng, III, pk);
                     else if (A.kind == SIM_BG) emit_bg<SimArgs, RngPhilox, false>(A, rng, id, pk);
-                    else                       emit_hp<RngPhilox, false>(A, rng, pk);
+                    else                       emit_hp<SimArgs, RngPhilox, false>(A, rng, pk);
                     start_packet(A, rng, pk, A.kind != SIM_HP);
                     if (pk.ind >= 0) {
                         alive = true; wsc = false;
@@ -843,11 +791,20 @@ __global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant_
                 wsc = true;
                 if (LEAN_SCAT(f.sn) > 20u) { alive = false; wsc = false; }
             } else {
-                if (px)      { f.cx--; f.tx = f.rdx; }
-                else if (py) { f.cy--; f.ty = f.rdy; }
-                else         { f.cz--; f.tz = f.rdz; }
-                f.ind = nind; f.rho = rho_n;
-                alive = inb;
+                const int abit_ = px ? 1 : (py ? 2 : 4);
+                if (!inb && (A.mirror & (px ? 3 : (py ? 12 : 48)) & ((f.upm & abit_) ? 42 : 21))) {
+                    // reflecting border: same cell, the packet turns around on this axis
+                    f.upm ^= abit_;
+                    if (px)      { f.cx = G.nx - 1; f.tx = f.rdx; }
+                    else if (py) { f.cy = G.ny - 1; f.ty = f.rdy; }
+                    else         { f.cz = G.nz - 1; f.tz = f.rdz; }
+                } else {
+                    if (px)      { f.cx--; f.tx = f.rdx; }
+                    else if (py) { f.cy--; f.ty = f.rdy; }
+                    else         { f.cz--; f.tz = f.rdz; }
+                    f.ind = nind; f.rho = rho_n;
+                    alive = inb;
+                }
             }
             bool stuck = false;
             if (LEAN_STEPS(f.sn) > (unsigned)A.max_steps) { alive = false; wsc = false; stuck = true; }
@@ -932,7 +889,7 @@ __global__ void __launch_bounds__(256, 4) sim_walk_kernel(const __grid_constant_
                     int id = (int)(q / (unsigned)A.batch), III = (int)(q % (unsigned)A.batch);
                     if (A.kind == SIM_PS)      emit_ps<SimArgs, RngPhilox, true>(A, rng, III, pk);
                     else if (A.kind == SIM_BG) emit_bg<SimArgs, RngPhilox, true>(A, rng, id, pk);
-                    else                       emit_hp<RngPhilox, true>(A, rng, pk);
+                    else                       emit_hp<SimArgs, RngPhilox, true>(A, rng, pk);
                 }
                 start_packet(A, rng, pk, A.kind != SIM_HP);
                 cnt.packets++;
@@ -954,9 +911,15 @@ __global__ void __launch_bounds__(256, 4) sim_walk_kernel(const __grid_constant_
                     walker_fraction(w, fx, fy, fz);
                     RngBlock rb(A.phx, rid, 0x10000u + (unsigned)scat);
                     free_path = free_path_fast(A, rb, photons);
-                    float ct = __ldg(A.csc + clampi((int)(rb.uniform() * A.bins), 0, A.bins - 1));
+                    const float u_ct = rb.uniform(), u_phi = rb.uniform();
+                    const float *csc = A.csc;
+                    if (GENERAL && A.with_msf) {
+                        const int oc = G.off[w.level] + w.ind;
+                        csc += A.bins * msf_pick(A.abu, A.scav, A.ndust, __ldg(A.opt + 2 * (size_t)oc + 1), oc, rb.uniform());
+                    }
+                    float ct = __ldg(csc + clampi((int)(u_ct * A.bins), 0, A.bins - 1));
                     vec3 nd = w.d;
-                    scatter_rotate(nd, ct, SOC_TWOPI * rb.uniform());
+                    scatter_rotate(nd, ct, SOC_TWOPI * u_phi);
                     walker_set_direction(w, nd, fx, fy, fz);
                     tau = 0.0f;
                     phase = WALK_LEAF;
@@ -1027,7 +990,7 @@ __global__ void __launch_bounds__(256, 4) sim_walk_kernel(const __grid_constant_
         #pragma unroll 1
         for (int hop = 0; hop < A.nav_hops; hop++) {
             if (alive && phase == WALK_CLIMB) { nav_climb(G, w, ax); phase = WALK_CROSS; }
-            if (alive && phase == WALK_CROSS) { phase = nav_cross(G, w, ax); if (w.ind < 0) alive = false; }
+            if (alive && phase == WALK_CROSS) { phase = nav_cross(G, w, ax, A.mirror); if (w.ind < 0) alive = false; }
             if (alive && phase == WALK_DESCEND) phase = nav_descend(G, w, ax);
         }
         if (was_alive && !alive) { cnt.steps += nstep; cnt.scat += min(scat, 20); }
@@ -1092,7 +1055,7 @@ static void launch_lean(SimArgs A, int dep, int blocks, int threads, cudaStream_
     else                      sim_lean_kernel<DEP_TILE, BRICK, PEND><<<blocks, threads, 0, stream>>>(A);
 }
 
-static bool sim_is_general(const SimArgs &A) { return A.with_abu || A.save_int2 || A.with_ali || A.kind == SIM_CL; }
+static bool sim_is_general(const SimArgs &A) { return A.with_msf || A.with_abu || A.save_int2 || A.with_ali || A.kind == SIM_CL; }
 
 // the lean kernel keeps the work unit in 32 bits and the step count of a packet in 24
 static bool sim_uses_lean(const SimArgs &A) { return !sim_is_general(A) && A.nlocal < (1LL << 32) && A.max_steps < (1 << 24) - 2; }

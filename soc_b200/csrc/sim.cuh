@@ -35,6 +35,8 @@ struct SimArgs {
     const float *__restrict__ pspos, *__restrict__ ps, *__restrict__ xps_area;
     const int *__restrict__ xps_nside, *__restrict__ xps_side;
     const float *__restrict__ hpbg, *__restrict__ hpbgp;
+    const float *__restrict__ abu, *__restrict__ scav;   // WITH_MSF: ABU[cells*ndust], SCA[ndust]
+    int with_msf, ndust, mirror;
     float kabs, ksca, bg, tw, adhoc, sw_a, sw_b;
     int kind, batch, global;
     int bins, no_ps, ps_method, with_abu, with_ali, use_int, save_int2, use_emweight, hpbg_weighted, step_weight;

@@ -144,7 +144,10 @@ __device__ __forceinline__ void nav_climb(const GridDesc &G, Walker &w, const in
 // try to cross the face of axis `ax` at the current level.  Returns the new phase: LEAF / DESCEND when the
 // neighbour was found (its value is loaded into w.rho), CLIMB when the octet has to be left first; w.ind < 0
 // when the ray leaves the cloud.
-__device__ __forceinline__ int nav_cross(const GridDesc &G, Walker &w, const int ax) {
+// `mirror`: MIRROR bit mask (1 x=0, 2 x=NX, 4 y=0, 8 y=NY, 16 z=0, 32 z=NZ): at a reflecting border the ray stays in the
+// root cell it has climbed to, the crossed direction component changes sign and the walk descends again towards the
+// leaf at the border (the descent enters "through the near face" of the crossed axis, which now is the border).
+__device__ __forceinline__ int nav_cross(const GridDesc &G, Walker &w, const int ax, const int mirror = 0) {
     const int abit = 1 << ax;
     const bool up = (w.up & abit) != 0;
     const float rda = (ax == 0) ? w.rdx : ((ax == 1) ? w.rdy : w.rdz);
@@ -153,9 +156,15 @@ __device__ __forceinline__ int nav_cross(const GridDesc &G, Walker &w, const int
         const int sgn = up ? 1 : -1;
         const int c = ((ax == 0) ? w.ix : ((ax == 1) ? w.iy : w.iz)) + sgn;
         const int lim = (ax == 0) ? G.nx : ((ax == 1) ? G.ny : G.nz);
-        if ((unsigned)c >= (unsigned)lim) { w.ind = -1; return WALK_LEAF; }
-        w.ix += (ax == 0) ? sgn : 0; w.iy += (ax == 1) ? sgn : 0; w.iz += (ax == 2) ? sgn : 0;
-        w.ind = (w.iz * G.ny + w.iy) * G.nx + w.ix;
+        if ((unsigned)c >= (unsigned)lim) {
+            if (mirror & ((up ? 2 : 1) << (2 * ax))) {
+                w.up ^= abit;
+                if (ax == 0) w.d.x = -w.d.x; else if (ax == 1) w.d.y = -w.d.y; else w.d.z = -w.d.z;
+            } else { w.ind = -1; return WALK_LEAF; }
+        } else {
+            w.ix += (ax == 0) ? sgn : 0; w.iy += (ax == 1) ? sgn : 0; w.iz += (ax == 2) ? sgn : 0;
+            w.ind = (w.iz * G.ny + w.iy) * G.nx + w.ix;
+        }
         ta = rda;
     } else {
         if ((((w.ind ^ w.up) & 7) & abit) == 0) return WALK_CLIMB;

@@ -22,6 +22,10 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 MC_CASES = sorted(k for k in CASES if not k.startswith(("map_", "hpmap_")))
 MAP_CASES = sorted(k for k in CASES if k.startswith(("map_", "hpmap_")))
+# The shipped scattered-light SimRAM_HP / SimRAM_CL run their `#ifdef HG_TEST` branch (analytic g=0.65 phase function,
+# 1-exp(-tau)); the library implements the intended #else branch.  The oracle restates both (flag hg_test, the shipped
+# one pinned against the reference kernels); the goldens of these cases hold the shipped variant.
+SHIPPED_HG_TEST = tuple(k for k in CASES if k.startswith(("sca_hp", "sca_cl")))
 
 
 def _backend(cloud, rng_mode, **opts):
@@ -67,6 +71,8 @@ def test_reference_streams_match_oracle(name):
 def test_reference_streams_match_golden(name):
     """Same comparison against the vectors produced by the reference's own kernels (tests/golden)."""
     from soc_b200 import backend
+    if name in SHIPPED_HG_TEST:
+        pytest.skip("golden holds the reference's HG_TEST branch; the intended branch is checked against the oracle")
     make, opts, run = CASES[name]
     gold = np.load(os.path.join(GOLD, name + ".npz"))
     B = _backend(make(), backend.RNG_REFERENCE, **opts)
