@@ -27,7 +27,7 @@ class OrcParams(C.Structure):
         "nx", "ny", "nz", "levels", "cells", "bins", "no_ps", "ps_method", "with_abu", "with_ali", "noabsorbed",
         "save_intensity", "use_emweight", "hpbg_weighted", "ffs", "step_weight", "level_threshold", "sca_exact_level")] + \
         [(n, C.c_float) for n in ("sw_a", "sw_b", "length", "factor", "adhoc", "reserved1")] + \
-        [(n, C.c_int32) for n in ("with_msf", "ndust", "mirror", "map_interpolation", "hg_test", "r2a", "r2b", "r2c")]
+        [(n, C.c_int32) for n in ("with_msf", "ndust", "mirror", "map_interpolation", "hg_test", "mirror_exact", "r2b", "r2c")]
 
 
 class OrcGrid(C.Structure):
@@ -100,6 +100,7 @@ class Oracle:
         P.with_msf, P.ndust, P.mirror = opts.get("with_msf", 0), opts.get("ndust", 1), opts.get("mirror", 0)
         P.map_interpolation = opts.get("map_interpolation", 0)
         P.hg_test = opts.get("hg_test", 0)
+        P.mirror_exact = opts.get("mirror_exact", 0)
         P.length = float("%.5e" % (gl * 3.08567758e+18))     # -D LENGTH=%.5ef (ASOC.py:347,356)
         P.factor = 1.0e20
         P.adhoc = 1.0

@@ -221,7 +221,17 @@ static void surface(const nav_t *N, v3 *p, const v3 *d) {
 /* Mirror(): kernel_ASOC_aux.c:1054-1083, restated literally: `if (c) a ; b ;` -- the direction component of every
  * enabled border is negated whether or not that border was crossed (a second enabled border of the same axis undoes
  * the reflection). */
-static void mirror(const nav_t *N, int mask, v3 *p, v3 *d, int *level, int *ind) {
+static void mirror(const nav_t *N, int mask, int exact, v3 *p, v3 *d, int *level, int *ind) {
+    if (exact) {          /* geometrically intended behaviour: reflect at the border that was crossed, nothing else */
+        if ((mask & 1)  && p->x < 0.0f)  { p->x = S_EPS;         d->x = -d->x; }
+        if ((mask & 2)  && p->x > N->nx) { p->x = N->nx - S_EPS; d->x = -d->x; }
+        if ((mask & 4)  && p->y < 0.0f)  { p->y = S_EPS;         d->y = -d->y; }
+        if ((mask & 8)  && p->y > N->ny) { p->y = N->ny - S_EPS; d->y = -d->y; }
+        if ((mask & 16) && p->z < 0.0f)  { p->z = S_EPS;         d->z = -d->z; }
+        if ((mask & 32) && p->z > N->nz) { p->z = N->nz - S_EPS; d->z = -d->z; }
+        index_g(N, p, level, ind);
+        return;
+    }
     if (mask & 1)  { if (p->x < 0.0f)  p->x = S_EPS;          d->x = -d->x; index_g(N, p, level, ind); }
     if (mask & 2)  { if (p->x > N->nx) p->x = N->nx - S_EPS;  d->x = -d->x; index_g(N, p, level, ind); }
     if (mask & 4)  { if (p->y < 0.0f)  p->y = S_EPS;          d->y = -d->y; index_g(N, p, level, ind); }
@@ -397,7 +407,7 @@ static void propagate(sim_t *S, rng_t *r, v3 pos, v3 dir, int level, int ind, fl
             if (kind == 0 && level == level0 && ind == ind0) {             /* kernel_ASOC.c:649-665 */
                 pos.x += S_PEPS * dir.x; pos.y += S_PEPS * dir.y; pos.z += S_PEPS * dir.z;
             }
-            if (S->P->mirror > 0 && ind < 0) mirror(N, S->P->mirror, &pos, &dir, &level, &ind);   /* :686-688, 1540-1542 */
+            if (S->P->mirror > 0 && ind < 0) mirror(N, S->P->mirror, S->P->mirror_exact, &pos, &dir, &level, &ind);   /* :686-688, 1540-1542 */
         }
         if (ind < 0) break;
         scatterings++;
@@ -954,7 +964,7 @@ static void sca_propagate(sca_t *S, rng_t *r, v3 pos, v3 dir, int level, int ind
             S->c.steps++;
             if (free_path < (tau + dtau)) { ind = ind0; break; }
             tau += dtau;
-            if (P->mirror > 0 && ind < 0) mirror(N, P->mirror, &pos, &dir, &level, &ind);   /* kernel_ASOC_sca.c:280, 940, 1280, 1780 */
+            if (P->mirror > 0 && ind < 0) mirror(N, P->mirror, P->mirror_exact, &pos, &dir, &level, &ind);   /* kernel_ASOC_sca.c:280, 940, 1280, 1780 */
         }
         if (ind < 0) break;
         scatterings++; S->c.scatterings++;

@@ -109,7 +109,7 @@ __device__ __forceinline__ void advance(const ScaArgs &S, Lane &L, RNG &rng, Sca
             delta *= L.dscale;
             const float theta = acosf(-r.dir.z), phi = atan2f(r.dir.y, r.dir.x);
             const int ipix = ang2pix_ring(S.nside, phi, theta);
-            if (ipix >= 0) atomicAdd(&S.out[ipix], delta);
+            if ((unsigned)ipix < 12u * S.nside * S.nside) atomicAdd(&S.out[ipix], delta);
             L.idir = 1;
         } else {
             vec3 p = { xsub(r.pos.x, S.centre.x), xsub(r.pos.y, S.centre.y), xsub(r.pos.z, S.centre.z) };
@@ -383,8 +383,8 @@ __global__ void __launch_bounds__(256, 3) sca_walk_kernel(const __grid_constant_
                 }
                 float delta = photons * __expf(-tau) * __ldg(dsc + clampi((int)(S.bins * (1.0f + cos_theta) * 0.5f), 0, S.bins - 1));
                 if (S.nside > 0) {                                    // Healpix image seen from odir[0..2]
-                    const int ipix = ang2pix_ring(S.nside, atan2f(od.y, od.x), acosf(-od.z));
-                    if (ipix >= 0) atomicAdd(&S.out[ipix], delta * dscale);
+                    const int ipix = ang2pix_ring(S.nside, atan2f(od.y, od.x), acosf(clampf(-od.z, -1.0f, 1.0f)));
+                    if ((unsigned)ipix < 12u * S.nside * S.nside) atomicAdd(&S.out[ipix], delta * dscale);
                     idir = S.ndir;
                 } else {
                     vec3 p = { k.gpos.x - S.centre.x, k.gpos.y - S.centre.y, k.gpos.z - S.centre.z };

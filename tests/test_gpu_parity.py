@@ -13,7 +13,7 @@ import os
 import numpy as np
 import pytest
 
-from tests.cases import CASES, run_bg, run_ps, run_abu, run_hp, run_cl, run_sca, _reg, _oct
+from tests.cases import CASES, run_bg, run_ps, run_abu, run_hp, run_cl, run_sca, run_bg_msf, _reg, _oct
 from tests.stats import chi2_per_dof
 from soc_b200 import synth
 
@@ -131,6 +131,13 @@ STAT_CASES = {
     "hp_reg12_w": (_reg(12), dict(hpbg_weighted=1), lambda s: run_hp(True, batch=24, seed=s), "tabs"),
     "cl_reg10": (_reg(10), {}, lambda s: run_cl(False, batch=6, seed=s), "tabs"),
     "cl_oct6_ew_ali": (_oct(6, 3), dict(use_emweight=1, with_ali=1), lambda s: run_cl(True, batch=2, seed=s), "tabs"),
+    # several scattering functions (WITH_MSF), reflecting borders (MIRROR; the expectation is the oracle's
+    # mirror_exact variant: the production kernels reflect only the border that was crossed)
+    "bg_reg12_msf": (_reg(12), dict(with_abu=1, with_msf=1, ndust=2), lambda s: run_bg_msf(batch=8, seed=s), "tabs"),
+    "bg_oct6_msf": (_oct(6, 3), dict(with_abu=1, with_msf=1, ndust=2), lambda s: run_bg_msf(batch=16, seed=s), "tabs"),
+    "bg_box_mirror": (lambda: synth.box_cloud(20, 12, 8), dict(mirror=1 + 8 + 32), lambda s: run_bg(batch=6, seed=s), "tabs"),
+    "bg_reg12_mirror_abu": (_reg(12), dict(with_abu=1, mirror=2 + 4), lambda s: run_abu(batch=8, seed=s), "tabs"),
+    "bg_oct6_mirror": (_oct(6, 3), dict(mirror=32 + 1), lambda s: run_bg(batch=16, seed=s), "tabs"),
 }
 
 
@@ -143,7 +150,7 @@ def test_packet_streams_statistical_parity(name):
     make, opts, fac, key = STAT_CASES[name]
     cloud = make()
     K = 16
-    O = orc.Oracle(cloud, **opts)
+    O = orc.Oracle(cloud, mirror_exact=1, **opts)
     a = _repeat(O, fac, K, key)
     B = _backend(cloud, backend.RNG_PACKET, **opts)
     if name.endswith("_refgeo"):
@@ -161,6 +168,14 @@ SCA_STAT_CASES = {
     "sca_ps_oct8_noffs": (_oct(8, 3), dict(no_ps=1, ffs=0), lambda s: run_sca("ps", pspos=[(4.3, 4.2, 3.9)], batch=96, glob=2048, seed=s)),
     "sca_bg_reg12": (_reg(12), {}, lambda s: run_sca("bg", batch=24, seed=s)),
     "sca_bg_oct6": (_oct(6, 3), {}, lambda s: run_sca("bg", batch=48, dirs=((45.0, 45.0),), seed=s)),
+    "sca_hp_reg12": (_reg(12), {}, lambda s: run_sca("hp", batch=64, glob=1024, seed=s)),
+    "sca_hp_oct6_w": (_oct(6, 3), dict(hpbg_weighted=1, ffs=0), lambda s: run_sca("hp", batch=128, glob=1024, dirs=((120.0, 200.0),), seed=s)),
+    "sca_cl_reg10": (_reg(10), {}, lambda s: run_sca("cl", batch=24, glob=256, seed=s)),
+    "sca_cl_oct6_ew": (_oct(6, 3), dict(use_emweight=1), lambda s: run_sca("cl", batch=1, glob=256, emweight=True, dirs=((35.0, 110.0),), seed=s)),
+    "sca_ps_reg12_hpobs": (_reg(12), dict(no_ps=1), lambda s: run_sca("ps", pspos=[(6.3, 6.2, 5.9)], batch=64, glob=2048, hp_observer=(14.5, 7.31, 6.63), seed=s)),     # observer outside: 1/d^2 stays bounded
+    "sca_bg_oct6_hpobs": (_oct(6, 3), {}, lambda s: run_sca("bg", batch=48, hp_observer=(7.5, 2.03, 3.47), nside=8, seed=s)),
+    "sca_bg_reg12_msf": (_reg(12), dict(with_abu=1, with_msf=1, ndust=2), lambda s: run_sca("bg", batch=24, msf=True, seed=s)),
+    "sca_bg_reg12_mirror": (_reg(12), dict(mirror=1 + 8), lambda s: run_sca("bg", batch=24, seed=s)),
 }
 
 
@@ -176,11 +191,18 @@ def test_scattered_light_statistical_parity(name):
     # On octrees the reference displaces the scattering point with the level of the *next* cell
     # (kernel_ASOC_sca.c:958); the production kernel is geometrically exact, so the expectation is the oracle's
     # exact-level variant (the reference-faithful variant is what the REFSTREAMS/REFGEOMETRY kernels are tested on).
-    a = _repeat(orc.Oracle(cloud, sca_exact_level=1, **opts), fac, K, "out").reshape(K, -1)
+    a = _repeat(orc.Oracle(cloud, sca_exact_level=1, mirror_exact=1, **opts), fac, K, "out").reshape(K, -1)
     B = _backend(cloud, backend.RNG_PACKET, **opts)
     b = _repeat(B, fac, K, "out").reshape(K, -1)
+    assert np.isfinite(b).all()
+    # Healpix observer: a peel-off direction with an exactly zero component (scattering point level with the observer
+    # to the last float bit, ~1 in 1e7 scatterings) makes the reference's GetStep divide by zero and the pixel inf
+    # (kernel_ASOC_aux.c:289-296); the oracle restates that, the library clamps the component.  Drop such runs.
+    good = np.isfinite(a).all(1)
+    assert good.sum() >= K - 6
+    a, b = a[good], b[good]
     chi2, dof, tot, tot_sigma = chi2_per_dof(b, a, min_rel=0.02)
-    assert dof > 60
+    assert dof > (12 if name.endswith("hpobs") else 60)       # a Healpix observer sees the cloud in few bright pixels
     assert chi2 <= 1.1, "%s: chi2/dof = %.3f over %d pixels" % (name, chi2, dof)
     assert tot <= max(4.0 * tot_sigma, 1e-4), "%s: total flux differs by %.2e (sigma %.2e)" % (name, tot, tot_sigma)
     assert B.counters.reserved[0] == 0
