@@ -21,6 +21,7 @@ import numpy as np
 
 from . import backend as bk
 from .constants import FACTOR, PLANCK, PARSEC, ADHOC, SEED0, SEED1, GLOBAL_0, HPBG_NPIX, f2um
+from .fits import write_fits
 from .formats import read_cloud, read_otfile, write_cloud
 from .hostmath import fix, observer_directions_rad, energy_temperature_table, trapezoid_weights
 from .ini import User
@@ -52,13 +53,40 @@ def read_dusts(USER):
 
 
 def read_scattering_functions(USER):
-    if len(USER.file_scafunc) < 1:
+    """FDSC, FCSC [ndust, NFREQ, BINS]; ndust is 1 or the number of dusts (=> WITH_MSF) -- ASOC_aux.py:619-650."""
+    ndust = len(USER.file_scafunc)
+    if ndust < 1:
         print("*** No scattering function defined: keyword dsc")
         sys.exit()
-    with open(USER.file_scafunc[0], 'rb') as fp:
-        dsc = np.fromfile(fp, np.float32, USER.NFREQ * USER.DSC_BINS).reshape(USER.NFREQ, USER.DSC_BINS)
-        csc = np.fromfile(fp, np.float32).reshape(USER.NFREQ, USER.DSC_BINS)
+    if ndust != len(USER.file_optical) and ndust != 1:
+        print("Must have either a single scattering function (DSC file) or one for each dust!")
+        sys.exit()
+    dsc = np.zeros((ndust, USER.NFREQ, USER.DSC_BINS), np.float32)
+    csc = np.zeros((ndust, USER.NFREQ, USER.DSC_BINS), np.float32)
+    for i in range(ndust):
+        with open(USER.file_scafunc[i], 'rb') as fp:
+            dsc[i] = np.fromfile(fp, np.float32, USER.NFREQ * USER.DSC_BINS).reshape(USER.NFREQ, USER.DSC_BINS)
+            csc[i] = np.fromfile(fp, np.float32, USER.NFREQ * USER.DSC_BINS).reshape(USER.NFREQ, USER.DSC_BINS)
     return dsc, csc
+
+
+def mirror_mask(USER):
+    """MIRROR bit mask of ASOC.py:319-321: lower / upper border of x, y, z = x X y Y z Z."""
+    m = USER.MIRROR
+    return 1 * ('x' in m) + 2 * ('X' in m) + 4 * ('y' in m) + 8 * ('Y' in m) + 16 * ('z' in m) + 32 * ('Z' in m)
+
+
+def upload_scattering(dev, FDSC, FCSC, ifreq, AFABS=None, AFSCA=None):
+    """DSC / CSC of one frequency: [BINS], or [NDUST*BINS] plus the ABS / SCA vectors with several scattering
+    functions (ASOC.py:1162-1166, 1234-1243)."""
+    if FDSC.shape[0] == 1:
+        dev.upload(bk.BUF_DSC, FDSC[0, ifreq])
+        dev.upload(bk.BUF_CSC, FCSC[0, ifreq])
+    else:
+        dev.upload(bk.BUF_DSC, np.ascontiguousarray(FDSC[:, ifreq, :]).reshape(-1))
+        dev.upload(bk.BUF_CSC, np.ascontiguousarray(FCSC[:, ifreq, :]).reshape(-1))
+        dev.upload(bk.BUF_ABSV, np.asarray([a[ifreq] for a in AFABS], np.float32))
+        dev.upload(bk.BUF_SCAV, np.asarray([a[ifreq] for a in AFSCA], np.float32))
 
 
 def read_background(USER):
@@ -263,9 +291,13 @@ def main(argv=None, device_factory=None):
     USER.AREA = cloud.AREA
     ABU = read_abundances(CELLS, NDUST, USER)
     WITH_ABU = ABU.shape[0] > 0
+    WITH_MSF = FDSC.shape[0] > 1
     if WITH_ABU and USER.SINGLE_ABU and NDUST != 2:
         print("Option USER.SINGLE_ABU assumes exactly two dust components !!")
         sys.exit(0)
+    if WITH_MSF and (USER.SINGLE_ABU or not WITH_ABU):
+        print("Cannot have multiple scattering functions without multiple dusts with variable abundances")
+        sys.exit()
     DIFFUSERAD = []
     if len(USER.file_diffuse) > 0:
         dims = np.fromfile(USER.file_diffuse, np.int32, 2)
@@ -323,8 +355,12 @@ def main(argv=None, device_factory=None):
                    save_intensity=USER.SAVE_INTENSITY if USER.SAVE_INTENSITY in (1, 2) else 0,
                    use_emweight=USER.USE_EMWEIGHT, hpbg_weighted=int(USER.HPBG_WEIGHTED), step_weight=USER.STEP_WEIGHT[0],
                    sw_a=float("%.3e" % USER.STEP_WEIGHT[1]), sw_b=float("%.3e" % USER.STEP_WEIGHT[2]),
-                   level_threshold=USER.LEVEL_THRESHOLD, length=length, factor=FACTOR, adhoc=ADHOC)
+                   level_threshold=USER.LEVEL_THRESHOLD, length=length, factor=FACTOR, adhoc=ADHOC,
+                   with_msf=int(WITH_MSF), ndust=NDUST, mirror=mirror_mask(USER),
+                   map_interpolation=USER.MAP_INTERPOLATION)
     dev.set_grid(cloud)
+    if WITH_MSF:
+        dev.upload(bk.BUF_ABU, np.ascontiguousarray(ABU, np.float32).reshape(-1))
     dev.set_rng_mode(bk.RNG_REFERENCE if 'REFSTREAMS' in USER.KEYS else bk.RNG_PACKET)
     dev.set_geometry(1 if 'REFGEOMETRY' in USER.KEYS else 0)
     dev.set_shard(comm.rank, comm.world)
@@ -526,8 +562,7 @@ def main(argv=None, device_factory=None):
                     else:
                         dev.upload(bk.BUF_HPBG, np.asarray((WBG / FREQ) * HPBG[IFREQ, :], np.float32))
                 FF = float(FF_ALL[IFREQ])
-                dev.upload(bk.BUF_DSC, FDSC[IFREQ])
-                dev.upload(bk.BUF_CSC, FCSC[IFREQ])
+                upload_scattering(dev, FDSC, FCSC, IFREQ, AFABS, AFSCA)
                 if USER.SEED > 0:
                     seed = float(np.fmod(USER.SEED + SEED0 + IFREQ * SEED1, 1.0))
                 else:
@@ -601,8 +636,7 @@ def main(argv=None, device_factory=None):
                 # sic: with variable abundances the reference sums the opacities from dust 1 on here (ASOC.py:1673)
                 kabs, ksca = set_opacity(IFREQ, first=0 if USER.SINGLE_ABU else (1 if WITH_ABU else 0))
                 FF = float(FF_ALL[IFREQ])
-                dev.upload(bk.BUF_DSC, FDSC[IFREQ])
-                dev.upload(bk.BUF_CSC, FCSC[IFREQ])
+                upload_scattering(dev, FDSC, FCSC, IFREQ, AFABS, AFSCA)
                 if IFREQ < REMIT_I1 or IFREQ > REMIT_I2:
                     continue
                 if USER.WITH_REFERENCE:
@@ -769,9 +803,14 @@ def main(argv=None, device_factory=None):
         npx, npy = USER.NPIX['x'], USER.NPIX['y']
         npix = npx * npy
         fpmap = []
-        for idir in range(NDIR):
-            fpmap.append(open("map_dir_%02d.bin" % idir, "wb"))
-            np.asarray([npx, npy], np.int32).tofile(fpmap[idir])
+        # FITS files per direction and wavelength when `fits` and `singlemap`-style frequencies are given
+        # (ASOC.py:2984-2996), else one binary file per direction
+        using_fits = USER.FITS > 0 and len(USER.SINGLE_MAP_FREQ) > 0
+        fits_pix = USER.GL * USER.MAP_DX / (USER.DISTANCE if USER.DISTANCE > 0.0 else 1000.0)
+        if not using_fits:
+            for idir in range(NDIR):
+                fpmap.append(open("map_dir_%02d.bin" % idir, "wb"))
+                np.asarray([npx, npy], np.int32).tofile(fpmap[idir])
         first_freq = True
         savetau_freq = np.asarray(USER.savetau_freq, np.float64)
         for IFREQ in range(NFREQ):
@@ -806,16 +845,23 @@ def main(argv=None, device_factory=None):
                 suffix = '_dir%d' % idir if NDIR > 1 else ''
                 dev.mapping(USER.MAP_DX, npx, npy, ODIR[idir], RA[idir], DE[idir], kabs, ksca, centre, USER.INTOBS, save_colden)
                 if save_spe:
-                    dev.download(bk.BUF_MAP, npix).tofile(fpmap[idir])
-                # the reference writes these two through astropy FITS; here the same pixels as raw float32
-                if save_colden > 0:
-                    name = '%s_colden%s.bin' % (USER.file_savetau, suffix) if NDIR == 1 else \
-                        '%s_colden%s_%03d.bin' % (USER.file_savetau, suffix, idir)
-                    dev.download(bk.BUF_SAVETAU, npix).tofile(name)
+                    if using_fits:
+                        name = "%s_%s.fits" % (USER.FITS_PREFIX, ums) if NDIR == 1 else "%s_%s_%03d.fits" % (USER.FITS_PREFIX, ums, idir)
+                        write_fits(name, dev.download(bk.BUF_MAP, npix).reshape(npy, npx), USER.FITS_RA, USER.FITS_DE, fits_pix)
+                    else:
+                        dev.download(bk.BUF_MAP, npix).tofile(fpmap[idir])
+                if save_colden > 0:                                         # always FITS (ASOC.py:3152-3159)
+                    name = '%s_colden%s.fits' % (USER.file_savetau, suffix) if NDIR == 1 else \
+                        '%s_colden%s_%03d.fits' % (USER.file_savetau, suffix, idir)
+                    write_fits(name, dev.download(bk.BUF_SAVETAU, npix).reshape(npy, npx), USER.FITS_RA, USER.FITS_DE, fits_pix)
                 if save_tau > 0:
-                    name = '%s_tau_%s%s.bin' % (USER.file_savetau, ums, suffix) if NDIR == 1 else \
-                        '%s_tau_%s%s_%03d.bin' % (USER.file_savetau, ums, suffix, idir)
-                    dev.download(bk.BUF_SAVETAU, npix).tofile(name)
+                    ext = 'fits' if using_fits else 'bin'
+                    name = '%s_tau_%s%s.%s' % (USER.file_savetau, ums, suffix, ext) if NDIR == 1 else \
+                        '%s_tau_%s%s_%03d.%s' % (USER.file_savetau, ums, suffix, idir, ext)
+                    if using_fits:
+                        write_fits(name, dev.download(bk.BUF_SAVETAU, npix).reshape(npy, npx), USER.FITS_RA, USER.FITS_DE, fits_pix)
+                    else:
+                        dev.download(bk.BUF_SAVETAU, npix).tofile(name)
             if VERBOSE:
                 print("IFREQ=%3d/%3d  %9.2f um -- save_spe %d, save_tau %d, save_colden %d" % (IFREQ, NFREQ, um, save_spe, save_tau, save_colden))
         for fp in fpmap:

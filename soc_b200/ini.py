@@ -377,14 +377,10 @@ class User:
             bad.append("polmap/polsim/polstat: polarisation maps are not implemented")
         if self.WITH_ROI_SAVE or self.WITH_ROI_LOAD or self.ROI_MAP or self.ROIPAC:
             bad.append("roi*: region-of-interest options are not implemented")
-        if self.MIRROR:
-            bad.append("mirror: reflective borders are not implemented")
         if self.DIR_WEIGHT[0] > 0:
             bad.append("dirweight: does not compile in the reference either (undeclared pweight)")
         if self.PS_METHOD == 3:
             bad.append("psmethod 3: not implemented in the reference either")
-        if len(self.file_scafunc) > 1:
-            bad.append("several dsc files (WITH_MSF) are not implemented")
         if self.MAP_INTERPOLATION:
             bad.append("mapint: map interpolation is not implemented")
         if self.FAST_MAP > 1:

@@ -8,7 +8,7 @@ from soc_b200.formats import write_cloud, write_dust, write_dsc
 
 
 def write_model(path, n=12, octree=False, nfreq=8, bgpac=40000, pspac=0, cellpac=0, iterations=1, extra="",
-                noabsorbed=True, absorbed=False, seed=0.4321, maps=True, abundance=False):
+                noabsorbed=True, absorbed=False, seed=0.4321, maps=True, abundance=False, two_dusts=False, hpbg=False):
     """Returns the ini file name.  Frequencies 3e11..3e15 Hz, silicate-like toy dust, HG scattering tables."""
     os.makedirs(path, exist_ok=True)
     cloud = synth.octree_cloud(n, 3, refine_fraction=0.2, seed=5) if octree else synth.regular_cloud(n, 0.25)
@@ -27,11 +27,33 @@ def write_model(path, n=12, octree=False, nfreq=8, bgpac=40000, pspac=0, cellpac
     if abundance:
         rng = np.random.default_rng(3)
         (0.5 + rng.random(cloud.CELLS)).astype(np.float32).tofile(os.path.join(path, "abu.bin"))
+    if two_dusts:
+        # second species: same frequency grid, different albedo and asymmetry, own abundance file and dsc file
+        write_dust(os.path.join(path, "toy2.dust"), freq, 0.3 * g, 1.4 * qabs, 0.5 * qsca, grain_density=1.0e-7, grain_size=1.0e-5)
+        dsc2 = np.zeros((nfreq, bins), np.float32)
+        csc2 = np.zeros((nfreq, bins), np.float32)
+        for i in range(nfreq):
+            dsc2[i], csc2[i] = synth.hg_tables(0.3 * g[i], bins)
+        write_dsc(os.path.join(path, "toy2.dsc"), dsc2, csc2)
+        rng = np.random.default_rng(4)
+        (0.5 + rng.random(cloud.CELLS)).astype(np.float32).tofile(os.path.join(path, "abu1.bin"))
+        (0.2 + rng.random(cloud.CELLS)).astype(np.float32).tofile(os.path.join(path, "abu2.bin"))
+    if hpbg:
+        rng = np.random.default_rng(6)
+        sky = (0.5 + rng.random(49152)).astype(np.float32)
+        sky[10000:12000] *= 5.0
+        np.outer(synth.isrf_like_background(freq32, 1.0), sky / sky.mean()).astype(np.float32).tofile(os.path.join(path, "hpbg.bin"))
     ini = os.path.join(path, "model.ini")
     with open(ini, "w") as fp:
         fp.write("cloud        model.cloud\n")
-        fp.write("optical      toy.dust%s\n" % ("  abu.bin" if abundance else ""))
-        fp.write("dsc          toy.dsc %d\n" % bins)
+        if two_dusts:
+            fp.write("optical      toy.dust  abu1.bin\noptical      toy2.dust  abu2.bin\n")
+            fp.write("dsc          toy.dsc %d\ndsc          toy2.dsc %d\n" % (bins, bins))
+        else:
+            fp.write("optical      toy.dust%s\n" % ("  abu.bin" if abundance else ""))
+            fp.write("dsc          toy.dsc %d\n" % bins)
+        if hpbg:
+            fp.write("hpbg         hpbg.bin 1.0 %d\n" % (1 if hpbg == 2 else 0))
         fp.write("gridlength   0.02\ndensity      %.3e   # scaling of densities\n" % (6.0 / n))   # tau_V across the model ~ 10
         fp.write("background   bg.bin  1.0\n")
         fp.write("bgpackets    %d\n" % bgpac)

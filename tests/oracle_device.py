@@ -30,7 +30,7 @@ class OracleDevice:
 
     # ---- configuration ------------------------------------------------------------------------------------
     def set_params(self, **kw):
-        if kw.get("with_msf") or kw.get("mirror") or kw.get("do_split"):
+        if kw.get("do_split") or kw.get("roi_flags") or kw.get("dir_weight"):
             raise bk.SocError("unsupported option")
         self.params = dict(kw)
         if self.cloud is not None:
@@ -44,9 +44,10 @@ class OracleDevice:
         p = dict(self.params)
         length = p.pop("length")
         bins = p.pop("bins", 2500)
-        for k in ("factor", "adhoc", "with_msf", "mirror", "dir_weight", "do_split", "roi_flags", "map_interpolation"):
+        for k in ("factor", "adhoc", "dir_weight", "do_split", "roi_flags"):
             p.pop(k, None)
-        self.O = orc.Oracle(self.cloud, gl=0.01, bins=bins, **p)
+        # the drivers are compared with the library's production kernels: exact mirror / scattering position
+        self.O = orc.Oracle(self.cloud, gl=0.01, bins=bins, mirror_exact=1, sca_exact_level=1, **p)
         self.O.P.length = length
         self.n = self.cloud.CELLS
 
@@ -60,6 +61,9 @@ class OracleDevice:
         pass
 
     def set_geometry(self, mode):
+        pass
+
+    def set_layout(self, mode):
         pass
 
     def sync(self):
@@ -110,6 +114,9 @@ class OracleDevice:
     def _g(self, b):
         return self.buf.get(b)
 
+    def _msf(self):
+        return dict(abu=self._g(bk.BUF_ABU), abs_v=self._g(bk.BUF_ABSV), sca_v=self._g(bk.BUF_SCAV))
+
     def _sharded(self, run, seed):
         """Run a launch; with world > 1 every rank contributes 1/world of a full launch with its own seed."""
         if self.world == 1:
@@ -128,17 +135,17 @@ class OracleDevice:
                                               dsc=self._g(bk.BUF_DSC), csc=self._g(bk.BUF_CSC), opt=self._g(bk.BUF_OPT),
                                               pspos=self._g(bk.BUF_PSPOS), ps=self._g(bk.BUF_PS),
                                               xps_nside=self._g(bk.BUF_XPS_NSIDE), xps_side=self._g(bk.BUF_XPS_SIDE),
-                                              xps_area=self._g(bk.BUF_XPS_AREA)), seed)
+                                              xps_area=self._g(bk.BUF_XPS_AREA), **self._msf()), seed)
 
     def sim_hp(self, packets, batch, seed, abs_, sca, tw, global_):
         self._sharded(lambda s: self.O.sim_hp(global_, packets, batch, s, tw, abs_=abs_, sca=sca, dsc=self._g(bk.BUF_DSC),
                                               csc=self._g(bk.BUF_CSC), opt=self._g(bk.BUF_OPT), hpbg=self._g(bk.BUF_HPBG),
-                                              hpbgp=self._g(bk.BUF_HPBGP)), seed)
+                                              hpbgp=self._g(bk.BUF_HPBGP), **self._msf()), seed)
 
     def sim_cl(self, source, packets, batch, seed, abs_, sca, tw, global_):
         self._sharded(lambda s: self.O.sim_cl(global_, packets, batch, s, tw, abs_=abs_, sca=sca, dsc=self._g(bk.BUF_DSC),
                                               csc=self._g(bk.BUF_CSC), opt=self._g(bk.BUF_OPT), emit=self._g(bk.BUF_EMIT),
-                                              emwei=self._g(bk.BUF_EMWEI)), seed)
+                                              emwei=self._g(bk.BUF_EMWEI), **self._msf()), seed)
 
     def absorbed_begin(self, nfreq):
         self.fabs = np.zeros((self.n, nfreq), np.float32)
@@ -181,24 +188,42 @@ class OracleDevice:
         return self.O.ps_tau(self.buf[bk.BUF_PSPOS][:3 * no], dir_, abs_, sca, opt=self._g(bk.BUF_OPT))
 
     def sca_zero_out(self, ndir, npx, npy):
-        self.buf[bk.BUF_OUT] = np.zeros(ndir * npx * npy, np.float32)
+        self.buf[bk.BUF_OUT] = np.zeros(ndir * npx * npy if ndir > 0 else 12 * ndir * ndir, np.float32)
 
     def _obs(self, ndir):
+        if ndir < 0:            # Healpix observer: ODIR holds the position, ORA / ODE are not used
+            z = np.zeros((1, 3), np.float32)
+            return self.buf[bk.BUF_ODIR][:3].reshape(1, 3), z, z
         return [self.buf[b].reshape(ndir, 3) for b in (bk.BUF_ODIR, bk.BUF_ORA, bk.BUF_ODE)]
 
-    def sca_ps(self, packets, batch, seed, abs_, sca, ndir, npx, npy, map_dx, centre, global_):
+    def _sca(self, fun, lead, seed, ndir, npx, npy, map_dx, centre, **bufs):
         od, ra, de = self._obs(ndir)
-        out = self.O.sca_ps(global_, packets, batch, seed, ndir, npx, npy, map_dx, centre, od, ra, de, abs_=abs_, sca=sca,
-                            dsc=self._g(bk.BUF_DSC), csc=self._g(bk.BUF_CSC), opt=self._g(bk.BUF_OPT),
-                            pspos=self._g(bk.BUF_PSPOS), ps=self._g(bk.BUF_PS))
+        if self.world > 1:
+            seed = float(np.fmod(seed + 0.37 * self.rank + 0.011, 1.0))
+        out = fun(*lead, seed, ndir, npx, npy, map_dx, centre, od, ra, de, dsc=self._g(bk.BUF_DSC), csc=self._g(bk.BUF_CSC),
+                  opt=self._g(bk.BUF_OPT), **self._msf(), **bufs)
         self.buf[bk.BUF_OUT] = self.buf[bk.BUF_OUT] + out.reshape(-1) / np.float32(self.world)
+
+    def sca_ps(self, packets, batch, seed, abs_, sca, ndir, npx, npy, map_dx, centre, global_):
+        self._sca(self.O.sca_ps, (global_, packets, batch), seed, ndir, npx, npy, map_dx, centre, abs_=abs_, sca=sca,
+                  pspos=self._g(bk.BUF_PSPOS), ps=self._g(bk.BUF_PS))
 
     def sca_pb(self, source, packets, batch, seed, abs_, sca, bg, ndir, npx, npy, map_dx, centre, global_):
         od, ra, de = self._obs(ndir)
+        if self.world > 1:
+            seed = float(np.fmod(seed + 0.37 * self.rank + 0.011, 1.0))
         out = self.O.sca_pb(global_, source, packets, batch, seed, bg, ndir, npx, npy, map_dx, centre, od, ra, de, abs_=abs_,
                             sca=sca, dsc=self._g(bk.BUF_DSC), csc=self._g(bk.BUF_CSC), opt=self._g(bk.BUF_OPT),
-                            pspos=self._g(bk.BUF_PSPOS), ps=self._g(bk.BUF_PS))
+                            pspos=self._g(bk.BUF_PSPOS), ps=self._g(bk.BUF_PS), **self._msf())
         self.buf[bk.BUF_OUT] = self.buf[bk.BUF_OUT] + out.reshape(-1) / np.float32(self.world)
+
+    def sca_hp(self, packets, batch, seed, abs_, sca, ndir, npx, npy, map_dx, centre, global_):
+        self._sca(self.O.sca_hp, (global_, packets, batch), seed, ndir, npx, npy, map_dx, centre, abs_=abs_, sca=sca,
+                  hpbg=self._g(bk.BUF_HPBG), hpbgp=self._g(bk.BUF_HPBGP))
+
+    def sca_cl(self, source, packets, batch, seed, abs_, sca, ndir, npx, npy, map_dx, centre, global_):
+        self._sca(self.O.sca_cl, (global_, packets, batch), seed, ndir, npx, npy, map_dx, centre, abs_=abs_, sca=sca,
+                  emit=self._g(bk.BUF_EMIT), emwei=self._g(bk.BUF_EMWEI))
 
     def counters(self):
         return _Counters(self.O.counters)

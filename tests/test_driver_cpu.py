@@ -110,3 +110,53 @@ def test_scattered_light_driver_writes_outcoming(tmp_path):
     freq, out = read_outcoming(str(tmp_path / "outcoming.socs"))
     assert out.shape == (8, 2, 8, 8) and len(freq) == 8
     assert np.isfinite(out).all() and (out >= 0).all() and out[4:].max() > 0
+
+
+def _run_asocs(tmp_path):
+    from soc_b200 import asocs
+    cwd = os.getcwd()
+    os.chdir(str(tmp_path))
+    try:
+        asocs.main(["ASOCS.py", "model.ini"], device_factory=OracleDevice)
+    finally:
+        os.chdir(cwd)
+
+
+def test_two_scattering_functions_mirror_and_fits(tmp_path):
+    """Two dust species with their own abundance and dsc files (=> WITH_MSF), reflecting borders, FITS products."""
+    from soc_b200.fits import read_fits
+    kw = dict(n=8, bgpac=20000, pspac=33000, two_dusts=True, noabsorbed=False, absorbed=True)
+    write_model(str(tmp_path), **kw)
+    um = 2.99792458e14 / np.loadtxt(str(tmp_path / "toy.dust"), skiprows=4)[:, 0]       # wavelengths of the grid
+    cloud = _run(tmp_path, extra="mirror xY\nfits 12.5 -3.0 img\nmapum %.4f %.4f\nsavetau tau -1 %.4f\n" % (um[1], um[2], um[2]), **kw)
+    a = read_cells_freq_file(str(tmp_path / "abs.data"))          # several dusts: the solve is external (A2E)
+    assert a.shape == (cloud.CELLS, 8) and (a >= 0).all() and (a.sum(axis=0) > 0).all()
+    names = sorted(f for f in os.listdir(str(tmp_path)) if f.endswith(".fits"))
+    assert any(f.startswith("img_") for f in names) and any("colden" in f for f in names) and any("_tau_" in f for f in names)
+    hdr, img = read_fits(str(tmp_path / [f for f in names if f.startswith("img_") and f.endswith("_000.fits")][0]))
+    assert img.shape == (8, 8) and hdr["CRVAL1"] == 12.5 and hdr["CTYPE1"] == "RA---TAN" and np.isfinite(img).all()
+    hdr, col = read_fits(str(tmp_path / [f for f in names if "colden" in f][0]))
+    assert col.min() > 0
+
+
+def test_scattered_light_healpix_sky_cell_emission_and_healpix_observer(tmp_path):
+    """ASOCS with every source of ASOCS.py:416-870 -- point source, Healpix sky, emission of the dust read from
+    the emitted file -- and a Healpix image seen by an internal observer."""
+    _run(tmp_path, n=8, bgpac=20000, pspac=33000, hpbg=2)                                # ASOC first: writes emit.data
+    ini, cloud = write_model(str(tmp_path), n=8, bgpac=20000, pspac=66000, cellpac=8 ** 3 * 2, hpbg=2,
+                             extra="perspective 3.3 4.1 2.7\noutnside 4\n")
+    _run_asocs(tmp_path)
+    raw = np.fromfile(str(tmp_path / "outcoming.socs"), np.int32, 2)
+    assert list(raw) == [4, 8]
+    data = np.fromfile(str(tmp_path / "outcoming.socs"), np.float32, offset=4 * (2 + 8)).reshape(8, 12 * 16)
+    assert np.isfinite(data).all() and (data >= 0).all() and (data[4:] > 0).mean() > 0.9
+
+
+def test_scattered_light_fits_cube(tmp_path):
+    from soc_b200.fits import read_fits
+    ini, cloud = write_model(str(tmp_path), n=8, bgpac=20000, pspac=66000)
+    txt = open(ini).read().replace("directions   70.0 30.0\n", "") + "fits\nscattering scat\n"
+    open(ini, "w").write(txt)
+    _run_asocs(tmp_path)
+    hdr, cube = read_fits(str(tmp_path / "scat.fits"))
+    assert cube.shape == (8, 8, 8) and hdr["NAXIS3"] == 8 and np.isfinite(cube).all() and cube[4:].max() > 0

@@ -104,3 +104,43 @@ def test_device_resident_absorbed_array_matches_host_accumulation(tmp_path):
     leaves = ~parents
     assert np.abs(a[leaves] - b[leaves]).max() <= 2e-5 * b[leaves].max()
     assert np.abs(a[leaves].sum() / b[leaves].sum() - 1.0) < 1e-5
+
+
+def test_two_dusts_msf_mirror_driver(tmp_path):
+    """Two dust species with their own scattering functions (WITH_MSF) and reflecting borders through the driver:
+    the absorbed file of the CUDA run agrees with the oracle-backed run within Monte Carlo noise."""
+    kw = dict(n=10, bgpac=300000, pspac=330000, two_dusts=True, noabsorbed=False, absorbed=True, maps=False, extra="mirror xY\n")
+    cloud = _run(tmp_path / "gpu", None, **kw)
+    _run(tmp_path / "cpu", OracleDevice, **kw)
+    ag = read_cells_freq_file(str(tmp_path / "gpu" / "abs.data")).astype(np.float64)
+    ac = read_cells_freq_file(str(tmp_path / "cpu" / "abs.data")).astype(np.float64)
+    tg, tc = ag.sum(axis=0), ac.sum(axis=0)
+    ok = tc > 0
+    assert np.abs(tg[ok] / tc[ok] - 1.0).max() < 0.015
+    f = np.argmax(tc)
+    rel = np.abs(ag[:, f] / ac[:, f] - 1.0)
+    assert np.median(rel) < 0.06
+
+
+def test_scattered_light_all_sources_healpix_observer(tmp_path):
+    """ASOCS with the Healpix sky, the emission of the dust (emitted file) and a Healpix image for an outside
+    observer: CUDA run vs oracle-backed run."""
+    from soc_b200 import asocs
+    res = []
+    for name, fac in (("gpu", None), ("cpu", OracleDevice)):
+        d = tmp_path / name
+        _run(d, fac, n=8, bgpac=60000, pspac=33000, hpbg=1, maps=False)          # ASOC first: writes emit.data
+        write_model(str(d), n=8, bgpac=200000, pspac=330000, cellpac=8 ** 3 * 40, hpbg=1,
+                    extra="perspective 12.3 4.1 2.7\noutnside 2\n")
+        cwd = os.getcwd()
+        os.chdir(str(d))
+        try:
+            asocs.main(["ASOCS.py", "model.ini"], device_factory=fac)
+        finally:
+            os.chdir(cwd)
+        res.append(np.fromfile(str(d / "outcoming.socs"), np.float32, offset=4 * (2 + 8)).reshape(8, 48).astype(np.float64))
+    g, c = res
+    assert np.isfinite(g).all()
+    for f in range(8):
+        if c[f].sum() > 0:
+            assert abs(g[f].sum() / c[f].sum() - 1.0) < 0.05, (f, g[f].sum(), c[f].sum())
