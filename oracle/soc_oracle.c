@@ -782,10 +782,78 @@ static void map_pixel(const OrcParams *P, const nav_t *N, int id, float map_dx, 
         if (fabsf(TMP.z) < 1.0e-5f) TMP.z = 1.0e-5f;
     }
     index_g_map(N, &POS, &level, &ind);
+    /* MAP_INTERPOLATION: two directions perpendicular to the line of sight, kernel_ASOC_map.c:656-684 */
+    const int MI = P->map_interpolation;
+    v3 ADIR = { 0, 0, 0 }, BDIR = { 0, 0, 0 }, MPOS, POS0;
+    int slevel, sind, level0, ind0;
+    float a, b, Adens, Bdens, Aemit, Bemit, K;
+    if (MI > 0) {
+        if (fabsf(TMP.x) > fabsf(TMP.y)) {
+            if (fabsf(TMP.z) > fabsf(TMP.x)) { ADIR.x = 0.0005f; ADIR.y = 1.0f; ADIR.z = -TMP.y / TMP.z; }
+            else                             { ADIR.x = -TMP.z / TMP.x; ADIR.y = 0.0005f; ADIR.z = 1.0f; }
+        } else {
+            if (fabsf(TMP.z) > fabsf(TMP.y)) { ADIR.x = 0.0005f; ADIR.y = 1.0f; ADIR.z = -TMP.y / TMP.z; }
+            else                             { ADIR.x = 1.0f; ADIR.y = -TMP.x / TMP.y; ADIR.z = 0.0005f; }
+        }
+        ADIR = v3_norm(ADIR);
+        BDIR.x = TMP.y * ADIR.z - TMP.z * ADIR.y;
+        BDIR.y = TMP.z * ADIR.x - TMP.x * ADIR.z;
+        BDIR.z = TMP.x * ADIR.y - TMP.y * ADIR.x;
+        BDIR = v3_norm(BDIR);
+    }
     while (ind >= 0) {                                                        /* kernel_ASOC_map.c:688-861 */
         oind = N->off[level] + ind; olevel = level;
+        if (MI > 0) { POS0 = POS; ind0 = ind; level0 = level; K = ldexpf(1.0f, -level0); }
         sx = get_step_map(N, &POS, &TMP, &level, &ind);
         dens = N->dens[oind]; em = emit[oind];
+        if (MI > 0) {                                                         /* :706-805 */
+            const float lim = (MI == 2) ? 0.52f : 0.502f;
+            if (MI == 2) {
+                a = 0.22f * K;
+                if (sx > a) {
+                    sx = a;
+                    POS.x = POS0.x + 0.22f * TMP.x; POS.y = POS0.y + 0.22f * TMP.y; POS.z = POS0.z + 0.22f * TMP.z;
+                    ind = ind0; level = level0;
+                    index_map(N, &POS, &level, &ind);
+                }
+            }
+            float h = 0.5f * sx / K;
+            slevel = level0; sind = ind0;
+            MPOS.x = POS0.x + h * TMP.x; MPOS.y = POS0.y + h * TMP.y; MPOS.z = POS0.z + h * TMP.z;
+            a = get_step_map(N, &MPOS, &ADIR, &slevel, &sind);
+            a /= K;
+            if (a <= lim && sind >= 0) { Adens = N->dens[N->off[slevel] + sind]; Aemit = emit[N->off[slevel] + sind]; }
+            else {
+                slevel = level0; sind = ind0; ADIR.x *= -1.0f; ADIR.y *= -1.0f; ADIR.z *= -1.0f;
+                MPOS.x = POS0.x + h * TMP.x; MPOS.y = POS0.y + h * TMP.y; MPOS.z = POS0.z + h * TMP.z;
+                a = get_step_map(N, &MPOS, &ADIR, &slevel, &sind);
+                a /= K;
+                if (a <= lim && sind >= 0) { Adens = N->dens[N->off[slevel] + sind]; Aemit = emit[N->off[slevel] + sind]; }
+                else { a = 0.5f; Adens = 0.0f; Aemit = 0.0f; }
+            }
+            slevel = level0; sind = ind0;
+            MPOS.x = POS0.x + h * TMP.x; MPOS.y = POS0.y + h * TMP.y; MPOS.z = POS0.z + h * TMP.z;
+            b = get_step_map(N, &MPOS, &BDIR, &slevel, &sind);
+            b /= K;
+            if (b <= lim && sind >= 0) { Bdens = N->dens[N->off[slevel] + sind]; Bemit = emit[N->off[slevel] + sind]; }
+            else {
+                slevel = level0; sind = ind0; BDIR.x *= -1.0f; BDIR.y *= -1.0f; BDIR.z *= -1.0f;
+                MPOS.x = POS0.x + h * TMP.x; MPOS.y = POS0.y + h * TMP.y; MPOS.z = POS0.z + h * TMP.z;
+                b = get_step_map(N, &MPOS, &BDIR, &slevel, &sind);
+                if (MI == 1) b /= K;                                          /* sic: missing in the MAP_INTERPOLATION==2 branch, :750 */
+                if (b <= lim && sind >= 0) { Bdens = N->dens[N->off[slevel] + sind]; Bemit = emit[N->off[slevel] + sind]; }
+                else { b = 0.5f; Bdens = 0.0f; Bemit = 0.0f; }
+            }
+            if (MI == 2) {
+                a = clampf(a, 0.0f, 0.51f); b = clampf(b, 0.0f, 0.51f);
+                dens = (0.5f - a) * Adens + (0.5f - b) * Bdens + (a + b) * dens;
+                em   = (0.5f - a) * Aemit + (0.5f - b) * Bemit + (a + b) * em;
+            } else {
+                a = 0.5f - a; b = 0.5f - b;
+                dens = (1.0f - a - b) * dens + a * Adens + b * Bdens;
+                em   = (1.0f - a - b) * em + a * Aemit + b * Bemit;
+            }
+        }
         if (P->with_abu) DTAU = sx * dens * (opt[2 * (long)oind] + opt[2 * (long)oind + 1]);
         else             DTAU = sx * dens * (sca_ + abs_);
         if (P->level_threshold <= 0 || olevel >= P->level_threshold) {

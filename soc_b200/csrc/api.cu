@@ -560,6 +560,7 @@ static int map_common(soc_context *c, MapArgs &M, size_t npixels, float abs, flo
     M.emit = dptr<float>(c, SOC_BUF_EMIT); M.opt = dptr<float>(c, SOC_BUF_OPT);
     M.kabs = abs; M.ksca = sca; M.length = c->P.length;
     M.with_abu = c->P.with_abu; M.level_threshold = c->P.level_threshold; M.save_colden = save_colden;
+    M.map_interpolation = c->P.map_interpolation;
     M.counters = c->counters;
     return SOC_OK;
 }

@@ -34,6 +34,23 @@ __device__ __forceinline__ void integrate(const MapArgs &M, vec3 POS, const vec3
     int level = 0, ind;
     float rho = 0.0f, TAU = 0.0f, PHOTONS = 0.0f, colden = 0.0f;
     index_global<OCT, true>(G, POS, level, ind, rho);
+    // MAP_INTERPOLATION (kernel_ASOC_map.c:656-684): two unit vectors perpendicular to the line of sight
+    const int MI = HEALPIX ? 0 : M.map_interpolation;
+    vec3 ADIR = { 0.0f, 0.0f, 0.0f }, BDIR = { 0.0f, 0.0f, 0.0f };
+    if (MI > 0) {
+        if (fabsf(TMP.x) > fabsf(TMP.y)) {
+            if (fabsf(TMP.z) > fabsf(TMP.x)) { ADIR.x = 0.0005f; ADIR.y = 1.0f; ADIR.z = xdiv(-TMP.y, TMP.z); }
+            else                             { ADIR.x = xdiv(-TMP.z, TMP.x); ADIR.y = 0.0005f; ADIR.z = 1.0f; }
+        } else {
+            if (fabsf(TMP.z) > fabsf(TMP.y)) { ADIR.x = 0.0005f; ADIR.y = 1.0f; ADIR.z = xdiv(-TMP.y, TMP.z); }
+            else                             { ADIR.x = 1.0f; ADIR.y = xdiv(-TMP.x, TMP.y); ADIR.z = 0.0005f; }
+        }
+        ADIR = normalize3(ADIR);
+        BDIR.x = xsub(xmul(TMP.y, ADIR.z), xmul(TMP.z, ADIR.y));
+        BDIR.y = xsub(xmul(TMP.z, ADIR.x), xmul(TMP.x, ADIR.z));
+        BDIR.z = xsub(xmul(TMP.x, ADIR.y), xmul(TMP.y, ADIR.x));
+        BDIR = normalize3(BDIR);
+    }
     while (ind >= 0) {
         int oind = OCT ? G.off[level] + ind : ind, olevel = level;
         float dens = rho;
@@ -41,7 +58,60 @@ __device__ __forceinline__ void integrate(const MapArgs &M, vec3 POS, const vec3
         float kext;
         if (M.with_abu) { float2 o = reinterpret_cast<const float2 *>(M.opt)[oind]; kext = xadd(o.x, o.y); }
         else            kext = xadd(M.ksca, M.kabs);
+        const vec3 POS0 = POS;
+        const int ind0 = ind, level0 = level;
         float sx = get_step<OCT, DBL, true>(G, POS, TMP, level, ind, rho);
+        if (MI > 0) {                                                          // kernel_ASOC_map.c:706-805
+            const float K = ldexpf(1.0f, -level0);
+            const float lim = (MI == 2) ? 0.52f : 0.502f;
+            if (MI == 2) {
+                const float amax = xmul(0.22f, K);
+                if (sx > amax) {                                               // the step is cut to 0.22 cells
+                    sx = amax;
+                    POS.x = xadd(POS0.x, xmul(0.22f, TMP.x)); POS.y = xadd(POS0.y, xmul(0.22f, TMP.y)); POS.z = xadd(POS0.z, xmul(0.22f, TMP.z));
+                    ind = ind0; level = level0;
+                    if (OCT) { if (DBL) index_octree<double, true>(G, POS, level, ind, rho); else index_octree<float, true>(G, POS, level, ind, rho); }
+                    else {
+                        if (!(POS.x > 0.0f && POS.x < G.nx && POS.y > 0.0f && POS.y < G.ny && POS.z > 0.0f && POS.z < G.nz)) ind = -1;
+                        else { ind = (int)floorf(POS.z) * G.nx * G.ny + (int)floorf(POS.y) * G.nx + (int)floorf(POS.x); rho = G.dens[ind]; }
+                    }
+                }
+            }
+            const float h = xdiv(xmul(0.5f, sx), K);
+            float a, b, Adens, Bdens, Aemit, Bemit, srho = 0.0f;
+            int slevel = level0, sind = ind0;
+            vec3 MPOS = { xadd(POS0.x, xmul(h, TMP.x)), xadd(POS0.y, xmul(h, TMP.y)), xadd(POS0.z, xmul(h, TMP.z)) };
+            a = xdiv(get_step<OCT, DBL, true>(G, MPOS, ADIR, slevel, sind, srho), K);
+            if (a <= lim && sind >= 0) { Adens = srho; Aemit = M.emit[(OCT ? G.off[slevel] : 0) + sind]; }
+            else {
+                slevel = level0; sind = ind0; ADIR.x = -ADIR.x; ADIR.y = -ADIR.y; ADIR.z = -ADIR.z;
+                MPOS.x = xadd(POS0.x, xmul(h, TMP.x)); MPOS.y = xadd(POS0.y, xmul(h, TMP.y)); MPOS.z = xadd(POS0.z, xmul(h, TMP.z));
+                a = xdiv(get_step<OCT, DBL, true>(G, MPOS, ADIR, slevel, sind, srho), K);
+                if (a <= lim && sind >= 0) { Adens = srho; Aemit = M.emit[(OCT ? G.off[slevel] : 0) + sind]; }
+                else { a = 0.5f; Adens = 0.0f; Aemit = 0.0f; }
+            }
+            slevel = level0; sind = ind0;
+            MPOS.x = xadd(POS0.x, xmul(h, TMP.x)); MPOS.y = xadd(POS0.y, xmul(h, TMP.y)); MPOS.z = xadd(POS0.z, xmul(h, TMP.z));
+            b = xdiv(get_step<OCT, DBL, true>(G, MPOS, BDIR, slevel, sind, srho), K);
+            if (b <= lim && sind >= 0) { Bdens = srho; Bemit = M.emit[(OCT ? G.off[slevel] : 0) + sind]; }
+            else {
+                slevel = level0; sind = ind0; BDIR.x = -BDIR.x; BDIR.y = -BDIR.y; BDIR.z = -BDIR.z;
+                MPOS.x = xadd(POS0.x, xmul(h, TMP.x)); MPOS.y = xadd(POS0.y, xmul(h, TMP.y)); MPOS.z = xadd(POS0.z, xmul(h, TMP.z));
+                b = get_step<OCT, DBL, true>(G, MPOS, BDIR, slevel, sind, srho);
+                if (MI == 1) b = xdiv(b, K);                                   // sic: not converted in the MAP_INTERPOLATION==2 branch (:750)
+                if (b <= lim && sind >= 0) { Bdens = srho; Bemit = M.emit[(OCT ? G.off[slevel] : 0) + sind]; }
+                else { b = 0.5f; Bdens = 0.0f; Bemit = 0.0f; }
+            }
+            if (MI == 2) {
+                a = clampf(a, 0.0f, 0.51f); b = clampf(b, 0.0f, 0.51f);
+                dens = xadd(xadd(xmul(xsub(0.5f, a), Adens), xmul(xsub(0.5f, b), Bdens)), xmul(xadd(a, b), dens));
+                em   = xadd(xadd(xmul(xsub(0.5f, a), Aemit), xmul(xsub(0.5f, b), Bemit)), xmul(xadd(a, b), em));
+            } else {
+                a = xsub(0.5f, a); b = xsub(0.5f, b);
+                dens = xadd(xadd(xmul(xsub(xsub(1.0f, a), b), dens), xmul(a, Adens)), xmul(b, Bdens));
+                em   = xadd(xadd(xmul(xsub(xsub(1.0f, a), b), em), xmul(a, Aemit)), xmul(b, Bemit));
+            }
+        }
         float DTAU = xmul(xmul(sx, dens), kext);
         if (HEALPIX || M.level_threshold <= 0 || olevel >= M.level_threshold) {
             float w = (DTAU < 1.0e-3f) ? xsub(1.0f, xmul(0.5f, DTAU)) : xdiv(xsub(1.0f, exp_cr(-DTAU)), DTAU);

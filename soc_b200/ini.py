@@ -381,8 +381,6 @@ class User:
             bad.append("dirweight: does not compile in the reference either (undeclared pweight)")
         if self.PS_METHOD == 3:
             bad.append("psmethod 3: not implemented in the reference either")
-        if self.MAP_INTERPOLATION:
-            bad.append("mapint: map interpolation is not implemented")
         if self.FAST_MAP > 1:
             bad.append("mapping ... fast: fast / per-level maps are not implemented")
         if self.USE_EMWEIGHT > 1:

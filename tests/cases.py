@@ -279,6 +279,10 @@ CASES = {
     "map_oct6_4_thr":  (_oct(6, 4, 0.25, 8), dict(level_threshold=1), run_map((20, 20), [(120.0, 200.0)], map_dx=0.35)),
     "map_reg16_persp": (_reg(16), {}, run_map((32, 16), [(0.0, 0.0)], intobs=(7.3, 8.4, 9.1))),
     "hpmap_oct8_3":    (_oct(8, 3), {}, run_hpmap(8, (4.2, 3.3, 5.1))),
+    "map_reg16_int1":  (_reg(16), dict(map_interpolation=1), run_map((20, 16), [(0.0, 0.0), (60.0, 30.0)])),
+    "map_oct8_3_int1": (_oct(8, 3), dict(map_interpolation=1), run_map((24, 24), [(35.0, 110.0)], map_dx=0.4)),
+    "map_reg16_int2":  (_reg(16), dict(map_interpolation=2), run_map((20, 16), [(90.0, 0.0), (60.0, 30.0)])),
+    "map_oct6_4_int2": (_oct(6, 4, 0.25, 8), dict(map_interpolation=2, with_abu=1), run_map((20, 20), [(120.0, 200.0)], map_dx=0.35, abu=True)),
     "map_pstau_reg16":  (_reg(16), dict(no_ps=3), run_pstau([(8.3, 8.3, 8.3), (2.2, 13.1, 5.5), (15.6, 0.7, 9.9)], [(0.0, 0.0), (60.0, 30.0)])),
     "map_pstau_oct8":   (_oct(8, 3), dict(no_ps=2, with_abu=1), run_pstau([(4.3, 4.2, 3.9), (1.1, 6.8, 2.4)], [(35.0, 110.0)], abu=True)),
     "sca_ps_reg16":    (_reg(16), dict(no_ps=2), run_sca("ps", pspos=[(8.3, 8.3, 8.3), (4.1, 10.7, 12.2)])),
