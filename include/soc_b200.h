@@ -20,8 +20,8 @@
  *                                           (kernel_ASOC.c:15, 831, 1223; ASOC.py:1317-1419, 1847)
  *   soc_absorbed_begin / _add / _finish     FABSORBED[:,f] += TMP and the final scaling loop
  *                                           (ASOC.py:1482-1497, 2782-2878), kept on the device
- *   soc_eq_temperature / soc_emission       kernels EqTemperature / Emission
- *                                           (kernel_ASOC_aux.c:745, 793; ASOC.py:2027-2040, 2185-2197)
+ *   soc_eq_temperature / soc_emission       kernels EqTemperature / Emission / Emission2
+ *     / soc_emission2                       (kernel_ASOC_aux.c:745, 793, 862; ASOC.py:2027-2040, 2154-2197)
  *   soc_ps_tau                              kernel PSTau (kernel_ASOC_map.c:1545; ASOC.py:3576-3644)
  *   soc_mapping / soc_healpix_mapping       kernels Mapping / HealpixMapping
  *                                           (kernel_ASOC_map.c:496, 890; ASOC.py:3127-3139)
@@ -81,7 +81,9 @@ typedef struct soc_params {
     float   adhoc;             /* ADHOC (1.0)                                                 */
     float   reserved;
     int32_t ndust;             /* NDUST (only read when with_msf != 0)                            */
-    int32_t reserved2[3];
+    int32_t opt_is_half;       /* OPT_IS_HALF: soc_upload(SOC_BUF_OPT) takes IEEE half values (ASOC.py:1155); they are
+                                  widened on the device, the kernels see exactly the half-rounded opacities  */
+    int32_t reserved2[2];
 } soc_params;
 
 /* Device buffers.  Names are those of the reference's kernel arguments. */
@@ -160,6 +162,9 @@ int  soc_sim_cl(soc_context *ctx, int source, int packets, int batch, float seed
  * E->T table.  Emission: reads TNEW, writes EMIT. */
 int  soc_eq_temperature(soc_context *ctx, int level, float adhoc, float kE, float Emin, int NE);
 int  soc_emission(soc_context *ctx, float freq, float fabs);
+/* Emission2 (kernel_ASOC_aux.c:862; ASOC.py:2157-2180, key EBATCH): emission of cells [c0,c1[ at all `nfreq` frequencies from
+ * TNEW in one launch; emit_out[(cell-c0)*nfreq + ifreq] on the host -- the layout of the emitted file. */
+int  soc_emission2(soc_context *ctx, int c0, int c1, int nfreq, const float *freq, const float *fabs, float *emit_out);
 
 /* Device-resident absorbed file (the [CELLS, NFREQ] array of ASOC.py:1482-1497 and its final scaling,
  * ASOC.py:2782-2878): _begin allocates and clears FABS[cells*nfreq] (frequency fastest, the file's layout),

@@ -187,6 +187,14 @@ class Oracle:
         self.L.orc_emission(C.byref(self.P), C.byref(self.G), C.c_float(freq), C.c_float(fabs_), _fp(t), _fp(out))
         return out
 
+    def emission2(self, c0, c1, freq, fabs_, t):
+        t = np.ascontiguousarray(t, np.float32)
+        freq = np.ascontiguousarray(freq, np.float32)
+        fabs_ = np.ascontiguousarray(fabs_, np.float32)
+        out = np.zeros((c1 - c0, len(freq)), np.float32)
+        self.L.orc_emission2(C.byref(self.P), C.c_int(c0), C.c_int(c1), C.c_int(len(freq)), _fp(freq), _fp(fabs_), _fp(t), _fp(out))
+        return out
+
     def mapping(self, map_dx, npx, npy, emit, dir_, ra, de, abs_, sca, centre, intobs=(-1e12, 0, 0), opt=None,
                 save_colden=0):
         m = np.zeros(npx * npy, np.float32)

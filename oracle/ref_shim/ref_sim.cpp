@@ -99,4 +99,8 @@ void ref_emission(int global, float FREQ, float FABS, float *DENS, float *T, flo
     REF_PARALLEL_FOR(global, refk::Emission(FREQ, FABS, DENS, T, EMIT));
 }
 
+void ref_emission2(int global, int c0, int c1, int nfreq, float *FREQ, float *FABS, float *DENS, float *T, float *EMIT) {
+    REF_PARALLEL_FOR(global, refk::Emission2(c0, c1, nfreq, FREQ, FABS, DENS, T, EMIT));
+}
+
 }  // extern "C"

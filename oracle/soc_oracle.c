@@ -715,6 +715,15 @@ void orc_emission(const OrcParams *P, const OrcGrid *G, float freq, float fabs_,
         emit[i] = (2.79639459e-20f * P->factor) * fabs_ * (freq * freq / (expf(4.7995074e-11f * freq / t[i]) - 1.0f)) / P->length;
 }
 
+/* Emission2: kernel_ASOC_aux.c:862-888 -- cells [c0,c1[, all nfreq frequencies, EMIT[(icell-c0)*nfreq+ifreq] */
+void orc_emission2(const OrcParams *P, int c0, int c1, int nfreq, const float *freq, const float *fabs_, const float *t, float *emit) {
+    #pragma omp parallel for
+    for (int icell = c0; icell < c1; icell++)
+        for (int ifreq = 0; ifreq < nfreq; ifreq++)
+            emit[(long)(icell - c0) * nfreq + ifreq] =
+                (2.79639459e-20f * P->factor) * fabs_[ifreq] * (freq[ifreq] * freq[ifreq] / (expf(4.7995074e-11f * freq[ifreq] / t[icell]) - 1.0f)) / P->length;
+}
+
 /* =================================================================================================
  * Map ray-tracer (kernel_ASOC_map.c:496-875; MAP_INTERPOLATION==0, ROI_MAP==0)
  * ================================================================================================= */

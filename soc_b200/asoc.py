@@ -22,7 +22,7 @@ import numpy as np
 from . import backend as bk
 from .constants import FACTOR, PLANCK, PARSEC, ADHOC, SEED0, SEED1, GLOBAL_0, HPBG_NPIX, f2um
 from .fits import write_fits
-from .formats import read_cloud, read_otfile, write_cloud
+from .formats import read_cloud, read_otfile, write_cloud, cut_levels
 from .hostmath import fix, observer_directions_rad, energy_temperature_table, trapezoid_weights
 from .ini import User
 
@@ -117,6 +117,22 @@ def read_sources(USER):
             sys.exit()
         lps[i] = tmp * USER.PS_SCALING[i]
     return lps
+
+
+def read_cloud_cut(USER, comm=None):
+    """Cloud file, cut to the `levels` of the ini file if it has more (ASOC_aux.py:749-762: a new file
+    <cloud>.MAX<levels> is written and used)."""
+    with open(USER.file_cloud, "rb") as fp:
+        levels = int(np.fromfile(fp, np.int32, 5)[3])
+    name = USER.file_cloud
+    if levels > USER.LEVELS:
+        name = '%s.MAX%d' % (USER.file_cloud, USER.LEVELS)
+        if comm is None or comm.rank == 0:
+            print("CUT LEVELS: %s -> %s" % (USER.file_cloud, name))
+            cut_levels(USER.file_cloud, name, USER.LEVELS - 1)
+        if comm is not None:
+            comm.barrier()
+    return read_cloud(name, USER.KDENSITY)
 
 
 def read_abundances(cells, ndust, USER):
@@ -282,10 +298,7 @@ def main(argv=None, device_factory=None):
     FDSC, FCSC = read_scattering_functions(USER)
     IBG = read_background(USER)
     LPS = read_sources(USER)
-    cloud = read_cloud(USER.file_cloud, USER.KDENSITY)
-    if cloud.LEVELS > USER.LEVELS:
-        print("*** soc_b200: keyword levels (cutting the hierarchy) is not implemented")
-        sys.exit()
+    cloud = read_cloud_cut(USER, comm)
     NX, NY, NZ, LEVELS, CELLS, LCELLS, OFF, DENS = cloud.NX, cloud.NY, cloud.NZ, cloud.LEVELS, cloud.CELLS, \
         cloud.LCELLS, cloud.OFF, cloud.DENS
     USER.AREA = cloud.AREA
@@ -357,7 +370,7 @@ def main(argv=None, device_factory=None):
                    sw_a=float("%.3e" % USER.STEP_WEIGHT[1]), sw_b=float("%.3e" % USER.STEP_WEIGHT[2]),
                    level_threshold=USER.LEVEL_THRESHOLD, length=length, factor=FACTOR, adhoc=ADHOC,
                    with_msf=int(WITH_MSF), ndust=NDUST, mirror=mirror_mask(USER),
-                   map_interpolation=USER.MAP_INTERPOLATION)
+                   map_interpolation=USER.MAP_INTERPOLATION, opt_is_half=int(bool(USER.OPT_IS_HALF)))
     dev.set_grid(cloud)
     if WITH_MSF:
         dev.upload(bk.BUF_ABU, np.ascontiguousarray(ABU, np.float32).reshape(-1))
@@ -419,11 +432,19 @@ def main(argv=None, device_factory=None):
     FF_ALL = trapezoid_weights(FFREQ)
 
     def emission_from_temperature(T):
-        """EMITTED[:, f] from temperatures with the Emission kernel (ASOC.py:736-760, 2185-2197)."""
+        """EMITTED[cells, freq] from temperatures.  Default: kernel Emission2 in batches of cells, all frequencies
+        per launch and one contiguous copy per batch (ASOC.py:2157-2180, the reference's EBATCH path); with the
+        key EMISSION1 one launch of kernel Emission and one strided host copy per frequency (ASOC.py:2185-2197)."""
         dev.upload(bk.BUF_TNEW, np.ascontiguousarray(T, np.float32))
-        for ifreq in range(REMIT_I1, REMIT_I2 + 1):
-            dev.emission(float(FFREQ[ifreq]), float(AFABS[0][ifreq]))
-            EMITTED[:, ifreq - REMIT_I1] = dev.download(bk.BUF_EMIT, CELLS, out=TMP)
+        if 'EMISSION1' in USER.KEYS:
+            for ifreq in range(REMIT_I1, REMIT_I2 + 1):
+                dev.emission(float(FFREQ[ifreq]), float(AFABS[0][ifreq]))
+                EMITTED[:, ifreq - REMIT_I1] = dev.download(bk.BUF_EMIT, CELLS, out=TMP)
+            return
+        batch = max(1, min(CELLS, (1 << 28) // max(1, REMIT_NFREQ)))        # <= 1 GiB of floats per launch
+        for a in range(0, CELLS, batch):
+            b = min(a + batch, CELLS)
+            EMITTED[a:b, :] = dev.emission2(a, b, FFREQ[REMIT_I1:REMIT_I2 + 1], AFABS[0][REMIT_I1:REMIT_I2 + 1])
 
     if USER.LOAD_TEMPERATURE and USER.ITERATIONS < 1:
         emission_from_temperature(TNEW)
@@ -452,7 +473,8 @@ def main(argv=None, device_factory=None):
     def set_opacity(ifreq, first=0):
         """Scalar ABS/SCA, or OPT upload for variable abundances.  Returns (abs, sca)."""
         if WITH_ABU:
-            dev.upload(bk.BUF_OPT, _opt_array(USER, ABU, AFABS, AFSCA, ifreq, first).reshape(-1))
+            o = _opt_array(USER, ABU, AFABS, AFSCA, ifreq, first).reshape(-1)
+            dev.upload(bk.BUF_OPT, o, np.float16 if USER.OPT_IS_HALF else np.float32)      # ASOC.py:1155-1158
             return 0.0, 0.0
         return float(sum(a[ifreq] for a in AFABS)), float(sum(s[ifreq] for s in AFSCA))
 

@@ -17,7 +17,7 @@ import numpy as np
 
 from . import backend as bk
 from .asoc import (read_dusts, read_scattering_functions, read_background, read_sources, read_abundances, Comm,
-                   _opt_array, mirror_mask, upload_scattering)
+                   _opt_array, mirror_mask, upload_scattering, read_cloud_cut)
 from .constants import PLANCK, PARSEC, FACTOR, ADHOC, SEED0, SEED1, GLOBAL_0_SCA, HPBG_NPIX
 from .fits import write_fits
 from .formats import read_cloud
@@ -51,7 +51,7 @@ def main(argv=None, device_factory=None):
     FDSC, FCSC = read_scattering_functions(USER)
     IBG = read_background(USER)
     LPS = read_sources(USER)
-    cloud = read_cloud(USER.file_cloud, USER.KDENSITY)
+    cloud = read_cloud_cut(USER, comm)
     NX, NY, NZ, CELLS = cloud.NX, cloud.NY, cloud.NZ, cloud.CELLS
     USER.AREA = cloud.AREA
     ABU = read_abundances(CELLS, NDUST, USER)
@@ -123,7 +123,7 @@ def main(argv=None, device_factory=None):
     dev = (device_factory or bk.Device)(ordinal)
     dev.set_params(bins=USER.DSC_BINS, no_ps=max(1, USER.NO_PS), ps_method=USER.PS_METHOD, with_abu=int(WITH_ABU),
                    ffs=USER.FFS, hpbg_weighted=int(USER.HPBG_WEIGHTED), use_emweight=USER.USE_EMWEIGHT,
-                   with_msf=int(WITH_MSF), ndust=NDUST, mirror=mirror_mask(USER),
+                   with_msf=int(WITH_MSF), ndust=NDUST, mirror=mirror_mask(USER), opt_is_half=int(bool(USER.OPT_IS_HALF)),
                    length=float("%.5e" % (USER.GL * PARSEC)), factor=FACTOR, adhoc=ADHOC)
     dev.set_grid(cloud)
     dev.set_rng_mode(bk.RNG_REFERENCE if 'REFSTREAMS' in USER.KEYS else bk.RNG_PACKET)
@@ -145,7 +145,8 @@ def main(argv=None, device_factory=None):
 
     def opacities(IFREQ):
         if WITH_ABU:
-            dev.upload(bk.BUF_OPT, _opt_array(USER, ABU, AFABS, AFSCA, IFREQ).reshape(-1))
+            o = _opt_array(USER, ABU, AFABS, AFSCA, IFREQ).reshape(-1)
+            dev.upload(bk.BUF_OPT, o, np.float16 if USER.OPT_IS_HALF else np.float32)
             return 0.0, 0.0
         return float(sum(a[IFREQ] for a in AFABS)), float(sum(s_[IFREQ] for s_ in AFSCA))
 

@@ -32,7 +32,7 @@ class SocParams(C.Structure):
         "hpbg_weighted", "ffs", "step_weight", "level_threshold", "with_msf", "mirror", "dir_weight", "do_split",
         "roi_flags", "map_interpolation")] + \
         [(n, C.c_float) for n in ("sw_a", "sw_b", "length", "factor", "adhoc", "reserved")] + \
-        [("ndust", C.c_int32), ("reserved2", C.c_int32 * 3)]
+        [("ndust", C.c_int32), ("opt_is_half", C.c_int32), ("reserved2", C.c_int32 * 2)]
 
 
 class SocCounters(C.Structure):
@@ -42,7 +42,7 @@ class SocCounters(C.Structure):
 
 _EXPORTS = """soc_last_error soc_version soc_create soc_destroy soc_sync soc_set_params soc_set_grid soc_set_rng_mode
 soc_set_shard soc_set_tuning soc_set_geometry soc_set_layout soc_upload soc_download soc_clear soc_device_ptr soc_zero_amc soc_sim_pb soc_sim_hp
-soc_sim_cl soc_absorbed_begin soc_absorbed_add soc_absorbed_finish soc_eq_temperature soc_emission soc_mapping soc_healpix_mapping soc_ps_tau soc_sca_zero_out soc_sca_ps soc_sca_pb soc_sca_hp soc_sca_cl
+soc_sim_cl soc_absorbed_begin soc_absorbed_add soc_absorbed_finish soc_eq_temperature soc_emission soc_emission2 soc_mapping soc_healpix_mapping soc_ps_tau soc_sca_zero_out soc_sca_ps soc_sca_pb soc_sca_hp soc_sca_cl
 soc_get_counters soc_reset_counters soc_last_launch_ms soc_stream""".split()
 
 _lib = None
@@ -86,6 +86,7 @@ def load_library(path=None):
     L.soc_absorbed_add.argtypes = [vp, i]
     L.soc_absorbed_finish.argtypes = [vp, f, f, i, vp]
     L.soc_emission.argtypes = [vp, f, f]
+    L.soc_emission2.argtypes = [vp, i, i, i, vp, vp, vp]
     L.soc_mapping.argtypes = [vp, f, i, i, fp, fp, fp, f, f, fp, fp, i]
     L.soc_healpix_mapping.argtypes = [vp, i, f, f, fp, i]
     L.soc_ps_tau.argtypes = [vp, i, fp, f, f, vp, vp]
@@ -151,6 +152,7 @@ class Device:
         p.sw_a, p.sw_b = kw.get("sw_a", 0.0), kw.get("sw_b", 0.0)
         p.length, p.factor, p.adhoc = kw["length"], kw.get("factor", 1.0e20), kw.get("adhoc", 1.0)
         p.ndust = kw.get("ndust", 1)
+        p.opt_is_half = kw.get("opt_is_half", 0)
         self._ck(self.L.soc_set_params(self.ctx, C.byref(p)))
         self.params = p
 
@@ -241,6 +243,15 @@ class Device:
         col, tau = np.zeros(no, np.float32), np.zeros(no, np.float32)
         self._ck(self.L.soc_ps_tau(self.ctx, no, k[1], abs_, sca, col.ctypes.data, tau.ctypes.data))
         return col, tau
+
+    def emission2(self, c0, c1, freq, fabs_, out=None):
+        fr = np.ascontiguousarray(freq, np.float32)
+        fa = np.ascontiguousarray(fabs_, np.float32)
+        if out is None:
+            out = np.empty((c1 - c0, len(fr)), np.float32)
+        assert out.flags.c_contiguous and out.dtype == np.float32 and out.size == (c1 - c0) * len(fr)
+        self._ck(self.L.soc_emission2(self.ctx, c0, c1, len(fr), fr.ctypes.data, fa.ctypes.data, out.ctypes.data))
+        return out
 
     def sca_zero_out(self, ndir, npx, npy):
         self._ck(self.L.soc_sca_zero_out(self.ctx, ndir, npx, npy))
@@ -375,6 +386,11 @@ class Backend:
         self.dev.sync()
         self.dev.emission(freq, fabs_)
         return self.dev.download(BUF_EMIT, self.n)
+
+    def emission2(self, c0, c1, freq, fabs_, t):
+        self.dev.upload(BUF_TNEW, t)
+        self.dev.sync()
+        return self.dev.emission2(c0, c1, freq, fabs_)
 
     def mapping(self, map_dx, npx, npy, emit, dir_, ra, de, abs_, sca, centre, intobs=(-1e12, 0, 0), opt=None,
                 save_colden=0):

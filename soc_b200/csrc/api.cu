@@ -41,6 +41,7 @@ struct soc_context {
     DevBuf buf[SOC_BUF_COUNT];
     unsigned long long *counters;      // device: packets, steps, scatterings, stuck, peels, work, -, -
     float *acc; size_t acc_bytes;      // per-launch scratch accumulator of the stream kernels (all zero between launches)
+    void *scratch; size_t scratch_bytes;   // temporary device array of soc_emission2
     float *dens_brick;                 // regular grids with even dimensions: DENS in 2x2x2-brick order (lean kernel)
     int layout;                        // 1 = use the bricked copy where the kernel supports it
     int pend;                          // 1 = merged deposits (vector reds) in the lean kernel
@@ -130,6 +131,7 @@ int soc_destroy(soc_context *c) {
     cudaFree(c->counters);
     if (c->acc) cudaFree(c->acc);
     if (c->dens_brick) cudaFree(c->dens_brick);
+    if (c->scratch) cudaFree(c->scratch);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -243,6 +245,20 @@ int soc_upload(soc_context *c, int b, const void *host, size_t nbytes) {
     NEED_CTX(c);
     if (b == SOC_BUF_DENS || b == SOC_BUF_PAR) return fail(SOC_ERR_ARG, "soc_upload: %s is set by soc_set_grid", buf_name(b));
     if (host == nullptr && nbytes) return fail(SOC_ERR_ARG, "soc_upload(%s): null host pointer", buf_name(b));
+    if (b == SOC_BUF_OPT && c->have_params && c->P.opt_is_half && nbytes) {          // half values in, float on the device
+        if (c->scratch_bytes < nbytes) {
+            if (c->scratch) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->scratch)); c->scratch = nullptr; c->scratch_bytes = 0; }
+            CU(cudaMalloc(&c->scratch, nbytes));
+            c->scratch_bytes = nbytes;
+        }
+        int r = ensure(c, b, 2 * nbytes);
+        if (r != SOC_OK) return r;
+        CU(cudaMemcpyAsync(c->scratch, host, nbytes, cudaMemcpyHostToDevice, c->stream));
+        launch_half_to_float(c->scratch, dptr<float>(c, b), (long long)(nbytes / 2), c->stream);
+        c->launches++;
+        CU(cudaGetLastError());
+        return SOC_OK;
+    }
     int r = ensure(c, b, nbytes);
     if (r != SOC_OK) return r;
     if (nbytes) CU(cudaMemcpyAsync(c->buf[b].ptr, host, nbytes, cudaMemcpyHostToDevice, c->stream));
@@ -543,6 +559,30 @@ int soc_emission(soc_context *c, float freq, float fabs_) {
     launch_emission(c->G.cells, freq, fabs_, c->P.factor, c->P.length, dptr<float>(c, SOC_BUF_TNEW), dptr<float>(c, SOC_BUF_EMIT), c->stream);
     c->launches++;
     CU(cudaGetLastError());
+    return SOC_OK;
+}
+
+int soc_emission2(soc_context *c, int c0, int c1, int nfreq, const float *freq, const float *fabs_, float *emit_out) {
+    NEED_CTX(c);
+    if (!c->have_grid || !c->have_params) return fail(SOC_ERR_STATE, "soc_emission2: grid and params first");
+    if (c0 < 0 || c1 <= c0 || c1 > c->G.cells || nfreq < 1 || !freq || !fabs_ || !emit_out) return fail(SOC_ERR_ARG, "soc_emission2: bad arguments");
+    int r;
+    if ((r = need(c, SOC_BUF_TNEW, (size_t)c->G.cells * 4, "soc_emission2")) != SOC_OK) return r;
+    const size_t nb = (size_t)(c1 - c0) * nfreq * 4;
+    if (c->scratch_bytes < nb + 2 * (size_t)nfreq * 4) {
+        if (c->scratch) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->scratch)); c->scratch = nullptr; c->scratch_bytes = 0; }
+        CU(cudaMalloc(&c->scratch, nb + 2 * (size_t)nfreq * 4));
+        c->scratch_bytes = nb + 2 * (size_t)nfreq * 4;
+    }
+    float *d_emit = reinterpret_cast<float *>(c->scratch);
+    float *d_freq = d_emit + (size_t)(c1 - c0) * nfreq, *d_fabs = d_freq + nfreq;
+    CU(cudaMemcpyAsync(d_freq, freq, (size_t)nfreq * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_fabs, fabs_, (size_t)nfreq * 4, cudaMemcpyHostToDevice, c->stream));
+    launch_emission2(c0, c1, nfreq, c->P.factor, c->P.length, d_freq, d_fabs, dptr<float>(c, SOC_BUF_TNEW), d_emit, c->stream);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(emit_out, d_emit, nb, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     return SOC_OK;
 }
 

@@ -4,6 +4,7 @@
 //   Emission       kernel_ASOC_aux.c:793-807   modified black body emission of every cell at one frequency
 // All three stream through the cell arrays once (grid-stride, coalesced).
 #include "aux.cuh"
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -41,6 +42,17 @@ __global__ void emission_kernel(int cells, float freq, float fabs_, float factor
                                 const float *__restrict__ t, float *__restrict__ emit) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += gridDim.x * blockDim.x)
         emit[i] = (2.79639459e-20f * factor) * fabs_ * (freq * freq / (expf(4.7995074e-11f * freq / t[i]) - 1.0f)) / length;
+}
+
+// Emission2 (kernel_ASOC_aux.c:862-888): cells [c0,c1[ x nfreq frequencies in one pass, EMIT[(icell-c0)*nfreq + ifreq] -- the
+// layout of the emitted file, written coalesced (one thread per element)
+__global__ void emission2_kernel(int c0, long long total, int nfreq, float factor, float length, const float *__restrict__ freq,
+                                 const float *__restrict__ fabs_, const float *__restrict__ t, float *__restrict__ emit) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int icell = c0 + (int)(e / nfreq), ifreq = (int)(e % nfreq);
+        const float f = freq[ifreq];
+        emit[e] = (2.79639459e-20f * factor) * fabs_[ifreq] * (f * f / (expf(4.7995074e-11f * f / t[icell]) - 1.0f)) / length;
+    }
 }
 
 // FABS[cell, ifreq] += INT[cell]: coalesced read, one 4-byte write per cell row of the [cells, nfreq] array
@@ -90,4 +102,22 @@ void launch_absorbed_add(float *fabs, const float *inten, int cells, int nfreq, 
 }
 void launch_absorbed_scale(const GridDesc &G, float *fabs, int nfreq, float coeff0, float nnnlimit, cudaStream_t stream) {
     absorbed_scale_kernel<<<grid_for((long long)G.cells * nfreq, 256), 256, 0, stream>>>(G, fabs, nfreq, coeff0, nnnlimit);
+}
+
+void launch_emission2(int c0, int c1, int nfreq, float factor, float length, const float *freq, const float *fabs_, const float *t,
+                      float *emit, cudaStream_t stream) {
+    const long long total = (long long)(c1 - c0) * nfreq;
+    long long b = (total + 255) / 256;
+    const long long cap = 148LL * 16;
+    emission2_kernel<<<(int)(b < 1 ? 1 : (b > cap ? cap : b)), 256, 0, stream>>>(c0, total, nfreq, factor, length, freq, fabs_, t, emit);
+}
+
+// OPT_IS_HALF: widen the uploaded half-precision opacities (vload_half in the reference, kernel_ASOC_aux.c:12-16)
+__global__ void half_to_float_kernel(const __half *__restrict__ src, float *__restrict__ dst, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = __half2float(src[i]);
+}
+void launch_half_to_float(const void *src, float *dst, long long n, cudaStream_t stream) {
+    long long b = (n + 255) / 256;
+    const long long cap = 148LL * 16;
+    half_to_float_kernel<<<(int)(b < 1 ? 1 : (b > cap ? cap : b)), 256, 0, stream>>>(reinterpret_cast<const __half *>(src), dst, n);
 }

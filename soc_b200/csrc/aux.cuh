@@ -9,3 +9,6 @@ void launch_emission(int cells, float freq, float fabs_, float factor, float len
                      cudaStream_t stream);
 void launch_absorbed_add(float *fabs, const float *inten, int cells, int nfreq, int ifreq, cudaStream_t stream);
 void launch_absorbed_scale(const GridDesc &G, float *fabs, int nfreq, float coeff0, float nnnlimit, cudaStream_t stream);
+void launch_emission2(int c0, int c1, int nfreq, float factor, float length, const float *freq, const float *fabs_, const float *t,
+                      float *emit, cudaStream_t stream);
+void launch_half_to_float(const void *src, float *dst, long long n, cudaStream_t stream);

@@ -85,6 +85,31 @@ def read_cloud(filename, kdensity=1.0):
     return Cloud(nx, ny, nz, lcells, np.concatenate(parts))
 
 
+def cut_levels(infile, outfile, maxlevel):
+    """Write a copy of a hierarchy file without the levels > maxlevel (0, 1, ...): parent cells of the removed
+    levels become leaves holding the plain average of their eight children (OT_cut_levels, ASOC_aux.py:651-713 with
+    kernel AverageParent, kernel_OT_tools.c:5-22; float32 sum in child order, then / 8)."""
+    with open(infile, "rb") as fp:
+        nx, ny, nz, levels, cells = np.fromfile(fp, np.int32, 5)
+        H = []
+        for _ in range(levels):
+            n = int(np.fromfile(fp, np.int32, 1)[0])
+            H.append(np.fromfile(fp, np.float32, n))
+    maxlevel = min(levels - 1, maxlevel)
+    for i in range(levels - 2, maxlevel - 1, -1):
+        par = np.nonzero(H[i] <= 1.0e-9)[0]
+        first = (-H[i][par]).view(np.int32)
+        acc = np.zeros(len(par), np.float32)
+        for k in range(8):
+            acc = acc + H[i + 1][first + k]
+        H[i][par] = acc / np.float32(8.0)
+    with open(outfile, "wb") as fp:
+        np.asarray([nx, ny, nz, maxlevel + 1, sum(len(h) for h in H[:maxlevel + 1])], np.int32).tofile(fp)
+        for h in H[:maxlevel + 1]:
+            np.asarray([len(h)], np.int32).tofile(fp)
+            np.asarray(h, np.float32).tofile(fp)
+
+
 def read_otfile(filename):
     """Hierarchy file -> flat value vector (ASOC_aux.py:1420-1442)."""
     with open(filename, "rb") as fp:

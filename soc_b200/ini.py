@@ -385,8 +385,6 @@ class User:
             bad.append("mapping ... fast: fast / per-level maps are not implemented")
         if self.USE_EMWEIGHT > 1:
             bad.append("emweight 2 is not implemented")
-        if self.OPT_IS_HALF:
-            bad.append("optishalf: half-precision opacities are not implemented")
         if self.LIB_ABS or self.LIB_MAPS:
             bad.append("libabs/libmaps: the library method is not implemented")
         if self.ABSTHIN > 1:

@@ -44,7 +44,7 @@ class OracleDevice:
         p = dict(self.params)
         length = p.pop("length")
         bins = p.pop("bins", 2500)
-        for k in ("factor", "adhoc", "dir_weight", "do_split", "roi_flags"):
+        for k in ("factor", "adhoc", "dir_weight", "do_split", "roi_flags", "opt_is_half"):
             p.pop(k, None)
         # the drivers are compared with the library's production kernels: exact mirror / scattering position
         self.O = orc.Oracle(self.cloud, gl=0.01, bins=bins, mirror_exact=1, sca_exact_level=1, **p)
@@ -88,7 +88,7 @@ class OracleDevice:
         if b in self._ACC:
             getattr(self.O, self._ACC[b])[:] = np.asarray(array, np.float32)
         else:
-            self.buf[b] = np.array(array, dtype).reshape(-1).copy()
+            self.buf[b] = np.array(array, dtype).reshape(-1).astype(np.float32 if dtype == np.float16 else dtype)
         return array
 
     def download(self, b, n, dtype=np.float32, out=None):
@@ -173,6 +173,13 @@ class OracleDevice:
 
     def emission(self, freq, fabs_):
         self.buf[bk.BUF_EMIT] = self.O.emission(freq, fabs_, self.buf[bk.BUF_TNEW])
+
+    def emission2(self, c0, c1, freq, fabs_, out=None):
+        e = self.O.emission2(c0, c1, freq, fabs_, self.buf[bk.BUF_TNEW])
+        if out is None:
+            return e
+        out[...] = e
+        return out
 
     def mapping(self, map_dx, npx, npy, dir_, ra, de, abs_, sca, centre, intobs, save_colden):
         m, t = self.O.mapping(map_dx, npx, npy, self.buf[bk.BUF_EMIT], dir_, ra, de, abs_, sca, centre, intobs=intobs,

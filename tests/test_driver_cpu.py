@@ -160,3 +160,22 @@ def test_scattered_light_fits_cube(tmp_path):
     _run_asocs(tmp_path)
     hdr, cube = read_fits(str(tmp_path / "scat.fits"))
     assert cube.shape == (8, 8, 8) and hdr["NAXIS3"] == 8 and np.isfinite(cube).all() and cube[4:].max() > 0
+
+
+def test_levels_keyword_cuts_the_hierarchy(tmp_path):
+    """`levels 2` on a 3-level cloud: <cloud>.MAX2 is written with the removed octets averaged into their parents
+    (ASOC_aux.py:749-762, kernel_OT_tools.c:5-22) and the run uses it."""
+    from soc_b200.formats import read_cloud
+    cloud = _run(tmp_path, n=6, octree=True, bgpac=20000, maps=False, extra="levels 2\n")
+    cut = read_cloud(str(tmp_path / "model.cloud.MAX2"))
+    assert cloud.LEVELS == 3 and cut.LEVELS == 2 and cut.CELLS == cloud.LCELLS[0] + cloud.LCELLS[1]
+    assert (cut.DENS[cut.OFF[1]:] > 0).all()                       # former parents of level 1 are leaves now
+    lv1 = cloud.DENS[cloud.OFF[1]:cloud.OFF[2]]
+    par = np.nonzero(lv1 <= 0)[0]
+    first = (-lv1[par]).view(np.int32)
+    lv2 = cloud.DENS[cloud.OFF[2]:]
+    want = np.array([lv2[f:f + 8].astype(np.float32).sum(dtype=np.float32) / np.float32(8) for f in first])
+    got = cut.DENS[cut.OFF[1]:][par]
+    assert np.allclose(got, want, rtol=1e-6)
+    T = read_otfile(str(tmp_path / "model.T"))
+    assert T.shape == (cut.CELLS,)

@@ -103,6 +103,48 @@ def test_maps_match_oracle_and_golden(name):
     B.close()
 
 
+def test_half_precision_opacities():
+    """OPT_IS_HALF: the uploaded half values are widened on the device; the run equals a float run on the same
+    half-rounded opacities bit for bit (same streams, same arithmetic)."""
+    from soc_b200 import backend
+    cloud = synth.regular_cloud(12)
+    rng = np.random.default_rng(5)
+    k = 0.1
+    opt = np.empty((cloud.CELLS, 2), np.float32)
+    opt[:, 0] = k * (1.0 + rng.random(cloud.CELLS))
+    opt[:, 1] = k * (1.5 + 2 * rng.random(cloud.CELLS))
+    dsc, csc = synth.hg_tables(0.6)
+    glob = 8 * cloud.AREA
+    res = []
+    for half in (1, 0):
+        B = _backend(cloud, backend.RNG_PACKET, with_abu=1, opt_is_half=half)
+        o16 = opt.reshape(-1).astype(np.float16)
+        B.dev.upload(backend.BUF_OPT, o16 if half else o16.astype(np.float32), np.float16 if half else np.float32)
+        B.zero(0)
+        B.sim_pb(glob, 1, glob * 2, 2, 0.3, 1.0, 1.0, dsc=dsc, csc=csc)
+        res.append(B.tabs.astype(np.float64))
+        B.close()
+    assert res[0].sum() > 0 and np.abs(res[0] - res[1]).max() <= 1e-5 * res[1].max()
+
+
+def test_emission2_matches_oracle():
+    """Emission2 (cells x frequencies in one launch) against the oracle restatement (pinned to the reference kernel)."""
+    from oracle import orc
+    from soc_b200 import backend
+    cloud = synth.octree_cloud(6, 3, refine_fraction=0.2, seed=3)
+    rng = np.random.default_rng(2)
+    t = (5.0 + 40.0 * rng.random(cloud.CELLS)).astype(np.float32)
+    freq = np.logspace(11.5, 14.5, 9).astype(np.float32)
+    fabs_ = (1e-6 * (freq / 1e12) ** 1.8).astype(np.float32)
+    a = orc.Oracle(cloud).emission2(17, cloud.CELLS - 5, freq, fabs_, t)
+    B = _backend(cloud, backend.RNG_PACKET)
+    b = B.emission2(17, cloud.CELLS - 5, freq, fabs_, t)
+    B.close()
+    assert a.shape == b.shape == (cloud.CELLS - 22, 9)
+    ok = a > 0
+    assert (b[~ok] == 0).all() and np.abs(b[ok] / a[ok] - 1.0).max() < 2e-5       # expf differs in the last bits
+
+
 def _repeat(X, runner_factory, K, key="tabs"):
     outs = []
     for k in range(K):

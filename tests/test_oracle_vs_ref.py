@@ -63,3 +63,16 @@ def test_step_counter_matches_atomic_count():
     R.atomic_count(reset=True)          # the shared object (and its counter) may have been used before
     run(O), run(R)
     assert O.counters.steps == R.atomic_count()
+
+
+def test_emission2_matches_reference():
+    """Emission2 (kernel_ASOC_aux.c:862): oracle == reference kernel."""
+    make, opts, _ = CASES["bg_oct8_3"]
+    cloud = make()
+    O, R = orc.Oracle(cloud, **opts), ref.Reference(cloud, **opts)
+    rng = np.random.default_rng(2)
+    t = (5.0 + 40.0 * rng.random(cloud.CELLS)).astype(np.float32)
+    freq = np.logspace(11.5, 14.5, 9).astype(np.float32)
+    fabs_ = (1e-6 * (freq / 1e12) ** 1.8).astype(np.float32)
+    a, b = O.emission2(30, cloud.CELLS - 9, freq, fabs_, t), R.emission2(30, cloud.CELLS - 9, freq, fabs_, t)
+    assert a.shape == b.shape and np.array_equal(a, b)
