@@ -331,7 +331,7 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": packets / (ems * 1e-3), "unit": "packets/s", "h2d_bytes_per_step": 2 * BINS * 4,
                     "d2h_bytes_per_step": 4 * n, "ms_per_step": ems / args.steps},
-            "gpu_launches": 2 * args.steps,
+            "gpu_launches": int(c.launches) * world,          # counted by the library: 2 packet kernels + 2 folds per step and rank
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
                          "kernel": "sim_lean_kernel<DEP_RED,%s> (background launch)" % ("brick" if os.environ.get("SOC_LAYOUT", "1") != "0" else "linear"),

@@ -73,7 +73,8 @@ typedef struct soc_params {
                                   DSC / CSC of ndust*bins entries (kernel_ASOC.c:777-794)        */
     int32_t mirror;            /* MIRROR bit mask: 1 x=0, 2 x=NX, 4 y=0, 8 y=NY, 16 z=0, 32 z=NZ are reflecting borders
                                   (ASOC.py:319-321, kernel_ASOC_aux.c:1054)                      */
-    int32_t dir_weight, do_split, roi_flags;   /* must be 0                                      */
+    int32_t dir_weight, do_split;              /* must be 0                                      */
+    int32_t roi_flags;         /* 1 WITH_ROI_LOAD, 2 WITH_ROI_SAVE, 4 ROI_MAP; geometry through soc_set_roi()     */
     int32_t map_interpolation; /* MAP_INTERPOLATION 0,1,2 (kernel_ASOC_map.c:656-811)            */
     float   sw_a, sw_b;        /* SW_A, SW_B                                                  */
     float   length;            /* LENGTH = GL*PARSEC rounded as "%.5e" (ASOC.py:347,356)      */
@@ -95,6 +96,8 @@ enum soc_buffer {
     SOC_BUF_TNEW, SOC_BUF_FABS,
     SOC_BUF_ABU,               /* WITH_MSF: abundances [CELLS*NDUST], dust index fastest        */
     SOC_BUF_ABSV, SOC_BUF_SCAV, /* WITH_MSF: the ABS / SCA kernel arguments as vectors [NDUST]  */
+    SOC_BUF_ROI_LOAD,          /* WITH_ROI_LOAD: external field [elements * 12*ROI_NSIDE^2] of one frequency */
+    SOC_BUF_ROI_SAVE,          /* WITH_ROI_SAVE: photons entering ROI [elements * 12*ROI_NSIDE^2]           */
     SOC_BUF_COUNT
 };
 
@@ -125,6 +128,12 @@ int  soc_sync(soc_context *ctx);
 int  soc_set_params(soc_context *ctx, const soc_params *p);
 int  soc_set_grid(soc_context *ctx, int32_t nx, int32_t ny, int32_t nz, int32_t levels, int64_t cells,
                   const int32_t *lcells, const int32_t *off, const float *dens);
+/* Region of interest (ASOC.py:906-945; kernel_ASOC.c:44-51, 141-179, 469-502, 615-643; kernel_ASOC_aux.c:1031):
+ * roi = [x0,x1,y0,y1,z0,z1] inclusive root-cell limits, roi_step = subdivision of a root cell on the ROI surface,
+ * roi_nside = Healpix NSIDE of the stored directions, roi_dim = dimensions (nx,ny,nz) of the file loaded with
+ * WITH_ROI_LOAD.  Which of the three ROI options are active is soc_params.roi_flags.  With WITH_ROI_SAVE the buffer
+ * SOC_BUF_ROI_SAVE is (re)allocated and cleared here; soc_sim_pb(source = 3) reads SOC_BUF_ROI_LOAD. */
+int  soc_set_roi(soc_context *ctx, const int32_t roi[6], int roi_step, int roi_nside, const int32_t roi_dim[3]);
 int  soc_set_rng_mode(soc_context *ctx, int mode);
 int  soc_set_shard(soc_context *ctx, int rank, int world);
 /* Accumulation engine of the absorption counters: deposit_mode 0 = one red.global.add.f32 per lane and step,

@@ -57,8 +57,9 @@ def macro_flags(cfg):
     add("-DAREA=%.0f" % area)
     add("-DNO_PS=%d" % max(1, cfg.get("NO_PS", 1)))
     add("-DWITH_ABU=%d" % cfg.get("WITH_ABU", 0))
-    add("-DROI_MAP=0"); add("-DMAX_SPLIT=4300"); add("-DSELEM=0")
-    add("-DROI_STEP=0"); add("-DROI_NSIDE=16"); add("-DWITH_ROI_LOAD=0"); add("-DWITH_ROI_SAVE=0")
+    add("-DROI_MAP=%d" % cfg.get("ROI_MAP", 0)); add("-DMAX_SPLIT=4300"); add("-DSELEM=0")
+    add("-DROI_STEP=%d" % cfg.get("ROI_STEP", 0)); add("-DROI_NSIDE=%d" % cfg.get("ROI_NSIDE", 16))
+    add("-DWITH_ROI_LOAD=%d" % cfg.get("WITH_ROI_LOAD", 0)); add("-DWITH_ROI_SAVE=%d" % cfg.get("WITH_ROI_SAVE", 0))
     add("-DAXY=%.5ff" % (nx * ny / area)); add("-DAXZ=%.5ff" % (nx * nz / area)); add("-DAYZ=%.5ff" % (ny * nz / area))
     add("-DLEVELS=%d" % cfg["LEVELS"])
     add("-DLENGTH=%.5ef" % (gl * PARSEC))
@@ -89,7 +90,7 @@ def tag_of(cfg):
     keys = ["NX", "NY", "NZ", "LEVELS", "CELLS"]
     opt = ["NO_PS", "PS_METHOD", "WITH_ABU", "NOABSORBED", "SAVE_INTENSITY", "USE_EMWEIGHT", "WITH_ALI",
            "HPBG_WEIGHTED", "FFS", "BINS", "MAP_NSIDE", "STEP_WEIGHT", "MIRROR", "MAP_INTERPOLATION",
-           "LEVEL_THRESHOLD", "GL", "WITH_MSF", "NDUST"]
+           "LEVEL_THRESHOLD", "GL", "WITH_MSF", "NDUST", "ROI_MAP", "ROI_STEP", "ROI_NSIDE", "WITH_ROI_LOAD", "WITH_ROI_SAVE"]
     s = "_".join(str(cfg[k]) for k in keys)
     for k in opt:
         if k in cfg:

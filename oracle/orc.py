@@ -27,7 +27,9 @@ class OrcParams(C.Structure):
         "nx", "ny", "nz", "levels", "cells", "bins", "no_ps", "ps_method", "with_abu", "with_ali", "noabsorbed",
         "save_intensity", "use_emweight", "hpbg_weighted", "ffs", "step_weight", "level_threshold", "sca_exact_level")] + \
         [(n, C.c_float) for n in ("sw_a", "sw_b", "length", "factor", "adhoc", "reserved1")] + \
-        [(n, C.c_int32) for n in ("with_msf", "ndust", "mirror", "map_interpolation", "hg_test", "mirror_exact", "r2b", "r2c")]
+        [(n, C.c_int32) for n in ("with_msf", "ndust", "mirror", "map_interpolation", "hg_test", "mirror_exact", "r2b", "r2c",
+                                  "with_roi_load", "with_roi_save", "roi_map", "roi_step", "roi_nside")] + \
+        [("roi", C.c_int32 * 6), ("roi_dim", C.c_int32 * 3)]
 
 
 class OrcGrid(C.Structure):
@@ -38,7 +40,8 @@ class OrcSimBufs(C.Structure):
     _fields_ = [(n, c_fp) for n in ("tabs", "xab", "intens", "intx", "inty", "intz", "emit", "emwei", "opt",
                                     "dsc", "csc")] + \
         [("abs", C.c_float), ("sca", C.c_float), ("pspos", c_fp), ("ps", c_fp), ("xps_nside", c_ip),
-         ("xps_side", c_ip), ("xps_area", c_fp), ("hpbg", c_fp), ("hpbgp", c_fp), ("abu", c_fp), ("abs_v", c_fp),
+         ("xps_side", c_ip), ("xps_area", c_fp), ("hpbg", c_fp), ("hpbgp", c_fp), ("roi_load", c_fp), ("roi_save", c_fp),
+         ("abu", c_fp), ("abs_v", c_fp),
          ("sca_v", c_fp)]
 
 
@@ -100,6 +103,16 @@ class Oracle:
         P.with_msf, P.ndust, P.mirror = opts.get("with_msf", 0), opts.get("ndust", 1), opts.get("mirror", 0)
         P.map_interpolation = opts.get("map_interpolation", 0)
         P.hg_test = opts.get("hg_test", 0)
+        P.with_roi_load, P.with_roi_save = opts.get("with_roi_load", 0), opts.get("with_roi_save", 0)
+        P.roi_map, P.roi_step, P.roi_nside = opts.get("roi_map", 0), opts.get("roi_step", 0), opts.get("roi_nside", 16)
+        for k, v in enumerate(opts.get("roi", [0] * 6)):
+            P.roi[k] = int(v)
+        for k, v in enumerate(opts.get("roi_dim", [1, 1, 1])):
+            P.roi_dim[k] = int(v)
+        self.roi_save = None
+        if P.with_roi_save:
+            nx, ny, nz = [(P.roi[2 * k + 1] - P.roi[2 * k] + 1) * P.roi_step for k in range(3)]
+            self.roi_save = np.zeros((nx * ny + ny * nz + nz * nx) * 12 * P.roi_nside ** 2, np.float32)
         P.mirror_exact = opts.get("mirror_exact", 0)
         P.length = float("%.5e" % (gl * 3.08567758e+18))     # -D LENGTH=%.5ef (ASOC.py:347,356)
         P.factor = 1.0e20
@@ -122,7 +135,8 @@ class Oracle:
         self._keep = []
 
     def _bufs(self, abs_=0.0, sca=0.0, dsc=None, csc=None, emit=None, emwei=None, opt=None, pspos=None, ps=None,
-              xps_nside=None, xps_side=None, xps_area=None, hpbg=None, hpbgp=None, abu=None, abs_v=None, sca_v=None):
+              xps_nside=None, xps_side=None, xps_area=None, hpbg=None, hpbgp=None, abu=None, abs_v=None, sca_v=None,
+              roi_load=None):
         def f(a):
             if a is None:
                 return None
@@ -147,6 +161,7 @@ class Oracle:
         B.xps_nside, B.xps_side, B.xps_area = _ip(i(xps_nside)), _ip(i(xps_side)), _fp(f(xps_area))
         B.hpbg, B.hpbgp = _fp(f(hpbg)), _fp(f(hpbgp))
         B.abu, B.abs_v, B.sca_v = _fp(f(abu)), _fp(f(abs_v)), _fp(f(sca_v))
+        B.roi_load, B.roi_save = _fp(f(roi_load)), _fp(self.roi_save)
         return B
 
     def zero(self, tag):

@@ -28,7 +28,12 @@ class Reference:
     def __init__(self, cloud, gl=0.01, bins=2500, map_nside=None, **opts):
         cfg = dict(NX=cloud.NX, NY=cloud.NY, NZ=cloud.NZ, LEVELS=cloud.LEVELS, CELLS=cloud.CELLS, BINS=bins, GL=gl)
         for k, v in opts.items():
+            if k in ("roi", "roi_dim"):          # run-time arrays, not macros
+                continue
             cfg[k.upper()] = v
+        self.roi = np.ascontiguousarray(opts.get("roi", [0] * 6), np.int32)
+        self.roi_dim = np.ascontiguousarray(opts.get("roi_dim", [1, 1, 1]), np.int32)
+        self.roi_save = None
         if map_nside is not None:
             cfg["MAP_NSIDE"] = map_nside
         path = build_ref.build(cfg)
@@ -89,6 +94,16 @@ class Reference:
         self._keep.append(a)
         return _ip(a)
 
+    def _roi_save(self):
+        """ROI_SAVE accumulates over launches like a device buffer; sized from ROI, ROI_STEP, ROI_NSIDE."""
+        if not self.opts.get("with_roi_save", 0):
+            return _fp(self._d)
+        if self.roi_save is None:
+            st, r = self.opts["roi_step"], self.roi
+            nx, ny, nz = [(int(r[2 * k + 1]) - int(r[2 * k]) + 1) * st for k in range(3)]
+            self.roi_save = np.zeros((nx * ny + ny * nz + nz * nx) * 12 * self.opts.get("roi_nside", 16) ** 2, np.float32)
+        return _fp(self.roi_save)
+
     def _as(self, abs_, sca, abs_v, sca_v):
         """ABS / SCA kernel arguments: one float each, or [NDUST] vectors with WITH_MSF."""
         if abs_v is not None:
@@ -97,7 +112,7 @@ class Reference:
 
     def sim_pb(self, global_, source, packets, batch, seed, bg, tw, abs_=0.0, sca=0.0, dsc=None, csc=None, emit=None,
                emwei=None, opt=None, pspos=None, ps=None, xps_nside=None, xps_side=None, xps_area=None, abu=None,
-               abs_v=None, sca_v=None, **_):
+               abs_v=None, sca_v=None, roi_load=None, **_):
         self._keep = []
         a, s = self._as(abs_, sca, abs_v, sca_v)
         self.L.ref_sim_pb(C.c_int(global_), C.c_int(source), C.c_int(packets), C.c_int(batch), C.c_float(seed),
@@ -105,7 +120,8 @@ class Reference:
                           _ip(self.lcells), _ip(self.off), _ip(self.par), _fp(self.dens), self._f(emit),
                           _fp(self.tabs), self._f(dsc), self._f(csc), _fp(self.xab), self._f(emwei),
                           _fp(self.int_), _fp(self.intx), _fp(self.inty), _fp(self.intz), self._f(opt),
-                          self._f(abu), self._i(xps_nside), self._i(xps_side), self._f(xps_area))
+                          self._f(abu), self._i(xps_nside), self._i(xps_side), self._f(xps_area), _ip(self.roi_dim),
+                          self._f(roi_load), _ip(self.roi), self._roi_save())
 
     def sim_hp(self, global_, packets, batch, seed, tw, abs_=0.0, sca=0.0, dsc=None, csc=None, opt=None, hpbg=None,
                hpbgp=None, abu=None, abs_v=None, sca_v=None, **_):
@@ -125,7 +141,7 @@ class Reference:
                           _fp(s), C.c_float(tw), _ip(self.lcells), _ip(self.off), _ip(self.par), _fp(self.dens),
                           self._f(emit), _fp(self.tabs), self._f(dsc), self._f(csc), _fp(self.xab), self._f(emwei),
                           _fp(self.int_), _fp(self.intx), _fp(self.inty), _fp(self.intz), _ip(self._di),
-                          self._f(opt), self._f(abu))
+                          self._f(opt), self._f(abu), _ip(self.roi), self._roi_save())
 
     def eq_temperature(self, level, adhoc, kE, Emin, NE, ttt, emit, tnew):
         ttt = np.ascontiguousarray(ttt, np.float32)
@@ -160,7 +176,7 @@ class Reference:
         self.L.ref_mapping(C.c_int(glob), C.c_float(map_dx), C.c_int(npx), C.c_int(npy), _fp(m), _fp(emit),
                            _fp(v[0]), _fp(v[1]), _fp(v[2]), _ip(self.lcells), _ip(self.off), _ip(self.par),
                            _fp(self.dens), C.c_float(abs_), C.c_float(sca), _fp(v[3]), _fp(v[4]), self._f(opt),
-                           _fp(t), C.c_int(save_colden))
+                           _fp(t), C.c_int(save_colden), _ip(self.roi))
         return m.reshape(npy, npx), t.reshape(npy, npx)
 
     def healpix_mapping(self, nside, emit, abs_, sca, intobs, opt=None, save_colden=0):
@@ -173,7 +189,7 @@ class Reference:
         self.L.ref_healpix_mapping(C.c_int(n), C.c_float(1.0), C.c_int(nside), C.c_int(0), _fp(m), _fp(emit),
                                    _fp(z), _fp(z), _fp(z), _ip(self.lcells), _ip(self.off), _ip(self.par),
                                    _fp(self.dens), C.c_float(abs_), C.c_float(sca), _fp(z), _fp(io), self._f(opt),
-                                   _fp(t), C.c_int(save_colden))
+                                   _fp(t), C.c_int(save_colden), _ip(self.roi))
         return m, t
 
     def ps_tau(self, pspos, dir_, abs_, sca, opt=None):
@@ -214,7 +230,8 @@ class Reference:
         return self._shape(out, ndir, npx, npy)
 
     def sca_pb(self, global_, source, packets, batch, seed, bg, ndir, npx, npy, map_dx, centre, odirs, ora, ode,
-               abs_=0.0, sca=0.0, dsc=None, csc=None, opt=None, pspos=None, ps=None, abu=None, abs_v=None, sca_v=None, **_):
+               abs_=0.0, sca=0.0, dsc=None, csc=None, opt=None, pspos=None, ps=None, abu=None, abs_v=None, sca_v=None,
+               roi_load=None, **_):
         self._keep = []
         a, s = self._as(abs_, sca, abs_v, sca_v)
         out = self._out(ndir, npx, npy)
@@ -224,7 +241,7 @@ class Reference:
                           _ip(self.off), _ip(self.par), _fp(self.dens), self._f(dsc), self._f(csc), C.c_int(ndir),
                           self._v3(odirs), C.c_int(npx), C.c_int(npy), C.c_float(map_dx), _fp(ce), self._v3(ora),
                           self._v3(ode), _fp(out), self._f(abu), self._f(opt), _fp(self._d), _fp(self._d),
-                          _fp(self._d))
+                          _fp(self._d), _ip(self.roi_dim), self._f(roi_load))
         return self._shape(out, ndir, npx, npy)
 
     def sca_hp(self, global_, packets, batch, seed, ndir, npx, npy, map_dx, centre, odirs, ora, ode, abs_=0.0,

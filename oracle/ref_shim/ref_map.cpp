@@ -13,25 +13,33 @@ extern "C" {
 void ref_mapping(int global, float MAP_DX, int npx, int npy, float *MAP, float *EMIT, const float *DIR,
                  const float *RA, const float *DE, const int *LCELLS, const int *OFF, int *PAR, float *DENS,
                  float ABS, float SCA, const float *CENTRE, const float *INTOBS, float *OPT, float *SAVETAU,
-                 int SAVE_COLDEN) {
+                 int SAVE_COLDEN, const int *ROI) {
     int2 NPIX(npx, npy);
     float3 d(DIR[0], DIR[1], DIR[2]), ra(RA[0], RA[1], RA[2]), de(DE[0], DE[1], DE[2]);
     float3 c(CENTRE[0], CENTRE[1], CENTRE[2]), io(INTOBS[0], INTOBS[1], INTOBS[2]);
     REF_PARALLEL_FOR(global,
         refm::Mapping(MAP_DX, NPIX, MAP, EMIT, d, ra, de, LCELLS, OFF, PAR, DENS, ABS, SCA, c, io, OPT, SAVETAU,
-                      SAVE_COLDEN));
+                      SAVE_COLDEN
+#if (ROI_MAP>0)
+                      , ROI
+#endif
+                      ));
 }
 
 void ref_healpix_mapping(int global, float MAP_DX, int npx, int npy, float *MAP, float *EMIT, const float *DIR,
                          const float *RA, const float *DE, const int *LCELLS, const int *OFF, int *PAR, float *DENS,
                          float ABS, float SCA, const float *CENTRE, const float *INTOBS, float *OPT,
-                         float *SAVETAU, int SAVE_COLDEN) {
+                         float *SAVETAU, int SAVE_COLDEN, const int *ROI) {
     int2 NPIX(npx, npy);
     float3 d(DIR[0], DIR[1], DIR[2]), ra(RA[0], RA[1], RA[2]), de(DE[0], DE[1], DE[2]);
     float3 c(CENTRE[0], CENTRE[1], CENTRE[2]), io(INTOBS[0], INTOBS[1], INTOBS[2]);
     REF_PARALLEL_FOR(global,
         refm::HealpixMapping(MAP_DX, NPIX, MAP, EMIT, d, ra, de, LCELLS, OFF, PAR, DENS, ABS, SCA, c, io, OPT,
-                             SAVETAU, SAVE_COLDEN));
+                             SAVETAU, SAVE_COLDEN
+#if (ROI_MAP>0)
+                             , ROI
+#endif
+                             ));
 }
 
 void ref_pstau(int global, int no, const float *PSPOS_xyz, const float *DIR, const float *RA, const float *DE,

@@ -30,11 +30,9 @@ void ref_sca_pb(int global, int SOURCE, int PACKETS, int BATCH, float SEED, floa
                 float *PSPOS_xyz, float *PS, const int *LCELLS, const int *OFF, int *PAR, float *DENS,
                 const float *DSC, const float *CSC, int NDIR, float *ODIRS_xyz, int npx, int npy, float MAP_DX,
                 const float *CENTRE, float *ORA_xyz, float *ODE_xyz, float *OUT, float *ABU, float *OPT,
-                float *XPS_NSIDE, float *XPS_SIDE, float *XPS_AREA) {
+                float *XPS_NSIDE, float *XPS_SIDE, float *XPS_AREA, const int *roi_dim, float *roi_load) {
     int2 NPIX(npx, npy);
     float3 c(CENTRE[0], CENTRE[1], CENTRE[2]);
-    static const int roi_dim[3] = {1, 1, 1};
-    static float roi_load[1] = {0.0f};
     REF_PARALLEL_FOR(global,
         refs::SimRAM_PB(SOURCE, PACKETS, BATCH, SEED, ABS, SCA, BG, (float3 *)PSPOS_xyz, PS, LCELLS, OFF, PAR, DENS,
                         DSC, CSC, NDIR, (float3 *)ODIRS_xyz, NPIX, MAP_DX, c, (float3 *)ORA_xyz, (float3 *)ODE_xyz,

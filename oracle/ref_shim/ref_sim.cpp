@@ -62,11 +62,20 @@ void ref_sim_pb(int global, int SOURCE, int PACKETS, int BATCH, float SEED, floa
                 float *PSPOS_xyz, float *PS, float TW, const int *LCELLS, const int *OFF, int *PAR, float *DENS,
                 float *EMIT, float *TABS, const float *DSC, const float *CSC, float *XAB, float *EMWEI,
                 float *INT, float *INTX, float *INTY, float *INTZ, float *OPT, float *ABU,
-                int *XPS_NSIDE, int *XPS_SIDE, float *XPS_AREA) {
+                int *XPS_NSIDE, int *XPS_SIDE, float *XPS_AREA, const int *ROI_DIM, float *ROI_LOAD, const int *ROI,
+                float *ROI_SAVE) {
+    // WITH_ROI_LOAD / WITH_ROI_SAVE append arguments to the kernel (kernel_ASOC.c:44-51)
     REF_PARALLEL_FOR(global,
         refk::SimRAM_PB(SOURCE, PACKETS, BATCH, SEED, ABS, SCA, BG, (float3 *)PSPOS_xyz, PS, TW, LCELLS, OFF, PAR,
                         DENS, EMIT, TABS, DSC, CSC, XAB, EMWEI, INT, INTX, INTY, INTZ, OPT, ABU,
-                        XPS_NSIDE, XPS_SIDE, XPS_AREA));
+                        XPS_NSIDE, XPS_SIDE, XPS_AREA
+#if (WITH_ROI_LOAD)
+                        , ROI_DIM, ROI_LOAD
+#endif
+#if (WITH_ROI_SAVE)
+                        , ROI, ROI_SAVE
+#endif
+                        ));
     flush_counter();
 }
 
@@ -83,10 +92,14 @@ void ref_sim_hp(int global, int PACKETS, int BATCH, float SEED, float *ABS, floa
 void ref_sim_cl(int global, int SOURCE, int PACKETS, int BATCH, float SEED, float *ABS, float *SCA, float TW,
                 const int *LCELLS, const int *OFF, int *PAR, float *DENS, float *EMIT, float *TABS,
                 const float *DSC, const float *CSC, float *XAB, float *EMWEI, float *INT, float *INTX, float *INTY,
-                float *INTZ, int *EMINDEX, float *OPT, float *ABU) {
+                float *INTZ, int *EMINDEX, float *OPT, float *ABU, const int *ROI, float *ROI_SAVE) {
     REF_PARALLEL_FOR(global,
         refk::SimRAM_CL(SOURCE, PACKETS, BATCH, SEED, ABS, SCA, TW, LCELLS, OFF, PAR, DENS, EMIT, TABS, DSC, CSC,
-                        XAB, EMWEI, INT, INTX, INTY, INTZ, EMINDEX, OPT, ABU));
+                        XAB, EMWEI, INT, INTX, INTY, INTZ, EMINDEX, OPT, ABU
+#if (WITH_ROI_SAVE)
+                        , ROI, ROI_SAVE
+#endif
+                        ));
     flush_counter();
 }
 

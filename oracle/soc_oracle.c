@@ -205,6 +205,43 @@ static void root_pos(const nav_t *N, v3 *p, int level, int ind) {
     }
 }
 
+static inline void addf(float *p, float v);
+/* InRoi(): kernel_ASOC_aux.c:1031-1048 -- root cell index if the cell lies inside ROI, else -1 */
+static int in_roi(const nav_t *N, const int32_t *ROI, int level, int ind) {
+    int i = ind, k = level, j;
+    while (k > 0) { i = N->par[N->off[k] + i - N->nxyz]; k--; }
+    k = i / (N->nx * N->ny);
+    j = (i / N->nx) % N->ny;
+    if ((i % N->nx) >= ROI[0] && (i % N->nx) <= ROI[1] && j >= ROI[2] && j <= ROI[3] && k >= ROI[4] && k <= ROI[5]) return i;
+    return -1;
+}
+/* a packet has stepped into ROI: add it to ROI_SAVE[surface element, direction pixel] (kernel_ASOC.c:617-642, 1510-1535) */
+static void roi_save_add(const OrcParams *P, const nav_t *N, float *roi_save, v3 pos, v3 dir, int level, int ind, float photons) {
+    const int32_t *ROI = P->roi;
+    const int RNX = (ROI[1] - ROI[0] + 1) * P->roi_step, RNY = (ROI[3] - ROI[2] + 1) * P->roi_step, RNZ = (ROI[5] - ROI[4] + 1) * P->roi_step;
+    const float st = (float)P->roi_step;
+    int ii = 0, jj;
+    v3 R = pos;
+    root_pos(N, &R, level, ind);
+    if (R.x < (ROI[0] + 1.0e-3f) || R.x > (ROI[1] + 0.999f)) {
+        ii = clampi((int)floorf((R.y - ROI[2]) * st), 0, RNY - 1); jj = clampi((int)floorf((R.z - ROI[4]) * st), 0, RNZ - 1);
+        ii = ii + RNY * jj;
+    }
+    if (R.y < (ROI[2] + 1.0e-3f) || R.y > (ROI[3] + 0.999f)) {
+        ii = clampi((int)floorf((R.x - ROI[0]) * st), 0, RNX - 1); jj = clampi((int)floorf((R.z - ROI[4]) * st), 0, RNZ - 1);
+        ii = RNY * RNZ + ii + RNX * jj;
+    }
+    if (R.z < (ROI[4] + 1.0e-3f) || R.z > (ROI[5] + 0.999f)) {
+        ii = clampi((int)floorf((R.x - ROI[0]) * st), 0, RNX - 1); jj = clampi((int)floorf((R.y - ROI[2]) * st), 0, RNY - 1);
+        ii = RNY * RNZ + RNX * RNZ + ii + RNX * jj;
+    }
+    float theta = acosf(dir.z), phi = atan2f(dir.y, dir.x);
+    jj = orc_ang2pix_ring(P->roi_nside, phi, theta);
+    ii = clampi(ii, 0, RNX * RNY + RNY * RNZ + RNZ * RNX - 1);
+    jj = clampi(jj, 0, 12 * P->roi_nside * P->roi_nside - 1);
+    addf(&roi_save[(long)ii * 12 * P->roi_nside * P->roi_nside + jj], photons);
+}
+
 /* Surface(): kernel_ASOC_aux.c:912-940 */
 static void surface(const nav_t *N, v3 *p, const v3 *d) {
     float dx, dy, dz;
@@ -391,9 +428,13 @@ static void propagate(sim_t *S, rng_t *r, v3 pos, v3 dir, int level, int ind, fl
     int scatterings = 0, oind = 0, ind0 = -1, level0 = 0;
     float tau, dtau, tauA, ds, dx, delta, kabs, ksca;
     v3 pos0 = pos;
+    const int rsave = S->P->with_roi_save > 0;
+    int roi = -1, oroi = -1;
+    if (rsave && ind >= 0) roi = oroi = in_roi(N, S->P->roi, level, ind);       /* kernel_ASOC.c:550, 1439 */
     while (ind >= 0) {
         tau = 0.0f;
         while (ind >= 0) {
+            oroi = roi;
             oind = N->off[level] + ind; ind0 = ind; level0 = level; pos0 = pos;
             ds = get_step(N, &pos, &dir, &level, &ind);
             cell_opacity(S, oind, &kabs, &ksca);
@@ -404,6 +445,10 @@ static void propagate(sim_t *S, rng_t *r, v3 pos, v3 dir, int level, int ind, fl
             deposit(S, oind, delta, &dir, e_index);
             photons *= expf(-tauA);
             tau += dtau;
+            if (rsave) {                                                   /* only at the end of a full step, :615-643 */
+                roi = (ind >= 0 || level == 0) ? in_roi(N, S->P->roi, level, ind) : -1;
+                if (roi >= 0 && oroi < 0) roi_save_add(S->P, N, S->B->roi_save, pos, dir, level, ind, photons);
+            }
             if (kind == 0 && level == level0 && ind == ind0) {             /* kernel_ASOC.c:649-665 */
                 pos.x += S_PEPS * dir.x; pos.y += S_PEPS * dir.y; pos.z += S_PEPS * dir.z;
             }
@@ -440,8 +485,46 @@ static void propagate(sim_t *S, rng_t *r, v3 pos, v3 dir, int level, int ind, fl
     }
 }
 
+/* ROI background (SOURCE==3, WITH_ROI_LOAD): 100 work items per surface element of the loaded file, `packets` =
+ * number of surface elements, batch = multiple of the Healpix pixel count (kernel_ASOC.c:97-179, 469-502; the same
+ * code in kernel_ASOC_sca.c:530-612, 812-845) */
+typedef struct { int ielem, iside; float rd, dx, dy, x0; } roi_src_t;
+static void roi_src_init(const OrcParams *P, int id, int packets, int batch, roi_src_t *r) {
+    const int32_t *RD = P->roi_dim;
+    int iside;
+    r->ielem = id % packets; iside = r->ielem;
+    r->rd = P->nx / ((float)RD[0]);
+    r->dx = r->dy = 0.0f;
+    if (iside < RD[1] * RD[2]) { r->dx = ((iside % RD[1]) + 0.5f) * r->rd; r->dy = ((iside / RD[1]) + 0.5f) * r->rd; iside = 0; }
+    else { iside -= RD[1] * RD[2];
+    if (iside < RD[0] * RD[2]) { r->dx = ((iside % RD[0]) + 0.5f) * r->rd; r->dy = ((iside / RD[0]) + 0.5f) * r->rd; iside = 1; }
+    else { iside -= RD[0] * RD[2];
+    if (iside < RD[0] * RD[1]) { r->dx = ((iside % RD[0]) + 0.5f) * r->rd; r->dy = ((iside / RD[0]) + 0.5f) * r->rd; iside = 2; } } }
+    r->iside = iside;
+    r->x0 = (float)(P->roi_nside * P->roi_nside * 12.0 / (100.0 * batch));
+}
+/* returns 0 when the direction pixel is empty (no packet, no random numbers) */
+static int roi_src_emit(const OrcParams *P, const OrcSimBufs *B, const nav_t *N, const roi_src_t *r, rng_t *rng, int III,
+                        v3 *pos, v3 *dir, int *level, int *ind, float *photons) {
+    const int npix = 12 * P->roi_nside * P->roi_nside, NX = P->nx, NY = P->ny, NZ = P->nz;
+    const float rd = r->rd;
+    *ind = III % npix;
+    *photons = r->x0 * B->roi_load[(long)r->ielem * npix + *ind];
+    if (*photons <= 0.0f) return 0;
+    float v1, v2;
+    orc_pix2ang_ring(P->roi_nside, *ind, &v1, &v2);
+    v1 += (rnd(rng) - 0.5f) * 0.05f;
+    v2 += (rnd(rng) - 0.5f) * 0.05f;
+    dir->x = sinf(v2) * cosf(v1); dir->y = sinf(v2) * sinf(v1); dir->z = cosf(v2);
+    if (r->iside == 0) { pos->y = r->dx + (-0.49f + 0.98f * rnd(rng)) * rd; pos->z = r->dy + (-0.49f + 0.98f * rnd(rng)) * rd; pos->x = (dir->x > 0.0f) ? S_PEPS : (NX - S_PEPS); }
+    if (r->iside == 1) { pos->x = r->dx + (-0.49f + 0.98f * rnd(rng)) * rd; pos->z = r->dy + (-0.49f + 0.98f * rnd(rng)) * rd; pos->y = (dir->y > 0.0f) ? S_PEPS : (NY - S_PEPS); }
+    if (r->iside == 2) { pos->x = r->dx + (-0.49f + 0.98f * rnd(rng)) * rd; pos->y = r->dy + (-0.49f + 0.98f * rnd(rng)) * rd; pos->z = (dir->z > 0.0f) ? S_PEPS : (NZ - S_PEPS); }
+    index_g(N, pos, level, ind);
+    return 1;
+}
+
 /* ---- SimRAM_PB: one work item (kernel_ASOC.c:15-824) ------------------------------------------ */
-static void pb_item(sim_t *S, int id, int source, int batch, float seed, float bg) {
+static void pb_item(sim_t *S, int id, int source, int packets, int batch, float seed, float bg) {
     const OrcParams *P = S->P; const OrcSimBufs *B = S->B; const nav_t *N = &S->N;
     const int NX = P->nx, NY = P->ny, NZ = P->nz;
     const int AREA = 2 * (NX * NY + NY * NZ + NZ * NX);
@@ -450,7 +533,9 @@ static void pb_item(sim_t *S, int id, int source, int batch, float seed, float b
     float X0 = 0, Y0 = 0, Z0 = 0, DX = 1, DY = 1, DZ = 1, photons = 0.0f;
     v3 pos = { 0, 0, 0 }, dir = { 0, 0, 0 };
     if (source == 1 && id >= 8 * AREA) return;
-    if (source == 3) return;
+    if (source == 3 && !(P->with_roi_load > 0)) return;
+    roi_src_t rs;
+    if (source == 3) { if (id >= 100 * packets) return; roi_src_init(P, id, packets, batch, &rs); }
     if (source == 1) {                                                       /* kernel_ASOC.c:109-138 */
         ind = id % AREA;
         if (ind < NY * NZ) { side = 0; X0 = S_PEPS; Y0 = ind % NY; Z0 = ind / NY; DX = 0.0f; }
@@ -553,6 +638,7 @@ static void pb_item(sim_t *S, int id, int source, int batch, float seed, float b
             photons = bg;
             index_g(N, &pos, &level, &ind);
         }
+        if (source == 3 && !roi_src_emit(P, B, N, &rs, &rng, III, &pos, &dir, &level, &ind, &photons)) continue;   /* :469-502 */
         dir_fix(&dir);
         float free_path = sample_free_path(P, &rng, &photons);
         S->c.packets++;
@@ -571,7 +657,7 @@ void orc_sim_pb(const OrcParams *P, const OrcGrid *G, const OrcSimBufs *B, int g
         sim_t S; S.P = P; S.B = B; S.N = nav_make(P, G); S.tw = tw;
         S.use_int = (P->save_intensity == 1 || P->save_intensity == 2 || P->noabsorbed == 0);
         memset(&S.c, 0, sizeof(S.c));
-        pb_item(&S, id, source, batch, seed, bg);
+        pb_item(&S, id, source, packets, batch, seed, bg);
         np += S.c.packets; ns += S.c.steps; nsc += S.c.scatterings;
     }
     if (C) { C->packets += np; C->steps += ns; C->scatterings += nsc; }
@@ -865,7 +951,8 @@ static void map_pixel(const OrcParams *P, const nav_t *N, int id, float map_dx, 
         }
         if (P->with_abu) DTAU = sx * dens * (opt[2 * (long)oind] + opt[2 * (long)oind + 1]);
         else             DTAU = sx * dens * (sca_ + abs_);
-        if (P->level_threshold <= 0 || olevel >= P->level_threshold) {
+        if ((P->level_threshold <= 0 || olevel >= P->level_threshold) &&
+            (P->roi_map <= 0 || in_roi(N, P->roi, olevel, oind - N->off[olevel]) >= 0)) {   /* ROI_MAP: kernel_ASOC_map.c:37-56, 822 */
             if (DTAU < 1.0e-3f) PHOTONS += expf(-TAU) * (1.0f - 0.5f * DTAU) * sx * em * dens;
             else                PHOTONS += expf(-TAU) * ((1.0f - expf(-DTAU)) / DTAU) * sx * em * dens;
         }
@@ -963,10 +1050,12 @@ void orc_healpix_mapping(const OrcParams *P, const OrcGrid *G, int nside, float 
         index_g_map(&N, &POS, &level, &ind);
         while (ind >= 0) {
             oind = N.off[level] + ind;
+            const int olevel = level;
             dx = get_step_map(&N, &POS, &TMP, &level, &ind);
             if (P->with_abu) DTAU = dx * N.dens[oind] * (opt[2 * (long)oind] + opt[2 * (long)oind + 1]);
             else             DTAU = dx * N.dens[oind] * (sca_ + abs_);
-            if (DTAU < 1.0e-3f) PHOTONS += expf(-TAU) * (1.0f - 0.5f * DTAU) * dx * emit[oind] * N.dens[oind];
+            if (P->roi_map > 0 && in_roi(&N, P->roi, olevel, oind - N.off[olevel]) < 0) ;        /* ROI_MAP, kernel_ASOC_map.c:947-957 */
+            else if (DTAU < 1.0e-3f) PHOTONS += expf(-TAU) * (1.0f - 0.5f * DTAU) * dx * emit[oind] * N.dens[oind];
             else                PHOTONS += expf(-TAU) * ((1.0f - expf(-DTAU)) / DTAU) * dx * emit[oind] * N.dens[oind];
             TAU += DTAU;
             colden += dx * N.dens[oind];
@@ -1170,15 +1259,17 @@ void orc_sca_ps(const OrcParams *P, const OrcGrid *G, const OrcSimBufs *B, const
 
 void orc_sca_pb(const OrcParams *P, const OrcGrid *G, const OrcSimBufs *B, const OrcScaBufs *O, int global,
                 int source, int packets, int batch, float seed, float bg, OrcCounters *C) {
-    (void)packets;
     const int NX = P->nx, NY = P->ny, NZ = P->nz;
     const int AREA = 2 * (NX * NY + NY * NZ + NZ * NX);
     uint64_t np = 0, ns = 0, nsc = 0, npl = 0;
     #pragma omp parallel for schedule(runtime) reduction(+:np,ns,nsc,npl)
     for (int id = 0; id < global; id++) {
         if (source == 1 && id >= 8 * AREA) continue;
+        if (source == 3 && (!(P->with_roi_load > 0) || id >= 100 * packets)) continue;
         sca_t S; S.P = P; S.B = B; S.O = O; S.N = nav_make(P, G); memset(&S.c, 0, sizeof(S.c));
         rng_t rng; rng_seed(&rng, seed, (uint64_t)id);
+        roi_src_t rs;
+        if (source == 3) roi_src_init(P, id, packets, batch, &rs);
         int ind = -1, level = 0, side = 0;
         float X0 = 0, Y0 = 0, Z0 = 0, DX = 1, DY = 1, DZ = 1, photons = 0.0f;
         v3 pos = { 0, 0, 0 }, dir = { 0, 0, 0 };
@@ -1216,6 +1307,7 @@ void orc_sca_pb(const OrcParams *P, const OrcGrid *G, const OrcSimBufs *B, const
                 photons = bg;
                 index_g(&S.N, &pos, &level, &ind);
             }
+            if (source == 3 && !roi_src_emit(P, B, &S.N, &rs, &rng, III, &pos, &dir, &level, &ind, &photons)) continue;
             dir_fix(&dir);
             S.c.packets++;
             sca_propagate(&S, &rng, pos, dir, level, ind, photons, 1);

@@ -16,7 +16,8 @@ LIB_PATH = os.path.join(HERE, "_lib", "libsoc_b200.so")
 
 (BUF_DENS, BUF_PAR, BUF_TABS, BUF_XAB, BUF_INT, BUF_INTX, BUF_INTY, BUF_INTZ, BUF_EMIT, BUF_EMWEI, BUF_OPT, BUF_DSC,
  BUF_CSC, BUF_PSPOS, BUF_PS, BUF_XPS_NSIDE, BUF_XPS_SIDE, BUF_XPS_AREA, BUF_HPBG, BUF_HPBGP, BUF_MAP, BUF_SAVETAU,
- BUF_OUT, BUF_ODIR, BUF_ORA, BUF_ODE, BUF_TTT, BUF_TNEW, BUF_FABS, BUF_ABU, BUF_ABSV, BUF_SCAV, BUF_COUNT) = range(33)
+ BUF_OUT, BUF_ODIR, BUF_ORA, BUF_ODE, BUF_TTT, BUF_TNEW, BUF_FABS, BUF_ABU, BUF_ABSV, BUF_SCAV, BUF_ROI_LOAD,
+ BUF_ROI_SAVE, BUF_COUNT) = range(35)
 
 RNG_REFERENCE, RNG_PACKET = 0, 1
 DEP_RED, DEP_WARP, DEP_TILE = 0, 1, 2
@@ -41,7 +42,7 @@ class SocCounters(C.Structure):
 
 
 _EXPORTS = """soc_last_error soc_version soc_create soc_destroy soc_sync soc_set_params soc_set_grid soc_set_rng_mode
-soc_set_shard soc_set_tuning soc_set_geometry soc_set_layout soc_upload soc_download soc_clear soc_device_ptr soc_zero_amc soc_sim_pb soc_sim_hp
+soc_set_shard soc_set_tuning soc_set_geometry soc_set_layout soc_set_roi soc_upload soc_download soc_clear soc_device_ptr soc_zero_amc soc_sim_pb soc_sim_hp
 soc_sim_cl soc_absorbed_begin soc_absorbed_add soc_absorbed_finish soc_eq_temperature soc_emission soc_emission2 soc_mapping soc_healpix_mapping soc_ps_tau soc_sca_zero_out soc_sca_ps soc_sca_pb soc_sca_hp soc_sca_cl
 soc_get_counters soc_reset_counters soc_last_launch_ms soc_stream""".split()
 
@@ -70,6 +71,7 @@ def load_library(path=None):
     L.soc_set_tuning.argtypes = [vp, i, i, i]
     L.soc_set_geometry.argtypes = [vp, i]
     L.soc_set_layout.argtypes = [vp, i]
+    L.soc_set_roi.argtypes = [vp, vp, i, i, vp]
     L.soc_upload.argtypes = [vp, i, vp, C.c_size_t]
     L.soc_download.argtypes = [vp, i, vp, C.c_size_t]
     L.soc_clear.argtypes = [vp, i, C.c_size_t]
@@ -148,7 +150,9 @@ class Device:
         p.use_emweight, p.hpbg_weighted = kw.get("use_emweight", 0), kw.get("hpbg_weighted", 0)
         p.ffs, p.step_weight, p.level_threshold = kw.get("ffs", 1), kw.get("step_weight", -1), kw.get("level_threshold", 0)
         p.with_msf, p.mirror, p.dir_weight = kw.get("with_msf", 0), kw.get("mirror", 0), kw.get("dir_weight", 0)
-        p.do_split, p.roi_flags, p.map_interpolation = kw.get("do_split", 0), kw.get("roi_flags", 0), kw.get("map_interpolation", 0)
+        roi_flags = kw.get("roi_flags", 1 * int(kw.get("with_roi_load", 0) > 0) + 2 * int(kw.get("with_roi_save", 0) > 0) +
+                           4 * int(kw.get("roi_map", 0) > 0))
+        p.do_split, p.roi_flags, p.map_interpolation = kw.get("do_split", 0), roi_flags, kw.get("map_interpolation", 0)
         p.sw_a, p.sw_b = kw.get("sw_a", 0.0), kw.get("sw_b", 0.0)
         p.length, p.factor, p.adhoc = kw["length"], kw.get("factor", 1.0e20), kw.get("adhoc", 1.0)
         p.ndust = kw.get("ndust", 1)
@@ -175,6 +179,11 @@ class Device:
 
     def set_geometry(self, mode):
         self._ck(self.L.soc_set_geometry(self.ctx, int(mode)))
+
+    def set_roi(self, roi, roi_step=0, roi_nside=16, roi_dim=(1, 1, 1)):
+        r = np.ascontiguousarray(roi, np.int32)
+        d = np.ascontiguousarray(roi_dim, np.int32)
+        self._ck(self.L.soc_set_roi(self.ctx, r.ctypes.data, int(roi_step), int(roi_nside), d.ctypes.data))
 
     def set_layout(self, mode):
         self._ck(self.L.soc_set_layout(self.ctx, int(mode)))
@@ -300,6 +309,8 @@ class Backend:
         length = float("%.5e" % (gl * 3.08567758e+18))           # -D LENGTH=%.5ef (ASOC.py:347,356)
         self.dev.set_params(bins=bins, length=length, **opts)
         self.dev.set_grid(cloud)
+        if self.dev.params.roi_flags:
+            self.dev.set_roi(opts.get("roi", [0] * 6), opts.get("roi_step", 0), opts.get("roi_nside", 16), opts.get("roi_dim", (1, 1, 1)))
         self.dev.set_rng_mode(rng_mode)
         self.bins = bins
         self.n = cloud.CELLS
@@ -339,6 +350,11 @@ class Backend:
         return self._get(BUF_INTZ) if self.save2 else np.zeros(self.n, np.float32)
 
     @property
+    def roi_save(self):
+        ptr, nbytes = self.dev.device_ptr(BUF_ROI_SAVE)
+        return self.dev.download(BUF_ROI_SAVE, nbytes // 4)
+
+    @property
     def counters(self):
         return self.dev.counters()
 
@@ -350,7 +366,8 @@ class Backend:
                      emwei=(BUF_EMWEI, np.float32), opt=(BUF_OPT, np.float32), pspos=(BUF_PSPOS, np.float32),
                      ps=(BUF_PS, np.float32), xps_nside=(BUF_XPS_NSIDE, np.int32), xps_side=(BUF_XPS_SIDE, np.int32),
                      xps_area=(BUF_XPS_AREA, np.float32), hpbg=(BUF_HPBG, np.float32), hpbgp=(BUF_HPBGP, np.float32),
-                     abu=(BUF_ABU, np.float32), abs_v=(BUF_ABSV, np.float32), sca_v=(BUF_SCAV, np.float32))
+                     abu=(BUF_ABU, np.float32), abs_v=(BUF_ABSV, np.float32), sca_v=(BUF_SCAV, np.float32),
+                     roi_load=(BUF_ROI_LOAD, np.float32))
         for k, v in bufs.items():
             if v is None:
                 continue

@@ -52,13 +52,14 @@ struct soc_context {
     int rng_mode, rank, world;
     int deposit, refill, agg_steps, geometry, sc_batch, nav_hops;
     int fabs_nfreq;
+    RoiDesc roi; bool have_roi;
     uint64_t pow2k[26];
 };
 
 static const char *buf_name(int b) {
     static const char *n[SOC_BUF_COUNT] = { "DENS", "PAR", "TABS", "XAB", "INT", "INTX", "INTY", "INTZ", "EMIT", "EMWEI",
         "OPT", "DSC", "CSC", "PSPOS", "PS", "XPS_NSIDE", "XPS_SIDE", "XPS_AREA", "HPBG", "HPBGP", "MAP", "SAVETAU", "OUT",
-        "ODIR", "ORA", "ODE", "TTT", "TNEW", "FABS", "ABU", "ABSV", "SCAV" };
+        "ODIR", "ORA", "ODE", "TTT", "TNEW", "FABS", "ABU", "ABSV", "SCAV", "ROI_LOAD", "ROI_SAVE" };
     return (b >= 0 && b < SOC_BUF_COUNT) ? n[b] : "?";
 }
 
@@ -148,8 +149,9 @@ int soc_sync(soc_context *c) {
 int soc_set_params(soc_context *c, const soc_params *p) {
     NEED_CTX(c);
     if (p == nullptr) return fail(SOC_ERR_ARG, "soc_set_params: null");
-    if (p->dir_weight || p->do_split || p->roi_flags)
-        return fail(SOC_ERR_UNSUPPORTED, "soc_set_params: DIR_WEIGHT / DO_SPLIT / ROI are not implemented");
+    if (p->dir_weight || p->do_split)
+        return fail(SOC_ERR_UNSUPPORTED, "soc_set_params: DIR_WEIGHT / DO_SPLIT are not implemented");
+    if (p->roi_flags < 0 || p->roi_flags > 7) return fail(SOC_ERR_ARG, "soc_set_params: roi_flags=%d", p->roi_flags);
     if (p->with_msf && (!p->with_abu || p->ndust < 1))
         return fail(SOC_ERR_ARG, "soc_set_params: WITH_MSF needs WITH_ABU and NDUST >= 1 (ASOC.py:1167)");
     if (p->mirror < 0 || p->mirror > 63) return fail(SOC_ERR_ARG, "soc_set_params: MIRROR=%d", p->mirror);
@@ -202,6 +204,49 @@ int soc_set_grid(soc_context *c, int32_t nx, int32_t ny, int32_t nz, int32_t lev
     }
     CU(cudaGetLastError());
     c->have_grid = true;
+    return SOC_OK;
+}
+
+static size_t roi_elems(const int n[3]) { return (size_t)n[0] * n[1] + (size_t)n[1] * n[2] + (size_t)n[2] * n[0]; }
+
+int soc_set_roi(soc_context *c, const int32_t roi[6], int roi_step, int roi_nside, const int32_t roi_dim[3]) {
+    NEED_CTX(c);
+    if (!c->have_params || !c->have_grid) return fail(SOC_ERR_STATE, "soc_set_roi: grid and params first");
+    if (roi == nullptr || roi_nside < 1 || roi_nside > 1024) return fail(SOC_ERR_ARG, "soc_set_roi: bad arguments");
+    const int flags = c->P.roi_flags;
+    memset(&c->roi, 0, sizeof(c->roi));
+    c->roi.flags = flags; c->roi.step = roi_step; c->roi.nside = roi_nside;
+    for (int k = 0; k < 6; k++) c->roi.lim[k] = roi[k];
+    for (int k = 0; k < 3; k++) c->roi.dim[k] = roi_dim ? roi_dim[k] : 1;
+    if (flags & 6) {
+        const int dim[3] = { c->G.nx, c->G.ny, c->G.nz };
+        for (int k = 0; k < 3; k++)
+            if (roi[2 * k] < 0 || roi[2 * k + 1] >= dim[k] || roi[2 * k] > roi[2 * k + 1]) return fail(SOC_ERR_ARG, "soc_set_roi: limits outside the root grid");
+    }
+    if (flags & 1) { if (!roi_dim || roi_dim[0] < 1 || roi_dim[1] < 1 || roi_dim[2] < 1) return fail(SOC_ERR_ARG, "soc_set_roi: ROI_DIM"); }
+    if (flags & 2) {
+        if (roi_step < 1) return fail(SOC_ERR_ARG, "soc_set_roi: ROI_STEP=%d", roi_step);
+        const int n[3] = { (roi[1] - roi[0] + 1) * roi_step, (roi[3] - roi[2] + 1) * roi_step, (roi[5] - roi[4] + 1) * roi_step };
+        int r = soc_clear(c, SOC_BUF_ROI_SAVE, roi_elems(n) * 12 * roi_nside * roi_nside * 4);
+        if (r != SOC_OK) return r;
+    }
+    c->have_roi = true;
+    return SOC_OK;
+}
+
+// RoiDesc with the device pointers, checked against the options in force
+static int roi_args(soc_context *c, RoiDesc &R, bool need_load, const char *who) {
+    memset(&R, 0, sizeof(R));
+    if (!c->P.roi_flags) return SOC_OK;
+    if (!c->have_roi) return fail(SOC_ERR_STATE, "%s: soc_set_roi first (roi_flags=%d)", who, c->P.roi_flags);
+    R = c->roi;
+    R.load = dptr<float>(c, SOC_BUF_ROI_LOAD); R.save = dptr<float>(c, SOC_BUF_ROI_SAVE);
+    const size_t npix = (size_t)12 * R.nside * R.nside * 4;
+    if (need_load) {
+        int r = need(c, SOC_BUF_ROI_LOAD, roi_elems(R.dim) * npix, who);
+        if (r != SOC_OK) return r;
+    }
+    if ((R.flags & 2) && R.save == nullptr) return fail(SOC_ERR_STATE, "%s: ROI_SAVE buffer missing", who);
     return SOC_OK;
 }
 
@@ -351,6 +396,9 @@ static int sim_common(soc_context *c, SimArgs &A, int kind, int batch, float see
     }
     A.abu = dptr<float>(c, SOC_BUF_ABU); A.scav = dptr<float>(c, SOC_BUF_SCAV);
     A.with_msf = P.with_msf; A.ndust = P.with_msf ? P.ndust : 1; A.mirror = P.mirror;
+    if ((r = roi_args(c, A.roi, kind == SIM_ROI, who)) != SOC_OK) return r;
+    A.roi.flags &= 3;
+    if (kind == SIM_HP) A.roi.flags &= ~2;                     // SimRAM_HP has no ROI_SAVE (kernel_ASOC.c:831-854)
     A.tabs = dptr<float>(c, SOC_BUF_TABS); A.xab = dptr<float>(c, SOC_BUF_XAB);
     A.inten = dptr<float>(c, SOC_BUF_INT); A.intx = dptr<float>(c, SOC_BUF_INTX);
     A.inty = dptr<float>(c, SOC_BUF_INTY); A.intz = dptr<float>(c, SOC_BUF_INTZ);
@@ -422,11 +470,21 @@ static int sim_launch(soc_context *c, SimArgs &A, const char *who) {
 int soc_sim_pb(soc_context *c, int source, int packets, int batch, float seed, float abs, float sca, float bg, float tw, int global) {
     NEED_CTX(c);
     (void)packets;
-    if (source != 0 && source != 1) return fail(SOC_ERR_UNSUPPORTED, "soc_sim_pb: SOURCE=%d (ROI loading is not implemented)", source);
+    if (source != 0 && source != 1 && source != 3) return fail(SOC_ERR_ARG, "soc_sim_pb: SOURCE=%d", source);
+    if (source == 3 && !(c->have_params && (c->P.roi_flags & 1))) return fail(SOC_ERR_STATE, "soc_sim_pb: SOURCE=3 needs WITH_ROI_LOAD (roi_flags & 1)");
     SimArgs A;
-    int r = sim_common(c, A, source == 0 ? SIM_PS : SIM_BG, batch, seed, abs, sca, tw, global, "soc_sim_pb");
+    int r = sim_common(c, A, source == 0 ? SIM_PS : (source == 1 ? SIM_BG : SIM_ROI), batch, seed, abs, sca, tw, global, "soc_sim_pb");
     if (r != SOC_OK) return r;
     A.bg = bg;
+    if (source == 3) {
+        // PACKETS = number of surface elements, 100 work items each, BATCH a multiple of the Healpix pixel count (ASOC.py:1093-1110)
+        if (packets < 1 || (size_t)packets != roi_elems(A.roi.dim)) return fail(SOC_ERR_ARG, "soc_sim_pb: SOURCE=3 takes PACKETS = number of ROI surface elements (%zu)", roi_elems(A.roi.dim));
+        A.roi_nelem = packets;
+        const long long items = 100LL * packets < global ? 100LL * packets : global;
+        A.nunits = (c->rng_mode == SOC_RNG_REFERENCE) ? global : items * batch;
+        if (A.deposit == DEP_TILE) A.deposit = DEP_RED;
+        return sim_launch(c, A, "soc_sim_pb");
+    }
     if (source == 0) {
         const size_t nps = (size_t)c->P.no_ps;
         if ((r = need(c, SOC_BUF_PSPOS, nps * 12, "soc_sim_pb")) != SOC_OK) return r;
@@ -601,6 +659,7 @@ static int map_common(soc_context *c, MapArgs &M, size_t npixels, float abs, flo
     M.kabs = abs; M.ksca = sca; M.length = c->P.length;
     M.with_abu = c->P.with_abu; M.level_threshold = c->P.level_threshold; M.save_colden = save_colden;
     M.map_interpolation = c->P.map_interpolation;
+    if ((r = roi_args(c, M.roi, false, who)) != SOC_OK) return r;
     M.counters = c->counters;
     return SOC_OK;
 }
@@ -764,9 +823,10 @@ int soc_sca_pb(soc_context *c, int source, int packets, int batch, float seed, f
                int npix_x, int npix_y, float map_dx, const float centre[3], int global) {
     NEED_CTX(c);
     (void)packets;
-    if (source != 0 && source != 1) return fail(SOC_ERR_UNSUPPORTED, "soc_sca_pb: SOURCE=%d", source);
+    if (source != 0 && source != 1 && source != 3) return fail(SOC_ERR_ARG, "soc_sca_pb: SOURCE=%d", source);
+    if (source == 3 && !(c->have_params && (c->P.roi_flags & 1))) return fail(SOC_ERR_STATE, "soc_sca_pb: SOURCE=3 needs WITH_ROI_LOAD (roi_flags & 1)");
     ScaArgs S;
-    int r = sca_common(c, S, source == 0 ? SIM_PS : SIM_BG, 1, batch, seed, abs, sca, ndir, npix_x, npix_y, map_dx, centre, global, "soc_sca_pb");
+    int r = sca_common(c, S, source == 0 ? SIM_PS : (source == 1 ? SIM_BG : SIM_ROI), 1, batch, seed, abs, sca, ndir, npix_x, npix_y, map_dx, centre, global, "soc_sca_pb");
     if (r != SOC_OK) return r;
     if (source == 0) {
         const size_t nps = (size_t)c->P.no_ps;
@@ -774,7 +834,12 @@ int soc_sca_pb(soc_context *c, int source, int packets, int batch, float seed, f
         if ((r = need(c, SOC_BUF_PS, nps * 4, "soc_sca_pb")) != SOC_OK) return r;
     }
     S.bg = bg;
-    long long items = (source == 1 && 8LL * c->G.area < global) ? 8LL * c->G.area : global;
+    if (source == 3) {
+        if ((r = roi_args(c, S.roi, true, "soc_sca_pb")) != SOC_OK) return r;
+        if (packets < 1 || (size_t)packets != roi_elems(S.roi.dim)) return fail(SOC_ERR_ARG, "soc_sca_pb: SOURCE=3 takes PACKETS = number of ROI surface elements");
+        S.roi_nelem = packets;
+    }
+    long long items = (source == 1 && 8LL * c->G.area < global) ? 8LL * c->G.area : ((source == 3 && 100LL * packets < global) ? 100LL * packets : global);
     S.nunits = (c->rng_mode == SOC_RNG_REFERENCE) ? global : items * batch;
     return sca_launch(c, S, "soc_sca_pb");
 }

@@ -305,6 +305,53 @@ __device__ __forceinline__ void to_surface(const GridDesc &G, vec3 &p, const vec
     p.x = xadd(p.x, xmul(dx, d.x)); p.y = xadd(p.y, xmul(dx, d.y)); p.z = xadd(p.z, xmul(dx, d.z));
 }
 
+// ---- region of interest ------------------------------------------------------------------------------------------
+struct RoiDesc {
+    int flags;                 // 1 WITH_ROI_LOAD, 2 WITH_ROI_SAVE, 4 ROI_MAP
+    int lim[6];                // [x0,x1,y0,y1,z0,z1], inclusive root-cell limits
+    int step, nside;           // ROI_STEP, ROI_NSIDE
+    int dim[3];                // dimensions of the loaded ROI file
+    const float *__restrict__ load;
+    float *save;
+};
+// InRoi (kernel_ASOC_aux.c:1031-1048 / kernel_ASOC_map.c:37-56): is the root ancestor of cell (level, ind) inside the box?
+template <bool OCT>
+__device__ __forceinline__ bool in_roi(const GridDesc &G, const RoiDesc &R, int level, int ind) {
+    int i = ind;
+    if (OCT) for (int k = level; k > 0; k--) i = G.par[G.off[k] + i - G.nxyz];
+    const int k = i / (G.nx * G.ny), j = (i / G.nx) % G.ny;
+    i = i % G.nx;
+    return i >= R.lim[0] && i <= R.lim[1] && j >= R.lim[2] && j <= R.lim[3] && k >= R.lim[4] && k <= R.lim[5];
+}
+__device__ __forceinline__ bool in_roi_xyz(const RoiDesc &R, int i, int j, int k) {
+    return i >= R.lim[0] && i <= R.lim[1] && j >= R.lim[2] && j <= R.lim[3] && k >= R.lim[4] && k <= R.lim[5];
+}
+__device__ inline int ang2pix_ring(int nside, float phi, float theta);
+// A packet has stepped into ROI at root-grid position `rp` moving along `d`: ROI_SAVE[surface element, direction pixel] += photons
+// (kernel_ASOC.c:617-642, 1510-1535)
+__device__ __forceinline__ void roi_save_add(const RoiDesc &R, const vec3 &rp, const vec3 &d, float photons) {
+    const int RNX = (R.lim[1] - R.lim[0] + 1) * R.step, RNY = (R.lim[3] - R.lim[2] + 1) * R.step, RNZ = (R.lim[5] - R.lim[4] + 1) * R.step;
+    const float st = (float)R.step;
+    int ii = 0, jj;
+    if (rp.x < xadd((float)R.lim[0], 1.0e-3f) || rp.x > xadd((float)R.lim[1], 0.999f)) {
+        ii = clampi((int)floorf(xmul(xsub(rp.y, (float)R.lim[2]), st)), 0, RNY - 1); jj = clampi((int)floorf(xmul(xsub(rp.z, (float)R.lim[4]), st)), 0, RNZ - 1);
+        ii = ii + RNY * jj;
+    }
+    if (rp.y < xadd((float)R.lim[2], 1.0e-3f) || rp.y > xadd((float)R.lim[3], 0.999f)) {
+        ii = clampi((int)floorf(xmul(xsub(rp.x, (float)R.lim[0]), st)), 0, RNX - 1); jj = clampi((int)floorf(xmul(xsub(rp.z, (float)R.lim[4]), st)), 0, RNZ - 1);
+        ii = RNY * RNZ + ii + RNX * jj;
+    }
+    if (rp.z < xadd((float)R.lim[4], 1.0e-3f) || rp.z > xadd((float)R.lim[5], 0.999f)) {
+        ii = clampi((int)floorf(xmul(xsub(rp.x, (float)R.lim[0]), st)), 0, RNX - 1); jj = clampi((int)floorf(xmul(xsub(rp.y, (float)R.lim[2]), st)), 0, RNY - 1);
+        ii = RNY * RNZ + RNX * RNZ + ii + RNX * jj;
+    }
+    const float theta = acosf(d.z), phi = atan2f(d.y, d.x);
+    jj = ang2pix_ring(R.nside, phi, theta);
+    ii = clampi(ii, 0, RNX * RNY + RNY * RNZ + RNZ * RNX - 1);
+    jj = clampi(jj, 0, 12 * R.nside * R.nside - 1);
+    atomicAdd(&R.save[(size_t)ii * 12 * R.nside * R.nside + jj], photons);
+}
+
 // Mirror (kernel_ASOC_aux.c:1054-1083), literally: every enabled border negates its direction component whether or
 // not it was crossed (`if (c) a ; b ;`).  Used by the parity / reference-geometry kernels; the production kernels
 // reflect only the crossed border.

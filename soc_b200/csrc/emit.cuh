@@ -7,6 +7,7 @@ struct Packet {
     vec3 pos, dir;
     float photons, free_path, tau, rho;
     int level, ind, scat, eidx, nstep;
+    int roi;            // WITH_ROI_SAVE: the packet was inside ROI after its last full step
 };
 
 
@@ -247,4 +248,44 @@ __device__ void emit_hp_sca(const ARGS &A, RNG &rng, Packet &pk) {
     pk.pos.x = xadd(xmul(0.5f, NX), xmul(Rout, p.x)); pk.pos.y = xadd(xmul(0.5f, NY), xmul(Rout, p.y)); pk.pos.z = xadd(xmul(0.5f, NZ), xmul(Rout, p.z));
     to_surface(G, pk.pos, pk.dir);
     locate<OCT>(G, pk);
+}
+
+// ---- emission: external field stored on the surface of the model (SOURCE == 3, WITH_ROI_LOAD) -----------------
+// kernel_ASOC.c:141-179, 469-502 (== kernel_ASOC_sca.c SimRAM_PB): work item id serves surface element id % nelem of
+// the loaded file (100 work items per element), ray III comes from Healpix pixel III % npix of that element.
+// Returns false when the pixel is empty (the reference skips it before drawing any random number).
+template <class ARGS, class RNG, bool OCT>
+__device__ bool emit_roi(const ARGS &A, RNG &rng, int id, int III, int nelem, Packet &pk) {
+    const GridDesc &G = A.G;
+    const int *RD = A.roi.dim;
+    const int ielem = id % nelem;
+    int iside = ielem;
+    const float rd = xdiv((float)G.nx, (float)RD[0]);
+    float DX = 0.0f, DY = 0.0f;
+    if (iside < RD[1] * RD[2]) { DX = xmul((float)(iside % RD[1]) + 0.5f, rd); DY = xmul((float)(iside / RD[1]) + 0.5f, rd); iside = 0; }
+    else { iside -= RD[1] * RD[2];
+    if (iside < RD[0] * RD[2]) { DX = xmul((float)(iside % RD[0]) + 0.5f, rd); DY = xmul((float)(iside / RD[0]) + 0.5f, rd); iside = 1; }
+    else { iside -= RD[0] * RD[2];
+    if (iside < RD[0] * RD[1]) { DX = xmul((float)(iside % RD[0]) + 0.5f, rd); DY = xmul((float)(iside / RD[0]) + 0.5f, rd); iside = 2; } } }
+    const int npix = 12 * A.roi.nside * A.roi.nside;
+    const float X0 = (float)(A.roi.nside * A.roi.nside * 12.0 / (100.0 * A.batch));
+    const int ipix = III % npix;
+    pk.photons = X0 * A.roi.load[(size_t)ielem * npix + ipix];
+    pk.ind = -1;
+    if (pk.photons <= 0.0f) return false;
+    float v1, v2;
+    pix2ang_ring(A.roi.nside, ipix, v1, v2, SOC_PI);
+    v1 = xadd(v1, xmul(xsub(rng.uniform(), 0.5f), 0.05f));
+    v2 = xadd(v2, xmul(xsub(rng.uniform(), 0.5f), 0.05f));
+    float s1, c1, s2, c2;
+    sincosf(v1, &s1, &c1); sincosf(v2, &s2, &c2);
+    pk.dir.x = xmul(s2, c1); pk.dir.y = xmul(s2, s1); pk.dir.z = c2;
+    const float NX = (float)G.nx, NY = (float)G.ny, NZ = (float)G.nz;
+    const float a = xadd(DX, xmul(xadd(-0.49f, xmul(0.98f, rng.uniform())), rd));
+    const float b = xadd(DY, xmul(xadd(-0.49f, xmul(0.98f, rng.uniform())), rd));
+    if (iside == 0)      { pk.pos.y = a; pk.pos.z = b; pk.pos.x = (pk.dir.x > 0.0f) ? SOC_PEPS : (NX - SOC_PEPS); }
+    else if (iside == 1) { pk.pos.x = a; pk.pos.z = b; pk.pos.y = (pk.dir.y > 0.0f) ? SOC_PEPS : (NY - SOC_PEPS); }
+    else                 { pk.pos.x = a; pk.pos.y = b; pk.pos.z = (pk.dir.z > 0.0f) ? SOC_PEPS : (NZ - SOC_PEPS); }
+    locate<OCT>(G, pk);
+    return true;
 }

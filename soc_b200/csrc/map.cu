@@ -113,7 +113,8 @@ __device__ __forceinline__ void integrate(const MapArgs &M, vec3 POS, const vec3
             }
         }
         float DTAU = xmul(xmul(sx, dens), kext);
-        if (HEALPIX || M.level_threshold <= 0 || olevel >= M.level_threshold) {
+        if ((HEALPIX || M.level_threshold <= 0 || olevel >= M.level_threshold) &&
+            (!(M.roi.flags & 4) || in_roi<OCT>(G, M.roi, olevel, ind0))) {                 // ROI_MAP: kernel_ASOC_map.c:37-56, 822, 948
             float w = (DTAU < 1.0e-3f) ? xsub(1.0f, xmul(0.5f, DTAU)) : xdiv(xsub(1.0f, exp_cr(-DTAU)), DTAU);
             PHOTONS = xadd(PHOTONS, xmul(xmul(xmul(xmul(exp_cr(-TAU), w), sx), em), dens));
         }

@@ -9,6 +9,7 @@ struct MapArgs {
     vec3 dir, ra, de, centre, intobs;
     float map_dx, kabs, ksca, length;
     int npx, npy, nside, with_abu, level_threshold, save_colden;
+    RoiDesc roi;                                           // ROI_MAP (flags & 4): only cells inside ROI emit
     int map_interpolation;                                 // MAP_INTERPOLATION 0/1/2 (orthographic and perspective maps)
     unsigned long long *counters;
 };

@@ -19,7 +19,7 @@
 namespace {
 
 enum RayMode { RAY_IDLE = 0, RAY_FFS = 1, RAY_MAIN = 2, RAY_PEEL = 3 };
-enum { SRC_PS = 0, SRC_BG = 1, SRC_HP = 2, SRC_CL = 3 };         // == SimKind
+enum { SRC_PS = 0, SRC_BG = 1, SRC_HP = 2, SRC_CL = 3, SRC_ROI = 4 };         // == SimKind
 
 struct Ray { vec3 pos, dir; float rho, tau; int level, ind; };
 
@@ -164,11 +164,14 @@ __device__ __forceinline__ void advance(const ScaArgs &S, Lane &L, RNG &rng, Sca
 }
 
 // one packet of a point source / the isotropic background / the Healpix sky (kernel_ASOC_sca.c:520-808, 104-220)
+// Returns false when nothing is emitted (empty direction of the stored ROI field, kernel_ASOC_sca.c:812-840).
 template <class RNG, bool OCT>
-__device__ __forceinline__ void emit_packet(const ScaArgs &S, RNG &rng, int id, int III, Packet &pk) {
-    if (S.kind == SRC_PS)      { emit_ps<ScaArgs, RNG, OCT>(S, rng, III, pk); fix_direction(pk.dir); }
-    else if (S.kind == SRC_BG) { emit_bg<ScaArgs, RNG, OCT>(S, rng, id, pk); fix_direction(pk.dir); }
-    else                       emit_hp_sca<ScaArgs, RNG, OCT>(S, rng, pk);
+__device__ __forceinline__ bool emit_packet(const ScaArgs &S, RNG &rng, int id, int III, Packet &pk) {
+    if (S.kind == SRC_PS)       { emit_ps<ScaArgs, RNG, OCT>(S, rng, III, pk); fix_direction(pk.dir); }
+    else if (S.kind == SRC_BG)  { emit_bg<ScaArgs, RNG, OCT>(S, rng, id, pk); fix_direction(pk.dir); }
+    else if (S.kind == SRC_ROI) { if (!emit_roi<ScaArgs, RNG, OCT>(S, rng, id, III, S.roi_nelem, pk)) return false; fix_direction(pk.dir); }
+    else                        emit_hp_sca<ScaArgs, RNG, OCT>(S, rng, pk);
+    return true;
 }
 
 __device__ __forceinline__ void flush(const ScaArgs &S, const ScaCounters &c) {
@@ -188,6 +191,7 @@ __global__ void __launch_bounds__(128) sca_item_kernel(const __grid_constant__ S
     bool have = id < S.nunits;
     if (S.kind == SRC_BG) have = have && id < 8LL * S.G.area;
     if (S.kind == SRC_CL) have = have && id < S.G.cells;
+    if (S.kind == SRC_ROI) have = have && id < 100LL * S.roi_nelem;
     RngMwc rng;
     if (have) rng.seed(S.mwc, (unsigned long long)id);
     Lane L; L.mode = RAY_IDLE;
@@ -211,9 +215,11 @@ __global__ void __launch_bounds__(128) sca_item_kernel(const __grid_constant__ S
                     begin_packet<RngMwc, OCT>(S, L, rng, pk);
                 }
             } else if (III < S.batch) {
-                emit_packet<RngMwc, OCT>(S, rng, (int)id, III, pk);
-                III++; cnt.packets++;
-                begin_packet<RngMwc, OCT>(S, L, rng, pk);
+                if (emit_packet<RngMwc, OCT>(S, rng, (int)id, III, pk)) {
+                    cnt.packets++;
+                    begin_packet<RngMwc, OCT>(S, L, rng, pk);
+                }
+                III++;
             } else have = false;
         }
         if (!__any_sync(FULL, L.mode != RAY_IDLE || have)) break;
@@ -255,9 +261,10 @@ __global__ void __launch_bounds__(128) sca_stream_kernel(const __grid_constant__
                         if (S.kind == SRC_CL) { icell = (int)q; iray = 0; nray = cl_rays(S, icell, pwei); }
                         else {
                             rng.seed(S.phx, q);
-                            emit_packet<RngPhilox, OCT>(S, rng, (int)(q / (unsigned)S.batch), (int)(q % (unsigned)S.batch), pk);
-                            cnt.packets++;
-                            begin_packet<RngPhilox, OCT>(S, L, rng, pk);
+                            if (emit_packet<RngPhilox, OCT>(S, rng, (int)(q / (unsigned)S.batch), (int)(q % (unsigned)S.batch), pk)) {
+                                cnt.packets++;
+                                begin_packet<RngPhilox, OCT>(S, L, rng, pk);
+                            }
                         }
                     }
                 }
@@ -346,9 +353,10 @@ __global__ void __launch_bounds__(256, 3) sca_walk_kernel(const __grid_constant_
             if (got) {
                 RngPhilox rng; rng.seed(S.phx, rid);
                 Packet pk; pk.ind = -1; pk.level = 0; pk.rho = 0.0f;
+                bool emitted = true;
                 if (S.kind == SRC_CL) { emit_cl(S, rng, icell, pwei, pk); fix_direction(pk.dir); }
-                else emit_packet<RngPhilox, OCT>(S, rng, (int)(rid / (unsigned)S.batch), (int)(rid % (unsigned)S.batch), pk);
-                cnt.packets++;
+                else emitted = emit_packet<RngPhilox, OCT>(S, rng, (int)(rid / (unsigned)S.batch), (int)(rid % (unsigned)S.batch), pk);
+                if (emitted) cnt.packets++; else pk.ind = -1;
                 photons = pk.photons; scat = 0; nstep = 0; nevent = 0; tau = 0.0f; phase = WALK_LEAF;
                 if (pk.ind >= 0) {
                     k.level = pk.level; k.ind = pk.ind; k.rho = pk.rho; k.dir = pk.dir;

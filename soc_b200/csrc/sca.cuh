@@ -21,6 +21,8 @@ struct ScaArgs {
     int nside;                         // > 0: one Healpix image of this NSIDE seen from odir[0..2] (reference: NDIR = -NSIDE)
     int bins, no_ps, ps_method, with_abu, ffs;
     int hpbg_weighted, use_emweight, with_ali, with_msf, ndust, mirror;
+    RoiDesc roi;                       // WITH_ROI_LOAD source (kind 4)
+    int roi_nelem;
     long long nunits;
     int rank, world, max_steps, ref_geometry;
     int nav_hops;                      // octree navigation rounds (climb / cross / descend) per loop iteration

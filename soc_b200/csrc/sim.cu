@@ -107,11 +107,25 @@ __device__ __forceinline__ float sample_free_path(const SimArgs &A, RNG &rng, fl
     return fp;
 }
 
+// one packet of a point source / the background / the Healpix sky / the stored ROI field; false = nothing emitted
+template <class RNG, bool OCT>
+__device__ __forceinline__ bool emit_source(const SimArgs &A, RNG &rng, int id, int III, Packet &pk) {
+    if (A.kind == SIM_PS)       emit_ps<SimArgs, RNG, OCT>(A, rng, III, pk);
+    else if (A.kind == SIM_BG)  emit_bg<SimArgs, RNG, OCT>(A, rng, id, pk);
+    else if (A.kind == SIM_ROI) return emit_roi<SimArgs, RNG, OCT>(A, rng, id, III, A.roi_nelem, pk);
+    else                        emit_hp<SimArgs, RNG, OCT>(A, rng, pk);
+    return true;
+}
+template <bool OCT>
+__device__ __forceinline__ void init_roi(const SimArgs &A, Packet &pk) {          // kernel_ASOC.c:550, 1439
+    if ((A.roi.flags & 2) && pk.ind >= 0) pk.roi = in_roi<OCT>(A.G, A.roi, pk.level, pk.ind) ? 1 : 0;
+}
+
 template <class RNG>
 __device__ __forceinline__ void start_packet(const SimArgs &A, RNG &rng, Packet &pk, bool fixdir) {
     if (fixdir) fix_direction(pk.dir);
     pk.free_path = sample_free_path(A, rng, pk.photons);
-    pk.tau = 0.0f; pk.scat = 0; pk.nstep = 0;
+    pk.tau = 0.0f; pk.scat = 0; pk.nstep = 0; pk.roi = 0;
 }
 
 // ---- one cell-step of the propagation loop (kernel_ASOC.c:556-820 / 1448-1679) -------------------------------
@@ -163,6 +177,15 @@ __device__ __forceinline__ bool finish_step(const SimArgs &A, Packet &pk, const 
         if (!CL && pk.scat > 20) return false;                     // kernel_ASOC.c:801-804
         return true;
     }
+    if (A.roi.flags & 2) {                                          // WITH_ROI_SAVE: kernel_ASOC.c:615-643, 1508-1535
+        const bool r = pk.ind >= 0 && in_roi<OCT>(A.G, A.roi, pk.level, pk.ind);
+        if (r && !pk.roi) {
+            vec3 rp = pk.pos;
+            if (OCT) root_position(A.G, rp, pk.level, pk.ind);
+            roi_save_add(A.roi, rp, pk.dir, pk.photons);
+        }
+        pk.roi = r;
+    }
     if (!CL && pk.level == t.level0 && pk.ind == t.ind0) {         // failed step: kernel_ASOC.c:649-665
         pk.pos.x = xadd(pk.pos.x, xmul(SOC_PEPS, pk.dir.x)); pk.pos.y = xadd(pk.pos.y, xmul(SOC_PEPS, pk.dir.y)); pk.pos.z = xadd(pk.pos.z, xmul(SOC_PEPS, pk.dir.z));
     }
@@ -211,6 +234,7 @@ __global__ void __launch_bounds__(128) sim_item_kernel(const __grid_constant__ S
     bool have = id < A.nunits;
     if (A.kind == SIM_BG || A.kind == SIM_HP) have = have && id < 8LL * A.G.area;      // kernel_ASOC.c:96, 878
     if (A.kind == SIM_CL) have = have && id < A.G.cells;
+    if (A.kind == SIM_ROI) have = have && id < 100LL * A.roi_nelem;                    // kernel_ASOC.c:99
     RNG rng;
     if (have) rng.seed_item(A, (unsigned long long)id);
     Packet pk; pk.ind = -1; pk.level = 0; pk.eidx = -1; pk.rho = 0.0f;
@@ -232,15 +256,17 @@ __global__ void __launch_bounds__(128) sim_item_kernel(const __grid_constant__ S
                     III++;
                     emit_cl(A, rng, icell, pwei, pk);
                     start_packet(A, rng, pk, true);
+                    init_roi<OCT>(A, pk);
                     cnt.packets++; alive = true;
                 }
             } else if (III < A.batch) {
-                if (A.kind == SIM_PS)      emit_ps<SimArgs, RNG, OCT>(A, rng, III, pk);
-                else if (A.kind == SIM_BG) emit_bg<SimArgs, RNG, OCT>(A, rng, (int)id, pk);
-                else                       emit_hp<SimArgs, RNG, OCT>(A, rng, pk);
-                start_packet(A, rng, pk, A.kind != SIM_HP);
-                III++; cnt.packets++;
-                alive = pk.ind >= 0;
+                if (emit_source<RNG, OCT>(A, rng, (int)id, III, pk)) {
+                    start_packet(A, rng, pk, A.kind != SIM_HP);
+                    init_roi<OCT>(A, pk);
+                    cnt.packets++;
+                    alive = pk.ind >= 0;
+                }
+                III++;
             } else have = false;
         }
         if (!__any_sync(FULL, alive || have)) break;
@@ -302,12 +328,12 @@ __global__ void __launch_bounds__(256) sim_stream_kernel(const __grid_constant__
                         } else {
                             rng.seed(A.phx, q);
                             int id = (int)(q / (unsigned)A.batch), III = (int)(q % (unsigned)A.batch);
-                            if (A.kind == SIM_PS)      emit_ps<SimArgs, RngPhilox, OCT>(A, rng, III, pk);
-                            else if (A.kind == SIM_BG) emit_bg<SimArgs, RngPhilox, OCT>(A, rng, id, pk);
-                            else                       emit_hp<SimArgs, RngPhilox, OCT>(A, rng, pk);
-                            start_packet(A, rng, pk, A.kind != SIM_HP);
-                            cnt.packets++;
-                            alive = pk.ind >= 0;
+                            if (emit_source<RngPhilox, OCT>(A, rng, id, III, pk)) {
+                                start_packet(A, rng, pk, A.kind != SIM_HP);
+                                init_roi<OCT>(A, pk);
+                                cnt.packets++;
+                                alive = pk.ind >= 0;
+                            }
                         }
                     }
                 }
@@ -317,6 +343,7 @@ __global__ void __launch_bounds__(256) sim_stream_kernel(const __grid_constant__
                 iray++;
                 emit_cl(A, rng, icell, pwei, pk);
                 start_packet(A, rng, pk, true);
+                init_roi<OCT>(A, pk);
                 cnt.packets++; alive = true;
             }
             if (!__any_sync(FULL, alive || more || iray < nray)) break;
@@ -407,6 +434,7 @@ __global__ void __launch_bounds__(256, 4) sim_fast_kernel(const __grid_constant_
     const bool abu = GENERAL && A.with_abu;
     FastPk f; f.ind = 0; f.rid = 0; f.eidx = -1;
     bool alive = false, more = true;
+    bool in_roi_now = false;         // WITH_ROI_SAVE: the packet is inside the region of interest
     bool wsc = false;                // the packet sits at a scattering point and waits for the batched scatter block
     int icell = 0, iray = 0, nray = 0;
     float pwei = 1.0f;
@@ -437,17 +465,18 @@ __global__ void __launch_bounds__(256, 4) sim_fast_kernel(const __grid_constant_
             if (got) {
                 RngPhilox rng; rng.seed(A.phx, q);
                 Packet pk; pk.ind = -1; pk.level = 0; pk.eidx = -1; pk.rho = 0.0f;
+                bool emitted = true;
                 if (GENERAL && cl) emit_cl(A, rng, icell, pwei, pk);
-                else {
-                    int id = (int)(q / (unsigned)A.batch), III = (int)(q % (unsigned)A.batch);
-                    if (A.kind == SIM_PS)      emit_ps<SimArgs, RngPhilox, false>(A, rng, III, pk);
-                    else if (A.kind == SIM_BG) emit_bg<SimArgs, RngPhilox, false>(A, rng, id, pk);
-                    else                       emit_hp<SimArgs, RngPhilox, false>(A, rng, pk);
+                else emitted = emit_source<RngPhilox, false>(A, rng, (int)(q / (unsigned)A.batch), (int)(q % (unsigned)A.batch), pk);
+                if (emitted) {
+                    start_packet(A, rng, pk, A.kind != SIM_HP);
+                    cnt.packets++;
+                    alive = pk.ind >= 0;
+                    if (alive) {
+                        fast_from_packet(A, pk, f); f.rid = q;
+                        if (GENERAL && (A.roi.flags & 2)) in_roi_now = in_roi_xyz(A.roi, f.ix, f.iy, f.iz);
+                    }
                 }
-                start_packet(A, rng, pk, A.kind != SIM_HP);
-                cnt.packets++;
-                alive = pk.ind >= 0;
-                if (alive) { fast_from_packet(A, pk, f); f.rid = q; }
             }
             if (!__any_sync(FULL, alive || more || iray < nray)) break;
         }
@@ -568,6 +597,17 @@ __global__ void __launch_bounds__(256, 4) sim_fast_kernel(const __grid_constant_
                     f.ind = nind; f.rho = rho_n;
                     if (abu) f.opt = opt_n;
                     alive = inb;
+                    if (GENERAL && (A.roi.flags & 2) && inb) {           // WITH_ROI_SAVE: kernel_ASOC.c:615-643
+                        const bool r = in_roi_xyz(A.roi, f.ix, f.iy, f.iz);
+                        if (r && !in_roi_now) {
+                            // entry point on the face just crossed; the other coordinates from the face distances
+                            const float ax_ = f.tx * fabsf(f.dir.x), ay_ = f.ty * fabsf(f.dir.y), az_ = f.tz * fabsf(f.dir.z);
+                            vec3 rp = { (float)f.ix + ((f.dir.x > 0.0f) ? 1.0f - ax_ : ax_), (float)f.iy + ((f.dir.y > 0.0f) ? 1.0f - ay_ : ay_),
+                                        (float)f.iz + ((f.dir.z > 0.0f) ? 1.0f - az_ : az_) };
+                            roi_save_add(A.roi, rp, f.dir, f.photons);
+                        }
+                        in_roi_now = r;
+                    }
                 }
             }
             if (f.nstep > A.max_steps) { alive = false; wsc = false; cnt.stuck++; }
@@ -851,6 +891,7 @@ __global__ void __launch_bounds__(256, 4) sim_walk_kernel(const __grid_constant_
     const bool abu = GENERAL && A.with_abu;
     Walker w; w.ind = -1; w.level = 0;
     int phase = WALK_LEAF, ax = 0;
+    bool in_roi_now = false;         // WITH_ROI_SAVE: the packet is inside the region of interest
     float photons = 0.0f, free_path = 0.0f, tau = 0.0f;
     int scat = 0, nstep = 0, eidx = -1;
     unsigned long long rid = 0;
@@ -884,20 +925,19 @@ __global__ void __launch_bounds__(256, 4) sim_walk_kernel(const __grid_constant_
             if (got) {
                 RngPhilox rng; rng.seed(A.phx, q);
                 Packet pk; pk.ind = -1; pk.level = 0; pk.eidx = -1; pk.rho = 0.0f;
+                bool emitted = true;
                 if (GENERAL && cl) emit_cl(A, rng, icell, pwei, pk);
-                else {
-                    int id = (int)(q / (unsigned)A.batch), III = (int)(q % (unsigned)A.batch);
-                    if (A.kind == SIM_PS)      emit_ps<SimArgs, RngPhilox, true>(A, rng, III, pk);
-                    else if (A.kind == SIM_BG) emit_bg<SimArgs, RngPhilox, true>(A, rng, id, pk);
-                    else                       emit_hp<SimArgs, RngPhilox, true>(A, rng, pk);
+                else emitted = emit_source<RngPhilox, true>(A, rng, (int)(q / (unsigned)A.batch), (int)(q % (unsigned)A.batch), pk);
+                if (emitted) {
+                    start_packet(A, rng, pk, A.kind != SIM_HP);
+                    cnt.packets++;
+                    alive = pk.ind >= 0;
                 }
-                start_packet(A, rng, pk, A.kind != SIM_HP);
-                cnt.packets++;
-                alive = pk.ind >= 0;
                 if (alive) {
                     walker_init<true>(G, w, pk.pos, pk.dir, pk.level, pk.ind, pk.rho);
                     photons = pk.photons; free_path = pk.free_path; tau = 0.0f; scat = 0; nstep = 0; eidx = pk.eidx; rid = q;
                     phase = WALK_LEAF;
+                    if (GENERAL && (A.roi.flags & 2)) in_roi_now = in_roi_xyz(A.roi, w.ix, w.iy, w.iz);
                 }
             }
             if (!__any_sync(FULL, alive || more || iray < nray)) break;
@@ -990,7 +1030,21 @@ __global__ void __launch_bounds__(256, 4) sim_walk_kernel(const __grid_constant_
         #pragma unroll 1
         for (int hop = 0; hop < A.nav_hops; hop++) {
             if (alive && phase == WALK_CLIMB) { nav_climb(G, w, ax); phase = WALK_CROSS; }
-            if (alive && phase == WALK_CROSS) { phase = nav_cross(G, w, ax, A.mirror); if (w.ind < 0) alive = false; }
+            if (alive && phase == WALK_CROSS) {
+                const bool at_root = GENERAL && (A.roi.flags & 2) && w.level == 0;
+                phase = nav_cross(G, w, ax, A.mirror);
+                if (w.ind < 0) alive = false;
+                else if (at_root && phase != WALK_CLIMB) {           // a new root cell: WITH_ROI_SAVE, kernel_ASOC.c:615-643
+                    const bool r = in_roi_xyz(A.roi, w.ix, w.iy, w.iz);
+                    if (r && !in_roi_now) {
+                        const float ax_ = w.tx * fabsf(w.d.x), ay_ = w.ty * fabsf(w.d.y), az_ = w.tz * fabsf(w.d.z);
+                        vec3 rp = { (float)w.ix + ((w.d.x > 0.0f) ? 1.0f - ax_ : ax_), (float)w.iy + ((w.d.y > 0.0f) ? 1.0f - ay_ : ay_),
+                                    (float)w.iz + ((w.d.z > 0.0f) ? 1.0f - az_ : az_) };
+                        roi_save_add(A.roi, rp, w.d, photons);
+                    }
+                    in_roi_now = r;
+                }
+            }
             if (alive && phase == WALK_DESCEND) phase = nav_descend(G, w, ax);
         }
         if (was_alive && !alive) { cnt.steps += nstep; cnt.scat += min(scat, 20); }
@@ -1055,7 +1109,7 @@ static void launch_lean(SimArgs A, int dep, int blocks, int threads, cudaStream_
     else                      sim_lean_kernel<DEP_TILE, BRICK, PEND><<<blocks, threads, 0, stream>>>(A);
 }
 
-static bool sim_is_general(const SimArgs &A) { return A.with_msf || A.with_abu || A.save_int2 || A.with_ali || A.kind == SIM_CL; }
+static bool sim_is_general(const SimArgs &A) { return (A.roi.flags & 2) || A.kind == SIM_ROI || A.with_msf || A.with_abu || A.save_int2 || A.with_ali || A.kind == SIM_CL; }
 
 // the lean kernel keeps the work unit in 32 bits and the step count of a packet in 24
 static bool sim_uses_lean(const SimArgs &A) { return !sim_is_general(A) && A.nlocal < (1LL << 32) && A.max_steps < (1 << 24) - 2; }

@@ -2,7 +2,7 @@
 #pragma once
 #include "common.cuh"
 
-enum SimKind { SIM_PS = 0, SIM_BG = 1, SIM_HP = 2, SIM_CL = 3 };
+enum SimKind { SIM_PS = 0, SIM_BG = 1, SIM_HP = 2, SIM_CL = 3, SIM_ROI = 4 };
 
 // accumulation engine of the absorption counters (north-star item b)
 enum DepositMode {
@@ -37,6 +37,8 @@ struct SimArgs {
     const float *__restrict__ hpbg, *__restrict__ hpbgp;
     const float *__restrict__ abu, *__restrict__ scav;   // WITH_MSF: ABU[cells*ndust], SCA[ndust]
     int with_msf, ndust, mirror;
+    RoiDesc roi;                 // region of interest (flags 1 load, 2 save)
+    int roi_nelem;               // SIM_ROI: number of surface elements of the loaded file (the PACKETS argument)
     float kabs, ksca, bg, tw, adhoc, sw_a, sw_b;
     int kind, batch, global;
     int bins, no_ps, ps_method, with_abu, with_ali, use_int, save_int2, use_emweight, hpbg_weighted, step_weight;

@@ -200,6 +200,33 @@ def run_bg_msf(batch=2, seed=0.44):
     return run
 
 
+def with_roi_save(run):
+    """Wrap a Monte Carlo case: also return the photons recorded on entering the region of interest."""
+    def wrapped(X):
+        out = run(X)
+        out["roi_save"] = np.array(X.roi_save, np.float32).copy()
+        return out
+    return wrapped
+
+
+def run_roi_load(roi_dim, nside, rounds=2, seed=0.27, tau_s=2.0):
+    """SOURCE == 3: packets from a stored external field, one Healpix map of directions per surface element."""
+    def run(X):
+        c = X.cloud
+        k = _tau_scale(c, 1.0)
+        nelem = roi_dim[0] * roi_dim[1] + roi_dim[1] * roi_dim[2] + roi_dim[2] * roi_dim[0]
+        npix = 12 * nside * nside
+        rng = np.random.default_rng(13)
+        field = rng.random(nelem * npix).astype(np.float32)
+        field[::5] = 0.0                                   # empty directions are skipped without a packet
+        X.zero(0)
+        X.zero(1)
+        X.sim_pb(100 * nelem, 3, nelem, rounds * npix, seed, 0.0, 0.9, abs_=1.5 * k, sca=tau_s * k, dsc=DSC6, csc=CSC6,
+                 roi_load=field)
+        return dict(tabs=X.tabs.copy())
+    return run
+
+
 def run_sca(kind, npix=(24, 20), dirs=((0.0, 0.0), (70.0, 30.0)), batch=3, glob=1024, seed=0.61, pspos=None,
             hp_observer=None, nside=4, msf=False, emweight=False):
     """kind: ps / bg / hp / cl.  hp_observer = (x,y,z): one Healpix image (NSIDE `nside`) seen from that position
@@ -223,6 +250,13 @@ def run_sca(kind, npix=(24, 20), dirs=((0.0, 0.0), (70.0, 30.0)), batch=3, glob=
         elif kind == "bg":
             g = 8 * c.AREA
             out = X.sca_pb(g, 1, g * batch, batch, seed, 1.5, *args, **opac)
+        elif kind == "roi":                                  # SOURCE == 3: the stored external field
+            rd_, ns_ = X.opts["roi_dim"], X.opts["roi_nside"]
+            nelem = rd_[0] * rd_[1] + rd_[1] * rd_[2] + rd_[2] * rd_[0]
+            rng = np.random.default_rng(13)
+            field = rng.random(nelem * 12 * ns_ * ns_).astype(np.float32)
+            field[::5] = 0.0
+            out = X.sca_pb(100 * nelem, 3, nelem, batch * 12 * ns_ * ns_, seed, 0.0, *args, roi_load=field, **opac)
         elif kind == "hp":
             rng = np.random.default_rng(11)
             sky = (0.2 + rng.random(49152)).astype(np.float32)
@@ -303,6 +337,17 @@ CASES = {
     "sca_bg_reg12_msf": (_reg(12), dict(with_abu=1, with_msf=1, ndust=2), run_sca("bg", batch=1, msf=True)),
     "sca_ps_oct6_msf": (_oct(6, 3), dict(no_ps=1, with_abu=1, with_msf=1, ndust=2),
                         run_sca("ps", pspos=[(3.3, 3.2, 2.9)], batch=8, glob=512, msf=True)),
+    "bg_reg12_roisave": (_reg(12), dict(with_roi_save=1, roi=[3, 8, 2, 7, 4, 9], roi_step=2, roi_nside=2),
+                         with_roi_save(run_bg(batch=2, seed=0.35))),
+    "ps_oct6_roisave": (_oct(6, 3), dict(no_ps=1, with_roi_save=1, roi=[3, 4, 2, 4, 1, 3], roi_step=1, roi_nside=4),
+                        with_roi_save(run_ps([(1.3, 1.2, 4.9)], batch=12))),
+    "cl_reg10_roisave": (_reg(10), dict(with_roi_save=1, roi=[2, 6, 3, 7, 2, 5], roi_step=1, roi_nside=2),
+                         with_roi_save(run_cl(False))),
+    "roi_reg12_load":  (_reg(12), dict(with_roi_load=1, roi_dim=[4, 4, 4], roi_nside=2), run_roi_load([4, 4, 4], 2)),
+    "roi_oct6_load":   (_oct(6, 3), dict(with_roi_load=1, roi_dim=[3, 3, 3], roi_nside=2, noabsorbed=0), run_roi_load([3, 3, 3], 2, rounds=1, tau_s=0.5)),   # few scatterings: few paths flip on libm rounding
+    "sca_roi_reg12_load": (_reg(12), dict(with_roi_load=1, roi_dim=[4, 4, 4], roi_nside=2), run_sca("roi", batch=1)),
+    "map_reg16_roi":   (_reg(16), dict(roi_map=1, roi=[4, 11, 3, 9, 5, 12]), run_map((20, 16), [(0.0, 0.0), (60.0, 30.0)])),
+    "map_oct8_3_roi":  (_oct(8, 3), dict(roi_map=1, roi=[2, 5, 1, 6, 3, 4]), run_map((24, 24), [(35.0, 110.0)], map_dx=0.4)),
     "bg_reg12_mirror": (_reg(12), dict(mirror=1 + 4), run_bg(batch=2, seed=0.57)),
     "bg_oct6_mirror":  (_oct(6, 3), dict(mirror=32), run_bg(batch=2, seed=0.58)),
     "cl_reg10_mirror": (_reg(10), dict(mirror=16 + 2), run_cl(False)),

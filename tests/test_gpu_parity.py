@@ -13,7 +13,7 @@ import os
 import numpy as np
 import pytest
 
-from tests.cases import CASES, run_bg, run_ps, run_abu, run_hp, run_cl, run_sca, run_bg_msf, _reg, _oct
+from tests.cases import CASES, run_bg, run_ps, run_abu, run_hp, run_cl, run_sca, run_bg_msf, run_roi_load, with_roi_save, _reg, _oct
 from tests.stats import chi2_per_dof
 from soc_b200 import synth
 
@@ -180,6 +180,15 @@ STAT_CASES = {
     "bg_box_mirror": (lambda: synth.box_cloud(20, 12, 8), dict(mirror=1 + 8 + 32), lambda s: run_bg(batch=6, seed=s), "tabs"),
     "bg_reg12_mirror_abu": (_reg(12), dict(with_abu=1, mirror=2 + 4), lambda s: run_abu(batch=8, seed=s), "tabs"),
     "bg_oct6_mirror": (_oct(6, 3), dict(mirror=32 + 1), lambda s: run_bg(batch=16, seed=s), "tabs"),
+    # region of interest: photons recorded on entering ROI (per surface element and direction), the stored field as a source
+    "bg_reg12_roisave": (_reg(12), dict(with_roi_save=1, roi=[3, 8, 2, 7, 4, 9], roi_step=1, roi_nside=1),
+                         lambda s: with_roi_save(run_bg(batch=8, seed=s)), "roi_save"),
+    "ps_oct6_roisave": (_oct(6, 3), dict(no_ps=1, with_roi_save=1, roi=[3, 4, 2, 4, 1, 3], roi_step=1, roi_nside=1),
+                        lambda s: with_roi_save(run_ps([(1.3, 1.2, 4.9)], batch=96, seed=s)), "roi_save"),
+    "bg_reg12_roisave_tabs": (_reg(12), dict(with_roi_save=1, roi=[3, 8, 2, 7, 4, 9], roi_step=2, roi_nside=2),
+                              lambda s: with_roi_save(run_bg(batch=8, seed=s)), "tabs"),
+    "roi_reg12_load": (_reg(12), dict(with_roi_load=1, roi_dim=[4, 4, 4], roi_nside=2), lambda s: run_roi_load([4, 4, 4], 2, rounds=1, seed=s), "tabs"),
+    "roi_oct6_load": (_oct(6, 3), dict(with_roi_load=1, roi_dim=[3, 3, 3], roi_nside=2), lambda s: run_roi_load([3, 3, 3], 2, rounds=2, seed=s), "tabs"),
 }
 
 
@@ -199,7 +208,7 @@ def test_packet_streams_statistical_parity(name):
         B.dev.set_geometry(1)
     b = _repeat(B, fac, K, key)
     chi2, dof, tot, tot_sigma = chi2_per_dof(b, a, min_rel=1e-4)
-    assert dof > 300
+    assert dof > (100 if key == "roi_save" else 300)
     assert chi2 <= 1.1, "%s: chi2/dof = %.3f over %d cells" % (name, chi2, dof)
     assert tot <= max(4.0 * tot_sigma, 1e-4), "%s: total energy differs by %.2e (sigma %.2e)" % (name, tot, tot_sigma)
     B.close()
@@ -218,6 +227,7 @@ SCA_STAT_CASES = {
     "sca_bg_oct6_hpobs": (_oct(6, 3), {}, lambda s: run_sca("bg", batch=48, hp_observer=(7.5, 2.03, 3.47), nside=8, seed=s)),
     "sca_bg_reg12_msf": (_reg(12), dict(with_abu=1, with_msf=1, ndust=2), lambda s: run_sca("bg", batch=24, msf=True, seed=s)),
     "sca_bg_reg12_mirror": (_reg(12), dict(mirror=1 + 8), lambda s: run_sca("bg", batch=24, seed=s)),
+    "sca_roi_reg12_load": (_reg(12), dict(with_roi_load=1, roi_dim=[4, 4, 4], roi_nside=2), lambda s: run_sca("roi", batch=2, seed=s)),
 }
 
 
