@@ -370,8 +370,34 @@ def main(argv=None, device_factory=None):
                    sw_a=float("%.3e" % USER.STEP_WEIGHT[1]), sw_b=float("%.3e" % USER.STEP_WEIGHT[2]),
                    level_threshold=USER.LEVEL_THRESHOLD, length=length, factor=FACTOR, adhoc=ADHOC,
                    with_msf=int(WITH_MSF), ndust=NDUST, mirror=mirror_mask(USER),
-                   map_interpolation=USER.MAP_INTERPOLATION, opt_is_half=int(bool(USER.OPT_IS_HALF)))
+                   map_interpolation=USER.MAP_INTERPOLATION, opt_is_half=int(bool(USER.OPT_IS_HALF)),
+                   with_roi_load=int(USER.WITH_ROI_LOAD), with_roi_save=int(USER.WITH_ROI_SAVE), roi_map=int(USER.ROI_MAP))
     dev.set_grid(cloud)
+    # region of interest (ASOC.py:906-945): the external field to load, the file of photons entering ROI
+    ROI_LOAD = ROI_SAVE = None
+    ROI_LOAD_NELEM = ROI_SAVE_NPIX = 0
+    roi_dim = (1, 1, 1)
+    if USER.WITH_ROI_LOAD:
+        hdr = np.fromfile(USER.FILE_ROI_LOAD, np.int32, 5)                   # (nx, ny, nz, nside, nfreq)
+        if hdr[3] != USER.ROI_NSIDE:
+            print("ROI file %s has nside %d, ini-file has %d" % (USER.FILE_ROI_LOAD, hdr[3], USER.ROI_NSIDE))
+            sys.exit()
+        if hdr[4] != NFREQ:
+            print("ROI file %s has %d, current run %d frequencies" % (USER.FILE_ROI_LOAD, hdr[4], NFREQ))
+            sys.exit()
+        roi_dim = tuple(int(v) for v in hdr[:3])
+        ROI_LOAD_NELEM = roi_dim[0] * roi_dim[1] + roi_dim[1] * roi_dim[2] + roi_dim[2] * roi_dim[0]
+        ROI_LOAD = np.memmap(USER.FILE_ROI_LOAD, dtype='float32', mode='r', offset=20,
+                             shape=(NFREQ, ROI_LOAD_NELEM * 12 * USER.ROI_NSIDE * USER.ROI_NSIDE))
+    if USER.WITH_ROI_SAVE:
+        rn = [(int(USER.ROI[2 * k + 1]) - int(USER.ROI[2 * k]) + 1) * USER.ROI_STEP for k in range(3)]
+        ROI_SAVE_NPIX = (rn[0] * rn[1] + rn[1] * rn[2] + rn[2] * rn[0]) * 12 * USER.ROI_NSIDE * USER.ROI_NSIDE
+        if root:
+            np.asarray(rn + [USER.ROI_NSIDE, NFREQ], np.int32).tofile(USER.FILE_ROI_SAVE)
+            ROI_SAVE = np.memmap(USER.FILE_ROI_SAVE, dtype='float32', mode='r+', offset=20, shape=(NFREQ, ROI_SAVE_NPIX))
+            ROI_SAVE[:, :] = 0.0
+    if USER.WITH_ROI_LOAD or USER.WITH_ROI_SAVE or USER.ROI_MAP:
+        dev.set_roi(USER.ROI, USER.ROI_STEP, USER.ROI_NSIDE, roi_dim)
     if WITH_MSF:
         dev.upload(bk.BUF_ABU, np.ascontiguousarray(ABU, np.float32).reshape(-1))
     dev.set_rng_mode(bk.RNG_REFERENCE if 'REFSTREAMS' in USER.KEYS else bk.RNG_PACKET)
@@ -506,6 +532,14 @@ def main(argv=None, device_factory=None):
                         INTENSITY[a:b, ifreq, icomp] += (PLANCK * FFREQ[ifreq] / kabs) * (8.0 ** level) * TMP[a:b] / DENS[a:b]
         Tpull += time.time() - t0
 
+    def harvest_roi(ifreq, scale):
+        """Photons that entered ROI during the last launch -> the roisave file (this rank's share reduced to rank 0)."""
+        if not USER.WITH_ROI_SAVE:
+            return
+        comm.allreduce(dev, bk.BUF_ROI_SAVE, ROI_SAVE_NPIX)
+        if root:
+            ROI_SAVE[ifreq, :] += dev.download(bk.BUF_ROI_SAVE, ROI_SAVE_NPIX) * np.float32(scale)
+
     # =============================================================================================================
     # constant sources: point sources, background, diffuse emission (ASOC.py:1004-1549)
     # =============================================================================================================
@@ -514,7 +548,7 @@ def main(argv=None, device_factory=None):
         CTABS = np.fromfile(USER.file_constant_load, np.float32, CELLS)
     else:
         skip = USER.EMWEIGHT_SKIP - 1
-        for II in range(3):
+        for II in range(4):                 # PSPAC, BGPAC, DFPAC, ROI background (ASOC.py:1028)
             if USER.ITERATIONS < 1:
                 continue
             WPS = WBG = 0.0
@@ -546,7 +580,7 @@ def main(argv=None, device_factory=None):
                 PACKETS = bgpac
                 if VERBOSE:
                     print("=== BG: BGPAC %d, BATCH %d, GLOBAL %d" % (bgpac, BATCH, GLOBAL))
-            else:
+            elif II == 2:
                 GLOBAL = GLOBAL_0
                 if len(DIFFUSERAD) < 1 or DFPAC < 1:
                     continue
@@ -554,6 +588,15 @@ def main(argv=None, device_factory=None):
                 PACKETS = DFPAC
                 if VERBOSE:
                     print("=== DFPAC %d, GLOBAL %d, BATCH %d" % (DFPAC, GLOBAL, BATCH))
+            else:                               # ROI background: the stored field re-emitted from the surface (ASOC.py:1093-1110)
+                if USER.ROIPAC < 1 or not USER.WITH_ROI_LOAD:
+                    continue
+                npix_roi = 12 * USER.ROI_NSIDE * USER.ROI_NSIDE
+                GLOBAL = fix(100 * ROI_LOAD_NELEM, LOCAL)
+                BATCH = max([1, int(USER.ROIPAC / (100.0 * npix_roi * ROI_LOAD_NELEM))]) * npix_roi
+                PACKETS = ROI_LOAD_NELEM
+                if VERBOSE:
+                    print("=== ROI: GLOBAL %d, BATCH %d, ROI_LOAD_NELEM %d" % (GLOBAL, BATCH, ROI_LOAD_NELEM))
             dev.zero_amc(0)
             for IFREQ in range(NFREQ):
                 T000 = time.time()
@@ -608,9 +651,15 @@ def main(argv=None, device_factory=None):
                             EMWEI[np.nonzero(host_rng.random(CELLS) > EMWEI)] = 0.0
                             comm.broadcast_host(EMWEI)
                             dev.upload(bk.BUF_EMWEI, EMWEI)
+                if USER.WITH_ROI_SAVE:
+                    dev.clear(bk.BUF_ROI_SAVE, 4 * ROI_SAVE_NPIX)               # per frequency (ASOC.py:1301-1302)
+                if II == 3:
+                    dev.upload(bk.BUF_ROI_LOAD, np.asarray(ROI_LOAD[IFREQ, :] * USER.ROI_LOAD_SCALE / (USER.GL * USER.GL), np.float32))
                 Tpush += time.time() - t0
                 t0 = time.time()
-                if II == 2:
+                if II == 3:
+                    dev.sim_pb(3, PACKETS, BATCH, seed, kabs, ksca, BG, FF, GLOBAL)
+                elif II == 2:
                     dev.sim_cl(II, PACKETS, BATCH, seed, kabs, ksca, FF, GLOBAL)
                 elif II == 1 and len(HPBG) > 0:
                     dev.sim_hp(PACKETS, BATCH, seed, kabs, ksca, FF, GLOBAL)
@@ -619,6 +668,7 @@ def main(argv=None, device_factory=None):
                 dev.sync()
                 Tkernel += time.time() - t0
                 harvest(IFREQ, kabs)
+                harvest_roi(IFREQ, USER.GL * USER.GL)                            # ASOC.py:1468-1476
                 if VERBOSE:
                     sys.stdout.write("  FREQ %3d/%3d  %10.3e   BG %12.4e   TW %10.3e   %7.2f\n" % (IFREQ + 1, NFREQ, FREQ, BG, FF, time.time() - T000))
             comm.allreduce(dev, bk.BUF_TABS, CELLS)
@@ -690,6 +740,8 @@ def main(argv=None, device_factory=None):
                     seed = float(np.fmod(USER.SEED + IFREQ * SEED1, 1.0))
                 else:
                     seed = float(host_rng.random())
+                if USER.WITH_ROI_SAVE:
+                    dev.clear(bk.BUF_ROI_SAVE, 4 * ROI_SAVE_NPIX)
                 Tpush += time.time() - t0
                 t0 = time.time()
                 dev.sim_cl(2, CLPAC, BATCH, seed, kabs, ksca, FF, GLOBAL)
@@ -697,6 +749,7 @@ def main(argv=None, device_factory=None):
                 Tkernel += time.time() - t0
                 if iteration == USER.ITERATIONS - 1:
                     harvest(IFREQ, kabs)
+                    harvest_roi(IFREQ, 1.0)                                      # sic: no GL^2 here (ASOC.py:1908-1914)
                 if VERBOSE:
                     print("  FREQ %3d/%3d  %10.3e" % (IFREQ + 1, NFREQ, FREQ))
             if USER.WITH_ALI:
@@ -782,6 +835,9 @@ def main(argv=None, device_factory=None):
                 np.asarray([CELLS, NFREQ], np.int32).tofile(fpa)
                 FABSORBED.tofile(fpa)
         del FABSORBED
+    if ROI_SAVE is not None:
+        ROI_SAVE.flush()
+        del ROI_SAVE
     if INTENSITY is not None:
         hdr = [CELLS, NFREQ] if USER.SAVE_INTENSITY == 1 else [CELLS, NFREQ, 4]
         if USER.SAVE_INTENSITY == 2:

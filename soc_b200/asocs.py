@@ -7,7 +7,7 @@ inputs and the `outcoming.socs` / `<scattering>.fits` outputs follow the referen
 Sources, as in ASOCS.py:416-870: point sources (kernel SimRAM_PS), the isotropic or Healpix background (SimRAM_PB /
 SimRAM_HP), a diffuse field from a file and the emission of the dust itself read from the `emitted` file
 (SimRAM_CL).  Observers: orthographic maps (`directions`) or one Healpix image seen from inside/outside the model
-(`perspective x y z` + `outnside`, ASOCS.py:44-47).  Not implemented: ROI loading (II == 3).
+(`perspective x y z` + `outnside`, ASOCS.py:44-47).  `roiload` + `roipac` add the stored external field (II == 3).
 Weights follow ASOCS.py:437-475 (WPS, WBG), the final scaling ASOCS.py:874-884.
 """
 import sys
@@ -124,8 +124,21 @@ def main(argv=None, device_factory=None):
     dev.set_params(bins=USER.DSC_BINS, no_ps=max(1, USER.NO_PS), ps_method=USER.PS_METHOD, with_abu=int(WITH_ABU),
                    ffs=USER.FFS, hpbg_weighted=int(USER.HPBG_WEIGHTED), use_emweight=USER.USE_EMWEIGHT,
                    with_msf=int(WITH_MSF), ndust=NDUST, mirror=mirror_mask(USER), opt_is_half=int(bool(USER.OPT_IS_HALF)),
+                   with_roi_load=int(USER.WITH_ROI_LOAD),
                    length=float("%.5e" % (USER.GL * PARSEC)), factor=FACTOR, adhoc=ADHOC)
     dev.set_grid(cloud)
+    ROI_LOAD, ROI_LOAD_NELEM = None, 0
+    if USER.WITH_ROI_LOAD:                                       # ASOCS.py:176-197
+        hdr = np.fromfile(USER.FILE_ROI_LOAD, np.int32, 5)       # (nx, ny, nz, nside, nfreq)
+        if hdr[3] != USER.ROI_NSIDE or hdr[4] != NFREQ:
+            print("ROI file %s: nside %d, %d frequencies; the run has nside %d, %d frequencies" %
+                  (USER.FILE_ROI_LOAD, hdr[3], hdr[4], USER.ROI_NSIDE, NFREQ))
+            sys.exit()
+        roi_dim = tuple(int(v) for v in hdr[:3])
+        ROI_LOAD_NELEM = roi_dim[0] * roi_dim[1] + roi_dim[1] * roi_dim[2] + roi_dim[2] * roi_dim[0]
+        ROI_LOAD = np.memmap(USER.FILE_ROI_LOAD, dtype='float32', mode='r', offset=20,
+                             shape=(NFREQ, ROI_LOAD_NELEM * 12 * USER.ROI_NSIDE * USER.ROI_NSIDE))
+        dev.set_roi(USER.ROI, USER.ROI_STEP, USER.ROI_NSIDE, roi_dim)
     dev.set_rng_mode(bk.RNG_REFERENCE if 'REFSTREAMS' in USER.KEYS else bk.RNG_PACKET)
     dev.set_shard(comm.rank, comm.world)
     if USER.NO_PS > 0:
@@ -168,7 +181,7 @@ def main(argv=None, device_factory=None):
             OUTCOMING[IFREQ] += dev.download(bk.BUF_OUT, NOUT)
 
     # ---- constant sources: point sources, background, diffuse field (ASOCS.py:416-720) ----------------------
-    for II in range(3):
+    for II in range(4):
         WPS = WBG = 0.0
         if II == 0:
             GLOBAL = GLOBAL_0
@@ -193,12 +206,19 @@ def main(argv=None, device_factory=None):
                 PACKETS = GLOBAL * BATCH
                 Rout = 0.5 * np.sqrt(NX * NX + NY * NY + NZ * NZ)
                 WBG = np.pi * 4.0 * np.pi * Rout ** 2.0 / (PLANCK * PACKETS)
-        else:
+        elif II == 2:
             GLOBAL = GLOBAL_0
             if len(DIFFUSERAD) < 1 or DFPAC < 1:
                 continue
             BATCH = int(DFPAC / CELLS)
             PACKETS = DFPAC
+        else:                                                    # the stored external field (ASOCS.py:483-499)
+            if USER.ROIPAC < 1 or not USER.WITH_ROI_LOAD:
+                continue
+            npix_roi = 12 * USER.ROI_NSIDE * USER.ROI_NSIDE
+            GLOBAL = fix(100 * ROI_LOAD_NELEM, LOCAL)
+            BATCH = max([1, int(USER.ROIPAC / (100.0 * npix_roi * ROI_LOAD_NELEM))]) * npix_roi
+            PACKETS = ROI_LOAD_NELEM
         skip = 2
         for IFREQ in range(NFREQ):
             FREQ = FFREQ[IFREQ]
@@ -238,8 +258,12 @@ def main(argv=None, device_factory=None):
                     if skip == 3:
                         skip = 0
                         emission_weights(IFREQ, CLPAC)         # sic: the reference scales with CLPAC here too (ASOCS.py:566)
+            if II == 3:
+                dev.upload(bk.BUF_ROI_LOAD, np.asarray(ROI_LOAD[IFREQ, :] * USER.ROI_LOAD_SCALE / (USER.GL * USER.GL), np.float32))
             t0 = time.time()
-            if II == 0:
+            if II == 3:
+                dev.sca_pb(3, PACKETS, BATCH, seed, kabs, ksca, 0.0, NDIR, npx, npy, USER.MAP_DX, centre, GLOBAL)
+            elif II == 0:
                 dev.sca_ps(PACKETS, BATCH, seed, kabs, ksca, NDIR, npx, npy, USER.MAP_DX, centre, GLOBAL)
             elif II == 1 and len(HPBG) > 0:
                 dev.sca_hp(PACKETS, BATCH, seed, kabs, ksca, NDIR, npx, npy, USER.MAP_DX, centre, GLOBAL)
@@ -251,7 +275,7 @@ def main(argv=None, device_factory=None):
             Tkernel += time.time() - t0
             harvest(IFREQ)
             if VERBOSE:
-                print("  %s FREQ %3d/%3d  %10.3e  ABS %.3e  SCA %.3e" % (["PS", "BG", "DF"][II], IFREQ + 1, NFREQ, FREQ, kabs, ksca))
+                print("  %s FREQ %3d/%3d  %10.3e  ABS %.3e  SCA %.3e" % (["PS", "BG", "DF", "ROI"][II], IFREQ + 1, NFREQ, FREQ, kabs, ksca))
 
     # ---- emission of the dust itself, read from the emitted file (ASOCS.py:723-868) -------------------------
     if CLPAC > 0:

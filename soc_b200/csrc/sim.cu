@@ -1052,8 +1052,10 @@ __global__ void __launch_bounds__(256, 4) sim_walk_kernel(const __grid_constant_
     flush_counters(A, cnt);
 }
 
+static bool sim_is_general(const SimArgs &A) { return (A.roi.flags & 2) || A.kind == SIM_ROI || A.with_msf || A.with_abu || A.save_int2 || A.with_ali || A.kind == SIM_CL; }
+
 static void launch_walk(const SimArgs &A, int blocks, int threads, cudaStream_t stream) {
-    const bool general = A.with_abu || A.save_int2 || A.with_ali || A.kind == SIM_CL;
+    const bool general = sim_is_general(A);
     // combining lanes pays only when packets share cells: point-source packets (measured on the bench octree: the
     // background launch runs 4.6e10 cell-steps/s with plain adds, 4.0e10 with the match/reduce path)
     const bool red = (A.save_int2 || A.with_ali) || A.deposit == DEP_RED || A.kind != SIM_PS;
@@ -1109,7 +1111,6 @@ static void launch_lean(SimArgs A, int dep, int blocks, int threads, cudaStream_
     else                      sim_lean_kernel<DEP_TILE, BRICK, PEND><<<blocks, threads, 0, stream>>>(A);
 }
 
-static bool sim_is_general(const SimArgs &A) { return (A.roi.flags & 2) || A.kind == SIM_ROI || A.with_msf || A.with_abu || A.save_int2 || A.with_ali || A.kind == SIM_CL; }
 
 // the lean kernel keeps the work unit in 32 bits and the step count of a packet in 24
 static bool sim_uses_lean(const SimArgs &A) { return !sim_is_general(A) && A.nlocal < (1LL << 32) && A.max_steps < (1 << 24) - 2; }

@@ -93,6 +93,12 @@ class User:
         self.OPT_IS_HALF = 0
         self.savetau_freq = []
         self.pssavetau_freq = -1.0
+        self.ROI = np.zeros(6, np.int32)
+        self.ROI_STEP = 0
+        self.ROI_NSIDE = 16
+        self.ROI_LOAD_SCALE = 1.0
+        self.FILE_ROI_SAVE = ''
+        self.FILE_ROI_LOAD = ''
         self.WITH_ROI_SAVE = 0
         self.WITH_ROI_LOAD = 0
         self.ROI_MAP = 0
@@ -239,6 +245,8 @@ class User:
                 self.CLPAC = int(round(float(a)))
             if key.find('roipac') == 0:
                 self.ROIPAC = int(round(float(a)))
+            if key.find('roinside') == 0:
+                self.ROI_NSIDE = int(round(float(a)))
             if key.find('diffpac') == 0:
                 self.DFPAC = int(a)
             if key.find('seed') == 0:
@@ -304,10 +312,14 @@ class User:
                 self.OBS_PHI.append(float(b) * D2R)
             if key.find('wavelen') == 0:
                 self.MAP_FREQ = [um2f(float(b)), um2f(float(a))]
-            if key.find('roisave') == 0:
+            if key.find('roisave') == 0:                   # roisave <file> <step>      (ASOC_aux.py:448-451)
                 self.WITH_ROI_SAVE = 1
-            if key.find('roiload') == 0:
+                self.FILE_ROI_SAVE = a
+                self.ROI_STEP = int(b)
+            if key.find('roiload') == 0:                   # roiload <file> <scale>     (ASOC_aux.py:452-455)
                 self.WITH_ROI_LOAD = 1
+                self.FILE_ROI_LOAD = a
+                self.ROI_LOAD_SCALE = float(b)
             if len(s) < 4:
                 continue
             # keywords with three arguments
@@ -328,6 +340,8 @@ class User:
                         self.FAST_MAP = int(s[4])
                     except ValueError:
                         pass
+            if key == 'roi' and len(s) >= 7:                 # roi x0 x1 y0 y1 z0 z1 (inclusive root cells, ASOC_aux.py:527)
+                self.ROI = np.asarray([int(v) for v in s[1:7]], np.int32)
             if key.find('mapcent') == 0:
                 self.MAPCENTRE = np.array([float(a), float(b), float(c)], np.float32)
             if key.find('mapview') == 0:
@@ -375,8 +389,6 @@ class User:
             bad.append("split: packet splitting (SimBgSplit/SimHpSplit) is not implemented")
         if self.POLMAP or self.POLSIM or self.POLSTAT:
             bad.append("polmap/polsim/polstat: polarisation maps are not implemented")
-        if self.WITH_ROI_SAVE or self.WITH_ROI_LOAD or self.ROI_MAP or self.ROIPAC:
-            bad.append("roi*: region-of-interest options are not implemented")
         if self.DIR_WEIGHT[0] > 0:
             bad.append("dirweight: does not compile in the reference either (undeclared pweight)")
         if self.PS_METHOD == 3:

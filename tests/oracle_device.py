@@ -27,6 +27,7 @@ class OracleDevice:
         self.buf = {}
         self.rank, self.world = 0, 1
         self.cloud = None
+        self.roi = {}
 
     # ---- configuration ------------------------------------------------------------------------------------
     def set_params(self, **kw):
@@ -47,9 +48,14 @@ class OracleDevice:
         for k in ("factor", "adhoc", "dir_weight", "do_split", "roi_flags", "opt_is_half"):
             p.pop(k, None)
         # the drivers are compared with the library's production kernels: exact mirror / scattering position
+        p.update(self.roi)
         self.O = orc.Oracle(self.cloud, gl=0.01, bins=bins, mirror_exact=1, sca_exact_level=1, **p)
         self.O.P.length = length
         self.n = self.cloud.CELLS
+
+    def set_roi(self, roi, roi_step=0, roi_nside=16, roi_dim=(1, 1, 1)):
+        self.roi = dict(roi=[int(v) for v in roi], roi_step=int(roi_step), roi_nside=int(roi_nside), roi_dim=[int(v) for v in roi_dim])
+        self._make()
 
     def set_rng_mode(self, mode):
         pass
@@ -82,6 +88,8 @@ class OracleDevice:
     def host_view(self, b, count):
         if b in self._ACC:
             return getattr(self.O, self._ACC[b])[:count]
+        if b == bk.BUF_ROI_SAVE:
+            return self.O.roi_save[:count]
         return self.buf[b][:count]
 
     def upload(self, b, array, dtype=np.float32):
@@ -99,6 +107,9 @@ class OracleDevice:
         return out
 
     def clear(self, b, nbytes):
+        if b == bk.BUF_ROI_SAVE:
+            self.O.roi_save[:] = 0.0
+            return
         self.buf[b] = np.zeros(nbytes // 4, np.float32)
 
     def device_ptr(self, b):
@@ -135,7 +146,7 @@ class OracleDevice:
                                               dsc=self._g(bk.BUF_DSC), csc=self._g(bk.BUF_CSC), opt=self._g(bk.BUF_OPT),
                                               pspos=self._g(bk.BUF_PSPOS), ps=self._g(bk.BUF_PS),
                                               xps_nside=self._g(bk.BUF_XPS_NSIDE), xps_side=self._g(bk.BUF_XPS_SIDE),
-                                              xps_area=self._g(bk.BUF_XPS_AREA), **self._msf()), seed)
+                                              xps_area=self._g(bk.BUF_XPS_AREA), roi_load=self._g(bk.BUF_ROI_LOAD), **self._msf()), seed)
 
     def sim_hp(self, packets, batch, seed, abs_, sca, tw, global_):
         self._sharded(lambda s: self.O.sim_hp(global_, packets, batch, s, tw, abs_=abs_, sca=sca, dsc=self._g(bk.BUF_DSC),
@@ -221,7 +232,7 @@ class OracleDevice:
             seed = float(np.fmod(seed + 0.37 * self.rank + 0.011, 1.0))
         out = self.O.sca_pb(global_, source, packets, batch, seed, bg, ndir, npx, npy, map_dx, centre, od, ra, de, abs_=abs_,
                             sca=sca, dsc=self._g(bk.BUF_DSC), csc=self._g(bk.BUF_CSC), opt=self._g(bk.BUF_OPT),
-                            pspos=self._g(bk.BUF_PSPOS), ps=self._g(bk.BUF_PS), **self._msf())
+                            pspos=self._g(bk.BUF_PSPOS), ps=self._g(bk.BUF_PS), roi_load=self._g(bk.BUF_ROI_LOAD), **self._msf())
         self.buf[bk.BUF_OUT] = self.buf[bk.BUF_OUT] + out.reshape(-1) / np.float32(self.world)
 
     def sca_hp(self, packets, batch, seed, abs_, sca, ndir, npx, npy, map_dx, centre, global_):

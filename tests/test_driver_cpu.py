@@ -179,3 +179,32 @@ def test_levels_keyword_cuts_the_hierarchy(tmp_path):
     assert np.allclose(got, want, rtol=1e-6)
     T = read_otfile(str(tmp_path / "model.T"))
     assert T.shape == (cut.CELLS,)
+
+
+def test_region_of_interest_save_then_load(tmp_path):
+    """roisave: the photons entering ROI are written per frequency, surface element and direction; a second run loads
+    that file as an external field (roiload + roipac) on a model of the ROI's size; roimap restricts the maps."""
+    big = tmp_path / "big"
+    cloud = _run(big, n=8, bgpac=40000, pspac=0, maps=True,
+                 extra="roi 2 5 2 5 2 5\nroisave roi.save 1\nroinside 1\nroimap\n")
+    hdr = np.fromfile(str(big / "roi.save"), np.int32, 5)
+    assert list(hdr) == [4, 4, 4, 1, 8]
+    data = np.fromfile(str(big / "roi.save"), np.float32, offset=20).reshape(8, 48 * 12)
+    assert np.isfinite(data).all() and (data >= 0).all() and (data[2:].sum(axis=1) > 0).all()
+    m = read_map_file(str(big / "map_dir_00.bin"))
+    assert m[0].max() > 0 and (m[0][0, :] == 0).all() and (m[0][:, 0] == 0).all()      # lines of sight that miss ROI are empty
+    small = tmp_path / "small"
+    write_model(str(small), n=4, bgpac=0, pspac=0, maps=False)
+    import shutil
+    shutil.copy(str(big / "roi.save"), str(small / "roi.load"))
+    ini = str(small / "model.ini")
+    txt = open(ini).read().replace("bgpackets    0\n", "bgpackets    0\nroiload roi.load 1.0\nroinside 1\nroipac 200000\n")
+    open(ini, "w").write(txt)
+    cwd = os.getcwd()
+    os.chdir(str(small))
+    try:
+        asoc.main(["ASOC.py", "model.ini"], device_factory=OracleDevice)
+    finally:
+        os.chdir(cwd)
+    T = read_otfile(str(small / "model.T"))
+    assert T.shape == (64,) and (T > 3.0).all() and (T < 80.0).all() and T.std() > 0.0
