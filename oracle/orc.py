@@ -164,6 +164,10 @@ class Oracle:
         B.roi_load, B.roi_save = _fp(f(roi_load)), _fp(self.roi_save)
         return B
 
+    def clear_roi_save(self):
+        if self.roi_save is not None:
+            self.roi_save[:] = 0
+
     def zero(self, tag):
         if tag == 0:
             self.tabs[:] = 0

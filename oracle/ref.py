@@ -70,6 +70,11 @@ class Reference:
     def atomic_count(self, reset=True):
         return int(self.L.ref_atomic_count(C.c_int(1 if reset else 0)))
 
+    def clear_roi_save(self):
+        self._roi_save()
+        if self.roi_save is not None:
+            self.roi_save[:] = 0
+
     def zero(self, tag):
         if tag == 0:
             self.tabs[:] = 0

@@ -349,6 +349,11 @@ class Backend:
     def intz(self):
         return self._get(BUF_INTZ) if self.save2 else np.zeros(self.n, np.float32)
 
+    def clear_roi_save(self):
+        ptr, nbytes = self.dev.device_ptr(BUF_ROI_SAVE)
+        if nbytes:
+            self.dev.clear(BUF_ROI_SAVE, nbytes)
+
     @property
     def roi_save(self):
         ptr, nbytes = self.dev.device_ptr(BUF_ROI_SAVE)

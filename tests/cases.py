@@ -203,6 +203,7 @@ def run_bg_msf(batch=2, seed=0.44):
 def with_roi_save(run):
     """Wrap a Monte Carlo case: also return the photons recorded on entering the region of interest."""
     def wrapped(X):
+        X.clear_roi_save()
         out = run(X)
         out["roi_save"] = np.array(X.roi_save, np.float32).copy()
         return out
