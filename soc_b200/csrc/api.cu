@@ -42,6 +42,8 @@ struct soc_context {
     unsigned long long *counters;      // device: packets, steps, scatterings, stuck, peels, work, -, -
     float *acc; size_t acc_bytes;      // per-launch scratch accumulator of the stream kernels (all zero between launches)
     void *scratch; size_t scratch_bytes;   // temporary device array of soc_emission2
+    int *nbr;                          // octrees: neighbour table [6*cells] (linkwalk.cuh)
+    int use_nbr;
     float *dens_brick;                 // regular grids with even dimensions: DENS in 2x2x2-brick order (lean kernel)
     int layout;                        // 1 = use the bricked copy where the kernel supports it
     int pend;                          // 1 = merged deposits (vector reds) in the lean kernel
@@ -108,6 +110,8 @@ int soc_create(int device_ordinal, soc_context **out) {
     c->rng_mode = SOC_RNG_PACKET; c->rank = 0; c->world = 1;
     c->deposit = DEP_TILE; c->refill = 8; c->agg_steps = 24; c->sc_batch = 0;        // 0 = by grid type
     c->nav_hops = 1; c->layout = 1;
+    c->use_nbr = 1;
+    if (const char *e = getenv("SOC_NBR")) c->use_nbr = atoi(e) != 0;                                                  // tuning knob
     c->pend = 0;          // measured on the bench step: 58.9 ms with, 59.0 ms without -- the merged reds trade L2 work for issue slots
     if (const char *e = getenv("SOC_PEND")) c->pend = atoi(e) != 0;                                                    // tuning knob
     if (const char *e = getenv("SOC_LAYOUT")) c->layout = atoi(e) != 0;                                               // tuning knob
@@ -132,6 +136,7 @@ int soc_destroy(soc_context *c) {
     cudaFree(c->counters);
     if (c->acc) cudaFree(c->acc);
     if (c->dens_brick) cudaFree(c->dens_brick);
+    if (c->nbr) cudaFree(c->nbr);
     if (c->scratch) cudaFree(c->scratch);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
@@ -196,6 +201,12 @@ int soc_set_grid(soc_context *c, int32_t nx, int32_t ny, int32_t nz, int32_t lev
     G.dens = dptr<float>(c, SOC_BUF_DENS);
     G.par = dptr<int>(c, SOC_BUF_PAR);
     if (levels > 1) { launch_parents(G, dptr<int>(c, SOC_BUF_PAR), c->stream); c->launches += levels - 1; }
+    if (c->nbr) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->nbr)); c->nbr = nullptr; }
+    if (levels > 1 && c->use_nbr && cells < (1LL << 27)) {
+        // neighbour table of the production octree kernel: 24 B per cell, built once per grid
+        if (cudaMalloc(&c->nbr, (size_t)cells * 24) == cudaSuccess) { launch_neighbours(G, c->nbr, c->stream); c->launches++; }
+        else { c->nbr = nullptr; cudaGetLastError(); }
+    }
     if (c->dens_brick) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->dens_brick)); c->dens_brick = nullptr; }
     if (levels == 1 && nx % 2 == 0 && ny % 2 == 0 && nz % 2 == 0) {
         CU(cudaMalloc(&c->dens_brick, (size_t)cells * 4));
@@ -453,6 +464,7 @@ static int sim_launch(soc_context *c, SimArgs &A, const char *who) {
         A.acc = c->acc; A.use_acc = 1;
         A.dens_brick = c->layout ? c->dens_brick : nullptr;
         A.brick = sim_uses_bricks(A, c->rng_mode) ? 1 : 0;
+        A.nbr = c->nbr;
         A.pend = c->pend;
         A.slab_xy = A.G.nx * A.G.ny; A.brick_by = 4 * A.G.nx - 2; A.brick_bz = 2 * A.G.nx * A.G.ny - 4;
     }

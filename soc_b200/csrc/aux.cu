@@ -5,6 +5,7 @@
 // All three stream through the cell arrays once (grid-stride, coalesced).
 #include "aux.cuh"
 #include <cuda_fp16.h>
+#include "linkwalk.cuh"
 
 namespace {
 
@@ -120,4 +121,44 @@ void launch_half_to_float(const void *src, float *dst, long long n, cudaStream_t
     long long b = (n + 255) / 256;
     const long long cap = 148LL * 16;
     half_to_float_kernel<<<(int)(b < 1 ? 1 : (b > cap ? cap : b)), 256, 0, stream>>>(reinterpret_cast<const __half *>(src), dst, n);
+}
+
+// Neighbour table of linkwalk.cuh: NBR[6*cell + face], face = 2*axis + (towards +axis).  For every cell the cell of
+// the same level behind the face if the hierarchy has it (possibly refined further), else the coarser leaf covering it.
+__global__ void neighbours_kernel(GridDesc G, int *__restrict__ nbr) {
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < G.cells; g += gridDim.x * blockDim.x) {
+        int level = 0;
+        while (level + 1 < G.levels && g >= G.off[level + 1]) level++;
+        // integer coordinates of the cell at its own level
+        int cx = 0, cy = 0, cz = 0, i = g - G.off[level];
+        for (int l = level, sh = 0; l > 0; l--, sh++) {
+            cx |= (i & 1) << sh; cy |= ((i >> 1) & 1) << sh; cz |= ((i >> 2) & 1) << sh;
+            i = G.par[G.off[l] + i - G.nxyz];
+        }
+        cx |= (i % G.nx) << level; cy |= ((i / G.nx) % G.ny) << level; cz |= (i / (G.nx * G.ny)) << level;
+        for (int f = 0; f < 6; f++) {
+            const int ax = f >> 1, sgn = (f & 1) ? 1 : -1;
+            const int tx = cx + (ax == 0 ? sgn : 0), ty = cy + (ax == 1 ? sgn : 0), tz = cz + (ax == 2 ? sgn : 0);
+            int e = -1;
+            if (tx >= 0 && ty >= 0 && tz >= 0 && tx < (G.nx << level) && ty < (G.ny << level) && tz < (G.nz << level)) {
+                int lev = 0;
+                int c = ((tz >> level) * G.ny + (ty >> level)) * G.nx + (tx >> level);
+                float rho = G.dens[c];
+                while (!is_leaf(rho) && lev < level) {
+                    const int base = link_index(rho);
+                    lev++;
+                    const int sh = level - lev;
+                    c = G.off[lev] + base + (((tz >> sh) & 1) << 2 | ((ty >> sh) & 1) << 1 | ((tx >> sh) & 1));
+                    rho = G.dens[c];
+                }
+                e = (lev << SOC_NBR_LEVEL_SHIFT) | c;
+            }
+            nbr[6 * (size_t)g + f] = e;
+        }
+    }
+}
+void launch_neighbours(const GridDesc &G, int *nbr, cudaStream_t stream) {
+    long long b = ((long long)G.cells + 255) / 256;
+    const long long cap = 148LL * 16;
+    neighbours_kernel<<<(int)(b < 1 ? 1 : (b > cap ? cap : b)), 256, 0, stream>>>(G, nbr);
 }

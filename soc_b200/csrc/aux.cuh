@@ -12,3 +12,4 @@ void launch_absorbed_scale(const GridDesc &G, float *fabs, int nfreq, float coef
 void launch_emission2(int c0, int c1, int nfreq, float factor, float length, const float *freq, const float *fabs_, const float *t,
                       float *emit, cudaStream_t stream);
 void launch_half_to_float(const void *src, float *dst, long long n, cudaStream_t stream);
+void launch_neighbours(const GridDesc &G, int *nbr, cudaStream_t stream);      // neighbour table of linkwalk.cuh, [6*cells]

@@ -18,6 +18,7 @@
 #include "sim.cuh"
 #include "emit.cuh"
 #include "walk.cuh"
+#include "linkwalk.cuh"
 
 #define FULL 0xffffffffu
 
@@ -1052,6 +1053,180 @@ __global__ void __launch_bounds__(256, 4) sim_walk_kernel(const __grid_constant_
     flush_counters(A, cnt);
 }
 
+template <int DEP, bool GENERAL>
+__global__ void __launch_bounds__(256, 4) sim_link_kernel(const __grid_constant__ SimArgs A) {
+    const GridDesc &G = A.G;
+    Counters cnt = { 0, 0, 0, 0 };
+    const int lane = threadIdx.x & 31;
+    const long long nlocal = (A.nunits - A.rank + A.world - 1) / A.world;
+    const bool cl = GENERAL && A.kind == SIM_CL;
+    const bool abu = GENERAL && A.with_abu;
+    LWalker w; w.cell = -1; w.level = 0;
+    const int *__restrict__ nbr = A.nbr;
+    int phase = WALK_LEAF, ax = 0;
+    bool in_roi_now = false;         // WITH_ROI_SAVE: the packet is inside the region of interest
+    float photons = 0.0f, free_path = 0.0f, tau = 0.0f;
+    int scat = 0, nstep = 0, eidx = -1;
+    unsigned long long rid = 0;
+    bool alive = false, more = true;
+    int icell = 0, iray = 0, nray = 0;
+    float pwei = 1.0f;
+    const int refill = A.refill;
+    for (;;) {
+        unsigned idle = __ballot_sync(FULL, !alive);
+        if (idle == FULL || (__popc(idle) >= refill && __any_sync(FULL, more))) {
+            bool need = !alive && more && iray >= nray;
+            unsigned nm = __ballot_sync(FULL, need);
+            unsigned long long q = 0;
+            bool got = false;
+            if (nm) {
+                int leader = __ffs(nm) - 1;
+                unsigned long long base = 0;
+                if (lane == leader) base = atomicAdd(A.work, (unsigned long long)__popc(nm));
+                base = __shfl_sync(FULL, base, leader);
+                if (need) {
+                    long long u = (long long)base + __popc(nm & ((1u << lane) - 1u));
+                    if (u >= nlocal) more = false;
+                    else { q = (unsigned long long)u * A.world + A.rank; got = true; }
+                }
+            }
+            if (got && cl) { icell = (int)q; iray = 0; nray = cl_rays(A, icell, pwei); got = false; }
+            if (cl && !alive && iray < nray) {
+                q = (unsigned long long)(unsigned)icell | ((unsigned long long)(unsigned)iray << 32);
+                iray++; got = true;
+            }
+            if (got) {
+                RngPhilox rng; rng.seed(A.phx, q);
+                Packet pk; pk.ind = -1; pk.level = 0; pk.eidx = -1; pk.rho = 0.0f;
+                bool emitted = true;
+                if (GENERAL && cl) emit_cl(A, rng, icell, pwei, pk);
+                else emitted = emit_source<RngPhilox, true>(A, rng, (int)(q / (unsigned)A.batch), (int)(q % (unsigned)A.batch), pk);
+                if (emitted) {
+                    start_packet(A, rng, pk, A.kind != SIM_HP);
+                    cnt.packets++;
+                    alive = pk.ind >= 0;
+                }
+                if (alive) {
+                    lw_init(G, w, pk.pos, pk.dir, pk.level, pk.ind, pk.rho);
+                    photons = pk.photons; free_path = pk.free_path; tau = 0.0f; scat = 0; nstep = 0; eidx = pk.eidx; rid = q;
+                    phase = WALK_LEAF;
+                    if (GENERAL && (A.roi.flags & 2)) in_roi_now = in_roi_xyz(A.roi, w.cx >> w.level, w.cy >> w.level, w.cz >> w.level);
+                }
+            }
+            if (!__any_sync(FULL, alive || more || iray < nray)) break;
+        }
+        // scatterings, several lanes at a time (see sim_fast_kernel)
+        {
+            const unsigned sm = __ballot_sync(FULL, alive && phase == WALK_SCATTER);
+            if (sm && (__popc(sm) >= A.sc_batch || !__any_sync(FULL, alive && phase != WALK_SCATTER))) {
+                if (alive && phase == WALK_SCATTER) {
+                    float fx, fy, fz;
+                    lw_fraction(w, fx, fy, fz);
+                    RngBlock rb(A.phx, rid, 0x10000u + (unsigned)scat);
+                    free_path = free_path_fast(A, rb, photons);
+                    const float u_ct = rb.uniform(), u_phi = rb.uniform();
+                    const float *csc = A.csc;
+                    if (GENERAL && A.with_msf) {
+                        const int oc = w.cell;
+                        csc += A.bins * msf_pick(A.abu, A.scav, A.ndust, __ldg(A.opt + 2 * (size_t)oc + 1), oc, rb.uniform());
+                    }
+                    float ct = __ldg(csc + clampi((int)(u_ct * A.bins), 0, A.bins - 1));
+                    vec3 nd = w.d;
+                    scatter_rotate(nd, ct, SOC_TWOPI * u_phi);
+                    lw_set_direction(w, nd, fx, fy, fz);
+                    tau = 0.0f;
+                    phase = WALK_LEAF;
+                }
+            }
+        }
+        bool d = false, sc = false;
+        float delta = 0.0f, ds = 0.0f, tmin = 0.0f;
+        int oind = 0;
+        const bool was_alive = alive;
+        const bool ready = alive && phase == WALK_LEAF;
+        if (ready) {
+            // physics of the current leaf
+            oind = w.cell;
+            tmin = fminf(w.tx, fminf(w.ty, w.tz));
+            ax = (w.tx <= w.ty && w.tx <= w.tz) ? 0 : ((w.ty <= w.tz) ? 1 : 2);
+            ds = fmaxf(tmin, 0.0f);
+            float kabs = A.kabs, ksca = A.ksca;
+            if (abu) { float2 o = __ldg(reinterpret_cast<const float2 *>(A.opt) + oind); kabs = o.x; ksca = o.y; }
+            const float dtau = ds * w.rho * ksca;
+            sc = free_path < tau + dtau;
+            d = true;
+            if (sc) {
+                scat++;
+                if (cl && scat > 20) { d = false; alive = false; }
+                ds = fminf(ds, (free_path - tau) * rcp_approx(ksca * w.rho));
+            } else tau += dtau;
+            const float tauA = ds * w.rho * kabs;
+            const float e = expf(-tauA);
+            delta = (tauA > SOC_TAULIM) ? (photons * (1.0f - e)) : (photons * tauA * (1.0f - 0.5f * tauA));
+            if (d) { photons *= e; nstep++; }
+        }
+        if (GENERAL && (A.save_int2 || A.with_ali)) {
+            if (d) {
+                if (A.with_ali && oind == eidx) red_add(&A.xab[oind], delta * A.tw);
+                else red_add(&A.acc[oind], delta);
+                if (A.save_int2) {
+                    red_add(&A.intx[oind], delta * w.d.x); red_add(&A.inty[oind], delta * w.d.y); red_add(&A.intz[oind], delta * w.d.z);
+                }
+            }
+        } else if (DEP == DEP_RED) {
+            if (d) red_add(&A.acc[oind], delta);
+        } else {
+            if (__any_sync(FULL, d && nstep < A.agg_steps)) {
+                unsigned act = __ballot_sync(FULL, d);
+                if (d) {
+                    unsigned peers = __match_any_sync(act, oind);
+                    if (peers != (1u << lane)) {
+                        delta = reduce_peers(peers, delta, lane);
+                        if (lane != __ffs(peers) - 1) d = false;
+                    }
+                }
+            }
+            if (d) red_add(&A.acc[oind], delta);
+        }
+        if (ready && alive) {
+            if (sc) {
+                w.tx -= ds; w.ty -= ds; w.tz -= ds;
+                phase = WALK_SCATTER;
+                if (!cl && scat > 20) { alive = false; phase = WALK_LEAF; }
+            } else {
+                w.tx -= tmin; w.ty -= tmin; w.tz -= tmin;
+                phase = WALK_CROSS;
+            }
+            if (nstep > A.max_steps) { alive = false; phase = WALK_LEAF; cnt.stuck++; }
+        }
+        // navigation: one table look-up per face crossing, then one descent per iteration while the cell entered is refined
+        if (alive && phase == WALK_DESCEND) phase = lw_descend(G, w, ax) ? WALK_LEAF : WALK_DESCEND;
+        if (alive && phase == WALK_CROSS) {
+            const int r0x = w.cx >> w.level, r0y = w.cy >> w.level, r0z = w.cz >> w.level;
+            phase = lw_cross(G, nbr, w, ax, A.mirror) ? WALK_LEAF : WALK_DESCEND;
+            if (w.cell < 0) alive = false;
+            else if (phase == WALK_DESCEND) phase = lw_descend(G, w, ax) ? WALK_LEAF : WALK_DESCEND;    // one level right away
+            if (alive && GENERAL && (A.roi.flags & 2)) {                 // WITH_ROI_SAVE: a new root cell? kernel_ASOC.c:615-643
+                const int rx = w.cx >> w.level, ry = w.cy >> w.level, rz = w.cz >> w.level;
+                if (rx != r0x || ry != r0y || rz != r0z) {
+                    const bool r = in_roi_xyz(A.roi, rx, ry, rz);
+                    if (r && !in_roi_now) {
+                        // entry point in root coordinates: cell origin + fractional position, scaled by the cell size
+                        float fx, fy, fz;
+                        lw_fraction(w, fx, fy, fz);
+                        const float sz = lw_size(w.level);
+                        vec3 rp = { ((float)w.cx + fx) * sz, ((float)w.cy + fy) * sz, ((float)w.cz + fz) * sz };
+                        roi_save_add(A.roi, rp, w.d, photons);
+                    }
+                    in_roi_now = r;
+                }
+            }
+        }
+        if (was_alive && !alive) { cnt.steps += nstep; cnt.scat += min(scat, 20); }
+    }
+    flush_counters(A, cnt);
+}
+
 static bool sim_is_general(const SimArgs &A) { return (A.roi.flags & 2) || A.kind == SIM_ROI || A.with_msf || A.with_abu || A.save_int2 || A.with_ali || A.kind == SIM_CL; }
 
 static void launch_walk(const SimArgs &A, int blocks, int threads, cudaStream_t stream) {
@@ -1059,7 +1234,15 @@ static void launch_walk(const SimArgs &A, int blocks, int threads, cudaStream_t 
     // combining lanes pays only when packets share cells: point-source packets (measured on the bench octree: the
     // background launch runs 4.6e10 cell-steps/s with plain adds, 4.0e10 with the match/reduce path)
     const bool red = (A.save_int2 || A.with_ali) || A.deposit == DEP_RED || A.kind != SIM_PS;
-    if (general) {
+    if (A.nbr != nullptr) {              // neighbour table: no climbs (linkwalk.cuh)
+        if (general) {
+            if (red) sim_link_kernel<DEP_RED, true><<<blocks, threads, 0, stream>>>(A);
+            else     sim_link_kernel<DEP_WARP, true><<<blocks, threads, 0, stream>>>(A);
+        } else {
+            if (red) sim_link_kernel<DEP_RED, false><<<blocks, threads, 0, stream>>>(A);
+            else     sim_link_kernel<DEP_WARP, false><<<blocks, threads, 0, stream>>>(A);
+        }
+    } else if (general) {
         if (red) sim_walk_kernel<DEP_RED, true><<<blocks, threads, 0, stream>>>(A);
         else     sim_walk_kernel<DEP_WARP, true><<<blocks, threads, 0, stream>>>(A);
     } else {

@@ -27,6 +27,7 @@ struct SimArgs {
     // order and fold_acc() un-bricks it (brick = 1)
     const float *__restrict__ dens_brick;
     int brick;
+    const int *__restrict__ nbr; // octrees: neighbour table [6*cells] of linkwalk.cuh (nullptr: climb through PAR, walk.cuh)
     int pend;                    // lean kernel: merge deposits into aligned 4-cell groups (red.global.add.v4.f32)
     int slab_xy, brick_by, brick_bz;   // nx*ny; index increments to the next brick along y and z
     // inputs
