@@ -784,6 +784,7 @@ static int sca_common(soc_context *c, ScaArgs &S, int kind, int flavour, int bat
     S.bins = P.bins; S.no_ps = P.no_ps; S.ps_method = P.ps_method; S.with_abu = P.with_abu; S.ffs = P.ffs;
     S.hpbg_weighted = P.hpbg_weighted; S.use_emweight = P.use_emweight; S.with_ali = 0;
     S.with_msf = P.with_msf; S.ndust = P.with_msf ? P.ndust : 1; S.mirror = P.mirror;
+    S.nbr = c->nbr;
     S.rank = c->rank; S.world = c->world; S.ref_geometry = c->geometry; S.ev_batch = c->sc_batch > 0 ? c->sc_batch : 3; S.nav_hops = c->nav_hops;
     long long ms = 100LL * ((long long)c->G.nx + c->G.ny + c->G.nz) << (c->G.levels - 1);
     S.max_steps = (int)(ms > INT_MAX ? INT_MAX : ms);

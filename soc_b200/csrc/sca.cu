@@ -13,6 +13,7 @@
 #include "sca.cuh"
 #include "emit.cuh"
 #include "walk.cuh"
+#include "linkwalk.cuh"
 
 #define FULL 0xffffffffu
 
@@ -505,6 +506,208 @@ __global__ void __launch_bounds__(256, 3) sca_walk_kernel(const __grid_constant_
     flush(S, cnt);
 }
 
+struct LScatterPoint {
+    float fx, fy, fz;
+    vec3 dir, gpos;
+    float rho;
+    int level, cell, cx, cy, cz;
+};
+__device__ __forceinline__ void ray_from_point(LWalker &w, const LScatterPoint &k, const vec3 &dir) {
+    w.level = k.level; w.cell = k.cell; w.cx = k.cx; w.cy = k.cy; w.cz = k.cz; w.rho = k.rho;
+    lw_set_direction(w, dir, k.fx, k.fy, k.fz);
+}
+
+// The same kernel on the neighbour table of linkwalk.cuh (octrees): a face crossing is one table look-up, no climbs.
+template <bool OCT>
+__global__ void __launch_bounds__(256, 3) sca_link_kernel(const __grid_constant__ ScaArgs S) {
+    const GridDesc &G = S.G;
+    ScaCounters cnt = { 0, 0, 0, 0, 0 };
+    const int lane = threadIdx.x & 31;
+    const long long nlocal = (S.nunits - S.rank + S.world - 1) / S.world;
+    LWalker w; w.cell = -1; w.level = 0;
+    LScatterPoint k;
+    const int *__restrict__ nbr = S.nbr;
+    int mode = RAY_IDLE, phase = WALK_LEAF, ax = 0, idir = 0, scat = 0, nstep = 0, nevent = 0;
+    float photons = 0.0f, free_path = 0.0f, tau = 0.0f;
+    float dleft = 0.0f, dscale = 1.0f;            // Healpix observer: distance left on the peel-off ray, 1/d^2
+    unsigned long long rid = 0;
+    bool more = true;
+    int icell = 0, iray = 0, nray = 0;            // SimRAM_CL: cell of this lane and its rays
+    float pwei = 1.0f;
+    const float cclamp = cos_clamp(S);
+    for (;;) {
+        unsigned idle = __ballot_sync(FULL, mode == RAY_IDLE);
+        if (idle == FULL || (__popc(idle) >= 8 && __any_sync(FULL, more))) {
+            bool need = mode == RAY_IDLE && more && iray >= nray;
+            unsigned nm = __ballot_sync(FULL, need);
+            bool got = false;
+            if (nm) {
+                int leader = __ffs(nm) - 1;
+                unsigned long long base = 0;
+                if (lane == leader) base = atomicAdd(S.work, (unsigned long long)__popc(nm));
+                base = __shfl_sync(FULL, base, leader);
+                if (need) {
+                    long long u = (long long)base + __popc(nm & ((1u << lane) - 1u));
+                    if (u >= nlocal) more = false;
+                    else {
+                        rid = (unsigned long long)u * S.world + S.rank;
+                        if (S.kind == SRC_CL) { icell = (int)rid; iray = 0; nray = cl_rays(S, icell, pwei); }
+                        else got = true;
+                    }
+                }
+            }
+            if (S.kind == SRC_CL && mode == RAY_IDLE && iray < nray) {
+                rid = (unsigned long long)(unsigned)icell | ((unsigned long long)(unsigned)iray << 32);
+                iray++; got = true;
+            }
+            if (got) {
+                RngPhilox rng; rng.seed(S.phx, rid);
+                Packet pk; pk.ind = -1; pk.level = 0; pk.rho = 0.0f;
+                bool emitted = true;
+                if (S.kind == SRC_CL) { emit_cl(S, rng, icell, pwei, pk); fix_direction(pk.dir); }
+                else emitted = emit_packet<RngPhilox, OCT>(S, rng, (int)(rid / (unsigned)S.batch), (int)(rid % (unsigned)S.batch), pk);
+                if (emitted) cnt.packets++; else pk.ind = -1;
+                photons = pk.photons; scat = 0; nstep = 0; nevent = 0; tau = 0.0f; phase = WALK_LEAF;
+                if (pk.ind >= 0) {
+                    lw_init(G, w, pk.pos, pk.dir, pk.level, pk.ind, pk.rho);
+                    k.level = w.level; k.cell = w.cell; k.cx = w.cx; k.cy = w.cy; k.cz = w.cz; k.rho = pk.rho; k.dir = pk.dir;
+                    k.fx = pk.pos.x - floorf(pk.pos.x); k.fy = pk.pos.y - floorf(pk.pos.y); k.fz = pk.pos.z - floorf(pk.pos.z);
+                    k.gpos = pk.pos;
+                    if (OCT) root_position(G, k.gpos, pk.level, pk.ind);
+                    ray_from_point(w, k, k.dir);
+                    if (S.ffs > 0) mode = RAY_FFS;
+                    else { free_path = uniform_fast_log(rng.uniform()); mode = RAY_MAIN; }
+                }
+            }
+            if (!__any_sync(FULL, mode != RAY_IDLE || more || iray < nray)) break;
+        }
+        // ---- rays that have reached the surface, several lanes at a time (the block is long and rare per lane) ----
+        const unsigned em = __ballot_sync(FULL, mode != RAY_IDLE && phase == WALK_END);
+        if (em && (__popc(em) >= S.ev_batch || !__any_sync(FULL, mode != RAY_IDLE && phase != WALK_END)))
+        if (mode != RAY_IDLE && phase == WALK_END) {
+            phase = WALK_LEAF; nstep = 0;
+            if (mode == RAY_PEEL) {                                  // kernel_ASOC_sca.c:1010-1046 / 1849-1885
+                cnt.peels++;
+                const vec3 od = w.d;
+                float cos_theta = clampf(k.dir.x * od.x + k.dir.y * od.y + k.dir.z * od.z, -cclamp, +cclamp);
+                const int kcell = k.cell;
+                // WITH_MSF: one Philox block per peel-off ray / scattering for the dust species draws
+                const float *dsc = S.dsc;
+                if (S.with_msf) {
+                    RngBlock rm(S.phx, rid, 0x20000u + (unsigned)(scat * 64 + idir));
+                    dsc += S.bins * msf_pick(S.abu, S.scav, S.ndust, __ldg(S.opt + 2 * (size_t)kcell + 1), kcell, rm.uniform());
+                }
+                float delta = photons * __expf(-tau) * __ldg(dsc + clampi((int)(S.bins * (1.0f + cos_theta) * 0.5f), 0, S.bins - 1));
+                if (S.nside > 0) {                                    // Healpix image seen from odir[0..2]
+                    const int ipix = ang2pix_ring(S.nside, atan2f(od.y, od.x), acosf(clampf(-od.z, -1.0f, 1.0f)));
+                    if ((unsigned)ipix < 12u * S.nside * S.nside) atomicAdd(&S.out[ipix], delta * dscale);
+                    idir = S.ndir;
+                } else {
+                    vec3 p = { k.gpos.x - S.centre.x, k.gpos.y - S.centre.y, k.gpos.z - S.centre.z };
+                    const float *ra = S.ora + 3 * idir, *de = S.ode + 3 * idir;
+                    int i = (int)((0.5f * S.npx - 0.00005f) + (p.x * ra[0] + p.y * ra[1] + p.z * ra[2]) / S.map_dx);
+                    int j = (int)((0.5f * S.npy - 0.00005f) + (p.x * de[0] + p.y * de[1] + p.z * de[2]) / S.map_dx);
+                    if (i >= 0 && j >= 0 && i < S.npx && j < S.npy) atomicAdd(&S.out[i + idir * S.npx * S.npy + j * S.npx], delta);
+                    idir++;
+                }
+                tau = 0.0f;
+                if (idir < S.ndir) {
+                    vec3 nd = { S.odir[3 * idir], S.odir[3 * idir + 1], S.odir[3 * idir + 2] };
+                    ray_from_point(w, k, nd);
+                } else if (scat == 30) mode = RAY_IDLE;               // MAX_SCATTERINGS, kernel_ASOC_sca.c:5
+                else {
+                    RngBlock rb(S.phx, rid, 0x10000u + (unsigned)(nevent++));
+                    const float u_ct = rb.uniform(), u_phi = rb.uniform(), u_fp = rb.uniform();
+                    const float *csc = S.csc;
+                    if (S.with_msf) csc += S.bins * msf_pick(S.abu, S.scav, S.ndust, __ldg(S.opt + 2 * (size_t)kcell + 1), kcell, rb.uniform());
+                    float ct = __ldg(csc + clampi((int)(u_ct * S.bins), 0, S.bins - 1));
+                    vec3 nd = k.dir;
+                    scatter_rotate(nd, ct, SOC_TWOPI * u_phi);
+                    free_path = uniform_fast_log(u_fp);
+                    k.dir = nd;
+                    ray_from_point(w, k, nd);
+                    mode = RAY_MAIN;
+                }
+            } else if (mode == RAY_FFS) {                            // kernel_ASOC_sca.c:888-910 / 1720-1750
+                if (S.flavour >= 2 && tau < 1.0e-22f) mode = RAY_IDLE;         // SimRAM_HP / CL: nothing on the line of sight
+                else {
+                    RngBlock rb(S.phx, rid, 0x10000u + (unsigned)(nevent++));
+                    float W;
+                    if (S.flavour == 0) { W = -expm1f(-tau); free_path = -logf(1.0f - W * rb.uniform()); }
+                    else                { W = 1.0f - (float)exp(-(double)tau); free_path = (float)(-log(1.0 - (double)(W * rb.uniform()))); }
+                    photons *= W;
+                    mode = (tau < 1.0e-22f) ? RAY_IDLE : RAY_MAIN;
+                    tau = 0.0f;
+                    ray_from_point(w, k, k.dir);
+                }
+            } else mode = RAY_IDLE;                                   // the packet itself has left the cloud
+        }
+        // ---- one cell of whichever ray the lane is tracing -----------------------------------------------------
+        const bool ready = mode != RAY_IDLE && phase == WALK_LEAF;
+        if (ready) {
+            const int oind = w.cell;
+            const float tmin = fminf(w.tx, fminf(w.ty, w.tz));
+            ax = (w.tx <= w.ty && w.tx <= w.tz) ? 0 : ((w.ty <= w.tz) ? 1 : 2);
+            float ds = fmaxf(tmin, 0.0f);
+            float kabs = S.kabs, ksca = S.ksca;
+            if (S.with_abu) { float2 o = __ldg(reinterpret_cast<const float2 *>(S.opt) + oind); kabs = o.x; ksca = o.y; }
+            cnt.steps++; nstep++;
+            bool go = true;
+            if (mode == RAY_PEEL) {
+                if (S.nside > 0) {                                    // the ray ends at the observer
+                    ds = fminf(ds, dleft);
+                    dleft -= ds;
+                    if (dleft <= 0.0f) { go = false; phase = WALK_END; }
+                }
+                tau += ds * w.rho * (kabs + ksca);
+            }
+            else if (mode == RAY_FFS) tau += ds * w.rho * ksca;
+            else {
+                const float dtau = ds * w.rho * ksca;
+                if (free_path < tau + dtau) {
+                    // scattering inside this cell: remember the point, start the peel-off rays
+                    ds = fminf(ds, (free_path - tau) * rcp_approx(ksca * w.rho));
+                    w.tx -= ds; w.ty -= ds; w.tz -= ds;
+                    lw_fraction(w, k.fx, k.fy, k.fz);
+                    k.level = w.level; k.cell = w.cell; k.cx = w.cx; k.cy = w.cy; k.cz = w.cz; k.rho = w.rho; k.dir = w.d;
+                    k.gpos.x += ds * w.d.x; k.gpos.y += ds * w.d.y; k.gpos.z += ds * w.d.z;
+                    photons *= __expf(-free_path * kabs / ksca);
+                    scat++; cnt.scat++;
+                    idir = 0; mode = RAY_PEEL; tau = 0.0f; nstep = 0;
+                    vec3 od;
+                    if (S.nside > 0) {
+                        od.x = S.odir[0] - k.gpos.x; od.y = S.odir[1] - k.gpos.y; od.z = S.odir[2] - k.gpos.z;
+                        const float d2 = od.x * od.x + od.y * od.y + od.z * od.z;
+                        const float id_ = rsqrtf(fmaxf(d2, 1.0e-30f));
+                        dleft = d2 * id_; dscale = id_ * id_;
+                        od.x *= id_; od.y *= id_; od.z *= id_;
+                        // the walker needs non-zero direction components
+                        if (fabsf(od.x) < 1.0e-6f) od.x = 1.0e-6f;
+                        if (fabsf(od.y) < 1.0e-6f) od.y = 1.0e-6f;
+                        if (fabsf(od.z) < 1.0e-6f) od.z = 1.0e-6f;
+                    } else { od.x = S.odir[0]; od.y = S.odir[1]; od.z = S.odir[2]; }
+                    ray_from_point(w, k, od);
+                    go = false;
+                } else {
+                    tau += dtau;
+                    k.gpos.x += ds * w.d.x; k.gpos.y += ds * w.d.y; k.gpos.z += ds * w.d.z;
+                }
+            }
+            if (go) { w.tx -= tmin; w.ty -= tmin; w.tz -= tmin; phase = WALK_CROSS; }
+            if (nstep > S.max_steps) { mode = RAY_IDLE; phase = WALK_LEAF; cnt.stuck++; }
+        }
+        // ---- navigation: table look-up per crossing, one descent per iteration while the cell entered is refined --------
+        if (mode != RAY_IDLE && phase == WALK_DESCEND) phase = lw_descend(G, w, ax) ? WALK_LEAF : WALK_DESCEND;
+        if (mode != RAY_IDLE && phase == WALK_CROSS) {
+            // only the packet itself is reflected by a mirror border; look-ahead and peel-off rays leave
+            phase = lw_cross(G, nbr, w, ax, mode == RAY_MAIN ? S.mirror : 0) ? WALK_LEAF : WALK_DESCEND;
+            if (w.cell < 0) phase = WALK_END;
+            else if (phase == WALK_DESCEND) phase = lw_descend(G, w, ax) ? WALK_LEAF : WALK_DESCEND;
+        }
+    }
+    flush(S, cnt);
+}
+
 }  // namespace
 
 void launch_sca(const ScaArgs &S, int rng_mode, int blocks, int threads, cudaStream_t stream) {
@@ -514,8 +717,9 @@ void launch_sca(const ScaArgs &S, int rng_mode, int blocks, int threads, cudaStr
         else if (!dbl) sca_item_kernel<true, false><<<blocks, threads, 0, stream>>>(S);
         else           sca_item_kernel<true, true><<<blocks, threads, 0, stream>>>(S);
     } else if (!S.ref_geometry) {
-        if (!oct) sca_walk_kernel<false><<<blocks, threads, 0, stream>>>(S);
-        else      sca_walk_kernel<true><<<blocks, threads, 0, stream>>>(S);
+        if (!oct)       sca_walk_kernel<false><<<blocks, threads, 0, stream>>>(S);
+        else if (S.nbr) sca_link_kernel<true><<<blocks, threads, 0, stream>>>(S);
+        else            sca_walk_kernel<true><<<blocks, threads, 0, stream>>>(S);
     } else {
         if (!oct)      sca_stream_kernel<false, false><<<blocks, threads, 0, stream>>>(S);
         else if (!dbl) sca_stream_kernel<true, false><<<blocks, threads, 0, stream>>>(S);
