@@ -330,6 +330,34 @@ def test_brick_layout_equals_reference_order(kind):
         assert abs(a.sum() - b.sum()) <= 3e-5 * a.sum()
 
 
+@pytest.mark.parametrize("kind", ["abs", "sca"])
+def test_neighbour_table_walker_equals_climb_walker(kind, monkeypatch):
+    """Octree production kernels: stepping through the per-cell neighbour table (linkwalk.cuh) follows the same Philox
+    streams through the same cells as the climb / cross / descend walker (walk.cuh); only the rounding of the face
+    distances differs, so a few packets may part ways at a cell corner."""
+    from soc_b200 import backend
+    cloud = synth.box_cloud(10, 6, 4, levels=4, refine_fraction=0.25)
+    res, cnt = [], []
+    for nbr in ("1", "0"):
+        monkeypatch.setenv("SOC_NBR", nbr)
+        if kind == "abs":
+            B = _backend(cloud, backend.RNG_PACKET, noabsorbed=0)
+            out = run_bg(batch=12, seed=0.37)(B)["int"]
+        else:
+            B = _backend(cloud, backend.RNG_PACKET, no_ps=1)
+            out = run_sca("ps", pspos=[(4.3, 3.2, 1.7)], batch=24, glob=1024, seed=0.37)(B)["out"]
+        res.append(out.astype(np.float64))
+        c = B.counters
+        cnt.append((c.packets, c.steps, c.scatterings))
+        assert c.reserved[0] == 0
+        B.close()
+    assert cnt[0][0] == cnt[1][0] and abs(int(cnt[0][1]) - int(cnt[1][1])) <= 2e-3 * cnt[1][1]
+    a, b = res
+    bad = np.abs(a - b) > 1e-5 * np.abs(b).max() + 1e-3 * np.abs(b)
+    assert bad.mean() < 0.05, "%d of %d differ" % (bad.sum(), bad.size)
+    assert abs(a.sum() - b.sum()) <= 5e-4 * b.sum()
+
+
 def test_invariants_at_full_size():
     """Size-independent properties at the 256^3 bench size (the oracle would need minutes here):
     no absorption opacity => TABS == 0; the absorbed energy is bounded by the injected energy and grows with
