@@ -47,6 +47,7 @@ struct soc_context {
     float *dens_brick;                 // regular grids with even dimensions: DENS in 2x2x2-brick order (lean kernel)
     int layout;                        // 1 = use the bricked copy where the kernel supports it
     int pend;                          // 1 = merged deposits (vector reds) in the lean kernel
+    int ahead;                         // 1 = look-ahead variant of the lean kernel (geometry one cell ahead, cp.async density ring)
     unsigned long long launches;
     soc_params P;
     bool have_params, have_grid;
@@ -114,6 +115,8 @@ int soc_create(int device_ordinal, soc_context **out) {
     if (const char *e = getenv("SOC_NBR")) c->use_nbr = atoi(e) != 0;                                                  // tuning knob
     c->pend = 0;          // measured on the bench step: 58.9 ms with, 59.0 ms without -- the merged reds trade L2 work for issue slots
     if (const char *e = getenv("SOC_PEND")) c->pend = atoi(e) != 0;                                                    // tuning knob
+    c->ahead = 1;
+    if (const char *e = getenv("SOC_AHEAD")) c->ahead = atoi(e);                                                       // tuning knob
     if (const char *e = getenv("SOC_LAYOUT")) c->layout = atoi(e) != 0;                                               // tuning knob
     if (const char *e = getenv("SOC_NAV_HOPS")) { int v = atoi(e); if (v >= 1 && v <= 8) c->nav_hops = v; }          // tuning knob
     if (const char *e = getenv("SOC_SC_BATCH")) { int v = atoi(e); if (v >= 1 && v <= 32) c->sc_batch = v; }   // tuning knob
@@ -465,7 +468,7 @@ static int sim_launch(soc_context *c, SimArgs &A, const char *who) {
         A.dens_brick = c->layout ? c->dens_brick : nullptr;
         A.brick = sim_uses_bricks(A, c->rng_mode) ? 1 : 0;
         A.nbr = c->nbr;
-        A.pend = c->pend;
+        A.pend = c->pend; A.ahead = c->ahead;
         A.slab_xy = A.G.nx * A.G.ny; A.brick_by = 4 * A.G.nx - 2; A.brick_bz = 2 * A.G.nx * A.G.ny - 4;
     }
     CU(cudaEventRecord(c->ev0, c->stream));

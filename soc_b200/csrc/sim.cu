@@ -878,6 +878,231 @@ __global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant_
 }
 
 // =================================================================================================================
+// Look-ahead kernel: the lean kernel with the geometry running one cell ahead of the physics.
+// ncu on the lean kernel: half of all stall samples sit on the one instruction that receives the density of the
+// next cell -- the gather is issued and consumed within the same iteration (~45 instructions apart), so every
+// iteration pays an L2 (or DRAM) round trip that only the other 7 warps of the scheduler can cover.  The DDA does
+// not depend on the density, so here
+//   * the geometry state (face distances, crossing counters, index) describes the entry point of cell A, the cell
+//     AFTER the one the physics works on; every iteration advances it by one cell and requests the density of the
+//     cell behind A with cp.async (LDGSTS: global -> a two-slot per-lane ring in shared memory, no register
+//     scoreboard, no register move that would force the wait);
+//   * the physics of cell i uses (rho, seg, ind) in registers; at the end of the iteration the density of A --
+//     requested one full iteration earlier -- is picked up from the ring after cp.async.wait_group 1;
+//   * a packet that scatters in cell i steps its geometry back by the unused part of the segment (one crossing to
+//     undo, the axis is remembered) and re-primes: one geometry-only iteration per emission / scattering;
+//   * the axis update is branch-free (the lean kernel ran three divergent paths, 35 issue slots per iteration).
+// Same packets, same Philox draws and same physics as the lean kernel; results differ by float rounding of the
+// stepped-back scattering positions only.  Reflecting borders (MIRROR) stay with the lean kernel.
+// =================================================================================================================
+__device__ __forceinline__ void cp_async_f32(unsigned saddr, const float *g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ float lds_f32(unsigned saddr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory"); return v; }
+
+// per-lane state word of the look-ahead kernel
+#define AH_UPM     0x7u        // bit a: the packet moves towards +axis a
+#define AH_AXA     0x70u       // axis bit (<<4) of the crossing from the physics cell into A
+#define AH_ALIVE   0x100u
+#define AH_WSC     0x200u      // waits at a scattering point
+#define AH_SLOT    0x400u      // ring slot the next density request writes (byte offset 1024 = one row of the ring)
+#define AH_PRIMED  0x800u      // (rho, seg, ind) of the physics cell are valid
+#define AH_AIN     0x1000u     // A lies inside the grid
+
+template <int DEP, bool BRICK, int CTAS>
+__global__ void __launch_bounds__(256, CTAS) sim_ahead_kernel(const __grid_constant__ SimArgs A) {
+    __shared__ float smem[DEP == DEP_TILE ? SOC_TILE_CELLS : 1];
+    __shared__ float s_ring[2 * 256];                        // slot s of lane t: s_ring[s * 256 + t]
+    __shared__ unsigned s_cnt[4];
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
+    float *tile = nullptr;
+    if (DEP == DEP_TILE) tile = tile_begin(A, smem); else __syncthreads();
+    const GridDesc &G = A.G;
+    const float *__restrict__ dens = BRICK ? A.dens_brick : G.dens;
+    const int lane = threadIdx.x & 31;
+    const float kabs = A.kabs, ksca = A.ksca;
+    const unsigned ring = (unsigned)__cvta_generic_to_shared(&s_ring[threadIdx.x]);
+    LeanPk<BRICK> f; f.ind = 0; f.u = 0; f.rho = 0.0f; f.sn = 0; f.upm = 0;        // f.ind = index of cell A
+    int ind = 0;                     // cell the physics works on
+    float seg = 0.0f;                // path length through it (at a scattering: the part not used)
+    unsigned st = 0u;                // AH_* bits
+    bool more = true;
+    for (;;) {
+        unsigned live = __ballot_sync(FULL, (st & AH_ALIVE) != 0u);
+        if (more ? (32 - __popc(live) >= A.refill) : (live == 0u)) {
+            if (!more) break;
+            const unsigned nm = ~live;
+            const int leader = __ffs(nm) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(A.work, (unsigned long long)__popc(nm));
+            base = __shfl_sync(FULL, base, leader);
+            if (!(st & AH_ALIVE)) {
+                const unsigned long long u = base + __popc(nm & ((1u << lane) - 1u));
+                if (u < (unsigned long long)A.nlocal) {
+                    const unsigned long long q = u * A.world + A.rank;
+                    RngPhilox rng; rng.seed(A.phx, q);
+                    Packet pk; pk.ind = -1; pk.level = 0; pk.eidx = -1; pk.rho = 0.0f;
+                    const int id = (int)(q / (unsigned)A.batch), III = (int)(q % (unsigned)A.batch);
+                    if (A.kind == SIM_PS)      emit_ps<SimArgs, RngPhilox, false>(A, rng, III, pk);
+                    else if (A.kind == SIM_BG) emit_bg<SimArgs, RngPhilox, false>(A, rng, id, pk);
+                    else                       emit_hp<SimArgs, RngPhilox, false>(A, rng, pk);
+                    start_packet(A, rng, pk, A.kind != SIM_HP);
+                    if (pk.ind >= 0) {
+                        const int ix = clampi((int)floorf(pk.pos.x), 0, G.nx - 1), iy = clampi((int)floorf(pk.pos.y), 0, G.ny - 1),
+                                  iz = clampi((int)floorf(pk.pos.z), 0, G.nz - 1);
+                        lean_set_direction<BRICK>(G, f, pk.dir, ix, iy, iz, pk.pos.x - (float)ix, pk.pos.y - (float)iy, pk.pos.z - (float)iz);
+                        st = (st & AH_SLOT) | AH_ALIVE | (unsigned)f.upm;
+                        f.ind = BRICK ? brick_index(ix, iy, iz, G.nx >> 1, G.ny >> 1) : (iz * G.ny + iy) * G.nx + ix;
+                        ind = f.ind;
+                        f.rho = pk.rho; f.photons = pk.photons; f.free_path = pk.free_path; f.tau = 0.0f;
+                        f.sn = 0; f.u = (unsigned)u;
+                    }
+                }
+            }
+            more = base + (unsigned long long)__popc(nm) < (unsigned long long)A.nlocal;
+            if (lane == leader) {
+                const unsigned long long left = base < (unsigned long long)A.nlocal ? (unsigned long long)A.nlocal - base : 0ull;
+                count_add(&s_cnt[0], A.counters + 0, (unsigned)min((unsigned long long)__popc(nm), left));
+            }
+            live = __ballot_sync(FULL, (st & AH_ALIVE) != 0u);
+            if (live == 0u && !more) break;
+        }
+        // ---- scatterings, batched over the lanes of the warp ------------------------------------------------------
+        {
+            const unsigned sm = __ballot_sync(FULL, (st & AH_WSC) != 0u);
+            if (sm != 0u && (__popc(sm) >= A.sc_batch || sm == live)) {
+                if (st & AH_WSC) {
+                    // the geometry stands at the entry of A: step back by `seg` (the unused part of the segment) into
+                    // the physics cell -- every face is that much further away, the face just crossed is `seg` ahead
+                    asm volatile("cp.async.wait_all;" ::: "memory");      // the abandoned request of A must not land later
+                    const bool ax = (st & 0x10u) != 0u, ay = (st & 0x20u) != 0u, az = (st & 0x40u) != 0u;
+                    f.tx = ax ? seg : f.tx + seg; f.ty = ay ? seg : f.ty + seg; f.tz = az ? seg : f.tz + seg;
+                    f.cx += ax; f.cy += ay; f.cz += az;
+                    const bool ux = (st & 1u) != 0u, uy = (st & 2u) != 0u, uz = (st & 4u) != 0u;
+                    const float adx = rcp_approx(f.rdx), ady = rcp_approx(f.rdy), adz = rcp_approx(f.rdz);
+                    const float px_ = f.tx * adx, py_ = f.ty * ady, pz_ = f.tz * adz;
+                    const float fx = ux ? 1.0f - px_ : px_, fy = uy ? 1.0f - py_ : py_, fz = uz ? 1.0f - pz_ : pz_;
+                    const int ix = ux ? G.nx - 1 - f.cx : f.cx, iy = uy ? G.ny - 1 - f.cy : f.cy, iz = uz ? G.nz - 1 - f.cz : f.cz;
+                    RngBlock rb(A.phx, (unsigned long long)f.u * A.world + A.rank, 0x10000u + LEAN_SCAT(f.sn));
+                    f.free_path = free_path_fast(A, rb, f.photons);
+                    const float ct = __ldg(A.csc + clampi((int)(rb.uniform() * A.bins), 0, A.bins - 1));
+                    vec3 nd = { ux ? adx : -adx, uy ? ady : -ady, uz ? adz : -adz };
+                    scatter_rotate(nd, ct, SOC_TWOPI * rb.uniform());
+                    lean_set_direction<BRICK>(G, f, nd, ix, iy, iz, fx, fy, fz);
+                    st = (st & AH_SLOT) | AH_ALIVE | (unsigned)f.upm;          // not primed, not waiting
+                    f.ind = ind;
+                    f.tau = 0.0f;
+                }
+            }
+        }
+        // ---- one iteration: physics of cell `ind`, geometry from A to the cell behind it --------------------------
+        const bool run = (st & (AH_ALIVE | AH_WSC)) == AH_ALIVE;
+        const bool phys = (st & (AH_ALIVE | AH_WSC | AH_PRIMED)) == (AH_ALIVE | AH_PRIMED);
+        float delta = 0.0f, len = seg;
+        bool sc = false;
+        if (phys) {
+            const float krho = ksca * f.rho;
+            const float tend = fmaf(seg, krho, f.tau);
+            sc = f.free_path < tend;
+            const float tsc = (f.free_path - f.tau) * rcp_approx(krho);
+            if (sc) { len = fminf(seg, tsc); f.sn += 1u << 24; } else f.tau = tend;
+            const float x = len * f.rho * kabs;
+            const float e = exp2f_approx(-1.4426950408889634f * x);
+            const float ser = x * fmaf(x, fmaf(x, 0.16666667f, -0.5f), 1.0f);
+            const float dfrac = (x < 0.01f) ? ser : (1.0f - e);
+            delta = f.photons * dfrac;
+            f.photons -= delta;
+            f.sn++;
+        }
+        // ---- deposit ----------------------------------------------------------------------------------------------
+        bool d = phys;
+        if (DEP != DEP_RED) {
+            if (__any_sync(FULL, d && LEAN_STEPS(f.sn) < (unsigned)A.agg_steps)) {
+                const unsigned act = __ballot_sync(FULL, d);
+                if (d) {
+                    const unsigned peers = __match_any_sync(act, ind);
+                    if (peers != (1u << lane)) {
+                        delta = reduce_peers(peers, delta, lane);
+                        if (lane != __ffs(peers) - 1) d = false;
+                    }
+                }
+            }
+        }
+        if (d) {
+            bool in_tile = false;
+            if (DEP == DEP_TILE) {
+                if ((unsigned)(ind - A.tile_lo) < (unsigned)A.tile_span) {
+                    // coordinates of the physics cell: the counters belong to A, one crossing (axis AH_AXA) further on
+                    const int kx = f.cx + ((st >> 4) & 1u), ky = f.cy + ((st >> 5) & 1u), kz = f.cz + ((st >> 6) & 1u);
+                    const int ix = (st & 1u) ? G.nx - 1 - kx : kx, iy = (st & 2u) ? G.ny - 1 - ky : ky,
+                              iz = (st & 4u) ? G.nz - 1 - kz : kz;
+                    const unsigned ux = (unsigned)(ix - A.tile_x0), uy = (unsigned)(iy - A.tile_y0), uz = (unsigned)(iz - A.tile_z0);
+                    if (ux < SOC_TILE_N && uy < SOC_TILE_N && uz < SOC_TILE_N) {
+                        atomicAdd(&tile[(uz * SOC_TILE_N + uy) * SOC_TILE_N + ux], delta);
+                        in_tile = true;
+                    }
+                }
+            }
+            if (!in_tile) red_add(&A.acc[ind], delta);
+        }
+        if (run) {
+            if (sc) {
+                st |= AH_WSC;
+                seg -= len;                                      // distance back from the entry of A to the scattering point
+                if (LEAN_SCAT(f.sn) > 20u) st &= ~(AH_ALIVE | AH_WSC);
+            } else if ((st & (AH_PRIMED | AH_AIN)) == AH_PRIMED) {
+                st &= ~AH_ALIVE;                                 // the physics cell was the last one inside the grid
+            } else {
+                // geometry: from the entry of A (unprimed: from the packet's position in its cell) to the next face
+                const float tmin = fminf(f.tx, fminf(f.ty, f.tz));
+                const bool px = f.tx == tmin, py = !px && (f.ty == tmin), pz = !px && !py;
+                const unsigned abit = px ? 1u : (py ? 2u : 4u);
+                const int far_yz = BRICK ? (py ? A.brick_by : A.brick_bz) : (py ? G.nx : A.slab_xy);
+                const int far = px ? (BRICK ? 7 : 1) : far_yz;
+                const int mag = (BRICK && (((unsigned)f.ind ^ st) & abit) != 0u) ? (int)abit : far;
+                const int nind = f.ind + ((st & abit) ? mag : -mag);
+                const int crem = px ? f.cx : (py ? f.cy : f.cz);
+                const bool inb = crem > 0;
+                const unsigned wslot = ring + (st & AH_SLOT);
+                if (inb) cp_async_f32(wslot, dens + nind);
+                cp_async_commit();
+                f.tx = px ? f.rdx : f.tx - tmin; f.ty = py ? f.rdy : f.ty - tmin; f.tz = pz ? f.rdz : f.tz - tmin;
+                f.cx -= px; f.cy -= py; f.cz -= pz;
+                if (st & AH_PRIMED) {                            // density of A, requested one iteration ago
+                    cp_async_wait1();
+                    f.rho = lds_f32(ring + ((st & AH_SLOT) ^ AH_SLOT));
+                }
+                ind = f.ind; f.ind = nind; seg = tmin;
+                st = ((st & ~(AH_AXA | AH_AIN)) ^ AH_SLOT) | AH_PRIMED | (abit << 4) | (inb ? AH_AIN : 0u);
+            }
+            bool stuck = false;
+            if (LEAN_STEPS(f.sn) > (unsigned)A.max_steps) { st &= ~(AH_ALIVE | AH_WSC); stuck = true; }
+            if (!(st & AH_ALIVE)) {                             // packet finished: once per packet
+                count_add(&s_cnt[1], A.counters + 1, LEAN_STEPS(f.sn));
+                count_add(&s_cnt[2], A.counters + 2, min(LEAN_SCAT(f.sn), 20u));
+                if (stuck) count_add(&s_cnt[3], A.counters + 3, 1u);
+            }
+        }
+    }
+    if (DEP == DEP_TILE) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < SOC_TILE_CELLS; i += blockDim.x) {
+            const float v = tile[i];
+            if (v != 0.0f) {
+                const int ux = i % SOC_TILE_N, uy = (i / SOC_TILE_N) % SOC_TILE_N, uz = i / (SOC_TILE_N * SOC_TILE_N);
+                const int ix = A.tile_x0 + ux, iy = A.tile_y0 + uy, iz = A.tile_z0 + uz;
+                if (ix < G.nx && iy < G.ny && iz < G.nz)
+                    red_add(&A.acc[BRICK ? brick_index(ix, iy, iz, G.nx >> 1, G.ny >> 1) : (iz * G.ny + iy) * G.nx + ix], v);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 4 && s_cnt[threadIdx.x]) atomicAdd(A.counters + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
+}
+
+// =================================================================================================================
 // Walk kernel: the production path on octree clouds (LEVELS > 1).  Same persistent-warp / refill / Philox /
 // scratch-accumulator design as the fast kernel; the stepping is the incremental octree walk of walk.cuh, taken
 // one hop (climb / cross / descend) per loop iteration so that lanes with long climbs do not idle the warp.
@@ -1282,12 +1507,41 @@ struct RngMwcItem : RngMwc {
 
 }  // namespace
 
+template <int DEP, bool BRICK, int CTAS>
+static void launch_ahead_dep(const SimArgs &A, int blocks, int threads, cudaStream_t stream) {
+    static int per_sm = 0, sms = 0;                   // resident CTAs of this instantiation: the persistent grid is sms x per_sm
+    if (per_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sim_ahead_kernel<DEP, BRICK, CTAS>, threads, 0);
+        if (per_sm < 1) per_sm = 1;
+    }
+    if (blocks > sms * per_sm) blocks = sms * per_sm;
+    sim_ahead_kernel<DEP, BRICK, CTAS><<<blocks, threads, 0, stream>>>(A);
+}
+
+template <bool BRICK, int CTAS>
+static void launch_ahead(const SimArgs &A, int dep, int blocks, int threads, cudaStream_t stream) {
+    if (dep == DEP_RED)       launch_ahead_dep<DEP_RED, BRICK, CTAS>(A, blocks, threads, stream);
+    else if (dep == DEP_WARP) launch_ahead_dep<DEP_WARP, BRICK, CTAS>(A, blocks, threads, stream);
+    else                      launch_ahead_dep<DEP_TILE, BRICK, CTAS>(A, blocks, threads, stream);
+}
+
 template <bool BRICK, bool PEND>
 static void launch_lean(SimArgs A, int dep, int blocks, int threads, cudaStream_t stream) {
     if (BRICK && dep == DEP_TILE) {          // z-slab of the shared-memory tile in bricked order
         const int slab = 2 * A.G.nx * A.G.ny, z0 = A.tile_z0;
         A.tile_lo = (z0 >> 1) * slab;
         A.tile_span = (((z0 + SOC_TILE_N - 1) >> 1) - (z0 >> 1) + 1) * slab;
+    }
+    // geometry one cell ahead of the physics (cp.async density ring).  Measured on the bench step: background launch
+    // (plain adds) 60.4 -> 57.9 ms; the point-source launch with the shared-memory tile runs 66.6 ms on the lean kernel,
+    // 77 ms (3 CTAs / SM) or 72 ms (4 CTAs / SM) here, so ahead = 1 takes the plain-add launches only
+    if (A.ahead && !PEND && A.mirror == 0 && (dep == DEP_RED || A.ahead > 1)) {
+        if (A.ahead == 2) launch_ahead<BRICK, 4>(A, dep, blocks, threads, stream);
+        else              launch_ahead<BRICK, 3>(A, dep, blocks, threads, stream);
+        return;
     }
     if (dep == DEP_RED)       sim_lean_kernel<DEP_RED, BRICK, PEND><<<blocks, threads, 0, stream>>>(A);
     else if (dep == DEP_WARP) sim_lean_kernel<DEP_WARP, BRICK, PEND><<<blocks, threads, 0, stream>>>(A);

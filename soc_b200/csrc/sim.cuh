@@ -29,6 +29,7 @@ struct SimArgs {
     int brick;
     const int *__restrict__ nbr; // octrees: neighbour table [6*cells] of linkwalk.cuh (nullptr: climb through PAR, walk.cuh)
     int pend;                    // lean kernel: merge deposits into aligned 4-cell groups (red.global.add.v4.f32)
+    int ahead;                   // lean kernel: geometry one cell ahead of the physics (sim_ahead_kernel)
     int slab_xy, brick_by, brick_bz;   // nx*ny; index increments to the next brick along y and z
     // inputs
     const float *__restrict__ emit, *__restrict__ emwei, *__restrict__ opt;
