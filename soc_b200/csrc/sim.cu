@@ -686,6 +686,7 @@ __global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant_
     const float kabs = A.kabs, ksca = A.ksca;
     LeanPk<BRICK> f; f.ind = 0; f.u = 0; f.rho = 0.0f; f.sn = 0;
     bool alive = false, wsc = false;
+    int tskip = 0;                   // DEP_TILE: the packet cannot be inside the tile during its next tskip steps
     bool more = true;                                        // warp-uniform: the work counter has not run out yet
     for (;;) {
         unsigned live = __ballot_sync(FULL, alive);
@@ -708,7 +709,7 @@ __global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant_
                     else                       emit_hp<SimArgs, RngPhilox, false>(A, rng, pk);
                     start_packet(A, rng, pk, A.kind != SIM_HP);
                     if (pk.ind >= 0) {
-                        alive = true; wsc = false;
+                        alive = true; wsc = false; tskip = 0;
                         const int ix = clampi((int)floorf(pk.pos.x), 0, G.nx - 1), iy = clampi((int)floorf(pk.pos.y), 0, G.ny - 1),
                                   iz = clampi((int)floorf(pk.pos.z), 0, G.nz - 1);
                         lean_set_direction<BRICK>(G, f, pk.dir, ix, iy, iz, pk.pos.x - (float)ix, pk.pos.y - (float)iy, pk.pos.z - (float)iz);
@@ -759,9 +760,11 @@ __global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant_
             // index increment: x-fastest order +-(1, nx, nx*ny); bricks: +-(1,2,4) inside the brick (the parity bit of the
             // axis, a bit of the index itself, tells on which side of its brick the cell lies), else to the next brick
             const int abit = px ? 1 : (py ? 2 : 4);
-            int mag;
-            if (BRICK) mag = (((f.ind ^ f.upm) & abit) != 0) ? abit : (px ? 7 : (py ? A.brick_by : A.brick_bz));
-            else       mag = px ? 1 : (py ? G.nx : A.slab_xy);
+            // (written with the y/z stride as a value of its own: nvcc 12.9 folds `px ? 7 : (py ? by : bz)` to
+            //  `px ? 7 : bz` once the kernel also holds pz = !px && !py -- seen in the PTX, so keep this form)
+            const int far_yz = BRICK ? (py ? A.brick_by : A.brick_bz) : (py ? G.nx : A.slab_xy);
+            const int far = px ? (BRICK ? 7 : 1) : far_yz;
+            const int mag = (BRICK && ((f.ind ^ f.upm) & abit) != 0) ? abit : far;
             const int step = (f.upm & abit) ? mag : -mag;
             const int crem = px ? f.cx : (py ? f.cy : f.cz);
             nind = f.ind + step;
@@ -796,18 +799,18 @@ __global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant_
         }
         if (d) {
             bool in_tile = false;
-            if (DEP == DEP_TILE) {
-                // tile_lo/tile_span select the z-slab of the tile in the layout in use (set by the host)
-                if ((unsigned)(oind - A.tile_lo) < (unsigned)A.tile_span) {
-                    // coordinates at the time of the deposit: the crossing counters have not been updated yet
-                    const int ix = (f.upm & 1) ? G.nx - 1 - f.cx : f.cx, iy = (f.upm & 2) ? G.ny - 1 - f.cy : f.cy,
-                              iz = (f.upm & 4) ? G.nz - 1 - f.cz : f.cz;
-                    const unsigned ux = (unsigned)(ix - A.tile_x0), uy = (unsigned)(iy - A.tile_y0), uz = (unsigned)(iz - A.tile_z0);
-                    if (ux < SOC_TILE_N && uy < SOC_TILE_N && uz < SOC_TILE_N) {
-                        atomicAdd(&tile[(uz * SOC_TILE_N + uy) * SOC_TILE_N + ux], delta);
-                        in_tile = true;
-                    }
-                }
+            if (DEP == DEP_TILE && tskip == 0) {
+                // coordinates at the time of the deposit: the crossing counters have not been updated yet.  A cell at
+                // Chebyshev distance D from the tile cannot be followed by a tile cell within the next D - 1 steps (one
+                // step moves one cell along one axis), so the test is skipped that long.
+                const int ix = (f.upm & 1) ? G.nx - 1 - f.cx : f.cx, iy = (f.upm & 2) ? G.ny - 1 - f.cy : f.cy,
+                          iz = (f.upm & 4) ? G.nz - 1 - f.cz : f.cz;
+                const int ux = ix - A.tile_x0, uy = iy - A.tile_y0, uz = iz - A.tile_z0;
+                const int tfar = max(max(max(-ux, ux - (SOC_TILE_N - 1)), max(-uy, uy - (SOC_TILE_N - 1))), max(-uz, uz - (SOC_TILE_N - 1)));
+                if (tfar <= 0) {
+                    atomicAdd(&tile[(uz * SOC_TILE_N + uy) * SOC_TILE_N + ux], delta);
+                    in_tile = true;
+                } else tskip = tfar;                             // decremented below: tfar - 1 steps without the test
             }
             if (!in_tile) {
                 if (PEND) {
@@ -828,21 +831,22 @@ __global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant_
         }
         if (run) {
             f.tx -= tmin; f.ty -= tmin; f.tz -= tmin;
+            if (DEP == DEP_TILE && tskip > 0) tskip--;
             if (sc) {
                 wsc = true;
                 if (LEAN_SCAT(f.sn) > 20u) { alive = false; wsc = false; }
             } else {
                 const int abit_ = px ? 1 : (py ? 2 : 4);
-                if (!inb && (A.mirror & (px ? 3 : (py ? 12 : 48)) & ((f.upm & abit_) ? 42 : 21))) {
+                if (A.mirror != 0 && !inb && (A.mirror & (px ? 3 : (py ? 12 : 48)) & ((f.upm & abit_) ? 42 : 21))) {
                     // reflecting border: same cell, the packet turns around on this axis
                     f.upm ^= abit_;
                     if (px)      { f.cx = G.nx - 1; f.tx = f.rdx; }
                     else if (py) { f.cy = G.ny - 1; f.ty = f.rdy; }
                     else         { f.cz = G.nz - 1; f.tz = f.rdz; }
-                } else {
-                    if (px)      { f.cx--; f.tx = f.rdx; }
-                    else if (py) { f.cy--; f.ty = f.rdy; }
-                    else         { f.cz--; f.tz = f.rdz; }
+                } else {                                         // branch-free: the three axes are selects, not code paths
+                    const bool pz = !px && !py;
+                    f.tx = px ? f.rdx : f.tx; f.ty = py ? f.rdy : f.ty; f.tz = pz ? f.rdz : f.tz;
+                    f.cx -= px; f.cy -= py; f.cz -= pz;
                     f.ind = nind; f.rho = rho_n;
                     alive = inb;
                 }
@@ -928,6 +932,7 @@ __global__ void __launch_bounds__(256, CTAS) sim_ahead_kernel(const __grid_const
     int ind = 0;                     // cell the physics works on
     float seg = 0.0f;                // path length through it (at a scattering: the part not used)
     unsigned st = 0u;                // AH_* bits
+    int tskip = 0;                   // DEP_TILE: the packet cannot be inside the tile during its next tskip steps
     bool more = true;
     for (;;) {
         unsigned live = __ballot_sync(FULL, (st & AH_ALIVE) != 0u);
@@ -954,6 +959,7 @@ __global__ void __launch_bounds__(256, CTAS) sim_ahead_kernel(const __grid_const
                                   iz = clampi((int)floorf(pk.pos.z), 0, G.nz - 1);
                         lean_set_direction<BRICK>(G, f, pk.dir, ix, iy, iz, pk.pos.x - (float)ix, pk.pos.y - (float)iy, pk.pos.z - (float)iz);
                         st = (st & AH_SLOT) | AH_ALIVE | (unsigned)f.upm;
+                        tskip = 0;
                         f.ind = BRICK ? brick_index(ix, iy, iz, G.nx >> 1, G.ny >> 1) : (iz * G.ny + iy) * G.nx + ix;
                         ind = f.ind;
                         f.rho = pk.rho; f.photons = pk.photons; f.free_path = pk.free_path; f.tau = 0.0f;
@@ -1032,21 +1038,22 @@ __global__ void __launch_bounds__(256, CTAS) sim_ahead_kernel(const __grid_const
         }
         if (d) {
             bool in_tile = false;
-            if (DEP == DEP_TILE) {
-                if ((unsigned)(ind - A.tile_lo) < (unsigned)A.tile_span) {
-                    // coordinates of the physics cell: the counters belong to A, one crossing (axis AH_AXA) further on
-                    const int kx = f.cx + ((st >> 4) & 1u), ky = f.cy + ((st >> 5) & 1u), kz = f.cz + ((st >> 6) & 1u);
-                    const int ix = (st & 1u) ? G.nx - 1 - kx : kx, iy = (st & 2u) ? G.ny - 1 - ky : ky,
-                              iz = (st & 4u) ? G.nz - 1 - kz : kz;
-                    const unsigned ux = (unsigned)(ix - A.tile_x0), uy = (unsigned)(iy - A.tile_y0), uz = (unsigned)(iz - A.tile_z0);
-                    if (ux < SOC_TILE_N && uy < SOC_TILE_N && uz < SOC_TILE_N) {
-                        atomicAdd(&tile[(uz * SOC_TILE_N + uy) * SOC_TILE_N + ux], delta);
-                        in_tile = true;
-                    }
-                }
+            if (DEP == DEP_TILE && tskip == 0) {
+                // coordinates of the physics cell: the counters belong to A, one crossing (axis AH_AXA) further on.  A cell
+                // at Chebyshev distance D from the tile is not followed by a tile cell within D - 1 steps: test skipped
+                const int kx = f.cx + ((st >> 4) & 1u), ky = f.cy + ((st >> 5) & 1u), kz = f.cz + ((st >> 6) & 1u);
+                const int ix = (st & 1u) ? G.nx - 1 - kx : kx, iy = (st & 2u) ? G.ny - 1 - ky : ky,
+                          iz = (st & 4u) ? G.nz - 1 - kz : kz;
+                const int ux = ix - A.tile_x0, uy = iy - A.tile_y0, uz = iz - A.tile_z0;
+                const int tfar = max(max(max(-ux, ux - (SOC_TILE_N - 1)), max(-uy, uy - (SOC_TILE_N - 1))), max(-uz, uz - (SOC_TILE_N - 1)));
+                if (tfar <= 0) {
+                    atomicAdd(&tile[(uz * SOC_TILE_N + uy) * SOC_TILE_N + ux], delta);
+                    in_tile = true;
+                } else tskip = tfar;
             }
             if (!in_tile) red_add(&A.acc[ind], delta);
         }
+        if (DEP == DEP_TILE && phys && tskip > 0) tskip--;
         if (run) {
             if (sc) {
                 st |= AH_WSC;
