@@ -25,6 +25,7 @@
  *   soc_ps_tau                              kernel PSTau (kernel_ASOC_map.c:1545; ASOC.py:3576-3644)
  *   soc_mapping / soc_healpix_mapping       kernels Mapping / HealpixMapping
  *                                           (kernel_ASOC_map.c:496, 890; ASOC.py:3127-3139)
+ *   soc_mapping_levels                      kernel Mapping of kernel_ASOC_map_H.c:380 (ASOC.py:3320-3440)
  *   soc_sca_zero_out / soc_sca_ps / _pb     kernels zero_out / SimRAM_PS / SimRAM_PB / SimRAM_HP / SimRAM_CL of
  *     / soc_sca_hp / soc_sca_cl             kernel_ASOC_sca.c:14, 1462, 471, 40, 1098 (ASOCS.py:515, 665-708)
  * New (no counterpart in the single-device reference):
@@ -190,6 +191,13 @@ int  soc_mapping(soc_context *ctx, float map_dx, int npix_x, int npix_y, const f
                  const float de[3], float abs, float sca, const float centre[3], const float intobs[3],
                  int save_colden);
 int  soc_healpix_mapping(soc_context *ctx, int nside, float abs, float sca, const float intobs[3], int save_colden);
+/* Per-level Mapping (kernel_ASOC_map_H.c:380; ASOC.py:3320-3440, ini `mapping nx ny dx 999`): one image per hierarchy
+ * level, MAP[LEVELS*npix_y*npix_x] (level-major); with save_colden the column density (x LENGTH) goes to SAVETAU.
+ * The reference's copy of Index() in that file drops rays that climb into root-grid leaves; this
+ * entry point steps like soc_mapping. */
+int  soc_mapping_levels(soc_context *ctx, float map_dx, int npix_x, int npix_y, const float dir[3], const float ra[3],
+                        const float de[3], float abs, float sca, const float centre[3], const float intobs[3],
+                        int save_colden);
 
 /* PSTau (kernel_ASOC_map.c:1545; ASOC.py:3576-3644): optical depth and column density (x LENGTH) from each of the
  * first `no` point sources in PSPOS towards the observer direction `dir`; results are copied to the host arrays. */

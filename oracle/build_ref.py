@@ -139,6 +139,40 @@ def build(cfg, force=False, verbose=False):
     return out
 
 
+def lib_path_levels(cfg):
+    return os.path.join(OUTDIR, "libsocrefH_%s_a%d_c%d.so" % (tag_of(cfg), int(cfg.get("USE_ABU", 0)), int(cfg.get("WITH_COLDEN", 0))))
+
+
+def build_levels(cfg, force=False, verbose=False):
+    """Per-level map kernel (kernel_ASOC_map_H.c: Mapping) as a library of its own.  The file is cut after Mapping:
+    its HealpixMapping refers to OPT without having the argument under USE_ABU, the polarisation kernels use macros
+    the map run of ASOC.py never defines.  USE_ABU and
+    WITH_COLDEN are the file's own switches; the reference host defines neither (ASOC.py:3329-3330)."""
+    out = lib_path_levels(cfg)
+    if os.path.exists(out) and not force:
+        return out
+    src = os.path.join(REFDIR, "kernel_ASOC_map_H.c")
+    if not os.path.exists(src):
+        return None
+    os.makedirs(OUTDIR, exist_ok=True)
+    tmp = tempfile.mkdtemp(prefix="socrefh_")
+    try:
+        txt = open(src).read()
+        cut = txt.index("__kernel void HealpixMapping(")   # keep Mapping only: with USE_ABU the file's HealpixMapping does not compile
+        open(os.path.join(tmp, "kernel_ASOC_map_H.c"), "w").write(txt[:cut])
+        cmd = ["g++", "-std=c++17", "-fpermissive", "-w", "-O2", "-fopenmp", "-fPIC", "-ffp-contract=off", "-shared",
+               "-I", tmp, "-I", SHIM] + macro_flags(cfg) + ["-DNSIDE=%d" % cfg.get("MAP_NSIDE", cfg["NX"])]
+        if cfg.get("USE_ABU", 0):
+            cmd.append("-DUSE_ABU=1")
+        cmd += ["-DWITH_COLDEN=%d" % int(cfg.get("WITH_COLDEN", 0)), os.path.join(SHIM, "ref_maph.cpp"), "-o", out]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return out
+
+
 if __name__ == "__main__":
     # tiny CLI: build_ref.py NX NY NZ LEVELS CELLS [KEY=VAL ...]
     a = sys.argv[1:]

@@ -27,7 +27,7 @@ class OrcParams(C.Structure):
         "nx", "ny", "nz", "levels", "cells", "bins", "no_ps", "ps_method", "with_abu", "with_ali", "noabsorbed",
         "save_intensity", "use_emweight", "hpbg_weighted", "ffs", "step_weight", "level_threshold", "sca_exact_level")] + \
         [(n, C.c_float) for n in ("sw_a", "sw_b", "length", "factor", "adhoc", "reserved1")] + \
-        [(n, C.c_int32) for n in ("with_msf", "ndust", "mirror", "map_interpolation", "hg_test", "mirror_exact", "r2b", "r2c",
+        [(n, C.c_int32) for n in ("with_msf", "ndust", "mirror", "map_interpolation", "hg_test", "mirror_exact", "maph_literal", "r2c",
                                   "with_roi_load", "with_roi_save", "roi_map", "roi_step", "roi_nside")] + \
         [("roi", C.c_int32 * 6), ("roi_dim", C.c_int32 * 3)]
 
@@ -103,6 +103,7 @@ class Oracle:
         P.with_msf, P.ndust, P.mirror = opts.get("with_msf", 0), opts.get("ndust", 1), opts.get("mirror", 0)
         P.map_interpolation = opts.get("map_interpolation", 0)
         P.hg_test = opts.get("hg_test", 0)
+        P.maph_literal = opts.get("maph_literal", 0)
         P.with_roi_load, P.with_roi_save = opts.get("with_roi_load", 0), opts.get("with_roi_save", 0)
         P.roi_map, P.roi_step, P.roi_nside = opts.get("roi_map", 0), opts.get("roi_step", 0), opts.get("roi_nside", 16)
         for k, v in enumerate(opts.get("roi", [0] * 6)):
@@ -225,6 +226,21 @@ class Oracle:
                            _fp(emit), _fp(v[0]), _fp(v[1]), _fp(v[2]), C.c_float(abs_), C.c_float(sca), _fp(v[3]),
                            _fp(v[4]), _fp(opt), _fp(t), C.c_int(save_colden), C.byref(self.counters))
         return m.reshape(npy, npx), t.reshape(npy, npx)
+
+    def mapping_levels(self, map_dx, npx, npy, emit, dir_, ra, de, abs_, sca, centre, intobs=(-1e12, 0, 0), opt=None,
+                       colden=False):
+        """kernel_ASOC_map_H.c Mapping: images [LEVELS, npy, npx] (+ column density image when colden)."""
+        levels = int(self.P.levels)
+        m = np.zeros(levels * npx * npy, np.float32)
+        cd = np.zeros(npx * npy, np.float32) if colden else None
+        v = [np.ascontiguousarray(x, np.float32) for x in (dir_, ra, de, centre, intobs)]
+        emit = np.ascontiguousarray(emit, np.float32)
+        opt = None if opt is None else np.ascontiguousarray(opt, np.float32)
+        self.L.orc_mapping_levels(C.byref(self.P), C.byref(self.G), C.c_float(map_dx), C.c_int(npx), C.c_int(npy), _fp(m),
+                                  _fp(emit), _fp(v[0]), _fp(v[1]), _fp(v[2]), C.c_float(abs_), C.c_float(sca), _fp(v[3]),
+                                  _fp(v[4]), _fp(opt), _fp(cd))
+        m = m.reshape(levels, npy, npx)
+        return (m, cd.reshape(npy, npx)) if colden else m
 
     def ps_tau(self, pspos, dir_, abs_, sca, opt=None):
         pp = np.ascontiguousarray(np.asarray(pspos, np.float32).reshape(-1))

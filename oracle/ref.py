@@ -36,6 +36,7 @@ class Reference:
         self.roi_save = None
         if map_nside is not None:
             cfg["MAP_NSIDE"] = map_nside
+        self.cfg = cfg
         path = build_ref.build(cfg)
         if path is None:
             raise RuntimeError("reference library for %s not available" % build_ref.tag_of(cfg))
@@ -183,6 +184,29 @@ class Reference:
                            _fp(self.dens), C.c_float(abs_), C.c_float(sca), _fp(v[3]), _fp(v[4]), self._f(opt),
                            _fp(t), C.c_int(save_colden), _ip(self.roi))
         return m.reshape(npy, npx), t.reshape(npy, npx)
+
+    def mapping_levels(self, map_dx, npx, npy, emit, dir_, ra, de, abs_, sca, centre, intobs=(-1e12, 0, 0), opt=None,
+                       colden=False):
+        """kernel_ASOC_map_H.c Mapping through its own library (build_ref.build_levels)."""
+        cfg = dict(self.cfg)
+        cfg["USE_ABU"] = 1 if opt is not None else 0
+        cfg["WITH_COLDEN"] = 1 if colden else 0
+        path = build_ref.build_levels(cfg)
+        if path is None:
+            raise RuntimeError("reference per-level map library not available")
+        L = C.CDLL(path)
+        self._keep = []
+        levels = int(self.cloud.LEVELS)
+        m = np.zeros(levels * npx * npy, np.float32)
+        cd = np.zeros(npx * npy, np.float32)
+        v = [np.ascontiguousarray(x, np.float32) for x in (dir_, ra, de, centre, intobs)]
+        emit = np.ascontiguousarray(emit, np.float32)
+        glob = (1 + (npx * npy) // 8) * 8
+        L.ref_mapping_levels(C.c_int(glob), C.c_float(map_dx), C.c_int(npx), C.c_int(npy), _fp(m), _fp(emit),
+                             _fp(v[0]), _fp(v[1]), _fp(v[2]), _ip(self.lcells), _ip(self.off), _ip(self.par),
+                             _fp(self.dens), C.c_float(abs_), C.c_float(sca), _fp(v[3]), _fp(v[4]), self._f(opt), _fp(cd))
+        m = m.reshape(levels, npy, npx)
+        return (m, cd.reshape(npy, npx)) if colden else m
 
     def healpix_mapping(self, nside, emit, abs_, sca, intobs, opt=None, save_colden=0):
         self._keep = []

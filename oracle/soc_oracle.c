@@ -169,6 +169,9 @@ static inline void index_sim(const nav_t *N, v3 *p, int *level, int *ind) {
 static inline void index_map(const nav_t *N, v3 *p, int *level, int *ind) {
     if (N->dbl_map) index_walk_d(N, p, level, ind, 1); else index_walk_f(N, p, level, ind, 1);
 }
+static inline void index_maph(const nav_t *N, v3 *p, int *level, int *ind) {     /* kernel_ASOC_map_H.c:216-291 as shipped */
+    if (N->dbl_map) index_walk_d(N, p, level, ind, 2); else index_walk_f(N, p, level, ind, 2);
+}
 
 /* GetStep(): kernel_ASOC_aux.c:282-315 (float branch; the NX>9999 double branch is dead for int32 grids
  * we accept) and kernel_ASOC_map.c:387-429.  Only PEPS and the Index flavour differ. */
@@ -179,7 +182,7 @@ static inline float get_step_any(const nav_t *N, v3 *p, const v3 *d, int *level,
     dx = fminf_(dx, fminf_(dy, dz));
     p->x += dx * d->x; p->y += dx * d->y; p->z += dx * d->z;
     dx = ldexpf(dx, -(*level));
-    if (map) index_map(N, p, level, ind); else index_sim(N, p, level, ind);
+    if (map == 2) index_maph(N, p, level, ind); else if (map) index_map(N, p, level, ind); else index_sim(N, p, level, ind);
     return dx;
 }
 static inline float get_step(const nav_t *N, v3 *p, const v3 *d, int *level, int *ind) {
@@ -978,6 +981,83 @@ void orc_mapping(const OrcParams *P, const OrcGrid *G, float map_dx, int npx, in
         steps += s;
     }
     if (C) C->steps += steps;
+}
+
+/* Per-level Mapping: kernel_ASOC_map_H.c:380-506 (its IndexG / Index / GetStep, :179-347, are the ones of
+ * kernel_ASOC_map.c -- same EPS / PEPS, same z<=0 containment quirk, double Index for NX>100).  One image per
+ * hierarchy level: MAP[ilev*npx*npy + id] = emission of the cells of level ilev along the line of sight, attenuated
+ * by all the material in front.  The ray set-up differs from kernel_ASOC_map.c: the start point is found from behind
+ * the cloud as the LAST face crossing (largest step that still lies inside), without the 1e-5 clamp of the direction
+ * components; the perspective branch has the other sign / axis convention (:418-423).  colden may be NULL
+ * (WITH_COLDEN == 0).  P->maph_literal = 1 restates the file's own Index(), which forgets to store the root coordinates
+ * when a ray climbs out of a refined region into a root-grid leaf (:250) and then continues from the wrong place;
+ * 0 (default) is the Index() of kernel_ASOC_map.c, which has the store -- the expectation for the product. */
+static void map_levels_pixel(const OrcParams *P, const nav_t *N, int id, float map_dx, int npx, int npy, float *map,
+                             const float *emit, v3 DIR, v3 RA, v3 DE, float abs_, float sca_, v3 CENTRE, v3 INTOBS,
+                             const float *opt, float *colden_out) {
+    const int NX = P->nx, NY = P->ny, NZ = P->nz, LEVELS = P->levels;
+    float DTAU, TAU = 0.0f, colden = 0.0f, sx, sy, sz;
+    float PHOTONS[16];
+    for (int l = 0; l < LEVELS; l++) PHOTONS[l] = 0.0f;
+    v3 POS, TMP;
+    int ind, level = 0, oind, olevel;
+    int i = id % npx, j = id / npx;
+    if (INTOBS.x > -1e10f) {                                                  /* :403-430 */
+        float phi = M_TWOPI * i / (float)(npx);
+        phi += M_PI_F;
+        float pix = M_TWOPI / npx;
+        float theta = pix * (j - (npy - 1) / 2);
+        POS = INTOBS;
+        TMP.x = -cosf(theta) * sinf(phi); TMP.y = -cosf(theta) * cosf(phi); TMP.z = +sinf(theta);
+        if (fabsf(TMP.x) < 1.0e-5f) TMP.x = 1.0e-5f;
+        if (fabsf(TMP.y) < 1.0e-5f) TMP.y = 1.0e-5f;
+        if (fabsf(TMP.z) < 1.0e-5f) TMP.z = 1.0e-5f;
+        if (fmodf(POS.x, 1.0f) < 1.0e-5f) POS.x += 2.0e-5f;
+        if (fmodf(POS.y, 1.0f) < 1.0e-5f) POS.y += 2.0e-5f;
+        if (fmodf(POS.z, 1.0f) < 1.0e-5f) POS.z += 2.0e-5f;
+    } else {                                                                  /* :431-457 */
+        POS.x = CENTRE.x + (i - 0.5f * (npx - 1)) * map_dx * RA.x + (j - 0.5f * (npy - 1)) * map_dx * DE.x;
+        POS.y = CENTRE.y + (i - 0.5f * (npx - 1)) * map_dx * RA.y + (j - 0.5f * (npy - 1)) * map_dx * DE.y;
+        POS.z = CENTRE.z + (i - 0.5f * (npx - 1)) * map_dx * RA.z + (j - 0.5f * (npy - 1)) * map_dx * DE.z;
+        float far_ = (float)(NX + NY + NZ);
+        POS.x -= far_ * DIR.x; POS.y -= far_ * DIR.y; POS.z -= far_ * DIR.z;
+        if (DIR.x >= 0.0f) sx = (NX - POS.x) / (DIR.x + 1.0e-10f) - M_EPS; else sx = (0.0f - POS.x) / DIR.x - M_EPS;
+        if (DIR.y >= 0.0f) sy = (NY - POS.y) / (DIR.y + 1.0e-10f) - M_EPS; else sy = (0.0f - POS.y) / DIR.y - M_EPS;
+        if (DIR.z >= 0.0f) sz = (NZ - POS.z) / (DIR.z + 1.0e-10f) - M_EPS; else sz = (0.0f - POS.z) / DIR.z - M_EPS;
+        TMP.x = POS.x + sx * DIR.x; TMP.y = POS.y + sx * DIR.y; TMP.z = POS.z + sx * DIR.z;
+        if (TMP.x <= 0.0f || TMP.x >= NX || TMP.y <= 0.0f || TMP.y >= NY || TMP.z <= 0.0f || TMP.z >= NZ) sx = -1e10f;
+        TMP.x = POS.x + sy * DIR.x; TMP.y = POS.y + sy * DIR.y; TMP.z = POS.z + sy * DIR.z;
+        if (TMP.x <= 0.0f || TMP.x >= NX || TMP.y <= 0.0f || TMP.y >= NY || TMP.z <= 0.0f || TMP.z >= NZ) sy = -1e10f;
+        TMP.x = POS.x + sz * DIR.x; TMP.y = POS.y + sz * DIR.y; TMP.z = POS.z + sz * DIR.z;
+        if (TMP.x <= 0.0f || TMP.x >= NX || TMP.y <= 0.0f || TMP.y >= NY || TMP.z <= 0.0f || TMP.z >= NZ) sz = -1e10f;
+        sx = fmaxf(sx, fmaxf(sy, sz));
+        POS.x = POS.x + sx * DIR.x; POS.y = POS.y + sx * DIR.y; POS.z = POS.z + sx * DIR.z;
+        TMP.x = -DIR.x; TMP.y = -DIR.y; TMP.z = -DIR.z;
+    }
+    index_g_map(N, &POS, &level, &ind);
+    while (ind >= 0) {                                                        /* :468-488 */
+        oind = N->off[level] + ind; olevel = level;
+        sx = get_step_any(N, &POS, &TMP, &level, &ind, M_PEPS, P->maph_literal ? 2 : 1);
+        if (P->with_abu) DTAU = sx * N->dens[oind] * (opt[2 * (long)oind] + opt[2 * (long)oind + 1]);
+        else             DTAU = sx * N->dens[oind] * (sca_ + abs_);
+        if (DTAU < 1.0e-3f) PHOTONS[olevel] += expf(-TAU) * (1.0f - 0.5f * DTAU) * sx * emit[oind] * N->dens[oind];
+        else                PHOTONS[olevel] += expf(-TAU) * ((1.0f - expf(-DTAU)) / DTAU) * sx * emit[oind] * N->dens[oind];
+        TAU += DTAU;
+        colden += sx * N->dens[oind];
+    }
+    for (int l = 0; l < LEVELS; l++) map[(long)l * npx * npy + id] = PHOTONS[l];
+    if (colden_out) colden_out[id] = colden * P->length;
+}
+
+void orc_mapping_levels(const OrcParams *P, const OrcGrid *G, float map_dx, int npx, int npy, float *map, const float *emit,
+                        const float *dir, const float *ra, const float *de, float abs_, float sca_, const float *centre,
+                        const float *intobs, const float *opt, float *colden) {
+    v3 D = { dir[0], dir[1], dir[2] }, R = { ra[0], ra[1], ra[2] }, E = { de[0], de[1], de[2] };
+    v3 CE = { centre[0], centre[1], centre[2] }, IO = { intobs[0], intobs[1], intobs[2] };
+    nav_t N = nav_make(P, G);
+    #pragma omp parallel for schedule(runtime)
+    for (int id = 0; id < npx * npy; id++)
+        map_levels_pixel(P, &N, id, map_dx, npx, npy, map, emit, D, R, E, abs_, sca_, CE, IO, opt, colden);
 }
 
 /* PSTau: kernel_ASOC_map.c:1545-1599 -- optical depth and column density from every point source towards the observer */

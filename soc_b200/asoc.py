@@ -875,6 +875,32 @@ def main(argv=None, device_factory=None):
                     with open("%s.%d" % (USER.file_savetau, 0), "wb") as fq:
                         np.asarray([nside, USER.NPIX['y']], np.int32).tofile(fq)
                         dev.download(bk.BUF_SAVETAU, 12 * nside * nside).tofile(fq)
+    elif not USER.NOMAP and root and len(USER.OBS_THETA) > 0 and USER.FAST_MAP >= 999:
+        # one image per hierarchy level (ASOC.py:3320-3440, kernel_ASOC_map_H.c): map_dir_%02d_H.bin holds
+        # [npx, npy], [nfreq, LEVELS], then per frequency LEVELS images of npy x npx pixels
+        print('Write maps')
+        NDIR = len(USER.OBS_THETA)
+        npx, npy = USER.NPIX['x'], USER.NPIX['y']
+        freqs = [i for i in range(REMIT_I1, REMIT_I2 + 1) if USER.MAP_FREQ[0] <= FFREQ[i] <= USER.MAP_FREQ[1]]
+        fpmap = []
+        for idir in range(NDIR):
+            fpmap.append(open("map_dir_%02d_H.bin" % idir, "wb"))
+            np.asarray([npx, npy], np.int32).tofile(fpmap[idir])
+            np.asarray([len(freqs), LEVELS], np.int32).tofile(fpmap[idir])
+        for n_done, IFREQ in enumerate(freqs):
+            kabs, ksca = set_opacity(IFREQ)
+            EMIT[:] = EMITTED[:, IFREQ - REMIT_I1] * KK * FFREQ[IFREQ]
+            dev.upload(bk.BUF_EMIT, EMIT)
+            want_colden = 1 if (n_done == 0 and len(USER.file_savetau) > 0) else 0
+            for idir in range(NDIR):
+                dev.mapping_levels(USER.MAP_DX, npx, npy, ODIR[idir], RA[idir], DE[idir], kabs, ksca, centre, USER.INTOBS, want_colden)
+                dev.download(bk.BUF_MAP, LEVELS * npx * npy).tofile(fpmap[idir])
+                if want_colden:                                             # column density of the first frequency (ASOC.py:3419-3425)
+                    with open("%s.%d" % (USER.file_savetau, idir), "wb") as fq:
+                        np.asarray([npx, npy], np.int32).tofile(fq)
+                        dev.download(bk.BUF_SAVETAU, npx * npy).tofile(fq)
+        for fp in fpmap:
+            fp.close()
     elif not USER.NOMAP and root and len(USER.OBS_THETA) > 0:
         print('Write maps')
         NDIR = len(USER.OBS_THETA)

@@ -43,7 +43,7 @@ class SocCounters(C.Structure):
 
 _EXPORTS = """soc_last_error soc_version soc_create soc_destroy soc_sync soc_set_params soc_set_grid soc_set_rng_mode
 soc_set_shard soc_set_tuning soc_set_geometry soc_set_layout soc_set_roi soc_upload soc_download soc_clear soc_device_ptr soc_zero_amc soc_sim_pb soc_sim_hp
-soc_sim_cl soc_absorbed_begin soc_absorbed_add soc_absorbed_finish soc_eq_temperature soc_emission soc_emission2 soc_mapping soc_healpix_mapping soc_ps_tau soc_sca_zero_out soc_sca_ps soc_sca_pb soc_sca_hp soc_sca_cl
+soc_sim_cl soc_absorbed_begin soc_absorbed_add soc_absorbed_finish soc_eq_temperature soc_emission soc_emission2 soc_mapping soc_mapping_levels soc_healpix_mapping soc_ps_tau soc_sca_zero_out soc_sca_ps soc_sca_pb soc_sca_hp soc_sca_cl
 soc_get_counters soc_reset_counters soc_last_launch_ms soc_stream""".split()
 
 _lib = None
@@ -90,6 +90,7 @@ def load_library(path=None):
     L.soc_emission.argtypes = [vp, f, f]
     L.soc_emission2.argtypes = [vp, i, i, i, vp, vp, vp]
     L.soc_mapping.argtypes = [vp, f, i, i, fp, fp, fp, f, f, fp, fp, i]
+    L.soc_mapping_levels.argtypes = [vp, f, i, i, fp, fp, fp, f, f, fp, fp, i]
     L.soc_healpix_mapping.argtypes = [vp, i, f, f, fp, i]
     L.soc_ps_tau.argtypes = [vp, i, fp, f, f, vp, vp]
     L.soc_sca_zero_out.argtypes = [vp, i, i, i]
@@ -242,6 +243,11 @@ class Device:
         k = [_f3(v) for v in (dir_, ra, de, centre, intobs)]
         self._ck(self.L.soc_mapping(self.ctx, map_dx, npx, npy, k[0][1], k[1][1], k[2][1], abs_, sca, k[3][1], k[4][1],
                                     save_colden))
+
+    def mapping_levels(self, map_dx, npx, npy, dir_, ra, de, abs_, sca, centre, intobs, save_colden):
+        k = [_f3(v) for v in (dir_, ra, de, centre, intobs)]
+        self._ck(self.L.soc_mapping_levels(self.ctx, map_dx, npx, npy, k[0][1], k[1][1], k[2][1], abs_, sca, k[3][1], k[4][1],
+                                           save_colden))
 
     def healpix_mapping(self, nside, abs_, sca, intobs, save_colden):
         k = _f3(intobs)
@@ -421,6 +427,14 @@ class Backend:
         m = self.dev.download(BUF_MAP, npx * npy)
         t = self.dev.download(BUF_SAVETAU, npx * npy)
         return m.reshape(npy, npx), t.reshape(npy, npx)
+
+    def mapping_levels(self, map_dx, npx, npy, emit, dir_, ra, de, abs_, sca, centre, intobs=(-1e12, 0, 0), opt=None,
+                       colden=False):
+        self._put(emit=emit, opt=opt)
+        self.dev.mapping_levels(map_dx, npx, npy, dir_, ra, de, abs_, sca, centre, intobs, 1 if colden else 0)
+        levels = int(self.cloud.LEVELS)
+        m = self.dev.download(BUF_MAP, levels * npx * npy).reshape(levels, npy, npx)
+        return (m, self.dev.download(BUF_SAVETAU, npx * npy).reshape(npy, npx)) if colden else m
 
     def healpix_mapping(self, nside, emit, abs_, sca, intobs, opt=None, save_colden=0):
         self._put(emit=emit, opt=opt)

@@ -700,6 +700,26 @@ int soc_mapping(soc_context *c, float map_dx, int npix_x, int npix_y, const floa
     return SOC_OK;
 }
 
+int soc_mapping_levels(soc_context *c, float map_dx, int npix_x, int npix_y, const float dir[3], const float ra[3],
+                       const float de[3], float abs, float sca, const float centre[3], const float intobs[3], int save_colden) {
+    NEED_CTX(c);
+    if (npix_x < 1 || npix_y < 1 || !dir || !ra || !de || !centre || !intobs) return fail(SOC_ERR_ARG, "soc_mapping_levels: bad arguments");
+    if (c->have_grid && c->G.levels > 12) return fail(SOC_ERR_UNSUPPORTED, "soc_mapping_levels: at most 12 hierarchy levels (%d)", c->G.levels);
+    MapArgs M;
+    int r = map_common(c, M, (size_t)npix_x * npix_y * (size_t)(c->have_grid ? c->G.levels : 1), abs, sca, save_colden, "soc_mapping_levels");
+    if (r != SOC_OK) return r;
+    if (!save_colden) M.savetau = nullptr;
+    M.dir = { dir[0], dir[1], dir[2] }; M.ra = { ra[0], ra[1], ra[2] }; M.de = { de[0], de[1], de[2] };
+    M.centre = { centre[0], centre[1], centre[2] }; M.intobs = { intobs[0], intobs[1], intobs[2] };
+    M.map_dx = map_dx; M.npx = npix_x; M.npy = npix_y;
+    CU(cudaEventRecord(c->ev0, c->stream));
+    launch_mapping_levels(M, c->stream);
+    CU(cudaEventRecord(c->ev1, c->stream));
+    c->timed = true; c->launches++;
+    CU(cudaGetLastError());
+    return SOC_OK;
+}
+
 int soc_healpix_mapping(soc_context *c, int nside, float abs, float sca, const float intobs[3], int save_colden) {
     NEED_CTX(c);
     if (nside < 1 || nside > 8192 || !intobs) return fail(SOC_ERR_ARG, "soc_healpix_mapping: bad arguments");

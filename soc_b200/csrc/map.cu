@@ -209,6 +209,85 @@ __global__ void __launch_bounds__(128) healpix_mapping_kernel(const __grid_const
     warp_add_counter(M.counters + 1, steps);
 }
 
+// Per-level Mapping (kernel_ASOC_map_H.c:380-506; ASOC.py:3320-3440, `mapping nx ny dx 999`): MAP[l*npix + id] =
+// emission of the level-l cells along the line of sight behind all the material in front of them.  The ray set-up is
+// that file's own (start point = last face crossing found from behind the cloud, no clamp of the direction components,
+// its own perspective convention); stepping is the map kernel's Index -- the copy in kernel_ASOC_map_H.c:250 forgets to
+// store the root coordinates when a ray climbs into a root-grid leaf and loses ~15 % of the flux of a refined cloud
+// (DESIGN.md section 7), which is not reproduced.  Level sums stay in registers: the adds are predicated, not indexed.
+#define SOC_MAP_MAXLEV 12
+template <bool OCT, bool DBL>
+__global__ void __launch_bounds__(128) mapping_levels_kernel(const __grid_constant__ MapArgs M) {
+    const GridDesc &G = M.G;
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long steps = 0;
+    if (id < M.npx * M.npy) {
+        const float NX = (float)G.nx, NY = (float)G.ny, NZ = (float)G.nz;
+        const int i = id % M.npx, j = id / M.npx;
+        vec3 POS, TMP;
+        const vec3 DIR = M.dir;
+        if (M.intobs.x > -1e10f) {                                              // :403-430
+            float phi = xdiv(xmul(SOC_MAP_TWOPI, (float)i), (float)M.npx);
+            phi = xadd(phi, SOC_MAP_PI);
+            float pix = xdiv(SOC_MAP_TWOPI, (float)M.npx);
+            float theta = xmul(pix, (float)(j - (M.npy - 1) / 2));
+            POS = M.intobs;
+            float st, ct, sp, cp;
+            sincosf(theta, &st, &ct); sincosf(phi, &sp, &cp);
+            TMP.x = -xmul(ct, sp); TMP.y = -xmul(ct, cp); TMP.z = st;
+            clamp_dir(TMP);
+            if (fmod1(POS.x) < 1.0e-5f) POS.x = xadd(POS.x, 2.0e-5f);
+            if (fmod1(POS.y) < 1.0e-5f) POS.y = xadd(POS.y, 2.0e-5f);
+            if (fmod1(POS.z) < 1.0e-5f) POS.z = xadd(POS.z, 2.0e-5f);
+        } else {                                                                // :431-457
+            float fi = xmul(xsub((float)i, xmul(0.5f, (float)(M.npx - 1))), M.map_dx);
+            float fj = xmul(xsub((float)j, xmul(0.5f, (float)(M.npy - 1))), M.map_dx);
+            POS.x = xadd(xadd(M.centre.x, xmul(fi, M.ra.x)), xmul(fj, M.de.x));
+            POS.y = xadd(xadd(M.centre.y, xmul(fi, M.ra.y)), xmul(fj, M.de.y));
+            POS.z = xadd(xadd(M.centre.z, xmul(fi, M.ra.z)), xmul(fj, M.de.z));
+            float far_ = (float)(G.nx + G.ny + G.nz);
+            POS.x = xsub(POS.x, xmul(far_, DIR.x)); POS.y = xsub(POS.y, xmul(far_, DIR.y)); POS.z = xsub(POS.z, xmul(far_, DIR.z));
+            float sx = (DIR.x >= 0.0f) ? xsub(xdiv(xsub(NX, POS.x), xadd(DIR.x, 1.0e-10f)), SOC_MAP_EPS) : xsub(xdiv(xsub(0.0f, POS.x), DIR.x), SOC_MAP_EPS);
+            float sy = (DIR.y >= 0.0f) ? xsub(xdiv(xsub(NY, POS.y), xadd(DIR.y, 1.0e-10f)), SOC_MAP_EPS) : xsub(xdiv(xsub(0.0f, POS.y), DIR.y), SOC_MAP_EPS);
+            float sz = (DIR.z >= 0.0f) ? xsub(xdiv(xsub(NZ, POS.z), xadd(DIR.z, 1.0e-10f)), SOC_MAP_EPS) : xsub(xdiv(xsub(0.0f, POS.z), DIR.z), SOC_MAP_EPS);
+            vec3 t;
+            t = back(POS, -sx, DIR); if (t.x <= 0.0f || t.x >= NX || t.y <= 0.0f || t.y >= NY || t.z <= 0.0f || t.z >= NZ) sx = -1e10f;
+            t = back(POS, -sy, DIR); if (t.x <= 0.0f || t.x >= NX || t.y <= 0.0f || t.y >= NY || t.z <= 0.0f || t.z >= NZ) sy = -1e10f;
+            t = back(POS, -sz, DIR); if (t.x <= 0.0f || t.x >= NX || t.y <= 0.0f || t.y >= NY || t.z <= 0.0f || t.z >= NZ) sz = -1e10f;
+            sx = fmaxf(sx, fmaxf(sy, sz));
+            POS = back(POS, -sx, DIR);
+            TMP.x = -DIR.x; TMP.y = -DIR.y; TMP.z = -DIR.z;
+        }
+        int level = 0, ind;
+        float rho = 0.0f, TAU = 0.0f, colden = 0.0f;
+        float PH[SOC_MAP_MAXLEV];
+        #pragma unroll
+        for (int l = 0; l < SOC_MAP_MAXLEV; l++) PH[l] = 0.0f;
+        index_global<OCT, true>(G, POS, level, ind, rho);
+        while (ind >= 0) {                                                      // :468-488
+            const int oind = OCT ? G.off[level] + ind : ind, olevel = level;
+            const float dens = rho, em = M.emit[oind];
+            float kext;
+            if (M.with_abu) { float2 o = reinterpret_cast<const float2 *>(M.opt)[oind]; kext = xadd(o.x, o.y); }
+            else            kext = xadd(M.ksca, M.kabs);
+            const float sx = get_step<OCT, DBL, true>(G, POS, TMP, level, ind, rho);
+            const float DTAU = xmul(xmul(sx, dens), kext);
+            const float w = (DTAU < 1.0e-3f) ? xsub(1.0f, xmul(0.5f, DTAU)) : xdiv(xsub(1.0f, exp_cr(-DTAU)), DTAU);
+            const float term = xmul(xmul(xmul(xmul(exp_cr(-TAU), w), sx), em), dens);
+            #pragma unroll
+            for (int l = 0; l < SOC_MAP_MAXLEV; l++) if (l == olevel) PH[l] = xadd(PH[l], term);
+            TAU = xadd(TAU, DTAU);
+            colden = xadd(colden, xmul(sx, dens));
+            steps++;
+        }
+        const long long npix = (long long)M.npx * M.npy;
+        #pragma unroll
+        for (int l = 0; l < SOC_MAP_MAXLEV; l++) if (l < G.levels) M.map[l * npix + id] = PH[l];
+        if (M.savetau != nullptr) M.savetau[id] = xmul(colden, M.length);
+    }
+    warp_add_counter(M.counters + 1, steps);
+}
+
 // PSTau (kernel_ASOC_map.c:1545-1599): tau and column density from each point source towards the observer
 template <bool OCT, bool DBL>
 __global__ void pstau_kernel(const __grid_constant__ MapArgs M, int no, const float *__restrict__ pspos, float *__restrict__ colden_out,
@@ -242,6 +321,14 @@ void launch_pstau(const MapArgs &M, int no, const float *pspos, float *colden, f
     if (!oct)      pstau_kernel<false, false><<<blocks, threads, 0, stream>>>(M, no, pspos, colden, tau);
     else if (!dbl) pstau_kernel<true, false><<<blocks, threads, 0, stream>>>(M, no, pspos, colden, tau);
     else           pstau_kernel<true, true><<<blocks, threads, 0, stream>>>(M, no, pspos, colden, tau);
+}
+
+void launch_mapping_levels(const MapArgs &M, cudaStream_t stream) {
+    const bool oct = M.G.levels > 1, dbl = M.G.dbl_map != 0;
+    const int n = M.npx * M.npy, threads = 128, blocks = (n + threads - 1) / threads;
+    if (!oct)      mapping_levels_kernel<false, false><<<blocks, threads, 0, stream>>>(M);
+    else if (!dbl) mapping_levels_kernel<true, false><<<blocks, threads, 0, stream>>>(M);
+    else           mapping_levels_kernel<true, true><<<blocks, threads, 0, stream>>>(M);
 }
 
 void launch_mapping(const MapArgs &M, bool healpix, cudaStream_t stream) {

@@ -15,4 +15,5 @@ struct MapArgs {
 };
 
 void launch_mapping(const MapArgs &M, bool healpix, cudaStream_t stream);
+void launch_mapping_levels(const MapArgs &M, cudaStream_t stream);    // map = [levels*npy*npx], savetau = column density or nullptr
 void launch_pstau(const MapArgs &M, int no, const float *pspos, float *colden, float *tau, cudaStream_t stream);

@@ -393,8 +393,10 @@ class User:
             bad.append("dirweight: does not compile in the reference either (undeclared pweight)")
         if self.PS_METHOD == 3:
             bad.append("psmethod 3: not implemented in the reference either")
-        if self.FAST_MAP > 1:
-            bad.append("mapping ... fast: fast / per-level maps are not implemented")
+        if 1 < self.FAST_MAP < 999:
+            bad.append("mapping ... fast: kernel_ASOC_map_X.c does not exist in the reference either (ASOC.py:3442)")
+        if self.FAST_MAP >= 999 and self.NPIX['y'] <= 0:
+            bad.append("mapping ... 999 with a Healpix map: per-level Healpix maps are not implemented")
         if self.USE_EMWEIGHT > 1:
             bad.append("emweight 2 is not implemented")
         if self.LIB_ABS or self.LIB_MAPS:

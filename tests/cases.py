@@ -141,6 +141,34 @@ def run_map(npix, dirs, map_dx=1.0, intobs=None, colden=0, abu=False, centre_off
     return run
 
 
+def run_maplev(npix, dirs, map_dx=1.0, intobs=None, colden=False, abu=False, centre_off=0.0):
+    """Per-level images (kernel_ASOC_map_H.c Mapping)."""
+    def run(X):
+        c = X.cloud
+        k = _tau_scale(c, 1.0)
+        rng = np.random.default_rng(9)
+        emit = np.where(c.DENS > 0, 1.0 + rng.random(c.CELLS), 0.0).astype(np.float32)
+        opt = None
+        if abu:
+            opt = np.empty((c.CELLS, 2), np.float32)
+            opt[:, 0] = k * (0.5 + rng.random(c.CELLS))
+            opt[:, 1] = k * (0.5 + rng.random(c.CELLS))
+            opt = opt.reshape(-1)
+        out = {}
+        _, od, ra, de = observer_directions([d[0] for d in dirs], [d[1] for d in dirs])
+        centre = np.array([0.5 * c.NX + centre_off, 0.5 * c.NY, 0.5 * c.NZ - centre_off], np.float32)
+        for i in range(len(dirs)):
+            io = (-1e12, 0.0, 0.0) if intobs is None else intobs
+            r = X.mapping_levels(map_dx, npix[0], npix[1], emit, od[i], ra[i], de[i], 1.2 * k, 0.8 * k, centre,
+                                 intobs=io, opt=opt, colden=colden)
+            if colden:
+                out["map%d" % i], out["colden%d" % i] = r[0].copy(), r[1].copy()
+            else:
+                out["map%d" % i] = r.copy()
+        return out
+    return run
+
+
 def run_hpmap(nside, intobs):
     def run(X):
         c = X.cloud
@@ -314,6 +342,9 @@ CASES = {
     "map_oct6_4_thr":  (_oct(6, 4, 0.25, 8), dict(level_threshold=1), run_map((20, 20), [(120.0, 200.0)], map_dx=0.35)),
     "map_reg16_persp": (_reg(16), {}, run_map((32, 16), [(0.0, 0.0)], intobs=(7.3, 8.4, 9.1))),
     "hpmap_oct8_3":    (_oct(8, 3), {}, run_hpmap(8, (4.2, 3.3, 5.1))),
+    "map_lev_oct8_3":  (_oct(8, 3), {}, run_maplev((24, 20), [(0.0, 0.0), (60.0, 30.0)], map_dx=0.4)),
+    "map_lev_oct6_4_abu": (_oct(6, 4, 0.25, 8), dict(with_abu=1), run_maplev((20, 20), [(120.0, 200.0)], map_dx=0.35, abu=True, colden=True, centre_off=0.3)),
+    "map_lev_reg16_persp": (_reg(16), {}, run_maplev((32, 16), [(0.0, 0.0)], intobs=(7.3, 8.4, 9.1))),
     "map_reg16_int1":  (_reg(16), dict(map_interpolation=1), run_map((20, 16), [(0.0, 0.0), (60.0, 30.0)])),
     "map_oct8_3_int1": (_oct(8, 3), dict(map_interpolation=1), run_map((24, 24), [(35.0, 110.0)], map_dx=0.4)),
     "map_reg16_int2":  (_reg(16), dict(map_interpolation=2), run_map((20, 16), [(90.0, 0.0), (60.0, 30.0)])),

@@ -4,6 +4,7 @@
 The vectors let machines without /root/reference (the GPU box) check the oracle against the reference.
 
     python tests/golden/make_golden.py          # rewrites every fixture
+    python tests/golden/make_golden.py NAME...  # only the named cases
 """
 import os
 import sys
@@ -18,7 +19,7 @@ from tests.cases import CASES, MAP_NSIDE    # noqa: E402
 
 
 def main():
-    for name in sorted(CASES):
+    for name in (sys.argv[1:] or sorted(CASES)):
         make, opts, run = CASES[name]
         cloud = make()
         R = ref.Reference(cloud, map_nside=MAP_NSIDE.get(name), **opts)

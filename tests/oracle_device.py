@@ -197,6 +197,14 @@ class OracleDevice:
                               opt=self._g(bk.BUF_OPT), save_colden=save_colden)
         self.buf[bk.BUF_MAP], self.buf[bk.BUF_SAVETAU] = m.reshape(-1), t.reshape(-1)
 
+    def mapping_levels(self, map_dx, npx, npy, dir_, ra, de, abs_, sca, centre, intobs, save_colden):
+        r = self.O.mapping_levels(map_dx, npx, npy, self.buf[bk.BUF_EMIT], dir_, ra, de, abs_, sca, centre, intobs=intobs,
+                                  opt=self._g(bk.BUF_OPT), colden=bool(save_colden))
+        if save_colden:
+            self.buf[bk.BUF_MAP], self.buf[bk.BUF_SAVETAU] = r[0].reshape(-1), r[1].reshape(-1)
+        else:
+            self.buf[bk.BUF_MAP] = r.reshape(-1)
+
     def healpix_mapping(self, nside, abs_, sca, intobs, save_colden):
         m, t = self.O.healpix_mapping(nside, self.buf[bk.BUF_EMIT], abs_, sca, intobs, opt=self._g(bk.BUF_OPT),
                                       save_colden=save_colden)

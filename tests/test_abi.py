@@ -24,7 +24,7 @@ def _declared():
 def test_header_declares_the_documented_surface():
     names = _declared()
     for must in ("soc_create", "soc_set_grid", "soc_set_params", "soc_upload", "soc_download", "soc_zero_amc",
-                 "soc_sim_pb", "soc_sim_hp", "soc_sim_cl", "soc_mapping", "soc_healpix_mapping", "soc_sca_ps",
+                 "soc_sim_pb", "soc_sim_hp", "soc_sim_cl", "soc_mapping", "soc_mapping_levels", "soc_healpix_mapping", "soc_sca_ps",
                  "soc_sca_pb", "soc_eq_temperature", "soc_emission", "soc_get_counters"):
         assert must in names
 

@@ -62,6 +62,22 @@ def test_pssavetau_writes_source_optical_depths(tmp_path):
     assert os.path.exists(str(tmp_path / "pstau_1.dat"))
 
 
+def test_per_level_maps(tmp_path):
+    """`mapping nx ny dx 999` (ASOC.py:3320-3440): map_dir_%02d_H.bin = [npx, npy], [nfreq, LEVELS], then LEVELS images per
+    frequency; their sum over the levels is the ordinary map of the same run."""
+    cloud = _run(tmp_path / "lev", n=6, octree=True, bgpac=20000, extra="mapping 6 6 1.0 999\nsavetau colden -1\n")
+    _run(tmp_path / "all", n=6, octree=True, bgpac=20000, extra="mapping 6 6 1.0\n")
+    raw = np.fromfile(str(tmp_path / "lev" / "map_dir_01_H.bin"), np.int32, 4)
+    assert list(raw[:2]) == [6, 6] and raw[3] == cloud.LEVELS
+    nfreq = int(raw[2])
+    lev = np.fromfile(str(tmp_path / "lev" / "map_dir_01_H.bin"), np.float32, offset=16).reshape(nfreq, cloud.LEVELS, 6, 6)
+    full = read_map_file(str(tmp_path / "all" / "map_dir_01.bin"))
+    assert full.shape == (nfreq, 6, 6)
+    assert (lev[:, 1:] > 0).any() and np.allclose(lev.sum(axis=1), full, rtol=2e-5, atol=0)
+    col = np.fromfile(str(tmp_path / "lev" / "colden.1"), np.float32, offset=8)
+    assert col.shape == (36,) and (col > 0).all()
+
+
 def test_absorbed_file_and_octree(tmp_path):
     cloud = _run(tmp_path, n=6, octree=True, bgpac=20000, pspac=33000, noabsorbed=False, absorbed=True, maps=False)
     a = read_cells_freq_file(str(tmp_path / "abs.data"))

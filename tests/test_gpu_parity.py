@@ -92,7 +92,12 @@ def test_maps_match_oracle_and_golden(name):
     B = _backend(cloud, backend.RNG_REFERENCE, **opts)
     out_g = run(B)
     gold = np.load(os.path.join(GOLD, name + ".npz"))
-    for ref in (out_o, {k: gold[k] for k in gold.files}):
+    refs = [out_o, {k: gold[k] for k in gold.files}]
+    if name.startswith("map_lev") and cloud.LEVELS > 1:
+        # the goldens hold kernel_ASOC_map_H.c as shipped, whose Index() loses rays that climb into root-grid leaves
+        # (pinned by the oracle's maph_literal variant on the CPU); the library steps like kernel_ASOC_map.c
+        refs = refs[:1]
+    for ref in refs:
         for key in ref:
             a, b = out_g[key].astype(np.float64), ref[key].astype(np.float64)
             nz = b != 0.0

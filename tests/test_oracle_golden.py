@@ -21,7 +21,7 @@ def test_every_case_has_a_fixture():
 def test_oracle_reproduces_golden(name):
     make, opts, run = CASES[name]
     gold = np.load(os.path.join(GOLD, name + ".npz"))
-    O = orc.Oracle(make(), hg_test=1, **opts)      # scattered-light HP / CL kernels as shipped (see soc_oracle.h)
+    O = orc.Oracle(make(), hg_test=1, maph_literal=1, **opts)      # scattered-light HP / CL kernels as shipped (see soc_oracle.h)
     orc.set_threads(1)
     out = run(O)
     for key in gold.files:

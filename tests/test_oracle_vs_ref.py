@@ -18,7 +18,7 @@ pytestmark = pytest.mark.skipif(not build_ref.reference_available(), reason="/ro
 def _run(name):
     make, opts, run = CASES[name]
     cloud = make()
-    O = orc.Oracle(cloud, hg_test=1, **opts)      # the scattered-light HP / CL kernels exactly as shipped (soc_oracle.h)
+    O = orc.Oracle(cloud, hg_test=1, maph_literal=1, **opts)      # the scattered-light HP / CL kernels exactly as shipped (soc_oracle.h)
     R = ref.Reference(cloud, map_nside=MAP_NSIDE.get(name), **opts)
     orc.set_threads(1)          # one thread: work items run in id order, float sums in the same order
     R.set_threads(1)
