@@ -47,6 +47,7 @@ struct soc_context {
     float *dens_brick;                 // regular grids with even dimensions: DENS in 2x2x2-brick order (lean kernel)
     int layout;                        // 1 = use the bricked copy where the kernel supports it
     int pend;                          // 1 = merged deposits (vector reds) in the lean kernel
+    float2 *kappa; size_t kappa_cells; // WITH_ABU on regular grids: (kabs*n, ksca*n) per cell, rebuilt before every launch
     int ahead;                         // 1 = look-ahead variant of the lean kernel (geometry one cell ahead, cp.async density ring)
     unsigned long long launches;
     soc_params P;
@@ -141,6 +142,7 @@ int soc_destroy(soc_context *c) {
     if (c->dens_brick) cudaFree(c->dens_brick);
     if (c->nbr) cudaFree(c->nbr);
     if (c->scratch) cudaFree(c->scratch);
+    if (c->kappa) cudaFree(c->kappa);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -466,12 +468,22 @@ static int sim_launch(soc_context *c, SimArgs &A, const char *who) {
         }
         A.acc = c->acc; A.use_acc = 1;
         A.dens_brick = c->layout ? c->dens_brick : nullptr;
+        A.kappa = nullptr;
+        if (sim_kappa_eligible(A, c->rng_mode) && !getenv("SOC_NO_KAPPA")) {
+            if (c->kappa == nullptr || c->kappa_cells != (size_t)A.G.cells) {
+                if (c->kappa) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->kappa)); c->kappa = nullptr; }
+                CU(cudaMalloc(&c->kappa, (size_t)A.G.cells * sizeof(float2)));
+                c->kappa_cells = (size_t)A.G.cells;
+            }
+            A.kappa = c->kappa;
+        }
         A.brick = sim_uses_bricks(A, c->rng_mode) ? 1 : 0;
         A.nbr = c->nbr;
         A.pend = c->pend; A.ahead = c->ahead;
         A.slab_xy = A.G.nx * A.G.ny; A.brick_by = 4 * A.G.nx - 2; A.brick_bz = 2 * A.G.nx * A.G.ny - 4;
     }
     CU(cudaEventRecord(c->ev0, c->stream));
+    if (A.kappa != nullptr) { launch_kappa(A, c->stream); c->launches++; }     // OPT may have changed since the last launch
     launch_sim(A, c->rng_mode, blocks, threads, c->stream);
     if (A.use_acc) { launch_fold_acc(A, c->stream); c->launches++; }
     CU(cudaEventRecord(c->ev1, c->stream));

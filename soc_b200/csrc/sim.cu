@@ -905,6 +905,12 @@ __device__ __forceinline__ void cp_async_f32(unsigned saddr, const float *g) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ float lds_f32(unsigned saddr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory"); return v; }
+__device__ __forceinline__ void cp_async_f32x2(unsigned saddr, const float2 *g) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ float2 lds_f32x2(unsigned saddr) {
+    float2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr) : "memory"); return v;
+}
 
 // per-lane state word of the look-ahead kernel
 #define AH_UPM     0x7u        // bit a: the packet moves towards +axis a
@@ -915,19 +921,25 @@ __device__ __forceinline__ float lds_f32(unsigned saddr) { float v; asm volatile
 #define AH_PRIMED  0x800u      // (rho, seg, ind) of the physics cell are valid
 #define AH_AIN     0x1000u     // A lies inside the grid
 
-template <int DEP, bool BRICK, int CTAS>
+// KAPPA: per-cell opacities (WITH_ABU).  The kernel then reads ONE float2 per cell, (kabs*n, ksca*n) in the layout of the
+// density array (kappa_kernel builds it from DENS and OPT before the launch), instead of the density and the two
+// opacities: 8 B gathered per step instead of 12, and the ring slots are 8 bytes wide.
+#define AH_SLOT_SHIFT(KAPPA) ((KAPPA) ? 1 : 0)
+template <int DEP, bool BRICK, int CTAS, bool KAPPA>
 __global__ void __launch_bounds__(256, CTAS) sim_ahead_kernel(const __grid_constant__ SimArgs A) {
     __shared__ float smem[DEP == DEP_TILE ? SOC_TILE_CELLS : 1];
-    __shared__ float s_ring[2 * 256];                        // slot s of lane t: s_ring[s * 256 + t]
+    __shared__ __align__(8) float s_ring[(KAPPA ? 4 : 2) * 256];   // slot s of lane t: s_ring[s * 256 + t] (float or float2 units)
     __shared__ unsigned s_cnt[4];
     if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
     float *tile = nullptr;
     if (DEP == DEP_TILE) tile = tile_begin(A, smem); else __syncthreads();
     const GridDesc &G = A.G;
     const float *__restrict__ dens = BRICK ? A.dens_brick : G.dens;
+    const float2 *__restrict__ kappa = A.kappa;
     const int lane = threadIdx.x & 31;
     const float kabs = A.kabs, ksca = A.ksca;
-    const unsigned ring = (unsigned)__cvta_generic_to_shared(&s_ring[threadIdx.x]);
+    const unsigned ring = (unsigned)__cvta_generic_to_shared(&s_ring[KAPPA ? 2 * threadIdx.x : threadIdx.x]);
+    float ka = 0.0f;                 // KAPPA: kabs*n of the physics cell (f.rho holds ksca*n)
     LeanPk<BRICK> f; f.ind = 0; f.u = 0; f.rho = 0.0f; f.sn = 0; f.upm = 0;        // f.ind = index of cell A
     int ind = 0;                     // cell the physics works on
     float seg = 0.0f;                // path length through it (at a scattering: the part not used)
@@ -963,6 +975,7 @@ __global__ void __launch_bounds__(256, CTAS) sim_ahead_kernel(const __grid_const
                         f.ind = BRICK ? brick_index(ix, iy, iz, G.nx >> 1, G.ny >> 1) : (iz * G.ny + iy) * G.nx + ix;
                         ind = f.ind;
                         f.rho = pk.rho; f.photons = pk.photons; f.free_path = pk.free_path; f.tau = 0.0f;
+                        if (KAPPA) { const float2 k2 = __ldg(kappa + f.ind); ka = k2.x; f.rho = k2.y; }
                         f.sn = 0; f.u = (unsigned)u;
                     }
                 }
@@ -1009,12 +1022,12 @@ __global__ void __launch_bounds__(256, CTAS) sim_ahead_kernel(const __grid_const
         float delta = 0.0f, len = seg;
         bool sc = false;
         if (phys) {
-            const float krho = ksca * f.rho;
+            const float krho = KAPPA ? f.rho : ksca * f.rho;
             const float tend = fmaf(seg, krho, f.tau);
             sc = f.free_path < tend;
             const float tsc = (f.free_path - f.tau) * rcp_approx(krho);
             if (sc) { len = fminf(seg, tsc); f.sn += 1u << 24; } else f.tau = tend;
-            const float x = len * f.rho * kabs;
+            const float x = KAPPA ? len * ka : len * f.rho * kabs;
             const float e = exp2f_approx(-1.4426950408889634f * x);
             const float ser = x * fmaf(x, fmaf(x, 0.16666667f, -0.5f), 1.0f);
             const float dfrac = (x < 0.01f) ? ser : (1.0f - e);
@@ -1072,14 +1085,16 @@ __global__ void __launch_bounds__(256, CTAS) sim_ahead_kernel(const __grid_const
                 const int nind = f.ind + ((st & abit) ? mag : -mag);
                 const int crem = px ? f.cx : (py ? f.cy : f.cz);
                 const bool inb = crem > 0;
-                const unsigned wslot = ring + (st & AH_SLOT);
-                if (inb) cp_async_f32(wslot, dens + nind);
+                const unsigned wslot = ring + ((st & AH_SLOT) << AH_SLOT_SHIFT(KAPPA));
+                if (inb) { if (KAPPA) cp_async_f32x2(wslot, kappa + nind); else cp_async_f32(wslot, dens + nind); }
                 cp_async_commit();
                 f.tx = px ? f.rdx : f.tx - tmin; f.ty = py ? f.rdy : f.ty - tmin; f.tz = pz ? f.rdz : f.tz - tmin;
                 f.cx -= px; f.cy -= py; f.cz -= pz;
                 if (st & AH_PRIMED) {                            // density of A, requested one iteration ago
                     cp_async_wait1();
-                    f.rho = lds_f32(ring + ((st & AH_SLOT) ^ AH_SLOT));
+                    const unsigned rslot = ring + (((st & AH_SLOT) ^ AH_SLOT) << AH_SLOT_SHIFT(KAPPA));
+                    if (KAPPA) { const float2 k2 = lds_f32x2(rslot); ka = k2.x; f.rho = k2.y; }
+                    else f.rho = lds_f32(rslot);
                 }
                 ind = f.ind; f.ind = nind; seg = tmin;
                 st = ((st & ~(AH_AXA | AH_AIN)) ^ AH_SLOT) | AH_PRIMED | (abit << 4) | (inb ? AH_AIN : 0u);
@@ -1459,7 +1474,11 @@ __global__ void __launch_bounds__(256, 4) sim_link_kernel(const __grid_constant_
     flush_counters(A, cnt);
 }
 
-static bool sim_is_general(const SimArgs &A) { return (A.roi.flags & 2) || A.kind == SIM_ROI || A.with_msf || A.with_abu || A.save_int2 || A.with_ali || A.kind == SIM_CL; }
+// with_abu alone stays on the lean path (look-ahead kernel with the per-cell opacity array) unless a border reflects
+static bool sim_is_general(const SimArgs &A) {
+    return (A.roi.flags & 2) || A.kind == SIM_ROI || A.with_msf || (A.with_abu && (A.mirror != 0 || A.kappa == nullptr)) || A.save_int2 ||
+           A.with_ali || A.kind == SIM_CL;
+}
 
 static void launch_walk(const SimArgs &A, int blocks, int threads, cudaStream_t stream) {
     const bool general = sim_is_general(A);
@@ -1514,25 +1533,25 @@ struct RngMwcItem : RngMwc {
 
 }  // namespace
 
-template <int DEP, bool BRICK, int CTAS>
+template <int DEP, bool BRICK, int CTAS, bool KAPPA>
 static void launch_ahead_dep(const SimArgs &A, int blocks, int threads, cudaStream_t stream) {
     static int per_sm = 0, sms = 0;                   // resident CTAs of this instantiation: the persistent grid is sms x per_sm
     if (per_sm == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sim_ahead_kernel<DEP, BRICK, CTAS>, threads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sim_ahead_kernel<DEP, BRICK, CTAS, KAPPA>, threads, 0);
         if (per_sm < 1) per_sm = 1;
     }
     if (blocks > sms * per_sm) blocks = sms * per_sm;
-    sim_ahead_kernel<DEP, BRICK, CTAS><<<blocks, threads, 0, stream>>>(A);
+    sim_ahead_kernel<DEP, BRICK, CTAS, KAPPA><<<blocks, threads, 0, stream>>>(A);
 }
 
-template <bool BRICK, int CTAS>
+template <bool BRICK, int CTAS, bool KAPPA>
 static void launch_ahead(const SimArgs &A, int dep, int blocks, int threads, cudaStream_t stream) {
-    if (dep == DEP_RED)       launch_ahead_dep<DEP_RED, BRICK, CTAS>(A, blocks, threads, stream);
-    else if (dep == DEP_WARP) launch_ahead_dep<DEP_WARP, BRICK, CTAS>(A, blocks, threads, stream);
-    else                      launch_ahead_dep<DEP_TILE, BRICK, CTAS>(A, blocks, threads, stream);
+    if (dep == DEP_RED)       launch_ahead_dep<DEP_RED, BRICK, CTAS, KAPPA>(A, blocks, threads, stream);
+    else if (dep == DEP_WARP) launch_ahead_dep<DEP_WARP, BRICK, CTAS, KAPPA>(A, blocks, threads, stream);
+    else                      launch_ahead_dep<DEP_TILE, BRICK, CTAS, KAPPA>(A, blocks, threads, stream);
 }
 
 template <bool BRICK, bool PEND>
@@ -1542,12 +1561,17 @@ static void launch_lean(SimArgs A, int dep, int blocks, int threads, cudaStream_
         A.tile_lo = (z0 >> 1) * slab;
         A.tile_span = (((z0 + SOC_TILE_N - 1) >> 1) - (z0 >> 1) + 1) * slab;
     }
+    // per-cell opacities: only the look-ahead kernel has the variant (one float2 per cell, see sim_ahead_kernel)
+    if (A.with_abu) {
+        launch_ahead<BRICK, 3, true>(A, dep, blocks, threads, stream);
+        return;
+    }
     // geometry one cell ahead of the physics (cp.async density ring).  Measured on the bench step: background launch
-    // (plain adds) 60.4 -> 57.9 ms; the point-source launch with the shared-memory tile runs 66.6 ms on the lean kernel,
-    // 77 ms (3 CTAs / SM) or 72 ms (4 CTAs / SM) here, so ahead = 1 takes the plain-add launches only
+    // (plain adds) 60.4 -> 57.9 ms; the point-source launch with the shared-memory tile runs 63.9 ms on the lean kernel,
+    // 73.6 ms (3 CTAs / SM) or 71.8 ms (4 CTAs / SM) here, so ahead = 1 takes the plain-add launches only
     if (A.ahead && !PEND && A.mirror == 0 && (dep == DEP_RED || A.ahead > 1)) {
-        if (A.ahead == 2) launch_ahead<BRICK, 4>(A, dep, blocks, threads, stream);
-        else              launch_ahead<BRICK, 3>(A, dep, blocks, threads, stream);
+        if (A.ahead == 2) launch_ahead<BRICK, 4, false>(A, dep, blocks, threads, stream);
+        else              launch_ahead<BRICK, 3, false>(A, dep, blocks, threads, stream);
         return;
     }
     if (dep == DEP_RED)       sim_lean_kernel<DEP_RED, BRICK, PEND><<<blocks, threads, 0, stream>>>(A);
@@ -1571,6 +1595,31 @@ static void launch_fast(const SimArgs &A, int blocks, int threads, cudaStream_t 
     } else {
         if (A.pend) launch_lean<false, true>(A, dep, blocks, threads, stream);
         else        launch_lean<false, false>(A, dep, blocks, threads, stream);
+    }
+}
+
+bool sim_kappa_eligible(const SimArgs &A, int rng_mode) {
+    return rng_mode != SOC_RNG_REFERENCE && A.G.levels == 1 && !A.ref_geometry && A.with_abu && !A.with_msf && A.mirror == 0 &&
+           !(A.roi.flags & 2) && (A.kind == SIM_PS || A.kind == SIM_BG || A.kind == SIM_HP) && !A.save_int2 && !A.with_ali &&
+           A.nlocal < (1LL << 32) && A.max_steps < (1 << 24) - 2;
+}
+
+// (kabs*n, ksca*n) per cell, in 2x2x2-brick order when the launch uses bricks: one thread per output cell
+__global__ void __launch_bounds__(256) kappa_kernel(const float *__restrict__ dens, const float2 *__restrict__ opt, float2 *__restrict__ out,
+                                                    int nx, int ny, long long n, int brick) {
+    const int hx = nx >> 1, hy = ny >> 1;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        long long src = i;
+        if (brick) {
+            const long long b = i >> 3;
+            const int sub = (int)(i & 7);
+            const int bx = (int)(b % hx), by = (int)((b / hx) % hy), bz = (int)(b / ((long long)hx * hy));
+            src = ((long long)(2 * bz + (sub >> 2)) * ny + (2 * by + ((sub >> 1) & 1))) * nx + 2 * bx + (sub & 1);
+        }
+        const float d = dens[src];
+        const float2 o = opt[src];
+        out[i] = make_float2(o.x * d, o.y * d);
     }
 }
 
@@ -1652,6 +1701,12 @@ static int stream_grid(long long n) {
 void launch_brick_permute(const GridDesc &G, float *dens_brick, cudaStream_t stream) {
     const long long n = G.nxyz;
     brick_permute_kernel<<<stream_grid(n), 256, 0, stream>>>(G.dens, dens_brick, G.nx, G.ny, n);
+}
+
+void launch_kappa(const SimArgs &A, cudaStream_t stream) {
+    const long long n = A.G.nxyz;
+    kappa_kernel<<<stream_grid(n), 256, 0, stream>>>(A.G.dens, reinterpret_cast<const float2 *>(A.opt), const_cast<float2 *>(A.kappa),
+                                                     A.G.nx, A.G.ny, n, A.brick);
 }
 
 void launch_fold_acc(const SimArgs &A, cudaStream_t stream) {

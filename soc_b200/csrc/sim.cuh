@@ -27,6 +27,7 @@ struct SimArgs {
     // order and fold_acc() un-bricks it (brick = 1)
     const float *__restrict__ dens_brick;
     int brick;
+    const float2 *__restrict__ kappa;   // WITH_ABU on the lean path: (kabs*n, ksca*n) per cell in the layout of the density array
     const int *__restrict__ nbr; // octrees: neighbour table [6*cells] of linkwalk.cuh (nullptr: climb through PAR, walk.cuh)
     int pend;                    // lean kernel: merge deposits into aligned 4-cell groups (red.global.add.v4.f32)
     int ahead;                   // lean kernel: geometry one cell ahead of the physics (sim_ahead_kernel)
@@ -65,5 +66,7 @@ struct SimArgs {
 void launch_sim(const SimArgs &A, int rng_mode, int blocks, int threads, cudaStream_t stream);
 void launch_fold_acc(const SimArgs &A, cudaStream_t stream);     // TABS += acc*TW*ADHOC; INT += acc; acc = 0
 void launch_brick_permute(const GridDesc &G, float *dens_brick, cudaStream_t stream);   // DENS -> 2x2x2-brick order
+bool sim_kappa_eligible(const SimArgs &A, int rng_mode);          // per-cell opacities can take the look-ahead kernel (needs A.kappa)
+void launch_kappa(const SimArgs &A, cudaStream_t stream);        // fills A.kappa from DENS and OPT (bricked when A.brick)
 bool sim_uses_bricks(const SimArgs &A, int rng_mode);            // does launch_sim() take the bricked kernel?
 int  sim_blocks_per_sm(int rng_mode, bool octree, bool dbl, int threads);

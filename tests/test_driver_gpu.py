@@ -144,3 +144,16 @@ def test_scattered_light_all_sources_healpix_observer(tmp_path):
     for f in range(8):
         if c[f].sum() > 0:
             assert abs(g[f].sum() / c[f].sum() - 1.0) < 0.05, (f, g[f].sum(), c[f].sum())
+
+
+def test_per_level_maps_sum_to_the_ordinary_map(tmp_path):
+    """`mapping nx ny dx 999`: the per-level images of the CUDA library add up to its ordinary map (same emission:
+    REFSTREAMS makes the two runs identical up to the map step)."""
+    kw = dict(n=6, octree=True, bgpac=20000)
+    cloud = _run(tmp_path / "lev", None, extra="REFSTREAMS\nmapping 6 6 1.0 999\n", **kw)
+    _run(tmp_path / "all", None, extra="REFSTREAMS\nmapping 6 6 1.0\n", **kw)
+    hdr = np.fromfile(str(tmp_path / "lev" / "map_dir_01_H.bin"), np.int32, 4)
+    assert list(hdr[:2]) == [6, 6] and hdr[3] == cloud.LEVELS
+    lev = np.fromfile(str(tmp_path / "lev" / "map_dir_01_H.bin"), np.float32, offset=16).reshape(int(hdr[2]), cloud.LEVELS, 6, 6)
+    full = read_map_file(str(tmp_path / "all" / "map_dir_01.bin"))
+    assert (lev[:, 1:] > 0).any() and np.allclose(lev.sum(axis=1), full, rtol=3e-5, atol=0)

@@ -158,6 +158,15 @@ def _repeat(X, runner_factory, K, key="tabs"):
     return np.array(outs)
 
 
+def _abu_opt(cells):
+    rng = np.random.default_rng(5)
+    k = 1.0 / 12
+    opt = np.empty((cells, 2), np.float32)
+    opt[:, 0] = 2.0 * k * (1.0 + rng.random(cells))
+    opt[:, 1] = 2.0 * k * (0.5 + rng.random(cells))
+    return opt.reshape(-1)
+
+
 STAT_CASES = {
     # name: (cloud, options, runner factory(seed), output key)
     "bg_reg16": (_reg(16), {}, lambda s: run_bg(batch=4, seed=s), "tabs"),
@@ -174,6 +183,10 @@ STAT_CASES = {
     "bg_reg12_int": (_reg(12), dict(noabsorbed=0), lambda s: run_bg(batch=8, seed=s), "int"),
     "bg_reg12_int2": (_reg(12), dict(save_intensity=2), lambda s: run_bg(batch=8, seed=s), "tabs"),
     "bg_reg12_abu": (_reg(12), dict(with_abu=1), lambda s: run_abu(batch=8, seed=s), "tabs"),
+    # per-cell opacities on the look-ahead kernel: odd dimensions (x-fastest layout), point source with the tile, per-frequency array
+    "bg_box_9_7_5_abu": (lambda: synth.box_cloud(9, 7, 5), dict(with_abu=1), lambda s: run_abu(batch=24, seed=s), "tabs"),
+    "ps_reg12_abu": (_reg(12), dict(with_abu=1, no_ps=1), lambda s: run_ps([(6.3, 6.2, 5.9)], batch=48, seed=s, opt=_abu_opt(12 ** 3)), "tabs"),
+    "bg_reg12_abu_int": (_reg(12), dict(with_abu=1, noabsorbed=0), lambda s: run_abu(batch=8, seed=s), "int"),
     "hp_reg12": (_reg(12), {}, lambda s: run_hp(False, batch=24, seed=s), "tabs"),
     "hp_reg12_w": (_reg(12), dict(hpbg_weighted=1), lambda s: run_hp(True, batch=24, seed=s), "tabs"),
     "cl_reg10": (_reg(10), {}, lambda s: run_cl(False, batch=6, seed=s), "tabs"),

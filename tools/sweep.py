@@ -31,6 +31,11 @@ def main():
     dev = B.dev
     for b, a in ((backend.BUF_PSPOS, w["pspos"]), (backend.BUF_PS, w["ps"]), (backend.BUF_DSC, w["dsc"]), (backend.BUF_CSC, w["csc"])):
         dev.upload(b, a)
+    if opts.get("with_abu"):          # per-cell opacities holding the same constants: same physics through the general kernel
+        n = w["cloud"].CELLS
+        o = np.empty((n, 2), np.float32)
+        o[:, 0], o[:, 1] = w["kabs"], w["ksca"]
+        dev.upload(backend.BUF_OPT, o.reshape(-1))
     for dep in [int(x) for x in args.deposit.split(",")]:
         for refill in [int(x) for x in args.refill.split(",")]:
             for agg in [int(x) for x in args.agg.split(",")]:
