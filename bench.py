@@ -334,7 +334,8 @@ def run_ours(args):
             "gpu_launches": int(c.launches) * world,          # counted by the library: 2 packet kernels + 2 folds per step and rank
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_source": (traffic or {}).get("source"),
-                         "kernel": "sim_lean_kernel<DEP_RED,%s> (background launch)" % ("brick" if os.environ.get("SOC_LAYOUT", "1") != "0" else "linear"),
+                         "kernel": "%s<DEP_RED,%s> (background launch)" % ("sim_lean_kernel" if os.environ.get("SOC_AHEAD", "1") == "0" else "sim_ahead_kernel",
+                                                                              "brick" if os.environ.get("SOC_LAYOUT", "1") != "0" else "linear"),
                          "kernel_ms": kavg, "cell_steps_per_launch": ksteps, "alg_bytes_per_cell_step": ALG_BYTES_PER_STEP,
                          "peak_source": peak_src},
             "stuck_packets": counts[3].item(),
