@@ -121,6 +121,7 @@ int soc_create(int device_ordinal, soc_context **out) {
     if (const char *e = getenv("SOC_LAYOUT")) c->layout = atoi(e) != 0;                                               // tuning knob
     if (const char *e = getenv("SOC_NAV_HOPS")) { int v = atoi(e); if (v >= 1 && v <= 8) c->nav_hops = v; }          // tuning knob
     if (const char *e = getenv("SOC_SC_BATCH")) { int v = atoi(e); if (v >= 1 && v <= 32) c->sc_batch = v; }   // tuning knob
+    if (const char *e = getenv("SOC_L2_FETCH")) { int v = atoi(e); if (v == 32 || v == 64 || v == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v); }   // tuning knob
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&c->ev0));
     CU(cudaEventCreate(&c->ev1));
