@@ -42,7 +42,7 @@ struct soc_context {
     unsigned long long *counters;      // device: packets, steps, scatterings, stuck, peels, work, -, -
     float *acc; size_t acc_bytes;      // per-launch scratch accumulator of the stream kernels (all zero between launches)
     void *scratch; size_t scratch_bytes;   // temporary device array of soc_emission2
-    int *nbr;                          // octrees: neighbour table [6*cells] (linkwalk.cuh)
+    int *nbr;                          // octrees: neighbour table [6*cells] of {cell, density} pairs (linkwalk.cuh)
     int use_nbr;
     float *dens_brick;                 // regular grids with even dimensions: DENS in 2x2x2-brick order (lean kernel)
     int layout;                        // 1 = use the bricked copy where the kernel supports it
@@ -210,7 +210,7 @@ int soc_set_grid(soc_context *c, int32_t nx, int32_t ny, int32_t nz, int32_t lev
     if (c->nbr) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->nbr)); c->nbr = nullptr; }
     if (levels > 1 && c->use_nbr && cells < (1LL << 27)) {
         // neighbour table of the production octree kernel: 24 B per cell, built once per grid
-        if (cudaMalloc(&c->nbr, (size_t)cells * 24) == cudaSuccess) { launch_neighbours(G, c->nbr, c->stream); c->launches++; }
+        if (cudaMalloc(&c->nbr, (size_t)cells * 48) == cudaSuccess) { launch_neighbours(G, c->nbr, c->stream); c->launches++; }
         else { c->nbr = nullptr; cudaGetLastError(); }
     }
     if (c->dens_brick) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->dens_brick)); c->dens_brick = nullptr; }

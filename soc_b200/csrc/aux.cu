@@ -140,6 +140,7 @@ __global__ void neighbours_kernel(GridDesc G, int *__restrict__ nbr) {
             const int ax = f >> 1, sgn = (f & 1) ? 1 : -1;
             const int tx = cx + (ax == 0 ? sgn : 0), ty = cy + (ax == 1 ? sgn : 0), tz = cz + (ax == 2 ? sgn : 0);
             int e = -1;
+            float erho = 0.0f;
             if (tx >= 0 && ty >= 0 && tz >= 0 && tx < (G.nx << level) && ty < (G.ny << level) && tz < (G.nz << level)) {
                 int lev = 0;
                 int c = ((tz >> level) * G.ny + (ty >> level)) * G.nx + (tx >> level);
@@ -152,8 +153,9 @@ __global__ void neighbours_kernel(GridDesc G, int *__restrict__ nbr) {
                     rho = G.dens[c];
                 }
                 e = (lev << SOC_NBR_LEVEL_SHIFT) | c;
+                erho = rho;
             }
-            nbr[6 * (size_t)g + f] = e;
+            reinterpret_cast<int2 *>(nbr)[6 * (size_t)g + f] = make_int2(e, __float_as_int(erho));
         }
     }
 }

@@ -3,7 +3,7 @@
 // walk.cuh finds the cell behind a face by climbing through PAR until the face is inside an octet: one loop
 // iteration of the kernel per level climbed, with only the lanes that climb active.  Here every cell carries the
 // six cells behind its faces -- the neighbour of the same level where the hierarchy has one, else the coarser leaf
-// that covers it -- built once per grid on the device (24 B per cell).  A face crossing is then one table look-up
+// that covers it, together with that cell's density or link -- built once per grid on the device (48 B per cell).  A face crossing is then one table look-up
 // plus integer arithmetic on the cell coordinates (cx,cy,cz at the cell's own level): no climb, the only level
 // changes left are descents through the links of a refined neighbour (one DENS read per level, as before).
 #pragma once
@@ -83,7 +83,10 @@ __device__ __forceinline__ bool lw_descend(const GridDesc &G, LWalker &w, const 
 __device__ __forceinline__ bool lw_cross(const GridDesc &G, const int *__restrict__ nbr, LWalker &w, const int ax, const int mirror) {
     const int abit = 1 << ax;
     const bool up = (w.up & abit) != 0;
-    const int e = __ldg(nbr + 6 * (size_t)w.cell + 2 * ax + (up ? 1 : 0));
+    // entry = {level << 27 | cell, density (or link) of that cell}: the density comes with the look-up, the walk has one
+    // dependent gather per crossing instead of two
+    const int2 e2 = __ldg(reinterpret_cast<const int2 *>(nbr) + 6 * (size_t)w.cell + 2 * ax + (up ? 1 : 0));
+    const int e = e2.x;
     const float rda = (ax == 0) ? w.rdx : ((ax == 1) ? w.rdy : w.rdz);
     if (e < 0) {                                                    // border of the cloud (rare: once per packet)
         if (mirror & ((up ? 2 : 1) << (2 * ax))) {
@@ -112,6 +115,6 @@ __device__ __forceinline__ bool lw_cross(const GridDesc &G, const int *__restric
     w.tz = ez ? ta : fmaf((float)kz * so, w.rdz, w.tz);
     w.cx = nx_; w.cy = ny_; w.cz = nz_;
     w.level = nl; w.cell = e & SOC_NBR_INDEX_MASK;
-    w.rho = __ldg(G.dens + w.cell);
+    w.rho = __int_as_float(e2.y);
     return is_leaf(w.rho);
 }
