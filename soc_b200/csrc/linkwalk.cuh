@@ -14,8 +14,7 @@
 
 struct LWalker {
     float tx, ty, tz;          // distance along the ray to the next face per axis, root-grid units
-    float rdx, rdy, rdz;       // 1/|d|
-    vec3 d;
+    float rdx, rdy, rdz;       // 1/|d|; the direction itself is not kept (lw_dir: |d_i| = 1/rd_i, sign from `up`)
     int level, cell;           // current cell: level and GLOBAL index (OFF[level] + index within the level)
     int cx, cy, cz;            // integer coordinates of the cell at its own level (root coordinate * 2^level + ...)
     int up;                    // bit b set: the ray moves towards +axis b
@@ -26,7 +25,6 @@ __device__ __forceinline__ float lw_size(int level) { return __int_as_float((127
 
 __device__ __forceinline__ void lw_set_direction(LWalker &w, const vec3 &d, float fx, float fy, float fz) {
     const float s = lw_size(w.level);
-    w.d = d;
     w.up = (d.x > 0.0f ? 1 : 0) | (d.y > 0.0f ? 2 : 0) | (d.z > 0.0f ? 4 : 0);
     w.rdx = __fdividef(1.0f, fabsf(d.x)); w.rdy = __fdividef(1.0f, fabsf(d.y)); w.rdz = __fdividef(1.0f, fabsf(d.z));
     fx = fminf(fmaxf(fx, 0.0f), 1.0f); fy = fminf(fmaxf(fy, 0.0f), 1.0f); fz = fminf(fmaxf(fz, 0.0f), 1.0f);
@@ -35,12 +33,19 @@ __device__ __forceinline__ void lw_set_direction(LWalker &w, const vec3 &d, floa
     w.tz = ((d.z > 0.0f) ? 1.0f - fz : fz) * s * w.rdz;
 }
 
+// direction of the ray, rebuilt from 1/|d| and the sign bits (used at scatterings and ray ends only)
+__device__ __forceinline__ vec3 lw_dir(const LWalker &w) {
+    const float ax = __fdividef(1.0f, w.rdx), ay = __fdividef(1.0f, w.rdy), az = __fdividef(1.0f, w.rdz);
+    vec3 d = { (w.up & 1) ? ax : -ax, (w.up & 2) ? ay : -ay, (w.up & 4) ? az : -az };
+    return d;
+}
+
 __device__ __forceinline__ void lw_fraction(const LWalker &w, float &fx, float &fy, float &fz) {
     const float is = __int_as_float((127 + w.level) << 23);       // 2^level = 1/size
-    fx = w.tx * fabsf(w.d.x) * is; fy = w.ty * fabsf(w.d.y) * is; fz = w.tz * fabsf(w.d.z) * is;
-    if (w.d.x > 0.0f) fx = 1.0f - fx;
-    if (w.d.y > 0.0f) fy = 1.0f - fy;
-    if (w.d.z > 0.0f) fz = 1.0f - fz;
+    fx = w.tx * __fdividef(1.0f, w.rdx) * is; fy = w.ty * __fdividef(1.0f, w.rdy) * is; fz = w.tz * __fdividef(1.0f, w.rdz) * is;
+    if (w.up & 1) fx = 1.0f - fx;
+    if (w.up & 2) fy = 1.0f - fy;
+    if (w.up & 4) fz = 1.0f - fz;
 }
 
 // Start at a point located by index_global(): `pos` in the level-local coordinates of (level, ind).
@@ -92,9 +97,7 @@ __device__ __forceinline__ bool lw_cross(const GridDesc &G, const int *__restric
         if (mirror & ((up ? 2 : 1) << (2 * ax))) {
             w.up ^= abit;
             const float t = lw_size(w.level) * rda;
-            if (ax == 0) { w.d.x = -w.d.x; w.tx = t; }
-            else if (ax == 1) { w.d.y = -w.d.y; w.ty = t; }
-            else { w.d.z = -w.d.z; w.tz = t; }
+            if (ax == 0) w.tx = t; else if (ax == 1) w.ty = t; else w.tz = t;
             return true;
         }
         w.cell = -1;

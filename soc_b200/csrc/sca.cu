@@ -521,7 +521,9 @@ __device__ __forceinline__ void ray_from_point(LWalker &w, const LScatterPoint &
 template <bool OCT>
 __global__ void __launch_bounds__(256, 3) sca_link_kernel(const __grid_constant__ ScaArgs S) {
     const GridDesc &G = S.G;
-    ScaCounters cnt = { 0, 0, 0, 0, 0 };
+    // per-lane work counters in 32 bits (64-bit ones cost ten registers in the loop); moved to the global counters at the
+    // end of the launch, steps and peel-off rays also whenever a lane passes 2^31
+    unsigned c_packets = 0u, c_steps = 0u, c_scat = 0u, c_stuck = 0u, c_peels = 0u;
     const int lane = threadIdx.x & 31;
     const long long nlocal = (S.nunits - S.rank + S.world - 1) / S.world;
     LWalker w; w.cell = -1; w.level = 0;
@@ -566,7 +568,11 @@ __global__ void __launch_bounds__(256, 3) sca_link_kernel(const __grid_constant_
                 bool emitted = true;
                 if (S.kind == SRC_CL) { emit_cl(S, rng, icell, pwei, pk); fix_direction(pk.dir); }
                 else emitted = emit_packet<RngPhilox, OCT>(S, rng, (int)(rid / (unsigned)S.batch), (int)(rid % (unsigned)S.batch), pk);
-                if (emitted) cnt.packets++; else pk.ind = -1;
+                if (emitted) c_packets++; else pk.ind = -1;
+                if ((c_steps | c_peels) & 0x80000000u) {
+                    atomicAdd(S.counters + 1, (unsigned long long)c_steps); atomicAdd(S.counters + 4, (unsigned long long)c_peels);
+                    c_steps = 0u; c_peels = 0u;
+                }
                 photons = pk.photons; scat = 0; nstep = 0; nevent = 0; tau = 0.0f; phase = WALK_LEAF;
                 if (pk.ind >= 0) {
                     lw_init(G, w, pk.pos, pk.dir, pk.level, pk.ind, pk.rho);
@@ -587,8 +593,8 @@ __global__ void __launch_bounds__(256, 3) sca_link_kernel(const __grid_constant_
         if (mode != RAY_IDLE && phase == WALK_END) {
             phase = WALK_LEAF; nstep = 0;
             if (mode == RAY_PEEL) {                                  // kernel_ASOC_sca.c:1010-1046 / 1849-1885
-                cnt.peels++;
-                const vec3 od = w.d;
+                c_peels++;
+                const vec3 od = lw_dir(w);
                 float cos_theta = clampf(k.dir.x * od.x + k.dir.y * od.y + k.dir.z * od.z, -cclamp, +cclamp);
                 const int kcell = k.cell;
                 // WITH_MSF: one Philox block per peel-off ray / scattering for the dust species draws
@@ -651,7 +657,7 @@ __global__ void __launch_bounds__(256, 3) sca_link_kernel(const __grid_constant_
             float ds = fmaxf(tmin, 0.0f);
             float kabs = S.kabs, ksca = S.ksca;
             if (S.with_abu) { float2 o = __ldg(reinterpret_cast<const float2 *>(S.opt) + oind); kabs = o.x; ksca = o.y; }
-            cnt.steps++; nstep++;
+            c_steps++; nstep++;
             bool go = true;
             if (mode == RAY_PEEL) {
                 if (S.nside > 0) {                                    // the ray ends at the observer
@@ -669,10 +675,10 @@ __global__ void __launch_bounds__(256, 3) sca_link_kernel(const __grid_constant_
                     ds = fminf(ds, (free_path - tau) * rcp_approx(ksca * w.rho));
                     w.tx -= ds; w.ty -= ds; w.tz -= ds;
                     lw_fraction(w, k.fx, k.fy, k.fz);
-                    k.level = w.level; k.cell = w.cell; k.cx = w.cx; k.cy = w.cy; k.cz = w.cz; k.rho = w.rho; k.dir = w.d;
-                    k.gpos.x += ds * w.d.x; k.gpos.y += ds * w.d.y; k.gpos.z += ds * w.d.z;
+                    k.level = w.level; k.cell = w.cell; k.cx = w.cx; k.cy = w.cy; k.cz = w.cz; k.rho = w.rho; k.dir = lw_dir(w);
+                    k.gpos.x += ds * k.dir.x; k.gpos.y += ds * k.dir.y; k.gpos.z += ds * k.dir.z;
                     photons *= __expf(-free_path * kabs / ksca);
-                    scat++; cnt.scat++;
+                    scat++; c_scat++;
                     idir = 0; mode = RAY_PEEL; tau = 0.0f; nstep = 0;
                     vec3 od;
                     if (S.nside > 0) {
@@ -690,11 +696,12 @@ __global__ void __launch_bounds__(256, 3) sca_link_kernel(const __grid_constant_
                     go = false;
                 } else {
                     tau += dtau;
-                    k.gpos.x += ds * w.d.x; k.gpos.y += ds * w.d.y; k.gpos.z += ds * w.d.z;
+                    const vec3 wd = lw_dir(w);
+                    k.gpos.x += ds * wd.x; k.gpos.y += ds * wd.y; k.gpos.z += ds * wd.z;
                 }
             }
             if (go) { w.tx -= tmin; w.ty -= tmin; w.tz -= tmin; phase = WALK_CROSS; }
-            if (nstep > S.max_steps) { mode = RAY_IDLE; phase = WALK_LEAF; cnt.stuck++; }
+            if (nstep > S.max_steps) { mode = RAY_IDLE; phase = WALK_LEAF; c_stuck++; }
         }
         // ---- navigation: table look-up per crossing, one descent per iteration while the cell entered is refined --------
         if (mode != RAY_IDLE && phase == WALK_DESCEND) phase = lw_descend(G, w, ax) ? WALK_LEAF : WALK_DESCEND;
@@ -705,7 +712,7 @@ __global__ void __launch_bounds__(256, 3) sca_link_kernel(const __grid_constant_
             else if (phase == WALK_DESCEND) phase = lw_descend(G, w, ax) ? WALK_LEAF : WALK_DESCEND;
         }
     }
-    flush(S, cnt);
+    { const ScaCounters cnt = { c_packets, c_steps, c_scat, c_stuck, c_peels }; flush(S, cnt); }
 }
 
 }  // namespace

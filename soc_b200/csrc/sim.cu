@@ -1303,7 +1303,10 @@ __global__ void __launch_bounds__(256, 4) sim_walk_kernel(const __grid_constant_
 template <int DEP, bool GENERAL>
 __global__ void __launch_bounds__(256, 4) sim_link_kernel(const __grid_constant__ SimArgs A) {
     const GridDesc &G = A.G;
-    Counters cnt = { 0, 0, 0, 0 };
+    // work counters: shared memory, touched once per packet (8 registers of 64-bit counters were spilled in the loop)
+    __shared__ unsigned s_cnt[4];
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const long long nlocal = (A.nunits - A.rank + A.world - 1) / A.world;
     const bool cl = GENERAL && A.kind == SIM_CL;
@@ -1350,7 +1353,7 @@ __global__ void __launch_bounds__(256, 4) sim_link_kernel(const __grid_constant_
                 else emitted = emit_source<RngPhilox, true>(A, rng, (int)(q / (unsigned)A.batch), (int)(q % (unsigned)A.batch), pk);
                 if (emitted) {
                     start_packet(A, rng, pk, A.kind != SIM_HP);
-                    cnt.packets++;
+                    count_add(&s_cnt[0], A.counters + 0, 1u);
                     alive = pk.ind >= 0;
                 }
                 if (alive) {
@@ -1378,7 +1381,7 @@ __global__ void __launch_bounds__(256, 4) sim_link_kernel(const __grid_constant_
                         csc += A.bins * msf_pick(A.abu, A.scav, A.ndust, __ldg(A.opt + 2 * (size_t)oc + 1), oc, rb.uniform());
                     }
                     float ct = __ldg(csc + clampi((int)(u_ct * A.bins), 0, A.bins - 1));
-                    vec3 nd = w.d;
+                    vec3 nd = lw_dir(w);
                     scatter_rotate(nd, ct, SOC_TWOPI * u_phi);
                     lw_set_direction(w, nd, fx, fy, fz);
                     tau = 0.0f;
@@ -1417,7 +1420,8 @@ __global__ void __launch_bounds__(256, 4) sim_link_kernel(const __grid_constant_
                 if (A.with_ali && oind == eidx) red_add(&A.xab[oind], delta * A.tw);
                 else red_add(&A.acc[oind], delta);
                 if (A.save_int2) {
-                    red_add(&A.intx[oind], delta * w.d.x); red_add(&A.inty[oind], delta * w.d.y); red_add(&A.intz[oind], delta * w.d.z);
+                    const vec3 wd = lw_dir(w);
+                    red_add(&A.intx[oind], delta * wd.x); red_add(&A.inty[oind], delta * wd.y); red_add(&A.intz[oind], delta * wd.z);
                 }
             }
         } else if (DEP == DEP_RED) {
@@ -1444,7 +1448,7 @@ __global__ void __launch_bounds__(256, 4) sim_link_kernel(const __grid_constant_
                 w.tx -= tmin; w.ty -= tmin; w.tz -= tmin;
                 phase = WALK_CROSS;
             }
-            if (nstep > A.max_steps) { alive = false; phase = WALK_LEAF; cnt.stuck++; }
+            if (nstep > A.max_steps) { alive = false; phase = WALK_LEAF; count_add(&s_cnt[3], A.counters + 3, 1u); }
         }
         // navigation: one table look-up per face crossing, then one descent per iteration while the cell entered is refined
         if (alive && phase == WALK_DESCEND) phase = lw_descend(G, w, ax) ? WALK_LEAF : WALK_DESCEND;
@@ -1463,15 +1467,16 @@ __global__ void __launch_bounds__(256, 4) sim_link_kernel(const __grid_constant_
                         lw_fraction(w, fx, fy, fz);
                         const float sz = lw_size(w.level);
                         vec3 rp = { ((float)w.cx + fx) * sz, ((float)w.cy + fy) * sz, ((float)w.cz + fz) * sz };
-                        roi_save_add(A.roi, rp, w.d, photons);
+                        roi_save_add(A.roi, rp, lw_dir(w), photons);
                     }
                     in_roi_now = r;
                 }
             }
         }
-        if (was_alive && !alive) { cnt.steps += nstep; cnt.scat += min(scat, 20); }
+        if (was_alive && !alive) { count_add(&s_cnt[1], A.counters + 1, (unsigned)nstep); count_add(&s_cnt[2], A.counters + 2, (unsigned)min(scat, 20)); }
     }
-    flush_counters(A, cnt);
+    __syncthreads();
+    if (threadIdx.x < 4 && s_cnt[threadIdx.x]) atomicAdd(A.counters + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
 }
 
 // with_abu alone stays on the lean path (look-ahead kernel with the per-cell opacity array) unless a border reflects
