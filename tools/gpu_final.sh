@@ -11,3 +11,7 @@ ncu --set full --clock-control none --import-source on -k regex:sim_ahead_kernel
 ncu -i gpurun_out/prof_r1_ahead_bg.ncu-rep --page details > gpurun_out/prof_r1_ahead_bg_details.txt 2>&1
 ncu --set full --clock-control none --import-source on -k regex:sim_lean_kernel -s 3 -c 1 -o gpurun_out/prof_r1_lean_ps -f python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_full_ps.log 2>&1
 ncu -i gpurun_out/prof_r1_lean_ps.ncu-rep --page details > gpurun_out/prof_r1_lean_ps_details.txt 2>&1
+rm -f gpurun_out/prof_r1_lean_ps.ncu-rep
+ncu --set full --clock-control none --import-source on -k regex:sim_link_kernel -s 1 -c 1 -o gpurun_out/prof_r1_link -f python tools/bench_octree.py --cpu-seconds 0.2 --bg-batch 60 > gpurun_out/ncu_link.log 2>&1
+ncu -i gpurun_out/prof_r1_link.ncu-rep --page details > gpurun_out/prof_r1_link_details.txt 2>&1
+rm -f gpurun_out/prof_r1_link.ncu-rep
