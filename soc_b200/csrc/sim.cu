@@ -1574,7 +1574,7 @@ static void launch_lean(SimArgs A, int dep, int blocks, int threads, cudaStream_
     // geometry one cell ahead of the physics (cp.async density ring).  Measured on the bench step: background launch
     // (plain adds) 60.4 -> 57.9 ms; the point-source launch with the shared-memory tile runs 63.9 ms on the lean kernel,
     // 73.6 ms (3 CTAs / SM) or 71.8 ms (4 CTAs / SM) here, so ahead = 1 takes the plain-add launches only
-    // Grids whose DENS + ACC exceed the L2 (512^3: 1 GiB) are bound by DRAM latency instead: there the look-ahead wins for
+    // Grids whose DENS + ACC exceed the L2 (512^3: 1 GiB) are bound by the rate of random DRAM transactions instead: there the look-ahead wins for
     // every accumulation engine (512^3 point-source launch 368 -> 342 ms, background 310 -> 275 ms)
     const bool beyond_l2 = A.G.nxyz > (1LL << 25);
     if (A.ahead && !PEND && A.mirror == 0 && (dep == DEP_RED || A.ahead > 1 || beyond_l2)) {
