@@ -409,6 +409,44 @@ def test_invariants_at_full_size():
     B.close()
 
 
+def test_kernel_variants_agree_at_full_size(monkeypatch):
+    """256^3, one background launch (3.1e6 packets) through the three regular-grid kernels: lean (SOC_AHEAD=0), look-ahead
+    (default) and look-ahead on per-cell opacities that hold the same constants.  Same Philox streams => same paths: the
+    results differ only by float rounding (stepped-back scattering positions, kabs*n formed in a different order)."""
+    from soc_b200 import backend, synth
+    n = 256
+    cloud = synth.regular_cloud(n)
+    dsc, csc = synth.hg_tables(0.6)
+    glob = 8 * cloud.AREA
+    kabs, ksca = 3.0 / n, 5.0 / n
+
+    def run(with_abu, **env):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        B = _backend(cloud, backend.RNG_PACKET, **(dict(with_abu=1) if with_abu else {}))
+        opt = None
+        if with_abu:
+            opt = np.empty((cloud.CELLS, 2), np.float32)
+            opt[:, 0], opt[:, 1] = kabs, ksca
+            opt = opt.reshape(-1)
+        B.zero(0)
+        B.sim_pb(glob, 1, glob, 1, 0.7, 1.0, 1.0, abs_=kabs, sca=ksca, dsc=dsc, csc=csc, opt=opt)
+        out, steps = B.tabs.astype(np.float64), B.counters.steps
+        B.close()
+        for k in env:
+            monkeypatch.delenv(k)
+        return out, steps
+
+    lean, s0 = run(False, SOC_AHEAD="0")
+    ahead, s1 = run(False)
+    kappa, s2 = run(True)
+    scale = lean.max()
+    assert abs(s1 - s0) <= 1e-6 * s0 and abs(s2 - s0) <= 1e-6 * s0          # a path flips at a cell face only by rounding
+    for other in (ahead, kappa):
+        assert abs(other.sum() - lean.sum()) <= 2e-6 * lean.sum()
+        assert (np.abs(other - lean) > 1e-4 * scale).mean() < 1e-4
+
+
 def test_c_abi_error_paths():
     from soc_b200 import backend
     make, opts, _ = CASES["bg_reg16"]
