@@ -518,6 +518,9 @@ __device__ __forceinline__ void ray_from_point(LWalker &w, const LScatterPoint &
 }
 
 // The same kernel on the neighbour table of linkwalk.cuh (octrees): a face crossing is one table look-up, no climbs.
+#ifndef SOC_SCA_REPS
+#define SOC_SCA_REPS 2
+#endif
 template <bool OCT>
 __global__ void __launch_bounds__(256, 3) sca_link_kernel(const __grid_constant__ ScaArgs S) {
     const GridDesc &G = S.G;
@@ -648,6 +651,8 @@ __global__ void __launch_bounds__(256, 3) sca_link_kernel(const __grid_constant_
                 }
             } else mode = RAY_IDLE;                                   // the packet itself has left the cloud
         }
+        #pragma unroll
+        for (int rep = 0; rep < SOC_SCA_REPS; rep++) {           // cells per refill / ray-end check
         // ---- one cell of whichever ray the lane is tracing -----------------------------------------------------
         const bool ready = mode != RAY_IDLE && phase == WALK_LEAF;
         if (ready) {
@@ -710,6 +715,7 @@ __global__ void __launch_bounds__(256, 3) sca_link_kernel(const __grid_constant_
             phase = lw_cross(G, nbr, w, ax, mode == RAY_MAIN ? S.mirror : 0) ? WALK_LEAF : WALK_DESCEND;
             if (w.cell < 0) phase = WALK_END;
             else if (phase == WALK_DESCEND) phase = lw_descend(G, w, ax) ? WALK_LEAF : WALK_DESCEND;
+        }
         }
     }
     { const ScaCounters cnt = { c_packets, c_steps, c_scat, c_stuck, c_peels }; flush(S, cnt); }

@@ -1314,6 +1314,9 @@ __global__ void __launch_bounds__(256, 4) sim_walk_kernel(const __grid_constant_
     flush_counters(A, cnt);
 }
 
+#ifndef SOC_LINK_REPS
+#define SOC_LINK_REPS 2
+#endif
 template <int DEP, bool GENERAL>
 __global__ void __launch_bounds__(256, 4) sim_link_kernel(const __grid_constant__ SimArgs A) {
     const GridDesc &G = A.G;
@@ -1403,6 +1406,8 @@ __global__ void __launch_bounds__(256, 4) sim_link_kernel(const __grid_constant_
                 }
             }
         }
+        #pragma unroll
+        for (int rep = 0; rep < SOC_LINK_REPS; rep++) {          // cell-steps / navigation rounds per refill and scattering check
         bool d = false, sc = false;
         float delta = 0.0f, ds = 0.0f, tmin = 0.0f;
         int oind = 0;
@@ -1488,6 +1493,7 @@ __global__ void __launch_bounds__(256, 4) sim_link_kernel(const __grid_constant_
             }
         }
         if (was_alive && !alive) { count_add(&s_cnt[1], A.counters + 1, (unsigned)nstep); count_add(&s_cnt[2], A.counters + 2, (unsigned)min(scat, 20)); }
+        }
     }
     __syncthreads();
     if (threadIdx.x < 4 && s_cnt[threadIdx.x]) atomicAdd(A.counters + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
