@@ -6,7 +6,7 @@ python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log
 python tools/bench_octree.py > gpurun_out/octree.log 2>&1; tail -3 gpurun_out/octree.log | cut -c1-300
 python tools/sweep.py --n 512 --deposit 2 --refill 8 --agg 24 --reps 2 > gpurun_out/sweep_512.log 2>&1; tail -1 gpurun_out/sweep_512.log
 python tools/sweep.py --n 512 --deposit 2 --refill 8 --agg 24 --reps 2 --opts noabsorbed=0,with_abu=1 > gpurun_out/sweep_512_abu.log 2>&1; tail -1 gpurun_out/sweep_512_abu.log
-ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_r1_final.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_list3.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_r1_final.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_list3.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:sim_ahead_kernel -s 3 -c 1 -o gpurun_out/prof_r1_ahead_bg -f python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_full_bg.log 2>&1
 ncu -i gpurun_out/prof_r1_ahead_bg.ncu-rep --page details > gpurun_out/prof_r1_ahead_bg_details.txt 2>&1
 ncu --set full --clock-control none --import-source on -k regex:sim_lean_kernel -s 3 -c 1 -o gpurun_out/prof_r1_lean_ps -f python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_full_ps.log 2>&1
