@@ -131,6 +131,12 @@ def cpu_leg(w, seconds_target=12.0, use_ref=True):
             kind = "reference"
     if X is None:
         X = orc.Oracle(cloud, **REF_OPTS)
+    # all host cores this process may use, whatever OMP_NUM_THREADS says (torchrun sets it to 1 for every rank)
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    (X.set_threads if kind == "reference" else orc.set_threads)(max(1, ncpu))
     cores = X.threads() if kind == "reference" else orc.threads()
     (X.set_chunk if kind == "reference" else orc.set_chunk)(4)
     common = dict(abs_=w["kabs"], sca=w["ksca"], dsc=w["dsc"], csc=w["csc"])
