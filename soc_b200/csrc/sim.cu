@@ -51,8 +51,10 @@ struct Deposit {
     __device__ __forceinline__ Deposit(const SimArgs &a, float *t) : A(a), tile(t) {}
 
     __device__ __forceinline__ void one(int oind, float delta, const vec3 &dir, int eidx, int level, int ind) const {
-        if (A.with_ali && oind == eidx) red_add(&A.xab[oind], delta * A.tw);                 // kernel_ASOC.c:1486-1494
-        else {
+        if (A.with_ali && oind == eidx) {                                                     // kernel_ASOC.c:1486-1499
+            red_add(&A.xab[oind], delta * A.tw);
+            if (A.use_int && A.use_acc) red_add(&A.inten[oind], delta);      // INT takes every absorption (the fold only sees acc)
+        } else {
             float v = A.use_acc ? delta : delta * A.tw * A.adhoc;
             float *main = A.use_acc ? A.acc : A.tabs;
             bool in_tile = false;
@@ -547,8 +549,10 @@ __global__ void __launch_bounds__(256, 4) sim_fast_kernel(const __grid_constant_
         // ---- deposit: one red.global.add.f32 (or a shared-memory tile / warp-combined add) ------------------
         if (GENERAL && (A.save_int2 || A.with_ali)) {
             if (d) {
-                if (A.with_ali && oind == f.eidx) red_add(&A.xab[oind], delta * A.tw);
-                else red_add(&A.acc[oind], delta);
+                if (A.with_ali && oind == f.eidx) {          // kernel_ASOC.c:1486-1499: XAB instead of TABS, INT as ever
+                    red_add(&A.xab[oind], delta * A.tw);
+                    if (A.use_int) red_add(&A.inten[oind], delta);
+                } else red_add(&A.acc[oind], delta);
                 if (A.save_int2) {
                     red_add(&A.intx[oind], delta * f.dir.x); red_add(&A.inty[oind], delta * f.dir.y); red_add(&A.intz[oind], delta * f.dir.z);
                 }
@@ -1256,8 +1260,10 @@ __global__ void __launch_bounds__(256, 4) sim_walk_kernel(const __grid_constant_
         }
         if (GENERAL && (A.save_int2 || A.with_ali)) {
             if (d) {
-                if (A.with_ali && oind == eidx) red_add(&A.xab[oind], delta * A.tw);
-                else red_add(&A.acc[oind], delta);
+                if (A.with_ali && oind == eidx) {            // kernel_ASOC.c:1486-1499: XAB instead of TABS, INT as ever
+                    red_add(&A.xab[oind], delta * A.tw);
+                    if (A.use_int) red_add(&A.inten[oind], delta);
+                } else red_add(&A.acc[oind], delta);
                 if (A.save_int2) {
                     red_add(&A.intx[oind], delta * w.d.x); red_add(&A.inty[oind], delta * w.d.y); red_add(&A.intz[oind], delta * w.d.z);
                 }
@@ -1436,8 +1442,10 @@ __global__ void __launch_bounds__(256, 4) sim_link_kernel(const __grid_constant_
         }
         if (GENERAL && (A.save_int2 || A.with_ali)) {
             if (d) {
-                if (A.with_ali && oind == eidx) red_add(&A.xab[oind], delta * A.tw);
-                else red_add(&A.acc[oind], delta);
+                if (A.with_ali && oind == eidx) {            // kernel_ASOC.c:1486-1499: XAB instead of TABS, INT as ever
+                    red_add(&A.xab[oind], delta * A.tw);
+                    if (A.use_int) red_add(&A.inten[oind], delta);
+                } else red_add(&A.acc[oind], delta);
                 if (A.save_int2) {
                     const vec3 wd = lw_dir(w);
                     red_add(&A.intx[oind], delta * wd.x); red_add(&A.inty[oind], delta * wd.y); red_add(&A.intz[oind], delta * wd.z);

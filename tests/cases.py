@@ -112,7 +112,7 @@ def run_cl(emweight, batch=2, glob=512, seed=0.13):
         X.zero(1)
         X.sim_cl(glob, c.CELLS * batch, batch, seed, 1.1, abs_=2.0 * k, sca=1.5 * k, dsc=DSC6, csc=CSC6, emit=emit,
                  emwei=emwei)
-        return dict(tabs=X.tabs.copy(), xab=X.xab.copy())
+        return dict(tabs=X.tabs.copy(), xab=X.xab.copy(), int=X.int_.copy())
     return run
 
 
@@ -330,14 +330,23 @@ CASES = {
     "ps_reg12_ext5":   (_reg(12), dict(no_ps=1, ps_method=5),
                         run_ps([(6.0, 6.0, 25.0)], batch=10, xps_nside=[1], xps_side=[4, 0, 0],
                                xps_area=[0.8, 0.0, 0.0])),
+    # PS_METHOD 4 (kernel_ASOC.c:377-397): source above the cloud in z, packets sent into the cone that holds the cloud
+    "ps_reg12_ext4":   (_reg(12), dict(no_ps=1, ps_method=4), run_ps([(6.0, 6.0, 30.0)], batch=20)),
+    # NX > 100 with LEVELS >= 3: positions in double precision (DIMLIM, kernel_ASOC_aux.c:25-37, 207-211)
+    "bg_oct101_dbl":   (lambda: synth.box_cloud(101, 6, 6, levels=3, refine_fraction=0.15), dict(noabsorbed=0), run_bg(batch=2, seed=0.45)),
     "hp_reg12":        (_reg(12), {}, run_hp(False)),
     "hp_reg12_w":      (_reg(12), dict(hpbg_weighted=1), run_hp(True)),
     "cl_reg10":        (_reg(10), {}, run_cl(False)),
     "cl_oct6_ew_ali":  (_oct(6, 3), dict(use_emweight=1, with_ali=1), run_cl(True)),
+    # ALI with per-frequency absorptions: INT takes the absorptions of the emitting cell too (kernel_ASOC.c:1486-1499)
+    "cl_reg10_ali_int": (_reg(10), dict(with_ali=1, noabsorbed=0), run_cl(False, seed=0.17)),
     "map_reg16":       (_reg(16), {}, run_map((20, 16), [(0.0, 0.0), (90.0, 0.0), (60.0, 30.0)])),
     "map_reg16_colden": (_reg(16), {}, run_map((16, 16), [(35.0, 110.0)], map_dx=0.7, colden=1, centre_off=0.8)),
     "map_reg120_dbl":  (lambda: Cloud(120, 8, 8, [120 * 64], synth.plummer_density(120)[56:64, 56:64, :].ravel()),
                         {}, run_map((30, 8), [(90.0, 90.0), (50.0, 20.0)], map_dx=3.9)),
+    # NX >= 200: the other ray set-up branch of Mapping (kernel_ASOC_map.c:571-626), the one 256^3 / 512^3 runs take
+    "map_reg200_far":  (lambda: Cloud(200, 8, 8, [200 * 64], synth.plummer_density(200)[96:104, 96:104, :].ravel()),
+                        {}, run_map((40, 8), [(90.0, 90.0), (50.0, 20.0), (0.0, 0.0)], map_dx=4.9)),
     "map_oct8_3":      (_oct(8, 3), dict(with_abu=1), run_map((24, 24), [(0.0, 0.0), (60.0, 30.0)], map_dx=0.4, abu=True)),
     "map_oct6_4_thr":  (_oct(6, 4, 0.25, 8), dict(level_threshold=1), run_map((20, 20), [(120.0, 200.0)], map_dx=0.35)),
     "map_reg16_persp": (_reg(16), {}, run_map((32, 16), [(0.0, 0.0)], intobs=(7.3, 8.4, 9.1))),

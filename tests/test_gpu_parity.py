@@ -151,11 +151,16 @@ def test_emission2_matches_oracle():
 
 
 def _repeat(X, runner_factory, K, key="tabs"):
-    outs = []
+    """K repetitions with different seeds; `key` may be a tuple of output names (returns a dict of arrays then)."""
+    keys = key if isinstance(key, tuple) else (key,)
+    outs = {k: [] for k in keys}
     for k in range(K):
         run = runner_factory(0.05 + 0.9 * (k + 0.5) / K)
-        outs.append(run(X)[key])
-    return np.array(outs)
+        res = run(X)
+        for kk in keys:
+            outs[kk].append(res[kk])
+    outs = {k: np.array(v) for k, v in outs.items()}
+    return outs if isinstance(key, tuple) else outs[key]
 
 
 def _abu_opt(cells):
@@ -190,7 +195,20 @@ STAT_CASES = {
     "hp_reg12": (_reg(12), {}, lambda s: run_hp(False, batch=24, seed=s), "tabs"),
     "hp_reg12_w": (_reg(12), dict(hpbg_weighted=1), lambda s: run_hp(True, batch=24, seed=s), "tabs"),
     "cl_reg10": (_reg(10), {}, lambda s: run_cl(False, batch=6, seed=s), "tabs"),
-    "cl_oct6_ew_ali": (_oct(6, 3), dict(use_emweight=1, with_ali=1), lambda s: run_cl(True, batch=2, seed=s), "tabs"),
+    "cl_oct6_ew_ali": (_oct(6, 3), dict(use_emweight=1, with_ali=1), lambda s: run_cl(True, batch=2, seed=s), ("tabs", "xab")),
+    # ALI with per-frequency absorptions: XAB takes the emitting cell's share of TABS, INT takes everything (kernel_ASOC.c:1486-1499)
+    "cl_reg16_ali_int": (_reg(16), dict(with_ali=1, noabsorbed=0), lambda s: run_cl(False, batch=4, seed=s), ("tabs", "xab", "int")),
+    "cl_oct6_ali_int": (_oct(6, 3), dict(with_ali=1, noabsorbed=0), lambda s: run_cl(False, batch=3, seed=s), ("tabs", "xab", "int")),
+    # optically thick (tau ~ 20 per cell: packets die in the surface layers, many scatterings per cell) and very thin
+    # (tau ~ 1e-4 per cell: the series branch of the absorbed fraction) media
+    "bg_reg16_thick": (_reg(16), dict(noabsorbed=0), lambda s: run_bg(batch=16, seed=s, tau_a=80.0, tau_s=240.0), ("tabs", "int")),
+    "ps_reg16_thick": (_reg(16), dict(no_ps=1), lambda s: run_ps([(8.3, 8.2, 7.9)], batch=48, seed=s, tau_a=2.0, tau_s=8.0), "tabs"),     # tau ~ 8 per cell at the source: few cells see the packets
+    "bg_oct6_thick": (_oct(6, 3), {}, lambda s: run_bg(batch=32, seed=s, tau_a=40.0, tau_s=80.0), "tabs"),
+    "bg_reg16_thin": (_reg(16), dict(noabsorbed=0), lambda s: run_bg(batch=4, seed=s, tau_a=1.0e-3, tau_s=1.0e-3), ("tabs", "int")),
+    "ps_reg16_thin": (_reg(16), dict(no_ps=1), lambda s: run_ps([(8.3, 8.2, 7.9)], batch=24, seed=s, tau_a=2.0e-3, tau_s=1.0e-3), "tabs"),
+    # the cone of PS_METHOD 4 (kernel_ASOC.c:377-397); positions in double precision (NX > 100 with LEVELS >= 3)
+    "ps_reg12_ext4": (_reg(12), dict(no_ps=1, ps_method=4), lambda s: run_ps([(6.0, 6.0, 30.0)], batch=48, seed=s), "tabs"),
+    "bg_oct101_dbl": (lambda: synth.box_cloud(101, 6, 6, levels=3, refine_fraction=0.15), dict(noabsorbed=0), lambda s: run_bg(batch=4, seed=s), "int"),
     # several scattering functions (WITH_MSF), reflecting borders (MIRROR; the expectation is the oracle's
     # mirror_exact variant: the production kernels reflect only the border that was crossed)
     "bg_reg12_msf": (_reg(12), dict(with_abu=1, with_msf=1, ndust=2), lambda s: run_bg_msf(batch=8, seed=s), "tabs"),
@@ -219,16 +237,19 @@ def test_packet_streams_statistical_parity(name):
     make, opts, fac, key = STAT_CASES[name]
     cloud = make()
     K = 16
+    keys = key if isinstance(key, tuple) else (key,)
     O = orc.Oracle(cloud, mirror_exact=1, **opts)
-    a = _repeat(O, fac, K, key)
+    a = _repeat(O, fac, K, keys)
     B = _backend(cloud, backend.RNG_PACKET, **opts)
     if name.endswith("_refgeo"):
         B.dev.set_geometry(1)
-    b = _repeat(B, fac, K, key)
-    chi2, dof, tot, tot_sigma = chi2_per_dof(b, a, min_rel=1e-4)
-    assert dof > (100 if key == "roi_save" else 300)
-    assert chi2 <= 1.1, "%s: chi2/dof = %.3f over %d cells" % (name, chi2, dof)
-    assert tot <= max(4.0 * tot_sigma, 1e-4), "%s: total energy differs by %.2e (sigma %.2e)" % (name, tot, tot_sigma)
+    b = _repeat(B, fac, K, keys)
+    for kk in keys:          # every accumulator the options enable
+        chi2, dof, tot, tot_sigma = chi2_per_dof(b[kk], a[kk], min_rel=1e-4)
+        assert dof > (50 if name == "ps_reg16_thick" else (100 if kk == "roi_save" else 300)), "%s/%s: %d cells" % (name, kk, dof)
+        assert chi2 <= 1.1, "%s/%s: chi2/dof = %.3f over %d cells" % (name, kk, chi2, dof)
+        assert tot <= max(4.0 * tot_sigma, 1e-4), "%s/%s: total energy differs by %.2e (sigma %.2e)" % (name, kk, tot, tot_sigma)
+    assert B.counters.reserved[0] == 0, "%s: packets killed by the step guard" % name
     B.close()
 
 
