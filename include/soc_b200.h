@@ -31,7 +31,7 @@
  * New (no counterpart in the single-device reference):
  *   soc_set_shard, soc_device_ptr           packet sharding over ranks and the device addresses a
  *                                           host-side NCCL all-reduce needs
- *   soc_set_rng_mode, soc_set_tuning, soc_set_geometry, soc_set_layout,
+ *   soc_set_rng_mode, soc_set_tuning, soc_set_geometry, soc_set_layout, soc_set_domains,
  *   soc_get_counters, soc_last_launch_ms,
  *   soc_stream                              stream layout, accumulation engine, work counters, device timing
  */
@@ -152,6 +152,14 @@ int  soc_set_geometry(soc_context *ctx, int mode);
  * dimensions: 1 (default) = 2x2x2 bricks (one 32-byte sector per brick), 0 = the reference's x-fastest order.
  * Buffers seen through this ABI always use the reference order. */
 int  soc_set_layout(soc_context *ctx, int mode);
+
+/* Domain-tiled propagation on regular grids (production layout): the grid is cut into boxes of at most `edge` cells per
+ * axis, the packet kernels work on one box at a time so that its density / accumulator arrays stay in the L2, and a
+ * packet leaving a box through an interior face is parked (its full stepping state) until the box it enters is
+ * processed -- same packets, same paths, same results up to the order of the float additions.  edge = 0 (default):
+ * automatic, boxes of <= 256 cells per axis when DENS + the scratch accumulator exceed the L2 (more than 2^25 cells);
+ * edge < 0: off; edge > 0 (even): forced with that box size.  Launches in this mode return when the packets are done. */
+int  soc_set_domains(soc_context *ctx, int edge);
 
 int  soc_upload(soc_context *ctx, int buffer, const void *host, size_t nbytes);
 int  soc_download(soc_context *ctx, int buffer, void *host, size_t nbytes);

@@ -42,7 +42,7 @@ class SocCounters(C.Structure):
 
 
 _EXPORTS = """soc_last_error soc_version soc_create soc_destroy soc_sync soc_set_params soc_set_grid soc_set_rng_mode
-soc_set_shard soc_set_tuning soc_set_geometry soc_set_layout soc_set_roi soc_upload soc_download soc_clear soc_device_ptr soc_zero_amc soc_sim_pb soc_sim_hp
+soc_set_shard soc_set_tuning soc_set_geometry soc_set_layout soc_set_domains soc_set_roi soc_upload soc_download soc_clear soc_device_ptr soc_zero_amc soc_sim_pb soc_sim_hp
 soc_sim_cl soc_absorbed_begin soc_absorbed_add soc_absorbed_finish soc_eq_temperature soc_emission soc_emission2 soc_mapping soc_mapping_levels soc_healpix_mapping soc_ps_tau soc_sca_zero_out soc_sca_ps soc_sca_pb soc_sca_hp soc_sca_cl
 soc_get_counters soc_reset_counters soc_last_launch_ms soc_stream""".split()
 
@@ -71,6 +71,7 @@ def load_library(path=None):
     L.soc_set_tuning.argtypes = [vp, i, i, i]
     L.soc_set_geometry.argtypes = [vp, i]
     L.soc_set_layout.argtypes = [vp, i]
+    L.soc_set_domains.argtypes = [vp, i]
     L.soc_set_roi.argtypes = [vp, vp, i, i, vp]
     L.soc_upload.argtypes = [vp, i, vp, C.c_size_t]
     L.soc_download.argtypes = [vp, i, vp, C.c_size_t]
@@ -188,6 +189,9 @@ class Device:
 
     def set_layout(self, mode):
         self._ck(self.L.soc_set_layout(self.ctx, int(mode)))
+
+    def set_domains(self, edge):
+        self._ck(self.L.soc_set_domains(self.ctx, int(edge)))
 
     def upload(self, buf, array, dtype=np.float32):
         a = np.ascontiguousarray(array, dtype)

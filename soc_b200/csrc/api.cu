@@ -46,9 +46,15 @@ struct soc_context {
     int use_nbr;
     float *dens_brick;                 // regular grids with even dimensions: DENS in 2x2x2-brick order (lean kernel)
     int layout;                        // 1 = use the bricked copy where the kernel supports it
+    int brick_ns[3];                   // domains per axis the bricked copy is laid out for (0 = not permuted yet)
     int pend;                          // 1 = merged deposits (vector reds) in the lean kernel
     float2 *kappa; size_t kappa_cells; // WITH_ABU on regular grids: (kabs*n, ksca*n) per cell, rebuilt before every launch
     int ahead;                         // 1 = look-ahead variant of the lean kernel (geometry one cell ahead, cp.async density ring)
+    int domains;                       // domain-tiled propagation: 0 auto, < 0 off, > 0 forced box edge (soc_set_domains)
+    QPk *queues; size_t queue_bytes;   // domain mode: packet queues of all domains
+    unsigned *q_tail, *h_tail;         // queue lengths on the device / in pinned host memory
+    QPk *q_sorted; size_t q_sorted_bytes; unsigned *q_hist;   // domain mode: one queue sorted by entry block and direction
+    unsigned long long domain_launches, domain_parked;   // statistics of the last domain-mode launch
     unsigned long long launches;
     soc_params P;
     bool have_params, have_grid;
@@ -119,6 +125,7 @@ int soc_create(int device_ordinal, soc_context **out) {
     c->ahead = 1;
     if (const char *e = getenv("SOC_AHEAD")) c->ahead = atoi(e);                                                       // tuning knob
     if (const char *e = getenv("SOC_LAYOUT")) c->layout = atoi(e) != 0;                                               // tuning knob
+    if (const char *e = getenv("SOC_DOMAINS")) c->domains = atoi(e);                                                  // tuning knob
     if (const char *e = getenv("SOC_NAV_HOPS")) { int v = atoi(e); if (v >= 1 && v <= 8) c->nav_hops = v; }          // tuning knob
     if (const char *e = getenv("SOC_SC_BATCH")) { int v = atoi(e); if (v >= 1 && v <= 32) c->sc_batch = v; }   // tuning knob
     if (const char *e = getenv("SOC_L2_FETCH")) { int v = atoi(e); if (v == 32 || v == 64 || v == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v); }   // tuning knob
@@ -144,6 +151,11 @@ int soc_destroy(soc_context *c) {
     if (c->nbr) cudaFree(c->nbr);
     if (c->scratch) cudaFree(c->scratch);
     if (c->kappa) cudaFree(c->kappa);
+    if (c->queues) cudaFree(c->queues);
+    if (c->q_tail) cudaFree(c->q_tail);
+    if (c->q_sorted) cudaFree(c->q_sorted);
+    if (c->q_hist) cudaFree(c->q_hist);
+    if (c->h_tail) cudaFreeHost(c->h_tail);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -215,10 +227,9 @@ int soc_set_grid(soc_context *c, int32_t nx, int32_t ny, int32_t nz, int32_t lev
     }
     if (c->dens_brick) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->dens_brick)); c->dens_brick = nullptr; }
     if (levels == 1 && nx % 2 == 0 && ny % 2 == 0 && nz % 2 == 0) {
-        CU(cudaMalloc(&c->dens_brick, (size_t)cells * 4));
-        launch_brick_permute(G, c->dens_brick, c->stream);
-        c->launches++;
+        CU(cudaMalloc(&c->dens_brick, (size_t)cells * 4));       // permuted by the first launch that uses it (sim_launch)
     }
+    c->brick_ns[0] = c->brick_ns[1] = c->brick_ns[2] = 0;
     CU(cudaGetLastError());
     c->have_grid = true;
     return SOC_OK;
@@ -293,6 +304,13 @@ int soc_set_layout(soc_context *c, int mode) {
     NEED_CTX(c);
     if (mode != 0 && mode != 1) return fail(SOC_ERR_ARG, "soc_set_layout: %d", mode);
     c->layout = mode;
+    return SOC_OK;
+}
+
+int soc_set_domains(soc_context *c, int edge) {
+    NEED_CTX(c);
+    if (edge > 0 && (edge % 2 != 0 || edge < 4)) return fail(SOC_ERR_ARG, "soc_set_domains: box edge %d must be even and >= 4", edge);
+    c->domains = edge;
     return SOC_OK;
 }
 
@@ -442,6 +460,134 @@ static int sim_common(soc_context *c, SimArgs &A, int kind, int batch, float see
     return SOC_OK;
 }
 
+// Domain-tiled propagation (soc_set_domains, sim.cuh): emission pass into the queues of the domains, then the domain with
+// the longest queue is processed until every queue is empty.  The last few packets (ping-pong between domains after many
+// scatterings) are finished on the whole grid by the general kernel, which parks nothing.  A.dsplit / A.dsize hold the
+// boxes; DENS (and KAPPA) are already laid out for them.
+static int sim_launch_domains(soc_context *c, SimArgs &A, int blocks, int threads) {
+    const int dim[3] = { A.G.nx, A.G.ny, A.G.nz };
+    const int *ns = A.dsplit, *ds = A.dsize;
+    const int D = ns[0] * ns[1] * ns[2];
+    if (D > 4096) return fail(SOC_ERR_UNSUPPORTED, "soc_set_domains: %d domains (at most 4096)", D);
+    const long long dcells = (long long)ds[0] * ds[1] * ds[2];
+    // chunk of work units in flight: every queue must be able to hold all of them
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    long long chunk = 1LL << 24;
+    if (const char *e = getenv("SOC_DOMAIN_CHUNK")) { long long v = atoll(e); if (v >= 1024) chunk = v; }      // tuning knob
+    const size_t budget = (free_b + c->queue_bytes) / 2;
+    while (chunk > 65536 && (size_t)chunk * D * sizeof(QPk) > budget) chunk >>= 1;
+    if (chunk > A.nlocal) chunk = A.nlocal > 0 ? A.nlocal : 1;
+    const size_t need_b = (size_t)chunk * D * sizeof(QPk);
+    if (c->queue_bytes < need_b) {
+        if (c->queues) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->queues)); c->queues = nullptr; c->queue_bytes = 0; }
+        CU(cudaMalloc(&c->queues, need_b));
+        c->queue_bytes = need_b;
+    }
+    if (c->q_tail == nullptr) { CU(cudaMalloc(&c->q_tail, 4096 * sizeof(unsigned))); CU(cudaMallocHost(&c->h_tail, 4096 * sizeof(unsigned))); }
+    int sort = 1;                              // queues sorted by entry block and direction before they are processed
+    if (const char *e = getenv("SOC_DOMAIN_SORT")) sort = atoi(e);                                               // tuning knob
+    if (sort) {
+        const size_t sb = (size_t)chunk * sizeof(QPk);
+        if (c->q_sorted_bytes < sb) {
+            if (c->q_sorted) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->q_sorted)); c->q_sorted = nullptr; c->q_sorted_bytes = 0; }
+            CU(cudaMalloc(&c->q_sorted, sb));
+            c->q_sorted_bytes = sb;
+        }
+        if (c->q_hist == nullptr) CU(cudaMalloc(&c->q_hist, 32768 * sizeof(unsigned)));
+    }
+    // below this many parked packets the rest runs over the whole grid: a domain launch with few packets costs its
+    // latency (~0.5 ms: one packet after the other through ~250 dependent steps) whatever it holds
+    long long cleanup = 1LL << 18;
+    if (const char *e = getenv("SOC_DOMAIN_CLEANUP")) cleanup = atoll(e);                                         // tuning knob
+    long long sort_min = 1LL << 16;
+    static bool first_pass[4096];
+    const int verbose = getenv("SOC_DOMAIN_VERBOSE") ? atoi(getenv("SOC_DOMAIN_VERBOSE")) : 0;
+    A.dom = 1; A.q_base = c->queues; A.q_tail = c->q_tail; A.q_cap = chunk;
+    const int deposit = A.deposit;
+    const long long nlocal = A.nlocal;
+    c->domain_launches = 0; c->domain_parked = 0;
+    for (long long u0 = 0; u0 < nlocal; u0 += chunk) {
+        const long long n = nlocal - u0 < chunk ? nlocal - u0 : chunk;
+        CU(cudaMemsetAsync(c->q_tail, 0, D * sizeof(unsigned), c->stream));
+        A.unit0 = u0; A.q_base = c->queues;
+        for (int d = 0; d < D; d++) first_pass[d] = true;
+        launch_sim_emit(A, n, c->stream);
+        c->launches++;
+        for (;;) {
+            CU(cudaMemcpyAsync(c->h_tail, c->q_tail, D * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            long long total = 0; int best = -1;
+            for (int d = 0; d < D; d++) { total += c->h_tail[d]; if (c->h_tail[d] > 0 && (best < 0 || c->h_tail[d] > c->h_tail[best])) best = d; }
+            if (total == 0) break;
+            const bool whole = total <= cleanup && D > 1;
+            if (whole && D <= 64) {                  // every queue in one launch of the general kernel
+                A.q_nparts = D; A.q_part[0] = 0;
+                for (int d = 0; d < D; d++) A.q_part[d + 1] = A.q_part[d] + c->h_tail[d];
+                A.nlocal = total;
+                long long needb = (total + threads - 1) / threads;
+                const int b = (int)(needb < blocks ? (needb < 1 ? 1 : needb) : blocks);
+                CU(cudaMemsetAsync(c->q_tail, 0, D * sizeof(unsigned), c->stream));
+                CU(cudaMemsetAsync(A.work, 0, sizeof(unsigned long long), c->stream));
+                launch_sim_cleanup(A, b, threads, c->stream);
+                c->launches++; c->domain_launches++; c->domain_parked += total;
+                CU(cudaGetLastError());
+                break;                               // nothing is parked by this pass
+            }
+            for (int d = 0; d < D; d++) {
+                if (c->h_tail[d] == 0 || (!whole && d != best)) continue;
+                const int dd[3] = { d % ns[0], (d / ns[0]) % ns[1], d / (ns[0] * ns[1]) };
+                A.dom_faces = 0;
+                for (int k = 0; k < 3; k++) {
+                    A.dom_lo[k] = dd[k] * ds[k];
+                    A.dom_hi[k] = (dd[k] + 1) * ds[k] - 1;
+                    if (A.dom_lo[k] == 0) A.dom_faces |= 1 << (2 * k);
+                    if (A.dom_hi[k] == dim[k] - 1) A.dom_faces |= 2 << (2 * k);
+                }
+                A.dom_base = (int)(d * dcells);
+                // the shared-memory tile around the point source only where the domain holds a part of it
+                A.deposit = deposit;
+                if (deposit == DEP_TILE) {
+                    const int t0[3] = { A.tile_x0, A.tile_y0, A.tile_z0 };
+                    for (int k = 0; k < 3; k++) if (t0[k] > A.dom_hi[k] || t0[k] + SOC_TILE_N - 1 < A.dom_lo[k]) A.deposit = DEP_RED;
+                }
+                A.q_in = c->queues + (size_t)d * (size_t)chunk;
+                A.nlocal = c->h_tail[d];
+                A.q_nparts = 1; A.q_part[0] = 0; A.q_part[1] = A.nlocal;
+                A.q_base = whole ? c->queues + (size_t)d * (size_t)chunk : c->queues;      // the clean-up kernel addresses queue `part` of q_base
+                long long needb = (A.nlocal + threads - 1) / threads;
+                const int b = (int)(needb < blocks ? (needb < 1 ? 1 : needb) : blocks);
+                CU(cudaMemsetAsync(c->q_tail + d, 0, sizeof(unsigned), c->stream));
+                CU(cudaMemsetAsync(A.work, 0, sizeof(unsigned long long), c->stream));
+                if (verbose > 1) { CU(cudaEventRecord(c->ev0, c->stream)); }
+                // not the emission queue of a point source: all its packets start in one cell, and lanes that walk the same cells
+                // in step serialise on their adds (same-address RED / shared-memory atomics)
+                const bool fresh = first_pass[d];
+                first_pass[d] = false;
+                if (!whole && sort && A.nlocal >= (long long)sort_min && !(sort < 3 && fresh && A.kind == SIM_PS) && !(sort == 2 && A.kind == SIM_PS)) {
+                    launch_queue_sort(A.q_in, A.nlocal, c->q_sorted, c->q_hist, A.dom_lo, c->stream);
+                    A.q_in = c->q_sorted;
+                    c->launches += 3;
+                }
+                if (whole) launch_sim_cleanup(A, b, threads, c->stream);
+                else       launch_sim_domain(A, b, threads, c->stream);
+                if (verbose > 1) {
+                    CU(cudaEventRecord(c->ev1, c->stream)); CU(cudaEventSynchronize(c->ev1));
+                    float ms = 0.0f; cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+                    fprintf(stderr, "soc_b200:   domain %d%s: %u packets, dep %d, %.3f ms\n", d, whole ? " (whole grid)" : "", c->h_tail[d], A.deposit, ms);
+                }
+                c->launches++; c->domain_launches++; c->domain_parked += c->h_tail[d];
+            }
+            CU(cudaGetLastError());
+        }
+    }
+    A.deposit = deposit; A.nlocal = nlocal; A.dom = 0;
+    if (verbose)
+        fprintf(stderr, "soc_b200: %d domains of %dx%dx%d cells, chunk %lld, %llu domain launches, %llu packet visits for %lld packets\n",
+                D, ds[0], ds[1], ds[2], chunk, c->domain_launches, c->domain_parked, nlocal);
+    return SOC_OK;
+}
+
 static int sim_launch(soc_context *c, SimArgs &A, const char *who) {
     A.nlocal = (A.nunits - A.rank + A.world - 1) / A.world;
     const bool oct = A.G.levels > 1, dbl = A.G.dbl_sim != 0;
@@ -481,11 +627,40 @@ static int sim_launch(soc_context *c, SimArgs &A, const char *who) {
         A.brick = sim_uses_bricks(A, c->rng_mode) ? 1 : 0;
         A.nbr = c->nbr;
         A.pend = c->pend; A.ahead = c->ahead;
-        A.slab_xy = A.G.nx * A.G.ny; A.brick_by = 4 * A.G.nx - 2; A.brick_bz = 2 * A.G.nx * A.G.ny - 4;
+        if (const char *e = getenv("SOC_SCRAMBLE")) A.scramble = atoi(e) ? 1000003ull : 0ull;                    // experiment: packets in scattered order
+        A.slab_xy = A.G.nx * A.G.ny;
     }
     CU(cudaEventRecord(c->ev0, c->stream));
+    // layout of the bricked arrays: one box (plain brick order), or the boxes of the domain mode (soc_set_domains)
+    int edge = 0;
+    A.dsplit[0] = A.dsplit[1] = A.dsplit[2] = 1;
+    A.dsize[0] = A.G.nx; A.dsize[1] = A.G.ny; A.dsize[2] = A.G.nz;
+    if (c->rng_mode != SOC_RNG_REFERENCE && c->domains >= 0 && A.brick && sim_domains_eligible(A, c->rng_mode))
+        edge = c->domains > 0 ? c->domains : (A.G.nxyz > (1LL << 25) ? 256 : 0);
+    bool domains = false;
+    if (edge > 0 && (c->domains > 0 || A.G.nx > edge || A.G.ny > edge || A.G.nz > edge)) {       // forced: also with a single domain
+        const int dim[3] = { A.G.nx, A.G.ny, A.G.nz };
+        domains = true;
+        for (int k = 0; k < 3; k++) {
+            const int ns = (dim[k] + edge - 1) / edge;
+            if (dim[k] % ns != 0 || ((dim[k] / ns) & 1)) domains = false;        // boxes of one size with even edges only
+            A.dsplit[k] = ns; A.dsize[k] = dim[k] / ns;
+        }
+        if (!domains) { A.dsplit[0] = A.dsplit[1] = A.dsplit[2] = 1; A.dsize[0] = dim[0]; A.dsize[1] = dim[1]; A.dsize[2] = dim[2]; }
+    }
+    if (A.brick) {
+        if (c->brick_ns[0] != A.dsplit[0] || c->brick_ns[1] != A.dsplit[1] || c->brick_ns[2] != A.dsplit[2]) {
+            launch_brick_permute(A, c->dens_brick, c->stream);
+            c->launches++;
+            for (int k = 0; k < 3; k++) c->brick_ns[k] = A.dsplit[k];
+        }
+        A.brick_by = 4 * A.dsize[0] - 2; A.brick_bz = 2 * A.dsize[0] * A.dsize[1] - 4;
+    }
     if (A.kappa != nullptr) { launch_kappa(A, c->stream); c->launches++; }     // OPT may have changed since the last launch
-    launch_sim(A, c->rng_mode, blocks, threads, c->stream);
+    if (domains) {
+        int r = sim_launch_domains(c, A, blocks, threads);
+        if (r != SOC_OK) return r;
+    } else launch_sim(A, c->rng_mode, blocks, threads, c->stream);
     if (A.use_acc) { launch_fold_acc(A, c->stream); c->launches++; }
     CU(cudaEventRecord(c->ev1, c->stream));
     c->timed = true;

@@ -422,6 +422,40 @@ __device__ __forceinline__ float free_path_fast(const SimArgs &A, RNG &rng, floa
     return sample_free_path(A, rng, photons);
 }
 
+// ---- domain queues (QPk, sim.cuh) ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void q_store(QPk *p, const QPk &v) {
+    const float4 *s = reinterpret_cast<const float4 *>(&v);
+    float4 *d = reinterpret_cast<float4 *>(p);
+    d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
+}
+__device__ __forceinline__ QPk q_load(const QPk *p) {
+    QPk v;
+    const float4 *s = reinterpret_cast<const float4 *>(p);
+    float4 *d = reinterpret_cast<float4 *>(&v);
+    d[0] = __ldcs(s); d[1] = __ldcs(s + 1); d[2] = __ldcs(s + 2); d[3] = __ldcs(s + 3);      // read once: streaming
+    return v;
+}
+// parks the packet in the queue of the domain that holds cell (ix,iy,iz)
+__device__ __forceinline__ void q_push(const SimArgs &A, const QPk &v) {
+    const int d = ((v.iz / A.dsize[2]) * A.dsplit[1] + v.iy / A.dsize[1]) * A.dsplit[0] + v.ix / A.dsize[0];
+    const unsigned slot = atomicAdd(A.q_tail + d, 1u);
+    q_store(A.q_base + (size_t)d * (size_t)A.q_cap + slot, v);
+}
+// the same for a whole warp (emission pass: every lane calls; `have` = this lane has a packet): one atomic per domain
+// and warp instead of one per packet -- 3e7 adds to a single counter would serialise in the L2
+__device__ __forceinline__ void q_push_warp(const SimArgs &A, const QPk &v, bool have) {
+    const unsigned act = __ballot_sync(FULL, have);
+    if (!have) return;
+    const int lane = threadIdx.x & 31;
+    const int d = ((v.iz / A.dsize[2]) * A.dsplit[1] + v.iy / A.dsize[1]) * A.dsplit[0] + v.ix / A.dsize[0];
+    const unsigned peers = __match_any_sync(act, d);
+    const int leader = __ffs(peers) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(A.q_tail + d, (unsigned)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    q_store(A.q_base + (size_t)d * (size_t)A.q_cap + base + __popc(peers & ((1u << lane) - 1u)), v);
+}
+
 // DEP: accumulation engine (DepositMode).  GENERAL = false drops the per-cell opacities, the intensity vector,
 // the ALI split and the cell-emission source from the loop (uniform tests the common runs never take).
 template <int DEP, bool GENERAL>
@@ -431,7 +465,9 @@ __global__ void __launch_bounds__(256, 4) sim_fast_kernel(const __grid_constant_
     const GridDesc &G = A.G;
     Counters cnt = { 0, 0, 0, 0 };
     const int lane = threadIdx.x & 31;
-    const long long nlocal = (A.nunits - A.rank + A.world - 1) / A.world;
+    // A.dom: clean-up pass of the domain mode -- the work units are packets parked in a queue (q_in[0 .. nlocal)), resumed
+    // here on the whole grid in the reference's cell order; their absorptions go straight to TABS / INT
+    const long long nlocal = A.dom ? A.nlocal : (A.nunits - A.rank + A.world - 1) / A.world;
     const int sy_ = G.nx, sz_ = G.nx * G.ny;
     const bool cl = GENERAL && A.kind == SIM_CL;
     const bool abu = GENERAL && A.with_abu;
@@ -457,7 +493,7 @@ __global__ void __launch_bounds__(256, 4) sim_fast_kernel(const __grid_constant_
                 if (need) {
                     long long u = (long long)base + __popc(nm & ((1u << lane) - 1u));
                     if (u >= nlocal) more = false;
-                    else { q = (unsigned long long)u * A.world + A.rank; got = true; }
+                    else { q = A.dom ? (unsigned long long)u : (unsigned long long)u * A.world + A.rank; got = true; }
                 }
             }
             if (got && cl) { icell = (int)q; iray = 0; nray = cl_rays(A, icell, pwei); got = false; }
@@ -465,7 +501,21 @@ __global__ void __launch_bounds__(256, 4) sim_fast_kernel(const __grid_constant_
                 q = (unsigned long long)(unsigned)icell | ((unsigned long long)(unsigned)iray << 32);
                 iray++; got = true;
             }
-            if (got) {
+            if (got && A.dom) {                      // resume a parked packet
+                int part = 0;                        // which queue the unit lies in (all non-empty queues in one launch)
+                while (part + 1 < A.q_nparts && (long long)q >= A.q_part[part + 1]) part++;
+                const QPk s = q_load(A.q_base + (size_t)part * (size_t)A.q_cap + (q - (unsigned long long)A.q_part[part]));
+                f.tx = s.tx; f.ty = s.ty; f.tz = s.tz; f.rdx = s.rdx; f.rdy = s.rdy; f.rdz = s.rdz;
+                const float adx = rcp_approx(s.rdx), ady = rcp_approx(s.rdy), adz = rcp_approx(s.rdz);
+                f.dir.x = (s.upm & 1u) ? adx : -adx; f.dir.y = (s.upm & 2u) ? ady : -ady; f.dir.z = (s.upm & 4u) ? adz : -adz;
+                f.ix = s.ix; f.iy = s.iy; f.iz = s.iz; f.ind = (s.iz * G.ny + s.iy) * G.nx + s.ix;
+                f.rho = __ldg(G.dens + f.ind);
+                f.photons = s.photons; f.free_path = s.free_path; f.tau = s.tau;
+                f.scat = (int)(s.sn >> 24); f.nstep = (int)(s.sn & 0xffffffu); f.eidx = -1;
+                f.rid = (unsigned long long)s.u * A.world + A.rank;
+                if (A.with_abu) f.opt = __ldg(reinterpret_cast<const float2 *>(A.opt) + f.ind);
+                alive = true;
+            } else if (got) {
                 RngPhilox rng; rng.seed(A.phx, q);
                 Packet pk; pk.ind = -1; pk.level = 0; pk.eidx = -1; pk.rho = 0.0f;
                 bool emitted = true;
@@ -558,7 +608,10 @@ __global__ void __launch_bounds__(256, 4) sim_fast_kernel(const __grid_constant_
                 }
             }
         } else if (DEP == DEP_RED) {
-            if (d) red_add(&A.acc[oind], delta);
+            if (d) {
+                if (A.dom) { red_add(&A.tabs[oind], delta * A.tw * A.adhoc); if (A.use_int) red_add(&A.inten[oind], delta); }
+                else red_add(&A.acc[oind], delta);
+            }
         } else {
             bool comb = __any_sync(FULL, d && f.nstep < A.agg_steps);
             if (comb) {
@@ -640,8 +693,18 @@ __global__ void __launch_bounds__(256, 4) sim_fast_kernel(const __grid_constant_
 //     picked by the parity bit of the axis, which is a bit of the bricked index itself.
 // Same Philox packet streams, same draw order and same physics as the fast kernel.
 // =================================================================================================================
-__device__ __forceinline__ int brick_index(int ix, int iy, int iz, int hx, int hy) {
+__host__ __device__ __forceinline__ int brick_index(int ix, int iy, int iz, int hx, int hy) {
     return ((((iz >> 1) * hy + (iy >> 1)) * hx + (ix >> 1)) << 3) | ((iz & 1) << 2) | ((iy & 1) << 1) | (ix & 1);
+}
+// Domain-major brick order: the grid is cut into dsplit[0] x dsplit[1] x dsplit[2] boxes of dsize[] cells (all of one size,
+// even edges), each box is one contiguous run of 2x2x2 bricks -- a launch that works on one box touches one contiguous
+// piece of DENS and of the accumulator (L2 sets, DRAM pages and the 256 MB reach of the TLB all see a small array).
+// One box = the plain brick order.
+__device__ __forceinline__ int layout_index(const SimArgs &A, int ix, int iy, int iz) {
+    const int dx = ix / A.dsize[0], dy = iy / A.dsize[1], dz = iz / A.dsize[2];
+    const int d = (dz * A.dsplit[1] + dy) * A.dsplit[0] + dx;
+    return d * (A.dsize[0] * A.dsize[1] * A.dsize[2]) +
+           brick_index(ix - dx * A.dsize[0], iy - dy * A.dsize[1], iz - dz * A.dsize[2], A.dsize[0] >> 1, A.dsize[1] >> 1);
 }
 
 // cell-steps per pass of the outer loop (refill and scattering checks once per pass): measured on the bench step, lean
@@ -667,13 +730,22 @@ struct LeanPk {
 #define LEAN_SCAT(sn)  ((sn) >> 24)
 
 // direction-dependent part of the state from the fractional position (fx,fy,fz) inside cell (ix,iy,iz)
+// cells lo..hi (inclusive) per axis: the box the crossing counters refer to -- the grid, or the domain of the launch
+struct Box { int lox, loy, loz, hix, hiy, hiz; };
+template <bool DOM>
+__device__ __forceinline__ Box launch_box(const SimArgs &A) {
+    Box b;
+    b.lox = DOM ? A.dom_lo[0] : 0; b.loy = DOM ? A.dom_lo[1] : 0; b.loz = DOM ? A.dom_lo[2] : 0;
+    b.hix = DOM ? A.dom_hi[0] : A.G.nx - 1; b.hiy = DOM ? A.dom_hi[1] : A.G.ny - 1; b.hiz = DOM ? A.dom_hi[2] : A.G.nz - 1;
+    return b;
+}
 template <bool BRICK>
-__device__ __forceinline__ void lean_set_direction(const GridDesc &G, LeanPk<BRICK> &f, const vec3 &d, int ix, int iy, int iz,
+__device__ __forceinline__ void lean_set_direction(const Box &b, LeanPk<BRICK> &f, const vec3 &d, int ix, int iy, int iz,
                                                    float fx, float fy, float fz) {
     f.rdx = rcp_approx(fabsf(d.x)); f.rdy = rcp_approx(fabsf(d.y)); f.rdz = rcp_approx(fabsf(d.z));     // |d_i| >= DEPS/sqrt(3)
     f.tx = face_distance(fx, d.x, f.rdx); f.ty = face_distance(fy, d.y, f.rdy); f.tz = face_distance(fz, d.z, f.rdz);
     const bool ux = d.x > 0.0f, uy = d.y > 0.0f, uz = d.z > 0.0f;
-    f.cx = ux ? G.nx - 1 - ix : ix; f.cy = uy ? G.ny - 1 - iy : iy; f.cz = uz ? G.nz - 1 - iz : iz;
+    f.cx = ux ? b.hix - ix : ix - b.lox; f.cy = uy ? b.hiy - iy : iy - b.loy; f.cz = uz ? b.hiz - iz : iz - b.loz;
     f.upm = (ux ? 1 : 0) | (uy ? 2 : 0) | (uz ? 4 : 0);
 }
 
@@ -683,7 +755,7 @@ __device__ __forceinline__ void count_add(unsigned *s32, unsigned long long *g64
     if (old < 0x80000000u && old + v >= 0x80000000u) { atomicSub(s32, 0x80000000u); atomicAdd(g64, 0x80000000ull); }
 }
 
-template <int DEP, bool BRICK, bool PEND>
+template <int DEP, bool BRICK, bool PEND, bool DOM>
 __global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant__ SimArgs A) {
     __shared__ float smem[DEP == DEP_TILE ? SOC_TILE_CELLS : 1];
     __shared__ float s_pend[PEND ? 4 * 256 : 1];
@@ -696,6 +768,7 @@ __global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant_
     const float *__restrict__ dens = BRICK ? A.dens_brick : G.dens;
     const int lane = threadIdx.x & 31;
     const float kabs = A.kabs, ksca = A.ksca;
+    const Box box = launch_box<DOM>(A);
     LeanPk<BRICK> f; f.ind = 0; f.u = 0; f.rho = 0.0f; f.sn = 0;
     bool alive = false, wsc = false;
     int tskip = 0;                   // DEP_TILE: the packet cannot be inside the tile during its next tskip steps
@@ -711,8 +784,19 @@ __global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant_
             base = __shfl_sync(FULL, base, leader);
             if (!alive) {
                 const unsigned long long u = base + __popc(nm & ((1u << lane) - 1u));
-                if (u < (unsigned long long)A.nlocal) {
-                    const unsigned long long q = u * A.world + A.rank;
+                if (DOM && u < (unsigned long long)A.nlocal) {        // a packet parked at the border of this domain
+                    const QPk s = q_load(A.q_in + u);
+                    alive = true; wsc = false; tskip = 0;
+                    f.tx = s.tx; f.ty = s.ty; f.tz = s.tz; f.rdx = s.rdx; f.rdy = s.rdy; f.rdz = s.rdz;
+                    f.photons = s.photons; f.free_path = s.free_path; f.tau = s.tau; f.sn = s.sn; f.u = s.u; f.upm = (int)s.upm;
+                    f.cx = (s.upm & 1u) ? box.hix - s.ix : s.ix - box.lox; f.cy = (s.upm & 2u) ? box.hiy - s.iy : s.iy - box.loy;
+                    f.cz = (s.upm & 4u) ? box.hiz - s.iz : s.iz - box.loz;
+                    f.ind = A.dom_base + brick_index(s.ix - box.lox, s.iy - box.loy, s.iz - box.loz, A.dsize[0] >> 1, A.dsize[1] >> 1);
+                    f.rho = __ldg(dens + f.ind);
+                }
+                if (!DOM && u < (unsigned long long)A.nlocal) {
+                    const unsigned long long us = A.scramble ? (u * A.scramble) % (unsigned long long)A.nlocal : u;
+                    const unsigned long long q = us * A.world + A.rank;
                     RngPhilox rng; rng.seed(A.phx, q);
                     Packet pk; pk.ind = -1; pk.level = 0; pk.eidx = -1; pk.rho = 0.0f;
                     const int id = (int)(q / (unsigned)A.batch), III = (int)(q % (unsigned)A.batch);
@@ -724,15 +808,15 @@ __global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant_
                         alive = true; wsc = false; tskip = 0;
                         const int ix = clampi((int)floorf(pk.pos.x), 0, G.nx - 1), iy = clampi((int)floorf(pk.pos.y), 0, G.ny - 1),
                                   iz = clampi((int)floorf(pk.pos.z), 0, G.nz - 1);
-                        lean_set_direction<BRICK>(G, f, pk.dir, ix, iy, iz, pk.pos.x - (float)ix, pk.pos.y - (float)iy, pk.pos.z - (float)iz);
+                        lean_set_direction<BRICK>(box, f, pk.dir, ix, iy, iz, pk.pos.x - (float)ix, pk.pos.y - (float)iy, pk.pos.z - (float)iz);
                         f.ind = BRICK ? brick_index(ix, iy, iz, G.nx >> 1, G.ny >> 1) : (iz * G.ny + iy) * G.nx + ix;
                         f.rho = pk.rho; f.photons = pk.photons; f.free_path = pk.free_path; f.tau = 0.0f;
-                        f.sn = 0; f.u = (unsigned)u;
+                        f.sn = 0; f.u = (unsigned)us;
                     }
                 }
             }
             more = base + (unsigned long long)__popc(nm) < (unsigned long long)A.nlocal;
-            if (lane == leader) {                                  // packets started by this warp
+            if (!DOM && lane == leader) {                          // packets started by this warp (domain mode: counted at emission)
                 const unsigned long long left = base < (unsigned long long)A.nlocal ? (unsigned long long)A.nlocal - base : 0ull;
                 count_add(&s_cnt[0], A.counters + 0, (unsigned)min((unsigned long long)__popc(nm), left));
             }
@@ -748,13 +832,13 @@ __global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant_
                     const float adx = rcp_approx(f.rdx), ady = rcp_approx(f.rdy), adz = rcp_approx(f.rdz);
                     const float ax = f.tx * adx, ay = f.ty * ady, az = f.tz * adz;
                     const float fx = ux ? 1.0f - ax : ax, fy = uy ? 1.0f - ay : ay, fz = uz ? 1.0f - az : az;
-                    const int ix = ux ? G.nx - 1 - f.cx : f.cx, iy = uy ? G.ny - 1 - f.cy : f.cy, iz = uz ? G.nz - 1 - f.cz : f.cz;
+                    const int ix = ux ? box.hix - f.cx : box.lox + f.cx, iy = uy ? box.hiy - f.cy : box.loy + f.cy, iz = uz ? box.hiz - f.cz : box.loz + f.cz;
                     RngBlock rb(A.phx, (unsigned long long)f.u * A.world + A.rank, 0x10000u + LEAN_SCAT(f.sn));
                     f.free_path = free_path_fast(A, rb, f.photons);
                     const float ct = __ldg(A.csc + clampi((int)(rb.uniform() * A.bins), 0, A.bins - 1));
                     vec3 nd = { ux ? adx : -adx, uy ? ady : -ady, uz ? adz : -adz };
                     scatter_rotate(nd, ct, SOC_TWOPI * rb.uniform());
-                    lean_set_direction<BRICK>(G, f, nd, ix, iy, iz, fx, fy, fz);
+                    lean_set_direction<BRICK>(box, f, nd, ix, iy, iz, fx, fy, fz);
                     f.tau = 0.0f;
                     wsc = false;
                 }
@@ -767,6 +851,7 @@ __global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant_
         float delta = 0.0f, tmin = 0.0f, rho_n = 0.0f;
         int nind = 0;
         bool px = false, py = false, inb = false, sc = false;
+        bool parked = false;             // DOM: the packet went to the queue of the next domain
         const int oind = f.ind;
         if (run) {
             tmin = fminf(f.tx, fminf(f.ty, f.tz));
@@ -817,8 +902,8 @@ __global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant_
                 // coordinates at the time of the deposit: the crossing counters have not been updated yet.  A cell at
                 // Chebyshev distance D from the tile cannot be followed by a tile cell within the next D - 1 steps (one
                 // step moves one cell along one axis), so the test is skipped that long.
-                const int ix = (f.upm & 1) ? G.nx - 1 - f.cx : f.cx, iy = (f.upm & 2) ? G.ny - 1 - f.cy : f.cy,
-                          iz = (f.upm & 4) ? G.nz - 1 - f.cz : f.cz;
+                const int ix = (f.upm & 1) ? box.hix - f.cx : box.lox + f.cx, iy = (f.upm & 2) ? box.hiy - f.cy : box.loy + f.cy,
+                          iz = (f.upm & 4) ? box.hiz - f.cz : box.loz + f.cz;
                 const int ux = ix - A.tile_x0, uy = iy - A.tile_y0, uz = iz - A.tile_z0;
                 const int tfar = max(max(max(-ux, ux - (SOC_TILE_N - 1)), max(-uy, uy - (SOC_TILE_N - 1))), max(-uz, uz - (SOC_TILE_N - 1)));
                 if (tfar <= 0) {
@@ -863,15 +948,32 @@ __global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant_
                     f.cx -= px; f.cy -= py; f.cz -= pz;
                     f.ind = nind; f.rho = rho_n;
                     alive = inb;
+                    if (DOM && !inb) {
+                        // left the domain: through a face of the grid the packet is gone, through an interior face it is parked
+                        // for the domain it enters (complete DDA state; the counter of the crossed axis stands at -1 = one
+                        // cell beyond the border)
+                        const int face = (px ? 0 : (py ? 2 : 4)) + ((f.upm & abit_) ? 1 : 0);
+                        if (!((A.dom_faces >> face) & 1)) parked = true;       // stored at the end of the step, the warp together
+                    }
                 }
             }
             bool stuck = false;
-            if (LEAN_STEPS(f.sn) > (unsigned)A.max_steps) { alive = false; wsc = false; stuck = true; }
-            if (!alive) {                                       // packet finished: once per packet
+            if (LEAN_STEPS(f.sn) > (unsigned)A.max_steps && !parked) { alive = false; wsc = false; stuck = true; }
+            if (!alive && !parked) {                            // packet finished: once per packet
                 count_add(&s_cnt[1], A.counters + 1, LEAN_STEPS(f.sn));
                 count_add(&s_cnt[2], A.counters + 2, min(LEAN_SCAT(f.sn), 20u));
                 if (stuck) count_add(&s_cnt[3], A.counters + 3, 1u);
             }
+        }
+        if (DOM && __any_sync(FULL, parked)) {                  // one queue slot request per target domain and warp
+            QPk o;
+            o.tx = f.tx; o.ty = f.ty; o.tz = f.tz; o.rdx = f.rdx; o.rdy = f.rdy; o.rdz = f.rdz;
+            o.photons = f.photons; o.free_path = f.free_path; o.tau = f.tau;
+            o.ix = (f.upm & 1) ? box.hix - f.cx : box.lox + f.cx; o.iy = (f.upm & 2) ? box.hiy - f.cy : box.loy + f.cy;
+            o.iz = (f.upm & 4) ? box.hiz - f.cz : box.loz + f.cz;
+            o.upm = (unsigned)f.upm; o.sn = f.sn; o.u = f.u; o.pad = 0u;
+            if (!parked) { o.ix = box.lox; o.iy = box.loy; o.iz = box.loz; }
+            q_push_warp(A, o, parked);
         }
         }
     }
@@ -888,7 +990,7 @@ __global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant_
                 const int ux = i % SOC_TILE_N, uy = (i / SOC_TILE_N) % SOC_TILE_N, uz = i / (SOC_TILE_N * SOC_TILE_N);
                 const int ix = A.tile_x0 + ux, iy = A.tile_y0 + uy, iz = A.tile_z0 + uz;
                 if (ix < G.nx && iy < G.ny && iz < G.nz)
-                    red_add(&A.acc[BRICK ? brick_index(ix, iy, iz, G.nx >> 1, G.ny >> 1) : (iz * G.ny + iy) * G.nx + ix], v);
+                    red_add(&A.acc[BRICK ? layout_index(A, ix, iy, iz) : (iz * G.ny + iy) * G.nx + ix], v);
             }
         }
     }
@@ -940,7 +1042,7 @@ __device__ __forceinline__ float2 lds_f32x2(unsigned saddr) {
 // density array (kappa_kernel builds it from DENS and OPT before the launch), instead of the density and the two
 // opacities: 8 B gathered per step instead of 12, and the ring slots are 8 bytes wide.
 #define AH_SLOT_SHIFT(KAPPA) ((KAPPA) ? 1 : 0)
-template <int DEP, bool BRICK, int CTAS, bool KAPPA>
+template <int DEP, bool BRICK, int CTAS, bool KAPPA, bool DOM>
 __global__ void __launch_bounds__(256, CTAS) sim_ahead_kernel(const __grid_constant__ SimArgs A) {
     __shared__ float smem[DEP == DEP_TILE ? SOC_TILE_CELLS : 1];
     __shared__ __align__(8) float s_ring[(KAPPA ? 4 : 2) * 256];   // slot s of lane t: s_ring[s * 256 + t] (float or float2 units)
@@ -954,6 +1056,7 @@ __global__ void __launch_bounds__(256, CTAS) sim_ahead_kernel(const __grid_const
     const int lane = threadIdx.x & 31;
     const float kabs = A.kabs, ksca = A.ksca;
     const unsigned ring = (unsigned)__cvta_generic_to_shared(&s_ring[KAPPA ? 2 * threadIdx.x : threadIdx.x]);
+    const Box box = launch_box<DOM>(A);
     float ka = 0.0f;                 // KAPPA: kabs*n of the physics cell (f.rho holds ksca*n)
     LeanPk<BRICK> f; f.ind = 0; f.u = 0; f.rho = 0.0f; f.sn = 0; f.upm = 0;        // f.ind = index of cell A
     int ind = 0;                     // cell the physics works on
@@ -972,8 +1075,22 @@ __global__ void __launch_bounds__(256, CTAS) sim_ahead_kernel(const __grid_const
             base = __shfl_sync(FULL, base, leader);
             if (!(st & AH_ALIVE)) {
                 const unsigned long long u = base + __popc(nm & ((1u << lane) - 1u));
-                if (u < (unsigned long long)A.nlocal) {
-                    const unsigned long long q = u * A.world + A.rank;
+                if (DOM && u < (unsigned long long)A.nlocal) {        // a packet parked at the border of this domain: not primed
+                    const QPk s = q_load(A.q_in + u);
+                    f.tx = s.tx; f.ty = s.ty; f.tz = s.tz; f.rdx = s.rdx; f.rdy = s.rdy; f.rdz = s.rdz;
+                    f.photons = s.photons; f.free_path = s.free_path; f.tau = s.tau; f.sn = s.sn; f.u = s.u; f.upm = (int)s.upm;
+                    f.cx = (s.upm & 1u) ? box.hix - s.ix : s.ix - box.lox; f.cy = (s.upm & 2u) ? box.hiy - s.iy : s.iy - box.loy;
+                    f.cz = (s.upm & 4u) ? box.hiz - s.iz : s.iz - box.loz;
+                    f.ind = A.dom_base + brick_index(s.ix - box.lox, s.iy - box.loy, s.iz - box.loz, A.dsize[0] >> 1, A.dsize[1] >> 1);
+                    ind = f.ind;
+                    st = (st & AH_SLOT) | AH_ALIVE | s.upm;
+                    tskip = 0;
+                    if (KAPPA) { const float2 k2 = __ldg(kappa + f.ind); ka = k2.x; f.rho = k2.y; }
+                    else f.rho = __ldg(dens + f.ind);
+                }
+                if (!DOM && u < (unsigned long long)A.nlocal) {
+                    const unsigned long long us = A.scramble ? (u * A.scramble) % (unsigned long long)A.nlocal : u;
+                    const unsigned long long q = us * A.world + A.rank;
                     RngPhilox rng; rng.seed(A.phx, q);
                     Packet pk; pk.ind = -1; pk.level = 0; pk.eidx = -1; pk.rho = 0.0f;
                     const int id = (int)(q / (unsigned)A.batch), III = (int)(q % (unsigned)A.batch);
@@ -984,19 +1101,19 @@ __global__ void __launch_bounds__(256, CTAS) sim_ahead_kernel(const __grid_const
                     if (pk.ind >= 0) {
                         const int ix = clampi((int)floorf(pk.pos.x), 0, G.nx - 1), iy = clampi((int)floorf(pk.pos.y), 0, G.ny - 1),
                                   iz = clampi((int)floorf(pk.pos.z), 0, G.nz - 1);
-                        lean_set_direction<BRICK>(G, f, pk.dir, ix, iy, iz, pk.pos.x - (float)ix, pk.pos.y - (float)iy, pk.pos.z - (float)iz);
+                        lean_set_direction<BRICK>(box, f, pk.dir, ix, iy, iz, pk.pos.x - (float)ix, pk.pos.y - (float)iy, pk.pos.z - (float)iz);
                         st = (st & AH_SLOT) | AH_ALIVE | (unsigned)f.upm;
                         tskip = 0;
                         f.ind = BRICK ? brick_index(ix, iy, iz, G.nx >> 1, G.ny >> 1) : (iz * G.ny + iy) * G.nx + ix;
                         ind = f.ind;
                         f.rho = pk.rho; f.photons = pk.photons; f.free_path = pk.free_path; f.tau = 0.0f;
                         if (KAPPA) { const float2 k2 = __ldg(kappa + f.ind); ka = k2.x; f.rho = k2.y; }
-                        f.sn = 0; f.u = (unsigned)u;
+                        f.sn = 0; f.u = (unsigned)us;
                     }
                 }
             }
             more = base + (unsigned long long)__popc(nm) < (unsigned long long)A.nlocal;
-            if (lane == leader) {
+            if (!DOM && lane == leader) {
                 const unsigned long long left = base < (unsigned long long)A.nlocal ? (unsigned long long)A.nlocal - base : 0ull;
                 count_add(&s_cnt[0], A.counters + 0, (unsigned)min((unsigned long long)__popc(nm), left));
             }
@@ -1018,13 +1135,13 @@ __global__ void __launch_bounds__(256, CTAS) sim_ahead_kernel(const __grid_const
                     const float adx = rcp_approx(f.rdx), ady = rcp_approx(f.rdy), adz = rcp_approx(f.rdz);
                     const float px_ = f.tx * adx, py_ = f.ty * ady, pz_ = f.tz * adz;
                     const float fx = ux ? 1.0f - px_ : px_, fy = uy ? 1.0f - py_ : py_, fz = uz ? 1.0f - pz_ : pz_;
-                    const int ix = ux ? G.nx - 1 - f.cx : f.cx, iy = uy ? G.ny - 1 - f.cy : f.cy, iz = uz ? G.nz - 1 - f.cz : f.cz;
+                    const int ix = ux ? box.hix - f.cx : box.lox + f.cx, iy = uy ? box.hiy - f.cy : box.loy + f.cy, iz = uz ? box.hiz - f.cz : box.loz + f.cz;
                     RngBlock rb(A.phx, (unsigned long long)f.u * A.world + A.rank, 0x10000u + LEAN_SCAT(f.sn));
                     f.free_path = free_path_fast(A, rb, f.photons);
                     const float ct = __ldg(A.csc + clampi((int)(rb.uniform() * A.bins), 0, A.bins - 1));
                     vec3 nd = { ux ? adx : -adx, uy ? ady : -ady, uz ? adz : -adz };
                     scatter_rotate(nd, ct, SOC_TWOPI * rb.uniform());
-                    lean_set_direction<BRICK>(G, f, nd, ix, iy, iz, fx, fy, fz);
+                    lean_set_direction<BRICK>(box, f, nd, ix, iy, iz, fx, fy, fz);
                     st = (st & AH_SLOT) | AH_ALIVE | (unsigned)f.upm;          // not primed, not waiting
                     f.ind = ind;
                     f.tau = 0.0f;
@@ -1038,6 +1155,7 @@ __global__ void __launch_bounds__(256, CTAS) sim_ahead_kernel(const __grid_const
         const bool phys = (st & (AH_ALIVE | AH_WSC | AH_PRIMED)) == (AH_ALIVE | AH_PRIMED);
         float delta = 0.0f, len = seg;
         bool sc = false;
+        bool parked = false;             // DOM: the packet went to the queue of the next domain
         if (phys) {
             const float krho = KAPPA ? f.rho : ksca * f.rho;
             const float tend = fmaf(seg, krho, f.tau);
@@ -1072,8 +1190,8 @@ __global__ void __launch_bounds__(256, CTAS) sim_ahead_kernel(const __grid_const
                 // coordinates of the physics cell: the counters belong to A, one crossing (axis AH_AXA) further on.  A cell
                 // at Chebyshev distance D from the tile is not followed by a tile cell within D - 1 steps: test skipped
                 const int kx = f.cx + ((st >> 4) & 1u), ky = f.cy + ((st >> 5) & 1u), kz = f.cz + ((st >> 6) & 1u);
-                const int ix = (st & 1u) ? G.nx - 1 - kx : kx, iy = (st & 2u) ? G.ny - 1 - ky : ky,
-                          iz = (st & 4u) ? G.nz - 1 - kz : kz;
+                const int ix = (st & 1u) ? box.hix - kx : box.lox + kx, iy = (st & 2u) ? box.hiy - ky : box.loy + ky,
+                          iz = (st & 4u) ? box.hiz - kz : box.loz + kz;
                 const int ux = ix - A.tile_x0, uy = iy - A.tile_y0, uz = iz - A.tile_z0;
                 const int tfar = max(max(max(-ux, ux - (SOC_TILE_N - 1)), max(-uy, uy - (SOC_TILE_N - 1))), max(-uz, uz - (SOC_TILE_N - 1)));
                 if (tfar <= 0) {
@@ -1090,7 +1208,14 @@ __global__ void __launch_bounds__(256, CTAS) sim_ahead_kernel(const __grid_const
                 seg -= len;                                      // distance back from the entry of A to the scattering point
                 if (LEAN_SCAT(f.sn) > 20u) st &= ~(AH_ALIVE | AH_WSC);
             } else if ((st & (AH_PRIMED | AH_AIN)) == AH_PRIMED) {
-                st &= ~AH_ALIVE;                                 // the physics cell was the last one inside the grid
+                st &= ~AH_ALIVE;                                 // the physics cell was the last one inside the grid (DOM: the domain)
+                if (DOM) {
+                    // the geometry stands at the entry of A, one cell beyond the border (the counter of the crossed axis is -1):
+                    // through an interior face the packet is parked for the domain that holds A, not primed
+                    const unsigned axb = (st >> 4) & 7u;
+                    const int face = ((axb & 1u) ? 0 : ((axb & 2u) ? 2 : 4)) + ((st & axb) ? 1 : 0);
+                    if (!((A.dom_faces >> face) & 1)) parked = true;           // stored at the end of the step, the warp together
+                }
             } else {
                 // geometry: from the entry of A (unprimed: from the packet's position in its cell) to the next face
                 const float tmin = fminf(f.tx, fminf(f.ty, f.tz));
@@ -1117,12 +1242,22 @@ __global__ void __launch_bounds__(256, CTAS) sim_ahead_kernel(const __grid_const
                 st = ((st & ~(AH_AXA | AH_AIN)) ^ AH_SLOT) | AH_PRIMED | (abit << 4) | (inb ? AH_AIN : 0u);
             }
             bool stuck = false;
-            if (LEAN_STEPS(f.sn) > (unsigned)A.max_steps) { st &= ~(AH_ALIVE | AH_WSC); stuck = true; }
-            if (!(st & AH_ALIVE)) {                             // packet finished: once per packet
+            if (LEAN_STEPS(f.sn) > (unsigned)A.max_steps && !parked) { st &= ~(AH_ALIVE | AH_WSC); stuck = true; }
+            if (!(st & AH_ALIVE) && !parked) {                  // packet finished: once per packet
                 count_add(&s_cnt[1], A.counters + 1, LEAN_STEPS(f.sn));
                 count_add(&s_cnt[2], A.counters + 2, min(LEAN_SCAT(f.sn), 20u));
                 if (stuck) count_add(&s_cnt[3], A.counters + 3, 1u);
             }
+        }
+        if (DOM && __any_sync(FULL, parked)) {                  // one queue slot request per target domain and warp
+            QPk o;
+            o.tx = f.tx; o.ty = f.ty; o.tz = f.tz; o.rdx = f.rdx; o.rdy = f.rdy; o.rdz = f.rdz;
+            o.photons = f.photons; o.free_path = f.free_path; o.tau = f.tau;
+            o.ix = (st & 1u) ? box.hix - f.cx : box.lox + f.cx; o.iy = (st & 2u) ? box.hiy - f.cy : box.loy + f.cy;
+            o.iz = (st & 4u) ? box.hiz - f.cz : box.loz + f.cz;
+            o.upm = st & AH_UPM; o.sn = f.sn; o.u = f.u; o.pad = 0u;
+            if (!parked) { o.ix = box.lox; o.iy = box.loy; o.iz = box.loz; }
+            q_push_warp(A, o, parked);
         }
         }
     }
@@ -1134,7 +1269,7 @@ __global__ void __launch_bounds__(256, CTAS) sim_ahead_kernel(const __grid_const
                 const int ux = i % SOC_TILE_N, uy = (i / SOC_TILE_N) % SOC_TILE_N, uz = i / (SOC_TILE_N * SOC_TILE_N);
                 const int ix = A.tile_x0 + ux, iy = A.tile_y0 + uy, iz = A.tile_z0 + uz;
                 if (ix < G.nx && iy < G.ny && iz < G.nz)
-                    red_add(&A.acc[BRICK ? brick_index(ix, iy, iz, G.nx >> 1, G.ny >> 1) : (iz * G.ny + iy) * G.nx + ix], v);
+                    red_add(&A.acc[BRICK ? layout_index(A, ix, iy, iz) : (iz * G.ny + iy) * G.nx + ix], v);
             }
         }
     }
@@ -1507,6 +1642,45 @@ __global__ void __launch_bounds__(256, 4) sim_link_kernel(const __grid_constant_
     if (threadIdx.x < 4 && s_cnt[threadIdx.x]) atomicAdd(A.counters + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
 }
 
+// =================================================================================================================
+// Domain mode, emission pass: one thread per work unit of the chunk; the packet is emitted exactly as the lean / look-ahead
+// kernels do it in their refill block and parked in the queue of the domain its first cell belongs to.
+// =================================================================================================================
+template <bool BRICK>
+__global__ void __launch_bounds__(256) sim_emit_queue_kernel(const __grid_constant__ SimArgs A, long long n) {
+    const GridDesc &G = A.G;
+    const Box box = launch_box<false>(A);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long nround = (n + 31) & ~31LL;                 // whole warps stay in the loop (warp-wide queue push)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+        const unsigned long long u = (unsigned long long)(A.unit0 + i);
+        const unsigned long long q = u * A.world + A.rank;
+        Packet pk; pk.ind = -1; pk.level = 0; pk.eidx = -1; pk.rho = 0.0f;
+        QPk o;
+        o.ix = o.iy = o.iz = 0;
+        if (i < n) {
+        RngPhilox rng; rng.seed(A.phx, q);
+        const int id = (int)(q / (unsigned)A.batch), III = (int)(q % (unsigned)A.batch);
+        if (A.kind == SIM_PS)      emit_ps<SimArgs, RngPhilox, false>(A, rng, III, pk);
+        else if (A.kind == SIM_BG) emit_bg<SimArgs, RngPhilox, false>(A, rng, id, pk);
+        else                       emit_hp<SimArgs, RngPhilox, false>(A, rng, pk);
+        start_packet(A, rng, pk, A.kind != SIM_HP);
+        }
+        if (pk.ind >= 0) {
+            const int ix = clampi((int)floorf(pk.pos.x), 0, G.nx - 1), iy = clampi((int)floorf(pk.pos.y), 0, G.ny - 1),
+                      iz = clampi((int)floorf(pk.pos.z), 0, G.nz - 1);
+            LeanPk<BRICK> f;
+            lean_set_direction<BRICK>(box, f, pk.dir, ix, iy, iz, pk.pos.x - (float)ix, pk.pos.y - (float)iy, pk.pos.z - (float)iz);
+            o.tx = f.tx; o.ty = f.ty; o.tz = f.tz; o.rdx = f.rdx; o.rdy = f.rdy; o.rdz = f.rdz;
+            o.photons = pk.photons; o.free_path = pk.free_path; o.tau = 0.0f;
+            o.ix = ix; o.iy = iy; o.iz = iz;
+            o.upm = (unsigned)f.upm; o.sn = 0u; o.u = (unsigned)u; o.pad = 0u;
+        }
+        q_push_warp(A, o, pk.ind >= 0);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(A.counters + 0, (unsigned long long)n);
+}
+
 // with_abu alone stays on the lean path (look-ahead kernel with the per-cell opacity array) unless a border reflects
 static bool sim_is_general(const SimArgs &A) {
     return (A.roi.flags & 2) || A.kind == SIM_ROI || A.with_msf || (A.with_abu && (A.mirror != 0 || A.kappa == nullptr)) || A.save_int2 ||
@@ -1566,25 +1740,25 @@ struct RngMwcItem : RngMwc {
 
 }  // namespace
 
-template <int DEP, bool BRICK, int CTAS, bool KAPPA>
+template <int DEP, bool BRICK, int CTAS, bool KAPPA, bool DOM>
 static void launch_ahead_dep(const SimArgs &A, int blocks, int threads, cudaStream_t stream) {
     static int per_sm = 0, sms = 0;                   // resident CTAs of this instantiation: the persistent grid is sms x per_sm
     if (per_sm == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sim_ahead_kernel<DEP, BRICK, CTAS, KAPPA>, threads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sim_ahead_kernel<DEP, BRICK, CTAS, KAPPA, DOM>, threads, 0);
         if (per_sm < 1) per_sm = 1;
     }
     if (blocks > sms * per_sm) blocks = sms * per_sm;
-    sim_ahead_kernel<DEP, BRICK, CTAS, KAPPA><<<blocks, threads, 0, stream>>>(A);
+    sim_ahead_kernel<DEP, BRICK, CTAS, KAPPA, DOM><<<blocks, threads, 0, stream>>>(A);
 }
 
-template <bool BRICK, int CTAS, bool KAPPA>
+template <bool BRICK, int CTAS, bool KAPPA, bool DOM = false>
 static void launch_ahead(const SimArgs &A, int dep, int blocks, int threads, cudaStream_t stream) {
-    if (dep == DEP_RED)       launch_ahead_dep<DEP_RED, BRICK, CTAS, KAPPA>(A, blocks, threads, stream);
-    else if (dep == DEP_WARP) launch_ahead_dep<DEP_WARP, BRICK, CTAS, KAPPA>(A, blocks, threads, stream);
-    else                      launch_ahead_dep<DEP_TILE, BRICK, CTAS, KAPPA>(A, blocks, threads, stream);
+    if (dep == DEP_RED)       launch_ahead_dep<DEP_RED, BRICK, CTAS, KAPPA, DOM>(A, blocks, threads, stream);
+    else if (dep == DEP_WARP) launch_ahead_dep<DEP_WARP, BRICK, CTAS, KAPPA, DOM>(A, blocks, threads, stream);
+    else                      launch_ahead_dep<DEP_TILE, BRICK, CTAS, KAPPA, DOM>(A, blocks, threads, stream);
 }
 
 template <bool BRICK, bool PEND>
@@ -1610,9 +1784,9 @@ static void launch_lean(SimArgs A, int dep, int blocks, int threads, cudaStream_
         else              launch_ahead<BRICK, 3, false>(A, dep, blocks, threads, stream);
         return;
     }
-    if (dep == DEP_RED)       sim_lean_kernel<DEP_RED, BRICK, PEND><<<blocks, threads, 0, stream>>>(A);
-    else if (dep == DEP_WARP) sim_lean_kernel<DEP_WARP, BRICK, PEND><<<blocks, threads, 0, stream>>>(A);
-    else                      sim_lean_kernel<DEP_TILE, BRICK, PEND><<<blocks, threads, 0, stream>>>(A);
+    if (dep == DEP_RED)       sim_lean_kernel<DEP_RED, BRICK, PEND, false><<<blocks, threads, 0, stream>>>(A);
+    else if (dep == DEP_WARP) sim_lean_kernel<DEP_WARP, BRICK, PEND, false><<<blocks, threads, 0, stream>>>(A);
+    else                      sim_lean_kernel<DEP_TILE, BRICK, PEND, false><<<blocks, threads, 0, stream>>>(A);
 }
 
 
@@ -1634,25 +1808,129 @@ static void launch_fast(const SimArgs &A, int blocks, int threads, cudaStream_t 
     }
 }
 
+// ---- domain mode ------------------------------------------------------------------------------------------------------
+// Eligible: the launches the bricked lean / look-ahead kernels serve, without reflecting borders (a domain face that is a
+// face of the grid ends the packet).  Whether it pays (DENS + accumulator beyond the L2) is decided by the caller.
+bool sim_domains_eligible(const SimArgs &A, int rng_mode) {
+    return sim_uses_bricks(A, rng_mode) && A.brick && A.mirror == 0 && !A.pend;
+}
+
+// ---- counting sort of a domain queue by (16^3-cell block of the entry cell, direction octant): neighbouring lanes then
+// work on packets that cross the same cells, which is what keeps the L1 / L2 sector traffic per step down (the order in
+// which packets are parked is random).  32768 keys; histogram, scan and scatter are three small kernels.
+#define Q_SORT_KEYS 32768
+__device__ __forceinline__ unsigned q_sort_key(const QPk &v, int lox, int loy, int loz) {
+    const unsigned kx = (unsigned)(v.ix - lox) >> 4, ky = (unsigned)(v.iy - loy) >> 4, kz = (unsigned)(v.iz - loz) >> 4;
+    return ((((kz & 15u) * 16u + (ky & 15u)) * 16u + (kx & 15u)) << 3) | (v.upm & 7u);
+}
+__global__ void __launch_bounds__(256) q_hist_kernel(const QPk *__restrict__ q, long long n, unsigned *__restrict__ hist, int lox, int loy, int loz) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        QPk v;
+        reinterpret_cast<float4 *>(&v)[2] = reinterpret_cast<const float4 *>(q + i)[2];      // tau, ix, iy, iz
+        reinterpret_cast<float4 *>(&v)[3] = reinterpret_cast<const float4 *>(q + i)[3];      // upm, ...
+        atomicAdd(hist + q_sort_key(v, lox, loy, loz), 1u);
+    }
+}
+// exclusive scan of hist[Q_SORT_KEYS] in place (one block of 1024 threads, 32 keys each)
+__global__ void __launch_bounds__(1024) q_scan_kernel(unsigned *__restrict__ hist) {
+    __shared__ unsigned part[1024];
+    const int t = threadIdx.x;
+    unsigned loc[32], sum = 0;
+    #pragma unroll
+    for (int k = 0; k < 32; k++) { loc[k] = hist[t * 32 + k]; sum += loc[k]; }
+    part[t] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        unsigned v = (t >= off) ? part[t - off] : 0u;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    unsigned run = part[t] - sum;
+    #pragma unroll
+    for (int k = 0; k < 32; k++) { hist[t * 32 + k] = run; run += loc[k]; }
+}
+__global__ void __launch_bounds__(256) q_scatter_kernel(const QPk *__restrict__ q, long long n, unsigned *__restrict__ cursor, QPk *__restrict__ out,
+                                                        int lox, int loy, int loz) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const QPk v = q_load(q + i);
+        const unsigned slot = atomicAdd(cursor + q_sort_key(v, lox, loy, loz), 1u);
+        q_store(out + slot, v);
+    }
+}
+void launch_queue_sort(const QPk *q, long long n, QPk *out, unsigned *hist, const int lo[3], cudaStream_t stream) {
+    long long b = (n + 255) / 256;
+    const int blocks = (int)(b < 1 ? 1 : (b > 148 * 8 ? 148 * 8 : b));
+    cudaMemsetAsync(hist, 0, Q_SORT_KEYS * sizeof(unsigned), stream);
+    q_hist_kernel<<<blocks, 256, 0, stream>>>(q, n, hist, lo[0], lo[1], lo[2]);
+    q_scan_kernel<<<1, 1024, 0, stream>>>(hist);
+    q_scatter_kernel<<<blocks, 256, 0, stream>>>(q, n, hist, out, lo[0], lo[1], lo[2]);
+}
+
+// the last parked packets, resumed on the whole grid by the general kernel (q_in, A.dom set by the caller)
+void launch_sim_cleanup(const SimArgs &A, int blocks, int threads, cudaStream_t stream) {
+    sim_fast_kernel<DEP_RED, true><<<blocks, threads, 0, stream>>>(A);
+}
+
+void launch_sim_emit(const SimArgs &A, long long nunits, cudaStream_t stream) {
+    long long b = (nunits + 255) / 256;
+    const long long cap = 148LL * 16;
+    sim_emit_queue_kernel<true><<<(int)(b < 1 ? 1 : (b > cap ? cap : b)), 256, 0, stream>>>(A, nunits);
+}
+
+// Same choice of kernel as launch_lean(): per-cell opacities and plain adds on the look-ahead kernel, the shared-memory
+// tile / lane combining of point-source launches on the lean kernel (a domain is sized to live in the L2).
+void launch_sim_domain(const SimArgs &A, int blocks, int threads, cudaStream_t stream) {
+    const int dep = A.deposit;
+    // without the emission code the look-ahead kernel needs <= 64 registers: 4 CTAs per SM
+    static int ctas = 0;
+    if (ctas == 0) { const char *e = getenv("SOC_DOM_CTAS"); ctas = (e && atoi(e) == 3) ? 3 : 4; }                    // tuning knob
+    if (A.with_abu) {
+        if (ctas == 4) launch_ahead<true, 4, true, true>(A, dep, blocks, threads, stream);
+        else           launch_ahead<true, 3, true, true>(A, dep, blocks, threads, stream);
+    } else if (A.ahead && (dep == DEP_RED || A.ahead > 1)) {
+        if (ctas == 4) launch_ahead<true, 4, false, true>(A, dep, blocks, threads, stream);
+        else           launch_ahead<true, 3, false, true>(A, dep, blocks, threads, stream);
+    }
+    else if (dep == DEP_RED)  sim_lean_kernel<DEP_RED, true, false, true><<<blocks, threads, 0, stream>>>(A);
+    else if (dep == DEP_WARP) sim_lean_kernel<DEP_WARP, true, false, true><<<blocks, threads, 0, stream>>>(A);
+    else                      sim_lean_kernel<DEP_TILE, true, false, true><<<blocks, threads, 0, stream>>>(A);
+}
+
 bool sim_kappa_eligible(const SimArgs &A, int rng_mode) {
     return rng_mode != SOC_RNG_REFERENCE && A.G.levels == 1 && !A.ref_geometry && A.with_abu && !A.with_msf && A.mirror == 0 &&
            !(A.roi.flags & 2) && (A.kind == SIM_PS || A.kind == SIM_BG || A.kind == SIM_HP) && !A.save_int2 && !A.with_ali &&
            A.nlocal < (1LL << 32) && A.max_steps < (1 << 24) - 2;
 }
 
-// (kabs*n, ksca*n) per cell, in 2x2x2-brick order when the launch uses bricks: one thread per output cell
+// position i of the (domain-major) brick order -> index of the cell in the reference's x-fastest order
+struct LayoutDesc { int nx, ny, ds0, ds1, ds2, ns0, ns1; long long dcells; };
+__device__ __forceinline__ long long layout_source(const LayoutDesc &L, long long i) {
+    const long long d = i / L.dcells, r = i - d * L.dcells;
+    const long long b = r >> 3;
+    const int sub = (int)(r & 7);
+    const int hx = L.ds0 >> 1, hy = L.ds1 >> 1;
+    const int bx = (int)(b % hx), by = (int)((b / hx) % hy), bz = (int)(b / ((long long)hx * hy));
+    const int dx = (int)(d % L.ns0), dy = (int)((d / L.ns0) % L.ns1), dz = (int)(d / ((long long)L.ns0 * L.ns1));
+    const int ix = dx * L.ds0 + 2 * bx + (sub & 1), iy = dy * L.ds1 + 2 * by + ((sub >> 1) & 1), iz = dz * L.ds2 + 2 * bz + (sub >> 2);
+    return ((long long)iz * L.ny + iy) * L.nx + ix;
+}
+static LayoutDesc layout_of(const SimArgs &A) {
+    LayoutDesc L;
+    L.nx = A.G.nx; L.ny = A.G.ny;
+    L.ds0 = A.dsize[0]; L.ds1 = A.dsize[1]; L.ds2 = A.dsize[2]; L.ns0 = A.dsplit[0]; L.ns1 = A.dsplit[1];
+    L.dcells = (long long)L.ds0 * L.ds1 * L.ds2;
+    return L;
+}
+
+// (kabs*n, ksca*n) per cell, in brick order when the launch uses bricks: one thread per output cell
 __global__ void __launch_bounds__(256) kappa_kernel(const float *__restrict__ dens, const float2 *__restrict__ opt, float2 *__restrict__ out,
-                                                    int nx, int ny, long long n, int brick) {
-    const int hx = nx >> 1, hy = ny >> 1;
+                                                    const LayoutDesc L, long long n, int brick) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        long long src = i;
-        if (brick) {
-            const long long b = i >> 3;
-            const int sub = (int)(i & 7);
-            const int bx = (int)(b % hx), by = (int)((b / hx) % hy), bz = (int)(b / ((long long)hx * hy));
-            src = ((long long)(2 * bz + (sub >> 2)) * ny + (2 * by + ((sub >> 1) & 1))) * nx + 2 * bx + (sub & 1);
-        }
+        const long long src = brick ? layout_source(L, i) : i;
         const float d = dens[src];
         const float2 o = opt[src];
         out[i] = make_float2(o.x * d, o.y * d);
@@ -1694,16 +1972,12 @@ int sim_blocks_per_sm(int rng_mode, bool octree, bool dbl, int threads) {
 // bricked scratch accumulator -> TABS / INT in the reference's cell order.  One thread per x-pair of a brick: the
 // accumulator is read as float2 in its own order (coalesced), TABS / INT are updated 8 bytes at a time.
 __global__ void __launch_bounds__(256) fold_acc_brick_kernel(float *__restrict__ acc, float *__restrict__ tabs, float *__restrict__ inten,
-                                                             float scale, int nx, int ny, long long npairs) {
-    const int hx = nx >> 1, hy = ny >> 1;
+                                                             float scale, const LayoutDesc L, long long npairs) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += stride) {
         float2 a = reinterpret_cast<float2 *>(acc)[i];
         if (a.x != 0.0f || a.y != 0.0f) {
-            const long long b = i >> 2;
-            const int sub = (int)(i & 3);                         // (z parity, y parity)
-            const int bx = (int)(b % hx), by = (int)((b / hx) % hy), bz = (int)(b / ((long long)hx * hy));
-            const long long lin = ((long long)(2 * bz + (sub >> 1)) * ny + (2 * by + (sub & 1))) * nx + 2 * bx;
+            const long long lin = layout_source(L, 2 * i);          // the pair (sub, sub + 1) differs in x only
             float2 t = *reinterpret_cast<float2 *>(tabs + lin);
             t.x += a.x * scale; t.y += a.y * scale;
             *reinterpret_cast<float2 *>(tabs + lin) = t;
@@ -1717,15 +1991,9 @@ __global__ void __launch_bounds__(256) fold_acc_brick_kernel(float *__restrict__
     }
 }
 
-__global__ void __launch_bounds__(256) brick_permute_kernel(const float *__restrict__ dens, float *__restrict__ out, int nx, int ny, long long n) {
-    const int hx = nx >> 1, hy = ny >> 1;
+__global__ void __launch_bounds__(256) brick_permute_kernel(const float *__restrict__ dens, float *__restrict__ out, const LayoutDesc L, long long n) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const long long b = i >> 3;
-        const int sub = (int)(i & 7);
-        const int bx = (int)(b % hx), by = (int)((b / hx) % hy), bz = (int)(b / ((long long)hx * hy));
-        out[i] = dens[((long long)(2 * bz + (sub >> 2)) * ny + (2 * by + ((sub >> 1) & 1))) * nx + 2 * bx + (sub & 1)];
-    }
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = dens[layout_source(L, i)];
 }
 
 static int stream_grid(long long n) {
@@ -1734,20 +2002,20 @@ static int stream_grid(long long n) {
     return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
-void launch_brick_permute(const GridDesc &G, float *dens_brick, cudaStream_t stream) {
-    const long long n = G.nxyz;
-    brick_permute_kernel<<<stream_grid(n), 256, 0, stream>>>(G.dens, dens_brick, G.nx, G.ny, n);
+void launch_brick_permute(const SimArgs &A, float *dens_brick, cudaStream_t stream) {
+    const long long n = A.G.nxyz;
+    brick_permute_kernel<<<stream_grid(n), 256, 0, stream>>>(A.G.dens, dens_brick, layout_of(A), n);
 }
 
 void launch_kappa(const SimArgs &A, cudaStream_t stream) {
     const long long n = A.G.nxyz;
     kappa_kernel<<<stream_grid(n), 256, 0, stream>>>(A.G.dens, reinterpret_cast<const float2 *>(A.opt), const_cast<float2 *>(A.kappa),
-                                                     A.G.nx, A.G.ny, n, A.brick);
+                                                     layout_of(A), n, A.brick);
 }
 
 void launch_fold_acc(const SimArgs &A, cudaStream_t stream) {
     const long long n = A.G.cells;
     const float scale = A.tw * A.adhoc;
-    if (A.brick) fold_acc_brick_kernel<<<stream_grid(n >> 1), 256, 0, stream>>>(A.acc, A.tabs, A.use_int ? A.inten : nullptr, scale, A.G.nx, A.G.ny, n >> 1);
+    if (A.brick) fold_acc_brick_kernel<<<stream_grid(n >> 1), 256, 0, stream>>>(A.acc, A.tabs, A.use_int ? A.inten : nullptr, scale, layout_of(A), n >> 1);
     else         fold_acc_kernel<<<stream_grid(n >> 2), 256, 0, stream>>>(A.acc, A.tabs, A.use_int ? A.inten : nullptr, scale, n);
 }

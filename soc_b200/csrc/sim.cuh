@@ -14,8 +14,31 @@ enum DepositMode {
 #define SOC_TILE_N 16                    // shared-memory tile edge (cells); SOC_TILE_N^3 floats = 16 KiB
 #define SOC_TILE_CELLS (SOC_TILE_N * SOC_TILE_N * SOC_TILE_N)
 
+// Domain-tiled propagation (regular grids whose DENS + scratch accumulator exceed the L2): the packet kernels work on
+// one box of cells ("domain") at a time so that its arrays stay in the L2; a packet that leaves the domain through an
+// interior face is parked in the queue of the domain it enters -- its complete DDA state, so that the path continues
+// bit for bit -- and picked up when that domain is processed.
+struct __align__(16) QPk {
+    float tx, ty, tz, rdx;          // face distances, 1/|d|
+    float rdy, rdz, photons, free_path;
+    float tau; int ix, iy, iz;      // root-grid coordinates of the cell the packet is in
+    unsigned upm, sn, u, pad;       // direction signs, steps | scatterings << 24, work unit (Philox stream)
+};
+
 struct SimArgs {
     GridDesc G;
+    // domain mode
+    int dom;                            // 1 = this launch works on one domain and takes its packets from q_in
+    int dom_lo[3], dom_hi[3];           // cells of the domain (inclusive)
+    int dom_faces;                      // bit 2*axis + (towards +axis ? 1 : 0): that face of the domain is a face of the grid
+    int dsplit[3], dsize[3];            // layout of the bricked arrays: domains per axis, cells per domain along each axis (one domain = plain brick order)
+    int dom_base;                       // first position of this launch's domain in the bricked arrays
+    const QPk *__restrict__ q_in;       // packets of this launch (nlocal of them)
+    QPk *q_base; unsigned *q_tail;      // queues of all domains: q_base[d * q_cap + i], i < q_tail[d]
+    long long q_cap;
+    int q_nparts; long long q_part[65];  // clean-up pass: q_in is q_nparts queues back to back in unit space, queue d holds units q_part[d] .. q_part[d+1]
+    long long unit0;                    // emission pass: first work unit of the chunk
+    unsigned long long scramble;        // experiment: work unit u runs packet (u * scramble) % nlocal (0 = in order)
     // accumulators [cells]
     float *tabs, *xab, *inten, *intx, *inty, *intz;
     // per-launch scratch accumulator [cells]: the stream kernels add the unweighted absorbed energy here and
@@ -64,8 +87,13 @@ struct SimArgs {
 };
 
 void launch_sim(const SimArgs &A, int rng_mode, int blocks, int threads, cudaStream_t stream);
+bool sim_domains_eligible(const SimArgs &A, int rng_mode);       // can this launch run domain by domain (launch_sim_emit / launch_sim_domain)?
+void launch_sim_emit(const SimArgs &A, long long nunits, cudaStream_t stream);    // emits units [unit0, unit0 + nunits) into the domain queues
+void launch_sim_domain(const SimArgs &A, int blocks, int threads, cudaStream_t stream);   // propagates q_in[0 .. nlocal) inside the domain
+void launch_queue_sort(const QPk *q, long long n, QPk *out, unsigned *hist /* 32768 */, const int lo[3], cudaStream_t stream);   // counting sort by entry block and direction octant
+void launch_sim_cleanup(const SimArgs &A, int blocks, int threads, cudaStream_t stream);  // finishes q_in[0 .. nlocal) on the whole grid (general kernel, adds straight into TABS / INT)
 void launch_fold_acc(const SimArgs &A, cudaStream_t stream);     // TABS += acc*TW*ADHOC; INT += acc; acc = 0
-void launch_brick_permute(const GridDesc &G, float *dens_brick, cudaStream_t stream);   // DENS -> 2x2x2-brick order
+void launch_brick_permute(const SimArgs &A, float *dens_brick, cudaStream_t stream);   // DENS -> (domain-major) 2x2x2-brick order, A.dsplit / A.dsize
 bool sim_kappa_eligible(const SimArgs &A, int rng_mode);          // per-cell opacities can take the look-ahead kernel (needs A.kappa)
 void launch_kappa(const SimArgs &A, cudaStream_t stream);        // fills A.kappa from DENS and OPT (bricked when A.brick)
 bool sim_uses_bricks(const SimArgs &A, int rng_mode);            // does launch_sim() take the bricked kernel?

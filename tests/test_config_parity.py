@@ -114,10 +114,10 @@ def test_c2_absorptions_match_the_reference_kernels(source):
         rb.append(_blocks(g) / gpu_mult), sb.append(_shells(g) / gpu_mult)
     assert B.counters.reserved[0] == 0
     B.close()
-    chi2, dof, tot, tot_sigma = chi2_per_dof(rb, ra, min_rel=1e-4)
-    assert dof > 20000
+    chi2, dof, tot, tot_sigma = chi2_per_dof(rb, ra, min_rel=1e-6, var_ratio=1.0 / gpu_mult)
+    assert dof > (20000 if source == 1 else 5000)       # the point source sits in the dense core: most of its energy stays there
     assert chi2 <= 1.1, "blocks: chi2/dof = %.3f over %d blocks" % (chi2, dof)
-    chi2s, dofs, _, _ = chi2_per_dof(sb, sa)
+    chi2s, dofs, _, _ = chi2_per_dof(sb, sa, var_ratio=1.0 / gpu_mult)
     assert dofs > 100
     # Few shells (129): the mean of t^2 itself scatters by sqrt(2/dof) ~ 0.12
     assert chi2s <= 1.1 + 3.0 * np.sqrt(2.0 / dofs), "shells: chi2/dof = %.3f over %d shells" % (chi2s, dofs)
@@ -296,7 +296,7 @@ def test_c3_octree_absorptions_and_image_match_the_reference_kernels():
             out.append(np.bincount(block, weights=v, minlength=4096))
             lout.append(np.bincount(level, weights=v, minlength=cloud.LEVELS))
     assert B.counters.reserved[0] == 0
-    chi2, dof, tot, tot_sigma = chi2_per_dof(b, a, min_rel=1e-4)
+    chi2, dof, tot, tot_sigma = chi2_per_dof(b, a, min_rel=1e-4, var_ratio=1.0 / mult)
     assert dof > 3000
     assert chi2 <= 1.1, "octree blocks: chi2/dof = %.3f over %d" % (chi2, dof)
     assert tot <= max(4.0 * tot_sigma, 1e-4), "octree total energy differs by %.2e (sigma %.2e)" % (tot, tot_sigma)
@@ -323,7 +323,7 @@ def test_c3_octree_absorptions_and_image_match_the_reference_kernels():
         a.append(o.astype(np.float64).ravel())
         o = B.sca_ps(items, items * batch * mult, batch * mult, seed, *args, abs_=k, sca=k, dsc=dsc, csc=csc, pspos=pspos, ps=ps)
         b.append(o.astype(np.float64).ravel() / mult)
-    chi2, dof, tot, tot_sigma = chi2_per_dof(b, a, min_rel=0.01)
+    chi2, dof, tot, tot_sigma = chi2_per_dof(b, a, min_rel=0.01, var_ratio=1.0 / mult)
     print("C3 scattered light: chi2/dof %.3f (%d), total %.2e (sigma %.2e)" % (chi2, dof, tot, tot_sigma))
     assert dof > 200
     assert chi2 <= 1.1 + 3.0 * np.sqrt(2.0 / dof), "octree image: chi2/dof = %.3f over %d pixels" % (chi2, dof)

@@ -397,6 +397,66 @@ def test_neighbour_table_walker_equals_climb_walker(kind, monkeypatch):
     assert abs(a.sum() - b.sum()) <= 5e-4 * b.sum()
 
 
+@pytest.mark.parametrize("kind", ["bg", "ps", "bg_abu", "ps_corner"])
+def test_domain_tiled_propagation_equals_whole_grid(kind):
+    """soc_set_domains: the grid cut into boxes, packets parked with their complete stepping state when they cross an
+    interior face.  Same Philox streams, bit-identical paths: the counters agree exactly, TABS / INT up to the order of the
+    float additions.  Non-cubic grid, box edge 8 (3 x 2 x 2 boxes, the last ones smaller) so that a wrong bound shows."""
+    from soc_b200 import backend
+    from soc_b200.formats import Cloud
+    nx, ny, nz = 20, 12, 16
+    d = synth.plummer_density(24)[2:2 + nz, 6:6 + ny, 2:2 + nx]
+    cloud = Cloud(nx, ny, nz, [nx * ny * nz], np.ascontiguousarray(d, np.float32).ravel())
+    opts = dict(noabsorbed=0)
+    if kind == "bg":
+        run = run_bg(batch=6, seed=0.37, tau_s=6.0)
+    elif kind == "bg_abu":
+        run, opts = run_abu(batch=6, seed=0.41), dict(noabsorbed=0, with_abu=1)
+    elif kind == "ps":
+        run, opts = run_ps([(9.3, 5.2, 7.7)], batch=50, glob=4096, tau_s=6.0), dict(no_ps=1, noabsorbed=0)
+    else:       # the shared-memory tile around a source that sits on the corner of eight boxes
+        run, opts = run_ps([(8.01, 7.99, 8.02)], batch=50, glob=4096, tau_s=6.0), dict(no_ps=1, noabsorbed=0)
+    res, cnt = [], []
+    for edge in (-1, 8):
+        B = _backend(cloud, backend.RNG_PACKET, **opts)
+        B.dev.set_domains(edge)
+        out = run(B)
+        res.append((out["tabs"].astype(np.float64), out["int"].astype(np.float64)))
+        c = B.counters
+        cnt.append((c.packets, c.steps, c.scatterings, c.reserved[0]))
+        B.close()
+    assert cnt[0] == cnt[1] and cnt[0][1] > 0 and cnt[0][3] == 0, cnt
+    for a, b in zip(res[0], res[1]):
+        assert np.abs(a - b).max() <= 1e-4 * a.max()
+        assert abs(a.sum() - b.sum()) <= 3e-5 * a.sum()
+
+
+def test_domain_tiled_propagation_at_512():
+    """512^3 (BASELINE.json configs 4/5): the automatic domain mode (2 x 2 x 2 boxes of 256^3) against the whole-grid
+    look-ahead kernel, one background launch: same packets, same paths."""
+    from soc_b200 import backend
+    n = 512
+    cloud = synth.regular_cloud(n)
+    dsc, csc = synth.hg_tables(0.6)
+    glob = 8 * cloud.AREA
+    kabs, ksca = 3.0 / n, 5.0 / n
+    res = []
+    for edge in (-1, 0):
+        B = _backend(cloud, backend.RNG_PACKET)
+        B.dev.set_domains(edge)
+        B.zero(0)
+        B.sim_pb(glob, 1, glob, 1, 0.7, 1.0, 1.0, abs_=kabs, sca=ksca, dsc=dsc, csc=csc)
+        c = B.counters
+        res.append((B.tabs.astype(np.float64), c.packets, c.steps, c.scatterings, c.reserved[0]))
+        B.close()
+    a, b = res
+    # the last parked packets are finished by the general kernel (true division instead of rcp.approx at a scattering):
+    # a path may flip at a cell face by rounding
+    assert a[1] == b[1] and abs(a[2] - b[2]) <= 1e-6 * a[2] and abs(a[3] - b[3]) <= 1e-5 * a[3] and a[4] == 0 and b[4] == 0, (a[1:], b[1:])
+    assert abs(a[0].sum() - b[0].sum()) <= 2e-6 * a[0].sum()
+    assert (np.abs(a[0] - b[0]) > 1e-4 * a[0].max()).mean() < 1e-5
+
+
 def test_invariants_at_full_size():
     """Size-independent properties at the 256^3 bench size (the oracle would need minutes here):
     no absorption opacity => TABS == 0; the absorbed energy is bounded by the injected energy and grows with
