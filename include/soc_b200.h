@@ -32,7 +32,7 @@
  *   soc_set_shard, soc_device_ptr           packet sharding over ranks and the device addresses a
  *                                           host-side NCCL all-reduce needs
  *   soc_set_rng_mode, soc_set_tuning, soc_set_geometry, soc_set_layout, soc_set_domains,
- *   soc_get_counters, soc_last_launch_ms,
+ *   soc_get_counters, soc_last_launch_ms, soc_last_kernel,
  *   soc_stream                              stream layout, accumulation engine, work counters, device timing
  */
 #ifndef SOC_B200_H
@@ -228,6 +228,7 @@ int  soc_sca_cl(soc_context *ctx, int source, int packets, int batch, float seed
 int  soc_get_counters(soc_context *ctx, soc_counters *out);
 int  soc_reset_counters(soc_context *ctx);
 int  soc_last_launch_ms(soc_context *ctx, float *ms);     /* device time of the most recent kernel launch */
+const char *soc_last_kernel(soc_context *ctx);            /* name (with its template arguments) of the packet kernel the most recent soc_sim_* call dispatched */
 void *soc_stream(soc_context *ctx);                       /* the context's cudaStream_t (for NCCL / event timing) */
 
 #ifdef __cplusplus

@@ -95,7 +95,17 @@ def tag_of(cfg):
     for k in opt:
         if k in cfg:
             s += "_%s%s" % (re.sub("[^A-Z]", "", k)[:3] + k[-1], cfg[k])
+    if cfg.get("TUNED"):
+        s += "_tuned"
     return re.sub(r"[^A-Za-z0-9_.]", "", s)
+
+
+# Compiler settings.  The default build is conservative (-O2, no contraction: the operation order of the reference
+# text, used for the bit-level comparisons of the tests).  TUNED=1 is what a CPU OpenCL driver would make of the
+# reference's `-cl-mad-enable` build line (ASOC.py:385): -O3, FMA contraction, AVX2-class vectors (x86-64-v3: the
+# library is built in the container and runs on the GPU box's host, so no -march=native).  Never -ffast-math: the
+# hierarchy links are denormal floats.
+OPT_FLAGS = {False: ["-O2", "-ffp-contract=off"], True: ["-O3", "-march=x86-64-v3", "-ffp-contract=fast"]}
 
 
 def lib_path(cfg):
@@ -121,8 +131,8 @@ def build(cfg, force=False, verbose=False):
         flags = macro_flags(cfg)
         # -ftrivial-auto-var-init=zero: the scattered-light SimRAM_CL indexes DSC with an uninitialised `idust` when
         # WITH_MSF==0 (kernel_ASOC_sca.c:1140 vs :83 where SimRAM_HP initialises it); zero is what the single-dust run means
-        common = ["g++", "-std=c++17", "-fpermissive", "-w", "-O2", "-fopenmp", "-fPIC", "-ffp-contract=off",
-                  "-ftrivial-auto-var-init=zero", "-I", tmp, "-I", SHIM]
+        common = ["g++", "-std=c++17", "-fpermissive", "-w", "-fopenmp", "-fPIC"] + OPT_FLAGS[bool(cfg.get("TUNED"))] + \
+                 ["-ftrivial-auto-var-init=zero", "-I", tmp, "-I", SHIM]
         objs = []
         for tu, extra in (("ref_sim.cpp", ["-DNSIDE=128"]),
                           ("ref_map.cpp", ["-DNSIDE=%d" % cfg.get("MAP_NSIDE", cfg["NX"])]),

@@ -68,6 +68,11 @@ class Reference:
     def set_chunk(self, n):
         self.L.ref_set_chunk(C.c_int(n))
 
+    def set_sampling(self, stride=1, offset=0, gsize=0):
+        """Loop index i of the following launches runs work item offset + i*stride of a launch of `gsize` work items
+        (bench.py's bounded samples: a stride covers the whole launch instead of its first work items)."""
+        self.L.ref_set_sampling(C.c_long(stride), C.c_long(offset), C.c_long(gsize))
+
     def atomic_count(self, reset=True):
         return int(self.L.ref_atomic_count(C.c_int(1 if reset else 0)))
 

@@ -9,12 +9,17 @@
 // "cell-step" unit of SURVEY.md section 8(d).
 extern thread_local unsigned long clshim_atomic_ok;
 
+// Sampling of the work items (bench.py's bounded CPU samples): loop index i runs work item ref_offset + i * ref_stride
+// of a launch of ref_gsize work items (0 = the loop count).  Defaults 1 / 0 / 0 = the plain launch.
+extern long ref_stride, ref_offset, ref_gsize;
+
 #define REF_PARALLEL_FOR(GLOBAL, BODY)                                          \
     do {                                                                        \
         const long _g = (long)(GLOBAL);                                         \
+        const long _gs = ref_gsize > 0 ? ref_gsize : _g;                        \
         _Pragma("omp parallel for schedule(runtime)")                       \
-        for (long _id = 0; _id < _g; ++_id) {                                   \
-            clshim_gid = (size_t)_id; clshim_gsize = (size_t)_g;                \
+        for (long _i = 0; _i < _g; ++_i) {                                      \
+            clshim_gid = (size_t)(ref_offset + _i * ref_stride); clshim_gsize = (size_t)_gs; \
             BODY;                                                               \
         }                                                                       \
     } while (0)

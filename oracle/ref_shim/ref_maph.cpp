@@ -4,6 +4,7 @@
 #include "ref_common.h"
 
 thread_local size_t clshim_gid = 0, clshim_gsize = 1;
+long ref_stride = 1, ref_offset = 0, ref_gsize = 0;
 thread_local unsigned long clshim_atomic_ok = 0;
 
 namespace refh {

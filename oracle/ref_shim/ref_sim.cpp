@@ -7,6 +7,7 @@
 thread_local size_t clshim_gid = 0, clshim_gsize = 1;
 thread_local unsigned long clshim_atomic_ok = 0;
 static unsigned long g_atomic_total = 0;
+long ref_stride = 1, ref_offset = 0, ref_gsize = 0;
 
 // override the shim's CAS so that successful updates are counted
 static inline unsigned int counted_cmpxchg(volatile unsigned int *p, unsigned int cmp, unsigned int val) {
@@ -35,6 +36,7 @@ void ref_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 // work items handed to a host thread at a time (OpenMP dynamic schedule); 256 unless changed
 void ref_set_chunk(int n) { omp_set_schedule(omp_sched_dynamic, n > 0 ? n : 256); }
 static struct RefInitSchedule { RefInitSchedule() { omp_set_schedule(omp_sched_dynamic, 256); } } ref_init_schedule;
+void ref_set_sampling(long stride, long offset, long gsize) { ref_stride = stride > 0 ? stride : 1; ref_offset = offset; ref_gsize = gsize; }
 unsigned long ref_atomic_count(int reset) { flush_counter(); unsigned long v = g_atomic_total; if (reset) g_atomic_total = 0; return v; }
 
 // MWC64X known-answer helper: first n outputs of the stream of work item `id`

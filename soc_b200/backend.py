@@ -44,7 +44,7 @@ class SocCounters(C.Structure):
 _EXPORTS = """soc_last_error soc_version soc_create soc_destroy soc_sync soc_set_params soc_set_grid soc_set_rng_mode
 soc_set_shard soc_set_tuning soc_set_geometry soc_set_layout soc_set_domains soc_set_roi soc_upload soc_download soc_clear soc_device_ptr soc_zero_amc soc_sim_pb soc_sim_hp
 soc_sim_cl soc_absorbed_begin soc_absorbed_add soc_absorbed_finish soc_eq_temperature soc_emission soc_emission2 soc_mapping soc_mapping_levels soc_healpix_mapping soc_ps_tau soc_sca_zero_out soc_sca_ps soc_sca_pb soc_sca_hp soc_sca_cl
-soc_get_counters soc_reset_counters soc_last_launch_ms soc_stream""".split()
+soc_get_counters soc_reset_counters soc_last_launch_ms soc_last_kernel soc_stream""".split()
 
 _lib = None
 
@@ -102,6 +102,8 @@ def load_library(path=None):
     L.soc_get_counters.argtypes = [vp, C.POINTER(SocCounters)]
     L.soc_reset_counters.argtypes = [vp]
     L.soc_last_launch_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.soc_last_kernel.argtypes = [vp]
+    L.soc_last_kernel.restype = C.c_char_p
     if path is None:
         _lib = L
     return L
@@ -300,6 +302,9 @@ class Device:
 
     def reset_counters(self):
         self._ck(self.L.soc_reset_counters(self.ctx))
+
+    def last_kernel(self):
+        return (self.L.soc_last_kernel(self.ctx) or b"").decode()
 
     def last_launch_ms(self):
         ms = C.c_float()

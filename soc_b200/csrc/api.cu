@@ -1118,6 +1118,8 @@ int soc_reset_counters(soc_context *c) {
     return SOC_OK;
 }
 
+const char *soc_last_kernel(soc_context *c) { (void)c; return sim_last_kernel(); }
+
 int soc_last_launch_ms(soc_context *c, float *ms) {
     NEED_CTX(c);
     if (ms == nullptr) return fail(SOC_ERR_ARG, "soc_last_launch_ms: null");

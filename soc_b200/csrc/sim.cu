@@ -15,6 +15,8 @@
 //
 // Per cell-step the kernels touch DENS[cell] (4 B gather, carried in a register from the step that entered
 // the cell) and TABS[cell] (+INT[cell]) through red.global.add.f32; nothing else leaves the SM.
+#include <cstdio>
+#include <cstdlib>
 #include "sim.cuh"
 #include "emit.cuh"
 #include "walk.cuh"
@@ -1740,6 +1742,15 @@ struct RngMwcItem : RngMwc {
 
 }  // namespace
 
+// name of the packet kernel the last launch_sim / launch_sim_domain dispatched (soc_last_kernel)
+static thread_local char g_kernel_name[96] = "";
+static void note_kernel(const char *base, int dep, int brick, int extra, const char *extra_name, int dom) {
+    static const char *deps[3] = { "DEP_RED", "DEP_WARP", "DEP_TILE" };
+    snprintf(g_kernel_name, sizeof(g_kernel_name), "%s<%s,%s,%s=%d%s>", base, deps[dep < 0 || dep > 2 ? 0 : dep], brick ? "brick" : "linear",
+             extra_name, extra, dom ? ",domains" : "");
+}
+const char *sim_last_kernel() { return g_kernel_name; }
+
 template <int DEP, bool BRICK, int CTAS, bool KAPPA, bool DOM>
 static void launch_ahead_dep(const SimArgs &A, int blocks, int threads, cudaStream_t stream) {
     static int per_sm = 0, sms = 0;                   // resident CTAs of this instantiation: the persistent grid is sms x per_sm
@@ -1752,6 +1763,7 @@ static void launch_ahead_dep(const SimArgs &A, int blocks, int threads, cudaStre
     }
     if (blocks > sms * per_sm) blocks = sms * per_sm;
     sim_ahead_kernel<DEP, BRICK, CTAS, KAPPA, DOM><<<blocks, threads, 0, stream>>>(A);
+    note_kernel("sim_ahead_kernel", DEP, BRICK, KAPPA, "kappa", DOM);
 }
 
 template <bool BRICK, int CTAS, bool KAPPA, bool DOM = false>
@@ -1787,6 +1799,7 @@ static void launch_lean(SimArgs A, int dep, int blocks, int threads, cudaStream_
     if (dep == DEP_RED)       sim_lean_kernel<DEP_RED, BRICK, PEND, false><<<blocks, threads, 0, stream>>>(A);
     else if (dep == DEP_WARP) sim_lean_kernel<DEP_WARP, BRICK, PEND, false><<<blocks, threads, 0, stream>>>(A);
     else                      sim_lean_kernel<DEP_TILE, BRICK, PEND, false><<<blocks, threads, 0, stream>>>(A);
+    note_kernel("sim_lean_kernel", dep, BRICK, PEND, "pend", 0);
 }
 
 
@@ -1796,6 +1809,7 @@ static bool sim_uses_lean(const SimArgs &A) { return !sim_is_general(A) && A.nlo
 static void launch_fast(const SimArgs &A, int blocks, int threads, cudaStream_t stream) {
     const int dep = (A.save_int2 || A.with_ali) ? DEP_RED : A.deposit;
     if (!sim_uses_lean(A)) {
+        note_kernel("sim_fast_kernel", dep, 0, 1, "general", 0);
         if (dep == DEP_RED)       sim_fast_kernel<DEP_RED, true><<<blocks, threads, 0, stream>>>(A);
         else if (dep == DEP_WARP) sim_fast_kernel<DEP_WARP, true><<<blocks, threads, 0, stream>>>(A);
         else                      sim_fast_kernel<DEP_TILE, true><<<blocks, threads, 0, stream>>>(A);
@@ -1894,9 +1908,12 @@ void launch_sim_domain(const SimArgs &A, int blocks, int threads, cudaStream_t s
         if (ctas == 4) launch_ahead<true, 4, false, true>(A, dep, blocks, threads, stream);
         else           launch_ahead<true, 3, false, true>(A, dep, blocks, threads, stream);
     }
-    else if (dep == DEP_RED)  sim_lean_kernel<DEP_RED, true, false, true><<<blocks, threads, 0, stream>>>(A);
-    else if (dep == DEP_WARP) sim_lean_kernel<DEP_WARP, true, false, true><<<blocks, threads, 0, stream>>>(A);
-    else                      sim_lean_kernel<DEP_TILE, true, false, true><<<blocks, threads, 0, stream>>>(A);
+    else {
+        if (dep == DEP_RED)       sim_lean_kernel<DEP_RED, true, false, true><<<blocks, threads, 0, stream>>>(A);
+        else if (dep == DEP_WARP) sim_lean_kernel<DEP_WARP, true, false, true><<<blocks, threads, 0, stream>>>(A);
+        else                      sim_lean_kernel<DEP_TILE, true, false, true><<<blocks, threads, 0, stream>>>(A);
+        note_kernel("sim_lean_kernel", dep, 1, 0, "pend", 1);
+    }
 }
 
 bool sim_kappa_eligible(const SimArgs &A, int rng_mode) {
@@ -1943,6 +1960,9 @@ bool sim_uses_bricks(const SimArgs &A, int rng_mode) {
 
 void launch_sim(const SimArgs &A, int rng_mode, int blocks, int threads, cudaStream_t stream) {
     const bool oct = A.G.levels > 1, dbl = A.G.dbl_sim != 0;
+    if (rng_mode == SOC_RNG_REFERENCE) snprintf(g_kernel_name, sizeof(g_kernel_name), "sim_item_kernel<MWC64X,%s,%s>", oct ? "octree" : "regular", dbl ? "f64" : "f32");
+    else if (oct && !A.ref_geometry) snprintf(g_kernel_name, sizeof(g_kernel_name), "%s<%s>", A.nbr != nullptr ? "sim_link_kernel" : "sim_walk_kernel", sim_is_general(A) ? "general" : "lean");
+    else if (A.ref_geometry) snprintf(g_kernel_name, sizeof(g_kernel_name), "sim_stream_kernel<%s,%s>", oct ? "octree" : "regular", dbl ? "f64" : "f32");
     if (rng_mode == SOC_RNG_REFERENCE) {
         if (!oct)      sim_item_kernel<RngMwcItem, false, false><<<blocks, threads, 0, stream>>>(A);
         else if (!dbl) sim_item_kernel<RngMwcItem, true, false><<<blocks, threads, 0, stream>>>(A);

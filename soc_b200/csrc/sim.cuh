@@ -97,4 +97,5 @@ void launch_brick_permute(const SimArgs &A, float *dens_brick, cudaStream_t stre
 bool sim_kappa_eligible(const SimArgs &A, int rng_mode);          // per-cell opacities can take the look-ahead kernel (needs A.kappa)
 void launch_kappa(const SimArgs &A, cudaStream_t stream);        // fills A.kappa from DENS and OPT (bricked when A.brick)
 bool sim_uses_bricks(const SimArgs &A, int rng_mode);            // does launch_sim() take the bricked kernel?
+const char *sim_last_kernel();       // name of the packet kernel dispatched last by this thread
 int  sim_blocks_per_sm(int rng_mode, bool octree, bool dbl, int threads);
