@@ -56,7 +56,8 @@ enum soc_status {
 
 /* The compile-time options of the reference kernels (ASOC.py:344-362) as run-time values.
  * Options that cannot work in the reference as shipped (DIR_WEIGHT, PS_METHOD 3) or that are out of
- * scope (ROI, DO_SPLIT, POLSTAT) are rejected with SOC_ERR_UNSUPPORTED. */
+ * scope (DO_SPLIT, POLSTAT) are rejected with SOC_ERR_UNSUPPORTED.  The region of interest (roi_flags: ROI_LOAD,
+ * ROI_SAVE, ROI_MAP) is implemented; its limits and buffers are set with soc_set_roi(). */
 typedef struct soc_params {
     int32_t bins;              /* BINS: length of the DSC / CSC tables                        */
     int32_t no_ps;             /* NO_PS (>=1)                                                 */

@@ -10,6 +10,7 @@ SimRAM_HP), a diffuse field from a file and the emission of the dust itself read
 (`perspective x y z` + `outnside`, ASOCS.py:44-47).  `roiload` + `roipac` add the stored external field (II == 3).
 Weights follow ASOCS.py:437-475 (WPS, WBG), the final scaling ASOCS.py:874-884.
 """
+import os
 import sys
 import time
 
@@ -119,7 +120,7 @@ def main(argv=None, device_factory=None):
             sys.exit()
         EMITTED = np.memmap(USER.file_emitted, dtype='float32', mode='r', shape=(CELLS, int(hdr[1])), offset=8)
 
-    ordinal = comm.local if comm.world > 1 else 0
+    ordinal = comm.local if comm.world > 1 else int(os.environ.get("SOC_DEVICE", "0"))
     dev = (device_factory or bk.Device)(ordinal)
     dev.set_params(bins=USER.DSC_BINS, no_ps=max(1, USER.NO_PS), ps_method=USER.PS_METHOD, with_abu=int(WITH_ABU),
                    ffs=USER.FFS, hpbg_weighted=int(USER.HPBG_WEIGHTED), use_emweight=USER.USE_EMWEIGHT,

@@ -221,7 +221,8 @@ int soc_set_grid(soc_context *c, int32_t nx, int32_t ny, int32_t nz, int32_t lev
     if (levels > 1) { launch_parents(G, dptr<int>(c, SOC_BUF_PAR), c->stream); c->launches += levels - 1; }
     if (c->nbr) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->nbr)); c->nbr = nullptr; }
     if (levels > 1 && c->use_nbr && cells < (1LL << 27)) {
-        // neighbour table of the production octree kernel: 24 B per cell, built once per grid
+        // neighbour table of the production octree kernel: 48 B per cell (six {cell, density} pairs), built once per grid;
+        // 2^27 cells = 6 GiB of table
         if (cudaMalloc(&c->nbr, (size_t)cells * 48) == cudaSuccess) { launch_neighbours(G, c->nbr, c->stream); c->launches++; }
         else { c->nbr = nullptr; cudaGetLastError(); }
     }

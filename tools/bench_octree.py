@@ -48,7 +48,7 @@ def main():
     c = dev.counters()
     t = np.mean(ms[1:]) * 1e-3
     line = {"workload": "octree %d^3 + %d levels, %d cells, isotropic background, TABS+INT" % (args.root, args.levels - 1, cloud.CELLS),
-            "kernel": "sim_walk_kernel", "packets_per_s": c.packets / 2 / t, "cell_steps_per_s": c.steps / 2 / t,
+            "kernel": dev.last_kernel(), "packets_per_s": c.packets / 2 / t, "cell_steps_per_s": c.steps / 2 / t,
             "steps_per_packet": c.steps / max(1, c.packets), "ms": t * 1e3, "stuck": int(c.reserved[0])}
     B.close()
     from oracle import orc
@@ -96,7 +96,7 @@ def main():
         c = dev.counters()
         t = np.mean(ms[1:]) * 1e-3
         line = {"workload": "scattered light (%s), same octree, 2 observers, %dx%d px" % (name, args.npix, args.npix),
-                "kernel": "sca_walk_kernel<octree>", "packets_per_s": c.packets / 2 / t, "cell_steps_per_s": c.steps / 2 / t,
+                "kernel": "sca_link_kernel", "packets_per_s": c.packets / 2 / t, "cell_steps_per_s": c.steps / 2 / t,
                 "peel_rays_per_s": c.peels / 2 / t, "steps_per_packet": c.steps / max(1, c.packets), "ms": t * 1e3,
                 "stuck": int(c.reserved[0])}
         O = orc.Oracle(cloud, no_ps=1, ffs=1)
