@@ -18,6 +18,7 @@
  *   soc_zero_amc                            kernel ZeroAMC (kernel_ASOC_aux.c:657; ASOC.py:1115, 1183)
  *   soc_sim_pb / soc_sim_hp / soc_sim_cl    kernels SimRAM_PB / SimRAM_HP / SimRAM_CL
  *                                           (kernel_ASOC.c:15, 831, 1223; ASOC.py:1317-1419, 1847)
+ *   soc_build_opt                           host loop OPT = sum_d ABU*K_d + upload (ASOC.py:1146-1175)
  *   soc_absorbed_begin / _add / _finish     FABSORBED[:,f] += TMP and the final scaling loop
  *                                           (ASOC.py:1482-1497, 2782-2878), kept on the device
  *   soc_eq_temperature / soc_emission       kernels EqTemperature / Emission / Emission2
@@ -161,6 +162,13 @@ int  soc_set_layout(soc_context *ctx, int mode);
  * automatic, boxes of <= 256 cells per axis when DENS + the scratch accumulator exceed the L2 (more than 2^25 cells);
  * edge < 0: off; edge > 0 (even): forced with that box size.  Launches in this mode return when the packets are done. */
 int  soc_set_domains(soc_context *ctx, int edge);
+
+/* OPT[CELLS,2] = per-cell (KABS, KSCA) built on the device from the abundances in buffer ABU ([CELLS, ndust] floats,
+ * uploaded once) and the per-species cross sections of one frequency: replaces the host loop of ASOC.py:1146-1161 and
+ * its 8*CELLS-byte upload per frequency.  Species `first` .. ndust-1 are summed (the reference starts from species 1 in
+ * its cell-emission loop, ASOC.py:1673); single_abu: OPT = a*K[0] + (1-a)*K[1] with one abundance per cell.  Same
+ * float32 operation order as the host code; with OPT_IS_HALF the values are rounded to half precision. */
+int  soc_build_opt(soc_context *ctx, int ndust, const float *kabs, const float *ksca, int first, int single_abu);
 
 int  soc_upload(soc_context *ctx, int buffer, const void *host, size_t nbytes);
 int  soc_download(soc_context *ctx, int buffer, void *host, size_t nbytes);

@@ -398,7 +398,7 @@ def main(argv=None, device_factory=None):
             ROI_SAVE[:, :] = 0.0
     if USER.WITH_ROI_LOAD or USER.WITH_ROI_SAVE or USER.ROI_MAP:
         dev.set_roi(USER.ROI, USER.ROI_STEP, USER.ROI_NSIDE, roi_dim)
-    if WITH_MSF:
+    if WITH_ABU:          # once: OPT of every frequency is built from it on the device (soc_build_opt)
         dev.upload(bk.BUF_ABU, np.ascontiguousarray(ABU, np.float32).reshape(-1))
     dev.set_rng_mode(bk.RNG_REFERENCE if 'REFSTREAMS' in USER.KEYS else bk.RNG_PACKET)
     dev.set_geometry(1 if 'REFGEOMETRY' in USER.KEYS else 0)
@@ -499,8 +499,11 @@ def main(argv=None, device_factory=None):
     def set_opacity(ifreq, first=0):
         """Scalar ABS/SCA, or OPT upload for variable abundances.  Returns (abs, sca)."""
         if WITH_ABU:
-            o = _opt_array(USER, ABU, AFABS, AFSCA, ifreq, first).reshape(-1)
-            dev.upload(bk.BUF_OPT, o, np.float16 if USER.OPT_IS_HALF else np.float32)      # ASOC.py:1155-1158
+            if 'HOSTOPT' in USER.KEYS:          # the reference's way: numpy loop over the species + 8*CELLS bytes over PCIe
+                o = _opt_array(USER, ABU, AFABS, AFSCA, ifreq, first).reshape(-1)
+                dev.upload(bk.BUF_OPT, o, np.float16 if USER.OPT_IS_HALF else np.float32)      # ASOC.py:1155-1158
+            else:
+                dev.build_opt([a[ifreq] for a in AFABS], [s[ifreq] for s in AFSCA], first, bool(USER.SINGLE_ABU))
             return 0.0, 0.0
         return float(sum(a[ifreq] for a in AFABS)), float(sum(s[ifreq] for s in AFSCA))
 
@@ -543,6 +546,17 @@ def main(argv=None, device_factory=None):
     # =============================================================================================================
     # constant sources: point sources, background, diffuse emission (ASOC.py:1004-1549)
     # =============================================================================================================
+    # Several ranks: the packets of every launch are dealt out over the ranks (packet q on rank q % world), or -- for the
+    # constant sources, whose frequencies are independent -- rank r takes frequencies r, r + world, ... whole:
+    # no per-frequency collective at all, one all-reduce of TABS per source and of the [CELLS, NFREQ] absorptions at the end.
+    # Frequency sharding needs every per-frequency product to stay on the device of the rank that made it.
+    n_sim = int(np.sum((FFREQ >= USER.SIM_F[0]) & (FFREQ <= USER.SIM_F[1])))
+    freq_shard = (comm.world > 1 and n_sim >= comm.world and USER.SAVE_INTENSITY == 0 and not USER.WITH_ROI_SAVE
+                  and (USER.NOABSORBED or fabs_on_device) and USER.USE_EMWEIGHT == 0 and 'PACKETSHARD' not in USER.KEYS)
+    if 'FREQSHARD' in USER.KEYS and comm.world > 1 and not freq_shard:
+        print("*** FREQSHARD: not possible with these options (saveint, roisave, emweight, HOSTABSORBED or fewer frequencies than ranks)")
+    if VERBOSE and comm.world > 1:
+        print("%d ranks: %s" % (comm.world, "constant sources sharded by frequency" if freq_shard else "packets of every launch sharded"))
     CTABS = np.zeros(CELLS, np.float32)
     if len(USER.file_constant_load) > 0:
         CTABS = np.fromfile(USER.file_constant_load, np.float32, CELLS)
@@ -598,10 +612,18 @@ def main(argv=None, device_factory=None):
                 if VERBOSE:
                     print("=== ROI: GLOBAL %d, BATCH %d, ROI_LOAD_NELEM %d" % (GLOBAL, BATCH, ROI_LOAD_NELEM))
             dev.zero_amc(0)
+            if freq_shard:
+                dev.set_shard(0, 1)                 # this rank runs all packets of its frequencies
+            i_sim = -1
             for IFREQ in range(NFREQ):
                 T000 = time.time()
                 FREQ = FFREQ[IFREQ]
                 if FREQ < USER.SIM_F[0] or FREQ > USER.SIM_F[1]:
+                    continue
+                i_sim += 1
+                if freq_shard and i_sim % comm.world != comm.rank:
+                    if USER.SEED <= 0:
+                        host_rng.random()           # keep the seed sequence of the frequencies independent of the number of ranks
                     continue
                 t0 = time.time()
                 kabs, ksca = set_opacity(IFREQ)
@@ -671,6 +693,8 @@ def main(argv=None, device_factory=None):
                 harvest_roi(IFREQ, USER.GL * USER.GL)                            # ASOC.py:1468-1476
                 if VERBOSE:
                     sys.stdout.write("  FREQ %3d/%3d  %10.3e   BG %12.4e   TW %10.3e   %7.2f\n" % (IFREQ + 1, NFREQ, FREQ, BG, FF, time.time() - T000))
+            if freq_shard:
+                dev.set_shard(comm.rank, comm.world)
             comm.allreduce(dev, bk.BUF_TABS, CELLS)
             CTABS += dev.download(bk.BUF_TABS, CELLS, out=TMP)
             if VERBOSE and CELLS < 1e8:

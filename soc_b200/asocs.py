@@ -144,7 +144,7 @@ def main(argv=None, device_factory=None):
     dev.set_shard(comm.rank, comm.world)
     if USER.NO_PS > 0:
         dev.upload(bk.BUF_PSPOS, np.ascontiguousarray(USER.PSPOS[:USER.NO_PS].reshape(-1)))
-    if WITH_MSF:
+    if WITH_ABU:          # once: OPT of every frequency is built from it on the device (soc_build_opt)
         dev.upload(bk.BUF_ABU, np.ascontiguousarray(ABU, np.float32).reshape(-1))
     for b, v in ((bk.BUF_ODIR, ODIR), (bk.BUF_ORA, RA), (bk.BUF_ODE, DE)):
         dev.upload(b, np.ascontiguousarray(np.asarray(v, np.float32)[:, :3].reshape(-1)))
@@ -159,8 +159,11 @@ def main(argv=None, device_factory=None):
 
     def opacities(IFREQ):
         if WITH_ABU:
-            o = _opt_array(USER, ABU, AFABS, AFSCA, IFREQ).reshape(-1)
-            dev.upload(bk.BUF_OPT, o, np.float16 if USER.OPT_IS_HALF else np.float32)
+            if 'HOSTOPT' in USER.KEYS:
+                o = _opt_array(USER, ABU, AFABS, AFSCA, IFREQ).reshape(-1)
+                dev.upload(bk.BUF_OPT, o, np.float16 if USER.OPT_IS_HALF else np.float32)
+            else:
+                dev.build_opt([a[IFREQ] for a in AFABS], [s_[IFREQ] for s_ in AFSCA], 0, bool(USER.SINGLE_ABU))
             return 0.0, 0.0
         return float(sum(a[IFREQ] for a in AFABS)), float(sum(s_[IFREQ] for s_ in AFSCA))
 

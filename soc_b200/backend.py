@@ -42,7 +42,7 @@ class SocCounters(C.Structure):
 
 
 _EXPORTS = """soc_last_error soc_version soc_create soc_destroy soc_sync soc_set_params soc_set_grid soc_set_rng_mode
-soc_set_shard soc_set_tuning soc_set_geometry soc_set_layout soc_set_domains soc_set_roi soc_upload soc_download soc_clear soc_device_ptr soc_zero_amc soc_sim_pb soc_sim_hp
+soc_build_opt soc_set_shard soc_set_tuning soc_set_geometry soc_set_layout soc_set_domains soc_set_roi soc_upload soc_download soc_clear soc_device_ptr soc_zero_amc soc_sim_pb soc_sim_hp
 soc_sim_cl soc_absorbed_begin soc_absorbed_add soc_absorbed_finish soc_eq_temperature soc_emission soc_emission2 soc_mapping soc_mapping_levels soc_healpix_mapping soc_ps_tau soc_sca_zero_out soc_sca_ps soc_sca_pb soc_sca_hp soc_sca_cl
 soc_get_counters soc_reset_counters soc_last_launch_ms soc_last_kernel soc_stream""".split()
 
@@ -74,6 +74,7 @@ def load_library(path=None):
     L.soc_set_domains.argtypes = [vp, i]
     L.soc_set_roi.argtypes = [vp, vp, i, i, vp]
     L.soc_upload.argtypes = [vp, i, vp, C.c_size_t]
+    L.soc_build_opt.argtypes = [vp, i, fp, fp, i, i]
     L.soc_download.argtypes = [vp, i, vp, C.c_size_t]
     L.soc_clear.argtypes = [vp, i, C.c_size_t]
     L.soc_device_ptr.argtypes = [vp, i, C.POINTER(C.c_size_t)]
@@ -188,6 +189,13 @@ class Device:
         r = np.ascontiguousarray(roi, np.int32)
         d = np.ascontiguousarray(roi_dim, np.int32)
         self._ck(self.L.soc_set_roi(self.ctx, r.ctypes.data, int(roi_step), int(roi_nside), d.ctypes.data))
+
+    def build_opt(self, kabs, ksca, first=0, single_abu=False):
+        """OPT from the uploaded abundances and the per-species cross sections of one frequency (ASOC.py:1146-1161)."""
+        a = np.ascontiguousarray(kabs, np.float32)
+        s = np.ascontiguousarray(ksca, np.float32)
+        self._ck(self.L.soc_build_opt(self.ctx, len(a), a.ctypes.data_as(C.POINTER(C.c_float)), s.ctypes.data_as(C.POINTER(C.c_float)),
+                                      int(first), 1 if single_abu else 0))
 
     def set_layout(self, mode):
         self._ck(self.L.soc_set_layout(self.ctx, int(mode)))

@@ -772,6 +772,26 @@ int soc_eq_temperature(soc_context *c, int level, float adhoc, float kE, float E
     return SOC_OK;
 }
 
+int soc_build_opt(soc_context *c, int ndust, const float *kabs, const float *ksca, int first, int single_abu) {
+    NEED_CTX(c);
+    if (!c->have_grid || !c->have_params) return fail(SOC_ERR_STATE, "soc_build_opt: grid and params first");
+    if (!c->P.with_abu) return fail(SOC_ERR_STATE, "soc_build_opt: the run has no variable abundances (WITH_ABU = 0)");
+    if (ndust < 1 || ndust > SOC_MAX_DUSTS || !kabs || !ksca || first < 0 || first >= ndust) return fail(SOC_ERR_ARG, "soc_build_opt: ndust=%d first=%d", ndust, first);
+    if (single_abu && ndust != 2) return fail(SOC_ERR_ARG, "soc_build_opt: SINGLE_ABU assumes exactly two dust species (ASOC.py:620)");
+    const size_t cells = (size_t)c->G.cells;
+    int r;
+    // SINGLE_ABU reads one abundance per cell, ABU[cells, 1]; else ABU[cells, ndust]
+    const int width = single_abu ? (int)(c->buf[SOC_BUF_ABU].bytes / (cells * 4)) : ndust;
+    if (width < 1 || (!single_abu && width != ndust)) return fail(SOC_ERR_STATE, "soc_build_opt: ABU holds %zu bytes, expected CELLS x %d floats", c->buf[SOC_BUF_ABU].bytes, ndust);
+    if ((r = need(c, SOC_BUF_ABU, cells * 4 * (size_t)width, "soc_build_opt")) != SOC_OK) return r;
+    if ((r = ensure(c, SOC_BUF_OPT, cells * 8)) != SOC_OK) return r;
+    launch_build_opt(dptr<float>(c, SOC_BUF_ABU), dptr<float>(c, SOC_BUF_OPT), (long long)cells, width, single_abu ? 0 : first, single_abu,
+                     c->P.opt_is_half, kabs, ksca, c->stream);
+    c->launches++;
+    CU(cudaGetLastError());
+    return SOC_OK;
+}
+
 int soc_absorbed_begin(soc_context *c, int nfreq) {
     NEED_CTX(c);
     if (!c->have_grid || !c->have_params) return fail(SOC_ERR_STATE, "soc_absorbed_begin: grid and params first");

@@ -123,6 +123,40 @@ void launch_half_to_float(const void *src, float *dst, long long n, cudaStream_t
     half_to_float_kernel<<<(int)(b < 1 ? 1 : (b > cap ? cap : b)), 256, 0, stream>>>(reinterpret_cast<const __half *>(src), dst, n);
 }
 
+// OPT[cells,2] = per-cell (KABS, KSCA) from the abundances: sum over the dust species of ABU[cell, d] * K[d], in the
+// reference's order and precision (ASOC.py:1146-1161: float32 products added one species after the other; SINGLE_ABU:
+// a*K0 + (1-a)*K1; OPT_IS_HALF: the result rounded to half precision).  Nothing of CELLS size crosses PCIe per frequency.
+struct OptCoeffs { float kabs[SOC_MAX_DUSTS], ksca[SOC_MAX_DUSTS]; };
+__global__ void __launch_bounds__(256) build_opt_kernel(const float *__restrict__ abu, float2 *__restrict__ opt, long long cells, int ndust,
+                                                        int first, int single_abu, int half, const OptCoeffs K) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += stride) {
+        float a = 0.0f, s = 0.0f;
+        if (single_abu) {
+            const float x = abu[i * ndust], y = __fsub_rn(1.0f, x);
+            a = __fadd_rn(__fmul_rn(x, K.kabs[0]), __fmul_rn(y, K.kabs[1]));
+            s = __fadd_rn(__fmul_rn(x, K.ksca[0]), __fmul_rn(y, K.ksca[1]));
+        } else {
+            for (int d = first; d < ndust; d++) {
+                const float x = abu[i * ndust + d];
+                a = __fadd_rn(a, __fmul_rn(x, K.kabs[d]));
+                s = __fadd_rn(s, __fmul_rn(x, K.ksca[d]));
+            }
+        }
+        if (half) { a = __half2float(__float2half_rn(a)); s = __half2float(__float2half_rn(s)); }
+        opt[i] = make_float2(a, s);
+    }
+}
+void launch_build_opt(const float *abu, float *opt, long long cells, int ndust, int first, int single_abu, int half,
+                      const float *kabs, const float *ksca, cudaStream_t stream) {
+    OptCoeffs K;
+    for (int d = 0; d < SOC_MAX_DUSTS; d++) { K.kabs[d] = d < ndust ? kabs[d] : 0.0f; K.ksca[d] = d < ndust ? ksca[d] : 0.0f; }
+    long long b = (cells + 255) / 256;
+    const long long cap = 148LL * 16;
+    build_opt_kernel<<<(int)(b < 1 ? 1 : (b > cap ? cap : b)), 256, 0, stream>>>(abu, reinterpret_cast<float2 *>(opt), cells, ndust, first, single_abu,
+                                                                                  half, K);
+}
+
 // Neighbour table of linkwalk.cuh: NBR[6*cell + face], face = 2*axis + (towards +axis).  For every cell the cell of
 // the same level behind the face if the hierarchy has it (possibly refined further), else the coarser leaf covering it.
 __global__ void neighbours_kernel(GridDesc G, int *__restrict__ nbr) {

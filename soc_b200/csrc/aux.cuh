@@ -11,5 +11,8 @@ void launch_absorbed_add(float *fabs, const float *inten, int cells, int nfreq, 
 void launch_absorbed_scale(const GridDesc &G, float *fabs, int nfreq, float coeff0, float nnnlimit, cudaStream_t stream);
 void launch_emission2(int c0, int c1, int nfreq, float factor, float length, const float *freq, const float *fabs_, const float *t,
                       float *emit, cudaStream_t stream);
+#define SOC_MAX_DUSTS 32
+void launch_build_opt(const float *abu, float *opt, long long cells, int ndust, int first, int single_abu, int half,
+                      const float *kabs, const float *ksca, cudaStream_t stream);   // OPT from ABU on the device
 void launch_half_to_float(const void *src, float *dst, long long n, cudaStream_t stream);
 void launch_neighbours(const GridDesc &G, int *nbr, cudaStream_t stream);      // neighbour table of linkwalk.cuh, [6*cells]

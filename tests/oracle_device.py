@@ -99,6 +99,23 @@ class OracleDevice:
             self.buf[b] = np.array(array, dtype).reshape(-1).astype(np.float32 if dtype == np.float16 else dtype)
         return array
 
+    def build_opt(self, kabs, ksca, first=0, single_abu=False):
+        """Host restatement of ASOC.py:1146-1161 on the uploaded abundances (the library does this on the device)."""
+        kabs, ksca = np.asarray(kabs, np.float32), np.asarray(ksca, np.float32)
+        abu = self.buf[bk.BUF_ABU].reshape(self.n, -1)
+        opt = np.zeros((self.n, 2), np.float32)
+        if single_abu:
+            a = abu[:, 0]
+            opt[:, 0] = a * kabs[0] + (1.0 - a) * kabs[1]
+            opt[:, 1] = a * ksca[0] + (1.0 - a) * ksca[1]
+        else:
+            for d in range(first, len(kabs)):
+                opt[:, 0] += abu[:, d] * kabs[d]
+                opt[:, 1] += abu[:, d] * ksca[d]
+        if self.params.get("opt_is_half"):
+            opt = opt.astype(np.float16).astype(np.float32)
+        self.buf[bk.BUF_OPT] = opt.reshape(-1)
+
     def download(self, b, n, dtype=np.float32, out=None):
         src = self.host_view(b, n)
         if out is None:

@@ -113,6 +113,38 @@ def test_two_gloo_ranks_agree_with_one(tmp_path):
     assert np.abs(m2[:2] / m1[:2] - 1.0).max() < 0.1
 
 
+@pytest.mark.parametrize("mode", ["frequencies", "packets"])
+def test_two_gloo_ranks_absorbed_file(tmp_path, mode):
+    """world_size 2 over gloo, absorbed file on: by default the constant sources are sharded by frequency (rank r runs
+    frequencies r, r+2, ... whole; no per-frequency collective), with PACKETSHARD by packet index.  Both must give the
+    1-rank absorbed file within Monte Carlo noise -- frequency sharding runs exactly the 1-rank launches, so with a fixed
+    seed it reproduces that file to rounding."""
+    from soc_b200.formats import read_cells_freq_file
+    kw = dict(n=8, bgpac=60000, pspac=33000, noabsorbed=False, absorbed=True, maps=False)
+    one, two = tmp_path / "one", tmp_path / "two"
+    _run(one, **kw)
+    write_model(str(two), extra="verbose 1\n" + ("PACKETSHARD\n" if mode == "packets" else ""), **kw)
+    (two / "run.py").write_text(
+        "import sys\nsys.path.insert(0, %r)\nfrom soc_b200 import asoc\nfrom tests.oracle_device import OracleDevice\n"
+        "asoc.main(['ASOC.py', 'model.ini'], device_factory=OracleDevice)\n" % ROOT)
+    env = dict(os.environ, SOC_DIST_BACKEND="gloo", OMP_NUM_THREADS="2")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29537" if mode == "packets" else "29539", "run.py"],
+                       cwd=str(two), env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert ("sharded by frequency" in r.stdout) == (mode == "frequencies"), r.stdout[-1500:]
+    a1 = read_cells_freq_file(str(one / "abs.data")).astype(np.float64)
+    a2 = read_cells_freq_file(str(two / "abs.data")).astype(np.float64)
+    assert a1.shape == a2.shape
+    t1, t2 = a1.sum(axis=0), a2.sum(axis=0)
+    ok = t1 > 0
+    if mode == "frequencies":
+        assert np.abs(t2[ok] / t1[ok] - 1.0).max() < 1e-5
+        assert np.abs(a2 - a1).max() <= 1e-5 * a1.max()
+    else:
+        assert np.abs(t2[ok] / t1[ok] - 1.0).max() < 0.03
+
+
 def test_scattered_light_driver_writes_outcoming(tmp_path):
     from soc_b200 import asocs
     from soc_b200.formats import read_outcoming

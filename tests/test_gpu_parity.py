@@ -150,6 +150,33 @@ def test_emission2_matches_oracle():
     assert (b[~ok] == 0).all() and np.abs(b[ok] / a[ok] - 1.0).max() < 2e-5       # expf differs in the last bits
 
 
+@pytest.mark.parametrize("mode", ["sum", "from_second", "single_abu", "half"])
+def test_opt_built_on_the_device_equals_the_host_loop(mode):
+    """soc_build_opt against the host loop of ASOC.py:1146-1161 (soc_b200.asoc._opt_array): same float32 operations in
+    the same order => bit-identical; OPT_IS_HALF rounds to half precision like numpy's astype(float16)."""
+    from types import SimpleNamespace
+    from soc_b200 import backend
+    from soc_b200.asoc import _opt_array
+    cloud = synth.octree_cloud(6, 3, refine_fraction=0.2, seed=3)
+    rng = np.random.default_rng(8)
+    ndust = 2 if mode == "single_abu" else 3
+    abu = (0.05 + rng.random((cloud.CELLS, ndust))).astype(np.float32)
+    afabs = [(1e-3 * (1 + d) * (0.5 + rng.random(4))).astype(np.float32) for d in range(ndust)]
+    afsca = [(2e-3 * (1 + d) * (0.5 + rng.random(4))).astype(np.float32) for d in range(ndust)]
+    first = 1 if mode == "from_second" else 0
+    user = SimpleNamespace(SINGLE_ABU=1 if mode == "single_abu" else 0)
+    B = _backend(cloud, backend.RNG_PACKET, with_abu=1, opt_is_half=1 if mode == "half" else 0)
+    B.dev.upload(backend.BUF_ABU, abu.reshape(-1))
+    for ifreq in range(4):
+        want = _opt_array(user, abu, afabs, afsca, ifreq, first)
+        if mode == "half":
+            want = want.astype(np.float16).astype(np.float32)
+        B.dev.build_opt([a[ifreq] for a in afabs], [s[ifreq] for s in afsca], first, mode == "single_abu")
+        got = B.dev.download(backend.BUF_OPT, 2 * cloud.CELLS).reshape(-1, 2)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (mode, ifreq, np.abs(got - want).max())
+    B.close()
+
+
 def _repeat(X, runner_factory, K, key="tabs"):
     """K repetitions with different seeds; `key` may be a tuple of output names (returns a dict of arrays then)."""
     keys = key if isinstance(key, tuple) else (key,)
