@@ -87,7 +87,13 @@ typedef struct soc_params {
     int32_t ndust;             /* NDUST (only read when with_msf != 0)                            */
     int32_t opt_is_half;       /* OPT_IS_HALF: soc_upload(SOC_BUF_OPT) takes IEEE half values (ASOC.py:1155); they are
                                   widened on the device, the kernels see exactly the half-rounded opacities  */
-    int32_t reserved2[2];
+    int32_t ref_quirks;        /* behaviour of the shipped reference where this library deliberately differs (ini key REFQUIRKS):
+                                  bit 0 (1): scattered-light SimRAM_HP / SimRAM_CL weight their peel-off rays with the `#ifdef
+                                  HG_TEST` branch that is live in kernel_ASOC_sca.c (analytic g = 0.65 phase function times
+                                  1-exp(-tau), :349-355, 1343-1349) instead of DSC * exp(-tau);
+                                  bit 1 (2): per-level maps step with the Index() copy of kernel_ASOC_map_H.c, which drops the
+                                  root coordinates when a ray climbs into a root-grid leaf (:250).  0 = the intended behaviour */
+    int32_t reserved2[1];
 } soc_params;
 
 /* Device buffers.  Names are those of the reference's kernel arguments. */

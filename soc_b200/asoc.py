@@ -371,7 +371,8 @@ def main(argv=None, device_factory=None):
                    level_threshold=USER.LEVEL_THRESHOLD, length=length, factor=FACTOR, adhoc=ADHOC,
                    with_msf=int(WITH_MSF), ndust=NDUST, mirror=mirror_mask(USER),
                    map_interpolation=USER.MAP_INTERPOLATION, opt_is_half=int(bool(USER.OPT_IS_HALF)),
-                   with_roi_load=int(USER.WITH_ROI_LOAD), with_roi_save=int(USER.WITH_ROI_SAVE), roi_map=int(USER.ROI_MAP))
+                   with_roi_load=int(USER.WITH_ROI_LOAD), with_roi_save=int(USER.WITH_ROI_SAVE), roi_map=int(USER.ROI_MAP),
+                   ref_quirks=3 if 'REFQUIRKS' in USER.KEYS else 0)
     dev.set_grid(cloud)
     # region of interest (ASOC.py:906-945): the external field to load, the file of photons entering ROI
     ROI_LOAD = ROI_SAVE = None

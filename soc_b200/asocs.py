@@ -125,7 +125,7 @@ def main(argv=None, device_factory=None):
     dev.set_params(bins=USER.DSC_BINS, no_ps=max(1, USER.NO_PS), ps_method=USER.PS_METHOD, with_abu=int(WITH_ABU),
                    ffs=USER.FFS, hpbg_weighted=int(USER.HPBG_WEIGHTED), use_emweight=USER.USE_EMWEIGHT,
                    with_msf=int(WITH_MSF), ndust=NDUST, mirror=mirror_mask(USER), opt_is_half=int(bool(USER.OPT_IS_HALF)),
-                   with_roi_load=int(USER.WITH_ROI_LOAD),
+                   with_roi_load=int(USER.WITH_ROI_LOAD), ref_quirks=3 if 'REFQUIRKS' in USER.KEYS else 0,
                    length=float("%.5e" % (USER.GL * PARSEC)), factor=FACTOR, adhoc=ADHOC)
     dev.set_grid(cloud)
     ROI_LOAD, ROI_LOAD_NELEM = None, 0

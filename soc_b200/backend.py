@@ -33,7 +33,7 @@ class SocParams(C.Structure):
         "hpbg_weighted", "ffs", "step_weight", "level_threshold", "with_msf", "mirror", "dir_weight", "do_split",
         "roi_flags", "map_interpolation")] + \
         [(n, C.c_float) for n in ("sw_a", "sw_b", "length", "factor", "adhoc", "reserved")] + \
-        [("ndust", C.c_int32), ("opt_is_half", C.c_int32), ("reserved2", C.c_int32 * 2)]
+        [("ndust", C.c_int32), ("opt_is_half", C.c_int32), ("ref_quirks", C.c_int32), ("reserved2", C.c_int32 * 1)]
 
 
 class SocCounters(C.Structure):
@@ -162,6 +162,7 @@ class Device:
         p.length, p.factor, p.adhoc = kw["length"], kw.get("factor", 1.0e20), kw.get("adhoc", 1.0)
         p.ndust = kw.get("ndust", 1)
         p.opt_is_half = kw.get("opt_is_half", 0)
+        p.ref_quirks = kw.get("ref_quirks", 0)
         self._ck(self.L.soc_set_params(self.ctx, C.byref(p)))
         self.params = p
 

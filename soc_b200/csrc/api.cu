@@ -183,6 +183,7 @@ int soc_set_params(soc_context *c, const soc_params *p) {
         return fail(SOC_ERR_UNSUPPORTED, "soc_set_params: PS_METHOD %d (the reference's method 3 does not compile either)", p->ps_method);
     if (p->bins < 2) return fail(SOC_ERR_ARG, "soc_set_params: BINS=%d", p->bins);
     if (p->no_ps < 1) return fail(SOC_ERR_ARG, "soc_set_params: NO_PS must be >= 1 (ASOC.py:344 passes max(1,NO_PS))");
+    if (p->ref_quirks < 0 || p->ref_quirks > 3) return fail(SOC_ERR_ARG, "soc_set_params: ref_quirks=%d", p->ref_quirks);
     if (p->save_intensity < 0 || p->save_intensity > 2) return fail(SOC_ERR_ARG, "soc_set_params: SAVE_INTENSITY=%d", p->save_intensity);
     if (!(p->length > 0.0f) || !(p->factor > 0.0f) || !(p->adhoc > 0.0f)) return fail(SOC_ERR_ARG, "soc_set_params: LENGTH, FACTOR, ADHOC must be positive");
     c->P = *p;
@@ -886,6 +887,7 @@ static int map_common(soc_context *c, MapArgs &M, size_t npixels, float abs, flo
     M.kabs = abs; M.ksca = sca; M.length = c->P.length;
     M.with_abu = c->P.with_abu; M.level_threshold = c->P.level_threshold; M.save_colden = save_colden;
     M.map_interpolation = c->P.map_interpolation;
+    M.maph_literal = (c->P.ref_quirks & 2) ? 1 : 0;
     if ((r = roi_args(c, M.roi, false, who)) != SOC_OK) return r;
     M.counters = c->counters;
     return SOC_OK;
@@ -1019,6 +1021,7 @@ static int sca_common(soc_context *c, ScaArgs &S, int kind, int flavour, int bat
     S.bins = P.bins; S.no_ps = P.no_ps; S.ps_method = P.ps_method; S.with_abu = P.with_abu; S.ffs = P.ffs;
     S.hpbg_weighted = P.hpbg_weighted; S.use_emweight = P.use_emweight; S.with_ali = 0;
     S.with_msf = P.with_msf; S.ndust = P.with_msf ? P.ndust : 1; S.mirror = P.mirror;
+    S.hg_test = (P.ref_quirks & 1) ? 1 : 0;
     S.nbr = c->nbr;
     S.rank = c->rank; S.world = c->world; S.ref_geometry = c->geometry; S.ev_batch = c->sc_batch > 0 ? c->sc_batch : 3; S.nav_hops = c->nav_hops;
     long long ms = 100LL * ((long long)c->G.nx + c->G.ny + c->G.nz) << (c->G.levels - 1);

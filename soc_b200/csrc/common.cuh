@@ -205,7 +205,9 @@ __device__ __forceinline__ void index_global(const GridDesc &G, vec3 &p, int &le
 
 // Index(): the leaf containing a position that has just left cell (level, ind)
 // (kernel_ASOC_aux.c:198-278; map flavour kernel_ASOC_map.c:294-379 with its z<=0 containment test).
-template <typename REAL, bool MAPK>
+// MAPH_LIT: the copy of Index() in kernel_ASOC_map_H.c:216-291, which returns without storing the root coordinates when the
+// ray climbs into a root-grid leaf (:250) -- only on request (soc_params.ref_quirks & 2).
+template <typename REAL, bool MAPK, bool MAPH_LIT = false>
 __device__ __forceinline__ void index_octree(const GridDesc &G, vec3 &pos, int &level, int &ind, float &rho) {
     REAL px = pos.x, py = pos.y, pz = pos.z;
     const int NX = G.nx, NY = G.ny, NZ = G.nz;
@@ -226,7 +228,7 @@ __device__ __forceinline__ void index_octree(const GridDesc &G, vec3 &pos, int &
                 }
                 ind = (int)floor_r(pz) * NX * NY + (int)floor_r(py) * NX + (int)floor_r(px);
                 rho = G.dens[ind]; need_rho = false;
-                if (is_leaf(rho)) { pos.x = (float)px; pos.y = (float)py; pos.z = (float)pz; return; }
+                if (is_leaf(rho)) { if (!MAPH_LIT) { pos.x = (float)px; pos.y = (float)py; pos.z = (float)pz; } return; }
                 break;
             } else {
                 int sid = ind & 7;
@@ -256,7 +258,7 @@ __device__ __forceinline__ void index_octree(const GridDesc &G, vec3 &pos, int &
 // GetStep (kernel_ASOC_aux.c:282-315, kernel_ASOC_map.c:387-429): distance to the next cell face with PEPS
 // overshoot, advance the local position, look up the neighbour.  Returns the step in root-grid units and the
 // density of the cell entered (`rho`, undefined when ind<0).
-template <bool OCT, bool DBL, bool MAPK>
+template <bool OCT, bool DBL, bool MAPK, bool MAPH_LIT = false>
 __device__ __forceinline__ float get_step(const GridDesc &G, vec3 &p, const vec3 &d, int &level, int &ind, float &rho) {
     const float peps = MAPK ? SOC_MAP_PEPS : SOC_PEPS;
     float dx = (d.x > 0.0f) ? xdiv(xsub(xadd(1.0f, peps), fmod1(p.x)), d.x) : xdiv(xsub(-peps, fmod1(p.x)), d.x);
@@ -266,8 +268,8 @@ __device__ __forceinline__ float get_step(const GridDesc &G, vec3 &p, const vec3
     p.x = xadd(p.x, xmul(dx, d.x)); p.y = xadd(p.y, xmul(dx, d.y)); p.z = xadd(p.z, xmul(dx, d.z));
     if (OCT) {
         dx = ldexpf(dx, -level);
-        if (DBL) index_octree<double, MAPK>(G, p, level, ind, rho);
-        else     index_octree<float, MAPK>(G, p, level, ind, rho);
+        if (DBL) index_octree<double, MAPK, MAPH_LIT>(G, p, level, ind, rho);
+        else     index_octree<float, MAPK, MAPH_LIT>(G, p, level, ind, rho);
     } else {
         if (!(p.x > 0.0f && p.x < G.nx && p.y > 0.0f && p.y < G.ny && p.z > 0.0f && p.z < G.nz)) { ind = -1; }
         else {

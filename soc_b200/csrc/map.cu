@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(128) healpix_mapping_kernel(const __grid_const
 // store the root coordinates when a ray climbs into a root-grid leaf and loses ~15 % of the flux of a refined cloud
 // (DESIGN.md section 7), which is not reproduced.  Level sums stay in registers: the adds are predicated, not indexed.
 #define SOC_MAP_MAXLEV 12
-template <bool OCT, bool DBL>
+template <bool OCT, bool DBL, bool LIT>
 __global__ void __launch_bounds__(128) mapping_levels_kernel(const __grid_constant__ MapArgs M) {
     const GridDesc &G = M.G;
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(128) mapping_levels_kernel(const __grid_consta
             float kext;
             if (M.with_abu) { float2 o = reinterpret_cast<const float2 *>(M.opt)[oind]; kext = xadd(o.x, o.y); }
             else            kext = xadd(M.ksca, M.kabs);
-            const float sx = get_step<OCT, DBL, true>(G, POS, TMP, level, ind, rho);
+            const float sx = get_step<OCT, DBL, true, LIT>(G, POS, TMP, level, ind, rho);
             const float DTAU = xmul(xmul(sx, dens), kext);
             const float w = (DTAU < 1.0e-3f) ? xsub(1.0f, xmul(0.5f, DTAU)) : xdiv(xsub(1.0f, exp_cr(-DTAU)), DTAU);
             const float term = xmul(xmul(xmul(xmul(exp_cr(-TAU), w), sx), em), dens);
@@ -326,9 +326,14 @@ void launch_pstau(const MapArgs &M, int no, const float *pspos, float *colden, f
 void launch_mapping_levels(const MapArgs &M, cudaStream_t stream) {
     const bool oct = M.G.levels > 1, dbl = M.G.dbl_map != 0;
     const int n = M.npx * M.npy, threads = 128, blocks = (n + threads - 1) / threads;
-    if (!oct)      mapping_levels_kernel<false, false><<<blocks, threads, 0, stream>>>(M);
-    else if (!dbl) mapping_levels_kernel<true, false><<<blocks, threads, 0, stream>>>(M);
-    else           mapping_levels_kernel<true, true><<<blocks, threads, 0, stream>>>(M);
+    if (!oct)      mapping_levels_kernel<false, false, false><<<blocks, threads, 0, stream>>>(M);
+    else if (M.maph_literal) {
+        if (!dbl) mapping_levels_kernel<true, false, true><<<blocks, threads, 0, stream>>>(M);
+        else      mapping_levels_kernel<true, true, true><<<blocks, threads, 0, stream>>>(M);
+    } else {
+        if (!dbl) mapping_levels_kernel<true, false, false><<<blocks, threads, 0, stream>>>(M);
+        else      mapping_levels_kernel<true, true, false><<<blocks, threads, 0, stream>>>(M);
+    }
 }
 
 void launch_mapping(const MapArgs &M, bool healpix, cudaStream_t stream) {

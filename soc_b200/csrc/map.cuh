@@ -10,6 +10,7 @@ struct MapArgs {
     float map_dx, kabs, ksca, length;
     int npx, npy, nside, with_abu, level_threshold, save_colden;
     RoiDesc roi;                                           // ROI_MAP (flags & 4): only cells inside ROI emit
+    int maph_literal;                                      // per-level maps: the file's own Index() (soc_params.ref_quirks & 2)
     int map_interpolation;                                 // MAP_INTERPOLATION 0/1/2 (orthographic and perspective maps)
     unsigned long long *counters;
 };

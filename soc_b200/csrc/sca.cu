@@ -35,6 +35,14 @@ struct Lane {
 struct ScaCounters { unsigned long long packets, steps, scat, stuck, peels; };
 
 // cos(theta) clamp before the DSC look-up: SimRAM_PS/PB use 0.999, SimRAM_HP/CL 0.9999 (kernel_ASOC_sca.c:991,1830 / 356,1329)
+// kernel_ASOC_sca.c:349-355, 392-398, 1343-1349, 1387-1393: the `#ifdef HG_TEST` branch that is live in the shipped SimRAM_HP /
+// SimRAM_CL (HG_TEST is #defined, as 0, in kernel_ASOC_aux.c:1): analytic Henyey-Greenstein function with g = 0.65 and
+// the scattered instead of the transmitted fraction.  Only on request (ScaArgs.hg_test).
+__device__ __forceinline__ float hg_test_weight(float cos_theta, float tau) {
+    const float g = 0.65f;
+    const float frac = (1.0f / (4.0f * SOC_PI)) * (1.0f - g * g) / powf(1.0f + g * g - 2.0f * g * cos_theta, 1.5f);
+    return frac * ((tau > SOC_TAULIM) ? (1.0f - expf(-tau)) : (tau * (1.0f - 0.5f * tau)));
+}
 __device__ __forceinline__ float cos_clamp(const ScaArgs &S) { return (S.flavour >= 2) ? 0.9999f : 0.999f; }
 
 template <class RNG, bool OCT>
@@ -106,6 +114,7 @@ __device__ __forceinline__ void advance(const ScaArgs &S, Lane &L, RNG &rng, Sca
         const float *dsc = S.dsc;
         if (S.with_msf) dsc += S.bins * msf_pick(S.abu, S.scav, S.ndust, S.opt[2 * (size_t)ocell + 1], ocell, rng.uniform());
         float delta = L.photons * expf(-r.tau) * dsc[clampi((int)xmul(xmul((float)S.bins, xadd(1.0f, cos_theta)), 0.5f), 0, S.bins - 1)];
+        if (S.hg_test && S.flavour >= 2) delta = L.photons * hg_test_weight(cos_theta, r.tau);
         if (S.nside > 0) {
             delta *= L.dscale;
             const float theta = acosf(-r.dir.z), phi = atan2f(r.dir.y, r.dir.x);
@@ -391,6 +400,7 @@ __global__ void __launch_bounds__(256, 3) sca_walk_kernel(const __grid_constant_
                     dsc += S.bins * msf_pick(S.abu, S.scav, S.ndust, __ldg(S.opt + 2 * (size_t)kcell + 1), kcell, rm.uniform());
                 }
                 float delta = photons * __expf(-tau) * __ldg(dsc + clampi((int)(S.bins * (1.0f + cos_theta) * 0.5f), 0, S.bins - 1));
+                if (S.hg_test && S.flavour >= 2) delta = photons * hg_test_weight(cos_theta, tau);
                 if (S.nside > 0) {                                    // Healpix image seen from odir[0..2]
                     const int ipix = ang2pix_ring(S.nside, atan2f(od.y, od.x), acosf(clampf(-od.z, -1.0f, 1.0f)));
                     if ((unsigned)ipix < 12u * S.nside * S.nside) atomicAdd(&S.out[ipix], delta * dscale);
@@ -607,6 +617,7 @@ __global__ void __launch_bounds__(256, 3) sca_link_kernel(const __grid_constant_
                     dsc += S.bins * msf_pick(S.abu, S.scav, S.ndust, __ldg(S.opt + 2 * (size_t)kcell + 1), kcell, rm.uniform());
                 }
                 float delta = photons * __expf(-tau) * __ldg(dsc + clampi((int)(S.bins * (1.0f + cos_theta) * 0.5f), 0, S.bins - 1));
+                if (S.hg_test && S.flavour >= 2) delta = photons * hg_test_weight(cos_theta, tau);
                 if (S.nside > 0) {                                    // Healpix image seen from odir[0..2]
                     const int ipix = ang2pix_ring(S.nside, atan2f(od.y, od.x), acosf(clampf(-od.z, -1.0f, 1.0f)));
                     if ((unsigned)ipix < 12u * S.nside * S.nside) atomicAdd(&S.out[ipix], delta * dscale);

@@ -21,6 +21,7 @@ struct ScaArgs {
     int nside;                         // > 0: one Healpix image of this NSIDE seen from odir[0..2] (reference: NDIR = -NSIDE)
     int bins, no_ps, ps_method, with_abu, ffs;
     int hpbg_weighted, use_emweight, with_ali, with_msf, ndust, mirror;
+    int hg_test;                       // SimRAM_HP / SimRAM_CL as shipped: `#ifdef HG_TEST` peel-off weight (soc_params.ref_quirks & 1)
     const int *__restrict__ nbr;       // octrees: neighbour table [6*cells] (linkwalk.cuh) or nullptr
     RoiDesc roi;                       // WITH_ROI_LOAD source (kind 4)
     int roi_nelem;

@@ -47,6 +47,8 @@ class OracleDevice:
         bins = p.pop("bins", 2500)
         for k in ("factor", "adhoc", "dir_weight", "do_split", "roi_flags", "opt_is_half"):
             p.pop(k, None)
+        q = p.pop("ref_quirks", 0)
+        p["hg_test"], p["maph_literal"] = int(bool(q & 1)), int(bool(q & 2))
         # the drivers are compared with the library's production kernels: exact mirror / scattering position
         p.update(self.roi)
         self.O = orc.Oracle(self.cloud, gl=0.01, bins=bins, mirror_exact=1, sca_exact_level=1, **p)

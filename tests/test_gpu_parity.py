@@ -71,11 +71,11 @@ def test_reference_streams_match_oracle(name):
 def test_reference_streams_match_golden(name):
     """Same comparison against the vectors produced by the reference's own kernels (tests/golden)."""
     from soc_b200 import backend
-    if name in SHIPPED_HG_TEST:
-        pytest.skip("golden holds the reference's HG_TEST branch; the intended branch is checked against the oracle")
     make, opts, run = CASES[name]
     gold = np.load(os.path.join(GOLD, name + ".npz"))
-    B = _backend(make(), backend.RNG_REFERENCE, **opts)
+    # the goldens of the scattered-light HP / CL cases hold the reference's HG_TEST branch: ref_quirks bit 0 reproduces it
+    # (the intended branch is checked against the oracle in test_reference_streams_match_oracle)
+    B = _backend(make(), backend.RNG_REFERENCE, ref_quirks=1 if name in SHIPPED_HG_TEST else 0, **opts)
     out = run(B)
     for key in gold.files:
         _compare_mc(name, key, out[key], gold[key])
@@ -92,14 +92,16 @@ def test_maps_match_oracle_and_golden(name):
     B = _backend(cloud, backend.RNG_REFERENCE, **opts)
     out_g = run(B)
     gold = np.load(os.path.join(GOLD, name + ".npz"))
-    refs = [out_o, {k: gold[k] for k in gold.files}]
+    refs = [(out_o, out_g), ({k: gold[k] for k in gold.files}, out_g)]
     if name.startswith("map_lev") and cloud.LEVELS > 1:
-        # the goldens hold kernel_ASOC_map_H.c as shipped, whose Index() loses rays that climb into root-grid leaves
-        # (pinned by the oracle's maph_literal variant on the CPU); the library steps like kernel_ASOC_map.c
-        refs = refs[:1]
-    for ref in refs:
+        # the goldens hold kernel_ASOC_map_H.c as shipped, whose Index() loses rays that climb into root-grid leaves;
+        # the library steps like kernel_ASOC_map.c unless ref_quirks bit 1 asks for the file's own Index()
+        Q = _backend(cloud, backend.RNG_REFERENCE, ref_quirks=2, **opts)
+        refs[1] = (refs[1][0], run(Q))
+        Q.close()
+    for ref, got in refs:
         for key in ref:
-            a, b = out_g[key].astype(np.float64), ref[key].astype(np.float64)
+            a, b = got[key].astype(np.float64), ref[key].astype(np.float64)
             nz = b != 0.0
             assert (a[~nz] == 0.0).all(), key
             rel = np.abs(a[nz] - b[nz]) / np.abs(b[nz])
@@ -294,6 +296,9 @@ SCA_STAT_CASES = {
     "sca_bg_reg12_msf": (_reg(12), dict(with_abu=1, with_msf=1, ndust=2), lambda s: run_sca("bg", batch=24, msf=True, seed=s)),
     "sca_bg_reg12_mirror": (_reg(12), dict(mirror=1 + 8), lambda s: run_sca("bg", batch=24, seed=s)),
     "sca_roi_reg12_load": (_reg(12), dict(with_roi_load=1, roi_dim=[4, 4, 4], roi_nside=2), lambda s: run_sca("roi", batch=2, seed=s)),
+    # ref_quirks bit 0: the production kernel with the peel-off weight of the shipped SimRAM_HP / SimRAM_CL (HG_TEST branch)
+    "sca_hp_reg12_quirk": (_reg(12), dict(ref_quirks=1), lambda s: run_sca("hp", batch=64, glob=1024, seed=s)),
+    "sca_cl_oct6_quirk": (_oct(6, 3), dict(ref_quirks=1), lambda s: run_sca("cl", batch=2, glob=256, dirs=((35.0, 110.0),), seed=s)),
 }
 
 
@@ -309,7 +314,7 @@ def test_scattered_light_statistical_parity(name):
     # On octrees the reference displaces the scattering point with the level of the *next* cell
     # (kernel_ASOC_sca.c:958); the production kernel is geometrically exact, so the expectation is the oracle's
     # exact-level variant (the reference-faithful variant is what the REFSTREAMS/REFGEOMETRY kernels are tested on).
-    a = _repeat(orc.Oracle(cloud, sca_exact_level=1, mirror_exact=1, **opts), fac, K, "out").reshape(K, -1)
+    a = _repeat(orc.Oracle(cloud, sca_exact_level=1, mirror_exact=1, hg_test=opts.get("ref_quirks", 0) & 1, **opts), fac, K, "out").reshape(K, -1)
     B = _backend(cloud, backend.RNG_PACKET, **opts)
     b = _repeat(B, fac, K, "out").reshape(K, -1)
     assert np.isfinite(b).all()
