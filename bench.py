@@ -17,6 +17,8 @@ the background, read-back of the per-frequency absorptions.
            replicated); INT of frequency f is reduced to rank 0 (ncclReduce) and read back on a second stream while
            the kernels of frequency f+1 run (two INT buffers), all inside the timed region.
   roofline        : both launches of the step, `kernel` = the one with the larger share of the step
+  e2e_driver      : the same configuration through the driver itself (bin/ASOC.py: files in, files out), wall clock with the
+                    driver's breakdown (context, uploads, kernels, solve, maps, file writes); N = 1 only
   extra_workloads : short runs of the other BASELINE.json configurations outside the timed headline -- 512^3
                     (configs 4/5), 256^3 with per-cell opacities (config 4 physics), the ~1e7-cell octree absorption
                     run and its scattered-light launch (config 3) -- each with its roofline fraction and the
@@ -422,6 +424,55 @@ def extra_octree(backend, local, peak, cpu_seconds=4.0):
     return lines
 
 
+def driver_e2e(n=N_GRID, nfreq=44, workdir=None, device_factory=None):
+    """BASELINE.json configs[1] through the reference-facing entry point, the ASOC driver itself (bin/ASOC.py <ini>, files
+    in, files out): 256^3 cloud file, 44 frequencies, point source + background with 3e7 packets each per frequency.
+    Two runs, as the reference is used (the driver, like ASOC.py, refuses to write the absorbed file and solve in one go):
+      absorbed : `nosolve`, `absorbed abs.data` -- the [CELLS, NFREQ] absorptions for an external dust solver (A2E);
+      maps     : `noabsorbed`, CLT / CLE -- absorptions integrated on the fly, equilibrium temperatures and emission on
+                 the device, three 256^2 maps per frequency.
+    Wall clock of each run in this process with the driver's own breakdown."""
+    import contextlib
+    import io
+    import shutil
+    import tempfile
+    from soc_b200 import asoc, synth
+    d = workdir or tempfile.mkdtemp(prefix="soc_c2_")
+    runs = {}
+    try:
+        for name in ("absorbed", "maps"):
+            t0 = time.perf_counter()
+            extra = "" if name == "absorbed" else ("CLT\nCLE\nmapping %d %d 1.0\ndirections 0.0 0.0\ndirections 90.0 0.0\ndirections 60.0 30.0\n" % (n, n))
+            ini, cloud = synth.write_model(d, n=n, nfreq=nfreq, bgpac=int(BGPAC_REQ), pspac=int(PSPAC_REQ), noabsorbed=(name == "maps"),
+                                           absorbed=(name == "absorbed"), maps=False, extra=extra)
+            if name == "maps":          # write_model(maps=False) writes `nomap`; this run has its own three directions
+                txt = open(ini).read().replace("nomap\n", "")
+                open(ini, "w").write(txt)
+            t_model = time.perf_counter() - t0
+            cwd = os.getcwd()
+            os.chdir(d)
+            try:
+                t0 = time.perf_counter()
+                with contextlib.redirect_stdout(io.StringIO()):
+                    asoc.main(["ASOC.py", "model.ini"], device_factory=device_factory)
+                wall = time.perf_counter() - t0
+            finally:
+                os.chdir(cwd)
+            t = dict(asoc.LAST_TIMINGS)
+            outputs = ("abs.data",) if name == "absorbed" else ("emit.data", "model.T", "map_dir_00.bin", "map_dir_01.bin", "map_dir_02.bin")
+            nbytes = int(sum(os.path.getsize(os.path.join(d, f)) for f in outputs if os.path.exists(os.path.join(d, f))))
+            packets = t.pop("packets", 0)
+            runs[name] = {"wall_s": round(wall, 3), "packets": packets, "packets_per_s": packets / wall, "cell_steps": t.pop("cell_steps", 0),
+                          "breakdown_s": {k: round(v, 3) for k, v in t.items()}, "output_bytes": nbytes,
+                          "model_files_written_in_s": round(t_model, 2)}
+    finally:
+        if workdir is None:
+            shutil.rmtree(d, ignore_errors=True)
+    runs["workload"] = ("bin/ASOC.py: %d^3 cloud, %d frequencies x (3e7 point-source + 3e7 background packets); run `absorbed` writes the "
+                        "absorbed file, run `maps` solves temperatures / emission and writes 3 maps of %dx%d px per frequency" % (n, nfreq, n, n))
+    return runs
+
+
 # ---------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -591,6 +642,11 @@ def run_ours(args):
             "stuck_packets": counts[3].item(),
             "extra_workloads": extras,
         }
+        if world == 1 and not args.no_driver:
+            try:
+                line["e2e_driver"] = driver_e2e()
+            except Exception as e:
+                line["e2e_driver"] = {"error": "%s: %s" % (type(e).__name__, e)}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_leg(w, seconds_target=10.0, tuned=False)
             tuned = cpu_leg(w, seconds_target=8.0, tuned=True)
@@ -612,6 +668,7 @@ def main():
     ap.add_argument("--agg-steps", type=int, default=24)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-driver", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

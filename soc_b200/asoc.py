@@ -271,6 +271,9 @@ def _opt_array(USER, ABU, AFABS, AFSCA, ifreq, first=0):
     return opt
 
 
+LAST_TIMINGS = {}          # wall-clock breakdown of the most recent main() in this process (seconds)
+
+
 def main(argv=None, device_factory=None):
     """`device_factory(ordinal)` returns the object that owns the device; default = the CUDA library."""
     argv = sys.argv if argv is None else argv
@@ -360,6 +363,8 @@ def main(argv=None, device_factory=None):
         HPBG = np.fromfile(USER.file_hpbg, np.float32).reshape(NFREQ, HPBG_NPIX) * np.float32(USER.scale_background)
 
     # ---- device: context, parameter block (the former -D macros, ASOC.py:344-362), grid --------------------
+    Tread = time.time() - t_start
+    t_ctx = time.time()
     ordinal = comm.local if comm.world > 1 else int(os.environ.get("SOC_DEVICE", "0"))
     dev = (device_factory or bk.Device)(ordinal)
     length = float("%.5e" % (USER.GL * PARSEC))
@@ -374,6 +379,8 @@ def main(argv=None, device_factory=None):
                    with_roi_load=int(USER.WITH_ROI_LOAD), with_roi_save=int(USER.WITH_ROI_SAVE), roi_map=int(USER.ROI_MAP),
                    ref_quirks=3 if 'REFQUIRKS' in USER.KEYS else 0)
     dev.set_grid(cloud)
+    dev.sync()
+    Tctx = time.time() - t_ctx          # CUDA context, library load, grid upload, parent / neighbour / brick tables
     # region of interest (ASOC.py:906-945): the external field to load, the file of photons entering ROI
     ROI_LOAD = ROI_SAVE = None
     ROI_LOAD_NELEM = ROI_SAVE_NPIX = 0
@@ -838,6 +845,7 @@ def main(argv=None, device_factory=None):
     # =============================================================================================================
     # absorbed file (ASOC.py:2782-2878), emitted file (:3971-3975)
     # =============================================================================================================
+    t_files = time.time()
     if fabs_on_device:
         comm.allreduce(dev, bk.BUF_FABS, CELLS * NFREQ)
         if root:
@@ -860,6 +868,7 @@ def main(argv=None, device_factory=None):
                 np.asarray([CELLS, NFREQ], np.int32).tofile(fpa)
                 FABSORBED.tofile(fpa)
         del FABSORBED
+    Tfiles = time.time() - t_files
     if ROI_SAVE is not None:
         ROI_SAVE.flush()
         del ROI_SAVE
@@ -1009,10 +1018,12 @@ def main(argv=None, device_factory=None):
                     fp.write('%6d  %12.4e  %12.4e\n' % (i, pscolden[i], pstau[i]))
     Tmap = time.time() - t0
 
+    t_files = time.time()
     if root and EMITTED is not None and not USER.MMAP_EMITTED and (not USER.NOSOLVE or USER.LOAD_TEMPERATURE):
         with open(USER.file_emitted, "wb") as fp:
             np.asarray([CELLS, REMIT_NFREQ], np.int32).tofile(fp)
             np.asarray(EMITTED, np.float32).tofile(fp)
+    Tfiles += time.time() - t_files
     c = dev.counters()
     if VERBOSE:
         print("        PUSH     %9.4f seconds" % Tpush)
@@ -1022,6 +1033,9 @@ def main(argv=None, device_factory=None):
         print("        MAPS     %9.4f seconds" % Tmap)
     dev.close()
     comm.close()
+    LAST_TIMINGS.clear()
+    LAST_TIMINGS.update(total=time.time() - t_start, read_inputs=Tread, context_and_grid=Tctx, push=Tpush, kernel=Tkernel, pull=Tpull,
+                        solve=Tsolve, maps=Tmap, write_files=Tfiles, packets=int(c.packets), cell_steps=int(c.steps))
     if root:
         print("@@ ASOC.py %.2f seconds WC" % (time.time() - t_start))
     return 0

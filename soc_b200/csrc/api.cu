@@ -629,7 +629,11 @@ static int sim_launch(soc_context *c, SimArgs &A, const char *who) {
         A.brick = sim_uses_bricks(A, c->rng_mode) ? 1 : 0;
         A.nbr = c->nbr;
         A.pend = c->pend; A.ahead = c->ahead;
-        if (const char *e = getenv("SOC_SCRAMBLE")) A.scramble = atoi(e) ? 1000003ull : 0ull;                    // experiment: packets in scattered order
+        // order of the work units: 0 = as numbered, 1 = background surface elements in 16 x 16 tiles (needs face edges that
+        // are multiples of 16), 2 = scattered (experiment)
+        A.scramble = 0ull;
+        if (const char *e = getenv("SOC_UNIT_ORDER")) { const int v = atoi(e); A.scramble = v == 2 ? 1000003ull : (unsigned long long)(v == 1); }   // tuning knob
+        if (A.scramble == 1ull && ((A.G.nx | A.G.ny | A.G.nz) & 15)) A.scramble = 0ull;
         A.slab_xy = A.G.nx * A.G.ny;
     }
     CU(cudaEventRecord(c->ev0, c->stream));

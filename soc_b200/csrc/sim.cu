@@ -751,6 +751,31 @@ __device__ __forceinline__ void lean_set_direction(const Box &b, LeanPk<BRICK> &
     f.upm = (ux ? 1 : 0) | (uy ? 2 : 0) | (uz ? 4 : 0);
 }
 
+// Order in which the work units of a launch are handed out (the packet a unit stands for keeps its Philox stream and its
+// emission, so the results do not depend on it -- only which packets are in flight together does).  Background launches:
+// the surface elements of a face are visited in 16 x 16 tiles instead of row by row, so that the ~1e5 packets in flight
+// start from a compact patch of the surface rather than a strip across it and share more L1 / L2 sectors.
+__device__ __forceinline__ unsigned long long unit_order(const SimArgs &A, unsigned long long u) {
+    if (A.scramble > 1) return (u * A.scramble) % (unsigned long long)A.nlocal;          // experiment: scattered order
+    if (A.scramble == 0 || A.kind != SIM_BG || A.world != 1) return u;
+    const GridDesc &G = A.G;
+    const unsigned batch = (unsigned)A.batch;
+    const unsigned long long id = u / batch;
+    const unsigned iii = (unsigned)(u - id * batch);
+    const unsigned long long round = id / (unsigned)G.area;
+    int e = (int)(id - round * (unsigned)G.area);
+    const int nyz = G.ny * G.nz, nxz = G.nx * G.nz;
+    int off, da;                                    // first element of the face, length of its rows
+    if (e < 2 * nyz)            { off = (e < nyz) ? 0 : nyz; da = G.ny; }
+    else if (e < 2 * nyz + 2 * nxz) { off = (e < 2 * nyz + nxz) ? 2 * nyz : 2 * nyz + nxz; da = G.nx; }
+    else                        { off = (e < 2 * nyz + 2 * nxz + G.nx * G.ny) ? 2 * nyz + 2 * nxz : 2 * nyz + 2 * nxz + G.nx * G.ny; da = G.nx; }
+    const int p = e - off, tpr = da >> 4;
+    const int t = p >> 8, w = p & 255;
+    const int a = ((t % tpr) << 4) | (w & 15), b = ((t / tpr) << 4) | (w >> 4);
+    e = off + b * da + a;
+    return ((round * (unsigned)G.area + (unsigned)e) * batch) + iii;
+}
+
 // work counters: 32-bit native shared-memory adds, spilled to the 64-bit global counter before they can wrap
 __device__ __forceinline__ void count_add(unsigned *s32, unsigned long long *g64, unsigned v) {
     const unsigned old = atomicAdd(s32, v);
@@ -797,7 +822,7 @@ __global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant_
                     f.rho = __ldg(dens + f.ind);
                 }
                 if (!DOM && u < (unsigned long long)A.nlocal) {
-                    const unsigned long long us = A.scramble ? (u * A.scramble) % (unsigned long long)A.nlocal : u;
+                    const unsigned long long us = unit_order(A, u);
                     const unsigned long long q = us * A.world + A.rank;
                     RngPhilox rng; rng.seed(A.phx, q);
                     Packet pk; pk.ind = -1; pk.level = 0; pk.eidx = -1; pk.rho = 0.0f;
@@ -1091,7 +1116,7 @@ __global__ void __launch_bounds__(256, CTAS) sim_ahead_kernel(const __grid_const
                     else f.rho = __ldg(dens + f.ind);
                 }
                 if (!DOM && u < (unsigned long long)A.nlocal) {
-                    const unsigned long long us = A.scramble ? (u * A.scramble) % (unsigned long long)A.nlocal : u;
+                    const unsigned long long us = unit_order(A, u);
                     const unsigned long long q = us * A.world + A.rank;
                     RngPhilox rng; rng.seed(A.phx, q);
                     Packet pk; pk.ind = -1; pk.level = 0; pk.eidx = -1; pk.rho = 0.0f;
