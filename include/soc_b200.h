@@ -20,6 +20,7 @@
  *                                           (kernel_ASOC.c:15, 831, 1223; ASOC.py:1317-1419, 1847)
  *   soc_build_opt                           host loop OPT = sum_d ABU*K_d + upload (ASOC.py:1146-1175)
  *   soc_absorbed_begin / _add / _finish     FABSORBED[:,f] += TMP and the final scaling loop
+ *   soc_split_absorbed                      kernel split_absorbed of kernel_A2E_MABU_aux.c (A2E_MABU.py:700-705)
  *                                           (ASOC.py:1482-1497, 2782-2878), kept on the device
  *   soc_eq_temperature / soc_emission       kernels EqTemperature / Emission / Emission2
  *     / soc_emission2                       (kernel_ASOC_aux.c:745, 793, 862; ASOC.py:2027-2040, 2154-2197)
@@ -205,6 +206,11 @@ int  soc_emission2(soc_context *ctx, int c0, int c1, int nfreq, const float *fre
  * cells with DENS <= nnnlimit (parents are links, i.e. <= 0) and copies the array to `host` (cells*nfreq floats;
  * NULL = leave it on the device, e.g. to all-reduce it first with finish_scale = 0). */
 int  soc_absorbed_begin(soc_context *ctx, int nfreq);
+/* Hand-off of the absorptions to the dust solver of one species (A2E_MABU.py:700-705, kernel split_absorbed of
+ * kernel_A2E_MABU_aux.c:3-24): host[cell, f] = FABS[cell, f] * rabs[f, idust] / sum_d ABU[cell, d] * rabs[f, d], on the
+ * [CELLS, nfreq] array in buffer FABS (left there by soc_absorbed_finish, or uploaded) and the abundances in buffer
+ * ABU [CELLS, ndust]; rabs = [nfreq, ndust] doubles.  Same arithmetic as the reference kernel. */
+int  soc_split_absorbed(soc_context *ctx, int idust, int ndust, int nfreq, const double *rabs, float *host);
 int  soc_absorbed_add(soc_context *ctx, int ifreq);
 int  soc_absorbed_finish(soc_context *ctx, float coeff0, float nnnlimit, int finish_scale, float *host);
 

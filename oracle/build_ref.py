@@ -183,6 +183,22 @@ def build_levels(cfg, force=False, verbose=False):
     return out
 
 
+def build_a2e(nfreq, ndust, force=False):
+    """kernel_A2E_MABU_aux.c (split_absorbed) as a library of its own; NFREQ / NDUST are its compile-time macros
+    (A2E_MABU.py:701)."""
+    out = os.path.join(OUTDIR, "libsocrefA_%d_%d.so" % (nfreq, ndust))
+    if os.path.exists(out) and not force:
+        return out
+    src = os.path.join(REFDIR, "kernel_A2E_MABU_aux.c")
+    if not os.path.exists(src):
+        return None
+    os.makedirs(OUTDIR, exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++17", "-fpermissive", "-w", "-O2", "-fopenmp", "-fPIC", "-ffp-contract=off", "-shared",
+                           "-I", REFDIR, "-I", SHIM, "-DNFREQ=%d" % nfreq, "-DNDUST=%d" % ndust,
+                           os.path.join(SHIM, "ref_a2e.cpp"), "-o", out])
+    return out
+
+
 if __name__ == "__main__":
     # tiny CLI: build_ref.py NX NY NZ LEVELS CELLS [KEY=VAL ...]
     a = sys.argv[1:]

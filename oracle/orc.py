@@ -328,3 +328,14 @@ def rng_stream_base(base, id_, n):
     lib().orc_rng_stream_base(C.c_uint64(base), C.c_int64(id_), C.c_int(n), out.ctypes.data_as(C.c_void_p),
                               st.ctypes.data_as(C.c_void_p))
     return st, out
+
+
+def split_absorbed(idust, rabs, abu, absorbed):
+    """kernel_A2E_MABU_aux.c split_absorbed on host arrays: rabs [nfreq, ndust] float64, abu [cells, ndust], absorbed [cells, nfreq]."""
+    rabs = np.ascontiguousarray(rabs, np.float64)
+    abu = np.ascontiguousarray(abu, np.float32)
+    a = np.ascontiguousarray(absorbed, np.float32)
+    out = np.zeros_like(a)
+    lib().orc_split_absorbed(C.c_int(idust), C.c_int(a.shape[0]), C.c_int(a.shape[1]), C.c_int(abu.shape[1]),
+                           rabs.ctypes.data_as(C.POINTER(C.c_double)), _fp(abu), _fp(a), _fp(out))
+    return out

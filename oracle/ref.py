@@ -311,3 +311,18 @@ def rng_stream(lib, seed, id_, gsize, n):
     lib.ref_rng_stream(C.c_float(seed), C.c_long(id_), C.c_long(gsize), C.c_int(n),
                        out.ctypes.data_as(C.c_void_p), st.ctypes.data_as(C.c_void_p))
     return st, out
+
+
+def split_absorbed(idust, rabs, abu, absorbed):
+    """The reference's split_absorbed kernel (kernel_A2E_MABU_aux.c) on host arrays; None where the library cannot be built."""
+    rabs = np.ascontiguousarray(rabs, np.float64)
+    abu = np.ascontiguousarray(abu, np.float32)
+    a = np.ascontiguousarray(absorbed, np.float32)
+    path = build_ref.build_a2e(a.shape[1], abu.shape[1])
+    if path is None:
+        return None
+    out = np.zeros_like(a)
+    n = a.shape[0]
+    C.CDLL(path).ref_split_absorbed(C.c_int(((n + 15) // 16) * 16), C.c_int(idust), C.c_int(n), rabs.ctypes.data_as(C.POINTER(C.c_double)),
+                                    _fp(abu), _fp(a), _fp(out))
+    return out

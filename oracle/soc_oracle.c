@@ -813,6 +813,19 @@ void orc_emission2(const OrcParams *P, int c0, int c1, int nfreq, const float *f
                 (2.79639459e-20f * P->factor) * fabs_[ifreq] * (freq[ifreq] * freq[ifreq] / (expf(4.7995074e-11f * freq[ifreq] / t[icell]) - 1.0f)) / P->length;
 }
 
+/* split_absorbed: kernel_A2E_MABU_aux.c:3-24 (A2E_MABU.py:700-705) -- the hand-off of the absorbed file to the dust solver
+ * of one species: OUT[cell, f] = IN[cell, f] * RABS[f, IDUST] / sum_d ABU[cell, d] * RABS[f, d].  RABS is double; `den` is a
+ * float that takes the double products one after the other, the quotient is formed in double and stored as float. */
+void orc_split_absorbed(int idust, int n, int nfreq, int ndust, const double *rabs, const float *abu, const float *in, float *out) {
+    #pragma omp parallel for
+    for (int icell = 0; icell < n; icell++)
+        for (int ifreq = 0; ifreq < nfreq; ifreq++) {
+            float den = 0.0f;
+            for (int d = 0; d < ndust; d++) den += abu[(long)icell * ndust + d] * rabs[ifreq * ndust + d];
+            out[(long)icell * nfreq + ifreq] = in[(long)icell * nfreq + ifreq] * rabs[ifreq * ndust + idust] / den;
+        }
+}
+
 /* =================================================================================================
  * Map ray-tracer (kernel_ASOC_map.c:496-875; MAP_INTERPOLATION==0, ROI_MAP==0)
  * ================================================================================================= */

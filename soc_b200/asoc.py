@@ -419,10 +419,14 @@ def main(argv=None, device_factory=None):
     Tkernel = Tpush = Tpull = Tsolve = Tmap = 0.0
     use_int = (not USER.NOABSORBED) or USER.SAVE_INTENSITY in (1, 2)
 
-    EMITTED = open_emitted(USER, CELLS, REMIT_NFREQ) if root else None
+    # the [CELLS, NFREQ] emission array is needed by the cell-emission iterations, the temperature solution and the maps; a
+    # pure absorption run (nosolve, nomap, no cell packets) neither reads nor writes it (the reference creates the file anyway)
+    need_emitted = not (USER.NOSOLVE and USER.NOMAP and CLPAC < 1 and not USER.LOAD_TEMPERATURE)
+    EMITTED = open_emitted(USER, CELLS, REMIT_NFREQ) if (root and need_emitted) else None
     comm.barrier()
-    if not root:
+    if not root and need_emitted:
         EMITTED = np.fromfile(USER.file_emitted, np.float32, offset=8).reshape(CELLS, REMIT_NFREQ)
+    emission_on_device = False          # BUF_TNEW holds the temperatures EMITTED was computed from (single dust)
     FABSORBED = None
     # [CELLS, NFREQ] absorptions: kept on the device and scaled / transposed there when it fits
     # (soc_absorbed_*), else accumulated on the host per frequency like the reference (ASOC.py:1482-1497)
@@ -469,7 +473,9 @@ def main(argv=None, device_factory=None):
         """EMITTED[cells, freq] from temperatures.  Default: kernel Emission2 in batches of cells, all frequencies
         per launch and one contiguous copy per batch (ASOC.py:2157-2180, the reference's EBATCH path); with the
         key EMISSION1 one launch of kernel Emission and one strided host copy per frequency (ASOC.py:2185-2197)."""
+        nonlocal emission_on_device
         dev.upload(bk.BUF_TNEW, np.ascontiguousarray(T, np.float32))
+        emission_on_device = True
         if 'EMISSION1' in USER.KEYS:
             for ifreq in range(REMIT_I1, REMIT_I2 + 1):
                 dev.emission(float(FFREQ[ifreq]), float(AFABS[0][ifreq]))
@@ -974,7 +980,11 @@ def main(argv=None, device_factory=None):
             if not save_spe and save_tau == 0 and save_colden == 0:
                 continue
             kabs, ksca = set_opacity(IFREQ)
-            if save_spe:
+            if save_spe and emission_on_device and 'HOSTEMIT' not in USER.KEYS:
+                # the emission of this frequency straight from the temperatures on the device (kernel Emission is linear in
+                # its FABS argument) instead of a strided host gather of EMITTED[:, f] and a 4*CELLS-byte upload per frequency
+                dev.emission(float(FREQ), float(np.float32(AFABS[0][IFREQ]) * np.float32(KK * FREQ)))
+            elif save_spe:
                 EMIT[:] = KK * FREQ * EMITTED[:, IFREQ - REMIT_I1]
                 dev.upload(bk.BUF_EMIT, EMIT)
             elif dev.device_ptr(bk.BUF_EMIT)[1] != 4 * CELLS:

@@ -42,7 +42,7 @@ class SocCounters(C.Structure):
 
 
 _EXPORTS = """soc_last_error soc_version soc_create soc_destroy soc_sync soc_set_params soc_set_grid soc_set_rng_mode
-soc_build_opt soc_set_shard soc_set_tuning soc_set_geometry soc_set_layout soc_set_domains soc_set_roi soc_upload soc_download soc_clear soc_device_ptr soc_zero_amc soc_sim_pb soc_sim_hp
+soc_build_opt soc_split_absorbed soc_set_shard soc_set_tuning soc_set_geometry soc_set_layout soc_set_domains soc_set_roi soc_upload soc_download soc_clear soc_device_ptr soc_zero_amc soc_sim_pb soc_sim_hp
 soc_sim_cl soc_absorbed_begin soc_absorbed_add soc_absorbed_finish soc_eq_temperature soc_emission soc_emission2 soc_mapping soc_mapping_levels soc_healpix_mapping soc_ps_tau soc_sca_zero_out soc_sca_ps soc_sca_pb soc_sca_hp soc_sca_cl
 soc_get_counters soc_reset_counters soc_last_launch_ms soc_last_kernel soc_stream""".split()
 
@@ -75,6 +75,7 @@ def load_library(path=None):
     L.soc_set_roi.argtypes = [vp, vp, i, i, vp]
     L.soc_upload.argtypes = [vp, i, vp, C.c_size_t]
     L.soc_build_opt.argtypes = [vp, i, fp, fp, i, i]
+    L.soc_split_absorbed.argtypes = [vp, i, i, i, C.POINTER(C.c_double), vp]
     L.soc_download.argtypes = [vp, i, vp, C.c_size_t]
     L.soc_clear.argtypes = [vp, i, C.c_size_t]
     L.soc_device_ptr.argtypes = [vp, i, C.POINTER(C.c_size_t)]
@@ -197,6 +198,15 @@ class Device:
         s = np.ascontiguousarray(ksca, np.float32)
         self._ck(self.L.soc_build_opt(self.ctx, len(a), a.ctypes.data_as(C.POINTER(C.c_float)), s.ctypes.data_as(C.POINTER(C.c_float)),
                                       int(first), 1 if single_abu else 0))
+
+    def split_absorbed(self, idust, rabs, cells):
+        """Absorptions of species `idust` from the [cells, nfreq] array in buffer FABS and the abundances in buffer ABU
+        (kernel_A2E_MABU_aux.c split_absorbed); rabs = [nfreq, ndust] float64."""
+        r = np.ascontiguousarray(rabs, np.float64)
+        out = np.empty((cells, r.shape[0]), np.float32)
+        self._ck(self.L.soc_split_absorbed(self.ctx, int(idust), r.shape[1], r.shape[0], r.ctypes.data_as(C.POINTER(C.c_double)),
+                                           out.ctypes.data))
+        return out
 
     def set_layout(self, mode):
         self._ck(self.L.soc_set_layout(self.ctx, int(mode)))

@@ -839,6 +839,31 @@ int soc_absorbed_finish(soc_context *c, float coeff0, float nnnlimit, int finish
     return SOC_OK;
 }
 
+int soc_split_absorbed(soc_context *c, int idust, int ndust, int nfreq, const double *rabs, float *host) {
+    NEED_CTX(c);
+    if (!c->have_grid) return fail(SOC_ERR_STATE, "soc_split_absorbed: grid first");
+    if (ndust < 1 || idust < 0 || idust >= ndust || nfreq < 1 || rabs == nullptr || host == nullptr) return fail(SOC_ERR_ARG, "soc_split_absorbed: bad arguments");
+    const size_t cells = (size_t)c->G.cells, nb = cells * (size_t)nfreq * 4;
+    int r;
+    if ((r = need(c, SOC_BUF_FABS, nb, "soc_split_absorbed")) != SOC_OK) return r;
+    if ((r = need(c, SOC_BUF_ABU, cells * (size_t)ndust * 4, "soc_split_absorbed")) != SOC_OK) return r;
+    const size_t rb = (size_t)nfreq * ndust * sizeof(double);
+    if (c->scratch_bytes < nb + rb) {
+        if (c->scratch) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->scratch)); c->scratch = nullptr; c->scratch_bytes = 0; }
+        CU(cudaMalloc(&c->scratch, nb + rb));
+        c->scratch_bytes = nb + rb;
+    }
+    double *d_rabs = reinterpret_cast<double *>(c->scratch);                     // 8-byte aligned: first
+    float *d_out = reinterpret_cast<float *>(reinterpret_cast<char *>(c->scratch) + rb);
+    CU(cudaMemcpyAsync(d_rabs, rabs, rb, cudaMemcpyHostToDevice, c->stream));
+    launch_split_absorbed(idust, (long long)cells, nfreq, ndust, d_rabs, dptr<float>(c, SOC_BUF_ABU), dptr<float>(c, SOC_BUF_FABS), d_out, c->stream);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(host, d_out, nb, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return SOC_OK;
+}
+
 int soc_emission(soc_context *c, float freq, float fabs_) {
     NEED_CTX(c);
     if (!c->have_grid || !c->have_params) return fail(SOC_ERR_STATE, "soc_emission: grid and params first");

@@ -157,6 +157,28 @@ void launch_build_opt(const float *abu, float *opt, long long cells, int ndust, 
                                                                                   half, K);
 }
 
+// split_absorbed (kernel_A2E_MABU_aux.c:3-24, A2E_MABU.py:700-705): the absorbed array handed to the dust solver of species
+// IDUST: OUT[cell, f] = IN[cell, f] * RABS[f, IDUST] / sum_d ABU[cell, d] * RABS[f, d].  Same precision as the reference: RABS
+// double, `den` a float that takes the double products one by one, quotient in double, result float.  One thread per
+// (cell, frequency); both arrays are streamed once.
+__global__ void __launch_bounds__(256) split_absorbed_kernel(int idust, long long cells, int nfreq, int ndust, const double *__restrict__ rabs,
+                                                             const float *__restrict__ abu, const float *__restrict__ in, float *__restrict__ out) {
+    const long long n = cells * nfreq, stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const long long icell = i / nfreq;
+        const int ifreq = (int)(i - icell * nfreq);
+        float den = 0.0f;
+        for (int d = 0; d < ndust; d++) den = (float)__dadd_rn((double)den, __dmul_rn((double)abu[icell * ndust + d], rabs[ifreq * ndust + d]));
+        out[i] = (float)__ddiv_rn(__dmul_rn((double)in[i], rabs[ifreq * ndust + idust]), (double)den);
+    }
+}
+void launch_split_absorbed(int idust, long long cells, int nfreq, int ndust, const double *rabs, const float *abu, const float *in, float *out,
+                           cudaStream_t stream) {
+    long long b = (cells * nfreq + 255) / 256;
+    const long long cap = 148LL * 16;
+    split_absorbed_kernel<<<(int)(b < 1 ? 1 : (b > cap ? cap : b)), 256, 0, stream>>>(idust, cells, nfreq, ndust, rabs, abu, in, out);
+}
+
 // Neighbour table of linkwalk.cuh: NBR[6*cell + face], face = 2*axis + (towards +axis).  For every cell the cell of
 // the same level behind the face if the hierarchy has it (possibly refined further), else the coarser leaf covering it.
 __global__ void neighbours_kernel(GridDesc G, int *__restrict__ nbr) {

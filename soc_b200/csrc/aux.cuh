@@ -14,5 +14,7 @@ void launch_emission2(int c0, int c1, int nfreq, float factor, float length, con
 #define SOC_MAX_DUSTS 32
 void launch_build_opt(const float *abu, float *opt, long long cells, int ndust, int first, int single_abu, int half,
                       const float *kabs, const float *ksca, cudaStream_t stream);   // OPT from ABU on the device
+void launch_split_absorbed(int idust, long long cells, int nfreq, int ndust, const double *rabs, const float *abu, const float *in, float *out,
+                           cudaStream_t stream);   // kernel_A2E_MABU_aux.c split_absorbed
 void launch_half_to_float(const void *src, float *dst, long long n, cudaStream_t stream);
 void launch_neighbours(const GridDesc &G, int *nbr, cudaStream_t stream);      // neighbour table of linkwalk.cuh, [6*cells]

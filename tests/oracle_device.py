@@ -118,6 +118,10 @@ class OracleDevice:
             opt = opt.astype(np.float16).astype(np.float32)
         self.buf[bk.BUF_OPT] = opt.reshape(-1)
 
+    def split_absorbed(self, idust, rabs, cells):
+        rabs = np.ascontiguousarray(rabs, np.float64)
+        return orc.split_absorbed(idust, rabs, self.buf[bk.BUF_ABU].reshape(cells, -1), self.buf[bk.BUF_FABS].reshape(cells, -1))
+
     def download(self, b, n, dtype=np.float32, out=None):
         src = self.host_view(b, n)
         if out is None:

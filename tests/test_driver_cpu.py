@@ -145,6 +145,28 @@ def test_two_gloo_ranks_absorbed_file(tmp_path, mode):
         assert np.abs(t2[ok] / t1[ok] - 1.0).max() < 0.03
 
 
+def test_absorbed_file_hand_off_per_species(tmp_path):
+    """soc_b200.a2e_handoff: the absorbed file of a two-species run split into the files the dust solver of each species
+    reads (A2E_MABU.py:700-705); abundance-weighted shares add up to the mixture's absorptions."""
+    from soc_b200.a2e_handoff import split_absorbed_file
+    from soc_b200.formats import read_cells_freq_file
+    cloud = _run(tmp_path, n=8, bgpac=40000, two_dusts=True, noabsorbed=False, absorbed=True, maps=False)
+    a = read_cells_freq_file(str(tmp_path / "abs.data")).astype(np.float64)
+    rng = np.random.default_rng(2)
+    rabs = 1e-21 * (0.5 + rng.random((a.shape[1], 2)))
+    abus = [str(tmp_path / "abu1.bin"), str(tmp_path / "abu2.bin")]
+    parts = []
+    for d in range(2):
+        out = str(tmp_path / ("abs_%d.data" % d))
+        split_absorbed_file(str(tmp_path / "abs.data"), rabs, d, out, abus, batch=200, device_factory=OracleDevice)
+        parts.append(read_cells_freq_file(out).astype(np.float64))
+        assert parts[-1].shape == a.shape
+    abu = np.stack([np.fromfile(f, np.float32, cloud.CELLS) for f in abus], axis=1).astype(np.float64)
+    ok = a > 0
+    tot = parts[0] * abu[:, :1] + parts[1] * abu[:, 1:]
+    assert np.abs(tot[ok] / a[ok] - 1.0).max() < 1e-5
+
+
 def test_scattered_light_driver_writes_outcoming(tmp_path):
     from soc_b200 import asocs
     from soc_b200.formats import read_outcoming

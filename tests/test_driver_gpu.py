@@ -157,3 +157,16 @@ def test_per_level_maps_sum_to_the_ordinary_map(tmp_path):
     lev = np.fromfile(str(tmp_path / "lev" / "map_dir_01_H.bin"), np.float32, offset=16).reshape(int(hdr[2]), cloud.LEVELS, 6, 6)
     full = read_map_file(str(tmp_path / "all" / "map_dir_01.bin"))
     assert (lev[:, 1:] > 0).any() and np.allclose(lev.sum(axis=1), full, rtol=3e-5, atol=0)
+
+
+@pytest.mark.parametrize("extra", ["reference 1\n", "ali 1\n", "reference 1\nali 1\nemweight 1\n"])
+def test_cell_emission_iterations_reference_field_and_ali(tmp_path, extra):
+    """Iterated dust re-emission with the reference-field bookkeeping (`reference 1`: only the change of the emission is
+    simulated), accelerated lambda iterations (`ali 1`: absorptions in the emitting cell go to XAB) and emission weighting,
+    through the driver: CUDA library vs oracle device (ASOC.py:1594-1990)."""
+    kw = dict(n=10, bgpac=200000, cellpac=10 ** 3 * 20, iterations=3, maps=False, extra=extra)
+    _run(tmp_path / "gpu", None, **kw)
+    _run(tmp_path / "cpu", OracleDevice, **kw)
+    Tg, Tc = read_otfile(str(tmp_path / "gpu" / "model.T")), read_otfile(str(tmp_path / "cpu" / "model.T"))
+    assert np.isfinite(Tg).all() and (Tg > 2.0).all()
+    assert np.abs(Tg / Tc - 1.0).mean() < 0.01 and np.abs(Tg / Tc - 1.0).max() < 0.08

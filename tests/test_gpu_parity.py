@@ -179,6 +179,28 @@ def test_opt_built_on_the_device_equals_the_host_loop(mode):
     B.close()
 
 
+def test_split_absorbed_equals_the_oracle():
+    """soc_split_absorbed (hand-off of the absorptions to the dust solver of one species, kernel_A2E_MABU_aux.c:3-24)
+    against the oracle restatement, which is pinned bit for bit to the reference kernel: identical bits."""
+    from oracle import orc
+    from soc_b200 import backend
+    cloud = synth.octree_cloud(6, 3, refine_fraction=0.2, seed=3)
+    rng = np.random.default_rng(1)
+    nfreq, ndust = 9, 3
+    abu = (0.1 + rng.random((cloud.CELLS, ndust))).astype(np.float32)
+    rabs = 1e-21 * (0.5 + rng.random((nfreq, ndust)))
+    a = (1e-3 * rng.random((cloud.CELLS, nfreq))).astype(np.float32)
+    a[cloud.DENS <= 0] = -1e20
+    B = _backend(cloud, backend.RNG_PACKET)
+    B.dev.upload(backend.BUF_FABS, a.reshape(-1))
+    B.dev.upload(backend.BUF_ABU, abu.reshape(-1))
+    for idust in range(ndust):
+        got = B.dev.split_absorbed(idust, rabs, cloud.CELLS)
+        want = orc.split_absorbed(idust, rabs, abu, a)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (idust, np.abs(got - want).max())
+    B.close()
+
+
 def _repeat(X, runner_factory, K, key="tabs"):
     """K repetitions with different seeds; `key` may be a tuple of output names (returns a dict of arrays then)."""
     keys = key if isinstance(key, tuple) else (key,)

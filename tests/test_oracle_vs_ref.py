@@ -76,3 +76,23 @@ def test_emission2_matches_reference():
     fabs_ = (1e-6 * (freq / 1e12) ** 1.8).astype(np.float32)
     a, b = O.emission2(30, cloud.CELLS - 9, freq, fabs_, t), R.emission2(30, cloud.CELLS - 9, freq, fabs_, t)
     assert a.shape == b.shape and np.array_equal(a, b)
+
+
+def test_split_absorbed_matches_reference():
+    """split_absorbed (kernel_A2E_MABU_aux.c:3-24, the hand-off of the absorbed file to the dust solver of one species):
+    oracle == reference kernel, bit for bit, parent markers (-1e20) included."""
+    rng = np.random.default_rng(1)
+    cells, nfreq, ndust = 5000, 7, 3
+    abu = (0.1 + rng.random((cells, ndust))).astype(np.float32)
+    rabs = 1e-21 * (0.5 + rng.random((nfreq, ndust)))
+    a = (1e-3 * rng.random((cells, nfreq))).astype(np.float32)
+    a[::17] = -1e20
+    for idust in range(ndust):
+        o, r = orc.split_absorbed(idust, rabs, abu, a), ref.split_absorbed(idust, rabs, abu, a)
+        assert r is not None and np.array_equal(o.view(np.uint32), r.view(np.uint32))
+    # a single species with abundance 1 is handed its absorptions unchanged; the shares of all species add up to the input
+    one = orc.split_absorbed(0, rabs[:, :1], np.ones((cells, 1), np.float32), a)
+    assert np.allclose(one, a, rtol=1e-6, atol=0)          # `den` is the float-rounded cross section
+    tot = sum(orc.split_absorbed(d, rabs, abu, a).astype(np.float64) * abu[:, d:d + 1] for d in range(ndust))
+    ok = a > 0
+    assert np.abs(tot[ok] / a[ok] - 1.0).max() < 1e-6
