@@ -1,5 +1,7 @@
-"""Development tool: the ASOC driver on 1 GPU and on 2 GPUs (torchrun, NCCL all-reduce of the absorption arrays) for the same
-model; the absorbed file and the temperatures must agree to the order of float additions (same Philox streams)."""
+"""Development tool: the ASOC driver on 1 GPU and on 2 GPUs (torchrun, NCCL) for the same model; the absorbed file and
+the temperatures must agree to the order of float additions (same Philox streams).  The constant sources are sharded by
+frequency by default (rank r runs frequencies r, r+2, ... whole: no per-frequency collective), by packet index with the
+ini key PACKETSHARD; both are run."""
 import os
 import subprocess
 import sys
@@ -23,12 +25,13 @@ def pair(name, script="ASOC.py", **kw):
     return os.path.join(base, name, "one"), os.path.join(base, name, "two")
 
 
-# absorbed file (per-frequency absorptions, all-reduced per frequency)
-d1, d2 = pair("abs", n=16, bgpac=400000, pspac=330000, noabsorbed=False, absorbed=True, maps=False)
-a1 = read_cells_freq_file(os.path.join(d1, "abs.data")).astype(np.float64)
-a2 = read_cells_freq_file(os.path.join(d2, "abs.data")).astype(np.float64)
-print("absorbed: max rel diff %.3e (sum %.6e vs %.6e)" % (np.abs(a1 - a2).max() / np.abs(a1).max(), a1.sum(), a2.sum()))
-assert np.abs(a1 - a2).max() <= 1e-4 * np.abs(a1).max()
+# absorbed file: the [CELLS, NFREQ] array stays on each rank's device and is all-reduced once at the end
+for name, extra in (("abs_freqshard", ""), ("abs_packetshard", "PACKETSHARD\n")):
+    d1, d2 = pair(name, n=16, bgpac=400000, pspac=330000, noabsorbed=False, absorbed=True, maps=False, extra=extra)
+    a1 = read_cells_freq_file(os.path.join(d1, "abs.data")).astype(np.float64)
+    a2 = read_cells_freq_file(os.path.join(d2, "abs.data")).astype(np.float64)
+    print("absorbed (%s): max rel diff %.3e (sum %.6e vs %.6e)" % (name, np.abs(a1 - a2).max() / np.abs(a1).max(), a1.sum(), a2.sum()))
+    assert np.abs(a1 - a2).max() <= 1e-4 * np.abs(a1).max()
 # integrated absorptions -> temperatures -> maps, octree
 d1, d2 = pair("temp", n=8, octree=True, bgpac=200000, pspac=330000, extra="CLT\nCLE\n")
 t1, t2 = read_otfile(os.path.join(d1, "model.T")), read_otfile(os.path.join(d2, "model.T"))
