@@ -485,9 +485,11 @@ def test_domain_tiled_propagation_equals_whole_grid(kind):
         assert abs(a.sum() - b.sum()) <= 3e-5 * a.sum()
 
 
-def test_domain_tiled_propagation_at_512():
+@pytest.mark.parametrize("kind", ["bg", "ps"])
+def test_domain_tiled_propagation_at_512(kind):
     """512^3 (BASELINE.json configs 4/5): the automatic domain mode (2 x 2 x 2 boxes of 256^3) against the whole-grid
-    look-ahead kernel, one background launch: same packets, same paths."""
+    look-ahead kernel (plain adds for the background launch, the shared-memory-tile variant for the point source, which sits
+    on the corner of the eight boxes): same packets, same paths."""
     from soc_b200 import backend
     n = 512
     cloud = synth.regular_cloud(n)
@@ -496,10 +498,15 @@ def test_domain_tiled_propagation_at_512():
     kabs, ksca = 3.0 / n, 5.0 / n
     res = []
     for edge in (-1, 0):
-        B = _backend(cloud, backend.RNG_PACKET)
+        B = _backend(cloud, backend.RNG_PACKET, **(dict(no_ps=1) if kind == "ps" else {}))
         B.dev.set_domains(edge)
         B.zero(0)
-        B.sim_pb(glob, 1, glob, 1, 0.7, 1.0, 1.0, abs_=kabs, sca=ksca, dsc=dsc, csc=csc)
+        if kind == "ps":
+            B.sim_pb(32768, 0, 32768 * 100, 100, 0.7, 0.0, 1.0, abs_=kabs, sca=ksca, dsc=dsc, csc=csc,
+                     pspos=np.array([0.5 * n + 0.3] * 3, np.float32), ps=np.ones(1, np.float32))
+            assert ("domains" in B.dev.last_kernel()) == (edge == 0) and (edge == 0 or "sim_ahead_kernel<DEP_TILE" in B.dev.last_kernel())
+        else:
+            B.sim_pb(glob, 1, glob, 1, 0.7, 1.0, 1.0, abs_=kabs, sca=ksca, dsc=dsc, csc=csc)
         c = B.counters
         res.append((B.tabs.astype(np.float64), c.packets, c.steps, c.scatterings, c.reserved[0]))
         B.close()
@@ -507,7 +514,8 @@ def test_domain_tiled_propagation_at_512():
     # the last parked packets are finished by the general kernel (true division instead of rcp.approx at a scattering):
     # a path may flip at a cell face by rounding
     assert a[1] == b[1] and abs(a[2] - b[2]) <= 1e-6 * a[2] and abs(a[3] - b[3]) <= 1e-5 * a[3] and a[4] == 0 and b[4] == 0, (a[1:], b[1:])
-    assert abs(a[0].sum() - b[0].sum()) <= 2e-6 * a[0].sum()
+    # (the cell of the point source takes 3e6 adds: float32 sums in a different grouping)
+    assert abs(a[0].sum() - b[0].sum()) <= (2e-6 if kind == "bg" else 3e-5) * a[0].sum()
     assert (np.abs(a[0] - b[0]) > 1e-4 * a[0].max()).mean() < 1e-5
 
 
