@@ -437,6 +437,13 @@ __device__ __forceinline__ QPk q_load(const QPk *p) {
     d[0] = __ldcs(s); d[1] = __ldcs(s + 1); d[2] = __ldcs(s + 2); d[3] = __ldcs(s + 3);      // read once: streaming
     return v;
 }
+__device__ __forceinline__ QPk q_load_shared(const QPk *p) {
+    QPk v;
+    const float4 *s = reinterpret_cast<const float4 *>(p);
+    float4 *d = reinterpret_cast<float4 *>(&v);
+    d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
+    return v;
+}
 // parks the packet in the queue of the domain that holds cell (ix,iy,iz)
 __device__ __forceinline__ void q_push(const SimArgs &A, const QPk &v) {
     const int d = ((v.iz / A.dsize[2]) * A.dsplit[1] + v.iy / A.dsize[1]) * A.dsplit[0] + v.ix / A.dsize[0];
@@ -456,6 +463,30 @@ __device__ __forceinline__ void q_push_warp(const SimArgs &A, const QPk &v, bool
     if (lane == leader) base = atomicAdd(A.q_tail + d, (unsigned)__popc(peers));
     base = __shfl_sync(peers, base, leader);
     q_store(A.q_base + (size_t)d * (size_t)A.q_cap + base + __popc(peers & ((1u << lane) - 1u)), v);
+}
+
+// Parked packets are staged per warp in shared memory and leave in groups: the slot request of q_push_warp is an atomic
+// WITH a return value, i.e. a full round trip to the L2 for the whole warp -- paid once per ~1.5 parked packets it was 18 %
+// of the stall samples of the domain kernels at 512^3 (ncu, SHFL after the ATOMG); staged, it is paid once per Q_STAGE_N.
+#define Q_STAGE_N 16
+__device__ __forceinline__ void q_stage_flush(const SimArgs &A, const QPk *stage, int &n) {
+    __syncwarp();
+    const int lane = threadIdx.x & 31;
+    const bool have = lane < n;
+    QPk v; v.ix = v.iy = v.iz = 0;
+    if (have) v = q_load_shared(stage + lane);
+    q_push_warp(A, v, have);
+    __syncwarp();
+    n = 0;
+}
+// every lane of the warp calls; `n` (entries staged so far) is warp-uniform
+__device__ __forceinline__ void q_stage_push(const SimArgs &A, QPk *stage, int &n, const QPk &v, bool have) {
+    const unsigned pm = __ballot_sync(FULL, have);
+    const int k = __popc(pm);
+    if (k > Q_STAGE_N) { q_push_warp(A, v, have); return; }
+    if (n + k > Q_STAGE_N) q_stage_flush(A, stage, n);
+    if (have) q_store(stage + n + __popc(pm & ((1u << (threadIdx.x & 31)) - 1u)), v);
+    n += k;
 }
 
 // DEP: accumulation engine (DepositMode).  GENERAL = false drops the per-cell opacities, the intensity vector,
@@ -788,6 +819,9 @@ __global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant_
     __shared__ float s_pend[PEND ? 4 * 256 : 1];
     int pend_h = -1;
     __shared__ unsigned s_cnt[4];
+    __shared__ __align__(16) QPk s_stage[DOM ? 8 * Q_STAGE_N : 1];     // parked packets of each warp (q_stage_push)
+    QPk *const stage = s_stage + (DOM ? (threadIdx.x >> 5) * Q_STAGE_N : 0);
+    int nstage = 0;
     if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
     float *tile = nullptr;
     if (DEP == DEP_TILE) tile = tile_begin(A, smem); else __syncthreads();
@@ -999,11 +1033,11 @@ __global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant_
             o.ix = (f.upm & 1) ? box.hix - f.cx : box.lox + f.cx; o.iy = (f.upm & 2) ? box.hiy - f.cy : box.loy + f.cy;
             o.iz = (f.upm & 4) ? box.hiz - f.cz : box.loz + f.cz;
             o.upm = (unsigned)f.upm; o.sn = f.sn; o.u = f.u; o.pad = 0u;
-            if (!parked) { o.ix = box.lox; o.iy = box.loy; o.iz = box.loz; }
-            q_push_warp(A, o, parked);
+            q_stage_push(A, stage, nstage, o, parked);
         }
         }
     }
+    if (DOM) q_stage_flush(A, stage, nstage);
     if (PEND && pend_h >= 0) {
         const float *slot = s_pend + threadIdx.x;
         atomicAdd(reinterpret_cast<float4 *>(A.acc) + pend_h, make_float4(slot[0], slot[256], slot[512], slot[768]));
@@ -1074,6 +1108,9 @@ __global__ void __launch_bounds__(256, CTAS) sim_ahead_kernel(const __grid_const
     __shared__ float smem[DEP == DEP_TILE ? SOC_TILE_CELLS : 1];
     __shared__ __align__(8) float s_ring[(KAPPA ? 4 : 2) * 256];   // slot s of lane t: s_ring[s * 256 + t] (float or float2 units)
     __shared__ unsigned s_cnt[4];
+    __shared__ __align__(16) QPk s_stage[DOM ? 8 * Q_STAGE_N : 1];     // parked packets of each warp (q_stage_push)
+    QPk *const stage = s_stage + (DOM ? (threadIdx.x >> 5) * Q_STAGE_N : 0);
+    int nstage = 0;
     if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
     float *tile = nullptr;
     if (DEP == DEP_TILE) tile = tile_begin(A, smem); else __syncthreads();
@@ -1283,11 +1320,11 @@ __global__ void __launch_bounds__(256, CTAS) sim_ahead_kernel(const __grid_const
             o.ix = (st & 1u) ? box.hix - f.cx : box.lox + f.cx; o.iy = (st & 2u) ? box.hiy - f.cy : box.loy + f.cy;
             o.iz = (st & 4u) ? box.hiz - f.cz : box.loz + f.cz;
             o.upm = st & AH_UPM; o.sn = f.sn; o.u = f.u; o.pad = 0u;
-            if (!parked) { o.ix = box.lox; o.iy = box.loy; o.iz = box.loz; }
-            q_push_warp(A, o, parked);
+            q_stage_push(A, stage, nstage, o, parked);
         }
         }
     }
+    if (DOM) q_stage_flush(A, stage, nstage);
     if (DEP == DEP_TILE) {
         __syncthreads();
         for (int i = threadIdx.x; i < SOC_TILE_CELLS; i += blockDim.x) {
