@@ -22,7 +22,8 @@ the background, read-back of the per-frequency absorptions.
   extra_workloads : short runs of the other BASELINE.json configurations outside the timed headline -- 512^3
                     (configs 4/5), 256^3 with per-cell opacities (config 4 physics), the ~1e7-cell octree absorption
                     run and its scattered-light launch (config 3) -- each with its roofline fraction and the
-                    reference kernels' rate on the host cores (kind "reference").  N > 1: the 512^3 line only.
+                    reference kernels' rate on the host cores (kind "reference"); and configs[4] itself: 512^3 with
+                    1e9 packets per frequency (one step, ~5 s on one GPU).  N > 1: the two 512^3 lines only (strong scaling).
 """
 import argparse
 import json
@@ -48,13 +49,13 @@ ALG_BYTES_PER_STEP = 20           # DENS gather 4 B + TABS RMW 8 B + INT RMW 8 B
 REF_OPTS = dict(no_ps=1, noabsorbed=0)
 
 
-def make_workload(n=N_GRID):
+def make_workload(n=N_GRID, pspac=PSPAC_REQ, bgpac_req=BGPAC_REQ):
     from soc_b200 import synth, hostmath
     cloud = synth.regular_cloud(n)
     dsc, csc = synth.hg_tables(0.6, BINS)
     k = 5.0 / n                                   # ABS = SCA = 5/N per cell and unit density
-    ps_batch = int(max(1, PSPAC_REQ / GLOBAL_PS))             # ASOC.py:1039
-    bg_batch, bgpac, _, bg_glob = hostmath.source_weights_bg(BGPAC_REQ, cloud.AREA)
+    ps_batch = int(max(1, pspac / GLOBAL_PS))                 # ASOC.py:1039
+    bg_batch, bgpac, _, bg_glob = hostmath.source_weights_bg(bgpac_req, cloud.AREA)
     w = dict(cloud=cloud, dsc=dsc, csc=csc, kabs=k, ksca=k, pspos=np.array([0.5 * n + 0.3] * 3, np.float32),
              ps=np.array([1.0], np.float32), ps_batch=ps_batch, ps_glob=GLOBAL_PS, bg_batch=bg_batch, bg_glob=bg_glob,
              packets=ps_batch * GLOBAL_PS + bgpac, bg=1.0, tw=1.0)
@@ -276,9 +277,10 @@ def _launch_rooflines(dev, w, alg_bytes, peak, reps=2):
     return out
 
 
-def extra_grid(backend, local, rank, world, n, peak, with_abu=False, steps=1, cpu_seconds=4.0, allreduce=None):
-    """One step (PS + BG launch) of the bench workload on an n^3 grid, optionally with per-cell opacities."""
-    w = make_workload(n)
+def extra_grid(backend, local, rank, world, n, peak, with_abu=False, steps=1, cpu_seconds=4.0, allreduce=None, pac_req=None, warm=True):
+    """One step (PS + BG launch) of the bench workload on an n^3 grid, optionally with per-cell opacities.
+    pac_req = (point-source, background) packets requested per step instead of the bench's 3e7 + 3e7."""
+    w = make_workload(n) if pac_req is None else make_workload(n, pac_req[0], pac_req[1])
     cloud = w["cloud"]
     opts = dict(REF_OPTS, **({"with_abu": 1} if with_abu else {}))
     B = backend.Backend(cloud, ordinal=local, rng_mode=backend.RNG_PACKET, **opts)
@@ -305,7 +307,12 @@ def extra_grid(backend, local, rank, world, n, peak, with_abu=False, steps=1, cp
             allreduce(dev, cloud.CELLS)
         return t
 
-    step(0.9)
+    if warm:
+        step(0.9)
+    else:                 # a long step: warm up on one short launch per source (same kernels, same buffers)
+        dev.zero_amc(1)
+        dev.sim_pb(0, w["ps_glob"], 1, 0.9, w["kabs"], w["ksca"], 0.0, w["tw"], w["ps_glob"])
+        dev.sim_pb(1, w["bg_glob"], 1, 0.9, w["kabs"], w["ksca"], w["bg"], w["tw"], w["bg_glob"])
     dev.sync()
     dev.reset_counters()
     import torch
@@ -329,7 +336,10 @@ def extra_grid(backend, local, rank, world, n, peak, with_abu=False, steps=1, cp
         counts[2] = tmax[0]
     packets, csteps, wall = [float(x) for x in counts.tolist()]
     ms = kms if world == 1 else wall             # 1 GPU: the library's CUDA events around the launches; N GPUs: wall clock between barriers
-    line = {"workload": "%d^3 regular grid, point source + isotropic background%s, TABS+INT" % (n, ", per-cell opacities (WITH_ABU)" if with_abu else ""),
+    line = {"workload": "%d^3 regular grid, point source + isotropic background%s, TABS+INT%s" % (
+                n, ", per-cell opacities (WITH_ABU)" if with_abu else "",
+                "" if pac_req is None else ", %.3g packets per frequency (BASELINE.json configs[4])" % w["packets"]),
+            "packets_per_step": w["packets"],
             "kernel": dev.last_kernel(), "n_gpus": world, "packets_per_s": packets / (ms * 1e-3), "cell_steps_per_s": csteps / (ms * 1e-3),
             "ms_per_step": ms / steps, "steps": steps,
             "roofline": {"bound": "hbm", "achieved": csteps * alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
@@ -610,6 +620,9 @@ def run_ours(args):
                 dist.reduce(t, dst=0)
         try:
             extras.append(extra_grid(backend, local, rank, world, 512, peak, steps=1, cpu_seconds=0 if args.no_cpu else 4.0,
+                                     allreduce=reduce_int if world > 1 else None))
+            # configs[4]: 512^3, 1e9 packets per frequency, packet-sharded over the ranks, INT reduced to rank 0 (strong scaling)
+            extras.append(extra_grid(backend, local, rank, world, 512, peak, steps=1, cpu_seconds=0, pac_req=(5.0e8, 5.0e8), warm=False,
                                      allreduce=reduce_int if world > 1 else None))
             if world == 1:
                 extras.append(extra_grid(backend, local, rank, world, 256, peak, with_abu=True, steps=2, cpu_seconds=0 if args.no_cpu else 4.0))

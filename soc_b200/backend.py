@@ -54,7 +54,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("SOC_B200_LIB") or LIB_PATH        # SOC_B200_LIB: development builds (tools/)
     if not os.path.exists(p):
         raise SocError("%s not found -- run `python -c 'import __graft_entry__ as g; g.build()'` "
                        "(soc_b200 has no CPU fallback)" % p)

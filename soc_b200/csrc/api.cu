@@ -478,9 +478,11 @@ static int sim_launch_domains(soc_context *c, SimArgs &A, int blocks, int thread
     long long chunk = 1LL << 24;
     if (const char *e = getenv("SOC_DOMAIN_CHUNK")) { long long v = atoll(e); if (v >= 1024) chunk = v; }      // tuning knob
     const size_t budget = (free_b + c->queue_bytes) / 2;
-    while (chunk > 65536 && (size_t)chunk * D * sizeof(QPk) > budget) chunk >>= 1;
+    const long long carry_cap = 1LL << 20;                 // room for the packets carried over into the next chunk (see below)
+    while (chunk > 65536 && (size_t)(chunk + carry_cap) * D * sizeof(QPk) > budget) chunk >>= 1;
     if (chunk > A.nlocal) chunk = A.nlocal > 0 ? A.nlocal : 1;
-    const size_t need_b = (size_t)chunk * D * sizeof(QPk);
+    const long long q_cap = chunk + carry_cap;
+    const size_t need_b = (size_t)q_cap * D * sizeof(QPk);
     if (c->queue_bytes < need_b) {
         if (c->queues) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->queues)); c->queues = nullptr; c->queue_bytes = 0; }
         CU(cudaMalloc(&c->queues, need_b));
@@ -490,7 +492,7 @@ static int sim_launch_domains(soc_context *c, SimArgs &A, int blocks, int thread
     int sort = 1;                              // queues sorted by entry block and direction before they are processed
     if (const char *e = getenv("SOC_DOMAIN_SORT")) sort = atoi(e);                                               // tuning knob
     if (sort) {
-        const size_t sb = (size_t)chunk * sizeof(QPk);
+        const size_t sb = (size_t)q_cap * sizeof(QPk);
         if (c->q_sorted_bytes < sb) {
             if (c->q_sorted) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->q_sorted)); c->q_sorted = nullptr; c->q_sorted_bytes = 0; }
             CU(cudaMalloc(&c->q_sorted, sb));
@@ -500,19 +502,26 @@ static int sim_launch_domains(soc_context *c, SimArgs &A, int blocks, int thread
     }
     // below this many parked packets the rest runs over the whole grid: a domain launch with few packets costs its
     // latency (~0.5 ms: one packet after the other through ~250 dependent steps) whatever it holds
-    long long cleanup = 1LL << 18;
+    long long cleanup = 1LL << 17;
     if (const char *e = getenv("SOC_DOMAIN_CLEANUP")) cleanup = atoll(e);                                         // tuning knob
+    // a launch of several chunks: when this few packets of a chunk are left, the next chunk is emitted on top of them, so
+    // that the tail of small launches and the clean-up pass are paid once per launch, not once per chunk
+    long long carry = 1LL << 20;
+    if (const char *e = getenv("SOC_DOMAIN_CARRY")) carry = atoll(e);                                             // tuning knob
+    if (carry < cleanup) carry = cleanup;
+    if (carry > carry_cap) carry = carry_cap;
     long long sort_min = 1LL << 16;
     static bool first_pass[4096];
     const int verbose = getenv("SOC_DOMAIN_VERBOSE") ? atoi(getenv("SOC_DOMAIN_VERBOSE")) : 0;
-    A.dom = 1; A.q_base = c->queues; A.q_tail = c->q_tail; A.q_cap = chunk;
+    A.dom = 1; A.q_base = c->queues; A.q_tail = c->q_tail; A.q_cap = q_cap;
     const int deposit = A.deposit;
     const long long nlocal = A.nlocal;
     c->domain_launches = 0; c->domain_parked = 0;
+    CU(cudaMemsetAsync(c->q_tail, 0, D * sizeof(unsigned), c->stream));
     for (long long u0 = 0; u0 < nlocal; u0 += chunk) {
         const long long n = nlocal - u0 < chunk ? nlocal - u0 : chunk;
-        CU(cudaMemsetAsync(c->q_tail, 0, D * sizeof(unsigned), c->stream));
-        A.unit0 = u0; A.q_base = c->queues;
+        const bool last_chunk = u0 + chunk >= nlocal;
+        A.unit0 = u0; A.q_base = c->queues; A.nlocal = nlocal;
         for (int d = 0; d < D; d++) first_pass[d] = true;
         launch_sim_emit(A, n, c->stream);
         c->launches++;
@@ -522,6 +531,7 @@ static int sim_launch_domains(soc_context *c, SimArgs &A, int blocks, int thread
             long long total = 0; int best = -1;
             for (int d = 0; d < D; d++) { total += c->h_tail[d]; if (c->h_tail[d] > 0 && (best < 0 || c->h_tail[d] > c->h_tail[best])) best = d; }
             if (total == 0) break;
+            if (!last_chunk && total <= carry) break;            // the rest travels with the next chunk
             const bool whole = total <= cleanup && D > 1;
             if (whole && D <= 64) {                  // every queue in one launch of the general kernel
                 A.q_nparts = D; A.q_part[0] = 0;
@@ -553,10 +563,10 @@ static int sim_launch_domains(soc_context *c, SimArgs &A, int blocks, int thread
                     const int t0[3] = { A.tile_x0, A.tile_y0, A.tile_z0 };
                     for (int k = 0; k < 3; k++) if (t0[k] > A.dom_hi[k] || t0[k] + SOC_TILE_N - 1 < A.dom_lo[k]) A.deposit = DEP_RED;
                 }
-                A.q_in = c->queues + (size_t)d * (size_t)chunk;
+                A.q_in = c->queues + (size_t)d * (size_t)q_cap;
                 A.nlocal = c->h_tail[d];
                 A.q_nparts = 1; A.q_part[0] = 0; A.q_part[1] = A.nlocal;
-                A.q_base = whole ? c->queues + (size_t)d * (size_t)chunk : c->queues;      // the clean-up kernel addresses queue `part` of q_base
+                A.q_base = whole ? c->queues + (size_t)d * (size_t)q_cap : c->queues;      // the clean-up kernel addresses queue `part` of q_base
                 long long needb = (A.nlocal + threads - 1) / threads;
                 const int b = (int)(needb < blocks ? (needb < 1 ? 1 : needb) : blocks);
                 CU(cudaMemsetAsync(c->q_tail + d, 0, sizeof(unsigned), c->stream));

@@ -468,7 +468,9 @@ __device__ __forceinline__ void q_push_warp(const SimArgs &A, const QPk &v, bool
 // Parked packets are staged per warp in shared memory and leave in groups: the slot request of q_push_warp is an atomic
 // WITH a return value, i.e. a full round trip to the L2 for the whole warp -- paid once per ~1.5 parked packets it was 18 %
 // of the stall samples of the domain kernels at 512^3 (ncu, SHFL after the ATOMG); staged, it is paid once per Q_STAGE_N.
+#ifndef Q_STAGE_N
 #define Q_STAGE_N 16
+#endif
 __device__ __forceinline__ void q_stage_flush(const SimArgs &A, const QPk *stage, int &n) {
     __syncwarp();
     const int lane = threadIdx.x & 31;
