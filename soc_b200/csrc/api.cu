@@ -51,6 +51,7 @@ struct soc_context {
     float2 *kappa; size_t kappa_cells; // WITH_ABU on regular grids: (kabs*n, ksca*n) per cell, rebuilt before every launch
     int ahead;                         // 1 = look-ahead variant of the lean kernel (geometry one cell ahead, cp.async density ring)
     int domains;                       // domain-tiled propagation: 0 auto, < 0 off, > 0 forced box edge (soc_set_domains)
+    int two_pass;                      // point-source launches with the shared-memory tile in two passes (sim_launch_two_pass)
     QPk *queues; size_t queue_bytes;   // domain mode: packet queues of all domains
     unsigned *q_tail, *h_tail;         // queue lengths on the device / in pinned host memory
     QPk *q_sorted; size_t q_sorted_bytes; unsigned *q_hist;   // domain mode: one queue sorted by entry block and direction
@@ -126,6 +127,8 @@ int soc_create(int device_ordinal, soc_context **out) {
     if (const char *e = getenv("SOC_AHEAD")) c->ahead = atoi(e);                                                       // tuning knob
     if (const char *e = getenv("SOC_LAYOUT")) c->layout = atoi(e) != 0;                                               // tuning knob
     if (const char *e = getenv("SOC_DOMAINS")) c->domains = atoi(e);                                                  // tuning knob
+    c->two_pass = 0;
+    if (const char *e = getenv("SOC_TWO_PASS")) c->two_pass = atoi(e);                                                // tuning knob
     if (const char *e = getenv("SOC_NAV_HOPS")) { int v = atoi(e); if (v >= 1 && v <= 8) c->nav_hops = v; }          // tuning knob
     if (const char *e = getenv("SOC_SC_BATCH")) { int v = atoi(e); if (v >= 1 && v <= 32) c->sc_batch = v; }   // tuning knob
     if (const char *e = getenv("SOC_L2_FETCH")) { int v = atoi(e); if (v == 32 || v == 64 || v == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v); }   // tuning knob
@@ -600,6 +603,78 @@ static int sim_launch_domains(soc_context *c, SimArgs &A, int blocks, int thread
     return SOC_OK;
 }
 
+// Two-pass point-source launch (sim.cu, sim_two_pass_eligible): per chunk of packets the tile pass (emission, the steps inside
+// the shared-memory tile, packets parked at its border), then the plain-add look-ahead kernel over the whole grid from the queue.
+static int sim_launch_two_pass(soc_context *c, SimArgs &A, int blocks, int threads) {
+    const int dim[3] = { A.G.nx, A.G.ny, A.G.nz };
+    long long chunk = 1LL << 24;
+    if (const char *e = getenv("SOC_DOMAIN_CHUNK")) { long long v = atoll(e); if (v >= 1024) chunk = v; }      // tuning knob
+    if (chunk > A.nlocal) chunk = A.nlocal > 0 ? A.nlocal : 1;
+    const size_t need_b = (size_t)chunk * sizeof(QPk);
+    if (c->queue_bytes < need_b) {
+        if (c->queues) { CU(cudaStreamSynchronize(c->stream)); CU(cudaFree(c->queues)); c->queues = nullptr; c->queue_bytes = 0; }
+        CU(cudaMalloc(&c->queues, need_b));
+        c->queue_bytes = need_b;
+    }
+    if (c->q_tail == nullptr) { CU(cudaMalloc(&c->q_tail, 4096 * sizeof(unsigned))); CU(cudaMallocHost(&c->h_tail, 4096 * sizeof(unsigned))); }
+    const int verbose = getenv("SOC_DOMAIN_VERBOSE") ? atoi(getenv("SOC_DOMAIN_VERBOSE")) : 0;
+    const long long nlocal = A.nlocal;
+    const int refill0 = A.refill, agg0 = A.agg_steps;
+    // tile pass: lanes refilled when half the warp is idle, lanes combined during a packet's first steps
+    int tp_refill = 16, tp_agg = 4;
+    if (const char *e = getenv("SOC_TILEPASS_REFILL")) { int v = atoi(e); if (v >= 1 && v <= 32) tp_refill = v; }     // tuning knob
+    if (const char *e = getenv("SOC_TILEPASS_AGG")) { int v = atoi(e); if (v >= 0) tp_agg = v; }                      // tuning knob
+    const int t0[3] = { A.tile_x0, A.tile_y0, A.tile_z0 };
+    A.dom = 1; A.q_base = c->queues; A.q_tail = c->q_tail; A.q_cap = chunk; A.q_in = c->queues; A.dom_base = 0;
+    A.q_nparts = 1; A.q_part[0] = 0;
+    c->domain_launches = 0; c->domain_parked = 0;
+    for (long long u0 = 0; u0 < nlocal; u0 += chunk) {
+        const long long n = nlocal - u0 < chunk ? nlocal - u0 : chunk;
+        CU(cudaMemsetAsync(c->q_tail, 0, sizeof(unsigned), c->stream));
+        CU(cudaMemsetAsync(A.work, 0, sizeof(unsigned long long), c->stream));
+        // pass 1: the box is the tile
+        A.dom_faces = 0;
+        for (int k = 0; k < 3; k++) {
+            A.dom_lo[k] = t0[k]; A.dom_hi[k] = t0[k] + SOC_TILE_N - 1;
+            if (A.dom_lo[k] == 0) A.dom_faces |= 1 << (2 * k);
+            if (A.dom_hi[k] == dim[k] - 1) A.dom_faces |= 2 << (2 * k);
+        }
+        A.deposit = DEP_TILE; A.unit0 = u0; A.nlocal = n;
+        A.refill = tp_refill; A.agg_steps = tp_agg;
+        long long needb = (n + threads - 1) / threads;
+        cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+        if (verbose > 1) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventRecord(e0, c->stream); }
+        launch_sim_tile_pass(A, (int)(needb < blocks ? (needb < 1 ? 1 : needb) : blocks), threads, c->stream);
+        if (verbose > 1) cudaEventRecord(e1, c->stream);
+        c->launches++; c->domain_launches++;
+        CU(cudaMemcpyAsync(c->h_tail, c->q_tail, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        const long long n2 = c->h_tail[0];
+        if (verbose == 1) fprintf(stderr, "soc_b200: two-pass launch: %lld packets emitted, %lld parked at the border of the tile\n", n, n2);
+        if (n2 > 0) {
+            // pass 2: the whole grid as one box, plain adds; nothing is parked
+            A.dom_faces = 0x3f;
+            for (int k = 0; k < 3; k++) { A.dom_lo[k] = 0; A.dom_hi[k] = dim[k] - 1; }
+            A.deposit = DEP_RED; A.unit0 = 0; A.nlocal = n2; A.q_part[1] = n2;
+            A.refill = refill0; A.agg_steps = agg0;
+            CU(cudaMemsetAsync(A.work, 0, sizeof(unsigned long long), c->stream));
+            needb = (n2 + threads - 1) / threads;
+            launch_sim_domain(A, (int)(needb < blocks ? (needb < 1 ? 1 : needb) : blocks), threads, c->stream);
+            c->launches++; c->domain_launches++; c->domain_parked += n2;
+        }
+        if (verbose > 1) {
+            cudaEventRecord(e2, c->stream); cudaEventSynchronize(e2);
+            float t1 = 0.0f, t2 = 0.0f; cudaEventElapsedTime(&t1, e0, e1); cudaEventElapsedTime(&t2, e1, e2);
+            fprintf(stderr, "soc_b200: two-pass launch: %lld packets, tile pass %.3f ms, %lld parked, second pass %.3f ms\n", n, t1, n2, t2);
+            cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+        }
+        CU(cudaGetLastError());
+    }
+    A.deposit = DEP_TILE; A.nlocal = nlocal; A.dom = 0; A.unit0 = 0; A.refill = refill0; A.agg_steps = agg0;
+    sim_note_two_pass();
+    return SOC_OK;
+}
+
 static int sim_launch(soc_context *c, SimArgs &A, const char *who) {
     A.nlocal = (A.nunits - A.rank + A.world - 1) / A.world;
     const bool oct = A.G.levels > 1, dbl = A.G.dbl_sim != 0;
@@ -676,6 +751,9 @@ static int sim_launch(soc_context *c, SimArgs &A, const char *who) {
     if (domains) {
         int r = sim_launch_domains(c, A, blocks, threads);
         if (r != SOC_OK) return r;
+    } else if (c->two_pass && sim_two_pass_eligible(A, c->rng_mode)) {
+        int r = sim_launch_two_pass(c, A, blocks, threads);
+        if (r != SOC_OK) return r;
     } else launch_sim(A, c->rng_mode, blocks, threads, c->stream);
     if (A.use_acc) { launch_fold_acc(A, c->stream); c->launches++; }
     CU(cudaEventRecord(c->ev1, c->stream));
@@ -731,6 +809,7 @@ int soc_sim_pb(soc_context *c, int source, int packets, int batch, float seed, f
                 if (o[k] < 0) o[k] = 0;
             }
             A.tile_x0 = o[0]; A.tile_y0 = o[1]; A.tile_z0 = o[2];
+            A.tile_inside = p[0] >= 0.0f && p[0] < (float)dim[0] && p[1] >= 0.0f && p[1] < (float)dim[1] && p[2] >= 0.0f && p[2] < (float)dim[2];
             A.tile_lo = o[2] * c->G.nx * c->G.ny;
             A.tile_span = SOC_TILE_N * c->G.nx * c->G.ny;
             // the tile takes the adds within 8 cells of the source: lanes are combined only that long (measured: PS launch

@@ -815,8 +815,11 @@ __device__ __forceinline__ void count_add(unsigned *s32, unsigned long long *g64
     if (old < 0x80000000u && old + v >= 0x80000000u) { atomicSub(s32, 0x80000000u); atomicAdd(g64, 0x80000000ull); }
 }
 
-template <int DEP, bool BRICK, bool PEND, bool DOM>
-__global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant__ SimArgs A) {
+// DOM: 0 = the whole grid, packets emitted here; 1 = one domain, packets from its queue, parked at its interior faces;
+// 2 = tile pass of a two-pass point-source launch: packets emitted here, the box is the shared-memory tile around the source
+// (every add goes to shared memory), packets are parked at its border for the plain-add pass over the whole grid
+template <int DEP, bool BRICK, bool PEND, int DOM>
+__global__ void __launch_bounds__(256, DOM == 2 ? 3 : 4) sim_lean_kernel(const __grid_constant__ SimArgs A) {
     __shared__ float smem[DEP == DEP_TILE ? SOC_TILE_CELLS : 1];
     __shared__ float s_pend[PEND ? 4 * 256 : 1];
     int pend_h = -1;
@@ -831,7 +834,7 @@ __global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant_
     const float *__restrict__ dens = BRICK ? A.dens_brick : G.dens;
     const int lane = threadIdx.x & 31;
     const float kabs = A.kabs, ksca = A.ksca;
-    const Box box = launch_box<DOM>(A);
+    const Box box = launch_box<(DOM != 0)>(A);
     LeanPk<BRICK> f; f.ind = 0; f.u = 0; f.rho = 0.0f; f.sn = 0;
     bool alive = false, wsc = false;
     int tskip = 0;                   // DEP_TILE: the packet cannot be inside the tile during its next tskip steps
@@ -847,7 +850,7 @@ __global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant_
             base = __shfl_sync(FULL, base, leader);
             if (!alive) {
                 const unsigned long long u = base + __popc(nm & ((1u << lane) - 1u));
-                if (DOM && u < (unsigned long long)A.nlocal) {        // a packet parked at the border of this domain
+                if (DOM == 1 && u < (unsigned long long)A.nlocal) {        // a packet parked at the border of this domain
                     const QPk s = q_load(A.q_in + u);
                     alive = true; wsc = false; tskip = 0;
                     f.tx = s.tx; f.ty = s.ty; f.tz = s.tz; f.rdx = s.rdx; f.rdy = s.rdy; f.rdz = s.rdz;
@@ -857,8 +860,8 @@ __global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant_
                     f.ind = A.dom_base + brick_index(s.ix - box.lox, s.iy - box.loy, s.iz - box.loz, A.dsize[0] >> 1, A.dsize[1] >> 1);
                     f.rho = __ldg(dens + f.ind);
                 }
-                if (!DOM && u < (unsigned long long)A.nlocal) {
-                    const unsigned long long us = unit_order(A, u);
+                if (DOM != 1 && u < (unsigned long long)A.nlocal) {
+                    const unsigned long long us = unit_order(A, DOM == 2 ? u + (unsigned long long)A.unit0 : u);
                     const unsigned long long q = us * A.world + A.rank;
                     RngPhilox rng; rng.seed(A.phx, q);
                     Packet pk; pk.ind = -1; pk.level = 0; pk.eidx = -1; pk.rho = 0.0f;
@@ -879,7 +882,7 @@ __global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant_
                 }
             }
             more = base + (unsigned long long)__popc(nm) < (unsigned long long)A.nlocal;
-            if (!DOM && lane == leader) {                          // packets started by this warp (domain mode: counted at emission)
+            if (DOM != 1 && lane == leader) {                      // packets started by this warp (domain mode: counted at emission)
                 const unsigned long long left = base < (unsigned long long)A.nlocal ? (unsigned long long)A.nlocal - base : 0ull;
                 count_add(&s_cnt[0], A.counters + 0, (unsigned)min((unsigned long long)__popc(nm), left));
             }
@@ -1712,6 +1715,186 @@ __global__ void __launch_bounds__(256, 4) sim_link_kernel(const __grid_constant_
 // Domain mode, emission pass: one thread per work unit of the chunk; the packet is emitted exactly as the lean / look-ahead
 // kernels do it in their refill block and parked in the queue of the domain its first cell belongs to.
 // =================================================================================================================
+// =================================================================================================================
+// Tile pass of the two-pass point-source launch (sim_launch_two_pass, api.cu): emission, the steps of every packet inside the
+// SOC_TILE_N^3 cells around the source, then the packet is parked -- complete stepping state, QPk -- at the border of the tile
+// for the plain-add look-ahead kernel.  The lean kernel with the tile as its box (DOM = 2) spends 293 warp instructions per
+// packet on this (ncu: 16 lanes per instruction, emission with 10; a third of the stall samples wait for instruction fetch):
+// here the density of the tile and its accumulator sit in shared memory under tile-local x-fastest indices (no tile test, no
+// brick arithmetic), lanes are refilled when half the warp is idle, and lanes are combined (__match_any_sync) only during a
+// packet's first steps, where the lanes of a warp share cells.  Arithmetic and order of operations are those of
+// sim_lean_kernel, so the paths are the same.
+// =================================================================================================================
+__global__ void __launch_bounds__(256, 3) sim_tile_pass_kernel(const __grid_constant__ SimArgs A) {
+    __shared__ float s_dens[SOC_TILE_CELLS];                                  // density of the tile, x fastest
+    __shared__ float s_acc[SOC_TILE_CELLS];                                   // its accumulator
+    __shared__ unsigned s_cnt[4];
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
+    const GridDesc &G = A.G;
+    for (int i = threadIdx.x; i < SOC_TILE_CELLS; i += blockDim.x) {
+        const int ux = i % SOC_TILE_N, uy = (i / SOC_TILE_N) % SOC_TILE_N, uz = i / (SOC_TILE_N * SOC_TILE_N);
+        s_dens[i] = __ldg(A.dens_brick + layout_index(A, A.tile_x0 + ux, A.tile_y0 + uy, A.tile_z0 + uz));
+        s_acc[i] = 0.0f;
+    }
+    __syncthreads();
+    const float kabs = A.kabs, ksca = A.ksca;
+    const Box box = launch_box<true>(A);                                      // the tile
+    LeanPk<true> f; f.rho = 0.0f; f.sn = 0; f.u = 0; f.upm = 0;
+    int ti = 0;                                                               // cell inside the tile
+    bool alive = false, wsc = false, more = true;
+    bool pend = false;               // parked at the border of the tile: stored at the next refill, the lanes of the warp together
+    const int refill = A.refill;
+    const unsigned agg = (unsigned)A.agg_steps;
+    for (;;) {
+        unsigned live = __ballot_sync(FULL, alive);
+        if (more ? (32 - __popc(live) >= refill) : (live == 0u)) {
+            // one round trip for both requests: queue slots for the packets parked since the last refill (the two-pass launch
+            // has a single queue) and new work units
+            const unsigned pm = __ballot_sync(FULL, pend);
+            const unsigned nm = ~live;
+            const int leader = __ffs(nm) - 1, pleader = __ffs(pm) - 1;
+            unsigned qbase = 0;
+            unsigned long long base = 0;
+            if (pm != 0u && lane == pleader) qbase = atomicAdd(A.q_tail, (unsigned)__popc(pm));
+            if (more && lane == leader) base = atomicAdd(A.work, (unsigned long long)__popc(nm));
+            if (pm != 0u) {
+                qbase = __shfl_sync(FULL, qbase, pleader);
+                if (pend) {
+                    QPk o;
+                    o.tx = f.tx; o.ty = f.ty; o.tz = f.tz; o.rdx = f.rdx; o.rdy = f.rdy; o.rdz = f.rdz;
+                    o.photons = f.photons; o.free_path = f.free_path; o.tau = f.tau;
+                    o.ix = (f.upm & 1) ? box.hix - f.cx : box.lox + f.cx; o.iy = (f.upm & 2) ? box.hiy - f.cy : box.loy + f.cy;
+                    o.iz = (f.upm & 4) ? box.hiz - f.cz : box.loz + f.cz;
+                    o.upm = (unsigned)f.upm; o.sn = f.sn; o.u = f.u; o.pad = 0u;
+                    q_store(A.q_base + qbase + __popc(pm & ((1u << lane) - 1u)), o);
+                    pend = false;
+                }
+            }
+            if (!more) break;
+            base = __shfl_sync(FULL, base, leader);
+            if (!alive) {
+                const unsigned long long u = base + __popc(nm & ((1u << lane) - 1u));
+                if (u < (unsigned long long)A.nlocal) {
+                    const unsigned long long us = u + (unsigned long long)A.unit0;
+                    const unsigned long long q = us * A.world + A.rank;
+                    RngPhilox rng; rng.seed(A.phx, q);
+                    Packet pk; pk.ind = -1; pk.level = 0; pk.eidx = -1; pk.rho = 0.0f;
+                    emit_ps<SimArgs, RngPhilox, false>(A, rng, (int)(q % (unsigned)A.batch), pk);
+                    start_packet(A, rng, pk, true);
+                    if (pk.ind >= 0) {
+                        alive = true; wsc = false;
+                        const int ix = clampi((int)floorf(pk.pos.x), 0, G.nx - 1), iy = clampi((int)floorf(pk.pos.y), 0, G.ny - 1),
+                                  iz = clampi((int)floorf(pk.pos.z), 0, G.nz - 1);
+                        lean_set_direction<true>(box, f, pk.dir, ix, iy, iz, pk.pos.x - (float)ix, pk.pos.y - (float)iy, pk.pos.z - (float)iz);
+                        ti = ((iz - box.loz) * SOC_TILE_N + (iy - box.loy)) * SOC_TILE_N + (ix - box.lox);
+                        f.rho = pk.rho; f.photons = pk.photons; f.free_path = pk.free_path; f.tau = 0.0f;
+                        f.sn = 0; f.u = (unsigned)us;
+                    }
+                }
+            }
+            more = base + (unsigned long long)__popc(nm) < (unsigned long long)A.nlocal;
+            if (lane == leader) {
+                const unsigned long long left = base < (unsigned long long)A.nlocal ? (unsigned long long)A.nlocal - base : 0ull;
+                count_add(&s_cnt[0], A.counters + 0, (unsigned)min((unsigned long long)__popc(nm), left));
+            }
+            live = __ballot_sync(FULL, alive);
+            if (live == 0u && !more) break;
+        }
+        #pragma unroll 1
+        for (int rep = 0; rep < 4; rep++) {
+            if (wsc) {                                                        // scattering (as in sim_lean_kernel)
+                const bool ux = (f.upm & 1) != 0, uy = (f.upm & 2) != 0, uz = (f.upm & 4) != 0;
+                const float adx = rcp_approx(f.rdx), ady = rcp_approx(f.rdy), adz = rcp_approx(f.rdz);
+                const float ax = f.tx * adx, ay = f.ty * ady, az = f.tz * adz;
+                const float fx = ux ? 1.0f - ax : ax, fy = uy ? 1.0f - ay : ay, fz = uz ? 1.0f - az : az;
+                const int ix = ux ? box.hix - f.cx : box.lox + f.cx, iy = uy ? box.hiy - f.cy : box.loy + f.cy, iz = uz ? box.hiz - f.cz : box.loz + f.cz;
+                RngBlock rb(A.phx, (unsigned long long)f.u * A.world + A.rank, 0x10000u + LEAN_SCAT(f.sn));
+                f.free_path = free_path_fast(A, rb, f.photons);
+                const float ct = __ldg(A.csc + clampi((int)(rb.uniform() * A.bins), 0, A.bins - 1));
+                vec3 nd = { ux ? adx : -adx, uy ? ady : -ady, uz ? adz : -adz };
+                scatter_rotate(nd, ct, SOC_TWOPI * rb.uniform());
+                lean_set_direction<true>(box, f, nd, ix, iy, iz, fx, fy, fz);
+                f.tau = 0.0f;
+                wsc = false;
+            }
+            // ---- one cell-step ---------------------------------------------------------------------------------------
+            float delta = 0.0f, tmin = 0.0f;
+            bool px = false, py = false, inb = false, sc = false, parked = false;
+            const int oti = ti;
+            bool d = alive;
+            if (alive) {
+                tmin = fminf(f.tx, fminf(f.ty, f.tz));
+                px = f.tx == tmin; py = !px && (f.ty == tmin);
+                const int crem = px ? f.cx : (py ? f.cy : f.cz);
+                inb = crem > 0;
+                const float krho = ksca * f.rho;
+                const float tend = fmaf(tmin, krho, f.tau);
+                sc = f.free_path < tend;
+                const float tsc = (f.free_path - f.tau) * rcp_approx(krho);
+                if (sc) { tmin = fminf(tmin, tsc); f.sn += 1u << 24; } else f.tau = tend;
+                const float x = tmin * f.rho * kabs;
+                const float e = exp2f_approx(-1.4426950408889634f * x);
+                const float ser = x * fmaf(x, fmaf(x, 0.16666667f, -0.5f), 1.0f);
+                const float dfrac = (x < 0.01f) ? ser : (1.0f - e);
+                delta = f.photons * dfrac;
+                f.photons -= delta;
+                f.sn++;
+            }
+            // ---- deposit: young packets of a warp share cells -- combined first -----------------------------------------
+            if (__any_sync(FULL, d && LEAN_STEPS(f.sn) <= agg)) {
+                const unsigned act = __ballot_sync(FULL, d);
+                if (d) {
+                    const unsigned peers = __match_any_sync(act, oti);
+                    if (peers != (1u << lane)) {
+                        delta = reduce_peers(peers, delta, lane);
+                        if (lane != __ffs(peers) - 1) d = false;
+                    }
+                }
+            }
+            if (d) atomicAdd(&s_acc[oti], delta);
+            if (alive) {
+                f.tx -= tmin; f.ty -= tmin; f.tz -= tmin;
+                if (sc) {
+                    wsc = true;
+                    if (LEAN_SCAT(f.sn) > 20u) { alive = false; wsc = false; }
+                } else {
+                    const bool pz = !px && !py;
+                    const int abit = px ? 1 : (py ? 2 : 4);
+                    const int stride = px ? 1 : (py ? SOC_TILE_N : SOC_TILE_N * SOC_TILE_N);
+                    f.tx = px ? f.rdx : f.tx; f.ty = py ? f.rdy : f.ty; f.tz = pz ? f.rdz : f.tz;
+                    f.cx -= px; f.cy -= py; f.cz -= pz;
+                    ti += (f.upm & abit) ? stride : -stride;
+                    alive = inb;
+                    if (inb) f.rho = s_dens[ti];
+                    else {
+                        // left the tile: through a face of the grid the packet is gone, else it is parked for the second pass
+                        // (the counter of the crossed axis stands at -1 = one cell beyond the border)
+                        const int face = (px ? 0 : (py ? 2 : 4)) + ((f.upm & abit) ? 1 : 0);
+                        if (!((A.dom_faces >> face) & 1)) { parked = true; pend = true; }
+                    }
+                }
+                bool stuck = false;
+                if (LEAN_STEPS(f.sn) > (unsigned)A.max_steps && !parked) { alive = false; wsc = false; stuck = true; }
+                if (!alive && !parked) {                            // packet finished: once per packet
+                    count_add(&s_cnt[1], A.counters + 1, LEAN_STEPS(f.sn));
+                    count_add(&s_cnt[2], A.counters + 2, min(LEAN_SCAT(f.sn), 20u));
+                    if (stuck) count_add(&s_cnt[3], A.counters + 3, 1u);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < SOC_TILE_CELLS; i += blockDim.x) {          // the tile's accumulator -> ACC (brick order)
+        const float v = s_acc[i];
+        if (v != 0.0f) {
+            const int ux = i % SOC_TILE_N, uy = (i / SOC_TILE_N) % SOC_TILE_N, uz = i / (SOC_TILE_N * SOC_TILE_N);
+            red_add(&A.acc[layout_index(A, A.tile_x0 + ux, A.tile_y0 + uy, A.tile_z0 + uz)], v);
+        }
+    }
+    if (threadIdx.x < 4 && s_cnt[threadIdx.x]) atomicAdd(A.counters + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
+}
+
 template <bool BRICK>
 __global__ void __launch_bounds__(256) sim_emit_queue_kernel(const __grid_constant__ SimArgs A, long long n) {
     const GridDesc &G = A.G;
@@ -1860,9 +2043,9 @@ static void launch_lean(SimArgs A, int dep, int blocks, int threads, cudaStream_
         else              launch_ahead<BRICK, 3, false>(A, dep, blocks, threads, stream);
         return;
     }
-    if (dep == DEP_RED)       sim_lean_kernel<DEP_RED, BRICK, PEND, false><<<blocks, threads, 0, stream>>>(A);
-    else if (dep == DEP_WARP) sim_lean_kernel<DEP_WARP, BRICK, PEND, false><<<blocks, threads, 0, stream>>>(A);
-    else                      sim_lean_kernel<DEP_TILE, BRICK, PEND, false><<<blocks, threads, 0, stream>>>(A);
+    if (dep == DEP_RED)       sim_lean_kernel<DEP_RED, BRICK, PEND, 0><<<blocks, threads, 0, stream>>>(A);
+    else if (dep == DEP_WARP) sim_lean_kernel<DEP_WARP, BRICK, PEND, 0><<<blocks, threads, 0, stream>>>(A);
+    else                      sim_lean_kernel<DEP_TILE, BRICK, PEND, 0><<<blocks, threads, 0, stream>>>(A);
     note_kernel("sim_lean_kernel", dep, BRICK, PEND, "pend", 0);
 }
 
@@ -1973,11 +2156,53 @@ void launch_sim_domain(const SimArgs &A, int blocks, int threads, cudaStream_t s
         else           launch_ahead<true, 3, false, true>(A, dep, blocks, threads, stream);
     }
     else {
-        if (dep == DEP_RED)       sim_lean_kernel<DEP_RED, true, false, true><<<blocks, threads, 0, stream>>>(A);
-        else if (dep == DEP_WARP) sim_lean_kernel<DEP_WARP, true, false, true><<<blocks, threads, 0, stream>>>(A);
-        else                      sim_lean_kernel<DEP_TILE, true, false, true><<<blocks, threads, 0, stream>>>(A);
+        if (dep == DEP_RED)       sim_lean_kernel<DEP_RED, true, false, 1><<<blocks, threads, 0, stream>>>(A);
+        else if (dep == DEP_WARP) sim_lean_kernel<DEP_WARP, true, false, 1><<<blocks, threads, 0, stream>>>(A);
+        else                      sim_lean_kernel<DEP_TILE, true, false, 1><<<blocks, threads, 0, stream>>>(A);
         note_kernel("sim_lean_kernel", dep, 1, 0, "pend", 1);
     }
+}
+
+// ---- two-pass point-source launch (grids that live in the L2) --------------------------------------------------------------
+// The one-pass launch runs the lean kernel with the shared-memory tile: the tile test, the lane combining and the emission
+// (8 of 32 lanes at a refill) are carried by every iteration of a launch that is bound by instruction issue.  Two passes:
+// (1) the lean kernel with the tile as its box -- emission, the first ~8 steps of every packet into shared memory, then the
+// packet is parked (complete stepping state) at the border of the tile; (2) the plain-add look-ahead kernel over the whole
+// grid, fed from the queue.  Same packets, same paths.
+bool sim_two_pass_eligible(const SimArgs &A, int rng_mode) {
+    return rng_mode != SOC_RNG_REFERENCE && A.kind == SIM_PS && A.deposit == DEP_TILE && A.tile_inside && A.brick && A.ahead && !A.pend &&
+           A.mirror == 0 && !A.with_abu && sim_uses_lean(A) && A.G.nx >= SOC_TILE_N && A.G.ny >= SOC_TILE_N && A.G.nz >= SOC_TILE_N;
+}
+void launch_sim_tile_pass(const SimArgs &A, int blocks, int threads, cudaStream_t stream) {
+    (void)blocks; (void)threads;
+    static int per_sm = 0, sms = 0, variant = -1;     // resident CTAs: the grid is sms x per_sm
+    if (variant < 0) { const char *e = getenv("SOC_TILE_PASS"); variant = e ? atoi(e) : 1; }                         // tuning knob: 0 = lean kernel with the tile as its box
+    if (variant == 0) {
+        int b = blocks;
+        if (per_sm == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sim_lean_kernel<DEP_TILE, true, false, 2>, threads, 0);
+            if (per_sm < 1) per_sm = 1;
+        }
+        if (b > sms * per_sm) b = sms * per_sm;
+        sim_lean_kernel<DEP_TILE, true, false, 2><<<b, threads, 0, stream>>>(A);
+        return;
+    }
+    if (per_sm == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sim_tile_pass_kernel, 256, 0);
+        if (per_sm < 1) per_sm = 1;
+    }
+    long long need = (A.nlocal + 255) / 256;
+    const int b = (int)(need < (long long)sms * per_sm ? (need < 1 ? 1 : need) : (long long)sms * per_sm);
+    sim_tile_pass_kernel<<<b, 256, 0, stream>>>(A);
+}
+void sim_note_two_pass() {
+    snprintf(g_kernel_name, sizeof(g_kernel_name), "sim_lean_kernel<DEP_TILE,brick,tile pass> + sim_ahead_kernel<DEP_RED,brick,queue>");
 }
 
 bool sim_kappa_eligible(const SimArgs &A, int rng_mode) {

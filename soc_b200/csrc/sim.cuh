@@ -80,6 +80,7 @@ struct SimArgs {
     int agg_steps;               // stream kernel: combine lanes only while a packet is younger than this
     int tile_x0, tile_y0, tile_z0;   // DEP_TILE: root-grid origin of the shared-memory tile
     int tile_lo, tile_span;          // first root-cell index of the tile's z-slab and the slab's length
+    int tile_inside;                 // DEP_TILE: the point source lies inside the grid (and so inside the tile)
     unsigned long long *counters;   // packets, steps, scatterings, stuck
     unsigned long long *work;       // stream kernel: next unit to hand out
     MwcLaunch mwc;
@@ -91,6 +92,9 @@ bool sim_domains_eligible(const SimArgs &A, int rng_mode);       // can this lau
 void launch_sim_emit(const SimArgs &A, long long nunits, cudaStream_t stream);    // emits units [unit0, unit0 + nunits) into the domain queues
 void launch_sim_domain(const SimArgs &A, int blocks, int threads, cudaStream_t stream);   // propagates q_in[0 .. nlocal) inside the domain
 void launch_queue_sort(const QPk *q, long long n, QPk *out, unsigned *hist /* 32768 */, const int lo[3], cudaStream_t stream);   // counting sort by entry block and direction octant
+bool sim_two_pass_eligible(const SimArgs &A, int rng_mode);       // point-source launch as tile pass + plain-add pass (sim.cu)
+void launch_sim_tile_pass(const SimArgs &A, int blocks, int threads, cudaStream_t stream);   // emits units [unit0, unit0 + nlocal), parks them at the border of the tile (box dom_lo .. dom_hi)
+void sim_note_two_pass();            // sets the name sim_last_kernel() reports for a two-pass launch
 void launch_sim_cleanup(const SimArgs &A, int blocks, int threads, cudaStream_t stream);  // finishes q_in[0 .. nlocal) on the whole grid (general kernel, adds straight into TABS / INT)
 void launch_fold_acc(const SimArgs &A, cudaStream_t stream);     // TABS += acc*TW*ADHOC; INT += acc; acc = 0
 void launch_brick_permute(const SimArgs &A, float *dens_brick, cudaStream_t stream);   // DENS -> (domain-major) 2x2x2-brick order, A.dsplit / A.dsize

@@ -499,6 +499,37 @@ def test_domain_tiled_propagation_equals_whole_grid(kind, schedule, monkeypatch)
         assert abs(a.sum() - b.sum()) <= 3e-5 * a.sum()
 
 
+@pytest.mark.parametrize("pos", [(9.3, 7.2, 8.7), (1.4, 14.6, 16.5)])
+def test_two_pass_point_source_launch_equals_one_pass(pos, monkeypatch):
+    """SOC_TWO_PASS=1: the steps of every point-source packet inside the shared-memory tile in a pass of their own (the lean
+    kernel with the tile as its box), the packets parked at the border of the tile with their complete stepping state, the rest
+    through the plain-add look-ahead kernel from the queue.  Same Philox streams: same packets, the steps / scatterings agree up
+    to paths that flip at a cell face by rounding (lean vs look-ahead kernel), TABS and INT up to that and the order of the
+    float additions.  Second position: the tile is clamped to the border of the grid; chunks of 65536 packets."""
+    from soc_b200 import backend
+    from soc_b200.formats import Cloud
+    nx, ny, nz = 20, 16, 18
+    d = synth.plummer_density(24)[2:2 + nz, 4:4 + ny, 2:2 + nx]
+    cloud = Cloud(nx, ny, nz, [nx * ny * nz], np.ascontiguousarray(d, np.float32).ravel())
+    run = run_ps([pos], batch=50, glob=4096, tau_s=6.0)
+    monkeypatch.setenv("SOC_DOMAIN_CHUNK", "65536")
+    res, cnt = [], []
+    for two in ("0", "1"):
+        monkeypatch.setenv("SOC_TWO_PASS", two)
+        B = _backend(cloud, backend.RNG_PACKET, no_ps=1, noabsorbed=0)
+        out = run(B)
+        res.append((out["tabs"].astype(np.float64), out["int"].astype(np.float64)))
+        c = B.counters
+        cnt.append((c.packets, c.steps, c.scatterings, c.reserved[0]))
+        assert ("tile pass" in B.dev.last_kernel()) == (two == "1"), B.dev.last_kernel()
+        B.close()
+    assert cnt[0][0] == cnt[1][0] and abs(cnt[0][1] - cnt[1][1]) <= 2e-5 * cnt[0][1] and abs(cnt[0][2] - cnt[1][2]) <= 2e-5 * cnt[0][2] \
+        and cnt[0][3] == 0 and cnt[1][3] == 0, cnt
+    for a, b in zip(res[0], res[1]):
+        assert (np.abs(a - b) > 1e-4 * a.max()).mean() < 1e-3
+        assert abs(a.sum() - b.sum()) <= 3e-5 * a.sum()
+
+
 @pytest.mark.parametrize("kind", ["bg", "ps"])
 def test_domain_tiled_propagation_at_512(kind):
     """512^3 (BASELINE.json configs 4/5): the automatic domain mode (2 x 2 x 2 boxes of 256^3) against the whole-grid
