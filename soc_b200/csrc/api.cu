@@ -127,7 +127,7 @@ int soc_create(int device_ordinal, soc_context **out) {
     if (const char *e = getenv("SOC_AHEAD")) c->ahead = atoi(e);                                                       // tuning knob
     if (const char *e = getenv("SOC_LAYOUT")) c->layout = atoi(e) != 0;                                               // tuning knob
     if (const char *e = getenv("SOC_DOMAINS")) c->domains = atoi(e);                                                  // tuning knob
-    c->two_pass = 0;
+    c->two_pass = 1;
     if (const char *e = getenv("SOC_TWO_PASS")) c->two_pass = atoi(e);                                                // tuning knob
     if (const char *e = getenv("SOC_NAV_HOPS")) { int v = atoi(e); if (v >= 1 && v <= 8) c->nav_hops = v; }          // tuning knob
     if (const char *e = getenv("SOC_SC_BATCH")) { int v = atoi(e); if (v >= 1 && v <= 32) c->sc_batch = v; }   // tuning knob
@@ -492,7 +492,9 @@ static int sim_launch_domains(soc_context *c, SimArgs &A, int blocks, int thread
         c->queue_bytes = need_b;
     }
     if (c->q_tail == nullptr) { CU(cudaMalloc(&c->q_tail, 4096 * sizeof(unsigned))); CU(cudaMallocHost(&c->h_tail, 4096 * sizeof(unsigned))); }
-    int sort = 1;                              // queues sorted by entry block and direction before they are processed
+    // queues sorted by entry block and direction before they are processed.  Background: yes.  Point source: no -- its packets
+    // stream radially, sorted neighbours walk the same cells in step and their adds serialise (512^3 launch 177 ms sorted, 133 ms not)
+    int sort = A.kind == SIM_PS ? 0 : 1;
     if (const char *e = getenv("SOC_DOMAIN_SORT")) sort = atoi(e);                                               // tuning knob
     if (sort) {
         const size_t sb = (size_t)q_cap * sizeof(QPk);
@@ -517,7 +519,12 @@ static int sim_launch_domains(soc_context *c, SimArgs &A, int blocks, int thread
     static bool first_pass[4096];
     const int verbose = getenv("SOC_DOMAIN_VERBOSE") ? atoi(getenv("SOC_DOMAIN_VERBOSE")) : 0;
     A.dom = 1; A.q_base = c->queues; A.q_tail = c->q_tail; A.q_cap = q_cap;
-    const int deposit = A.deposit;
+    const bool tile_first = c->two_pass && sim_tile_pass_eligible(A, c->rng_mode);
+    const int deposit = tile_first ? DEP_RED : A.deposit;      // accumulation engine of the box launches
+    const int refill0 = A.refill, agg0 = A.agg_steps, deposit0 = A.deposit;
+    int tp_refill = 24, tp_agg = 0;
+    if (const char *e = getenv("SOC_TILEPASS_REFILL")) { int v = atoi(e); if (v >= 1 && v <= 32) tp_refill = v; }     // tuning knob
+    if (const char *e = getenv("SOC_TILEPASS_AGG")) { int v = atoi(e); if (v >= 0) tp_agg = v; }                      // tuning knob
     const long long nlocal = A.nlocal;
     c->domain_launches = 0; c->domain_parked = 0;
     CU(cudaMemsetAsync(c->q_tail, 0, D * sizeof(unsigned), c->stream));
@@ -525,8 +532,22 @@ static int sim_launch_domains(soc_context *c, SimArgs &A, int blocks, int thread
         const long long n = nlocal - u0 < chunk ? nlocal - u0 : chunk;
         const bool last_chunk = u0 + chunk >= nlocal;
         A.unit0 = u0; A.q_base = c->queues; A.nlocal = nlocal;
-        for (int d = 0; d < D; d++) first_pass[d] = true;
-        launch_sim_emit(A, n, c->stream);
+        for (int d = 0; d < D; d++) first_pass[d] = !tile_first;
+        if (tile_first) {
+            // point source with the shared-memory tile: emission and the steps inside the tile in a pass of their own, which parks
+            // the packets at the border of the tile; every box launch then runs the plain-add look-ahead kernel
+            const int t0[3] = { A.tile_x0, A.tile_y0, A.tile_z0 };
+            A.dom_faces = 0;
+            for (int k = 0; k < 3; k++) {
+                A.dom_lo[k] = t0[k]; A.dom_hi[k] = t0[k] + SOC_TILE_N - 1;
+                if (A.dom_lo[k] == 0) A.dom_faces |= 1 << (2 * k);
+                if (A.dom_hi[k] == dim[k] - 1) A.dom_faces |= 2 << (2 * k);
+            }
+            A.deposit = DEP_TILE; A.nlocal = n; A.refill = tp_refill; A.agg_steps = tp_agg;
+            CU(cudaMemsetAsync(A.work, 0, sizeof(unsigned long long), c->stream));
+            launch_sim_tile_pass(A, blocks, threads, c->stream);
+            A.refill = refill0; A.agg_steps = agg0; A.nlocal = nlocal;
+        } else launch_sim_emit(A, n, c->stream);
         c->launches++;
         for (;;) {
             CU(cudaMemcpyAsync(c->h_tail, c->q_tail, D * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
@@ -596,7 +617,7 @@ static int sim_launch_domains(soc_context *c, SimArgs &A, int blocks, int thread
             CU(cudaGetLastError());
         }
     }
-    A.deposit = deposit; A.nlocal = nlocal; A.dom = 0;
+    A.deposit = deposit0; A.nlocal = nlocal; A.dom = 0;
     if (verbose)
         fprintf(stderr, "soc_b200: %d domains of %dx%dx%d cells, chunk %lld, %llu domain launches, %llu packet visits for %lld packets\n",
                 D, ds[0], ds[1], ds[2], chunk, c->domain_launches, c->domain_parked, nlocal);
@@ -620,8 +641,8 @@ static int sim_launch_two_pass(soc_context *c, SimArgs &A, int blocks, int threa
     const int verbose = getenv("SOC_DOMAIN_VERBOSE") ? atoi(getenv("SOC_DOMAIN_VERBOSE")) : 0;
     const long long nlocal = A.nlocal;
     const int refill0 = A.refill, agg0 = A.agg_steps;
-    // tile pass: lanes refilled when half the warp is idle, lanes combined during a packet's first steps
-    int tp_refill = 16, tp_agg = 4;
+    // tile pass: lanes refilled when 24 of the warp are idle; lanes combined during a packet's first tp_agg steps (beyond the very first)
+    int tp_refill = 24, tp_agg = 0;
     if (const char *e = getenv("SOC_TILEPASS_REFILL")) { int v = atoi(e); if (v >= 1 && v <= 32) tp_refill = v; }     // tuning knob
     if (const char *e = getenv("SOC_TILEPASS_AGG")) { int v = atoi(e); if (v >= 0) tp_agg = v; }                      // tuning knob
     const int t0[3] = { A.tile_x0, A.tile_y0, A.tile_z0 };

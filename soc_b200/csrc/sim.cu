@@ -815,11 +815,8 @@ __device__ __forceinline__ void count_add(unsigned *s32, unsigned long long *g64
     if (old < 0x80000000u && old + v >= 0x80000000u) { atomicSub(s32, 0x80000000u); atomicAdd(g64, 0x80000000ull); }
 }
 
-// DOM: 0 = the whole grid, packets emitted here; 1 = one domain, packets from its queue, parked at its interior faces;
-// 2 = tile pass of a two-pass point-source launch: packets emitted here, the box is the shared-memory tile around the source
-// (every add goes to shared memory), packets are parked at its border for the plain-add pass over the whole grid
-template <int DEP, bool BRICK, bool PEND, int DOM>
-__global__ void __launch_bounds__(256, DOM == 2 ? 3 : 4) sim_lean_kernel(const __grid_constant__ SimArgs A) {
+template <int DEP, bool BRICK, bool PEND, bool DOM>
+__global__ void __launch_bounds__(256, 4) sim_lean_kernel(const __grid_constant__ SimArgs A) {
     __shared__ float smem[DEP == DEP_TILE ? SOC_TILE_CELLS : 1];
     __shared__ float s_pend[PEND ? 4 * 256 : 1];
     int pend_h = -1;
@@ -834,7 +831,7 @@ __global__ void __launch_bounds__(256, DOM == 2 ? 3 : 4) sim_lean_kernel(const _
     const float *__restrict__ dens = BRICK ? A.dens_brick : G.dens;
     const int lane = threadIdx.x & 31;
     const float kabs = A.kabs, ksca = A.ksca;
-    const Box box = launch_box<(DOM != 0)>(A);
+    const Box box = launch_box<DOM>(A);
     LeanPk<BRICK> f; f.ind = 0; f.u = 0; f.rho = 0.0f; f.sn = 0;
     bool alive = false, wsc = false;
     int tskip = 0;                   // DEP_TILE: the packet cannot be inside the tile during its next tskip steps
@@ -850,7 +847,7 @@ __global__ void __launch_bounds__(256, DOM == 2 ? 3 : 4) sim_lean_kernel(const _
             base = __shfl_sync(FULL, base, leader);
             if (!alive) {
                 const unsigned long long u = base + __popc(nm & ((1u << lane) - 1u));
-                if (DOM == 1 && u < (unsigned long long)A.nlocal) {        // a packet parked at the border of this domain
+                if (DOM && u < (unsigned long long)A.nlocal) {        // a packet parked at the border of this domain
                     const QPk s = q_load(A.q_in + u);
                     alive = true; wsc = false; tskip = 0;
                     f.tx = s.tx; f.ty = s.ty; f.tz = s.tz; f.rdx = s.rdx; f.rdy = s.rdy; f.rdz = s.rdz;
@@ -860,8 +857,8 @@ __global__ void __launch_bounds__(256, DOM == 2 ? 3 : 4) sim_lean_kernel(const _
                     f.ind = A.dom_base + brick_index(s.ix - box.lox, s.iy - box.loy, s.iz - box.loz, A.dsize[0] >> 1, A.dsize[1] >> 1);
                     f.rho = __ldg(dens + f.ind);
                 }
-                if (DOM != 1 && u < (unsigned long long)A.nlocal) {
-                    const unsigned long long us = unit_order(A, DOM == 2 ? u + (unsigned long long)A.unit0 : u);
+                if (!DOM && u < (unsigned long long)A.nlocal) {
+                    const unsigned long long us = unit_order(A, u);
                     const unsigned long long q = us * A.world + A.rank;
                     RngPhilox rng; rng.seed(A.phx, q);
                     Packet pk; pk.ind = -1; pk.level = 0; pk.eidx = -1; pk.rho = 0.0f;
@@ -882,7 +879,7 @@ __global__ void __launch_bounds__(256, DOM == 2 ? 3 : 4) sim_lean_kernel(const _
                 }
             }
             more = base + (unsigned long long)__popc(nm) < (unsigned long long)A.nlocal;
-            if (DOM != 1 && lane == leader) {                      // packets started by this warp (domain mode: counted at emission)
+            if (!DOM && lane == leader) {                          // packets started by this warp (domain mode: counted at emission)
                 const unsigned long long left = base < (unsigned long long)A.nlocal ? (unsigned long long)A.nlocal - base : 0ull;
                 count_add(&s_cnt[0], A.counters + 0, (unsigned)min((unsigned long long)__popc(nm), left));
             }
@@ -1749,27 +1746,22 @@ __global__ void __launch_bounds__(256, 3) sim_tile_pass_kernel(const __grid_cons
     for (;;) {
         unsigned live = __ballot_sync(FULL, alive);
         if (more ? (32 - __popc(live) >= refill) : (live == 0u)) {
-            // one round trip for both requests: queue slots for the packets parked since the last refill (the two-pass launch
-            // has a single queue) and new work units
+            // one round trip for both requests: queue slots for the packets parked since the last refill and new work units
             const unsigned pm = __ballot_sync(FULL, pend);
             const unsigned nm = ~live;
-            const int leader = __ffs(nm) - 1, pleader = __ffs(pm) - 1;
-            unsigned qbase = 0;
+            const int leader = __ffs(nm) - 1;
             unsigned long long base = 0;
-            if (pm != 0u && lane == pleader) qbase = atomicAdd(A.q_tail, (unsigned)__popc(pm));
             if (more && lane == leader) base = atomicAdd(A.work, (unsigned long long)__popc(nm));
             if (pm != 0u) {
-                qbase = __shfl_sync(FULL, qbase, pleader);
-                if (pend) {
-                    QPk o;
-                    o.tx = f.tx; o.ty = f.ty; o.tz = f.tz; o.rdx = f.rdx; o.rdy = f.rdy; o.rdz = f.rdz;
-                    o.photons = f.photons; o.free_path = f.free_path; o.tau = f.tau;
-                    o.ix = (f.upm & 1) ? box.hix - f.cx : box.lox + f.cx; o.iy = (f.upm & 2) ? box.hiy - f.cy : box.loy + f.cy;
-                    o.iz = (f.upm & 4) ? box.hiz - f.cz : box.loz + f.cz;
-                    o.upm = (unsigned)f.upm; o.sn = f.sn; o.u = f.u; o.pad = 0u;
-                    q_store(A.q_base + qbase + __popc(pm & ((1u << lane) - 1u)), o);
-                    pend = false;
-                }
+                QPk o;
+                o.tx = f.tx; o.ty = f.ty; o.tz = f.tz; o.rdx = f.rdx; o.rdy = f.rdy; o.rdz = f.rdz;
+                o.photons = f.photons; o.free_path = f.free_path; o.tau = f.tau;
+                o.ix = (f.upm & 1) ? box.hix - f.cx : box.lox + f.cx; o.iy = (f.upm & 2) ? box.hiy - f.cy : box.loy + f.cy;
+                o.iz = (f.upm & 4) ? box.hiz - f.cz : box.loz + f.cz;
+                o.upm = (unsigned)f.upm; o.sn = f.sn; o.u = f.u; o.pad = 0u;
+                if (!pend) { o.ix = o.iy = o.iz = 0; }
+                q_push_warp(A, o, pend);                                      // the queue of the domain that holds the cell (one atomic per domain)
+                pend = false;
             }
             if (!more) break;
             base = __shfl_sync(FULL, base, leader);
@@ -1803,7 +1795,10 @@ __global__ void __launch_bounds__(256, 3) sim_tile_pass_kernel(const __grid_cons
         }
         #pragma unroll 1
         for (int rep = 0; rep < 4; rep++) {
-            if (wsc) {                                                        // scattering (as in sim_lean_kernel)
+            // scatterings, batched: a lane at a scattering point waits until three are (or nothing else can run)
+            const unsigned smask = __ballot_sync(FULL, wsc);
+            const bool scatter_now = smask != 0u && (__popc(smask) >= 3 || smask == __ballot_sync(FULL, alive));
+            if (wsc && scatter_now) {                                         // (as in sim_lean_kernel)
                 const bool ux = (f.upm & 1) != 0, uy = (f.upm & 2) != 0, uz = (f.upm & 4) != 0;
                 const float adx = rcp_approx(f.rdx), ady = rcp_approx(f.rdy), adz = rcp_approx(f.rdz);
                 const float ax = f.tx * adx, ay = f.ty * ady, az = f.tz * adz;
@@ -1822,8 +1817,9 @@ __global__ void __launch_bounds__(256, 3) sim_tile_pass_kernel(const __grid_cons
             float delta = 0.0f, tmin = 0.0f;
             bool px = false, py = false, inb = false, sc = false, parked = false;
             const int oti = ti;
-            bool d = alive;
-            if (alive) {
+            const bool run = alive && !wsc;
+            bool d = run;
+            if (run) {
                 tmin = fminf(f.tx, fminf(f.ty, f.tz));
                 px = f.tx == tmin; py = !px && (f.ty == tmin);
                 const int crem = px ? f.cx : (py ? f.cy : f.cz);
@@ -1841,7 +1837,21 @@ __global__ void __launch_bounds__(256, 3) sim_tile_pass_kernel(const __grid_cons
                 f.photons -= delta;
                 f.sn++;
             }
-            // ---- deposit: young packets of a warp share cells -- combined first -----------------------------------------
+            // ---- deposit ----------------------------------------------------------------------------------------------
+            // the first step of every packet lies in the cell of the source: the new lanes of the warp are summed with a
+            // butterfly and leave as one add
+            {
+                const bool first = d && f.sn == 1u;
+                const unsigned fm = __ballot_sync(FULL, first);
+                if (fm != 0u) {
+                    float v = first ? delta : 0.0f;
+                    #pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+                    if (lane == __ffs(fm) - 1) atomicAdd(&s_acc[oti], v);
+                    if (first) d = false;
+                }
+            }
+            // young packets of a warp still share cells: combined first
             if (__any_sync(FULL, d && LEAN_STEPS(f.sn) <= agg)) {
                 const unsigned act = __ballot_sync(FULL, d);
                 if (d) {
@@ -1853,7 +1863,7 @@ __global__ void __launch_bounds__(256, 3) sim_tile_pass_kernel(const __grid_cons
                 }
             }
             if (d) atomicAdd(&s_acc[oti], delta);
-            if (alive) {
+            if (run) {
                 f.tx -= tmin; f.ty -= tmin; f.tz -= tmin;
                 if (sc) {
                     wsc = true;
@@ -2043,9 +2053,9 @@ static void launch_lean(SimArgs A, int dep, int blocks, int threads, cudaStream_
         else              launch_ahead<BRICK, 3, false>(A, dep, blocks, threads, stream);
         return;
     }
-    if (dep == DEP_RED)       sim_lean_kernel<DEP_RED, BRICK, PEND, 0><<<blocks, threads, 0, stream>>>(A);
-    else if (dep == DEP_WARP) sim_lean_kernel<DEP_WARP, BRICK, PEND, 0><<<blocks, threads, 0, stream>>>(A);
-    else                      sim_lean_kernel<DEP_TILE, BRICK, PEND, 0><<<blocks, threads, 0, stream>>>(A);
+    if (dep == DEP_RED)       sim_lean_kernel<DEP_RED, BRICK, PEND, false><<<blocks, threads, 0, stream>>>(A);
+    else if (dep == DEP_WARP) sim_lean_kernel<DEP_WARP, BRICK, PEND, false><<<blocks, threads, 0, stream>>>(A);
+    else                      sim_lean_kernel<DEP_TILE, BRICK, PEND, false><<<blocks, threads, 0, stream>>>(A);
     note_kernel("sim_lean_kernel", dep, BRICK, PEND, "pend", 0);
 }
 
@@ -2156,9 +2166,9 @@ void launch_sim_domain(const SimArgs &A, int blocks, int threads, cudaStream_t s
         else           launch_ahead<true, 3, false, true>(A, dep, blocks, threads, stream);
     }
     else {
-        if (dep == DEP_RED)       sim_lean_kernel<DEP_RED, true, false, 1><<<blocks, threads, 0, stream>>>(A);
-        else if (dep == DEP_WARP) sim_lean_kernel<DEP_WARP, true, false, 1><<<blocks, threads, 0, stream>>>(A);
-        else                      sim_lean_kernel<DEP_TILE, true, false, 1><<<blocks, threads, 0, stream>>>(A);
+        if (dep == DEP_RED)       sim_lean_kernel<DEP_RED, true, false, true><<<blocks, threads, 0, stream>>>(A);
+        else if (dep == DEP_WARP) sim_lean_kernel<DEP_WARP, true, false, true><<<blocks, threads, 0, stream>>>(A);
+        else                      sim_lean_kernel<DEP_TILE, true, false, true><<<blocks, threads, 0, stream>>>(A);
         note_kernel("sim_lean_kernel", dep, 1, 0, "pend", 1);
     }
 }
@@ -2169,27 +2179,18 @@ void launch_sim_domain(const SimArgs &A, int blocks, int threads, cudaStream_t s
 // (1) the lean kernel with the tile as its box -- emission, the first ~8 steps of every packet into shared memory, then the
 // packet is parked (complete stepping state) at the border of the tile; (2) the plain-add look-ahead kernel over the whole
 // grid, fed from the queue.  Same packets, same paths.
-bool sim_two_pass_eligible(const SimArgs &A, int rng_mode) {
+// can the emission and the steps inside the shared-memory tile run as a pass of their own (sim_tile_pass_kernel)?
+bool sim_tile_pass_eligible(const SimArgs &A, int rng_mode) {
     return rng_mode != SOC_RNG_REFERENCE && A.kind == SIM_PS && A.deposit == DEP_TILE && A.tile_inside && A.brick && A.ahead && !A.pend &&
            A.mirror == 0 && !A.with_abu && sim_uses_lean(A) && A.G.nx >= SOC_TILE_N && A.G.ny >= SOC_TILE_N && A.G.nz >= SOC_TILE_N;
 }
+bool sim_two_pass_eligible(const SimArgs &A, int rng_mode) {
+    // larger grids run domain by domain (there the tile pass replaces the emission pass) or, with that switched off, the look-ahead tile kernel
+    return sim_tile_pass_eligible(A, rng_mode) && A.G.nxyz <= (1LL << 25);
+}
 void launch_sim_tile_pass(const SimArgs &A, int blocks, int threads, cudaStream_t stream) {
     (void)blocks; (void)threads;
-    static int per_sm = 0, sms = 0, variant = -1;     // resident CTAs: the grid is sms x per_sm
-    if (variant < 0) { const char *e = getenv("SOC_TILE_PASS"); variant = e ? atoi(e) : 1; }                         // tuning knob: 0 = lean kernel with the tile as its box
-    if (variant == 0) {
-        int b = blocks;
-        if (per_sm == 0) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sim_lean_kernel<DEP_TILE, true, false, 2>, threads, 0);
-            if (per_sm < 1) per_sm = 1;
-        }
-        if (b > sms * per_sm) b = sms * per_sm;
-        sim_lean_kernel<DEP_TILE, true, false, 2><<<b, threads, 0, stream>>>(A);
-        return;
-    }
+    static int per_sm = 0, sms = 0;                   // resident CTAs: the grid is sms x per_sm
     if (per_sm == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
@@ -2202,7 +2203,7 @@ void launch_sim_tile_pass(const SimArgs &A, int blocks, int threads, cudaStream_
     sim_tile_pass_kernel<<<b, 256, 0, stream>>>(A);
 }
 void sim_note_two_pass() {
-    snprintf(g_kernel_name, sizeof(g_kernel_name), "sim_lean_kernel<DEP_TILE,brick,tile pass> + sim_ahead_kernel<DEP_RED,brick,queue>");
+    snprintf(g_kernel_name, sizeof(g_kernel_name), "sim_tile_pass_kernel + sim_ahead_kernel<DEP_RED,brick,queue>");
 }
 
 bool sim_kappa_eligible(const SimArgs &A, int rng_mode) {

@@ -92,6 +92,7 @@ bool sim_domains_eligible(const SimArgs &A, int rng_mode);       // can this lau
 void launch_sim_emit(const SimArgs &A, long long nunits, cudaStream_t stream);    // emits units [unit0, unit0 + nunits) into the domain queues
 void launch_sim_domain(const SimArgs &A, int blocks, int threads, cudaStream_t stream);   // propagates q_in[0 .. nlocal) inside the domain
 void launch_queue_sort(const QPk *q, long long n, QPk *out, unsigned *hist /* 32768 */, const int lo[3], cudaStream_t stream);   // counting sort by entry block and direction octant
+bool sim_tile_pass_eligible(const SimArgs &A, int rng_mode);      // emission + the steps inside the shared-memory tile as a pass of their own (domain mode: instead of the emission pass)
 bool sim_two_pass_eligible(const SimArgs &A, int rng_mode);       // point-source launch as tile pass + plain-add pass (sim.cu)
 void launch_sim_tile_pass(const SimArgs &A, int blocks, int threads, cudaStream_t stream);   // emits units [unit0, unit0 + nlocal), parks them at the border of the tile (box dom_lo .. dom_hi)
 void sim_note_two_pass();            // sets the name sim_last_kernel() reports for a two-pass launch

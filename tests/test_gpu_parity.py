@@ -521,7 +521,7 @@ def test_two_pass_point_source_launch_equals_one_pass(pos, monkeypatch):
         res.append((out["tabs"].astype(np.float64), out["int"].astype(np.float64)))
         c = B.counters
         cnt.append((c.packets, c.steps, c.scatterings, c.reserved[0]))
-        assert ("tile pass" in B.dev.last_kernel()) == (two == "1"), B.dev.last_kernel()
+        assert ("sim_tile_pass_kernel" in B.dev.last_kernel()) == (two == "1"), B.dev.last_kernel()
         B.close()
     assert cnt[0][0] == cnt[1][0] and abs(cnt[0][1] - cnt[1][1]) <= 2e-5 * cnt[0][1] and abs(cnt[0][2] - cnt[1][2]) <= 2e-5 * cnt[0][2] \
         and cnt[0][3] == 0 and cnt[1][3] == 0, cnt
