@@ -478,7 +478,7 @@ static int sim_launch_domains(soc_context *c, SimArgs &A, int blocks, int thread
     // chunk of work units in flight: every queue must be able to hold all of them
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
-    long long chunk = 1LL << 24;
+    long long chunk = 1LL << 25;
     if (const char *e = getenv("SOC_DOMAIN_CHUNK")) { long long v = atoll(e); if (v >= 1024) chunk = v; }      // tuning knob
     const size_t budget = (free_b + c->queue_bytes) / 2;
     const long long carry_cap = 1LL << 20;                 // room for the packets carried over into the next chunk (see below)
@@ -600,7 +600,8 @@ static int sim_launch_domains(soc_context *c, SimArgs &A, int blocks, int thread
                 // in step serialise on their adds (same-address RED / shared-memory atomics)
                 const bool fresh = first_pass[d];
                 first_pass[d] = false;
-                if (!whole && sort && A.nlocal >= (long long)sort_min && !(sort < 3 && fresh && A.kind == SIM_PS) && !(sort == 2 && A.kind == SIM_PS)) {
+                if (!whole && sort && A.nlocal >= (long long)sort_min && !(sort < 3 && fresh && A.kind == SIM_PS) && !(sort == 2 && A.kind == SIM_PS) &&
+                    !(sort == 4 && fresh)) {
                     launch_queue_sort(A.q_in, A.nlocal, c->q_sorted, c->q_hist, A.dom_lo, c->stream);
                     A.q_in = c->q_sorted;
                     c->launches += 3;
@@ -628,7 +629,7 @@ static int sim_launch_domains(soc_context *c, SimArgs &A, int blocks, int thread
 // the shared-memory tile, packets parked at its border), then the plain-add look-ahead kernel over the whole grid from the queue.
 static int sim_launch_two_pass(soc_context *c, SimArgs &A, int blocks, int threads) {
     const int dim[3] = { A.G.nx, A.G.ny, A.G.nz };
-    long long chunk = 1LL << 24;
+    long long chunk = 1LL << 25;
     if (const char *e = getenv("SOC_DOMAIN_CHUNK")) { long long v = atoll(e); if (v >= 1024) chunk = v; }      // tuning knob
     if (chunk > A.nlocal) chunk = A.nlocal > 0 ? A.nlocal : 1;
     const size_t need_b = (size_t)chunk * sizeof(QPk);

@@ -1722,19 +1722,25 @@ __global__ void __launch_bounds__(256, 4) sim_link_kernel(const __grid_constant_
 // packet's first steps, where the lanes of a warp share cells.  Arithmetic and order of operations are those of
 // sim_lean_kernel, so the paths are the same.
 // =================================================================================================================
+// KAPPA: per-cell opacities, (kabs*n, ksca*n) per cell as in sim_ahead_kernel
+template <bool KAPPA>
 __global__ void __launch_bounds__(256, 3) sim_tile_pass_kernel(const __grid_constant__ SimArgs A) {
-    __shared__ float s_dens[SOC_TILE_CELLS];                                  // density of the tile, x fastest
-    __shared__ float s_acc[SOC_TILE_CELLS];                                   // its accumulator
+    extern __shared__ __align__(8) float tp_smem[];
+    float *const s_acc = tp_smem;                                             // accumulator of the tile, x fastest
+    float *const s_dens = tp_smem + SOC_TILE_CELLS;                           // its density (KAPPA: float2 per cell)
     __shared__ unsigned s_cnt[4];
     const int lane = threadIdx.x & 31;
     if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0u;
     const GridDesc &G = A.G;
     for (int i = threadIdx.x; i < SOC_TILE_CELLS; i += blockDim.x) {
         const int ux = i % SOC_TILE_N, uy = (i / SOC_TILE_N) % SOC_TILE_N, uz = i / (SOC_TILE_N * SOC_TILE_N);
-        s_dens[i] = __ldg(A.dens_brick + layout_index(A, A.tile_x0 + ux, A.tile_y0 + uy, A.tile_z0 + uz));
+        const int gi = layout_index(A, A.tile_x0 + ux, A.tile_y0 + uy, A.tile_z0 + uz);
+        if (KAPPA) reinterpret_cast<float2 *>(s_dens)[i] = __ldg(A.kappa + gi);
+        else s_dens[i] = __ldg(A.dens_brick + gi);
         s_acc[i] = 0.0f;
     }
     __syncthreads();
+    float ka = 0.0f;                 // KAPPA: kabs*n of the cell (f.rho holds ksca*n)
     const float kabs = A.kabs, ksca = A.ksca;
     const Box box = launch_box<true>(A);                                      // the tile
     LeanPk<true> f; f.rho = 0.0f; f.sn = 0; f.u = 0; f.upm = 0;
@@ -1781,6 +1787,7 @@ __global__ void __launch_bounds__(256, 3) sim_tile_pass_kernel(const __grid_cons
                         lean_set_direction<true>(box, f, pk.dir, ix, iy, iz, pk.pos.x - (float)ix, pk.pos.y - (float)iy, pk.pos.z - (float)iz);
                         ti = ((iz - box.loz) * SOC_TILE_N + (iy - box.loy)) * SOC_TILE_N + (ix - box.lox);
                         f.rho = pk.rho; f.photons = pk.photons; f.free_path = pk.free_path; f.tau = 0.0f;
+                        if (KAPPA) { const float2 k2 = reinterpret_cast<const float2 *>(s_dens)[ti]; ka = k2.x; f.rho = k2.y; }
                         f.sn = 0; f.u = (unsigned)us;
                     }
                 }
@@ -1824,12 +1831,12 @@ __global__ void __launch_bounds__(256, 3) sim_tile_pass_kernel(const __grid_cons
                 px = f.tx == tmin; py = !px && (f.ty == tmin);
                 const int crem = px ? f.cx : (py ? f.cy : f.cz);
                 inb = crem > 0;
-                const float krho = ksca * f.rho;
+                const float krho = KAPPA ? f.rho : ksca * f.rho;
                 const float tend = fmaf(tmin, krho, f.tau);
                 sc = f.free_path < tend;
                 const float tsc = (f.free_path - f.tau) * rcp_approx(krho);
                 if (sc) { tmin = fminf(tmin, tsc); f.sn += 1u << 24; } else f.tau = tend;
-                const float x = tmin * f.rho * kabs;
+                const float x = KAPPA ? tmin * ka : tmin * f.rho * kabs;
                 const float e = exp2f_approx(-1.4426950408889634f * x);
                 const float ser = x * fmaf(x, fmaf(x, 0.16666667f, -0.5f), 1.0f);
                 const float dfrac = (x < 0.01f) ? ser : (1.0f - e);
@@ -1876,7 +1883,10 @@ __global__ void __launch_bounds__(256, 3) sim_tile_pass_kernel(const __grid_cons
                     f.cx -= px; f.cy -= py; f.cz -= pz;
                     ti += (f.upm & abit) ? stride : -stride;
                     alive = inb;
-                    if (inb) f.rho = s_dens[ti];
+                    if (inb) {
+                        if (KAPPA) { const float2 k2 = reinterpret_cast<const float2 *>(s_dens)[ti]; ka = k2.x; f.rho = k2.y; }
+                        else f.rho = s_dens[ti];
+                    }
                     else {
                         // left the tile: through a face of the grid the packet is gone, else it is parked for the second pass
                         // (the counter of the crossed axis stands at -1 = one cell beyond the border)
@@ -2182,28 +2192,38 @@ void launch_sim_domain(const SimArgs &A, int blocks, int threads, cudaStream_t s
 // can the emission and the steps inside the shared-memory tile run as a pass of their own (sim_tile_pass_kernel)?
 bool sim_tile_pass_eligible(const SimArgs &A, int rng_mode) {
     return rng_mode != SOC_RNG_REFERENCE && A.kind == SIM_PS && A.deposit == DEP_TILE && A.tile_inside && A.brick && A.ahead && !A.pend &&
-           A.mirror == 0 && !A.with_abu && sim_uses_lean(A) && A.G.nx >= SOC_TILE_N && A.G.ny >= SOC_TILE_N && A.G.nz >= SOC_TILE_N;
+           A.mirror == 0 && sim_uses_lean(A) && A.G.nx >= SOC_TILE_N && A.G.ny >= SOC_TILE_N && A.G.nz >= SOC_TILE_N;
 }
 bool sim_two_pass_eligible(const SimArgs &A, int rng_mode) {
     // larger grids run domain by domain (there the tile pass replaces the emission pass) or, with that switched off, the look-ahead tile kernel
     return sim_tile_pass_eligible(A, rng_mode) && A.G.nxyz <= (1LL << 25);
 }
-void launch_sim_tile_pass(const SimArgs &A, int blocks, int threads, cudaStream_t stream) {
-    (void)blocks; (void)threads;
+template <bool KAPPA>
+static void launch_tile_pass(const SimArgs &A, cudaStream_t stream) {
     static int per_sm = 0, sms = 0;                   // resident CTAs: the grid is sms x per_sm
+    const size_t smem = (size_t)SOC_TILE_CELLS * (KAPPA ? 3 : 2) * sizeof(float);
     if (per_sm == 0) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sim_tile_pass_kernel, 256, 0);
+        cudaFuncSetAttribute(sim_tile_pass_kernel<KAPPA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sim_tile_pass_kernel<KAPPA>, 256, smem);
         if (per_sm < 1) per_sm = 1;
     }
     long long need = (A.nlocal + 255) / 256;
     const int b = (int)(need < (long long)sms * per_sm ? (need < 1 ? 1 : need) : (long long)sms * per_sm);
-    sim_tile_pass_kernel<<<b, 256, 0, stream>>>(A);
+    sim_tile_pass_kernel<KAPPA><<<b, 256, smem, stream>>>(A);
+}
+void launch_sim_tile_pass(const SimArgs &A, int blocks, int threads, cudaStream_t stream) {
+    (void)blocks; (void)threads;
+    if (A.with_abu) launch_tile_pass<true>(A, stream);
+    else            launch_tile_pass<false>(A, stream);
 }
 void sim_note_two_pass() {
-    snprintf(g_kernel_name, sizeof(g_kernel_name), "sim_tile_pass_kernel + sim_ahead_kernel<DEP_RED,brick,queue>");
+    const char *second = sim_last_kernel();          // what launch_sim_domain dispatched for the second pass
+    char tmp[96];
+    snprintf(tmp, sizeof(tmp), "sim_tile_pass_kernel + %s", second[0] ? second : "sim_ahead_kernel");
+    snprintf(g_kernel_name, sizeof(g_kernel_name), "%s", tmp);
 }
 
 bool sim_kappa_eligible(const SimArgs &A, int rng_mode) {

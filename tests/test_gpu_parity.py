@@ -374,14 +374,15 @@ def test_accumulation_engines_agree(deposit):
     assert abs(res[0].sum() - res[1].sum()) <= 3e-5 * res[0].sum()
 
 
-def test_sharded_ranks_sum_to_single_rank():
+@pytest.mark.parametrize("kind", ["bg", "ps"])
+def test_sharded_ranks_sum_to_single_rank(kind):
     """Packet q runs on rank q % world with the same Philox stream: the sum over ranks equals the 1-rank
-    result up to the order of float additions."""
+    result up to the order of float additions.  ps: the two-pass point-source launch (tile pass + queue-fed pass)."""
     from soc_b200 import backend
     make, opts, _ = CASES["bg_reg16"]
     cloud = make()
-    run = run_bg(batch=3, seed=0.37)
-    B = _backend(cloud, backend.RNG_PACKET)
+    run = run_bg(batch=3, seed=0.37) if kind == "bg" else run_ps([(7.3, 8.2, 6.7)], batch=20, glob=4096)
+    B = _backend(cloud, backend.RNG_PACKET, **(dict(no_ps=1) if kind == "ps" else {}))
     one = run(B)["tabs"].astype(np.float64)
     steps_one = B.counters.steps
     tot = np.zeros_like(one)
@@ -499,24 +500,34 @@ def test_domain_tiled_propagation_equals_whole_grid(kind, schedule, monkeypatch)
         assert abs(a.sum() - b.sum()) <= 3e-5 * a.sum()
 
 
+@pytest.mark.parametrize("abu", [False, True])
 @pytest.mark.parametrize("pos", [(9.3, 7.2, 8.7), (1.4, 14.6, 16.5)])
-def test_two_pass_point_source_launch_equals_one_pass(pos, monkeypatch):
+def test_two_pass_point_source_launch_equals_one_pass(pos, abu, monkeypatch):
     """SOC_TWO_PASS=1: the steps of every point-source packet inside the shared-memory tile in a pass of their own (the lean
     kernel with the tile as its box), the packets parked at the border of the tile with their complete stepping state, the rest
     through the plain-add look-ahead kernel from the queue.  Same Philox streams: same packets, the steps / scatterings agree up
     to paths that flip at a cell face by rounding (lean vs look-ahead kernel), TABS and INT up to that and the order of the
-    float additions.  Second position: the tile is clamped to the border of the grid; chunks of 65536 packets."""
+    float additions.  Second position: the tile is clamped to the border of the grid; chunks of 65536 packets.
+    abu: per-cell opacities (the (kabs*n, ksca*n) array in both passes)."""
     from soc_b200 import backend
     from soc_b200.formats import Cloud
     nx, ny, nz = 20, 16, 18
     d = synth.plummer_density(24)[2:2 + nz, 4:4 + ny, 2:2 + nx]
     cloud = Cloud(nx, ny, nz, [nx * ny * nz], np.ascontiguousarray(d, np.float32).ravel())
-    run = run_ps([pos], batch=50, glob=4096, tau_s=6.0)
+    extra, opts = {}, dict(no_ps=1, noabsorbed=0)
+    if abu:
+        rng = np.random.default_rng(5)
+        k = 6.0 / nx
+        opt = np.empty((cloud.CELLS, 2), np.float32)
+        opt[:, 0] = k * (0.3 + rng.random(cloud.CELLS))
+        opt[:, 1] = k * (0.8 + rng.random(cloud.CELLS))
+        extra, opts = dict(opt=opt.reshape(-1)), dict(no_ps=1, noabsorbed=0, with_abu=1)
+    run = run_ps([pos], batch=50, glob=4096, tau_s=6.0, **extra)
     monkeypatch.setenv("SOC_DOMAIN_CHUNK", "65536")
     res, cnt = [], []
     for two in ("0", "1"):
         monkeypatch.setenv("SOC_TWO_PASS", two)
-        B = _backend(cloud, backend.RNG_PACKET, no_ps=1, noabsorbed=0)
+        B = _backend(cloud, backend.RNG_PACKET, **opts)
         out = run(B)
         res.append((out["tabs"].astype(np.float64), out["int"].astype(np.float64)))
         c = B.counters
