@@ -167,7 +167,10 @@ int  soc_set_layout(soc_context *ctx, int mode);
  * packet leaving a box through an interior face is parked (its full stepping state) until the box it enters is
  * processed -- same packets, same paths, same results up to the order of the float additions.  edge = 0 (default):
  * automatic, boxes of <= 256 cells per axis when DENS + the scratch accumulator exceed the L2 (more than 2^25 cells);
- * edge < 0: off; edge > 0 (even): forced with that box size.  Launches in this mode return when the packets are done. */
+ * edge < 0: off; edge > 0 (even): forced with that box size.  Launches in this mode return when the packets are done.
+ * (Point-source launches with deposit_mode 2 on smaller regular grids use the same queues: emission and the steps inside
+ * the shared-memory tile run as a pass of their own that parks the packets at the border of the tile, the rest of the paths
+ * through the plain-add kernel -- DESIGN.md 4.1; also synchronous.) */
 int  soc_set_domains(soc_context *ctx, int edge);
 
 /* OPT[CELLS,2] = per-cell (KABS, KSCA) built on the device from the abundances in buffer ABU ([CELLS, ndust] floats,
