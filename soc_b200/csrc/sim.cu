@@ -2305,21 +2305,24 @@ int sim_blocks_per_sm(int rng_mode, bool octree, bool dbl, int threads) {
 // bricked scratch accumulator -> TABS / INT in the reference's cell order.  One thread per x-pair of a brick: the
 // accumulator is read as float2 in its own order (coalesced), TABS / INT are updated 8 bytes at a time.
 __global__ void __launch_bounds__(256) fold_acc_brick_kernel(float *__restrict__ acc, float *__restrict__ tabs, float *__restrict__ inten,
-                                                             float scale, const LayoutDesc L, long long npairs) {
+                                                             float scale, const LayoutDesc L, long long nquads) {
+    // one thread = half a brick: cells (x, y), (x+1, y), (x, y+1), (x+1, y+1) of one z -- 16 contiguous bytes of the accumulator,
+    // two 8-byte pieces of TABS / INT one row apart (the loads of a thread are independent: enough bytes in flight to stream)
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += stride) {
-        float2 a = reinterpret_cast<float2 *>(acc)[i];
-        if (a.x != 0.0f || a.y != 0.0f) {
-            const long long lin = layout_source(L, 2 * i);          // the pair (sub, sub + 1) differs in x only
-            float2 t = *reinterpret_cast<float2 *>(tabs + lin);
-            t.x += a.x * scale; t.y += a.y * scale;
-            *reinterpret_cast<float2 *>(tabs + lin) = t;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nquads; i += stride) {
+        const float4 a = reinterpret_cast<float4 *>(acc)[i];
+        if (a.x != 0.0f || a.y != 0.0f || a.z != 0.0f || a.w != 0.0f) {
+            const long long lin0 = layout_source(L, 4 * i), lin1 = lin0 + L.nx;
+            float2 t0 = *reinterpret_cast<float2 *>(tabs + lin0), t1 = *reinterpret_cast<float2 *>(tabs + lin1);
+            float2 v0 = make_float2(0.0f, 0.0f), v1 = v0;
+            if (inten != nullptr) { v0 = *reinterpret_cast<float2 *>(inten + lin0); v1 = *reinterpret_cast<float2 *>(inten + lin1); }
+            t0.x += a.x * scale; t0.y += a.y * scale; t1.x += a.z * scale; t1.y += a.w * scale;
+            *reinterpret_cast<float2 *>(tabs + lin0) = t0; *reinterpret_cast<float2 *>(tabs + lin1) = t1;
             if (inten != nullptr) {
-                float2 v = *reinterpret_cast<float2 *>(inten + lin);
-                v.x += a.x; v.y += a.y;
-                *reinterpret_cast<float2 *>(inten + lin) = v;
+                v0.x += a.x; v0.y += a.y; v1.x += a.z; v1.y += a.w;
+                *reinterpret_cast<float2 *>(inten + lin0) = v0; *reinterpret_cast<float2 *>(inten + lin1) = v1;
             }
-            reinterpret_cast<float2 *>(acc)[i] = make_float2(0.0f, 0.0f);
+            reinterpret_cast<float4 *>(acc)[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         }
     }
 }
@@ -2349,6 +2352,6 @@ void launch_kappa(const SimArgs &A, cudaStream_t stream) {
 void launch_fold_acc(const SimArgs &A, cudaStream_t stream) {
     const long long n = A.G.cells;
     const float scale = A.tw * A.adhoc;
-    if (A.brick) fold_acc_brick_kernel<<<stream_grid(n >> 1), 256, 0, stream>>>(A.acc, A.tabs, A.use_int ? A.inten : nullptr, scale, layout_of(A), n >> 1);
+    if (A.brick) fold_acc_brick_kernel<<<stream_grid(n >> 2), 256, 0, stream>>>(A.acc, A.tabs, A.use_int ? A.inten : nullptr, scale, layout_of(A), n >> 2);
     else         fold_acc_kernel<<<stream_grid(n >> 2), 256, 0, stream>>>(A.acc, A.tabs, A.use_int ? A.inten : nullptr, scale, n);
 }
