@@ -1220,8 +1220,10 @@ __global__ void __launch_bounds__(256, CTAS) sim_ahead_kernel(const __grid_const
             const float krho = KAPPA ? f.rho : ksca * f.rho;
             const float tend = fmaf(seg, krho, f.tau);
             sc = f.free_path < tend;
-            const float tsc = (f.free_path - f.tau) * rcp_approx(krho);
-            if (sc) { len = fminf(seg, tsc); f.sn += 1u << 24; } else f.tau = tend;
+            if (__builtin_expect(sc, 0)) {           // rare: the length to the scattering point is worked out only here
+                const float tsc = (f.free_path - f.tau) * rcp_approx(krho);
+                len = fminf(seg, tsc); f.sn += 1u << 24;
+            } else f.tau = tend;
             const float x = KAPPA ? len * ka : len * f.rho * kabs;
             const float e = exp2f_approx(-1.4426950408889634f * x);
             const float ser = x * fmaf(x, fmaf(x, 0.16666667f, -0.5f), 1.0f);
@@ -1302,7 +1304,8 @@ __global__ void __launch_bounds__(256, CTAS) sim_ahead_kernel(const __grid_const
                 st = ((st & ~(AH_AXA | AH_AIN)) ^ AH_SLOT) | AH_PRIMED | (abit << 4) | (inb ? AH_AIN : 0u);
             }
             bool stuck = false;
-            if (LEAN_STEPS(f.sn) > (unsigned)A.max_steps && !parked) { st &= ~(AH_ALIVE | AH_WSC); stuck = true; }
+            // guard against packets that never leave: looked at once per pass of the outer loop
+            if (rep == 0 && LEAN_STEPS(f.sn) > (unsigned)A.max_steps && !parked) { st &= ~(AH_ALIVE | AH_WSC); stuck = true; }
             if (!(st & AH_ALIVE) && !parked) {                  // packet finished: once per packet
                 count_add(&s_cnt[1], A.counters + 1, LEAN_STEPS(f.sn));
                 count_add(&s_cnt[2], A.counters + 2, min(LEAN_SCAT(f.sn), 20u));
