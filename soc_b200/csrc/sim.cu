@@ -768,6 +768,13 @@ __device__ __forceinline__ Box launch_box(const SimArgs &A) {
     b.hix = DOM ? A.dom_hi[0] : A.G.nx - 1; b.hiy = DOM ? A.dom_hi[1] : A.G.ny - 1; b.hiz = DOM ? A.dom_hi[2] : A.G.nz - 1;
     return b;
 }
+// the box that holds cell (ix,iy,iz) and the first position of its bricks (domain-major layout, A.dsplit / A.dsize)
+__device__ __forceinline__ void roam_box(const SimArgs &A, int ix, int iy, int iz, Box &b, int &dbase) {
+    const int dx = ix / A.dsize[0], dy = iy / A.dsize[1], dz = iz / A.dsize[2];
+    b.lox = dx * A.dsize[0]; b.loy = dy * A.dsize[1]; b.loz = dz * A.dsize[2];
+    b.hix = b.lox + A.dsize[0] - 1; b.hiy = b.loy + A.dsize[1] - 1; b.hiz = b.loz + A.dsize[2] - 1;
+    dbase = ((dz * A.dsplit[1] + dy) * A.dsplit[0] + dx) * (A.dsize[0] * A.dsize[1] * A.dsize[2]);
+}
 template <bool BRICK>
 __device__ __forceinline__ void lean_set_direction(const Box &b, LeanPk<BRICK> &f, const vec3 &d, int ix, int iy, int iz,
                                                    float fx, float fy, float fz) {
@@ -1099,7 +1106,11 @@ __device__ __forceinline__ float2 lds_f32x2(unsigned saddr) {
 // density array (kappa_kernel builds it from DENS and OPT before the launch), instead of the density and the two
 // opacities: 8 B gathered per step instead of 12, and the ring slots are 8 bytes wide.
 #define AH_SLOT_SHIFT(KAPPA) ((KAPPA) ? 1 : 0)
-template <int DEP, bool BRICK, int CTAS, bool KAPPA, bool DOM>
+// ROAM (with DOM): the clean-up pass of the domain mode.  The launch takes the packets of ALL queues (q_part) and nothing is
+// parked: a packet that leaves its box through an interior face is re-homed on the spot -- box bounds, crossing counters and brick
+// index of the box it enters, exactly what parking and picking it up again would have produced -- so the last few packets of a
+// launch (ping-pong between boxes after many scatterings) finish on the bricked layout instead of the general kernel's x-fastest one.
+template <int DEP, bool BRICK, int CTAS, bool KAPPA, bool DOM, bool ROAM = false>
 __global__ void __launch_bounds__(256, CTAS) sim_ahead_kernel(const __grid_constant__ SimArgs A) {
     __shared__ float smem[DEP == DEP_TILE ? SOC_TILE_CELLS : 1];
     __shared__ __align__(8) float s_ring[(KAPPA ? 4 : 2) * 256];   // slot s of lane t: s_ring[s * 256 + t] (float or float2 units)
@@ -1116,7 +1127,8 @@ __global__ void __launch_bounds__(256, CTAS) sim_ahead_kernel(const __grid_const
     const int lane = threadIdx.x & 31;
     const float kabs = A.kabs, ksca = A.ksca;
     const unsigned ring = (unsigned)__cvta_generic_to_shared(&s_ring[KAPPA ? 2 * threadIdx.x : threadIdx.x]);
-    const Box box = launch_box<DOM>(A);
+    Box box = launch_box<DOM>(A);    // ROAM: the box of this lane's packet
+    int dbase = A.dom_base;          // first position of that box in the bricked arrays
     float ka = 0.0f;                 // KAPPA: kabs*n of the physics cell (f.rho holds ksca*n)
     LeanPk<BRICK> f; f.ind = 0; f.u = 0; f.rho = 0.0f; f.sn = 0; f.upm = 0;        // f.ind = index of cell A
     int ind = 0;                     // cell the physics works on
@@ -1136,12 +1148,19 @@ __global__ void __launch_bounds__(256, CTAS) sim_ahead_kernel(const __grid_const
             if (!(st & AH_ALIVE)) {
                 const unsigned long long u = base + __popc(nm & ((1u << lane) - 1u));
                 if (DOM && u < (unsigned long long)A.nlocal) {        // a packet parked at the border of this domain: not primed
-                    const QPk s = q_load(A.q_in + u);
+                    const QPk *src = A.q_in + u;
+                    if (ROAM) {                                       // the queues back to back in unit space
+                        int part = 0;
+                        while (part + 1 < A.q_nparts && (long long)u >= A.q_part[part + 1]) part++;
+                        src = A.q_base + (size_t)part * (size_t)A.q_cap + (u - (unsigned long long)A.q_part[part]);
+                    }
+                    const QPk s = q_load(src);
+                    if (ROAM) roam_box(A, s.ix, s.iy, s.iz, box, dbase);
                     f.tx = s.tx; f.ty = s.ty; f.tz = s.tz; f.rdx = s.rdx; f.rdy = s.rdy; f.rdz = s.rdz;
                     f.photons = s.photons; f.free_path = s.free_path; f.tau = s.tau; f.sn = s.sn; f.u = s.u; f.upm = (int)s.upm;
                     f.cx = (s.upm & 1u) ? box.hix - s.ix : s.ix - box.lox; f.cy = (s.upm & 2u) ? box.hiy - s.iy : s.iy - box.loy;
                     f.cz = (s.upm & 4u) ? box.hiz - s.iz : s.iz - box.loz;
-                    f.ind = A.dom_base + brick_index(s.ix - box.lox, s.iy - box.loy, s.iz - box.loz, A.dsize[0] >> 1, A.dsize[1] >> 1);
+                    f.ind = dbase + brick_index(s.ix - box.lox, s.iy - box.loy, s.iz - box.loz, A.dsize[0] >> 1, A.dsize[1] >> 1);
                     ind = f.ind;
                     st = (st & AH_SLOT) | AH_ALIVE | s.upm;
                     tskip = 0;
@@ -1276,7 +1295,12 @@ __global__ void __launch_bounds__(256, CTAS) sim_ahead_kernel(const __grid_const
                     // through an interior face the packet is parked for the domain that holds A, not primed
                     const unsigned axb = (st >> 4) & 7u;
                     const int face = ((axb & 1u) ? 0 : ((axb & 2u) ? 2 : 4)) + ((st & axb) ? 1 : 0);
-                    if (!((A.dom_faces >> face) & 1)) parked = true;           // stored at the end of the step, the warp together
+                    if (ROAM) {                                      // is the face crossed a face of the grid?
+                        const bool upw = (st & axb) != 0u;
+                        const int lo = (axb & 1u) ? box.lox : ((axb & 2u) ? box.loy : box.loz), hi = (axb & 1u) ? box.hix : ((axb & 2u) ? box.hiy : box.hiz);
+                        const int dimv = (axb & 1u) ? G.nx : ((axb & 2u) ? G.ny : G.nz);
+                        if (!(upw ? hi == dimv - 1 : lo == 0)) parked = true;  // re-homed below
+                    } else if (!((A.dom_faces >> face) & 1)) parked = true;    // stored at the end of the step, the warp together
                 }
             } else {
                 // geometry: from the entry of A (unprimed: from the packet's position in its cell) to the next face
@@ -1312,7 +1336,21 @@ __global__ void __launch_bounds__(256, CTAS) sim_ahead_kernel(const __grid_const
                 if (stuck) count_add(&s_cnt[3], A.counters + 3, 1u);
             }
         }
-        if (DOM && __any_sync(FULL, parked)) {                  // one queue slot request per target domain and warp
+        if (ROAM) {
+            if (parked) {
+                // the geometry stands at the entry of A, one cell into the next box: that box becomes the lane's box
+                const int ix = (st & 1u) ? box.hix - f.cx : box.lox + f.cx, iy = (st & 2u) ? box.hiy - f.cy : box.loy + f.cy,
+                          iz = (st & 4u) ? box.hiz - f.cz : box.loz + f.cz;
+                roam_box(A, ix, iy, iz, box, dbase);
+                f.cx = (st & 1u) ? box.hix - ix : ix - box.lox; f.cy = (st & 2u) ? box.hiy - iy : iy - box.loy;
+                f.cz = (st & 4u) ? box.hiz - iz : iz - box.loz;
+                f.ind = dbase + brick_index(ix - box.lox, iy - box.loy, iz - box.loz, A.dsize[0] >> 1, A.dsize[1] >> 1);
+                ind = f.ind;
+                st = (st & (AH_SLOT | AH_UPM)) | AH_ALIVE;           // as picked up from a queue: not primed
+                if (KAPPA) { const float2 k2 = __ldg(kappa + f.ind); ka = k2.x; f.rho = k2.y; }
+                else f.rho = __ldg(dens + f.ind);
+            }
+        } else if (DOM && __any_sync(FULL, parked)) {           // one queue slot request per target domain and warp
             QPk o;
             o.tx = f.tx; o.ty = f.ty; o.tz = f.tz; o.rdx = f.rdx; o.rdy = f.rdy; o.rdz = f.rdz;
             o.photons = f.photons; o.free_path = f.free_path; o.tau = f.tau;
@@ -1323,7 +1361,7 @@ __global__ void __launch_bounds__(256, CTAS) sim_ahead_kernel(const __grid_const
         }
         }
     }
-    if (DOM) q_stage_flush(A, stage, nstage);
+    if (DOM && !ROAM) q_stage_flush(A, stage, nstage);
     if (DEP == DEP_TILE) {
         __syncthreads();
         for (int i = threadIdx.x; i < SOC_TILE_CELLS; i += blockDim.x) {
@@ -2149,6 +2187,24 @@ void launch_queue_sort(const QPk *q, long long n, QPk *out, unsigned *hist, cons
 
 // the last parked packets, resumed on the whole grid by the general kernel (q_in, A.dom set by the caller)
 void launch_sim_cleanup(const SimArgs &A, int blocks, int threads, cudaStream_t stream) {
+    // all queues in one launch on the bricked layout: the look-ahead kernel with re-homing (ROAM); one queue at a time (more than 64
+    // boxes) or SOC_AHEAD=0: the general kernel on the reference's cell order, which adds straight into TABS / INT
+    if (A.ahead && A.brick && A.q_nparts > 1) {
+        static int per_sm[2] = { 0, 0 }, sms = 0;
+        const int v = A.with_abu ? 1 : 0;
+        if (per_sm[v] == 0) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (v) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[v], sim_ahead_kernel<DEP_RED, true, 3, true, true, true>, threads, 0);
+            else   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[v], sim_ahead_kernel<DEP_RED, true, 3, false, true, true>, threads, 0);
+            if (per_sm[v] < 1) per_sm[v] = 1;
+        }
+        if (blocks > sms * per_sm[v]) blocks = sms * per_sm[v];
+        if (v) sim_ahead_kernel<DEP_RED, true, 3, true, true, true><<<blocks, threads, 0, stream>>>(A);
+        else   sim_ahead_kernel<DEP_RED, true, 3, false, true, true><<<blocks, threads, 0, stream>>>(A);
+        return;
+    }
     sim_fast_kernel<DEP_RED, true><<<blocks, threads, 0, stream>>>(A);
 }
 
