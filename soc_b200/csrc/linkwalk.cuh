@@ -81,16 +81,19 @@ __device__ __forceinline__ bool lw_descend(const GridDesc &G, LWalker &w, const 
     return is_leaf(w.rho);
 }
 
-// Cross the face of axis `ax`.  Returns true when the cell entered is a leaf (w.rho = density), false when it is
+// Cross the face of axis `ax` (e2: the table entry behind it).  Returns true when the cell entered is a leaf (w.rho = density), false when it is
 // refined (w.rho = link; call lw_descend until it returns true).  w.cell < 0: the ray has left the cloud.
 // `mirror`: MIRROR bit mask, the ray is reflected at such a border and stays in its cell.
 // A neighbour that is refined by one level (the common case at a refinement boundary) is resolved right here.
-__device__ __forceinline__ bool lw_cross(const GridDesc &G, const int *__restrict__ nbr, LWalker &w, const int ax, const int mirror) {
+// entry of the neighbour table behind the face of axis `ax` the ray leaves through: {level << 27 | cell, density (or link) of that
+// cell} -- the density comes with the look-up, the walk has one dependent gather per crossing instead of two
+__device__ __forceinline__ int2 lw_entry(const int *__restrict__ nbr, const LWalker &w, const int ax) {
+    return __ldg(reinterpret_cast<const int2 *>(nbr) + 6 * (size_t)w.cell + 2 * ax + ((w.up >> ax) & 1));
+}
+// e2 = lw_entry(nbr, w, ax), requested by the caller as early as the exit face is known (before the physics of the cell)
+__device__ __forceinline__ bool lw_cross(const GridDesc &G, const int2 e2, LWalker &w, const int ax, const int mirror) {
     const int abit = 1 << ax;
     const bool up = (w.up & abit) != 0;
-    // entry = {level << 27 | cell, density (or link) of that cell}: the density comes with the look-up, the walk has one
-    // dependent gather per crossing instead of two
-    const int2 e2 = __ldg(reinterpret_cast<const int2 *>(nbr) + 6 * (size_t)w.cell + 2 * ax + (up ? 1 : 0));
     const int e = e2.x;
     const float rda = (ax == 0) ? w.rdx : ((ax == 1) ? w.rdy : w.rdz);
     if (e < 0) {                                                    // border of the cloud (rare: once per packet)

@@ -666,10 +666,12 @@ __global__ void __launch_bounds__(256, 3) sca_link_kernel(const __grid_constant_
         for (int rep = 0; rep < SOC_SCA_REPS; rep++) {           // cells per refill / ray-end check
         // ---- one cell of whichever ray the lane is tracing -----------------------------------------------------
         const bool ready = mode != RAY_IDLE && phase == WALK_LEAF;
+        int2 e2 = make_int2(0, 0);
         if (ready) {
             const int oind = w.cell;
             const float tmin = fminf(w.tx, fminf(w.ty, w.tz));
             ax = (w.tx <= w.ty && w.tx <= w.tz) ? 0 : ((w.ty <= w.tz) ? 1 : 2);
+            e2 = lw_entry(nbr, w, ax);                                // the table entry behind the exit face, used after the physics
             float ds = fmaxf(tmin, 0.0f);
             float kabs = S.kabs, ksca = S.ksca;
             if (S.with_abu) { float2 o = __ldg(reinterpret_cast<const float2 *>(S.opt) + oind); kabs = o.x; ksca = o.y; }
@@ -723,7 +725,7 @@ __global__ void __launch_bounds__(256, 3) sca_link_kernel(const __grid_constant_
         if (mode != RAY_IDLE && phase == WALK_DESCEND) phase = lw_descend(G, w, ax) ? WALK_LEAF : WALK_DESCEND;
         if (mode != RAY_IDLE && phase == WALK_CROSS) {
             // only the packet itself is reflected by a mirror border; look-ahead and peel-off rays leave
-            phase = lw_cross(G, nbr, w, ax, mode == RAY_MAIN ? S.mirror : 0) ? WALK_LEAF : WALK_DESCEND;
+            phase = lw_cross(G, e2, w, ax, mode == RAY_MAIN ? S.mirror : 0) ? WALK_LEAF : WALK_DESCEND;
             if (w.cell < 0) phase = WALK_END;
             else if (phase == WALK_DESCEND) phase = lw_descend(G, w, ax) ? WALK_LEAF : WALK_DESCEND;
         }

@@ -1655,11 +1655,15 @@ __global__ void __launch_bounds__(256, 4) sim_link_kernel(const __grid_constant_
         int oind = 0;
         const bool was_alive = alive;
         const bool ready = alive && phase == WALK_LEAF;
+        int2 e2 = make_int2(0, 0);
         if (ready) {
             // physics of the current leaf
             oind = w.cell;
             tmin = fminf(w.tx, fminf(w.ty, w.tz));
             ax = (w.tx <= w.ty && w.tx <= w.tz) ? 0 : ((w.ty <= w.tz) ? 1 : 2);
+            // the exit face is known: the table entry behind it is requested now and used after the physics (it is not needed
+            // when the packet scatters in this cell: rare)
+            e2 = lw_entry(nbr, w, ax);
             ds = fmaxf(tmin, 0.0f);
             float kabs = A.kabs, ksca = A.ksca;
             if (abu) { float2 o = __ldg(reinterpret_cast<const float2 *>(A.opt) + oind); kabs = o.x; ksca = o.y; }
@@ -1717,7 +1721,7 @@ __global__ void __launch_bounds__(256, 4) sim_link_kernel(const __grid_constant_
         if (alive && phase == WALK_DESCEND) phase = lw_descend(G, w, ax) ? WALK_LEAF : WALK_DESCEND;
         if (alive && phase == WALK_CROSS) {
             const int r0x = w.cx >> w.level, r0y = w.cy >> w.level, r0z = w.cz >> w.level;
-            phase = lw_cross(G, nbr, w, ax, A.mirror) ? WALK_LEAF : WALK_DESCEND;
+            phase = lw_cross(G, e2, w, ax, A.mirror) ? WALK_LEAF : WALK_DESCEND;
             if (w.cell < 0) alive = false;
             else if (phase == WALK_DESCEND) phase = lw_descend(G, w, ax) ? WALK_LEAF : WALK_DESCEND;    // one level right away
             if (alive && GENERAL && (A.roi.flags & 2)) {                 // WITH_ROI_SAVE: a new root cell? kernel_ASOC.c:615-643
