@@ -60,3 +60,14 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not pat.search(txt), os.path.join(dirpath, f)
+
+
+def test_missing_library_is_a_loud_error(lib_path, monkeypatch, tmp_path):
+    """SOC_B200_LIB points the binding at a development build; a path that does not exist raises (no fallback to anything)."""
+    from soc_b200 import backend
+    monkeypatch.setattr(backend, "_lib", None)
+    monkeypatch.setenv("SOC_B200_LIB", str(tmp_path / "no_such_library.so"))
+    with pytest.raises(backend.SocError):
+        backend.load_library()
+    monkeypatch.setenv("SOC_B200_LIB", lib_path)
+    assert backend.load_library() is not None
