@@ -476,13 +476,16 @@ static int sim_launch_domains(soc_context *c, SimArgs &A, int blocks, int thread
     if (D > 4096) return fail(SOC_ERR_UNSUPPORTED, "soc_set_domains: %d domains (at most 4096)", D);
     const long long dcells = (long long)ds[0] * ds[1] * ds[2];
     // chunk of work units in flight: every queue must be able to hold all of them
-    size_t free_b = 0, total_b = 0;
-    CU(cudaMemGetInfo(&free_b, &total_b));
     long long chunk = 1LL << 25;
     if (const char *e = getenv("SOC_DOMAIN_CHUNK")) { long long v = atoll(e); if (v >= 1024) chunk = v; }      // tuning knob
-    const size_t budget = (free_b + c->queue_bytes) / 2;
     const long long carry_cap = 1LL << 20;                 // room for the packets carried over into the next chunk (see below)
-    while (chunk > 65536 && (size_t)(chunk + carry_cap) * D * sizeof(QPk) > budget) chunk >>= 1;
+    if ((size_t)((chunk < A.nlocal ? chunk : A.nlocal) + carry_cap) * D * sizeof(QPk) > c->queue_bytes) {
+        // the queues have to grow: at most half of the free memory (asked only then: cudaMemGetInfo is slow)
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        const size_t budget = (free_b + c->queue_bytes) / 2;
+        while (chunk > 65536 && (size_t)(chunk + carry_cap) * D * sizeof(QPk) > budget) chunk >>= 1;
+    }
     if (chunk > A.nlocal) chunk = A.nlocal > 0 ? A.nlocal : 1;
     const long long q_cap = chunk + carry_cap;
     const size_t need_b = (size_t)q_cap * D * sizeof(QPk);
